@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py — GH-ICP inner-loop benchmark (BASELINE.json metric: ICP iterations/s at N_src x N_tgt).
+
+A "step" = one body of GHRegistration::ghicp_reg's while-loop (src/ghicp_reg.cpp:49-103, viewer
+excluded): calED + calCD_* + findcorrespondence* + transformestimation + adjustweight.
+Default workload = BASELINE.json configs[1]: 50k x 50k keypoints, BSC descriptors, KM matching, 6-DoF.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
+
+Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for every field.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (N, M, feature, corr, bits)
+    "config1": dict(N=2000, M=2000, ft="none", ct="nn", bits=0, desc="2k x 2k, no feature, NN, 6-DoF"),
+    "config2": dict(N=50000, M=50000, ft="bsc", ct="km", bits=441, desc="50k x 50k, BSC-441 (reference's BSCEncoder(.,7)), KM, 6-DoF"),
+    "config2-672": dict(N=50000, M=50000, ft="bsc", ct="km", bits=672, desc="50k x 50k, BSC-672, KM, 6-DoF"),
+    "config2-nn": dict(N=50000, M=50000, ft="bsc", ct="nn", bits=441, desc="50k x 50k, BSC-441, NN, 6-DoF"),
+    "config2-nnr": dict(N=50000, M=50000, ft="bsc", ct="nnr", bits=441, desc="50k x 50k, BSC-441, NNR, 6-DoF"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, dev=0):
+        self.rows, self.stop, self.dev = [], threading.Event(), dev
+        self.t = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.dev}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_scene(g, wl, n_override=None, seed=2):
+    N = n_override or wl["N"]
+    M = n_override or wl["M"]
+    if wl["ft"] == "none":
+        sc = g.synth.gen_points(N, M, overlap=0.9, extent=(100, 100, 20), noise=0.02, seed=1)
+    else:
+        # same point density as config 2 at any size (so candidate statistics stay comparable)
+        f = (N / 50000.0) ** (1.0 / 3.0)
+        sc = g.synth.gen_points(N, M, overlap=0.6, extent=(200 * f, 200 * f, 40 * f), noise=0.05, seed=seed)
+        if wl["ft"] == "bsc":
+            g.synth.add_bsc(sc, bits=wl["bits"], V=4)
+    return sc
+
+
+FT = {"none": 3, "bsc": 0, "fpfh": 2}
+CT = {"nn": 0, "nnr": 1, "km": 2}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle (restated reference loop) + the reference's own km.cpp when compiled.
+# --------------------------------------------------------------------------------------------------
+def cpu_baseline(g, wl, threads, n_sample, iters=2):
+    import oracle
+    oracle.build()
+    use_ref = oracle.ref_km_lib() is not None and wl["ct"] == "km"
+    sc = make_scene(g, wl, n_override=n_sample)
+    cwd = os.getcwd()
+    import tempfile
+    os.chdir(tempfile.mkdtemp())  # Km::output writes Corres.txt (src/km.cpp:148)
+    try:
+        o = oracle.Oracle(FT[wl["ft"]], CT[wl["ct"]], bbx_magnitude=sc.bbx_magnitude, solve_mode=0,
+                          use_ref_km=use_ref, num_threads=threads)
+        o.set_keypoints(sc.S, sc.T)
+        if wl["ft"] == "bsc":
+            o.set_bsc(sc.bsc_s, sc.bsc_t, sc.bits)
+        t0 = time.perf_counter()
+        o.build_fd()
+        t_fd = time.perf_counter() - t0
+        t_cost, t_corr, t_solve = [], [], []
+        for _ in range(iters):
+            st = o.iterate()
+            t_cost.append(st.t_cost_ms); t_corr.append(st.t_corr_ms); t_solve.append(st.t_solve_ms)
+    finally:
+        os.chdir(cwd)
+    n = n_sample
+    N = wl["N"]
+    cost = float(np.median(t_cost)); corr = float(np.median(t_corr)); solve = float(np.median(t_solve))
+    # extrapolation laws: cost/NN/NNR ~ N*M, KM ~ n^3, solve ~ n
+    sc2 = (N / n) ** 2
+    sc3 = (N / n) ** 3
+    full_ms = cost * sc2 + (corr * sc3 if wl["ct"] == "km" else corr * sc2) + solve * (N / n)
+    return dict(value=1000.0 / full_ms, unit="iterations/s", cores=threads,
+                kind="reference" if use_ref else "port",
+                sample=(f"{n}x{n} subsample of the workload, {iters} iterations, median stage times "
+                        f"cost={cost:.1f} ms corr={corr:.1f} ms solve={solve:.2f} ms (one-time FD {t_fd*1e3:.0f} ms); "
+                        f"extrapolated to {N}x{wl['M']} with cost~N*M, {'KM~n^3' if wl['ct']=='km' else 'scan~N*M'}, solve~n "
+                        f"(the reference cannot run {N}x{wl['M']}: 24*N*M B of doubles + O(n^3) KM, SURVEY.md §6)"),
+                ms_per_step_sample=cost + corr + solve, ms_per_step_extrapolated=full_ms)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--n", type=int, default=0, help="override N=M (debug; makes the number non-headline)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="N=M of the CPU baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = dict(WORKLOADS[args.workload])
+    if args.n:
+        wl["N"] = wl["M"] = args.n
+    import ghicp_b200 as g
+
+    config = {"workload": args.workload + (f" (N=M={args.n} override)" if args.n else ""), "desc": wl["desc"],
+              "N_src": wl["N"], "N_tgt": wl["M"], "descriptor_bits": wl["bits"], "correspondence": wl["ct"],
+              "l2_policy": "inputs larger than L2 (FD plane u16 N x M streamed every step)" if wl["ft"] != "none"
+              else "matrix-free; working set < L2 by construction"}
+    ncores = os.cpu_count() or 1
+
+    # ---------------- reference arm: the reference's CPU implementation on the host cores ------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        n_s = args.cpu_sample or (1500 if wl["ct"] == "km" else min(wl["N"], 6000))
+        t0 = time.perf_counter()
+        cb = cpu_baseline(g, wl, threads=ncores, n_sample=min(n_s, wl["N"]), iters=max(1, min(args.steps, 2)))
+        line = {"impl": "reference", "metric": "ICP iterations/sec", "value": cb["value"], "unit": "iterations/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": cb["ms_per_step_extrapolated"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+        print(json.dumps(line))
+        return
+
+    # ---------------- our arm --------------------------------------------------------------------------
+    if g.device_count() <= 0:
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local_rank)
+        dist_mod.init_process_group("nccl")
+        dist = dist_mod
+    dev = local_rank
+    sc = make_scene(g, wl)
+    t0 = time.perf_counter()
+    reg = g.registration.from_scene(sc, FT[wl["ft"]], CT[wl["ct"]], device=dev)
+    t_upload = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    reg.build_fd()
+    t_fd = time.perf_counter() - t0
+
+    first_iters = []
+    for _ in range(args.warmup):
+        st = reg.iterate()
+        first_iters.append(dict(it=st.iteration, ms=st.ms_total, cor=st.cor, nnz=st.nnz, rounds=st.km_rounds))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    # ---- timed region 1: device-resident steps -----------------------------------------------------
+    barrier()
+    launches = 0
+    dev_ms, stage = [], []
+    with ClockSampler(dev) as cs:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            st = reg.iterate()  # ends with a stream synchronize
+            dev_ms.append(st.ms_total)
+            stage.append((st.ms_cost, st.ms_corr, st.ms_solve, st.nnz, st.km_rounds, st.cor))
+            launches += st.gpu_launches
+        wall = time.perf_counter() - t0
+    barrier()
+    clocks = cs.summary()
+    ms_per_step = wall * 1e3 / args.steps
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms_per_step], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_per_step = float(t.item())
+
+    # ---- timed region 2: end to end through the host-facing API -----------------------------------
+    # every step: host (pinned inside the library) -> device copy of the current source + target
+    # coordinates, one iteration, device -> host read of the stats, the pair lists and the updated source.
+    S_host = reg.source()
+    T_host = sc.T
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = args.steps
+    for _ in range(e2e_steps):
+        reg.set_keypoints(S_host, T_host)
+        st = reg.iterate()
+        sp, tp = reg.pairs()
+        S_host = reg.source()
+    e2e_wall = time.perf_counter() - t0
+    barrier()
+    e2e_ms = e2e_wall * 1e3 / e2e_steps
+    h2d = 24 * (wl["N"] + wl["M"])
+    d2h = 24 * wl["N"] + 8 * int(st.cor) + 400
+
+    if rank != 0:
+        return
+    hbm_peak, peak_src = peaks()
+    # dominant kernel accounting: the FD-plane stream of the cost stage
+    stage = np.array(stage, dtype=np.float64)
+    n_sweeps = 1 if wl["ct"] != "km" else 3
+    alg_bytes = (2 * wl["N"] * wl["M"] if wl["ft"] == "bsc" else 0) + 24 * (wl["N"] + wl["M"]) + 12 * wl["N"]
+    cost_ms = float(np.median(stage[:, 0]))
+    achieved = alg_bytes / (cost_ms * 1e-3) / 1e9 if cost_ms > 0 else 0.0
+    line = {
+        "metric": "ICP iterations/sec", "value": world * 1000.0 / ms_per_step if False else 1000.0 / ms_per_step,
+        "unit": "iterations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": config,
+        "device_ms_per_step": float(np.mean(dev_ms)),
+        "stage_ms": {"cost": cost_ms, "corr": float(np.median(stage[:, 1])), "solve": float(np.median(stage[:, 2]))},
+        "km": {"nnz": int(np.median(stage[:, 3])), "rounds": int(np.median(stage[:, 4]))} if wl["ct"] == "km" else None,
+        "cor": int(stage[-1, 5]),
+        "first_iterations": first_iters,
+        "one_time": {"fd_build_s": t_fd, "upload_s": t_upload},
+        "e2e": {"value": 1000.0 / e2e_ms, "unit": "iterations/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"kernel": "k_rowsweep<mode 0> (calED+calCD+row scan, FD plane stream)", "bound": "hbm",
+                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes, "sweeps_per_step": n_sweeps},
+    }
+    if not args.no_cpu:
+        n_s = args.cpu_sample or (1500 if wl["ct"] == "km" else min(wl["N"], 6000))
+        cb = cpu_baseline(g, wl, threads=1, n_sample=min(n_s, wl["N"]))
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

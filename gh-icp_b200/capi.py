@@ -1,0 +1,143 @@
+"""ctypes binding of libghicp_b200.so (include/ghicp_b200.h)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libghicp_b200.so")
+
+FT_BSC, FT_ROPS, FT_FPFH, FT_NONE = 0, 1, 2, 3   # include/utility.h:51-57
+CT_NN, CT_NNR, CT_KM = 0, 1, 2                   # include/utility.h:59-64
+
+GHICP_W_FEW_PAIRS = 1
+
+
+class GhicpError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"ghicp error {code}: {msg}")
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [("feature_type", C.c_int), ("corr_type", C.c_int), ("dof", C.c_int),
+                ("bbx_magnitude", C.c_float), ("nonmax", C.c_float), ("adjust_ratio", C.c_float),
+                ("adjust_step", C.c_float), ("estimated_iou", C.c_float), ("converge_t", C.c_float),
+                ("converge_r", C.c_float), ("max_iter", C.c_int), ("device", C.c_int),
+                ("km_eps", C.c_double), ("verbose", C.c_int), ("reserved", C.c_int * 7)]
+
+
+class IterStats(C.Structure):
+    _fields_ = [("iteration", C.c_int), ("cor", C.c_int), ("converged", C.c_int), ("warnings", C.c_int),
+                ("Rt", C.c_double * 16), ("Rt_tillnow", C.c_double * 16),
+                ("cd_mean", C.c_double), ("cd_std", C.c_double), ("penalty", C.c_double),
+                ("rmse", C.c_double), ("rmse_after", C.c_double), ("fdm", C.c_double), ("fdstd", C.c_double),
+                ("iou", C.c_double), ("para1", C.c_double), ("para2", C.c_double), ("km_energy", C.c_double),
+                ("ax", C.c_double), ("ay", C.c_double), ("az", C.c_double),
+                ("nnz", C.c_longlong), ("km_rounds", C.c_int), ("km_phases", C.c_int), ("gpu_launches", C.c_int),
+                ("ms_cost", C.c_float), ("ms_corr", C.c_float), ("ms_solve", C.c_float), ("ms_total", C.c_float)]
+
+    def Rt_np(self):
+        return np.array(self.Rt).reshape(4, 4).T.copy()
+
+    def Rt_tillnow_np(self):
+        return np.array(self.Rt_tillnow).reshape(4, 4).T.copy()
+
+
+def lib_path():
+    return _LIB
+
+
+def build_library(force=False):
+    """Compile gh-icp_b200/csrc for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    if force or not os.path.exists(_LIB):
+        r = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc"), "-j4"], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("building libghicp_b200.so failed:\n" + r.stdout[-4000:] + r.stderr[-4000:])
+    return _LIB
+
+
+_lib = None
+
+EXPORTS = ["ghicp_abi_version", "ghicp_device_count", "ghicp_last_error", "ghicp_create", "ghicp_destroy",
+           "ghicp_set_keypoints", "ghicp_set_bsc", "ghicp_set_fpfh", "ghicp_build_fd", "ghicp_iterate",
+           "ghicp_run", "ghicp_get_pairs", "ghicp_get_source", "ghicp_get_rt", "ghicp_get_fd",
+           "ghicp_probe_rowmin", "ghicp_set_state", "ghicp_km_solve", "ghicp_rigid_fit",
+           "ghicp_comm_unique_id", "ghicp_comm_init"]
+
+
+def lib():
+    """Load libghicp_b200.so. Fails loudly when it is missing: there is no fallback path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB):
+        raise GhicpError(-100, f"{_LIB} is missing: run __graft_entry__.build() (make -C gh-icp_b200/csrc); "
+                               "this package has no CPU fallback")
+    L = C.CDLL(_LIB)
+    dp, ip, vp = C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p
+    L.ghicp_abi_version.restype = C.c_int
+    L.ghicp_device_count.restype = C.c_int
+    L.ghicp_last_error.restype = C.c_char_p
+    L.ghicp_last_error.argtypes = [vp]
+    L.ghicp_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.ghicp_destroy.argtypes = [vp]
+    L.ghicp_set_keypoints.argtypes = [vp, dp, C.c_int, dp, C.c_int]
+    L.ghicp_set_bsc.argtypes = [vp, vp, C.c_int, vp, C.c_int]
+    L.ghicp_set_fpfh.argtypes = [vp, vp, vp]
+    L.ghicp_build_fd.argtypes = [vp]
+    L.ghicp_iterate.argtypes = [vp, C.POINTER(IterStats)]
+    L.ghicp_run.argtypes = [vp, dp, ip]
+    L.ghicp_get_pairs.argtypes = [vp, ip, ip, C.c_int, ip]
+    L.ghicp_get_source.argtypes = [vp, dp]
+    L.ghicp_get_rt.argtypes = [vp, dp]
+    L.ghicp_get_fd.argtypes = [vp, dp]
+    L.ghicp_probe_rowmin.argtypes = [vp, ip, dp, dp, dp, dp]
+    L.ghicp_set_state.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]
+    L.ghicp_km_solve.argtypes = [C.c_int, dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, ip, dp, ip]
+    L.ghicp_rigid_fit.argtypes = [C.c_int, dp, dp, C.c_int, dp]
+    L.ghicp_comm_unique_id.argtypes = [vp]
+    L.ghicp_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    _lib = L
+    return L
+
+
+def device_count():
+    return lib().ghicp_device_count()
+
+
+def check(rc, ctx=None):
+    if rc < 0:
+        msg = lib().ghicp_last_error(ctx)
+        raise GhicpError(rc, msg.decode() if msg else "")
+    return rc
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def km_solve(W, sp=None, tp=None, eps=0.01, penalty=1000.0, device=0):
+    """Stand-alone Km replacement on a dense weight matrix (include/km.h:38-53)."""
+    W = np.ascontiguousarray(W, dtype=np.float64)
+    n = W.shape[0]
+    sp = n if sp is None else sp
+    tp = n if tp is None else tp
+    match = np.zeros(n, np.int32)
+    e = C.c_double(0)
+    r = C.c_int(0)
+    check(lib().ghicp_km_solve(device, _dp(W), n, sp, tp, eps, penalty, _ip(match), C.byref(e), C.byref(r)))
+    return match, e.value, r.value
+
+
+def rigid_fit(S, T, device=0):
+    S = np.asfortranarray(S, dtype=np.float64)
+    T = np.asfortranarray(T, dtype=np.float64)
+    Rt = np.zeros(16)
+    check(lib().ghicp_rigid_fit(device, _dp(S), _dp(T), S.shape[0], _dp(Rt)))
+    return Rt.reshape(4, 4).T.copy()

@@ -1,0 +1,446 @@
+// ghicp_auction.cu — GPU replacement of Km::kmsolve (src/km.cpp:40-126) for the graph that
+// findcorrespondenceKM builds (src/ghicp_reg.cpp:348-365).
+//
+// The reference solves a max-weight PERFECT matching on the padded n x n matrix w = -CD (CD < penalty)
+// else -penalty, and then drops every matched pair whose weight == -penalty (src/km.cpp:162).  That is
+// exactly the max-GAIN PARTIAL matching over the candidate edges g_ij = penalty - CD_ij > 0 (any partial
+// matching completes to a perfect one with zero-gain edges).  We solve that sparse problem with an
+// epsilon-scaled Jacobi forward auction (persons = source rows, objects = target columns, every person
+// owns a private zero-gain dummy object) followed by a reverse auction that restores complementary
+// slackness for objects left unassigned with a positive price (Bertsekas & Castanon's forward/reverse
+// scheme for asymmetric assignment).  On termination with eps: total gain >= optimum - n_persons*eps,
+// the same guarantee the reference's eps-tight Kuhn–Munkres gives with KM_eps (include/ghicp_reg.h:38).
+//
+// All tie-breaks are explicit (value, then smaller index), so the result does not depend on the
+// order in which atomics land.
+#include <climits>
+#include <cstdio>
+
+#include "ghicp_internal.h"
+
+namespace ghicp_b200 {
+
+namespace {
+
+constexpr int UNASSIGNED = -1;
+constexpr int DUMMY = -2;
+constexpr int AUC_BLOCK = 256;
+constexpr int AUC_GRID = 148 * 4;
+
+__device__ __forceinline__ unsigned long long d2ull(double v) { return (unsigned long long)__double_as_longlong(v); }
+
+// (best value, its index, second-best value) merge with explicit tie-breaks
+struct Top2 {
+  double best, second;
+  int idx;
+};
+__device__ __forceinline__ void top2_push(Top2 &t, double v, int idx) {
+  if (v > t.best || (v == t.best && idx < t.idx)) {
+    t.second = t.best;
+    t.best = v;
+    t.idx = idx;
+  } else if (v > t.second) {
+    t.second = v;
+  }
+}
+__device__ __forceinline__ void top2_merge(Top2 &a, double ob, int oi, double os) {
+  if (ob > a.best || (ob == a.best && oi < a.idx)) {
+    double nb2 = fmax(a.best, os);
+    a.best = ob; a.idx = oi; a.second = nb2;
+  } else {
+    a.second = fmax(a.second, ob);
+  }
+}
+__device__ __forceinline__ void warp_top2(Top2 &t) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double ob = __shfl_xor_sync(0xffffffffu, t.best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, t.idx, o);
+    double os = __shfl_xor_sync(0xffffffffu, t.second, o);
+    // a real entry (oi >= 0) merges; empty lanes carry -inf
+    if (oi >= 0) top2_merge(t, ob, oi, os);
+  }
+}
+
+struct AucArgs {
+  const long long *rowptr; int n_chunks;  // row i spans rowptr[i*n_chunks] .. rowptr[(i+1)*n_chunks]
+  const int *csr_col; const double *csr_gain;
+  const long long *colptr; const int *csc_row; const double *csc_gain;
+  double *price, *profit;
+  int *assign, *owner;
+  unsigned long long *bidmax; int *bidwin;
+  int *bid_obj; double *bid_val, *bid_aux;
+  int *counters;  // [0],[1]: ping-pong list sizes, [2]: base list size
+  double eps;
+};
+
+__global__ void k_auc_init(int n_rows, int n_cols, const long long *rowptr, int n_chunks, double *price,
+                           int *base_list, int *counters, unsigned long long *bidmax, int *bidwin, int nmax) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_cols) price[i] = 0.0;
+  if (i < nmax) { bidmax[i] = 0ull; bidwin[i] = INT_MAX; }
+  if (i < n_rows) {
+    if (rowptr[(size_t)(i + 1) * n_chunks] > rowptr[(size_t)i * n_chunks]) {
+      int pos = atomicAdd(&counters[2], 1);
+      base_list[pos] = i;
+    }
+  }
+}
+
+__global__ void k_auc_phase_start(int n_rows, int n_cols, const long long *rowptr, int n_chunks, int *assign,
+                                  int *owner, double *profit) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_cols) owner[i] = -1;
+  if (i < n_rows) {
+    const bool has = rowptr[(size_t)(i + 1) * n_chunks] > rowptr[(size_t)i * n_chunks];
+    assign[i] = has ? UNASSIGNED : DUMMY;
+    profit[i] = 0.0;
+  }
+}
+
+// ---- forward round -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(AUC_BLOCK) k_fwd_bid(AucArgs a, const int *list, int cur) {
+  const int n_active = a.counters[cur];
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.counters[cur ^ 1] = 0;
+  for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_active; w += warps) {
+    const int i = list[w];
+    const long long b = a.rowptr[(size_t)i * a.n_chunks], e = a.rowptr[(size_t)(i + 1) * a.n_chunks];
+    Top2 t{-1e300, -1e300, -1};
+    double bgain = 0.0;
+    for (long long k = b + lane; k < e; k += 32) {
+      const int j = a.csr_col[k];
+      const double g = a.csr_gain[k];
+      const double v = g - a.price[j];
+      if (v > t.best || (v == t.best && j < t.idx)) bgain = g;
+      top2_push(t, v, j);
+    }
+    // reduce; carry the gain of the best edge along
+    {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        double ob = __shfl_xor_sync(0xffffffffu, t.best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, t.idx, o);
+        double os = __shfl_xor_sync(0xffffffffu, t.second, o);
+        double og = __shfl_xor_sync(0xffffffffu, bgain, o);
+        if (oi >= 0) {
+          if (ob > t.best || (ob == t.best && oi < t.idx) || t.idx < 0) bgain = og;
+          if (t.idx < 0) { t.best = ob; t.idx = oi; t.second = os; }
+          else top2_merge(t, ob, oi, os);
+        }
+      }
+    }
+    if (lane == 0) {
+      if (t.idx < 0 || t.best <= 0.0) {
+        // the private zero-gain dummy is at least as good: stay unmatched
+        a.assign[i] = DUMMY;
+        a.profit[i] = 0.0;
+      } else {
+        const double wv = fmax(t.second, 0.0);
+        const double newprice = a.price[t.idx] + (t.best - wv) + a.eps;
+        a.bid_obj[i] = t.idx;
+        a.bid_val[i] = newprice;
+        a.bid_aux[i] = bgain;
+        atomicMax(&a.bidmax[t.idx], d2ull(newprice));
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(AUC_BLOCK) k_fwd_resolve(AucArgs a, const int *list, int cur) {
+  const int n_active = a.counters[cur];
+  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_active; w += gridDim.x * blockDim.x) {
+    const int i = list[w];
+    if (a.assign[i] != UNASSIGNED) continue;
+    const int j = a.bid_obj[i];
+    if (d2ull(a.bid_val[i]) == a.bidmax[j]) atomicMin(&a.bidwin[j], i);
+  }
+}
+
+__global__ void __launch_bounds__(AUC_BLOCK) k_fwd_commit(AucArgs a, const int *list, int *next, int cur) {
+  const int n_active = a.counters[cur];
+  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_active; w += gridDim.x * blockDim.x) {
+    const int i = list[w];
+    if (a.assign[i] != UNASSIGNED) continue;  // went to its dummy
+    const int j = a.bid_obj[i];
+    if (a.bidwin[j] == i) {
+      const int prev = a.owner[j];
+      a.owner[j] = i;
+      a.price[j] = a.bid_val[i];
+      a.assign[i] = j;
+      a.profit[i] = a.bid_aux[i] - a.bid_val[i];
+      if (prev >= 0) {
+        a.assign[prev] = UNASSIGNED;
+        next[atomicAdd(&a.counters[cur ^ 1], 1)] = prev;
+      }
+    } else {
+      next[atomicAdd(&a.counters[cur ^ 1], 1)] = i;
+    }
+  }
+}
+// reset the per-object bid slots touched this round (separate pass: no read/write race with commit)
+__global__ void __launch_bounds__(AUC_BLOCK) k_fwd_reset(AucArgs a, const int *list, int cur) {
+  const int n_active = a.counters[cur];
+  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_active; w += gridDim.x * blockDim.x) {
+    const int i = list[w];
+    const int j = a.bid_obj[i];
+    if (j >= 0) { a.bidmax[j] = 0ull; a.bidwin[j] = INT_MAX; }
+  }
+}
+
+// ---- reverse round -------------------------------------------------------------------------------
+__global__ void k_rev_collect(int n_cols, const int *owner, const double *price, int *list, int *counters, int cur) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n_cols && owner[j] < 0 && price[j] > 0.0) list[atomicAdd(&counters[cur], 1)] = j;
+}
+
+__global__ void __launch_bounds__(AUC_BLOCK) k_rev_offer(AucArgs a, const int *list, int cur) {
+  const int n_active = a.counters[cur];
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.counters[cur ^ 1] = 0;
+  for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_active; w += warps) {
+    const int j = list[w];
+    const long long b = a.colptr[j], e = a.colptr[j + 1];
+    Top2 t{-1e300, -1e300, -1};
+    for (long long k = b + lane; k < e; k += 32) {
+      const int i = a.csc_row[k];
+      const double v = a.csc_gain[k] - a.profit[i];
+      top2_push(t, v, i);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      double ob = __shfl_xor_sync(0xffffffffu, t.best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, t.idx, o);
+      double os = __shfl_xor_sync(0xffffffffu, t.second, o);
+      if (oi >= 0) {
+        if (t.idx < 0) { t.best = ob; t.idx = oi; t.second = os; }
+        else top2_merge(t, ob, oi, os);
+      }
+    }
+    if (lane == 0) {
+      if (t.idx < 0 || t.best <= a.eps) {
+        a.price[j] = 0.0;   // nobody is worth attracting: price falls to the floor, object stays free
+        a.bid_obj[j] = -1;
+      } else {
+        const double delta = fmin(t.best, (t.best - t.second) + a.eps);
+        a.bid_obj[j] = t.idx;   // person attracted
+        a.bid_val[j] = delta;
+        a.bid_aux[j] = t.best;
+        atomicMax(&a.bidmax[t.idx], d2ull(delta));
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(AUC_BLOCK) k_rev_resolve(AucArgs a, const int *list, int cur) {
+  const int n_active = a.counters[cur];
+  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_active; w += gridDim.x * blockDim.x) {
+    const int j = list[w];
+    const int i = a.bid_obj[j];
+    if (i < 0) continue;
+    if (d2ull(a.bid_val[j]) == a.bidmax[i]) atomicMin(&a.bidwin[i], j);
+  }
+}
+
+__global__ void __launch_bounds__(AUC_BLOCK) k_rev_commit(AucArgs a, const int *list, int *next, int cur) {
+  const int n_active = a.counters[cur];
+  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_active; w += gridDim.x * blockDim.x) {
+    const int j = list[w];
+    const int i = a.bid_obj[j];
+    if (i < 0) continue;
+    if (a.bidwin[i] == j) {
+      const int old = a.assign[i];
+      a.assign[i] = j;
+      a.owner[j] = i;
+      a.price[j] = a.bid_aux[j] - a.bid_val[j];
+      a.profit[i] += a.bid_val[j];
+      if (old >= 0) {
+        a.owner[old] = -1;
+        if (a.price[old] > 0.0) next[atomicAdd(&a.counters[cur ^ 1], 1)] = old;
+      }
+    } else {
+      next[atomicAdd(&a.counters[cur ^ 1], 1)] = j;
+    }
+  }
+}
+__global__ void __launch_bounds__(AUC_BLOCK) k_rev_reset(AucArgs a, const int *list, int cur) {
+  const int n_active = a.counters[cur];
+  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_active; w += gridDim.x * blockDim.x) {
+    const int j = list[w];
+    const int i = a.bid_obj[j];
+    if (i >= 0) { a.bidmax[i] = 0ull; a.bidwin[i] = INT_MAX; }
+  }
+}
+
+// ---- CSC build ---------------------------------------------------------------------------------
+__global__ void k_col_count(const int *__restrict__ csr_col, long long nnz, int *__restrict__ colcnt) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < nnz) atomicAdd(&colcnt[csr_col[k]], 1);
+}
+__global__ void __launch_bounds__(1024) k_scan_i32(const int *__restrict__ cnt, long long *__restrict__ ptr,
+                                                   int *__restrict__ cursor, int L) {
+  __shared__ long long smem[33];
+  const int seg = (L + 1023) / 1024;
+  const int b = threadIdx.x * seg;
+  const int e = min(b + seg, L);
+  long long s = 0;
+  for (int k = b; k < e; ++k) s += cnt[k];
+  // block exclusive scan
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long x = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    long long y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) smem[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    long long w = smem[lane];
+    long long xs = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      long long y = __shfl_up_sync(0xffffffffu, xs, o);
+      if (lane >= o) xs += y;
+    }
+    smem[lane] = xs - w;
+    if (lane == 31) smem[32] = xs;
+  }
+  __syncthreads();
+  long long off = smem[warp] + x - s;
+  for (int k = b; k < e; ++k) {
+    ptr[k] = off;
+    off += cnt[k];
+    cursor[k] = 0;
+  }
+  if (threadIdx.x == 0) ptr[L] = smem[32];
+}
+__global__ void __launch_bounds__(AUC_BLOCK) k_csc_fill(int n_rows, const long long *rowptr, int n_chunks,
+                                                         const int *csr_col, const double *csr_gain,
+                                                         const long long *colptr, int *cursor, int *csc_row,
+                                                         double *csc_gain) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_rows; i += warps) {
+    const long long b = rowptr[(size_t)i * n_chunks], e = rowptr[(size_t)(i + 1) * n_chunks];
+    for (long long k = b + lane; k < e; k += 32) {
+      const int j = csr_col[k];
+      const long long pos = colptr[j] + atomicAdd(&cursor[j], 1);
+      csc_row[pos] = i;
+      csc_gain[pos] = csr_gain[k];
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_build_csc(Ctx *c, int n_rows, int n_cols, long long nnz) {
+  cudaError_t e;
+  if ((e = cudaMemsetAsync(c->d_colcnt, 0, sizeof(int) * (size_t)(n_cols + 1), c->stream)) != cudaSuccess) return e;
+  if (nnz > 0) {
+    k_col_count<<<(unsigned)((nnz + 255) / 256), 256, 0, c->stream>>>(c->d_csr_col, nnz, c->d_colcnt);
+    c->launches++;
+  }
+  // cursor reuse: d_bid_obj is free before the auction starts
+  k_scan_i32<<<1, 1024, 0, c->stream>>>(c->d_colcnt, c->d_colptr, c->d_bid_obj, n_cols);
+  c->launches++;
+  if (nnz > 0) {
+    k_csc_fill<<<AUC_GRID, AUC_BLOCK, 0, c->stream>>>(n_rows, c->d_rowptr, c->n_chunks, c->d_csr_col, c->d_csr_gain,
+                                                       c->d_colptr, c->d_bid_obj, c->d_csc_row, c->d_csc_gain);
+    c->launches++;
+  }
+  return cudaGetLastError();
+}
+
+int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, double max_gain, KmResult *res) {
+  cudaStream_t st = c->stream;
+  AucArgs a{};
+  a.rowptr = c->d_rowptr; a.n_chunks = c->n_chunks; a.csr_col = c->d_csr_col; a.csr_gain = c->d_csr_gain;
+  a.colptr = c->d_colptr; a.csc_row = c->d_csc_row; a.csc_gain = c->d_csc_gain;
+  a.price = c->d_price; a.profit = c->d_profit; a.assign = c->d_assign; a.owner = c->d_owner;
+  a.bidmax = c->d_bidmax; a.bidwin = c->d_bidwin; a.bid_obj = c->d_bid_obj; a.bid_val = c->d_bid_val;
+  a.bid_aux = c->d_bid_aux; a.counters = c->d_counters;
+  const int nmax = n_rows > n_cols ? n_rows : n_cols;
+  const int gmax = (nmax + 255) / 256;
+  int *base_list = c->d_flags;  // free during KM
+
+  cudaMemsetAsync(c->d_counters, 0, sizeof(int) * 8, st);
+  k_auc_init<<<gmax, 256, 0, st>>>(n_rows, n_cols, c->d_rowptr, c->n_chunks, c->d_price, base_list, c->d_counters,
+                                   c->d_bidmax, c->d_bidwin, nmax);
+  c->launches++;
+  cudaMemsetAsync(c->d_bid_obj, 0xff, sizeof(int) * (size_t)nmax, st);  // -1
+
+  // epsilon schedule
+  std::vector<double> eps_list;
+  {
+    double e0 = max_gain / 4.0;
+    while (e0 > eps_final * 1.0000001) { eps_list.push_back(e0); e0 /= 5.0; }
+    eps_list.push_back(eps_final);
+  }
+  if (nnz == 0) eps_list.assign(1, eps_final);
+
+  int rounds = 0;
+  const int max_rounds = 4000000;
+  for (size_t ph = 0; ph < eps_list.size(); ++ph) {
+    a.eps = eps_list[ph];
+    k_auc_phase_start<<<gmax, 256, 0, st>>>(n_rows, n_cols, c->d_rowptr, c->n_chunks, c->d_assign, c->d_owner,
+                                            c->d_profit);
+    c->launches++;
+    // active list 0 = base list
+    cudaMemcpyAsync(c->d_list[0], base_list, sizeof(int) * (size_t)n_rows, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(&c->d_counters[0], &c->d_counters[2], sizeof(int), cudaMemcpyDeviceToDevice, st);
+    int cur = 0;
+    // ---- forward rounds
+    int check_every = 1;
+    while (true) {
+      for (int r = 0; r < check_every; ++r) {
+        k_fwd_bid<<<AUC_GRID, AUC_BLOCK, 0, st>>>(a, c->d_list[cur], cur);
+        k_fwd_resolve<<<AUC_GRID, AUC_BLOCK, 0, st>>>(a, c->d_list[cur], cur);
+        k_fwd_commit<<<AUC_GRID, AUC_BLOCK, 0, st>>>(a, c->d_list[cur], c->d_list[cur ^ 1], cur);
+        k_fwd_reset<<<AUC_GRID, AUC_BLOCK, 0, st>>>(a, c->d_list[cur], cur);
+        c->launches += 4;
+        cur ^= 1;
+        ++rounds;
+      }
+      cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, st);
+      cudaError_t e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) { set_error(c, std::string("auction forward: ") + cudaGetErrorString(e)); return GHICP_E_CUDA; }
+      if (c->h_counters[cur] == 0) break;
+      if (rounds > max_rounds) { set_error(c, "auction: round limit exceeded"); return GHICP_E_NOCONV; }
+      check_every = check_every < 8 ? check_every * 2 : 8;
+    }
+    // ---- reverse rounds: objects left free with a positive price
+    cudaMemsetAsync(&c->d_counters[0], 0, sizeof(int) * 2, st);
+    cur = 0;
+    k_rev_collect<<<gmax, 256, 0, st>>>(n_cols, c->d_owner, c->d_price, c->d_list[cur], c->d_counters, cur);
+    c->launches++;
+    cudaMemsetAsync(c->d_bid_obj, 0xff, sizeof(int) * (size_t)nmax, st);
+    check_every = 1;
+    while (true) {
+      cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, st);
+      cudaError_t e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) { set_error(c, std::string("auction reverse: ") + cudaGetErrorString(e)); return GHICP_E_CUDA; }
+      if (c->h_counters[cur] == 0) break;
+      if (rounds > max_rounds) { set_error(c, "auction: round limit exceeded"); return GHICP_E_NOCONV; }
+      for (int r = 0; r < check_every; ++r) {
+        k_rev_offer<<<AUC_GRID, AUC_BLOCK, 0, st>>>(a, c->d_list[cur], cur);
+        k_rev_resolve<<<AUC_GRID, AUC_BLOCK, 0, st>>>(a, c->d_list[cur], cur);
+        k_rev_commit<<<AUC_GRID, AUC_BLOCK, 0, st>>>(a, c->d_list[cur], c->d_list[cur ^ 1], cur);
+        k_rev_reset<<<AUC_GRID, AUC_BLOCK, 0, st>>>(a, c->d_list[cur], cur);
+        c->launches += 4;
+        cur ^= 1;
+        ++rounds;
+      }
+      check_every = check_every < 8 ? check_every * 2 : 8;
+    }
+    cudaMemsetAsync(c->d_bid_obj, 0xff, sizeof(int) * (size_t)nmax, st);
+  }
+  if (res) { res->rounds = rounds; res->phases = (int)eps_list.size(); }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error(c, std::string("auction: ") + cudaGetErrorString(e)); return GHICP_E_CUDA; }
+  return GHICP_OK;
+}
+
+}  // namespace ghicp_b200

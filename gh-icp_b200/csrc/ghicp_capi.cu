@@ -1,0 +1,646 @@
+// ghicp_capi.cu — the C ABI of include/ghicp_b200.h: context management and the per-iteration
+// orchestration of GHRegistration::ghicp_reg's loop body (src/ghicp_reg.cpp:49-103).
+// Heavy work = CUDA kernels on the ctx stream; the scalar tail of an iteration (Euler angles,
+// convergence test, adjustweight, Rt accumulation — src/ghicp_reg.cpp:870-914, 771-789, 93) runs on
+// the host from one small read-back per iteration.  There is NO CPU fallback: without a CUDA device
+// every entry point fails with GHICP_E_NODEV.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+#include "ghicp_internal.h"
+
+namespace ghicp_b200 {
+
+static std::string g_last_error;
+static std::mutex g_err_mu;
+
+void set_error(Ctx *c, const std::string &msg) {
+  if (c) c->err = msg;
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  g_last_error = msg;
+}
+
+cudaError_t launch_solve_explicit(cudaStream_t stream, const double *d_s, const double *d_t, int n, DevIter *d_iter);
+
+#define CK(c, call)                                                                          \
+  do {                                                                                       \
+    cudaError_t e__ = (call);                                                                \
+    if (e__ != cudaSuccess) {                                                                \
+      set_error((c), std::string(#call) + ": " + cudaGetErrorString(e__));                   \
+      return (e__ == cudaErrorMemoryAllocation) ? GHICP_E_NOMEM : GHICP_E_CUDA;              \
+    }                                                                                        \
+  } while (0)
+
+template <typename T>
+static int dev_alloc(Ctx *c, T **p, size_t count) {
+  if (*p) { cudaFree(*p); *p = nullptr; }
+  if (count == 0) count = 1;
+  cudaError_t e = cudaMalloc((void **)p, count * sizeof(T));
+  if (e != cudaSuccess) {
+    *p = nullptr;
+    set_error(c, std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+    cudaGetLastError();
+    return GHICP_E_NOMEM;
+  }
+  return GHICP_OK;
+}
+template <typename T>
+static void dev_free(T **p) {
+  if (*p) { cudaFree(*p); *p = nullptr; }
+}
+
+static int use_device(Ctx *c) {
+  cudaError_t e = cudaSetDevice(c->device);
+  if (e != cudaSuccess) { set_error(c, std::string("cudaSetDevice: ") + cudaGetErrorString(e)); return GHICP_E_CUDA; }
+  return GHICP_OK;
+}
+
+static void free_all(Ctx *c) {
+  dev_free(&c->d_s); dev_free(&c->d_t);
+  dev_free(&c->d_bs); dev_free(&c->d_bt); dev_free(&c->d_fd16);
+  dev_free(&c->d_fs); dev_free(&c->d_ft); dev_free(&c->d_fdf);
+  dev_free(&c->d_part_cd); dev_free(&c->d_part_idx); dev_free(&c->d_part_stats);
+  dev_free(&c->d_row_cd); dev_free(&c->d_row_idx); dev_free(&c->d_col_cd); dev_free(&c->d_col_idx);
+  dev_free(&c->d_flags); dev_free(&c->d_sp); dev_free(&c->d_tp); dev_free(&c->d_iter);
+  dev_free(&c->d_cnt); dev_free(&c->d_rowptr); dev_free(&c->d_cursor);
+  dev_free(&c->d_csr_col); dev_free(&c->d_csr_gain); dev_free(&c->d_colptr); dev_free(&c->d_colcnt);
+  dev_free(&c->d_csc_row); dev_free(&c->d_csc_gain);
+  dev_free(&c->d_price); dev_free(&c->d_profit); dev_free(&c->d_assign); dev_free(&c->d_owner);
+  dev_free(&c->d_bidmax); dev_free(&c->d_bidwin); dev_free(&c->d_bid_obj); dev_free(&c->d_bid_val);
+  dev_free(&c->d_bid_aux); dev_free(&c->d_list[0]); dev_free(&c->d_list[1]); dev_free(&c->d_counters);
+  if (c->h_iter) { cudaFreeHost(c->h_iter); c->h_iter = nullptr; }
+  if (c->h_counters) { cudaFreeHost(c->h_counters); c->h_counters = nullptr; }
+  if (c->h_stage) { cudaFreeHost(c->h_stage); c->h_stage = nullptr; c->h_stage_cap = 0; }
+  c->csr_cap = c->csc_cap = 0;
+}
+
+static void reset_loop_state(Ctx *c) {
+  // Energyfunction::init (include/ghicp_reg.h:26-41) + GHRegistration ctor (include/ghicp_reg.h:77-117)
+  c->penalty_initial = 2.0;
+  c->para1 = 1.0;
+  c->para2 = 1.0;
+  c->min_cor = 10;
+  c->weight_changing_rate = 6;
+  c->KM_eps = (c->cfg.km_eps > 0.0) ? c->cfg.km_eps : 0.01;
+  c->scale_f = 0.005 * c->cfg.bbx_magnitude;  // double product rounded to float (ghicp_reg.h:40)
+  c->iteration = 0;
+  c->RMS = 99999;
+  c->FDM = 0; c->FDstd = 0; c->IoU = 0;
+  c->converge = false;
+  c->last_mean = 0.0;
+  for (int i = 0; i < 16; ++i) c->Rt_tillnow[i] = (i % 5 == 0) ? 1.0 : 0.0;
+}
+
+// workspaces that depend on (N, M)
+static int alloc_workspaces(Ctx *c) {
+  const int N = c->N, M = c->M;
+  const int nmax = std::max(N, M);
+  const int row_ctas = (N + 7) / 8;
+  int want = (148 * 4 + row_ctas - 1) / row_ctas;
+  int lim = std::max(1, M / 2048);
+  c->n_chunks = std::max(1, std::min(want, lim));
+  int rc;
+  const size_t L = (size_t)N * c->n_chunks;
+  if ((rc = dev_alloc(c, &c->d_part_cd, L))) return rc;
+  if ((rc = dev_alloc(c, &c->d_part_idx, L))) return rc;
+  c->part_stats_cap = (size_t)row_ctas * c->n_chunks * 2;
+  if ((rc = dev_alloc(c, &c->d_part_stats, c->part_stats_cap))) return rc;
+  if ((rc = dev_alloc(c, &c->d_row_cd, (size_t)N))) return rc;
+  if ((rc = dev_alloc(c, &c->d_row_idx, (size_t)N))) return rc;
+  if ((rc = dev_alloc(c, &c->d_col_cd, (size_t)M))) return rc;
+  if ((rc = dev_alloc(c, &c->d_col_idx, (size_t)M))) return rc;
+  if ((rc = dev_alloc(c, &c->d_flags, (size_t)nmax))) return rc;
+  if ((rc = dev_alloc(c, &c->d_sp, (size_t)nmax))) return rc;
+  if ((rc = dev_alloc(c, &c->d_tp, (size_t)nmax))) return rc;
+  if ((rc = dev_alloc(c, &c->d_iter, 1))) return rc;
+  if (!c->h_iter && cudaMallocHost((void **)&c->h_iter, sizeof(DevIter)) != cudaSuccess) return GHICP_E_NOMEM;
+  if (!c->h_counters && cudaMallocHost((void **)&c->h_counters, sizeof(int) * 8) != cudaSuccess) return GHICP_E_NOMEM;
+  if (c->cfg.corr_type == GHICP_CT_KM) {
+    if ((rc = dev_alloc(c, &c->d_cnt, L + 1))) return rc;
+    if ((rc = dev_alloc(c, &c->d_rowptr, L + 1))) return rc;
+    if ((rc = dev_alloc(c, &c->d_cursor, L + 1))) return rc;
+    if ((rc = dev_alloc(c, &c->d_colptr, (size_t)M + 1))) return rc;
+    if ((rc = dev_alloc(c, &c->d_colcnt, (size_t)M + 1))) return rc;
+    if ((rc = dev_alloc(c, &c->d_price, (size_t)M))) return rc;
+    if ((rc = dev_alloc(c, &c->d_profit, (size_t)N))) return rc;
+    if ((rc = dev_alloc(c, &c->d_assign, (size_t)N))) return rc;
+    if ((rc = dev_alloc(c, &c->d_owner, (size_t)M))) return rc;
+    if ((rc = dev_alloc(c, &c->d_bidmax, (size_t)nmax))) return rc;
+    if ((rc = dev_alloc(c, &c->d_bidwin, (size_t)nmax))) return rc;
+    if ((rc = dev_alloc(c, &c->d_bid_obj, (size_t)nmax))) return rc;
+    if ((rc = dev_alloc(c, &c->d_bid_val, (size_t)nmax))) return rc;
+    if ((rc = dev_alloc(c, &c->d_bid_aux, (size_t)nmax))) return rc;
+    if ((rc = dev_alloc(c, &c->d_list[0], (size_t)nmax))) return rc;
+    if ((rc = dev_alloc(c, &c->d_list[1], (size_t)nmax))) return rc;
+    if ((rc = dev_alloc(c, &c->d_counters, 8))) return rc;
+  }
+  return GHICP_OK;
+}
+
+static int ensure_edges(Ctx *c, long long nnz) {
+  const size_t need = (size_t)std::max<long long>(nnz, 1);
+  int rc;
+  if (need > c->csr_cap) {
+    size_t cap = need + need / 8 + 1024;
+    if ((rc = dev_alloc(c, &c->d_csr_col, cap))) return rc;
+    if ((rc = dev_alloc(c, &c->d_csr_gain, cap))) return rc;
+    c->csr_cap = cap;
+  }
+  if (need > c->csc_cap) {
+    size_t cap = need + need / 8 + 1024;
+    if ((rc = dev_alloc(c, &c->d_csc_row, cap))) return rc;
+    if ((rc = dev_alloc(c, &c->d_csc_gain, cap))) return rc;
+    c->csc_cap = cap;
+  }
+  return GHICP_OK;
+}
+
+static int build_fd(Ctx *c) {
+  if (c->fd_built) return GHICP_OK;
+  if (c->cfg.feature_type == GHICP_FT_BSC) {
+    if (!c->have_bsc) { set_error(c, "build_fd: BSC descriptors not set"); return GHICP_E_ARG; }
+    const int Vneed = (c->cfg.dof == 6) ? 4 : 2;
+    if (c->V < Vneed) { set_error(c, "build_fd: not enough BSC source variants for dof"); return GHICP_E_ARG; }
+    int rc = dev_alloc(c, &c->d_fd16, (size_t)c->N * c->ldM);
+    if (rc) return rc;
+    CK(c, launch_fd_bsc(c));
+  } else if (c->cfg.feature_type == GHICP_FT_FPFH) {
+    if (!c->have_fpfh) { set_error(c, "build_fd: FPFH descriptors not set"); return GHICP_E_ARG; }
+    int rc = dev_alloc(c, &c->d_fdf, (size_t)c->N * c->ldM);
+    if (rc) return rc;
+    CK(c, launch_fd_fpfh(c));
+  }
+  c->fd_built = true;
+  return GHICP_OK;
+}
+
+static CostParams make_cost_params(const Ctx *c) {
+  CostParams cp;
+  cp.scale = (double)c->scale_f;
+  cp.WFD = std::exp(-1.0 * c->iteration / c->weight_changing_rate);  // src/ghicp_reg.cpp:247
+  cp.WED = 1.0 - cp.WFD;
+  cp.ex = 1.0 / (c->iteration + 1);                                   // src/ghicp_reg.cpp:308
+  cp.pivot = c->last_mean;
+  return cp;
+}
+static LoopScalars make_loop_scalars(const Ctx *c, const CostParams &cp) {
+  LoopScalars ls;
+  ls.iteration = c->iteration;
+  ls.RMS = c->RMS; ls.FDM = c->FDM; ls.FDstd = c->FDstd;
+  ls.para1 = c->para1; ls.para2 = c->para2;
+  ls.scale = cp.scale; ls.WED = cp.WED; ls.WFD = cp.WFD;
+  ls.penalty_initial = c->penalty_initial;
+  return ls;
+}
+
+static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
+  if (c->N <= 0 || c->M <= 0) { set_error(c, "iterate: keypoints not set"); return GHICP_E_ARG; }
+  int rc;
+  if ((rc = build_fd(c))) return rc;
+  c->launches = 0;
+  cudaStream_t st = c->stream;
+  const CostParams cp = make_cost_params(c);
+  const LoopScalars ls = make_loop_scalars(c, cp);
+  KmResult kres;
+  long long nnz = 0;
+
+  CK(c, cudaEventRecord(c->ev[0], st));
+  // calED + calCD_* (+ the row scan of NN / NNR)
+  CK(c, launch_rowsweep(c, 0, cp));
+  CK(c, launch_finalize_stats(c, cp, ls));
+  CK(c, cudaEventRecord(c->ev[1], st));
+  // findcorrespondence*
+  if (c->cfg.corr_type == GHICP_CT_NN) {
+    CK(c, launch_select_nn(c));
+  } else if (c->cfg.corr_type == GHICP_CT_NNR) {
+    CK(c, launch_colsweep(c, cp));
+    CK(c, launch_select_nnr(c));
+  } else {
+    CK(c, launch_rowsweep(c, 1, cp));
+    CK(c, launch_scan_counts(c));
+    CK(c, cudaMemcpyAsync(c->h_iter, c->d_iter, sizeof(DevIter), cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    nnz = c->h_iter->nnz;
+    const double penalty = c->h_iter->penalty;
+    if ((rc = ensure_edges(c, nnz))) return rc;
+    if (nnz > 0) CK(c, launch_rowsweep(c, 2, cp));
+    CK(c, launch_build_csc(c, c->N, c->M, nnz));
+    if ((rc = km_auction(c, c->N, c->M, nnz, c->KM_eps, std::max(penalty, c->KM_eps), &kres))) return rc;
+    CK(c, launch_select_km(c));
+  }
+  CK(c, cudaEventRecord(c->ev[2], st));
+  // transformestimation (numeric core) + update of all source keypoints
+  CK(c, launch_solve(c, cp));
+  CK(c, launch_apply(c));
+  CK(c, cudaEventRecord(c->ev[3], st));
+  CK(c, cudaMemcpyAsync(c->h_iter, c->d_iter, sizeof(DevIter), cudaMemcpyDeviceToHost, st));
+  CK(c, cudaStreamSynchronize(st));
+
+  // ---- host tail (scalars only) -----------------------------------------------------------
+  const DevIter &h = *c->h_iter;
+  const int cor_number = h.cor;
+  c->last_cor = cor_number;
+  c->RMS = h.rmse;   // src/ghicp_reg.cpp:578, 695, 766
+  c->FDM = h.fdm;
+  c->FDstd = h.fdstd;
+  c->last_mean = h.cd_mean;
+  int warnings = 0;
+  if (cor_number < c->min_cor) { c->converge = true; warnings |= GHICP_W_FEW_PAIRS; }  // :796-797
+  c->IoU = 1.0 * cor_number / (c->N + c->M - cor_number);                                // :799
+  double R[3][3], t[3];
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) R[i][j] = h.Rt[j * 4 + i];
+    t[i] = h.Rt[12 + i];
+  }
+  const double dx = t[0], dy = t[1], dz = t[2];
+  double ax = std::atan2(R[2][1], R[2][2]);
+  double ay = std::atan2(-R[2][0], std::sqrt(R[2][1] * R[2][1] + R[2][2] * R[2][2]));
+  double az = std::atan2(R[0][1], R[0][0]);
+  const double pi = 3.1415926;  // src/ghicp_reg.cpp:876
+  ax = ax / pi * 180; ay = ay / pi * 180; az = az / pi * 180;
+  const double conv_t = (double)c->cfg.converge_t, conv_r = (double)c->cfg.converge_r;
+  if (std::abs(dx) < conv_t && std::abs(dy) < conv_t && std::abs(dz) < conv_t && std::abs(ax) < conv_r &&
+      std::abs(ay) < conv_r && std::abs(az) < conv_r)
+    c->converge = true;  // :909-914
+  // adjustweight (:771-789)
+  if (c->cfg.estimated_iou / c->IoU > c->cfg.adjust_ratio) {
+    c->para1 += c->cfg.adjust_step;
+    c->para2 += c->cfg.adjust_step;
+  } else if (c->IoU / c->cfg.estimated_iou > c->cfg.adjust_ratio) {
+    c->para1 -= c->cfg.adjust_step;
+    c->para2 -= c->cfg.adjust_step;
+  }
+  // Rt_tillnow = Rt_temp * Rt_tillnow (:93)
+  double acc[16];
+  for (int col = 0; col < 4; ++col)
+    for (int row = 0; row < 4; ++row) {
+      double s = 0;
+      for (int k = 0; k < 4; ++k) s += h.Rt[k * 4 + row] * c->Rt_tillnow[col * 4 + k];
+      acc[col * 4 + row] = s;
+    }
+  std::memcpy(c->Rt_tillnow, acc, sizeof(acc));
+
+  if (out) {
+    std::memset(out, 0, sizeof(*out));
+    out->iteration = c->iteration;
+    out->cor = cor_number;
+    out->converged = c->converge ? 1 : 0;
+    out->warnings = warnings;
+    std::memcpy(out->Rt, h.Rt, sizeof(double) * 16);
+    std::memcpy(out->Rt_tillnow, c->Rt_tillnow, sizeof(double) * 16);
+    out->cd_mean = h.cd_mean; out->cd_std = h.cd_std; out->penalty = h.penalty;
+    out->rmse = h.rmse; out->rmse_after = h.rmse_after; out->fdm = h.fdm; out->fdstd = h.fdstd;
+    out->iou = c->IoU; out->para1 = c->para1; out->para2 = c->para2;
+    const int n = std::max(c->N, c->M);
+    out->km_energy = (c->cfg.corr_type == GHICP_CT_KM) ? h.km_cd_sum + (double)(n - cor_number) * h.penalty : 0.0;
+    out->ax = ax; out->ay = ay; out->az = az;
+    out->nnz = nnz; out->km_rounds = kres.rounds; out->km_phases = kres.phases;
+    out->gpu_launches = c->launches;
+    float ms;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); out->ms_cost = ms;
+    cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); out->ms_corr = ms;
+    cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); out->ms_solve = ms;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]); out->ms_total = ms;
+  }
+  c->iteration++;
+  return warnings;
+}
+
+}  // namespace ghicp_b200
+
+using namespace ghicp_b200;
+
+extern "C" {
+
+int ghicp_abi_version(void) { return GHICP_ABI_VERSION; }
+
+int ghicp_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+const char *ghicp_last_error(const ghicp_ctx *ctx) {
+  const Ctx *c = reinterpret_cast<const Ctx *>(ctx);
+  if (c) return c->err.c_str();
+  return g_last_error.c_str();
+}
+
+int ghicp_create(const ghicp_config *cfg, ghicp_ctx **out) {
+  if (!cfg || !out) { set_error(nullptr, "ghicp_create: null argument"); return GHICP_E_ARG; }
+  *out = nullptr;
+  if (ghicp_device_count() <= 0) {
+    set_error(nullptr, "ghicp_create: no CUDA device visible (this library has no CPU fallback)");
+    return GHICP_E_NODEV;
+  }
+  if (cfg->device < 0 || cfg->device >= ghicp_device_count()) { set_error(nullptr, "ghicp_create: bad device"); return GHICP_E_ARG; }
+  if (cfg->corr_type < GHICP_CT_NN || cfg->corr_type > GHICP_CT_KM) { set_error(nullptr, "ghicp_create: bad corr_type"); return GHICP_E_ARG; }
+  if (cfg->feature_type != GHICP_FT_BSC && cfg->feature_type != GHICP_FT_FPFH && cfg->feature_type != GHICP_FT_NONE) {
+    set_error(nullptr, "ghicp_create: feature_type must be BSC, FPFH or None (RoPS is 'Not passed yet' in the reference, test/ghicp_main.cpp:130-134)");
+    return GHICP_E_ARG;
+  }
+  Ctx *c = new Ctx();
+  c->cfg = *cfg;
+  c->device = cfg->device;
+  int rc = use_device(c);
+  if (rc) { delete c; return rc; }
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return GHICP_E_CUDA; }
+  for (auto &e : c->ev) cudaEventCreate(&e);
+  reset_loop_state(c);
+  *out = reinterpret_cast<ghicp_ctx *>(c);
+  return GHICP_OK;
+}
+
+int ghicp_destroy(ghicp_ctx *ctx) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c) return GHICP_OK;
+  use_device(c);
+  cudaStreamSynchronize(c->stream);
+  free_all(c);
+  for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return GHICP_OK;
+}
+
+int ghicp_set_keypoints(ghicp_ctx *ctx, const double *sxyz, int N, const double *txyz, int M) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !sxyz || !txyz || N <= 0 || M <= 0) { set_error(c, "set_keypoints: bad argument"); return GHICP_E_ARG; }
+  int rc;
+  if ((rc = use_device(c))) return rc;
+  const bool resize = (N != c->N || M != c->M);
+  if (resize) {
+    c->N = N; c->M = M;
+    c->ldM = ((size_t)M + 63) / 64 * 64;
+    if ((rc = dev_alloc(c, &c->d_s, 3 * (size_t)N))) return rc;
+    if ((rc = dev_alloc(c, &c->d_t, 3 * (size_t)M))) return rc;
+    if ((rc = alloc_workspaces(c))) return rc;
+    c->have_bsc = c->have_fpfh = c->fd_built = false;
+    reset_loop_state(c);
+  }
+  const size_t need = 3 * ((size_t)N + M) * sizeof(double);
+  if (need > c->h_stage_cap) {
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (cudaMallocHost((void **)&c->h_stage, need) != cudaSuccess) { c->h_stage = nullptr; c->h_stage_cap = 0; return GHICP_E_NOMEM; }
+    c->h_stage_cap = need;
+  }
+  std::memcpy(c->h_stage, sxyz, 3 * (size_t)N * sizeof(double));
+  std::memcpy(c->h_stage + 3 * (size_t)N, txyz, 3 * (size_t)M * sizeof(double));
+  CK(c, cudaMemcpyAsync(c->d_s, c->h_stage, 3 * (size_t)N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CK(c, cudaMemcpyAsync(c->d_t, c->h_stage + 3 * (size_t)N, 3 * (size_t)M * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  return GHICP_OK;
+}
+
+int ghicp_set_bsc(ghicp_ctx *ctx, const uint8_t *s_bits, int V, const uint8_t *t_bits, int bits) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !s_bits || !t_bits || V <= 0 || V > 4 || bits <= 0 || bits > 65535 || c->N <= 0) {
+    set_error(c, "set_bsc: bad argument or keypoints not set");
+    return GHICP_E_ARG;
+  }
+  int rc;
+  if ((rc = use_device(c))) return rc;
+  c->V = V; c->bits = bits;
+  c->Bbytes = (int)std::ceil((float)bits / 8.f);  // include/stereo_binary_feature.h:50
+  c->W64 = (c->Bbytes + 7) / 8;
+  if ((rc = dev_alloc(c, &c->d_bs, (size_t)V * c->W64 * c->N))) return rc;
+  if ((rc = dev_alloc(c, &c->d_bt, (size_t)c->W64 * c->M))) return rc;
+  uint8_t *raw_s = nullptr, *raw_t = nullptr;
+  const size_t ns = (size_t)V * c->N * c->Bbytes, nt = (size_t)c->M * c->Bbytes;
+  if ((rc = dev_alloc(c, &raw_s, ns))) return rc;
+  if ((rc = dev_alloc(c, &raw_t, nt))) { dev_free(&raw_s); return rc; }
+  cudaError_t e = cudaMemcpyAsync(raw_s, s_bits, ns, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(raw_t, t_bits, nt, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) e = launch_pack_bsc(c, raw_s, raw_t);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  dev_free(&raw_s); dev_free(&raw_t);
+  if (e != cudaSuccess) { set_error(c, std::string("set_bsc: ") + cudaGetErrorString(e)); return GHICP_E_CUDA; }
+  c->have_bsc = true;
+  c->fd_built = false;
+  return GHICP_OK;
+}
+
+int ghicp_set_fpfh(ghicp_ctx *ctx, const float *s, const float *t) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !s || !t || c->N <= 0) { set_error(c, "set_fpfh: bad argument or keypoints not set"); return GHICP_E_ARG; }
+  int rc;
+  if ((rc = use_device(c))) return rc;
+  if ((rc = dev_alloc(c, &c->d_fs, (size_t)c->N * 33))) return rc;
+  if ((rc = dev_alloc(c, &c->d_ft, (size_t)c->M * 33))) return rc;
+  CK(c, cudaMemcpyAsync(c->d_fs, s, (size_t)c->N * 33 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  CK(c, cudaMemcpyAsync(c->d_ft, t, (size_t)c->M * 33 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  c->have_fpfh = true;
+  c->fd_built = false;
+  return GHICP_OK;
+}
+
+int ghicp_build_fd(ghicp_ctx *ctx) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c) return GHICP_E_ARG;
+  int rc;
+  if ((rc = use_device(c))) return rc;
+  if ((rc = build_fd(c))) return rc;
+  CK(c, cudaStreamSynchronize(c->stream));
+  return GHICP_OK;
+}
+
+int ghicp_iterate(ghicp_ctx *ctx, ghicp_iter_stats *out) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c) return GHICP_E_ARG;
+  int rc;
+  if ((rc = use_device(c))) return rc;
+  return iterate_impl(c, out);
+}
+
+int ghicp_run(ghicp_ctx *ctx, double Rt_final[16], int *iterations) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !Rt_final) return GHICP_E_ARG;
+  int rc;
+  if ((rc = use_device(c))) return rc;
+  int it = 0;
+  while (!c->converge) {  // src/ghicp_reg.cpp:49
+    ghicp_iter_stats st;
+    rc = iterate_impl(c, &st);
+    if (rc < 0) return rc;
+    ++it;
+    if (c->cfg.max_iter > 0 && it >= c->cfg.max_iter) break;
+  }
+  std::memcpy(Rt_final, c->Rt_tillnow, sizeof(double) * 16);  // :104
+  if (iterations) *iterations = it;
+  return c->converge ? GHICP_OK : GHICP_E_NOCONV;
+}
+
+int ghicp_get_pairs(ghicp_ctx *ctx, int *sp, int *tp, int cap, int *n) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !n) return GHICP_E_ARG;
+  int rc;
+  if ((rc = use_device(c))) return rc;
+  const int cor = c->last_cor;
+  *n = cor;
+  const int k = std::min(cor, cap);
+  if (k > 0 && sp) CK(c, cudaMemcpy(sp, c->d_sp, sizeof(int) * (size_t)k, cudaMemcpyDeviceToHost));
+  if (k > 0 && tp) CK(c, cudaMemcpy(tp, c->d_tp, sizeof(int) * (size_t)k, cudaMemcpyDeviceToHost));
+  return GHICP_OK;
+}
+
+int ghicp_get_source(ghicp_ctx *ctx, double *sxyz) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !sxyz || c->N <= 0) return GHICP_E_ARG;
+  int rc;
+  if ((rc = use_device(c))) return rc;
+  CK(c, cudaMemcpy(sxyz, c->d_s, 3 * (size_t)c->N * sizeof(double), cudaMemcpyDeviceToHost));
+  return GHICP_OK;
+}
+
+int ghicp_get_rt(ghicp_ctx *ctx, double Rt[16]) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !Rt) return GHICP_E_ARG;
+  std::memcpy(Rt, c->Rt_tillnow, sizeof(double) * 16);
+  return GHICP_OK;
+}
+
+int ghicp_get_fd(ghicp_ctx *ctx, double *fd) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !fd || c->N <= 0) return GHICP_E_ARG;
+  int rc;
+  if ((rc = use_device(c))) return rc;
+  if ((rc = build_fd(c))) return rc;
+  double *d_out = nullptr;
+  if ((rc = dev_alloc(c, &d_out, (size_t)c->N * c->M))) return rc;
+  cudaError_t e = launch_get_fd(c, d_out);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e == cudaSuccess) e = cudaMemcpy(fd, d_out, (size_t)c->N * c->M * sizeof(double), cudaMemcpyDeviceToHost);
+  dev_free(&d_out);
+  if (e != cudaSuccess) { set_error(c, std::string("get_fd: ") + cudaGetErrorString(e)); return GHICP_E_CUDA; }
+  return GHICP_OK;
+}
+
+int ghicp_probe_rowmin(ghicp_ctx *ctx, int *idx, double *cd, double *cd_mean, double *cd_std, double *penalty) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || c->N <= 0) return GHICP_E_ARG;
+  int rc;
+  if ((rc = use_device(c))) return rc;
+  if ((rc = build_fd(c))) return rc;
+  const CostParams cp = make_cost_params(c);
+  const LoopScalars ls = make_loop_scalars(c, cp);
+  CK(c, launch_rowsweep(c, 0, cp));
+  CK(c, launch_finalize_stats(c, cp, ls));
+  CK(c, cudaMemcpyAsync(c->h_iter, c->d_iter, sizeof(DevIter), cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  if (idx) CK(c, cudaMemcpy(idx, c->d_row_idx, sizeof(int) * (size_t)c->N, cudaMemcpyDeviceToHost));
+  if (cd) CK(c, cudaMemcpy(cd, c->d_row_cd, sizeof(double) * (size_t)c->N, cudaMemcpyDeviceToHost));
+  if (cd_mean) *cd_mean = c->h_iter->cd_mean;
+  if (cd_std) *cd_std = c->h_iter->cd_std;
+  if (penalty) *penalty = c->h_iter->penalty;
+  return GHICP_OK;
+}
+
+int ghicp_set_state(ghicp_ctx *ctx, int iteration, double rms, double fdm, double fdstd, double para1, double para2) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c) return GHICP_E_ARG;
+  c->iteration = iteration;
+  c->RMS = rms; c->FDM = fdm; c->FDstd = fdstd; c->para1 = para1; c->para2 = para2;
+  return GHICP_OK;
+}
+
+// ---- stand-alone stages ------------------------------------------------------------------------
+int ghicp_km_solve(int device, const double *W, int n, int sp, int tp, double eps, double penalty, int *match,
+                   double *energy, int *rounds) {
+  if (!W || !match || n <= 0 || sp <= 0 || tp <= 0 || sp > n || tp > n || !(eps > 0.0)) {
+    set_error(nullptr, "km_solve: bad argument");
+    return GHICP_E_ARG;
+  }
+  ghicp_config cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.feature_type = GHICP_FT_NONE;
+  cfg.corr_type = GHICP_CT_KM;
+  cfg.dof = 6;
+  cfg.device = device;
+  ghicp_ctx *ctx = nullptr;
+  int rc = ghicp_create(&cfg, &ctx);
+  if (rc) return rc;
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  c->N = sp; c->M = tp; c->ldM = ((size_t)tp + 63) / 64 * 64;
+  rc = alloc_workspaces(c);
+  if (rc) { ghicp_destroy(ctx); return rc; }
+  // candidate edges: weight != -penalty  (src/km.cpp:162), gain = penalty + w = penalty - CD
+  std::vector<long long> rowptr((size_t)sp * c->n_chunks + 1, 0);
+  std::vector<int> col;
+  std::vector<double> gain;
+  double max_gain = eps;
+  for (int i = 0; i < sp; ++i) {
+    for (int j = 0; j < tp; ++j) {
+      const double w = W[(size_t)i * n + j];
+      if (w != -penalty) {
+        const double g = penalty + w;
+        if (g > 0.0) { col.push_back(j); gain.push_back(g); max_gain = std::max(max_gain, g); }
+      }
+    }
+    for (int k = 0; k < c->n_chunks; ++k) rowptr[(size_t)i * c->n_chunks + k + 1] = (long long)col.size();
+  }
+  // (all of row i's edges live in chunk 0: rowptr[i*n_chunks] = start, the other chunk slots = end)
+  const long long nnz = (long long)col.size();
+  if ((rc = ensure_edges(c, nnz))) { ghicp_destroy(ctx); return rc; }
+  cudaMemcpy(c->d_rowptr, rowptr.data(), sizeof(long long) * rowptr.size(), cudaMemcpyHostToDevice);
+  if (nnz > 0) {
+    cudaMemcpy(c->d_csr_col, col.data(), sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice);
+    cudaMemcpy(c->d_csr_gain, gain.data(), sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice);
+  }
+  cudaError_t e = launch_build_csc(c, sp, tp, nnz);
+  if (e != cudaSuccess) { set_error(nullptr, cudaGetErrorString(e)); ghicp_destroy(ctx); return GHICP_E_CUDA; }
+  KmResult kres;
+  rc = km_auction(c, sp, tp, nnz, eps, max_gain, &kres);
+  if (rc) { set_error(nullptr, c->err); ghicp_destroy(ctx); return rc; }
+  std::vector<int> owner(tp);
+  cudaMemcpy(owner.data(), c->d_owner, sizeof(int) * (size_t)tp, cudaMemcpyDeviceToHost);
+  double en = 0.0;
+  int kept = 0;
+  for (int y = 0; y < n; ++y) match[y] = -1;
+  for (int y = 0; y < tp; ++y) {
+    if (owner[y] >= 0) { match[y] = owner[y]; en -= W[(size_t)owner[y] * n + y]; ++kept; }
+  }
+  en += (double)(n - kept) * penalty;
+  if (energy) *energy = en;
+  if (rounds) *rounds = kres.rounds;
+  ghicp_destroy(ctx);
+  return GHICP_OK;
+}
+
+int ghicp_rigid_fit(int device, const double *s, const double *t, int n, double Rt[16]) {
+  if (!s || !t || !Rt || n <= 0) { set_error(nullptr, "rigid_fit: bad argument"); return GHICP_E_ARG; }
+  if (ghicp_device_count() <= 0) { set_error(nullptr, "rigid_fit: no CUDA device"); return GHICP_E_NODEV; }
+  if (cudaSetDevice(device) != cudaSuccess) return GHICP_E_CUDA;
+  double *d_s = nullptr, *d_t = nullptr;
+  DevIter *d_iter = nullptr;
+  DevIter h;
+  cudaError_t e = cudaMalloc((void **)&d_s, 3 * (size_t)n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&d_t, 3 * (size_t)n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&d_iter, sizeof(DevIter));
+  if (e == cudaSuccess) e = cudaMemcpy(d_s, s, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_t, t, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(d_iter, 0, sizeof(DevIter));
+  if (e == cudaSuccess) e = launch_solve_explicit(0, d_s, d_t, n, d_iter);
+  if (e == cudaSuccess) e = cudaMemcpy(&h, d_iter, sizeof(DevIter), cudaMemcpyDeviceToHost);
+  if (d_s) cudaFree(d_s);
+  if (d_t) cudaFree(d_t);
+  if (d_iter) cudaFree(d_iter);
+  if (e != cudaSuccess) { set_error(nullptr, std::string("rigid_fit: ") + cudaGetErrorString(e)); return GHICP_E_CUDA; }
+  std::memcpy(Rt, h.Rt, sizeof(double) * 16);
+  return GHICP_OK;
+}
+
+int ghicp_comm_unique_id(void *) {
+  set_error(nullptr, "multi-GPU exchange not built in this revision");
+  return GHICP_E_NCCL;
+}
+int ghicp_comm_init(ghicp_ctx *, const void *, int, int) {
+  set_error(nullptr, "multi-GPU exchange not built in this revision");
+  return GHICP_E_NCCL;
+}
+
+}  // extern "C"

@@ -1,0 +1,153 @@
+// ghicp_internal.h — internal declarations shared by the translation units of libghicp_b200.so.
+// Not part of the ABI (the ABI is include/ghicp_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/ghicp_b200.h"
+
+namespace ghicp_b200 {
+
+// ---- small device-side structs -----------------------------------------------------------------
+// Parameters of one cost evaluation CD(i,j) (src/ghicp_reg.cpp:122, 224, 259, 308).
+struct CostParams {
+  double scale;    // (double)Energyfunction::scale
+  double WED, WFD; // BSC weights (src/ghicp_reg.cpp:247-249)
+  double ex;       // FPFH exponent 1/(it+1) (src/ghicp_reg.cpp:308)
+  double pivot;    // shift used for the one-pass variance accumulation
+};
+
+// Host-owned loop scalars passed to the device penalty rule (src/ghicp_reg.cpp:230-239, 279-287, 327-335).
+struct LoopScalars {
+  int iteration;
+  double RMS, FDM, FDstd, para1, para2;
+  double scale, WED, WFD, penalty_initial;
+};
+
+// Scalars produced on the device by one iteration and read back once at its end.
+struct DevIter {
+  double cd_sum_shift, cd_sumsq_shift;  // sums of (cd - pivot), (cd - pivot)^2
+  double cd_mean, cd_std, penalty;
+  int cor;
+  int pad0;
+  double rmse, fdm, fdstd, rmse_after;
+  double km_cd_sum;     // sum of CD over kept pairs
+  double Rt[16];        // column-major
+  long long nnz;
+  int solve_degenerate; // cor < 3: identity returned
+  int pad1;
+};
+
+// ---- the context ----------------------------------------------------------------------------------
+struct Ctx {
+  ghicp_config cfg{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  std::string err;
+
+  int N = 0, M = 0;
+  size_t ldM = 0;  // FD pitch in elements
+  // coordinates, SoA doubles
+  double *d_s = nullptr;  // [3][N]
+  double *d_t = nullptr;  // [3][M]
+  // BSC
+  int V = 0, bits = 0, Bbytes = 0, W64 = 0;
+  uint64_t *d_bs = nullptr;  // [V][W64][N]
+  uint64_t *d_bt = nullptr;  // [W64][M]
+  uint16_t *d_fd16 = nullptr;  // [N][ldM]
+  // FPFH
+  float *d_fs = nullptr, *d_ft = nullptr;  // raw [N][33], [M][33]
+  float *d_fdf = nullptr;                  // [N][ldM] float FD
+  bool have_bsc = false, have_fpfh = false, fd_built = false;
+
+  // per-iteration workspaces
+  int rows_per_cta = 8, n_chunks = 1;
+  double *d_part_cd = nullptr;   // [N][n_chunks]
+  int *d_part_idx = nullptr;     // [N][n_chunks]
+  double *d_part_stats = nullptr;  // [grid][2]
+  size_t part_stats_cap = 0;
+  double *d_row_cd = nullptr;  // [N]
+  int *d_row_idx = nullptr;    // [N]
+  double *d_col_cd = nullptr;  // [M]
+  int *d_col_idx = nullptr;    // [M]
+  int *d_flags = nullptr;      // [max(N,M)]
+  int *d_sp = nullptr, *d_tp = nullptr;  // [max(N,M)]
+  DevIter *d_iter = nullptr;
+  DevIter *h_iter = nullptr;  // pinned
+  double *h_stage = nullptr;  // pinned staging for coordinates
+  size_t h_stage_cap = 0;
+
+  // KM
+  int *d_cnt = nullptr;          // [N*n_chunks + 1]
+  long long *d_rowptr = nullptr; // [N*n_chunks + 1]
+  int *d_cursor = nullptr;       // [N*n_chunks]
+  int *d_csr_col = nullptr; double *d_csr_gain = nullptr; size_t csr_cap = 0;
+  long long *d_colptr = nullptr; // [M+1]
+  int *d_colcnt = nullptr;       // [M+1]
+  int *d_csc_row = nullptr; double *d_csc_gain = nullptr; size_t csc_cap = 0;
+  // auction state
+  double *d_price = nullptr;   // [M]
+  double *d_profit = nullptr;  // [N]
+  int *d_assign = nullptr;     // [N] person -> object (-1 unassigned, -2 dummy)
+  int *d_owner = nullptr;      // [M] object -> person (-1 none)
+  unsigned long long *d_bidmax = nullptr;  // [max(N,M)]
+  int *d_bidwin = nullptr;     // [max(N,M)]
+  int *d_bid_obj = nullptr; double *d_bid_val = nullptr;  // [max(N,M)]
+  double *d_bid_aux = nullptr; // [max(N,M)]
+  int *d_list[2] = {nullptr, nullptr};  // active lists [max(N,M)]
+  int *d_counters = nullptr;   // [8]
+  int *h_counters = nullptr;   // pinned [8]
+
+  // host loop state (include/ghicp_reg.h:173-202)
+  int iteration = 0;
+  double RMS = 99999, FDM = 0, FDstd = 0, IoU = 0;
+  double para1 = 1.0, para2 = 1.0, penalty_initial = 2.0;
+  int min_cor = 10, weight_changing_rate = 6;
+  double KM_eps = 0.01;
+  float scale_f = 0.f;
+  bool converge = false;
+  double Rt_tillnow[16];
+  double last_mean = 0.0;
+  int launches = 0;
+  int last_cor = 0;
+
+  // multi-GPU
+  void *nccl_comm = nullptr;
+  int rank = 0, world = 1;
+};
+
+struct KmResult {
+  int rounds = 0, phases = 0;
+};
+
+// ---- launchers (ghicp_kernels.cu) ---------------------------------------------------------------
+cudaError_t launch_pack_bsc(Ctx *c, const uint8_t *d_raw_s, const uint8_t *d_raw_t);
+cudaError_t launch_fd_bsc(Ctx *c);
+cudaError_t launch_fd_fpfh(Ctx *c);
+// mode: 0 rowmin+stats, 1 count (needs penalty in d_iter), 2 fill
+cudaError_t launch_rowsweep(Ctx *c, int mode, const CostParams &cp);
+cudaError_t launch_colsweep(Ctx *c, const CostParams &cp);
+cudaError_t launch_finalize_stats(Ctx *c, const CostParams &cp, const LoopScalars &ls);
+cudaError_t launch_select_nn(Ctx *c);    // flags from row minima + penalty, compaction → d_sp/d_tp, cor
+cudaError_t launch_select_nnr(Ctx *c);
+cudaError_t launch_select_km(Ctx *c);    // from d_owner
+cudaError_t launch_solve(Ctx *c, const CostParams &cp);  // stats + umeyama + rmse_after → d_iter
+cudaError_t launch_apply(Ctx *c);
+cudaError_t launch_solve_explicit(cudaStream_t stream, const double *d_s, const double *d_t, int n, DevIter *d_iter);
+cudaError_t launch_get_fd(Ctx *c, double *d_out);
+cudaError_t launch_scan_counts(Ctx *c);  // d_cnt → d_rowptr, nnz → d_iter->nnz
+
+// ---- KM (ghicp_auction.cu) ----------------------------------------------------------------------
+// Solves max-gain partial matching on the CSR in the ctx (rows = persons). Result in d_owner/d_assign.
+int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, double max_gain,
+               KmResult *res);
+cudaError_t launch_build_csc(Ctx *c, int n_rows, int n_cols, long long nnz);
+
+// misc
+int ensure_capacity(Ctx *c, void **ptr, size_t *cap, size_t need_bytes);
+void set_error(Ctx *c, const std::string &msg);
+
+}  // namespace ghicp_b200

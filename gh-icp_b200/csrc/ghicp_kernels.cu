@@ -1,0 +1,970 @@
+// ghicp_kernels.cu — cost build, correspondence scans, pair statistics, rigid solve and update kernels
+// of the GH-ICP inner loop for sm_100a.  Compiled with --fmad=false: every arithmetic operation on
+// the exact path is a separately rounded IEEE operation, in the reference's evaluation order, so
+// CD(i,j) is bit-identical to the reference's double arithmetic (src/ghicp_reg.cpp:122,259,308).
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+
+#include "ghicp_internal.h"
+
+namespace ghicp_b200 {
+
+namespace {
+
+constexpr int TR = 8;              // source rows per CTA in the row sweep
+constexpr int SWEEP_THREADS = 256;
+constexpr int COLS_PER_THREAD = 4;
+constexpr double MAXVALIUE = 9e20;  // initial mincd of the reference scans (src/ghicp_reg.cpp:618,711)
+
+// ---------------------------------------------------------------------------------------------
+// reductions
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// lexicographic (value, index) minimum: the reference keeps the FIRST minimum of an ascending scan
+__device__ __forceinline__ void lexmin(double &v, int &i, double ov, int oi) {
+  if (ov < v || (ov == v && oi < i)) { v = ov; i = oi; }
+}
+__device__ __forceinline__ void warp_lexmin(double &v, int &i) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double ov = __shfl_xor_sync(0xffffffffu, v, o);
+    int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    lexmin(v, i, ov, oi);
+  }
+}
+// block-wide sum of K doubles with a fixed reduction tree (deterministic). Result valid in thread 0.
+template <int K, int THREADS>
+__device__ __forceinline__ void block_sum(double (&v)[K], double *smem /* [K][THREADS/32] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = THREADS / 32;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    double w = warp_sum(v[k]);
+    if (lane == 0) smem[k * NW + warp] = w;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      double w = (lane < NW) ? smem[k * NW + lane] : 0.0;
+      w = warp_sum(w);
+      v[k] = w;
+    }
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact cost evaluation
+// ---------------------------------------------------------------------------------------------
+// EF.scale * sqrt(pow(dx,2) + pow(dy,2) + pow(dz,2))   (src/ghicp_reg.cpp:122)
+__device__ __forceinline__ double ed_exact(double sx, double sy, double sz, double tx, double ty, double tz,
+                                           double scale) {
+  double dx = sx - tx, dy = sy - ty, dz = sz - tz;
+  double d2 = (dx * dx + dy * dy) + dz * dz;
+  return scale * sqrt(d2);
+}
+// FT: 0 = BSC, 2 = FPFH, 3 = None (enum order of include/utility.h:51-57)
+template <int FT>
+__device__ __forceinline__ double cd_exact(double ed, double fd, const CostParams &cp) {
+  if (FT == GHICP_FT_BSC) return cp.WED * ed + cp.WFD * fd;             // src/ghicp_reg.cpp:259
+  if (FT == GHICP_FT_FPFH) return 1.0 * ed / pow(fd, cp.ex);            // src/ghicp_reg.cpp:308
+  return ed;                                                            // src/ghicp_reg.cpp:224
+}
+
+// ---------------------------------------------------------------------------------------------
+// BSC packing:  raw [V][N][B] bytes → words [V][W64][N]  (word-major planes, coalesced per word)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_pack_bsc(const uint8_t *__restrict__ raw, uint64_t *__restrict__ words, int V, int n, int B,
+                           int W64) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)V * W64 * n;
+  if (idx >= total) return;
+  int i = (int)(idx % n);
+  int w = (int)((idx / n) % W64);
+  int v = (int)(idx / ((long long)n * W64));
+  const uint8_t *p = raw + ((size_t)v * n + i) * B;
+  uint64_t word = 0;
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    int byte = w * 8 + b;
+    if (byte < B) word |= (uint64_t)p[byte] << (8 * b);
+  }
+  words[idx] = word;
+}
+
+// ---------------------------------------------------------------------------------------------
+// calFD_BSC (src/ghicp_reg.cpp:143-200): FD[i][j] = min_v popcount(bscS[v][i] ^ bscT[0][j]) → u16.
+// CTA = 128 threads = 128 target columns x 32 source rows; source words staged in shared memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int FDB_ROWS = 32;
+constexpr int FDB_THREADS = 128;
+template <int V>
+__global__ void __launch_bounds__(FDB_THREADS) k_fd_bsc(const uint64_t *__restrict__ bs,
+                                                         const uint64_t *__restrict__ bt,
+                                                         uint16_t *__restrict__ fd, int N, int M, size_t ldM,
+                                                         int W64) {
+  extern __shared__ uint64_t s_words[];  // [V][W64][FDB_ROWS]
+  const int i0 = blockIdx.y * FDB_ROWS;
+  const int j = blockIdx.x * FDB_THREADS + threadIdx.x;
+  for (int k = threadIdx.x; k < V * W64 * FDB_ROWS; k += FDB_THREADS) {
+    int r = k % FDB_ROWS;
+    int vw = k / FDB_ROWS;  // v*W64 + w
+    int i = i0 + r;
+    s_words[k] = (i < N) ? bs[(size_t)vw * N + i] : 0ull;
+  }
+  __syncthreads();
+  if (j >= M) return;
+  for (int rc = 0; rc < FDB_ROWS; rc += 8) {
+    int acc[8][V];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int v = 0; v < V; ++v) acc[r][v] = 0;
+    for (int w = 0; w < W64; ++w) {
+      const uint64_t tw = bt[(size_t)w * M + j];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const uint64_t *sw = &s_words[(v * W64 + w) * FDB_ROWS + rc];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) acc[r][v] += __popcll(sw[r] ^ tw);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      int i = i0 + rc + r;
+      if (i < N) {
+        int m = acc[r][0];
+#pragma unroll
+        for (int v = 1; v < V; ++v) m = min(m, acc[r][v]);
+        fd[(size_t)i * ldM + j] = (uint16_t)m;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// calFD_FPFH (src/ghicp_reg.cpp:202-214, include/fpfh.hpp:135-165), float32, reference op order.
+// Stage 1 (per point): mean (serial float sum / 33), centred histogram, serial sum of squares.
+// Stage 2 (per pair): serial float dot of centred histograms, / sqrt(d1*d2), fabs.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_fpfh_center(const float *__restrict__ h, float *__restrict__ hc /*[n][36]*/, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float *p = h + (size_t)i * 33;
+  float mean = 0.f;
+  for (int k = 0; k < 33; ++k) mean += p[k];
+  mean /= 33;
+  float d = 0.f;
+  float *q = hc + (size_t)i * 36;
+  for (int k = 0; k < 33; ++k) {
+    float c = p[k] - mean;
+    q[k] = c;
+    d += c * c;
+  }
+  q[33] = d;
+  q[34] = 0.f;
+  q[35] = 0.f;
+}
+
+constexpr int FPT = 16;  // tile edge
+__global__ void __launch_bounds__(FPT *FPT) k_fd_fpfh(const float *__restrict__ sc, const float *__restrict__ tc,
+                                                       float *__restrict__ fd, int N, int M, size_t ldM) {
+  __shared__ float s_s[FPT][37];
+  __shared__ float s_t[FPT][37];
+  const int tx = threadIdx.x % FPT, ty = threadIdx.x / FPT;
+  const int i0 = blockIdx.y * FPT, j0 = blockIdx.x * FPT;
+  for (int k = threadIdx.x; k < FPT * 36; k += FPT * FPT) {
+    int r = k / 36, q = k % 36;
+    s_s[r][q] = (i0 + r < N) ? sc[(size_t)(i0 + r) * 36 + q] : 0.f;
+    s_t[r][q] = (j0 + r < M) ? tc[(size_t)(j0 + r) * 36 + q] : 0.f;
+  }
+  __syncthreads();
+  const int i = i0 + ty, j = j0 + tx;
+  if (i >= N || j >= M) return;
+  float up = 0.f;
+#pragma unroll
+  for (int k = 0; k < 33; ++k) up += s_s[ty][k] * s_t[tx][k];
+  float d = up / sqrtf(s_s[ty][33] * s_t[tx][33]);
+  fd[(size_t)i * ldM + j] = fabsf(d);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row sweep: one CTA owns TR source rows and a chunk of target columns.
+//   MODE 0: per-row first-argmin of CD + sum(cd - pivot), sum((cd - pivot)^2)
+//           (calED + calCD_* + the NN scan, src/ghicp_reg.cpp:114-139, 216-341, 715-733)
+//   MODE 1: per-row count of CD < penalty                       (KM graph build, :358-365)
+//   MODE 2: emit (j, penalty - CD) for CD < penalty into the CSR
+// ---------------------------------------------------------------------------------------------
+struct SweepArgs {
+  const double *s;  // [3][N]
+  const double *t;  // [3][M]
+  const uint16_t *fd16;
+  const float *fdf;
+  size_t ldM;
+  int N, M, n_chunks, cols_per_chunk;
+  CostParams cp;
+  // mode 0
+  double *part_cd; int *part_idx; double *part_stats;
+  // mode 1/2
+  const DevIter *iter;  // penalty
+  int *cnt;
+  const long long *rowptr;
+  int *cursor;
+  int *csr_col; double *csr_gain;
+};
+
+template <int FT, int MODE>
+__global__ void __launch_bounds__(SWEEP_THREADS) k_rowsweep(const SweepArgs a) {
+  __shared__ double s_src[3][TR];
+  __shared__ double s_red[2 * (SWEEP_THREADS / 32)];
+  __shared__ double s_bv[TR][SWEEP_THREADS / 32];
+  __shared__ int s_bi[TR][SWEEP_THREADS / 32];
+  const int tid = threadIdx.x;
+  const int i0 = blockIdx.x * TR;
+  const int chunk = blockIdx.y;
+  const int nrows = min(TR, a.N - i0);
+  const int c0 = chunk * a.cols_per_chunk;
+  const int c1 = min(a.M, c0 + a.cols_per_chunk);
+  if (tid < 3 * TR) {
+    int k = tid / TR, r = tid % TR;
+    s_src[k][r] = (r < nrows) ? a.s[(size_t)k * a.N + i0 + r] : 0.0;
+  }
+  __syncthreads();
+
+  double best[TR];
+  int bidx[TR];
+  int cnt[TR];
+#pragma unroll
+  for (int r = 0; r < TR; ++r) { best[r] = MAXVALIUE; bidx[r] = 0; cnt[r] = 0; }
+  double sum = 0.0, sumsq = 0.0;
+  double penalty = 0.0;
+  if (MODE != 0) penalty = a.iter->penalty;
+
+  const double *tx = a.t, *ty = a.t + a.M, *tz = a.t + 2 * (size_t)a.M;
+  for (int j = c0 + tid * COLS_PER_THREAD; j < c1; j += SWEEP_THREADS * COLS_PER_THREAD) {
+    double cx[COLS_PER_THREAD], cy[COLS_PER_THREAD], cz[COLS_PER_THREAD];
+#pragma unroll
+    for (int c = 0; c < COLS_PER_THREAD; ++c) {
+      int jj = min(j + c, a.M - 1);
+      cx[c] = tx[jj]; cy[c] = ty[jj]; cz[c] = tz[jj];
+    }
+#pragma unroll
+    for (int r = 0; r < TR; ++r) {
+      if (r < nrows) {
+        const double sx = s_src[0][r], sy = s_src[1][r], sz = s_src[2][r];
+        double fdv[COLS_PER_THREAD];
+        if (FT == GHICP_FT_BSC) {
+          const uint2 q = *reinterpret_cast<const uint2 *>(a.fd16 + (size_t)(i0 + r) * a.ldM + j);
+          fdv[0] = (double)(q.x & 0xffffu); fdv[1] = (double)(q.x >> 16);
+          fdv[2] = (double)(q.y & 0xffffu); fdv[3] = (double)(q.y >> 16);
+        } else if (FT == GHICP_FT_FPFH) {
+          const float4 q = *reinterpret_cast<const float4 *>(a.fdf + (size_t)(i0 + r) * a.ldM + j);
+          fdv[0] = (double)q.x; fdv[1] = (double)q.y; fdv[2] = (double)q.z; fdv[3] = (double)q.w;
+        } else {
+          fdv[0] = fdv[1] = fdv[2] = fdv[3] = 0.0;
+        }
+#pragma unroll
+        for (int c = 0; c < COLS_PER_THREAD; ++c) {
+          if (j + c < c1) {
+            const double ed = ed_exact(sx, sy, sz, cx[c], cy[c], cz[c], a.cp.scale);
+            const double cd = cd_exact<FT>(ed, fdv[c], a.cp);
+            if (MODE == 0) {
+              if (cd < best[r]) { best[r] = cd; bidx[r] = j + c; }
+              const double d = cd - a.cp.pivot;
+              sum += d;
+              sumsq += d * d;
+            } else if (MODE == 1) {
+              cnt[r] += (cd < penalty) ? 1 : 0;
+            } else {
+              if (cd < penalty) {
+                const size_t slot = (size_t)(i0 + r) * a.n_chunks + chunk;
+                const long long pos = a.rowptr[slot] + atomicAdd(&a.cursor[slot], 1);
+                a.csr_col[pos] = j + c;
+                a.csr_gain[pos] = penalty - cd;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  const int lane = tid & 31, warp = tid >> 5;
+  if (MODE == 0) {
+#pragma unroll
+    for (int r = 0; r < TR; ++r) {
+      warp_lexmin(best[r], bidx[r]);
+      if (lane == 0) { s_bv[r][warp] = best[r]; s_bi[r][warp] = bidx[r]; }
+    }
+    double ws = warp_sum(sum), wq = warp_sum(sumsq);
+    if (lane == 0) { s_red[warp] = ws; s_red[SWEEP_THREADS / 32 + warp] = wq; }
+    __syncthreads();
+    if (tid < nrows) {
+      double v = s_bv[tid][0];
+      int ix = s_bi[tid][0];
+      for (int w = 1; w < SWEEP_THREADS / 32; ++w) lexmin(v, ix, s_bv[tid][w], s_bi[tid][w]);
+      a.part_cd[(size_t)(i0 + tid) * a.n_chunks + chunk] = v;
+      a.part_idx[(size_t)(i0 + tid) * a.n_chunks + chunk] = ix;
+    }
+    if (tid == 0) {
+      double S1 = 0.0, S2 = 0.0;
+      for (int w = 0; w < SWEEP_THREADS / 32; ++w) { S1 += s_red[w]; S2 += s_red[SWEEP_THREADS / 32 + w]; }
+      const size_t b = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+      a.part_stats[2 * b] = S1;
+      a.part_stats[2 * b + 1] = S2;
+    }
+  } else if (MODE == 1) {
+#pragma unroll
+    for (int r = 0; r < TR; ++r) {
+      int w = warp_sum_i(cnt[r]);
+      if (lane == 0) s_bi[r][warp] = w;
+    }
+    __syncthreads();
+    if (tid < nrows) {
+      int tot = 0;
+      for (int w = 0; w < SWEEP_THREADS / 32; ++w) tot += s_bi[tid][w];
+      a.cnt[(size_t)(i0 + tid) * a.n_chunks + chunk] = tot;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Column sweep (NNR, src/ghicp_reg.cpp:637-650): per target column first-argmin over source rows.
+// CTA = CT columns x a chunk of rows; thread per row, CT running minima in registers.
+// ---------------------------------------------------------------------------------------------
+constexpr int CT = 8;
+constexpr int COL_THREADS = 256;
+struct ColArgs {
+  const double *s, *t;
+  const uint16_t *fd16;
+  const float *fdf;
+  size_t ldM;
+  int N, M;
+  CostParams cp;
+  double *col_cd; int *col_idx;
+};
+template <int FT>
+__global__ void __launch_bounds__(COL_THREADS) k_colsweep(const ColArgs a) {
+  __shared__ double s_t[3][CT];
+  __shared__ double s_bv[CT][COL_THREADS / 32];
+  __shared__ int s_bi[CT][COL_THREADS / 32];
+  const int tid = threadIdx.x;
+  const int j0 = blockIdx.x * CT;
+  const int ncols = min(CT, a.M - j0);
+  if (tid < 3 * CT) {
+    int k = tid / CT, c = tid % CT;
+    s_t[k][c] = (c < ncols) ? a.t[(size_t)k * a.M + j0 + c] : 0.0;
+  }
+  __syncthreads();
+  double best[CT];
+  int bidx[CT];
+#pragma unroll
+  for (int c = 0; c < CT; ++c) { best[c] = MAXVALIUE; bidx[c] = 0; }
+  const double *sxp = a.s, *syp = a.s + a.N, *szp = a.s + 2 * (size_t)a.N;
+  for (int i = tid; i < a.N; i += COL_THREADS) {
+    const double sx = sxp[i], sy = syp[i], sz = szp[i];
+    double fdv[CT];
+    if (FT == GHICP_FT_BSC) {
+      const uint4 q = *reinterpret_cast<const uint4 *>(a.fd16 + (size_t)i * a.ldM + j0);
+      fdv[0] = (double)(q.x & 0xffffu); fdv[1] = (double)(q.x >> 16);
+      fdv[2] = (double)(q.y & 0xffffu); fdv[3] = (double)(q.y >> 16);
+      fdv[4] = (double)(q.z & 0xffffu); fdv[5] = (double)(q.z >> 16);
+      fdv[6] = (double)(q.w & 0xffffu); fdv[7] = (double)(q.w >> 16);
+    } else if (FT == GHICP_FT_FPFH) {
+      const float4 q0 = *reinterpret_cast<const float4 *>(a.fdf + (size_t)i * a.ldM + j0);
+      const float4 q1 = *reinterpret_cast<const float4 *>(a.fdf + (size_t)i * a.ldM + j0 + 4);
+      fdv[0] = q0.x; fdv[1] = q0.y; fdv[2] = q0.z; fdv[3] = q0.w;
+      fdv[4] = q1.x; fdv[5] = q1.y; fdv[6] = q1.z; fdv[7] = q1.w;
+    } else {
+#pragma unroll
+      for (int c = 0; c < CT; ++c) fdv[c] = 0.0;
+    }
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+      if (c < ncols) {
+        const double ed = ed_exact(sx, sy, sz, s_t[0][c], s_t[1][c], s_t[2][c], a.cp.scale);
+        const double cd = cd_exact<FT>(ed, fdv[c], a.cp);
+        if (cd < best[c]) { best[c] = cd; bidx[c] = i; }
+      }
+    }
+  }
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int c = 0; c < CT; ++c) {
+    warp_lexmin(best[c], bidx[c]);
+    if (lane == 0) { s_bv[c][warp] = best[c]; s_bi[c][warp] = bidx[c]; }
+  }
+  __syncthreads();
+  if (tid < ncols) {
+    double v = s_bv[tid][0];
+    int ix = s_bi[tid][0];
+    for (int w = 1; w < COL_THREADS / 32; ++w) lexmin(v, ix, s_bv[tid][w], s_bi[tid][w]);
+    a.col_cd[j0 + tid] = v;
+    a.col_idx[j0 + tid] = ix;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Finalise: merge per-chunk row minima, reduce statistics in a fixed order, apply the penalty rule
+// (src/ghicp_reg.cpp:228-239, 264-287, 317-335).  One CTA.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_finalize(const double *__restrict__ part_cd,
+                                                   const int *__restrict__ part_idx, int n_chunks, int N, int M,
+                                                   const double *__restrict__ part_stats, int n_parts,
+                                                   double *__restrict__ row_cd, int *__restrict__ row_idx,
+                                                   int feature_type, double pivot, LoopScalars ls,
+                                                   DevIter *iter) {
+  __shared__ double smem[2 * 32];
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    double v = part_cd[(size_t)i * n_chunks];
+    int ix = part_idx[(size_t)i * n_chunks];
+    for (int c = 1; c < n_chunks; ++c) lexmin(v, ix, part_cd[(size_t)i * n_chunks + c], part_idx[(size_t)i * n_chunks + c]);
+    row_cd[i] = v;
+    row_idx[i] = ix;
+  }
+  double acc[2] = {0.0, 0.0};
+  for (int p = threadIdx.x; p < n_parts; p += blockDim.x) {
+    acc[0] += part_stats[2 * p];
+    acc[1] += part_stats[2 * p + 1];
+  }
+  block_sum<2, 1024>(acc, smem);
+  if (threadIdx.x == 0) {
+    const double S1 = acc[0], S2 = acc[1];
+    const double n = (double)N * (double)M;
+    const double CDmean = pivot + S1 / M / N;
+    double var = (S2 - S1 * S1 / n) / n;
+    if (var < 0.0) var = 0.0;
+    const double CDstd = sqrt(var);
+    double penalty;
+    if (feature_type == GHICP_FT_BSC) {
+      if (ls.iteration > 1)
+        penalty = ls.RMS * ls.para1 * ls.scale * ls.WED + (ls.FDM + ls.para2 * ls.FDstd) * ls.WFD;
+      else
+        penalty = (CDmean - ls.penalty_initial * CDstd);
+      penalty = fmax(penalty, 5.0);
+    } else if (feature_type == GHICP_FT_FPFH) {
+      if (ls.iteration > 1)
+        penalty = ls.RMS * ls.para1 * ls.scale * ls.para2;
+      else
+        penalty = (CDmean / ls.penalty_initial);
+    } else {
+      penalty = fmax(CDmean, 1.0);
+    }
+    iter->cd_sum_shift = S1;
+    iter->cd_sumsq_shift = S2;
+    iter->cd_mean = CDmean;
+    iter->cd_std = (feature_type == GHICP_FT_BSC) ? CDstd : 0.0;
+    iter->penalty = penalty;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Single-CTA ordered compaction / exclusive scan helpers.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long block_exclusive_scan_1024(long long v, long long *smem /*[33]*/,
+                                                               long long *total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    long long y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) smem[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    long long w = smem[lane];
+    long long xs = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      long long y = __shfl_up_sync(0xffffffffu, xs, o);
+      if (lane >= o) xs += y;
+    }
+    smem[lane] = xs - w;  // exclusive warp offsets
+    if (lane == 31) smem[32] = xs;
+  }
+  __syncthreads();
+  long long excl = smem[warp] + x - v;
+  *total = smem[32];
+  __syncthreads();
+  return excl;
+}
+
+// counts[L] → rowptr[L+1] (exclusive), nnz → iter->nnz; cursor zeroed.
+__global__ void __launch_bounds__(1024) k_scan_counts(const int *__restrict__ cnt, long long *__restrict__ rowptr,
+                                                      int *__restrict__ cursor, long long L, DevIter *iter) {
+  __shared__ long long smem[33];
+  const long long seg = (L + 1023) / 1024;
+  const long long b = (long long)threadIdx.x * seg;
+  const long long e = (b + seg < L) ? b + seg : L;
+  long long s = 0;
+  for (long long k = b; k < e; ++k) s += cnt[k];
+  long long total;
+  long long off = block_exclusive_scan_1024(s, smem, &total);
+  for (long long k = b; k < e; ++k) {
+    rowptr[k] = off;
+    off += cnt[k];
+    cursor[k] = 0;
+  }
+  if (threadIdx.x == 0) {
+    rowptr[L] = total;
+    iter->nnz = total;
+  }
+}
+
+// kind 0: NN   keep row i iff row_cd[i] < penalty          (src/ghicp_reg.cpp:725-730)
+// kind 1: NNR  keep row i iff col_idx[row_idx[i]] == i     (src/ghicp_reg.cpp:652-662)
+// kind 2: KM   keep column j iff owner[j] >= 0; pairs ordered by target index (src/km.cpp:157-167)
+__global__ void __launch_bounds__(1024) k_select(int kind, int n, const double *__restrict__ row_cd,
+                                                 const int *__restrict__ row_idx, const int *__restrict__ col_idx,
+                                                 const int *__restrict__ owner, int *__restrict__ sp,
+                                                 int *__restrict__ tp, DevIter *iter) {
+  __shared__ long long smem[33];
+  const double penalty = iter->penalty;
+  const int seg = (n + 1023) / 1024;
+  const int b = threadIdx.x * seg;
+  const int e = min(b + seg, n);
+  auto keep = [&](int k) -> bool {
+    if (kind == 0) return row_cd[k] < penalty;
+    if (kind == 1) return col_idx[row_idx[k]] == k;
+    return owner[k] >= 0;
+  };
+  long long s = 0;
+  for (int k = b; k < e; ++k) s += keep(k) ? 1 : 0;
+  long long total;
+  long long off = block_exclusive_scan_1024(s, smem, &total);
+  for (int k = b; k < e; ++k) {
+    if (keep(k)) {
+      if (kind == 2) { sp[off] = owner[k]; tp[off] = k; }
+      else { sp[off] = k; tp[off] = row_idx[k]; }
+      ++off;
+    }
+  }
+  if (threadIdx.x == 0) iter->cor = (int)total;
+}
+
+// ---------------------------------------------------------------------------------------------
+// float32 3x3 SVD (one-sided Jacobi) and Umeyama from moments — PCL's
+// TransformationEstimationSVD → Eigen::umeyama (no scaling) as called at src/ghicp_reg.cpp:857-866.
+// ---------------------------------------------------------------------------------------------
+__device__ void svd3_f32(const float A[9], float U[9], float S[3], float V[9]) {
+  float a[9];
+  for (int i = 0; i < 9; ++i) a[i] = A[i];
+  float v[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  const float tol = 1e-7f;
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    int rotated = 0;
+    for (int p = 0; p < 2; ++p) {
+      for (int q = p + 1; q < 3; ++q) {
+        float alpha = 0.f, beta = 0.f, gamma = 0.f;
+        for (int i = 0; i < 3; ++i) {
+          alpha = alpha + a[i * 3 + p] * a[i * 3 + p];
+          beta = beta + a[i * 3 + q] * a[i * 3 + q];
+          gamma = gamma + a[i * 3 + p] * a[i * 3 + q];
+        }
+        if (gamma == 0.f || fabsf(gamma) <= tol * sqrtf(alpha * beta)) continue;
+        rotated = 1;
+        float zeta = (beta - alpha) / (2.0f * gamma);
+        float t = 1.0f / (fabsf(zeta) + sqrtf(1.0f + zeta * zeta));
+        if (zeta < 0.f) t = -t;
+        float c = 1.0f / sqrtf(1.0f + t * t);
+        float s = c * t;
+        for (int i = 0; i < 3; ++i) {
+          float ap = a[i * 3 + p], aq = a[i * 3 + q];
+          a[i * 3 + p] = c * ap - s * aq;
+          a[i * 3 + q] = s * ap + c * aq;
+          float vp = v[i * 3 + p], vq = v[i * 3 + q];
+          v[i * 3 + p] = c * vp - s * vq;
+          v[i * 3 + q] = s * vp + c * vq;
+        }
+      }
+    }
+    if (!rotated) break;
+  }
+  float sv[3];
+  for (int k = 0; k < 3; ++k) {
+    float n2 = 0.f;
+    for (int i = 0; i < 3; ++i) n2 = n2 + a[i * 3 + k] * a[i * 3 + k];
+    sv[k] = sqrtf(n2);
+  }
+  int idx[3] = {0, 1, 2};
+  for (int i = 1; i < 3; ++i)
+    for (int j = i; j > 0 && sv[idx[j]] > sv[idx[j - 1]]; --j) { int tmp = idx[j]; idx[j] = idx[j - 1]; idx[j - 1] = tmp; }
+  float u[9];
+  for (int k = 0; k < 3; ++k) {
+    int src = idx[k];
+    S[k] = sv[src];
+    for (int i = 0; i < 3; ++i) {
+      V[i * 3 + k] = v[i * 3 + src];
+      u[i * 3 + k] = a[i * 3 + src];
+    }
+  }
+  const float tiny = 1e-20f;
+  for (int k = 0; k < 2; ++k)
+    if (S[k] > tiny)
+      for (int i = 0; i < 3; ++i) u[i * 3 + k] = u[i * 3 + k] / S[k];
+  if (!(S[0] > tiny)) { u[0] = 1; u[3] = 0; u[6] = 0; }
+  if (!(S[1] > tiny)) {
+    float x = u[0], y = u[3], z = u[6];
+    float bx, by, bz;
+    if (fabsf(x) <= fabsf(y) && fabsf(x) <= fabsf(z)) { bx = 1; by = 0; bz = 0; }
+    else if (fabsf(y) <= fabsf(z)) { bx = 0; by = 1; bz = 0; }
+    else { bx = 0; by = 0; bz = 1; }
+    float cx = y * bz - z * by, cy = z * bx - x * bz, cz = x * by - y * bx;
+    float n = sqrtf(cx * cx + cy * cy + cz * cz);
+    u[1] = cx / n; u[4] = cy / n; u[7] = cz / n;
+  }
+  if (S[2] > 1e-6f * S[0] && S[2] > tiny) {
+    for (int i = 0; i < 3; ++i) u[i * 3 + 2] = u[i * 3 + 2] / S[2];
+  } else {
+    u[2] = u[3] * u[7] - u[6] * u[4];
+    u[5] = u[6] * u[1] - u[0] * u[7];
+    u[8] = u[0] * u[4] - u[3] * u[1];
+  }
+  for (int i = 0; i < 9; ++i) U[i] = u[i];
+}
+__device__ __forceinline__ float det3_f32(const float m[9]) {
+  return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) +
+         m[2] * (m[3] * m[7] - m[4] * m[6]);
+}
+__device__ void umeyama_from_moments_f32(const float mu_s[3], const float mu_d[3], const float sigma[9],
+                                         double Rt[16]) {
+  float U[9], S[3], V[9];
+  svd3_f32(sigma, U, S, V);
+  float sgn[3] = {1.f, 1.f, 1.f};
+  if (det3_f32(U) * det3_f32(V) < 0.f) sgn[2] = -1.f;
+  float R[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      float acc = 0.f;
+      for (int k = 0; k < 3; ++k) acc = acc + (U[i * 3 + k] * sgn[k]) * V[j * 3 + k];
+      R[i * 3 + j] = acc;
+    }
+  float t[3];
+  for (int i = 0; i < 3; ++i) {
+    float acc = 0.f;
+    for (int k = 0; k < 3; ++k) acc = acc + R[i * 3 + k] * mu_s[k];
+    t[i] = mu_d[i] - acc;
+  }
+  for (int i = 0; i < 16; ++i) Rt[i] = 0.0;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) Rt[j * 4 + i] = (double)R[i * 3 + j];
+    Rt[12 + i] = (double)t[i];
+  }
+  Rt[15] = 1.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pair statistics + rigid solve, one CTA (the pair list is at most max(N,M) long):
+//  pass 1  RMSE, FDM, centroids            (src/ghicp_reg.cpp:549-558)
+//  pass 2  FDstd, cross-covariance         (src/ghicp_reg.cpp:559-565; Umeyama sigma)
+//  solve   float32 SVD, R, t               (src/ghicp_reg.cpp:857-866)
+//  pass 3  RMSE after the update           (src/ghicp_reg.cpp:895-904)
+// Moments are accumulated in float64 and rounded once to float32 (the reference/PCL accumulates in
+// float32; the difference is O(1e-7) relative and documented in DESIGN.md).
+// ---------------------------------------------------------------------------------------------
+struct SolveArgs {
+  const double *s, *t;
+  const uint16_t *fd16;
+  const float *fdf;
+  size_t ldM;
+  int N, M, feature_type;
+  const int *sp, *tp;
+  const double *sxyz_pairs, *txyz_pairs;  // stand-alone rigid fit: explicit point lists (column-major n x 3)
+  int n_explicit;
+  CostParams cp;
+  DevIter *iter;
+};
+constexpr int SOLVE_THREADS = 1024;
+__global__ void __launch_bounds__(SOLVE_THREADS) k_solve(const SolveArgs a) {
+  __shared__ double smem[12 * (SOLVE_THREADS / 32)];
+  static_assert(12 >= 10, "smem sized for the widest block_sum");
+  __shared__ double s_b[16];
+  const bool explicit_pts = a.sxyz_pairs != nullptr;
+  const int cor = explicit_pts ? a.n_explicit : a.iter->cor;
+  auto load = [&](int p, double &sx, double &sy, double &sz, double &tx, double &ty, double &tz, double &fd) {
+    if (explicit_pts) {
+      sx = a.sxyz_pairs[p]; sy = a.sxyz_pairs[(size_t)cor + p]; sz = a.sxyz_pairs[2 * (size_t)cor + p];
+      tx = a.txyz_pairs[p]; ty = a.txyz_pairs[(size_t)cor + p]; tz = a.txyz_pairs[2 * (size_t)cor + p];
+      fd = 0.0;
+    } else {
+      const int i = a.sp[p], j = a.tp[p];
+      sx = a.s[i]; sy = a.s[(size_t)a.N + i]; sz = a.s[2 * (size_t)a.N + i];
+      tx = a.t[j]; ty = a.t[(size_t)a.M + j]; tz = a.t[2 * (size_t)a.M + j];
+      if (a.feature_type == GHICP_FT_BSC && a.fd16) fd = (double)a.fd16[(size_t)i * a.ldM + j];
+      else if (a.feature_type == GHICP_FT_FPFH && a.fdf) fd = (double)a.fdf[(size_t)i * a.ldM + j];
+      else fd = 0.0;
+    }
+  };
+  // pass 1
+  double acc1[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int p = threadIdx.x; p < cor; p += SOLVE_THREADS) {
+    double sx, sy, sz, tx, ty, tz, fd;
+    load(p, sx, sy, sz, tx, ty, tz, fd);
+    const double dx = sx - tx, dy = sy - ty, dz = sz - tz;
+    const double d2 = (dx * dx + dy * dy) + dz * dz;
+    acc1[0] += d2;
+    acc1[1] += fd;
+    acc1[2] += sx; acc1[3] += sy; acc1[4] += sz;
+    acc1[5] += tx; acc1[6] += ty; acc1[7] += tz;
+    // CD of the kept pair (for Km::Calenergy, src/km.cpp:128-141)
+    const double ed = a.cp.scale * sqrt(d2);
+    double cd;
+    if (a.feature_type == GHICP_FT_BSC) cd = a.cp.WED * ed + a.cp.WFD * fd;
+    else if (a.feature_type == GHICP_FT_FPFH) cd = 1.0 * ed / pow(fd, a.cp.ex);
+    else cd = ed;
+    acc1[8] += cd;
+  }
+  block_sum<9, SOLVE_THREADS>(acc1, smem);
+  if (threadIdx.x == 0) {
+    a.iter->km_cd_sum = acc1[8];
+    s_b[0] = acc1[0];               // sum of squared distances
+    s_b[1] = acc1[1] / cor;         // FDM (NaN when cor == 0, as the reference)
+    for (int k = 0; k < 6; ++k) s_b[2 + k] = acc1[2 + k] / cor;  // centroids
+  }
+  __syncthreads();
+  const double FDM = s_b[1];
+  const double mus[3] = {s_b[2], s_b[3], s_b[4]}, mud[3] = {s_b[5], s_b[6], s_b[7]};
+  // pass 2
+  double acc2[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int p = threadIdx.x; p < cor; p += SOLVE_THREADS) {
+    double sx, sy, sz, tx, ty, tz, fd;
+    load(p, sx, sy, sz, tx, ty, tz, fd);
+    const double ds[3] = {sx - mus[0], sy - mus[1], sz - mus[2]};
+    const double dd[3] = {tx - mud[0], ty - mud[1], tz - mud[2]};
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc2[r * 3 + c] += dd[r] * ds[c];
+    const double e = fd - FDM;
+    acc2[9] += e * e;
+  }
+  block_sum<10, SOLVE_THREADS>(acc2, smem);
+  __shared__ double s_Rt[16];
+  if (threadIdx.x == 0) {
+    DevIter *it = a.iter;
+    double RMSE = s_b[0] / cor;
+    it->rmse = sqrt(RMSE);
+    it->fdm = FDM;
+    it->fdstd = sqrt(acc2[9] / cor);
+    double Rt[16];
+    for (int i = 0; i < 16; ++i) Rt[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    it->solve_degenerate = 0;
+    if (cor >= 3) {
+      float mu_s[3], mu_d[3], sigma[9];
+      for (int k = 0; k < 3; ++k) { mu_s[k] = (float)mus[k]; mu_d[k] = (float)mud[k]; }
+      for (int k = 0; k < 9; ++k) sigma[k] = (float)(acc2[k] / cor);
+      umeyama_from_moments_f32(mu_s, mu_d, sigma, Rt);
+    } else {
+      it->solve_degenerate = 1;
+    }
+    for (int i = 0; i < 16; ++i) { it->Rt[i] = Rt[i]; s_Rt[i] = Rt[i]; }
+  }
+  __syncthreads();
+  // pass 3: RMSE after the update; R*v evaluated as ((R0*x + R1*y) + R2*z) + t like Eigen
+  double acc3[1] = {0};
+  {
+    const double R00 = s_Rt[0], R10 = s_Rt[1], R20 = s_Rt[2], R01 = s_Rt[4], R11 = s_Rt[5], R21 = s_Rt[6],
+                 R02 = s_Rt[8], R12 = s_Rt[9], R22 = s_Rt[10], t0 = s_Rt[12], t1 = s_Rt[13], t2 = s_Rt[14];
+    for (int p = threadIdx.x; p < cor; p += SOLVE_THREADS) {
+      double sx, sy, sz, tx, ty, tz, fd;
+      load(p, sx, sy, sz, tx, ty, tz, fd);
+      const double nx = ((R00 * sx + R01 * sy) + R02 * sz) + t0;
+      const double ny = ((R10 * sx + R11 * sy) + R12 * sz) + t1;
+      const double nz = ((R20 * sx + R21 * sy) + R22 * sz) + t2;
+      const double dx = nx - tx, dy = ny - ty, dz = nz - tz;
+      acc3[0] += (dx * dx + dy * dy) + dz * dz;
+    }
+  }
+  block_sum<1, SOLVE_THREADS>(acc3, smem);
+  if (threadIdx.x == 0) a.iter->rmse_after = sqrt(acc3[0] / cor);
+}
+
+// KP.kpSXYZ.row(i) = (R * row^T + t)^T for ALL source keypoints (src/ghicp_reg.cpp:891-894)
+__global__ void k_apply(double *__restrict__ s, int N, const DevIter *__restrict__ iter) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const double *Rt = iter->Rt;
+  const double x = s[i], y = s[(size_t)N + i], z = s[2 * (size_t)N + i];
+  s[i] = ((Rt[0] * x + Rt[4] * y) + Rt[8] * z) + Rt[12];
+  s[(size_t)N + i] = ((Rt[1] * x + Rt[5] * y) + Rt[9] * z) + Rt[13];
+  s[2 * (size_t)N + i] = ((Rt[2] * x + Rt[6] * y) + Rt[10] * z) + Rt[14];
+}
+
+__global__ void k_fd_to_double(const uint16_t *__restrict__ fd16, const float *__restrict__ fdf, size_t ldM,
+                               int N, int M, double *__restrict__ out) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)N * M) return;
+  const size_t i = idx / M, j = idx % M;
+  out[idx] = fd16 ? (double)fd16[i * ldM + j] : (fdf ? (double)fdf[i * ldM + j] : 0.0);
+}
+
+template <typename F>
+cudaError_t dispatch_ft(int ft, F &&f) {
+  switch (ft) {
+    case GHICP_FT_BSC: return f(std::integral_constant<int, GHICP_FT_BSC>());
+    case GHICP_FT_FPFH: return f(std::integral_constant<int, GHICP_FT_FPFH>());
+    default: return f(std::integral_constant<int, GHICP_FT_NONE>());
+  }
+}
+
+}  // namespace
+
+// =============================================================================================
+// launchers
+// =============================================================================================
+cudaError_t launch_pack_bsc(Ctx *c, const uint8_t *d_raw_s, const uint8_t *d_raw_t) {
+  {
+    long long total = (long long)c->V * c->W64 * c->N;
+    k_pack_bsc<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(d_raw_s, c->d_bs, c->V, c->N, c->Bbytes, c->W64);
+    c->launches++;
+  }
+  {
+    long long total = (long long)c->W64 * c->M;
+    k_pack_bsc<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(d_raw_t, c->d_bt, 1, c->M, c->Bbytes, c->W64);
+    c->launches++;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fd_bsc(Ctx *c) {
+  const int V = (c->cfg.dof == 6) ? 4 : 2;  // src/ghicp_reg.cpp:178-182
+  dim3 grid((c->M + FDB_THREADS - 1) / FDB_THREADS, (c->N + FDB_ROWS - 1) / FDB_ROWS);
+  size_t smem = (size_t)V * c->W64 * FDB_ROWS * sizeof(uint64_t);
+  if (V == 4)
+    k_fd_bsc<4><<<grid, FDB_THREADS, smem, c->stream>>>(c->d_bs, c->d_bt, c->d_fd16, c->N, c->M, c->ldM, c->W64);
+  else
+    k_fd_bsc<2><<<grid, FDB_THREADS, smem, c->stream>>>(c->d_bs, c->d_bt, c->d_fd16, c->N, c->M, c->ldM, c->W64);
+  c->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fd_fpfh(Ctx *c) {
+  float *sc = nullptr, *tc = nullptr;
+  cudaError_t e;
+  if ((e = cudaMallocAsync(&sc, (size_t)c->N * 36 * sizeof(float), c->stream)) != cudaSuccess) return e;
+  if ((e = cudaMallocAsync(&tc, (size_t)c->M * 36 * sizeof(float), c->stream)) != cudaSuccess) return e;
+  k_fpfh_center<<<(c->N + 127) / 128, 128, 0, c->stream>>>(c->d_fs, sc, c->N);
+  k_fpfh_center<<<(c->M + 127) / 128, 128, 0, c->stream>>>(c->d_ft, tc, c->M);
+  dim3 grid((c->M + FPT - 1) / FPT, (c->N + FPT - 1) / FPT);
+  k_fd_fpfh<<<grid, FPT * FPT, 0, c->stream>>>(sc, tc, c->d_fdf, c->N, c->M, c->ldM);
+  c->launches += 3;
+  cudaFreeAsync(sc, c->stream);
+  cudaFreeAsync(tc, c->stream);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rowsweep(Ctx *c, int mode, const CostParams &cp) {
+  SweepArgs a{};
+  a.s = c->d_s; a.t = c->d_t; a.fd16 = c->d_fd16; a.fdf = c->d_fdf; a.ldM = c->ldM;
+  a.N = c->N; a.M = c->M; a.n_chunks = c->n_chunks;
+  int cpc = (c->M + c->n_chunks - 1) / c->n_chunks;
+  cpc = (cpc + COLS_PER_THREAD - 1) / COLS_PER_THREAD * COLS_PER_THREAD;
+  a.cols_per_chunk = cpc;
+  a.cp = cp;
+  a.part_cd = c->d_part_cd; a.part_idx = c->d_part_idx; a.part_stats = c->d_part_stats;
+  a.iter = c->d_iter; a.cnt = c->d_cnt; a.rowptr = c->d_rowptr; a.cursor = c->d_cursor;
+  a.csr_col = c->d_csr_col; a.csr_gain = c->d_csr_gain;
+  dim3 grid((c->N + TR - 1) / TR, c->n_chunks);
+  cudaError_t e = dispatch_ft(c->cfg.feature_type, [&](auto ft) {
+    constexpr int FT = decltype(ft)::value;
+    if (mode == 0) k_rowsweep<FT, 0><<<grid, SWEEP_THREADS, 0, c->stream>>>(a);
+    else if (mode == 1) k_rowsweep<FT, 1><<<grid, SWEEP_THREADS, 0, c->stream>>>(a);
+    else k_rowsweep<FT, 2><<<grid, SWEEP_THREADS, 0, c->stream>>>(a);
+    return cudaGetLastError();
+  });
+  c->launches++;
+  return e;
+}
+
+cudaError_t launch_colsweep(Ctx *c, const CostParams &cp) {
+  ColArgs a{};
+  a.s = c->d_s; a.t = c->d_t; a.fd16 = c->d_fd16; a.fdf = c->d_fdf; a.ldM = c->ldM;
+  a.N = c->N; a.M = c->M; a.cp = cp; a.col_cd = c->d_col_cd; a.col_idx = c->d_col_idx;
+  dim3 grid((c->M + CT - 1) / CT);
+  cudaError_t e = dispatch_ft(c->cfg.feature_type, [&](auto ft) {
+    constexpr int FT = decltype(ft)::value;
+    k_colsweep<FT><<<grid, COL_THREADS, 0, c->stream>>>(a);
+    return cudaGetLastError();
+  });
+  c->launches++;
+  return e;
+}
+
+cudaError_t launch_finalize_stats(Ctx *c, const CostParams &cp, const LoopScalars &ls) {
+  const int n_parts = ((c->N + TR - 1) / TR) * c->n_chunks;
+  k_finalize<<<1, 1024, 0, c->stream>>>(c->d_part_cd, c->d_part_idx, c->n_chunks, c->N, c->M, c->d_part_stats,
+                                        n_parts, c->d_row_cd, c->d_row_idx, c->cfg.feature_type, cp.pivot, ls,
+                                        c->d_iter);
+  c->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scan_counts(Ctx *c) {
+  const long long L = (long long)c->N * c->n_chunks;
+  k_scan_counts<<<1, 1024, 0, c->stream>>>(c->d_cnt, c->d_rowptr, c->d_cursor, L, c->d_iter);
+  c->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_select_nn(Ctx *c) {
+  k_select<<<1, 1024, 0, c->stream>>>(0, c->N, c->d_row_cd, c->d_row_idx, nullptr, nullptr, c->d_sp, c->d_tp, c->d_iter);
+  c->launches++;
+  return cudaGetLastError();
+}
+cudaError_t launch_select_nnr(Ctx *c) {
+  k_select<<<1, 1024, 0, c->stream>>>(1, c->N, c->d_row_cd, c->d_row_idx, c->d_col_idx, nullptr, c->d_sp, c->d_tp, c->d_iter);
+  c->launches++;
+  return cudaGetLastError();
+}
+cudaError_t launch_select_km(Ctx *c) {
+  k_select<<<1, 1024, 0, c->stream>>>(2, c->M, nullptr, nullptr, nullptr, c->d_owner, c->d_sp, c->d_tp, c->d_iter);
+  c->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_solve(Ctx *c, const CostParams &cp) {
+  SolveArgs a{};
+  a.cp = cp;
+  a.s = c->d_s; a.t = c->d_t; a.fd16 = c->d_fd16; a.fdf = c->d_fdf; a.ldM = c->ldM;
+  a.N = c->N; a.M = c->M; a.feature_type = c->cfg.feature_type;
+  a.sp = c->d_sp; a.tp = c->d_tp; a.sxyz_pairs = nullptr; a.txyz_pairs = nullptr; a.n_explicit = 0;
+  a.iter = c->d_iter;
+  k_solve<<<1, SOLVE_THREADS, 0, c->stream>>>(a);
+  c->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_solve_explicit(cudaStream_t stream, const double *d_s, const double *d_t, int n, DevIter *d_iter) {
+  SolveArgs a{};
+  a.sxyz_pairs = d_s; a.txyz_pairs = d_t; a.n_explicit = n; a.iter = d_iter;
+  a.feature_type = GHICP_FT_NONE;
+  k_solve<<<1, SOLVE_THREADS, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_apply(Ctx *c) {
+  k_apply<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->d_s, c->N, c->d_iter);
+  c->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_get_fd(Ctx *c, double *d_out) {
+  const size_t total = (size_t)c->N * c->M;
+  k_fd_to_double<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(c->d_fd16, c->d_fdf, c->ldM, c->N, c->M, d_out);
+  c->launches++;
+  return cudaGetLastError();
+}
+
+}  // namespace ghicp_b200

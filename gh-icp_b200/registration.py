@@ -1,0 +1,170 @@
+"""Python mirror of the reference's registration interface (include/ghicp_reg.h:15-132) over the C ABI.
+
+Same names and argument meaning as the reference: `Energyfunction.init(kps_num, kpt_num, bbx_magnitude)`,
+`Keypoints.setCoordinate / setBSCfeature / setFPFHfeature`, `GHRegistration(Kp, Ef, Ft, Ct, radiusNonMax,
+weight_adjustment_ratio, weight_adjustment_step, dof_type, estimated_IoU, converge_tran, converge_rot)`,
+`ghicp_reg() -> Rt_final`.  Viewer / raw-cloud setters are accepted and ignored (out of scope).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import CT_KM, CT_NN, CT_NNR, FT_BSC, FT_FPFH, FT_NONE  # noqa: F401
+
+
+class Energyfunction:
+    """include/ghicp_reg.h:15-42 (the N x M matrices live on the device, not here)."""
+
+    def __init__(self):
+        self.bbx_magnitude = 0.0
+        self.kps_num = self.kpt_num = 0
+
+    def init(self, kps_num, kpt_num, bbx_magnitude):
+        self.kps_num, self.kpt_num, self.bbx_magnitude = kps_num, kpt_num, float(bbx_magnitude)
+        return self
+
+
+class Keypoints:
+    """include/ghicp_reg.h:44-72."""
+
+    def __init__(self):
+        self.kpSXYZ = self.kpTXYZ = None
+        self.bscS = self.bscT = None
+        self.bits = 0
+        self.fpfhS = self.fpfhT = None
+
+    def setCoordinate(self, kps, kpt):
+        self.kpSXYZ = np.asfortranarray(kps, dtype=np.float64)
+        self.kpTXYZ = np.asfortranarray(kpt, dtype=np.float64)
+        self.kps_num, self.kpt_num = self.kpSXYZ.shape[0], self.kpTXYZ.shape[0]
+        return self
+
+    def setBSCfeature(self, bsc_S, bsc_T, bits):
+        self.bscS = np.ascontiguousarray(bsc_S, dtype=np.uint8)   # (V, N, B)
+        self.bscT = np.ascontiguousarray(bsc_T, dtype=np.uint8)   # (M, B)
+        self.bits = int(bits)
+        return self
+
+    def setFPFHfeature(self, fpfh_S, fpfh_T):
+        self.fpfhS = np.ascontiguousarray(fpfh_S, dtype=np.float32)
+        self.fpfhT = np.ascontiguousarray(fpfh_T, dtype=np.float32)
+        return self
+
+
+class GHRegistration:
+    """include/ghicp_reg.h:74-132 over libghicp_b200.so."""
+
+    def __init__(self, Kp, Ef, Ft, Ct, radiusNonMax=1.0, weight_adjustment_ratio=1.1,
+                 weight_adjustment_step=0.1, dof_type=6, estimated_IoU=0.5,
+                 converge_tran=0.02, converge_rot=0.02, max_iter=0, device=0, km_eps=0.0):
+        self.L = capi.lib()
+        cfg = capi.Config()
+        cfg.feature_type, cfg.corr_type, cfg.dof = Ft, Ct, dof_type
+        cfg.bbx_magnitude = Ef.bbx_magnitude
+        cfg.nonmax = radiusNonMax
+        cfg.adjust_ratio, cfg.adjust_step = weight_adjustment_ratio, weight_adjustment_step
+        cfg.estimated_iou = estimated_IoU
+        cfg.converge_t, cfg.converge_r = converge_tran, converge_rot
+        cfg.max_iter, cfg.device, cfg.km_eps = max_iter, device, km_eps
+        self.ctx = C.c_void_p()
+        capi.check(self.L.ghicp_create(C.byref(cfg), C.byref(self.ctx)))
+        self.N, self.M = Kp.kps_num, Kp.kpt_num
+        self.Ft, self.Ct = Ft, Ct
+        self.upload(Kp)
+        self.history = []
+
+    def upload(self, Kp):
+        capi.check(self.L.ghicp_set_keypoints(self.ctx, capi._dp(Kp.kpSXYZ), Kp.kps_num,
+                                              capi._dp(Kp.kpTXYZ), Kp.kpt_num), self.ctx)
+        if self.Ft == FT_BSC:
+            capi.check(self.L.ghicp_set_bsc(self.ctx, Kp.bscS.ctypes.data, Kp.bscS.shape[0],
+                                            Kp.bscT.ctypes.data, Kp.bits), self.ctx)
+        elif self.Ft == FT_FPFH:
+            capi.check(self.L.ghicp_set_fpfh(self.ctx, Kp.fpfhS.ctypes.data, Kp.fpfhT.ctypes.data), self.ctx)
+
+    def set_keypoints(self, kps, kpt):
+        """Re-upload coordinates only (same sizes): the host->device leg of an end-to-end step."""
+        kps = np.asfortranarray(kps, dtype=np.float64)
+        kpt = np.asfortranarray(kpt, dtype=np.float64)
+        capi.check(self.L.ghicp_set_keypoints(self.ctx, capi._dp(kps), kps.shape[0], capi._dp(kpt),
+                                              kpt.shape[0]), self.ctx)
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.L.ghicp_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # reference no-ops (viewer / raw clouds are out of scope)
+    def set_raw_pointcloud(self, *a):
+        pass
+
+    def set_viewer(self, launch_viewer):
+        pass
+
+    def build_fd(self):
+        capi.check(self.L.ghicp_build_fd(self.ctx), self.ctx)
+
+    def iterate(self):
+        st = capi.IterStats()
+        capi.check(self.L.ghicp_iterate(self.ctx, C.byref(st)), self.ctx)
+        self.history.append(st)
+        return st
+
+    def ghicp_reg(self):
+        """Main entrance (src/ghicp_reg.cpp:24-112). Returns (Rt_final 4x4, iterations)."""
+        Rt = np.zeros(16)
+        it = C.c_int(0)
+        capi.check(self.L.ghicp_run(self.ctx, capi._dp(Rt), C.byref(it)), self.ctx)
+        return Rt.reshape(4, 4).T.copy(), it.value
+
+    def pairs(self):
+        cap = max(self.N, self.M)
+        sp = np.zeros(cap, np.int32)
+        tp = np.zeros(cap, np.int32)
+        n = C.c_int(0)
+        capi.check(self.L.ghicp_get_pairs(self.ctx, capi._ip(sp), capi._ip(tp), cap, C.byref(n)), self.ctx)
+        return sp[:n.value].copy(), tp[:n.value].copy()
+
+    def source(self):
+        out = np.zeros((self.N, 3), dtype=np.float64, order="F")
+        capi.check(self.L.ghicp_get_source(self.ctx, capi._dp(out)), self.ctx)
+        return out
+
+    def Rt_tillnow(self):
+        Rt = np.zeros(16)
+        capi.check(self.L.ghicp_get_rt(self.ctx, capi._dp(Rt)), self.ctx)
+        return Rt.reshape(4, 4).T.copy()
+
+    def fd(self):
+        out = np.zeros((self.N, self.M), dtype=np.float64)
+        capi.check(self.L.ghicp_get_fd(self.ctx, capi._dp(out)), self.ctx)
+        return out
+
+    def probe_rowmin(self):
+        idx = np.zeros(self.N, np.int32)
+        cd = np.zeros(self.N, np.float64)
+        m, s, p = C.c_double(0), C.c_double(0), C.c_double(0)
+        capi.check(self.L.ghicp_probe_rowmin(self.ctx, capi._ip(idx), capi._dp(cd), C.byref(m), C.byref(s),
+                                             C.byref(p)), self.ctx)
+        return idx, cd, m.value, s.value, p.value
+
+    def set_state(self, iteration, rms, fdm, fdstd, para1, para2):
+        capi.check(self.L.ghicp_set_state(self.ctx, iteration, rms, fdm, fdstd, para1, para2), self.ctx)
+
+
+def from_scene(scene, Ft, Ct, dof=6, **kw):
+    """Convenience: build Keypoints/Energyfunction/GHRegistration from a synth.Scene."""
+    Kp = Keypoints().setCoordinate(scene.S, scene.T)
+    if Ft == FT_BSC:
+        Kp.setBSCfeature(scene.bsc_s, scene.bsc_t, scene.bits)
+    elif Ft == FT_FPFH:
+        Kp.setFPFHfeature(scene.fpfh_s, scene.fpfh_t)
+    Ef = Energyfunction().init(Kp.kps_num, Kp.kpt_num, scene.bbx_magnitude)
+    return GHRegistration(Kp, Ef, Ft, Ct, dof_type=dof, **kw)

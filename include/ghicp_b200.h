@@ -1,0 +1,149 @@
+/*
+ * ghicp_b200.h — C ABI of the B200-native GH-ICP registration inner loop (libghicp_b200.so).
+ *
+ * Drop-in boundary for the hot path of YuePanEdward/GH-ICP (citations: file:line in the reference):
+ * the private stage methods of ghicp::GHRegistration (include/ghicp_reg.h:156-171) and the Km solver
+ * (include/km.h:32-61).  POD only — no Eigen / PCL / STL / torch types cross this boundary.
+ * Every function returns an int status (0 = ok, <0 = GHICP_E_*, >0 = GHICP_W_* warning bits);
+ * nothing throws across the ABI.  One ctx = one host thread at a time; a ctx owns one CUDA device,
+ * one stream and all its device memory.
+ *
+ * Layout conventions
+ *   coordinates : Eigen::MatrixX3d::data() layout = column-major N x 3 = SoA x[N], y[N], z[N]
+ *                 (include/ghicp_reg.h:47, Keypoints::kpSXYZ / kpTXYZ)
+ *   BSC bits    : bit k of a descriptor lives in byte k/8, bit k%8, LSB first
+ *                 (include/stereo_binary_feature.h:140-146); B = ceil(bits/8) bytes
+ *   FPFH        : float[33] per keypoint (pcl::FPFHSignature33::histogram, include/fpfh.hpp:135)
+ *   transforms  : 4x4 column-major doubles = Eigen::Matrix4d::data()
+ */
+#ifndef GHICP_B200_H_
+#define GHICP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GHICP_ABI_VERSION 1
+
+/* enum values follow include/utility.h:51-64 */
+enum ghicp_feature_type { GHICP_FT_BSC = 0, GHICP_FT_ROPS = 1, GHICP_FT_FPFH = 2, GHICP_FT_NONE = 3 };
+enum ghicp_corr_type { GHICP_CT_NN = 0, GHICP_CT_NNR = 1, GHICP_CT_KM = 2 };
+
+enum ghicp_status {
+  GHICP_OK = 0,
+  GHICP_E_ARG = -1,    /* bad argument / call order */
+  GHICP_E_NOMEM = -2,  /* device or host allocation failed / workspace budget exceeded */
+  GHICP_E_CUDA = -3,   /* CUDA runtime error, see ghicp_last_error */
+  GHICP_E_NCCL = -4,   /* NCCL error / NCCL not loadable */
+  GHICP_E_NOCONV = -5, /* ghicp_run hit max_iter without converging */
+  GHICP_E_NODEV = -6,  /* no CUDA device: the product path has NO CPU fallback */
+  GHICP_W_FEW_PAIRS = 1 /* cor < min_cor (include/ghicp_reg.h:36, src/ghicp_reg.cpp:796-797) */
+};
+
+/* Constructor arguments of ghicp::GHRegistration (include/ghicp_reg.h:77-81) + Energyfunction::init
+ * argument (include/ghicp_reg.h:26) + execution options. Zero-initialise, then fill. */
+typedef struct ghicp_config {
+  int feature_type;     /* ghicp_feature_type (Ft) */
+  int corr_type;        /* ghicp_corr_type (Ct) */
+  int dof;              /* dof_type: 6 → 4 BSC source variants, otherwise 2 (src/ghicp_reg.cpp:178-182) */
+  float bbx_magnitude;  /* Energyfunction::init(.., bbx_magnitude) → scale = 0.005*bbx (ghicp_reg.h:40) */
+  float nonmax;         /* radiusNonMax */
+  float adjust_ratio;   /* weight_adjustment_ratio */
+  float adjust_step;    /* weight_adjustment_step */
+  float estimated_iou;  /* estimated_IoU */
+  float converge_t;     /* converge_tran, reference default 0.02 m */
+  float converge_r;     /* converge_rot, reference default 0.02 deg */
+  int max_iter;         /* 0 = unbounded like the reference's while(!converge) (src/ghicp_reg.cpp:49) */
+  int device;           /* CUDA device ordinal */
+  double km_eps;        /* 0 → Energyfunction::KM_eps = 0.01 (ghicp_reg.h:38) */
+  int verbose;          /* 0 = silent (the reference prints every iteration; we do not by default) */
+  int reserved[7];
+} ghicp_config;
+
+/* Everything one loop body of GHRegistration::ghicp_reg (src/ghicp_reg.cpp:49-103) reports. */
+typedef struct ghicp_iter_stats {
+  int iteration;        /* iteration_number this body ran with (starts at 0) */
+  int cor;              /* number of correspondences */
+  int converged;        /* converge flag after this iteration */
+  int warnings;         /* GHICP_W_* bits */
+  double Rt[16];        /* this iteration's transform (Rt_temp), column-major */
+  double Rt_tillnow[16];/* accumulated transform */
+  double cd_mean, cd_std, penalty;          /* calCD_* outputs */
+  double rmse, rmse_after, fdm, fdstd, iou; /* findcorrespondence* / transformestimation outputs */
+  double para1, para2;                      /* after adjustweight */
+  double km_energy;                         /* Km::Calenergy equivalent (KM mode) */
+  double ax, ay, az;                        /* Euler angles in degrees (src/ghicp_reg.cpp:873-879) */
+  /* execution detail */
+  long long nnz;        /* KM: candidate edges with CD < penalty */
+  int km_rounds;        /* KM: auction bidding rounds (forward + reverse) */
+  int km_phases;        /* KM: epsilon-scaling phases */
+  int gpu_launches;     /* kernels launched by this call */
+  float ms_cost, ms_corr, ms_solve, ms_total; /* CUDA-event stage times on the ctx stream */
+} ghicp_iter_stats;
+
+typedef struct ghicp_ctx ghicp_ctx;
+
+int ghicp_abi_version(void);
+int ghicp_device_count(void);
+const char *ghicp_last_error(const ghicp_ctx *ctx); /* ctx may be NULL: last global error */
+
+/* GHRegistration::GHRegistration (include/ghicp_reg.h:77-117). */
+int ghicp_create(const ghicp_config *cfg, ghicp_ctx **out);
+int ghicp_destroy(ghicp_ctx *ctx);
+
+/* Keypoints::setCoordinate (include/ghicp_reg.h:54-60). Copies host → device. May be called again
+ * with the same N, M to replace the coordinates (e.g. to restart, or to re-upload per iteration). */
+int ghicp_set_keypoints(ghicp_ctx *ctx, const double *sxyz, int N, const double *txyz, int M);
+/* Keypoints::setBSCfeature (include/ghicp_reg.h:62-66). s_bits [V][N][B], t_bits [M][B]. */
+int ghicp_set_bsc(ghicp_ctx *ctx, const uint8_t *s_bits, int V, const uint8_t *t_bits, int bits);
+/* Keypoints::setFPFHfeature (include/ghicp_reg.h:68-72). s [N][33], t [M][33]. */
+int ghicp_set_fpfh(ghicp_ctx *ctx, const float *s, const float *t);
+
+/* calFD_BSC / calFD_FPFH (src/ghicp_reg.cpp:143-214): one-time feature-distance build. */
+int ghicp_build_fd(ghicp_ctx *ctx);
+
+/* One body of while(!converge): calED + calCD_* + findcorrespondence* + transformestimation +
+ * adjustweight + Rt_tillnow update (src/ghicp_reg.cpp:49-103, viewer excluded). */
+int ghicp_iterate(ghicp_ctx *ctx, ghicp_iter_stats *out);
+
+/* GHRegistration::ghicp_reg (src/ghicp_reg.cpp:24-112): build FD if needed, iterate to convergence. */
+int ghicp_run(ghicp_ctx *ctx, double Rt_final[16], int *iterations);
+
+/* Results of the last iteration. */
+int ghicp_get_pairs(ghicp_ctx *ctx, int *sp, int *tp, int cap, int *n); /* SP/TP index lists */
+int ghicp_get_source(ghicp_ctx *ctx, double *sxyz);                     /* current KP.kpSXYZ */
+int ghicp_get_rt(ghicp_ctx *ctx, double Rt_tillnow[16]);
+/* FD plane as doubles, row-major N x M (Energyfunction::FD). Test/debug: O(N*M) host memory. */
+int ghicp_get_fd(ghicp_ctx *ctx, double *fd);
+/* Per-source-row argmin of CD for the state *before* the next iterate (NN scan,
+ * src/ghicp_reg.cpp:715-733) without advancing the loop. idx[N], cd[N] (either may be NULL). */
+int ghicp_probe_rowmin(ghicp_ctx *ctx, int *idx, double *cd, double *cd_mean, double *cd_std,
+                       double *penalty);
+/* Loop state the reference keeps between iterations (include/ghicp_reg.h:173-202); for resume/tests. */
+int ghicp_set_state(ghicp_ctx *ctx, int iteration, double rms, double fdm, double fdstd, double para1,
+                    double para2);
+
+/* ---- stand-alone stages -------------------------------------------------------------------- */
+/* Km(graph, eps, penalty).kmsolve() + output() (include/km.h:38-53, src/km.cpp:40-233) on a dense
+ * n x n row-major weight matrix built like src/ghicp_reg.cpp:348-365 (w = -CD if CD < penalty else
+ * -penalty).  match[y] = x for kept pairs, -1 for pairs the reference drops (w == -penalty).
+ * energy = Km::Calenergy().  Solved on the GPU by epsilon-scaled forward/reverse auction. */
+int ghicp_km_solve(int device, const double *W, int n, int sp, int tp, double eps, double penalty,
+                   int *match, double *energy, int *rounds);
+/* pcl TransformationEstimationSVD::estimateRigidTransformation as called at src/ghicp_reg.cpp:857-866.
+ * s, t column-major n x 3 (Spoint / Tpoint). */
+int ghicp_rigid_fit(int device, const double *s, const double *t, int n, double Rt[16]);
+
+/* ---- multi-GPU (one process per GPU; source rows sharded, target replicated) ---------------- */
+/* 128-byte NCCL unique id; rank 0 creates it, the host runtime broadcasts it (torch.distributed,
+ * MPI, a file ...). No NCCL symbol is touched unless these are called (world == 1 → never). */
+int ghicp_comm_unique_id(void *id128);
+int ghicp_comm_init(ghicp_ctx *ctx, const void *id128, int rank, int world);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GHICP_B200_H_ */

@@ -1,0 +1,228 @@
+"""ctypes binding of oracle/liboracle*.so and oracle/_ref/libkm_ref.so (TEST INFRASTRUCTURE ONLY)."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+FT_BSC, FT_ROPS, FT_FPFH, FT_NONE = 0, 1, 2, 3
+CT_NN, CT_NNR, CT_KM = 0, 1, 2
+
+
+class OrcConfig(C.Structure):
+    _fields_ = [("feature_type", C.c_int), ("corr_type", C.c_int), ("dof", C.c_int),
+                ("bbx_magnitude", C.c_float), ("nonmax", C.c_float), ("adjust_ratio", C.c_float),
+                ("adjust_step", C.c_float), ("estimated_iou", C.c_float), ("converge_t", C.c_float),
+                ("converge_r", C.c_float), ("max_iter", C.c_int), ("solve_mode", C.c_int),
+                ("use_ref_km", C.c_int), ("num_threads", C.c_int)]
+
+
+class OrcIterStats(C.Structure):
+    _fields_ = [("iteration", C.c_int), ("cor", C.c_int), ("converged", C.c_int),
+                ("warn_few_pairs", C.c_int), ("Rt", C.c_double * 16), ("Rt_tillnow", C.c_double * 16),
+                ("cd_mean", C.c_double), ("cd_std", C.c_double), ("penalty", C.c_double),
+                ("rmse", C.c_double), ("rmse_after", C.c_double), ("fdm", C.c_double),
+                ("fdstd", C.c_double), ("iou", C.c_double), ("para1", C.c_double), ("para2", C.c_double),
+                ("km_energy", C.c_double), ("ax", C.c_double), ("ay", C.c_double), ("az", C.c_double),
+                ("t_cost_ms", C.c_double), ("t_corr_ms", C.c_double), ("t_solve_ms", C.c_double)]
+
+
+def build(force=False):
+    """Compile the oracle (and oracle/_ref when /root/reference is present). Building the checker is
+    not using it."""
+    need = force or not os.path.exists(os.path.join(_HERE, "liboracle.so")) \
+        or not os.path.exists(os.path.join(_HERE, "liboracle_omp.so"))
+    if need or (os.path.isdir("/root/reference") and
+                not os.path.exists(os.path.join(_HERE, "_ref", "libkm_ref.so"))):
+        subprocess.run(["make", "-C", _HERE, "all"], check=True, capture_output=True)
+
+
+_libs = {}
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def lib(omp=False):
+    key = "omp" if omp else "st"
+    if key in _libs:
+        return _libs[key]
+    build()
+    L = C.CDLL(os.path.join(_HERE, "liboracle_omp.so" if omp else "liboracle.so"))
+    L.orc_create.restype = C.c_void_p
+    L.orc_create.argtypes = [C.POINTER(OrcConfig)]
+    L.orc_destroy.argtypes = [C.c_void_p]
+    L.orc_set_keypoints.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_int]
+    L.orc_set_bsc.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    L.orc_set_fpfh.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_build_fd.argtypes = [C.c_void_p]
+    L.orc_iterate.argtypes = [C.c_void_p, C.POINTER(OrcIterStats)]
+    L.orc_run.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    L.orc_get_pairs.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]
+    L.orc_get_source.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    L.orc_fd.restype = C.POINTER(C.c_double)
+    L.orc_fd.argtypes = [C.c_void_p]
+    L.orc_cd.restype = C.POINTER(C.c_double)
+    L.orc_cd.argtypes = [C.c_void_p]
+    L.orc_set_state.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]
+    L.orc_hamming.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.orc_fpfh_distance.restype = C.c_float
+    L.orc_fpfh_distance.argtypes = [C.c_void_p, C.c_void_p]
+    L.orc_km_solve.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_double, C.POINTER(C.c_int)]
+    L.orc_km_output.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, C.c_double,
+                                C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    L.orc_rigid_fit.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_int,
+                                C.POINTER(C.c_double)]
+    L.orc_set_km_backend.argtypes = [C.c_void_p]
+    _libs[key] = L
+    return L
+
+
+def ref_km_lib():
+    """oracle/_ref/libkm_ref.so = the reference's own src/km.cpp, or None if not built."""
+    if "ref" in _libs:
+        return _libs["ref"]
+    build()
+    p = os.path.join(_HERE, "_ref", "libkm_ref.so")
+    if not os.path.exists(p):
+        _libs["ref"] = None
+        return None
+    R = C.CDLL(p)
+    R.kmref_solve.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_double, C.POINTER(C.c_int)]
+    R.kmref_solve_output.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                                     C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                     C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                     C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    _libs["ref"] = R
+    return R
+
+
+def km_solve(W, eps=0.01, backend="port"):
+    """W: (n,n) float64 weights. Returns match (match[y] = x)."""
+    W = np.ascontiguousarray(W, dtype=np.float64)
+    n = W.shape[0]
+    match = np.zeros(n, dtype=np.int32)
+    if backend == "ref":
+        R = ref_km_lib()
+        if R is None:
+            raise RuntimeError("oracle/_ref/libkm_ref.so not built")
+        R.kmref_solve(_dp(W), n, eps, _ip(match))
+    else:
+        lib().orc_km_solve(_dp(W), n, eps, _ip(match))
+    return match
+
+
+def km_output(W, sp, tp, penalty, match):
+    W = np.ascontiguousarray(W, dtype=np.float64)
+    n = W.shape[0]
+    match = np.ascontiguousarray(match, dtype=np.int32)
+    SP = np.zeros(n, np.int32); TP = np.zeros(n, np.int32)
+    SPo = np.zeros(2 * n, np.int32); TPo = np.zeros(2 * n, np.int32)
+    ns = C.c_int(0); nt = C.c_int(0); e = C.c_double(0)
+    cor = lib().orc_km_output(_dp(W), n, sp, tp, penalty, _ip(match), _ip(SP), _ip(TP), _ip(SPo),
+                              C.byref(ns), _ip(TPo), C.byref(nt), C.byref(e))
+    return SP[:cor].copy(), TP[:cor].copy(), SPo[:ns.value].copy(), TPo[:nt.value].copy(), e.value
+
+
+def km_graph(CD, penalty):
+    """findcorrespondenceKM graph construction (src/ghicp_reg.cpp:348-365)."""
+    CD = np.asarray(CD, dtype=np.float64)
+    N, M = CD.shape
+    size = max(N, M)
+    W = np.full((size, size), -float(penalty), dtype=np.float64)
+    sub = W[:N, :M]
+    mask = CD < penalty
+    sub[mask] = -CD[mask]
+    return W
+
+
+def rigid_fit(S, T, solve_mode=0):
+    """S, T: (n,3). Returns 4x4 (row-major numpy) transform."""
+    S = np.asfortranarray(S, dtype=np.float64); T = np.asfortranarray(T, dtype=np.float64)
+    Rt = np.zeros(16, np.float64)
+    lib().orc_rigid_fit(_dp(S), _dp(T), S.shape[0], solve_mode, _dp(Rt))
+    return Rt.reshape(4, 4).T.copy()
+
+
+class Oracle:
+    """Python face of the oracle loop; mirrors GHRegistration (include/ghicp_reg.h:74-132)."""
+
+    def __init__(self, feature_type, corr_type, dof=6, bbx_magnitude=1.0, nonmax=1.0, adjust_ratio=1.1,
+                 adjust_step=0.1, estimated_iou=0.5, converge_t=0.02, converge_r=0.02, max_iter=0,
+                 solve_mode=0, use_ref_km=False, num_threads=1):
+        self.L = lib(omp=num_threads > 1)
+        cfg = OrcConfig(feature_type, corr_type, dof, bbx_magnitude, nonmax, adjust_ratio, adjust_step,
+                        estimated_iou, converge_t, converge_r, max_iter, solve_mode, int(use_ref_km),
+                        num_threads)
+        if use_ref_km:
+            R = ref_km_lib()
+            if R is None:
+                raise RuntimeError("oracle/_ref/libkm_ref.so not built")
+            self.L.orc_set_km_backend(C.cast(R.kmref_solve, C.c_void_p))
+        self.ctx = C.c_void_p(self.L.orc_create(C.byref(cfg)))
+        self.N = self.M = 0
+        self._keep = []
+
+    def __del__(self):
+        try:
+            if self.ctx:
+                self.L.orc_destroy(self.ctx)
+                self.ctx = None
+        except Exception:
+            pass
+
+    def set_keypoints(self, S, T):
+        S = np.asfortranarray(S, dtype=np.float64); T = np.asfortranarray(T, dtype=np.float64)
+        self.N, self.M = S.shape[0], T.shape[0]
+        self.L.orc_set_keypoints(self.ctx, _dp(S), self.N, _dp(T), self.M)
+
+    def set_bsc(self, s_bits, t_bits, bits):
+        s_bits = np.ascontiguousarray(s_bits, dtype=np.uint8); t_bits = np.ascontiguousarray(t_bits, dtype=np.uint8)
+        self.L.orc_set_bsc(self.ctx, s_bits.ctypes.data, s_bits.shape[0], t_bits.ctypes.data, bits)
+
+    def set_fpfh(self, s, t):
+        s = np.ascontiguousarray(s, dtype=np.float32); t = np.ascontiguousarray(t, dtype=np.float32)
+        self.L.orc_set_fpfh(self.ctx, s.ctypes.data, t.ctypes.data)
+
+    def build_fd(self):
+        return self.L.orc_build_fd(self.ctx)
+
+    def iterate(self):
+        st = OrcIterStats()
+        self.L.orc_iterate(self.ctx, C.byref(st))
+        return st
+
+    def run(self):
+        Rt = np.zeros(16); it = C.c_int(0)
+        rc = self.L.orc_run(self.ctx, _dp(Rt), C.byref(it))
+        return Rt.reshape(4, 4).T.copy(), it.value, rc
+
+    def pairs(self):
+        cap = max(self.N, self.M)
+        sp = np.zeros(cap, np.int32); tp = np.zeros(cap, np.int32)
+        n = self.L.orc_get_pairs(self.ctx, _ip(sp), _ip(tp), cap)
+        return sp[:n].copy(), tp[:n].copy()
+
+    def source(self):
+        out = np.zeros((self.N, 3), dtype=np.float64, order="F")
+        self.L.orc_get_source(self.ctx, _dp(out))
+        return out
+
+    def fd(self):
+        p = self.L.orc_fd(self.ctx)
+        return np.ctypeslib.as_array(p, shape=(self.N, self.M)).copy()
+
+    def cd(self):
+        p = self.L.orc_cd(self.ctx)
+        return np.ctypeslib.as_array(p, shape=(self.N, self.M)).copy()
+
+    def set_state(self, iteration, rms, fdm, fdstd, para1, para2):
+        self.L.orc_set_state(self.ctx, iteration, rms, fdm, fdstd, para1, para2)

@@ -1,0 +1,154 @@
+"""Pins the CPU oracle against every golden vector the reference holds for the hot path
+(G1, G2, G4) and against the reference's own src/km.cpp compiled verbatim
+(oracle/_ref/libkm_ref.so), plus independent numpy/scipy cross-checks."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+G1_W = np.array([[-5, -2, -100], [-4, -2, -6], [-100, -1, -7]], dtype=np.float64)  # src/km.cpp:237-260
+# img/GH-ICPworkflow.jpg panels (e),(f): 7 source x 6 target M_cd, T_cd = 30, E_min = 106
+G2_CD = np.array([[11, 19, 4, 40, 10, 31], [17, 10, 16, 39, 17, 36], [20, 42, 5, 28, 11, 29],
+                  [50, 21, 32, 24, 47, 32], [18, 26, 6, 7, 12, 38], [23, 36, 27, 35, 48, 30],
+                  [22, 24, 7, 21, 13, 46]], dtype=np.float64)
+
+
+def backends(orc):
+    return ["port", "ref"] if orc.ref_km_lib() is not None else ["port"]
+
+
+def test_g1_km_known_answer(orc, scratch_cwd):
+    for be in backends(orc):
+        m = orc.km_solve(G1_W, 0.01, be)
+        assert list(m) == [0, 2, 1]
+        assert -sum(G1_W[m[y], y] for y in range(3)) == 12.0
+
+
+def test_g2_workflow_figure(orc, scratch_cwd):
+    G = orc.km_graph(G2_CD, 30.0)
+    assert G.shape == (7, 7)
+    for be in backends(orc):
+        m = orc.km_solve(G, 0.01, be)
+        SP, TP, SPo, TPo, e = orc.km_output(G, 7, 6, 30.0, m)
+        assert list(zip(SP.tolist(), TP.tolist())) == [(0, 0), (1, 1), (6, 2), (4, 3), (2, 4)]
+        assert sorted(SPo.tolist()) == [3, 5] and TPo.tolist() == [5]
+        assert e == 106.0
+
+
+def test_golden_fixture_file_matches(orc, scratch_cwd):
+    with open(os.path.join(GOLD, "km_golden.json")) as f:
+        gold = json.load(f)
+    for case in gold["cases"]:
+        W = np.array(case["W"], dtype=np.float64)
+        m = orc.km_solve(W, case["eps"], "port")
+        assert m.tolist() == case["match"], case["name"]
+
+
+@pytest.mark.parametrize("n,seed", [(8, 0), (40, 1), (150, 2), (300, 3)])
+def test_port_equals_reference_km_bitwise(orc, scratch_cwd, n, seed):
+    if orc.ref_km_lib() is None:
+        pytest.skip("oracle/_ref not built (reference absent)")
+    rng = np.random.default_rng(seed)
+    CD = rng.random((n, n - n // 5)) * 60.0
+    G = orc.km_graph(CD, 25.0)
+    a = orc.km_solve(G, 0.01, "port")
+    b = orc.km_solve(G, 0.01, "ref")
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("n,seed", [(30, 5), (120, 6)])
+def test_km_within_n_eps_of_optimum(orc, scratch_cwd, n, seed):
+    from scipy.optimize import linear_sum_assignment
+    rng = np.random.default_rng(seed)
+    CD = rng.random((n, n)) * 50.0
+    G = orc.km_graph(CD, 20.0)
+    m = orc.km_solve(G, 0.01, "port")
+    ours = sum(G[m[y], y] for y in range(n))
+    r, c = linear_sum_assignment(-G)
+    opt = G[r, c].sum()
+    assert ours <= opt + 1e-9 and ours >= opt - n * 0.01
+
+
+def test_constants_g4(orc):
+    """Energyfunction::init / ctor constants (include/ghicp_reg.h:32-40, 80-81, 98)."""
+    sc = np.float32(0.005 * np.float32(220.0))
+    o = orc.Oracle(orc.FT_NONE, orc.CT_NN, bbx_magnitude=220.0)
+    S = np.array([[0.0, 0, 0], [1, 0, 0], [0, 2, 0]])
+    T = np.array([[0.0, 0, 0.5], [1, 0, 0.5], [0, 2, 0.5]])
+    o.set_keypoints(S, T)
+    st = o.iterate()
+    assert st.iteration == 0
+    # CD = scale * dist; penalty = max(CDmean, 1.0) (src/ghicp_reg.cpp:239)
+    d = np.linalg.norm(S[:, None, :] - T[None, :, :], axis=2)
+    assert np.allclose(o.cd(), float(sc) * d, rtol=0, atol=1e-12)
+    assert st.penalty == max(st.cd_mean, 1.0)
+    assert st.cor == 3 and st.converged == 1 and st.warn_few_pairs == 1  # cor < min_cor = 10
+    assert st.para1 == pytest.approx(1.0 + np.float32(0.1)) or st.para1 == pytest.approx(1.0 - np.float32(0.1)) or st.para1 == 1.0
+
+
+def test_hamming_matches_numpy(orc):
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 256, 56, dtype=np.uint8)
+    b = rng.integers(0, 256, 56, dtype=np.uint8)
+    L = orc.lib()
+    assert L.orc_hamming(a.ctypes.data, b.ctypes.data, 56) == int(np.unpackbits(a ^ b).sum())
+
+
+def test_fpfh_distance_is_abs_pearson(orc):
+    rng = np.random.default_rng(1)
+    a = (rng.random(33) * 100).astype(np.float32)
+    b = (rng.random(33) * 100).astype(np.float32)
+    d = orc.lib().orc_fpfh_distance(a.ctypes.data, b.ctypes.data)
+    ref = abs(np.corrcoef(a.astype(np.float64), b.astype(np.float64))[0, 1])
+    assert abs(d - ref) < 1e-5
+
+
+def kabsch(S, T):
+    ms, mt = S.mean(0), T.mean(0)
+    H = (T - mt).T @ (S - ms)
+    U, _, Vt = np.linalg.svd(H)
+    D = np.diag([1, 1, np.sign(np.linalg.det(U) * np.linalg.det(Vt))])
+    R = U @ D @ Vt
+    return R, mt - R @ ms
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("n,planar", [(3, False), (50, False), (5000, False), (400, True)])
+def test_rigid_fit_against_numpy_kabsch(orc, mode, n, planar):
+    from ghicp_b200.synth import rot_xyz_deg, rot_angle
+    rng = np.random.default_rng(n)
+    S = rng.random((n, 3)) * [100, 100, 0.0 if planar else 20]
+    R = rot_xyz_deg(2.0, -1.0, 4.0)
+    t = np.array([0.5, -0.25, 0.1])
+    T = S @ R.T + t + rng.normal(0, 0.01, (n, 3))
+    Rt = orc.rigid_fit(S, T, mode)
+    Rk, tk = kabsch(S, T)
+    assert rot_angle(Rt[:3, :3], Rk) < 1e-5          # float32 solve vs float64 Kabsch
+    assert np.linalg.norm(Rt[:3, 3] - tk) < 2e-3 if mode == 0 else np.linalg.norm(Rt[:3, 3] - tk) < 5e-4
+    assert abs(np.linalg.det(Rt[:3, :3]) - 1) < 1e-5
+
+
+def test_rigid_fit_reflection_case(orc):
+    """Coplanar, noisy points whose unconstrained optimum is a reflection: S(2) = -1 branch of Umeyama."""
+    rng = np.random.default_rng(3)
+    S = rng.random((30, 3)) * [10, 10, 0.0]
+    T = S.copy()
+    T[:, 2] = rng.normal(0, 1e-3, 30)
+    T[:, 0] *= 1.0
+    Rt = orc.rigid_fit(S, T, 0)
+    assert np.linalg.det(Rt[:3, :3]) > 0.999
+
+
+def test_loop_converges_to_ground_truth(orc):
+    from ghicp_b200 import synth
+    sc = synth.config1(400, 400, seed=11)
+    o = orc.Oracle(orc.FT_NONE, orc.CT_NN, bbx_magnitude=sc.bbx_magnitude, max_iter=60)
+    o.set_keypoints(sc.S, sc.T)
+    Rt, it, rc = o.run()
+    assert rc == 0 and it < 60
+    assert synth.rot_angle(Rt[:3, :3], sc.R_gt) < 2e-3
+    assert np.linalg.norm(Rt[:3, 3] - sc.t_gt) < 0.5  # plain ICP with 10 % outliers: near, not exact
