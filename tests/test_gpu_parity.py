@@ -163,7 +163,7 @@ def test_loop_nn_nnr_features(g, orc, Ft, Ct):
 
 # ---- KM -----------------------------------------------------------------------------------------------
 def test_km_golden_g1_g2(g, orc):
-    from tests.test_oracle_golden import G1_W, G2_CD
+    from golden_vectors import G1_W, G2_CD
     m, e, _ = g.km_solve(G1_W, eps=0.01, penalty=1000.0)
     assert m.tolist() == [0, 2, 1]
     G = orc.km_graph(G2_CD, 30.0)
@@ -241,4 +241,3 @@ def test_error_paths(g):
     Ef = g.Energyfunction().init(50, 40, sc.bbx_magnitude)
     with pytest.raises(g.GhicpError):
         g.GHRegistration(Kp, Ef, 1, g.CT_NN)  # RoPS: "Not passed yet" in the reference
-    reg = g.GHRegistration(Kp, Ef, g.FT_BSC, g.CT_NN.__class__(0)) if False else None

@@ -10,11 +10,7 @@ import pytest
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
-G1_W = np.array([[-5, -2, -100], [-4, -2, -6], [-100, -1, -7]], dtype=np.float64)  # src/km.cpp:237-260
-# img/GH-ICPworkflow.jpg panels (e),(f): 7 source x 6 target M_cd, T_cd = 30, E_min = 106
-G2_CD = np.array([[11, 19, 4, 40, 10, 31], [17, 10, 16, 39, 17, 36], [20, 42, 5, 28, 11, 29],
-                  [50, 21, 32, 24, 47, 32], [18, 26, 6, 7, 12, 38], [23, 36, 27, 35, 48, 30],
-                  [22, 24, 7, 21, 13, 46]], dtype=np.float64)
+from golden_vectors import G1_W, G2_CD, G2_PAIRS  # noqa: E402
 
 
 def backends(orc):
