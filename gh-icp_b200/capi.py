@@ -25,7 +25,7 @@ class Config(C.Structure):
                 ("bbx_magnitude", C.c_float), ("nonmax", C.c_float), ("adjust_ratio", C.c_float),
                 ("adjust_step", C.c_float), ("estimated_iou", C.c_float), ("converge_t", C.c_float),
                 ("converge_r", C.c_float), ("max_iter", C.c_int), ("device", C.c_int),
-                ("km_eps", C.c_double), ("verbose", C.c_int), ("reserved", C.c_int * 7)]
+                ("km_eps", C.c_double), ("verbose", C.c_int), ("force_exact", C.c_int), ("reserved", C.c_int * 6)]
 
 
 class IterStats(C.Structure):
@@ -35,7 +35,7 @@ class IterStats(C.Structure):
                 ("rmse", C.c_double), ("rmse_after", C.c_double), ("fdm", C.c_double), ("fdstd", C.c_double),
                 ("iou", C.c_double), ("para1", C.c_double), ("para2", C.c_double), ("km_energy", C.c_double),
                 ("ax", C.c_double), ("ay", C.c_double), ("az", C.c_double),
-                ("nnz", C.c_longlong), ("km_rounds", C.c_int), ("km_phases", C.c_int), ("gpu_launches", C.c_int),
+                ("nnz", C.c_longlong), ("km_rounds", C.c_int), ("km_phases", C.c_int), ("gpu_launches", C.c_int), ("exact_fallback", C.c_int),
                 ("ms_cost", C.c_float), ("ms_corr", C.c_float), ("ms_solve", C.c_float), ("ms_total", C.c_float)]
 
     def Rt_np(self):

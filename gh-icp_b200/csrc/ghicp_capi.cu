@@ -72,6 +72,10 @@ static void free_all(Ctx *c) {
   dev_free(&c->d_price); dev_free(&c->d_profit); dev_free(&c->d_assign); dev_free(&c->d_owner);
   dev_free(&c->d_bidmax); dev_free(&c->d_bidwin); dev_free(&c->d_bid_obj); dev_free(&c->d_bid_val);
   dev_free(&c->d_bid_aux); dev_free(&c->d_list[0]); dev_free(&c->d_list[1]); dev_free(&c->d_counters);
+  dev_free(&c->d_S4); dev_free(&c->d_T4); dev_free(&c->d_sdev); dev_free(&c->d_row_thr); dev_free(&c->d_col_thr);
+  dev_free(&c->d_rowbest); dev_free(&c->d_colbest); dev_free(&c->d_rowidx2); dev_free(&c->d_colidx2);
+  dev_free(&c->d_cand[0]); dev_free(&c->d_cand[1]);
+  if (c->h_sdev) { cudaFreeHost(c->h_sdev); c->h_sdev = nullptr; }
   if (c->h_iter) { cudaFreeHost(c->h_iter); c->h_iter = nullptr; }
   if (c->h_counters) { cudaFreeHost(c->h_counters); c->h_counters = nullptr; }
   if (c->h_stage) { cudaFreeHost(c->h_stage); c->h_stage = nullptr; c->h_stage_cap = 0; }
@@ -103,12 +107,30 @@ static int alloc_workspaces(Ctx *c) {
   int want = (148 * 4 + row_ctas - 1) / row_ctas;
   int lim = std::max(1, M / 2048);
   c->n_chunks = std::max(1, std::min(want, lim));
+  if (c->cfg.corr_type == GHICP_CT_KM) c->n_chunks = 1;  // the streaming path keeps one CSR segment per row
   int rc;
   const size_t L = (size_t)N * c->n_chunks;
   if ((rc = dev_alloc(c, &c->d_part_cd, L))) return rc;
   if ((rc = dev_alloc(c, &c->d_part_idx, L))) return rc;
-  c->part_stats_cap = (size_t)row_ctas * c->n_chunks * 2;
+  c->part_stats_cap = std::max((size_t)row_ctas * c->n_chunks * 2, (size_t)stream_num_parts(c) * 2);
   if ((rc = dev_alloc(c, &c->d_part_stats, c->part_stats_cap))) return rc;
+  // streaming path
+  if ((rc = dev_alloc(c, &c->d_S4, 4 * (size_t)N))) return rc;
+  if ((rc = dev_alloc(c, &c->d_T4, 4 * (size_t)M))) return rc;
+  if ((rc = dev_alloc(c, &c->d_sdev, 1))) return rc;
+  if (!c->h_sdev && cudaMallocHost((void **)&c->h_sdev, sizeof(StreamDev)) != cudaSuccess) return GHICP_E_NOMEM;
+  if ((rc = dev_alloc(c, &c->d_row_thr, (size_t)N))) return rc;
+  if ((rc = dev_alloc(c, &c->d_col_thr, (size_t)M))) return rc;
+  if ((rc = dev_alloc(c, &c->d_rowbest, (size_t)N))) return rc;
+  if ((rc = dev_alloc(c, &c->d_colbest, (size_t)M))) return rc;
+  if ((rc = dev_alloc(c, &c->d_rowidx2, (size_t)N))) return rc;
+  if ((rc = dev_alloc(c, &c->d_colidx2, (size_t)M))) return rc;
+  if (c->cfg.corr_type != GHICP_CT_KM) {
+    c->cand_cap = (int)std::min<size_t>((size_t)96 * nmax + (1u << 20), (size_t)1 << 28);
+    if ((rc = dev_alloc(c, &c->d_cand[0], (size_t)c->cand_cap))) return rc;
+    if (c->cfg.corr_type == GHICP_CT_NNR) { if ((rc = dev_alloc(c, &c->d_cand[1], (size_t)c->cand_cap))) return rc; }
+  }
+  CK(c, cudaMemset(c->d_sdev, 0, sizeof(StreamDev)));
   if ((rc = dev_alloc(c, &c->d_row_cd, (size_t)N))) return rc;
   if ((rc = dev_alloc(c, &c->d_row_idx, (size_t)N))) return rc;
   if ((rc = dev_alloc(c, &c->d_col_cd, (size_t)M))) return rc;
@@ -120,7 +142,7 @@ static int alloc_workspaces(Ctx *c) {
   if (!c->h_iter && cudaMallocHost((void **)&c->h_iter, sizeof(DevIter)) != cudaSuccess) return GHICP_E_NOMEM;
   if (!c->h_counters && cudaMallocHost((void **)&c->h_counters, sizeof(int) * 8) != cudaSuccess) return GHICP_E_NOMEM;
   if (c->cfg.corr_type == GHICP_CT_KM) {
-    if ((rc = dev_alloc(c, &c->d_cnt, L + 1))) return rc;
+    if ((rc = dev_alloc(c, &c->d_cnt, L + 2))) return rc;
     if ((rc = dev_alloc(c, &c->d_rowptr, L + 1))) return rc;
     if ((rc = dev_alloc(c, &c->d_cursor, L + 1))) return rc;
     if ((rc = dev_alloc(c, &c->d_colptr, (size_t)M + 1))) return rc;
@@ -165,8 +187,10 @@ static int build_fd(Ctx *c) {
     if (!c->have_bsc) { set_error(c, "build_fd: BSC descriptors not set"); return GHICP_E_ARG; }
     const int Vneed = (c->cfg.dof == 6) ? 4 : 2;
     if (c->V < Vneed) { set_error(c, "build_fd: not enough BSC source variants for dof"); return GHICP_E_ARG; }
+    if (c->bits > 2048) { set_error(c, "build_fd: BSC descriptors longer than 2048 bits are not supported (fp16 FD plane)"); return GHICP_E_ARG; }
     int rc = dev_alloc(c, &c->d_fd16, (size_t)c->N * c->ldM);
     if (rc) return rc;
+    CK(c, cudaMemsetAsync(c->d_fd16, 0, (size_t)c->N * c->ldM * sizeof(uint16_t), c->stream));  // zero the pitch padding
     CK(c, launch_fd_bsc(c));
   } else if (c->cfg.feature_type == GHICP_FT_FPFH) {
     if (!c->have_fpfh) { set_error(c, "build_fd: FPFH descriptors not set"); return GHICP_E_ARG; }
@@ -209,28 +233,89 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
   long long nnz = 0;
 
   CK(c, cudaEventRecord(c->ev[0], st));
-  // calED + calCD_* (+ the row scan of NN / NNR)
-  CK(c, launch_rowsweep(c, 0, cp));
-  CK(c, launch_finalize_stats(c, cp, ls));
-  CK(c, cudaEventRecord(c->ev[1], st));
-  // findcorrespondence*
-  if (c->cfg.corr_type == GHICP_CT_NN) {
-    CK(c, launch_select_nn(c));
-  } else if (c->cfg.corr_type == GHICP_CT_NNR) {
-    CK(c, launch_colsweep(c, cp));
-    CK(c, launch_select_nnr(c));
-  } else {
-    CK(c, launch_rowsweep(c, 1, cp));
-    CK(c, launch_scan_counts(c));
+  const int ft = c->cfg.feature_type, ct = c->cfg.corr_type;
+  const bool fast = c->use_fast && (ft == GHICP_FT_NONE || ft == GHICP_FT_BSC);
+  bool exact_fallback = !fast;
+  bool ev1_done = false;
+  if (fast && ct != GHICP_CT_KM) {
+    // ---- streaming path, NN / NNR: one pass = calED + calCD + row (and column) scans + statistics
+    const bool cols = (ct == GHICP_CT_NNR);
+    CK(c, launch_stream_prep(c, cp, 0));
+    CK(c, launch_stream_seed(c, cp, cols));
+    CK(c, launch_stream(c, cp, cols ? 1 : 0, true));
+    CK(c, launch_finalize_fast(c, ls));
+    CK(c, launch_stream_resolve(c, cp, cols));
+    CK(c, cudaEventRecord(c->ev[1], st));
+    ev1_done = true;
+    if (cols) CK(c, launch_select_nnr(c));
+    else CK(c, launch_select_nn(c, 1e-5));
+    CK(c, cudaMemcpyAsync(c->h_sdev, c->d_sdev, sizeof(StreamDev), cudaMemcpyDeviceToHost, st));
     CK(c, cudaMemcpyAsync(c->h_iter, c->d_iter, sizeof(DevIter), cudaMemcpyDeviceToHost, st));
     CK(c, cudaStreamSynchronize(st));
-    nnz = c->h_iter->nnz;
+    // candidate buffer overflow, or an NN gate decision inside the error band of the fast statistics:
+    // redo this iteration's cost stage with the all-double kernels (rare)
+    if (c->h_sdev->overflow || (!cols && c->h_iter->ambiguous > 0)) exact_fallback = true;
+    else c->have_prev = true;
+    c->fallbacks += exact_fallback ? 1 : 0;
+  } else if (fast) {
+    // ---- streaming path, KM: [statistics pass] + count pass + fill pass over the FD plane
+    const bool stats_first = (ft == GHICP_FT_NONE) || (c->iteration <= 1);
+    CK(c, launch_stream_prep(c, cp, 0));
+    CK(c, cudaMemsetAsync(c->d_cnt, 0, sizeof(int) * ((size_t)c->N + 2), st));
+    if (stats_first) {
+      CK(c, launch_stream(c, cp, 2, true));   // gate disabled (thr = -1): statistics only
+      CK(c, launch_finalize_fast(c, ls));
+      CK(c, launch_stream_gate(c, cp));
+      CK(c, cudaEventRecord(c->ev[1], st));
+      CK(c, launch_stream(c, cp, 2, false));
+    } else {
+      CK(c, launch_penalty_only(c, ls));      // src/ghicp_reg.cpp:279-282: independent of this iteration's CD
+      CK(c, launch_stream_gate(c, cp));
+      CK(c, launch_stream(c, cp, 2, true));
+      CK(c, launch_finalize_fast(c, ls));
+      CK(c, cudaEventRecord(c->ev[1], st));
+    }
+    ev1_done = true;
+    CK(c, launch_scan_rows(c));
+    CK(c, cudaMemcpyAsync(c->h_iter, c->d_iter, sizeof(DevIter), cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    const long long nnz_super = c->h_iter->nnz;
     const double penalty = c->h_iter->penalty;
-    if ((rc = ensure_edges(c, nnz))) return rc;
-    if (nnz > 0) CK(c, launch_rowsweep(c, 2, cp));
-    CK(c, launch_build_csc(c, c->N, c->M, nnz));
-    if ((rc = km_auction(c, c->N, c->M, nnz, c->KM_eps, std::max(penalty, c->KM_eps), &kres))) return rc;
+    if ((rc = ensure_edges(c, nnz_super))) return rc;
+    if (nnz_super > 0) {
+      CK(c, launch_stream(c, cp, 3, false));
+      CK(c, launch_csr_check(c, cp));
+    }
+    CK(c, launch_build_csc(c, c->N, c->M, nnz_super));
+    if ((rc = km_auction(c, c->N, c->M, nnz_super, c->KM_eps, std::max(penalty, c->KM_eps), &kres))) return rc;
     CK(c, launch_select_km(c));
+    CK(c, cudaMemcpyAsync(c->h_sdev, c->d_sdev, sizeof(StreamDev), cudaMemcpyDeviceToHost, st));
+    nnz = -1;  // filled from h_sdev after the final synchronize
+  }
+  if (exact_fallback) {
+    // ---- all-double path (FPFH; forced; or fallback): calED + calCD_* (+ the row scan of NN / NNR)
+    CK(c, launch_rowsweep(c, 0, cp));
+    CK(c, launch_finalize_stats(c, cp, ls));
+    if (!ev1_done) CK(c, cudaEventRecord(c->ev[1], st));
+    if (ct == GHICP_CT_NN) {
+      CK(c, launch_select_nn(c));
+    } else if (ct == GHICP_CT_NNR) {
+      CK(c, launch_colsweep(c, cp));
+      CK(c, launch_select_nnr(c));
+    } else {
+      CK(c, launch_rowsweep(c, 1, cp));
+      CK(c, launch_scan_counts(c));
+      CK(c, cudaMemcpyAsync(c->h_iter, c->d_iter, sizeof(DevIter), cudaMemcpyDeviceToHost, st));
+      CK(c, cudaStreamSynchronize(st));
+      nnz = c->h_iter->nnz;
+      const double penalty = c->h_iter->penalty;
+      if ((rc = ensure_edges(c, nnz))) return rc;
+      if (nnz > 0) CK(c, launch_rowsweep(c, 2, cp));
+      CK(c, launch_build_csc(c, c->N, c->M, nnz));
+      if ((rc = km_auction(c, c->N, c->M, nnz, c->KM_eps, std::max(penalty, c->KM_eps), &kres))) return rc;
+      CK(c, launch_select_km(c));
+    }
+    if (ct != GHICP_CT_KM) c->have_prev = true;
   }
   CK(c, cudaEventRecord(c->ev[2], st));
   // transformestimation (numeric core) + update of all source keypoints
@@ -239,6 +324,7 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
   CK(c, cudaEventRecord(c->ev[3], st));
   CK(c, cudaMemcpyAsync(c->h_iter, c->d_iter, sizeof(DevIter), cudaMemcpyDeviceToHost, st));
   CK(c, cudaStreamSynchronize(st));
+  if (nnz < 0) nnz = (long long)c->h_sdev->nnz_valid;
 
   // ---- host tail (scalars only) -----------------------------------------------------------
   const DevIter &h = *c->h_iter;
@@ -300,6 +386,7 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
     out->ax = ax; out->ay = ay; out->az = az;
     out->nnz = nnz; out->km_rounds = kres.rounds; out->km_phases = kres.phases;
     out->gpu_launches = c->launches;
+    out->exact_fallback = (fast && exact_fallback) ? 1 : 0;
     float ms;
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); out->ms_cost = ms;
     cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); out->ms_corr = ms;
@@ -351,6 +438,7 @@ int ghicp_create(const ghicp_config *cfg, ghicp_ctx **out) {
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return GHICP_E_CUDA; }
   for (auto &e : c->ev) cudaEventCreate(&e);
   reset_loop_state(c);
+  c->use_fast = (cfg->force_exact == 0);
   *out = reinterpret_cast<ghicp_ctx *>(c);
   return GHICP_OK;
 }
@@ -380,7 +468,13 @@ int ghicp_set_keypoints(ghicp_ctx *ctx, const double *sxyz, int N, const double 
     if ((rc = dev_alloc(c, &c->d_t, 3 * (size_t)M))) return rc;
     if ((rc = alloc_workspaces(c))) return rc;
     c->have_bsc = c->have_fpfh = c->fd_built = false;
+    c->have_prev = false;
     reset_loop_state(c);
+  }
+  {  // centre of the FP32 filter coordinates: target centroid
+    double cx = 0, cy = 0, cz = 0;
+    for (int j = 0; j < M; ++j) { cx += txyz[j]; cy += txyz[(size_t)M + j]; cz += txyz[2 * (size_t)M + j]; }
+    c->center[0] = cx / M; c->center[1] = cy / M; c->center[2] = cz / M;
   }
   const size_t need = 3 * ((size_t)N + M) * sizeof(double);
   if (need > c->h_stage_cap) {

@@ -37,7 +37,36 @@ struct DevIter {
   double Rt[16];        // column-major
   long long nnz;
   int solve_degenerate; // cor < 3: identity returned
-  int pad1;
+  int ambiguous;        // NN gate decisions within the fast-statistics error band of the penalty
+};
+
+// ---- streaming (fast) path ----------------------------------------------------------------------
+struct Cand {  // a pair the FP32 filter could not rule out, with its exactly evaluated CD
+  int i, j;
+  double cd;
+};
+struct StreamDev {  // device-resident scalars of the streaming path
+  unsigned r2max_bits;   // max squared centred norm of any keypoint (float bits)
+  float margin;          // bound on |cd32 - cd64|
+  float thr_hi;          // KM superset gate
+  int cand_count[2];     // row / column candidates
+  int overflow;
+  unsigned long long nnz_valid;
+};
+struct StreamArgs {
+  const unsigned short *fd;  // fp16 FD plane or nullptr (no feature)
+  size_t ldM;
+  int N, M;
+  const float4 *S4, *T4;
+  const double *s, *t;
+  double scale, WED, WFD;
+  float b;
+  StreamDev *dev;
+  unsigned *row_thr_init; unsigned long long *rowbest; int *rowidx;
+  unsigned *col_thr_init; unsigned long long *colbest; int *colidx;
+  Cand *cand[2]; int cand_cap;
+  double *part_stats;
+  int *cnt; const long long *rowptr; int *cursor; int *csr_col;
 };
 
 // ---- the context ----------------------------------------------------------------------------------
@@ -101,6 +130,20 @@ struct Ctx {
   int *d_counters = nullptr;   // [8]
   int *h_counters = nullptr;   // pinned [8]
 
+  // streaming path
+  bool use_fast = true;
+  int fallbacks = 0;         // iterations that fell back to the all-double cost kernels
+  bool have_prev = false;    // d_row_idx / d_col_idx hold last iteration's partners
+  double center[3] = {0, 0, 0};
+  float *d_S4 = nullptr, *d_T4 = nullptr;   // float4[N], float4[M]
+  StreamDev *d_sdev = nullptr;
+  StreamDev *h_sdev = nullptr;              // pinned
+  unsigned *d_row_thr = nullptr, *d_col_thr = nullptr;
+  unsigned long long *d_rowbest = nullptr, *d_colbest = nullptr;
+  int *d_rowidx2 = nullptr, *d_colidx2 = nullptr;
+  Cand *d_cand[2] = {nullptr, nullptr};
+  int cand_cap = 0;
+
   // host loop state (include/ghicp_reg.h:173-202)
   int iteration = 0;
   double RMS = 99999, FDM = 0, FDstd = 0, IoU = 0;
@@ -131,7 +174,7 @@ cudaError_t launch_fd_fpfh(Ctx *c);
 cudaError_t launch_rowsweep(Ctx *c, int mode, const CostParams &cp);
 cudaError_t launch_colsweep(Ctx *c, const CostParams &cp);
 cudaError_t launch_finalize_stats(Ctx *c, const CostParams &cp, const LoopScalars &ls);
-cudaError_t launch_select_nn(Ctx *c);    // flags from row minima + penalty, compaction → d_sp/d_tp, cor
+cudaError_t launch_select_nn(Ctx *c, double amb_rel = 0.0);    // flags from row minima + penalty, compaction → d_sp/d_tp, cor
 cudaError_t launch_select_nnr(Ctx *c);
 cudaError_t launch_select_km(Ctx *c);    // from d_owner
 cudaError_t launch_solve(Ctx *c, const CostParams &cp);  // stats + umeyama + rmse_after → d_iter
@@ -139,6 +182,18 @@ cudaError_t launch_apply(Ctx *c);
 cudaError_t launch_solve_explicit(cudaStream_t stream, const double *d_s, const double *d_t, int n, DevIter *d_iter);
 cudaError_t launch_get_fd(Ctx *c, double *d_out);
 cudaError_t launch_scan_counts(Ctx *c);  // d_cnt → d_rowptr, nnz → d_iter->nnz
+
+// ---- streaming path (ghicp_stream.cu) -----------------------------------------------------------
+cudaError_t launch_stream_prep(Ctx *c, const CostParams &cp, int for_km_gate);
+cudaError_t launch_stream_gate(Ctx *c, const CostParams &cp);
+cudaError_t launch_stream_seed(Ctx *c, const CostParams &cp, bool with_cols);
+cudaError_t launch_stream(Ctx *c, const CostParams &cp, int mode, bool stats);  // 0 NN, 1 NNR, 2 count, 3 fill
+cudaError_t launch_stream_resolve(Ctx *c, const CostParams &cp, bool with_cols);
+cudaError_t launch_finalize_fast(Ctx *c, const LoopScalars &ls);
+cudaError_t launch_penalty_only(Ctx *c, const LoopScalars &ls);
+cudaError_t launch_scan_rows(Ctx *c);
+cudaError_t launch_csr_check(Ctx *c, const CostParams &cp);
+int stream_num_parts(const Ctx *c);
 
 // ---- KM (ghicp_auction.cu) ----------------------------------------------------------------------
 // Solves max-gain partial matching on the CSR in the ctx (rows = persons). Result in d_owner/d_assign.

@@ -5,6 +5,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <cuda_fp16.h>
 
 #include "ghicp_internal.h"
 
@@ -62,6 +63,12 @@ __device__ __forceinline__ void block_sum(double (&v)[K], double *smem /* [K][TH
     }
   }
   __syncthreads();
+}
+
+// The BSC feature-distance plane stores integer Hamming distances as IEEE half bits (exact for
+// 0..2048): one HADD2.F32-class conversion per value on the streaming path instead of unpack + I2F.
+__device__ __forceinline__ double h2d(unsigned int bits16) {
+  return (double)__half2float(__ushort_as_half((unsigned short)bits16));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -147,7 +154,7 @@ __global__ void __launch_bounds__(FDB_THREADS) k_fd_bsc(const uint64_t *__restri
         int m = acc[r][0];
 #pragma unroll
         for (int v = 1; v < V; ++v) m = min(m, acc[r][v]);
-        fd[(size_t)i * ldM + j] = (uint16_t)m;
+        fd[(size_t)i * ldM + j] = __half_as_ushort(__int2half_rn(m));
       }
     }
   }
@@ -266,8 +273,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_rowsweep(const SweepArgs a) {
         double fdv[COLS_PER_THREAD];
         if (FT == GHICP_FT_BSC) {
           const uint2 q = *reinterpret_cast<const uint2 *>(a.fd16 + (size_t)(i0 + r) * a.ldM + j);
-          fdv[0] = (double)(q.x & 0xffffu); fdv[1] = (double)(q.x >> 16);
-          fdv[2] = (double)(q.y & 0xffffu); fdv[3] = (double)(q.y >> 16);
+          fdv[0] = h2d(q.x & 0xffffu); fdv[1] = h2d(q.x >> 16);
+          fdv[2] = h2d(q.y & 0xffffu); fdv[3] = h2d(q.y >> 16);
         } else if (FT == GHICP_FT_FPFH) {
           const float4 q = *reinterpret_cast<const float4 *>(a.fdf + (size_t)(i0 + r) * a.ldM + j);
           fdv[0] = (double)q.x; fdv[1] = (double)q.y; fdv[2] = (double)q.z; fdv[3] = (double)q.w;
@@ -377,10 +384,10 @@ __global__ void __launch_bounds__(COL_THREADS) k_colsweep(const ColArgs a) {
     double fdv[CT];
     if (FT == GHICP_FT_BSC) {
       const uint4 q = *reinterpret_cast<const uint4 *>(a.fd16 + (size_t)i * a.ldM + j0);
-      fdv[0] = (double)(q.x & 0xffffu); fdv[1] = (double)(q.x >> 16);
-      fdv[2] = (double)(q.y & 0xffffu); fdv[3] = (double)(q.y >> 16);
-      fdv[4] = (double)(q.z & 0xffffu); fdv[5] = (double)(q.z >> 16);
-      fdv[6] = (double)(q.w & 0xffffu); fdv[7] = (double)(q.w >> 16);
+      fdv[0] = h2d(q.x & 0xffffu); fdv[1] = h2d(q.x >> 16);
+      fdv[2] = h2d(q.y & 0xffffu); fdv[3] = h2d(q.y >> 16);
+      fdv[4] = h2d(q.z & 0xffffu); fdv[5] = h2d(q.z >> 16);
+      fdv[6] = h2d(q.w & 0xffffu); fdv[7] = h2d(q.w >> 16);
     } else if (FT == GHICP_FT_FPFH) {
       const float4 q0 = *reinterpret_cast<const float4 *>(a.fdf + (size_t)i * a.ldM + j0);
       const float4 q1 = *reinterpret_cast<const float4 *>(a.fdf + (size_t)i * a.ldM + j0 + 4);
@@ -529,9 +536,12 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int *__restrict__ cn
 __global__ void __launch_bounds__(1024) k_select(int kind, int n, const double *__restrict__ row_cd,
                                                  const int *__restrict__ row_idx, const int *__restrict__ col_idx,
                                                  const int *__restrict__ owner, int *__restrict__ sp,
-                                                 int *__restrict__ tp, DevIter *iter) {
+                                                 int *__restrict__ tp, DevIter *iter, double amb_rel) {
   __shared__ long long smem[33];
   const double penalty = iter->penalty;
+  if (threadIdx.x == 0) iter->ambiguous = 0;
+  __syncthreads();
+  const double band = amb_rel * fmax(1.0, fabs(penalty));
   const int seg = (n + 1023) / 1024;
   const int b = threadIdx.x * seg;
   const int e = min(b + seg, n);
@@ -541,7 +551,12 @@ __global__ void __launch_bounds__(1024) k_select(int kind, int n, const double *
     return owner[k] >= 0;
   };
   long long s = 0;
-  for (int k = b; k < e; ++k) s += keep(k) ? 1 : 0;
+  int amb = 0;
+  for (int k = b; k < e; ++k) {
+    s += keep(k) ? 1 : 0;
+    if (kind == 0 && amb_rel > 0.0 && fabs(row_cd[k] - penalty) <= band) ++amb;
+  }
+  if (amb) atomicAdd(&iter->ambiguous, amb);
   long long total;
   long long off = block_exclusive_scan_1024(s, smem, &total);
   for (int k = b; k < e; ++k) {
@@ -702,7 +717,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(const SolveArgs a) {
       const int i = a.sp[p], j = a.tp[p];
       sx = a.s[i]; sy = a.s[(size_t)a.N + i]; sz = a.s[2 * (size_t)a.N + i];
       tx = a.t[j]; ty = a.t[(size_t)a.M + j]; tz = a.t[2 * (size_t)a.M + j];
-      if (a.feature_type == GHICP_FT_BSC && a.fd16) fd = (double)a.fd16[(size_t)i * a.ldM + j];
+      if (a.feature_type == GHICP_FT_BSC && a.fd16) fd = h2d(a.fd16[(size_t)i * a.ldM + j]);
       else if (a.feature_type == GHICP_FT_FPFH && a.fdf) fd = (double)a.fdf[(size_t)i * a.ldM + j];
       else fd = 0.0;
     }
@@ -807,7 +822,7 @@ __global__ void k_fd_to_double(const uint16_t *__restrict__ fd16, const float *_
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)N * M) return;
   const size_t i = idx / M, j = idx % M;
-  out[idx] = fd16 ? (double)fd16[i * ldM + j] : (fdf ? (double)fdf[i * ldM + j] : 0.0);
+  out[idx] = fd16 ? h2d(fd16[i * ldM + j]) : (fdf ? (double)fdf[i * ldM + j] : 0.0);
 }
 
 template <typename F>
@@ -918,18 +933,18 @@ cudaError_t launch_scan_counts(Ctx *c) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_select_nn(Ctx *c) {
-  k_select<<<1, 1024, 0, c->stream>>>(0, c->N, c->d_row_cd, c->d_row_idx, nullptr, nullptr, c->d_sp, c->d_tp, c->d_iter);
+cudaError_t launch_select_nn(Ctx *c, double amb_rel) {
+  k_select<<<1, 1024, 0, c->stream>>>(0, c->N, c->d_row_cd, c->d_row_idx, nullptr, nullptr, c->d_sp, c->d_tp, c->d_iter, amb_rel);
   c->launches++;
   return cudaGetLastError();
 }
 cudaError_t launch_select_nnr(Ctx *c) {
-  k_select<<<1, 1024, 0, c->stream>>>(1, c->N, c->d_row_cd, c->d_row_idx, c->d_col_idx, nullptr, c->d_sp, c->d_tp, c->d_iter);
+  k_select<<<1, 1024, 0, c->stream>>>(1, c->N, c->d_row_cd, c->d_row_idx, c->d_col_idx, nullptr, c->d_sp, c->d_tp, c->d_iter, 0.0);
   c->launches++;
   return cudaGetLastError();
 }
 cudaError_t launch_select_km(Ctx *c) {
-  k_select<<<1, 1024, 0, c->stream>>>(2, c->M, nullptr, nullptr, nullptr, c->d_owner, c->d_sp, c->d_tp, c->d_iter);
+  k_select<<<1, 1024, 0, c->stream>>>(2, c->M, nullptr, nullptr, nullptr, c->d_owner, c->d_sp, c->d_tp, c->d_iter, 0.0);
   c->launches++;
   return cudaGetLastError();
 }

@@ -1,0 +1,584 @@
+// ghicp_stream.cu — the streaming cost/correspondence kernel of the GH-ICP inner loop (sm_100a).
+//
+// One pass over the N x M feature-distance plane (fp16, 2 B/pair — the only O(N*M) HBM traffic of an
+// iteration) fuses calED + calCD_* + the NN / NNR scans or the KM candidate gate
+// (src/ghicp_reg.cpp:114-139, 216-293, 348-365, 622-650, 715-733) and the CD mean / std reductions
+// (:228, 264-272).  ED and CD are never stored.
+//
+// Arithmetic: the bulk runs in FP32 as a FILTER with a rigorous error margin; every decision the
+// reference takes on doubles (row / column argmin, the CD < penalty gate) is re-evaluated in FP64 with the
+// reference's exact operation order for the few pairs the filter cannot rule out, so index results are
+// identical to the all-double evaluation (and to the oracle).  The filter evaluates
+//      d2' = A*|s - t|^2 = S.w + T.w + S.x*T.x + S.y*T.y + S.z*T.z      (3 FFMA + 1 FADD)
+// with S = (s_c, A|s_c|^2), T = (-2A t_c, A|t_c|^2), A = (scale*WED)^2, coordinates centred on the target
+// centroid, then cd32 = sqrt.approx(d2') + WFD*fd.   |cd32 - cd64| <= margin (see k_margin).
+//
+// Thread mapping: a warp owns a 256-column panel (lane = 8 consecutive columns whose T operands stay in
+// registers) and sweeps ST_RB source rows; per row a lane issues one 16-byte load of the FD plane
+// (512 contiguous bytes per warp and row).  Row minima are warp-reduced with one REDUX per row.
+#include <climits>
+#include <cuda_fp16.h>
+
+#include "ghicp_internal.h"
+
+namespace ghicp_b200 {
+
+namespace {
+
+constexpr int ST_THREADS = 256;
+constexpr int ST_WARPS = ST_THREADS / 32;
+constexpr int ST_CPL = 8;                         // columns per lane
+constexpr int ST_PANEL = 32 * ST_CPL;             // columns per warp
+constexpr int ST_CTA_COLS = ST_WARPS * ST_PANEL;  // 2048
+constexpr int ST_RB = 128;                        // source rows per CTA
+constexpr int ST_UNROLL = 4;
+constexpr unsigned INF_BITS = 0x7f800000u;
+
+enum { SM_NN = 0, SM_NNR = 1, SM_COUNT = 2, SM_FILL = 3 };
+
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ unsigned long long ord64(double v) {  // CD >= 0: bit pattern is monotone
+  return (unsigned long long)__double_as_longlong(v);
+}
+__device__ __forceinline__ float half_lo(unsigned w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xffffu))); }
+__device__ __forceinline__ float half_hi(unsigned w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
+
+// exact CD(i,j), the reference's operation order, no FMA contraction (src/ghicp_reg.cpp:122,224,259)
+__device__ __noinline__ double exact_cd(const StreamArgs &a, int i, int j) {
+  const double sx = a.s[i], sy = a.s[(size_t)a.N + i], sz = a.s[2 * (size_t)a.N + i];
+  const double tx = a.t[j], ty = a.t[(size_t)a.M + j], tz = a.t[2 * (size_t)a.M + j];
+  const double dx = __dsub_rn(sx, tx), dy = __dsub_rn(sy, ty), dz = __dsub_rn(sz, tz);
+  const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+  const double ed = __dmul_rn(a.scale, __dsqrt_rn(d2));
+  if (a.fd) {
+    const double fd = (double)__half2float(__ushort_as_half(a.fd[(size_t)i * a.ldM + j]));
+    return __dadd_rn(__dmul_rn(a.WED, ed), __dmul_rn(a.WFD, fd));
+  }
+  return ed;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-iteration operand preparation
+// ---------------------------------------------------------------------------------------------
+__global__ void k_prep(const double *__restrict__ s, const double *__restrict__ t, int N, int M, double cx,
+                       double cy, double cz, double A, float4 *__restrict__ S4, float4 *__restrict__ T4,
+                       StreamDev *dev) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  float r2 = 0.f;
+  if (k < N) {
+    const double x = s[k] - cx, y = s[(size_t)N + k] - cy, z = s[2 * (size_t)N + k] - cz;
+    const double n2 = x * x + y * y + z * z;
+    S4[k] = make_float4((float)x, (float)y, (float)z, (float)(A * n2));
+    r2 = fmaxf(r2, __double2float_ru(n2));
+  }
+  if (k < M) {
+    const double x = t[k] - cx, y = t[(size_t)M + k] - cy, z = t[2 * (size_t)M + k] - cz;
+    const double n2 = x * x + y * y + z * z;
+    T4[k] = make_float4((float)(-2.0 * A * x), (float)(-2.0 * A * y), (float)(-2.0 * A * z), (float)(A * n2));
+    r2 = fmaxf(r2, __double2float_ru(n2));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(0xffffffffu, r2, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(&dev->r2max_bits, __float_as_uint(r2));
+}
+
+// Error bound of the FP32 filter.  d2' carries <= 32*2^-24*A*R^2 absolute error (input roundings of
+// S, T + 1 add + 3 fma on magnitudes <= 4*A*R^2, R = max centred norm), so |sqrt(d2'_32) - a*dist| <=
+// sqrt(that); sqrt.approx, the fd FFMA and the float weight add 2^-21-relative terms.
+__global__ void k_margin(StreamDev *dev, double A, double a, double b, double fdmax, const DevIter *iter,
+                         int use_iter_penalty, double rel_slack) {
+  const double R2 = (double)__uint_as_float(dev->r2max_bits);
+  const double E = 32.0 * 5.9604644775390625e-08 * A * R2;
+  const double R = sqrt(R2);
+  double m = sqrt(E) * 1.001 + 9.5367431640625e-07 * (2.0 * a * R + b * fdmax) + 1e-30;
+  dev->margin = __double2float_ru(m);
+  dev->cand_count[0] = 0;
+  dev->cand_count[1] = 0;
+  dev->overflow = 0;
+  dev->nnz_valid = 0;
+  if (use_iter_penalty) {
+    // KM gate: superset threshold = penalty*(1+slack) + margin, rounded up
+    const double p = iter->penalty;
+    dev->thr_hi = __double2float_ru(p + fabs(p) * rel_slack + m);
+  } else {
+    dev->thr_hi = -1.f;
+  }
+}
+
+// Seeds of the running row / column minima: CD of last iteration's partner under the current geometry
+// is an upper bound of the new minimum (exactly evaluated, rounded up).
+__global__ void k_seed(StreamArgs a, const int *__restrict__ prev_row_idx, const int *__restrict__ prev_col_idx,
+                       int have_prev) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < a.N) {
+    unsigned bits = INF_BITS;
+    if (have_prev) {
+      int j = prev_row_idx[k];
+      if (j >= 0 && j < a.M) bits = __float_as_uint(__double2float_ru(exact_cd(a, k, j)));
+    }
+    a.row_thr_init[k] = bits;
+    a.rowbest[k] = ~0ull;
+    a.rowidx[k] = INT_MAX;
+  }
+  if (a.col_thr_init && k < a.M) {
+    unsigned bits = INF_BITS;
+    if (have_prev) {
+      int i = prev_col_idx[k];
+      if (i >= 0 && i < a.N) bits = __float_as_uint(__double2float_ru(exact_cd(a, i, k)));
+    }
+    a.col_thr_init[k] = bits;
+    a.colbest[k] = ~0ull;
+    a.colidx[k] = INT_MAX;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the streaming kernel
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void push_candidate(const StreamArgs &a, int which, int i, int j, double cd) {
+  const int slot = atomicAdd(&a.dev->cand_count[which], 1);
+  if (slot < a.cand_cap) {
+    Cand c;
+    c.i = i; c.j = j; c.cd = cd;
+    a.cand[which][slot] = c;
+  } else {
+    a.dev->overflow = 1;
+  }
+}
+
+// slow paths (rare): kept out of line so the streaming loop stays compact in the instruction cache
+__device__ __noinline__ void slow_row(const StreamArgs &a, int i, int j, float cdv, float lim) {
+  if (cdv <= lim) {
+    const double e = exact_cd(a, i, j);
+    atomicMin(&a.rowbest[i], ord64(e));
+    push_candidate(a, 0, i, j, e);
+  }
+}
+__device__ __noinline__ void slow_col(const StreamArgs &a, int i, int j, float cdv, float lim) {
+  if (cdv <= lim) {
+    const double e = exact_cd(a, i, j);
+    atomicMin(&a.colbest[j], ord64(e));
+    push_candidate(a, 1, i, j, e);
+  }
+}
+
+template <int MODE, bool HAS_FD, bool STATS, bool FULL>
+__device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, unsigned *s_thr, int *s_cnt,
+                                      int r0, int nrows, int j0, int lane, double &dsum, double &dsq) {
+  float Tx[ST_CPL], Ty[ST_CPL], Tz[ST_CPL], Tw[ST_CPL];
+  float colrun[ST_CPL];
+#pragma unroll
+  for (int c = 0; c < ST_CPL; ++c) {
+    const int j = j0 + c;
+    if (FULL || j < a.M) {
+      const float4 T = a.T4[j];
+      Tx[c] = T.x; Ty[c] = T.y; Tz[c] = T.z; Tw[c] = T.w;
+      colrun[c] = (MODE == SM_NNR) ? __uint_as_float(a.col_thr_init[j]) : 0.f;
+    } else {
+      Tx[c] = Ty[c] = Tz[c] = 0.f;
+      Tw[c] = __uint_as_float(INF_BITS);  // cd = +inf: never a minimum, never below a threshold
+      colrun[c] = -1.f;                    // never triggers the column filter
+    }
+  }
+  const float margin = a.dev->margin;
+  const float m2 = 2.f * margin;
+  const float thr_hi = a.dev->thr_hi;
+  const float b = a.b;
+  const bool lane_loads = FULL || (j0 < a.M);
+  const unsigned short *fdp = HAS_FD ? a.fd + (size_t)r0 * a.ldM + j0 : nullptr;
+
+  for (int rb = 0; rb < nrows; rb += ST_UNROLL) {
+    uint4 q[ST_UNROLL];
+    if (HAS_FD) {
+#pragma unroll
+      for (int u = 0; u < ST_UNROLL; ++u) {
+        const int r = min(rb + u, nrows - 1);
+        q[u] = lane_loads ? ldg_stream(reinterpret_cast<const uint4 *>(fdp + (size_t)r * a.ldM)) : make_uint4(0, 0, 0, 0);
+      }
+    }
+    float psum = 0.f, psq = 0.f;
+#pragma unroll
+    for (int u = 0; u < ST_UNROLL; ++u) {
+      const int r = rb + u;
+      if (r < nrows) {
+        const float4 S = s_S4[r];
+        float cd[ST_CPL];
+#pragma unroll
+        for (int c = 0; c < ST_CPL; ++c) {
+          float d2 = fmaf(S.x, Tx[c], fmaf(S.y, Ty[c], fmaf(S.z, Tz[c], Tw[c] + S.w)));
+          d2 = fmaxf(d2, 0.f);
+          const float dist = sqrt_approx(d2);
+          if (HAS_FD) {
+            const unsigned w = (c < 2) ? q[u].x : (c < 4) ? q[u].y : (c < 6) ? q[u].z : q[u].w;
+            const float fdf = (c & 1) ? half_hi(w) : half_lo(w);
+            cd[c] = fmaf(b, fdf, dist);
+          } else {
+            cd[c] = dist;
+          }
+        }
+        if (STATS) {
+#pragma unroll
+          for (int c = 0; c < ST_CPL; ++c) {
+            if (FULL || (j0 + c < a.M)) {
+              psum += cd[c];
+              psq = fmaf(cd[c], cd[c], psq);
+            }
+          }
+        }
+        if (MODE == SM_NN || MODE == SM_NNR) {
+          float m8 = fminf(fminf(fminf(cd[0], cd[1]), fminf(cd[2], cd[3])), fminf(fminf(cd[4], cd[5]), fminf(cd[6], cd[7])));
+          const unsigned wmin = __reduce_min_sync(0xffffffffu, __float_as_uint(m8));
+          const float run = __uint_as_float(s_thr[r]);
+          if (__uint_as_float(wmin) <= run + m2) {  // warp-uniform, rare once the running minimum is tight
+            const float lim = run + m2;
+#pragma unroll
+            for (int c = 0; c < ST_CPL; ++c) slow_row(a, r0 + r, j0 + c, cd[c], lim);
+            if (lane == 0) atomicMin(&s_thr[r], wmin);
+          }
+          if (MODE == SM_NNR) {
+            bool hit = false;
+#pragma unroll
+            for (int c = 0; c < ST_CPL; ++c) hit |= (cd[c] <= colrun[c] + m2);
+            if (hit) {
+#pragma unroll
+              for (int c = 0; c < ST_CPL; ++c) slow_col(a, r0 + r, j0 + c, cd[c], colrun[c] + m2);
+            }
+#pragma unroll
+            for (int c = 0; c < ST_CPL; ++c) colrun[c] = fminf(colrun[c], cd[c]);
+          }
+        } else {
+          // KM gate on the superset threshold (exactly re-checked per CSR entry afterwards)
+          int c8 = 0;
+#pragma unroll
+          for (int c = 0; c < ST_CPL; ++c) c8 += (cd[c] < thr_hi) ? 1 : 0;
+          const int total = __reduce_add_sync(0xffffffffu, c8);
+          if (total) {
+            if (MODE == SM_COUNT) {
+              if (lane == 0) atomicAdd(&s_cnt[r], total);
+            } else {
+              int base = 0;
+              if (lane == 0) base = atomicAdd(&a.cursor[r0 + r], total);
+              base = __shfl_sync(0xffffffffu, base, 0);
+              int incl = c8;
+#pragma unroll
+              for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+              }
+              long long pos = a.rowptr[r0 + r] + base + (incl - c8);
+#pragma unroll
+              for (int c = 0; c < ST_CPL; ++c)
+                if (cd[c] < thr_hi) a.csr_col[pos++] = j0 + c;
+            }
+          }
+        }
+      }
+    }
+    if (STATS) {
+      dsum += (double)psum;
+      dsq += (double)psq;
+    }
+  }
+}
+
+template <int MODE, bool HAS_FD, bool STATS>
+__global__ void __launch_bounds__(ST_THREADS, 2) k_stream(const StreamArgs a) {
+  __shared__ float4 s_S4[ST_RB];
+  __shared__ unsigned s_thr[ST_RB];
+  __shared__ int s_cnt[ST_RB];
+  __shared__ double s_red[2][ST_WARPS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r0 = blockIdx.y * ST_RB;
+  const int nrows = min(ST_RB, a.N - r0);
+  for (int r = tid; r < ST_RB; r += ST_THREADS) {
+    s_S4[r] = (r < nrows) ? a.S4[r0 + r] : make_float4(0.f, 0.f, 0.f, 0.f);
+    s_thr[r] = ((MODE == SM_NN || MODE == SM_NNR) && r < nrows) ? a.row_thr_init[r0 + r] : INF_BITS;
+    s_cnt[r] = 0;
+  }
+  __syncthreads();
+  const int panel = blockIdx.x * ST_CTA_COLS + warp * ST_PANEL;
+  const int j0 = panel + lane * ST_CPL;
+  double dsum = 0.0, dsq = 0.0;
+  if (panel < a.M) {
+    if (panel + ST_PANEL <= a.M)
+      sweep<MODE, HAS_FD, STATS, true>(a, s_S4, s_thr, s_cnt, r0, nrows, j0, lane, dsum, dsq);
+    else
+      sweep<MODE, HAS_FD, STATS, false>(a, s_S4, s_thr, s_cnt, r0, nrows, j0, lane, dsum, dsq);
+  }
+  if (STATS) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+      dsq += __shfl_xor_sync(0xffffffffu, dsq, o);
+    }
+    if (lane == 0) { s_red[0][warp] = dsum; s_red[1][warp] = dsq; }
+  }
+  __syncthreads();
+  if (STATS && tid == 0) {
+    double S1 = 0.0, S2 = 0.0;
+    for (int w = 0; w < ST_WARPS; ++w) { S1 += s_red[0][w]; S2 += s_red[1][w]; }
+    const size_t blk = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+    a.part_stats[2 * blk] = S1;
+    a.part_stats[2 * blk + 1] = S2;
+  }
+  if (MODE == SM_COUNT) {
+    for (int r = tid; r < nrows; r += ST_THREADS)
+      if (s_cnt[r]) atomicAdd(&a.cnt[r0 + r], s_cnt[r]);
+  }
+}
+
+// exact index resolution: among the candidates whose exact CD equals the row (column) minimum keep the
+// smallest index — the reference's first-minimum tie-break (src/ghicp_reg.cpp:626, 641, 719).
+__global__ void k_resolve(const StreamArgs a, int which) {
+  const int n = min(a.dev->cand_count[which], a.cand_cap);
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const Cand c = a.cand[which][k];
+    if (which == 0) {
+      if (ord64(c.cd) == a.rowbest[c.i]) atomicMin(&a.rowidx[c.i], c.j);
+    } else {
+      if (ord64(c.cd) == a.colbest[c.j]) atomicMin(&a.colidx[c.j], c.i);
+    }
+  }
+}
+__global__ void k_publish(const StreamArgs a, double *row_cd, int *row_idx, double *col_cd, int *col_idx) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < a.N) {
+    row_cd[k] = __longlong_as_double((long long)a.rowbest[k]);
+    row_idx[k] = a.rowidx[k];
+  }
+  if (col_cd && k < a.M) {
+    col_cd[k] = __longlong_as_double((long long)a.colbest[k]);
+    col_idx[k] = a.colidx[k];
+  }
+}
+
+// fast statistics → mean / std / penalty (src/ghicp_reg.cpp:228-239, 264-287)
+__global__ void __launch_bounds__(1024) k_finalize_fast(const double *__restrict__ part_stats, int n_parts, int N,
+                                                        int M, int feature_type, LoopScalars ls, DevIter *iter) {
+  __shared__ double sm[2][32];
+  double a0 = 0.0, a1 = 0.0;
+  for (int p = threadIdx.x; p < n_parts; p += blockDim.x) { a0 += part_stats[2 * p]; a1 += part_stats[2 * p + 1]; }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); }
+  if (lane == 0) { sm[0][warp] = a0; sm[1][warp] = a1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double S1 = 0.0, S2 = 0.0;
+    for (int w = 0; w < 32; ++w) { S1 += sm[0][w]; S2 += sm[1][w]; }
+    const double n = (double)N * (double)M;
+    const double CDmean = S1 / M / N;
+    double var = (S2 - S1 * S1 / n) / n;
+    if (var < 0.0) var = 0.0;
+    const double CDstd = sqrt(var);
+    double penalty;
+    if (feature_type == GHICP_FT_BSC) {
+      if (ls.iteration > 1) penalty = ls.RMS * ls.para1 * ls.scale * ls.WED + (ls.FDM + ls.para2 * ls.FDstd) * ls.WFD;
+      else penalty = (CDmean - ls.penalty_initial * CDstd);
+      penalty = fmax(penalty, 5.0);
+    } else {
+      penalty = fmax(CDmean, 1.0);
+    }
+    iter->cd_sum_shift = S1;
+    iter->cd_sumsq_shift = S2;
+    iter->cd_mean = CDmean;
+    iter->cd_std = (feature_type == GHICP_FT_BSC) ? CDstd : 0.0;
+    iter->penalty = penalty;
+  }
+}
+// BSC iterations > 1: the penalty does not depend on this iteration's statistics (src/ghicp_reg.cpp:279-282)
+__global__ void k_penalty_only(LoopScalars ls, DevIter *iter) {
+  double penalty = ls.RMS * ls.para1 * ls.scale * ls.WED + (ls.FDM + ls.para2 * ls.FDstd) * ls.WFD;
+  iter->penalty = fmax(penalty, 5.0);
+}
+
+// KM: exact re-check of every CSR entry the FP32 gate let through; gain = penalty - CD (> 0 for true
+// candidates, src/ghicp_reg.cpp:362-363); entries that fail get gain = -1e300 (ignored by the auction).
+__global__ void __launch_bounds__(256) k_csr_check(const StreamArgs a, const DevIter *iter, double *csr_gain) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const double penalty = iter->penalty;
+  int valid = 0;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < a.N; i += warps) {
+    const long long b = a.rowptr[i], e = a.rowptr[i + 1];
+    for (long long k = b + lane; k < e; k += 32) {
+      const int j = a.csr_col[k];
+      const double cd = exact_cd(a, i, j);
+      if (cd < penalty) { csr_gain[k] = penalty - cd; ++valid; }
+      else csr_gain[k] = -1e300;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(0xffffffffu, valid, o);
+  if (lane == 0 && valid) atomicAdd(&a.dev->nnz_valid, (unsigned long long)valid);
+}
+
+__global__ void __launch_bounds__(1024) k_scan_rows(const int *__restrict__ cnt, long long *__restrict__ rowptr,
+                                                    int *__restrict__ cursor, int L, DevIter *iter) {
+  __shared__ long long smem[33];
+  const int seg = (L + 1023) / 1024;
+  const int b = threadIdx.x * seg;
+  const int e = min(b + seg, L);
+  long long s = 0;
+  for (int k = b; k < e; ++k) s += cnt[k];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long x = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    long long y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) smem[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    long long w = smem[lane];
+    long long xs = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      long long y = __shfl_up_sync(0xffffffffu, xs, o);
+      if (lane >= o) xs += y;
+    }
+    smem[lane] = xs - w;
+    if (lane == 31) smem[32] = xs;
+  }
+  __syncthreads();
+  long long off = smem[warp] + x - s;
+  for (int k = b; k < e; ++k) {
+    rowptr[k] = off;
+    off += cnt[k];
+    cursor[k] = 0;
+  }
+  if (threadIdx.x == 0) { rowptr[L] = smem[32]; iter->nnz = smem[32]; }
+}
+
+}  // namespace
+
+// =============================================================================================
+static StreamArgs make_args(Ctx *c, const CostParams &cp) {
+  StreamArgs a{};
+  a.fd = (c->cfg.feature_type == GHICP_FT_BSC) ? c->d_fd16 : nullptr;
+  a.ldM = c->ldM; a.N = c->N; a.M = c->M;
+  a.S4 = reinterpret_cast<const float4 *>(c->d_S4); a.T4 = reinterpret_cast<const float4 *>(c->d_T4);
+  a.s = c->d_s; a.t = c->d_t;
+  a.scale = cp.scale; a.WED = cp.WED; a.WFD = cp.WFD;
+  a.b = (c->cfg.feature_type == GHICP_FT_BSC) ? (float)cp.WFD : 0.f;
+  a.dev = c->d_sdev;
+  a.row_thr_init = c->d_row_thr; a.rowbest = c->d_rowbest; a.rowidx = c->d_rowidx2;
+  a.col_thr_init = nullptr; a.colbest = c->d_colbest; a.colidx = c->d_colidx2;
+  a.cand[0] = c->d_cand[0]; a.cand[1] = c->d_cand[1]; a.cand_cap = c->cand_cap;
+  a.part_stats = c->d_part_stats;
+  a.cnt = c->d_cnt; a.rowptr = c->d_rowptr; a.cursor = c->d_cursor; a.csr_col = c->d_csr_col;
+  return a;
+}
+
+static dim3 stream_grid(const Ctx *c) {
+  return dim3((c->M + ST_CTA_COLS - 1) / ST_CTA_COLS, (c->N + ST_RB - 1) / ST_RB);
+}
+int stream_num_parts(const Ctx *c) {
+  dim3 g = stream_grid(c);
+  return (int)(g.x * g.y);
+}
+
+cudaError_t launch_stream_prep(Ctx *c, const CostParams &cp, int for_km_gate) {
+  const bool bsc = c->cfg.feature_type == GHICP_FT_BSC;
+  const double a = bsc ? cp.scale * cp.WED : cp.scale;
+  const double A = a * a;
+  const double b = bsc ? cp.WFD : 0.0;
+  const int n = c->N > c->M ? c->N : c->M;
+  cudaMemsetAsync(&c->d_sdev->r2max_bits, 0, sizeof(unsigned), c->stream);
+  k_prep<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_s, c->d_t, c->N, c->M, c->center[0], c->center[1], c->center[2], A,
+                                                 reinterpret_cast<float4 *>(c->d_S4), reinterpret_cast<float4 *>(c->d_T4),
+                                                 c->d_sdev);
+  k_margin<<<1, 1, 0, c->stream>>>(c->d_sdev, A, a, b, (double)c->bits, c->d_iter, for_km_gate, 1e-5);
+  c->launches += 2;
+  return cudaGetLastError();
+}
+// refresh only the KM superset threshold (penalty has been (re)computed on the device)
+cudaError_t launch_stream_gate(Ctx *c, const CostParams &cp) {
+  const bool bsc = c->cfg.feature_type == GHICP_FT_BSC;
+  const double a = bsc ? cp.scale * cp.WED : cp.scale;
+  k_margin<<<1, 1, 0, c->stream>>>(c->d_sdev, a * a, a, bsc ? cp.WFD : 0.0, (double)c->bits, c->d_iter, 1, 1e-5);
+  c->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_stream_seed(Ctx *c, const CostParams &cp, bool with_cols) {
+  StreamArgs a = make_args(c, cp);
+  if (with_cols) a.col_thr_init = c->d_col_thr;
+  const int n = c->N > c->M ? c->N : c->M;
+  k_seed<<<(n + 255) / 256, 256, 0, c->stream>>>(a, c->d_row_idx, c->d_col_idx, c->have_prev ? 1 : 0);
+  c->launches++;
+  return cudaGetLastError();
+}
+
+// mode: 0 NN, 1 NNR, 2 KM count, 3 KM fill;  stats: accumulate sum / sumsq of CD
+cudaError_t launch_stream(Ctx *c, const CostParams &cp, int mode, bool stats) {
+  StreamArgs a = make_args(c, cp);
+  if (mode == SM_NNR) a.col_thr_init = c->d_col_thr;
+  const dim3 grid = stream_grid(c);
+  const bool fd = a.fd != nullptr;
+#define LAUNCH(MODE, FD, ST) k_stream<MODE, FD, ST><<<grid, ST_THREADS, 0, c->stream>>>(a)
+#define PICK(MODE)                                      \
+  do {                                                  \
+    if (fd) { if (stats) LAUNCH(MODE, true, true); else LAUNCH(MODE, true, false); }   \
+    else    { if (stats) LAUNCH(MODE, false, true); else LAUNCH(MODE, false, false); } \
+  } while (0)
+  switch (mode) {
+    case SM_NN: PICK(SM_NN); break;
+    case SM_NNR: PICK(SM_NNR); break;
+    case SM_COUNT: PICK(SM_COUNT); break;
+    default:
+      if (fd) LAUNCH(SM_FILL, true, false); else LAUNCH(SM_FILL, false, false);
+      break;
+  }
+#undef PICK
+#undef LAUNCH
+  c->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_stream_resolve(Ctx *c, const CostParams &cp, bool with_cols) {
+  StreamArgs a = make_args(c, cp);
+  k_resolve<<<148 * 4, 256, 0, c->stream>>>(a, 0);
+  if (with_cols) k_resolve<<<148 * 4, 256, 0, c->stream>>>(a, 1);
+  const int n = c->N > c->M ? c->N : c->M;
+  k_publish<<<(n + 255) / 256, 256, 0, c->stream>>>(a, c->d_row_cd, c->d_row_idx, with_cols ? c->d_col_cd : nullptr,
+                                                    with_cols ? c->d_col_idx : nullptr);
+  c->launches += with_cols ? 3 : 2;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_finalize_fast(Ctx *c, const LoopScalars &ls) {
+  k_finalize_fast<<<1, 1024, 0, c->stream>>>(c->d_part_stats, stream_num_parts(c), c->N, c->M, c->cfg.feature_type, ls,
+                                             c->d_iter);
+  c->launches++;
+  return cudaGetLastError();
+}
+cudaError_t launch_penalty_only(Ctx *c, const LoopScalars &ls) {
+  k_penalty_only<<<1, 1, 0, c->stream>>>(ls, c->d_iter);
+  c->launches++;
+  return cudaGetLastError();
+}
+cudaError_t launch_scan_rows(Ctx *c) {
+  k_scan_rows<<<1, 1024, 0, c->stream>>>(c->d_cnt, c->d_rowptr, c->d_cursor, c->N, c->d_iter);
+  c->launches++;
+  return cudaGetLastError();
+}
+cudaError_t launch_csr_check(Ctx *c, const CostParams &cp) {
+  StreamArgs a = make_args(c, cp);
+  k_csr_check<<<148 * 4, 256, 0, c->stream>>>(a, c->d_iter, c->d_csr_gain);
+  c->launches++;
+  return cudaGetLastError();
+}
+
+}  // namespace ghicp_b200

@@ -57,7 +57,7 @@ class GHRegistration:
 
     def __init__(self, Kp, Ef, Ft, Ct, radiusNonMax=1.0, weight_adjustment_ratio=1.1,
                  weight_adjustment_step=0.1, dof_type=6, estimated_IoU=0.5,
-                 converge_tran=0.02, converge_rot=0.02, max_iter=0, device=0, km_eps=0.0):
+                 converge_tran=0.02, converge_rot=0.02, max_iter=0, device=0, km_eps=0.0, force_exact=False):
         self.L = capi.lib()
         cfg = capi.Config()
         cfg.feature_type, cfg.corr_type, cfg.dof = Ft, Ct, dof_type
@@ -67,6 +67,7 @@ class GHRegistration:
         cfg.estimated_iou = estimated_IoU
         cfg.converge_t, cfg.converge_r = converge_tran, converge_rot
         cfg.max_iter, cfg.device, cfg.km_eps = max_iter, device, km_eps
+        cfg.force_exact = 1 if force_exact else 0
         self.ctx = C.c_void_p()
         capi.check(self.L.ghicp_create(C.byref(cfg), C.byref(self.ctx)))
         self.N, self.M = Kp.kps_num, Kp.kpt_num

@@ -60,7 +60,8 @@ typedef struct ghicp_config {
   int device;           /* CUDA device ordinal */
   double km_eps;        /* 0 → Energyfunction::KM_eps = 0.01 (ghicp_reg.h:38) */
   int verbose;          /* 0 = silent (the reference prints every iteration; we do not by default) */
-  int reserved[7];
+  int force_exact;      /* 1 = all-double cost kernels only (no FP32 filter); results are identical, slower */
+  int reserved[6];
 } ghicp_config;
 
 /* Everything one loop body of GHRegistration::ghicp_reg (src/ghicp_reg.cpp:49-103) reports. */
@@ -81,6 +82,7 @@ typedef struct ghicp_iter_stats {
   int km_rounds;        /* KM: auction bidding rounds (forward + reverse) */
   int km_phases;        /* KM: epsilon-scaling phases */
   int gpu_launches;     /* kernels launched by this call */
+  int exact_fallback;   /* 1 = this iteration re-ran its cost stage with the all-double kernels */
   float ms_cost, ms_corr, ms_solve, ms_total; /* CUDA-event stage times on the ctx stream */
 } ghicp_iter_stats;
 

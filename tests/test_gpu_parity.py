@@ -161,6 +161,49 @@ def test_loop_nn_nnr_features(g, orc, Ft, Ct):
     assert np.linalg.norm(Ra[:3, 3] - Rb[:3, 3]) < TRANS_TOL
 
 
+# ---- streaming (FP32 filter + FP64 refine) path against the all-double kernels ---------------------------
+@pytest.mark.parametrize("Ft", ["none", "bsc"])
+@pytest.mark.parametrize("Ct", ["nn", "nnr"])
+def test_streaming_path_equals_all_double_path(g, Ft, Ct):
+    N, M = 5000, 4309  # ragged: partial column panels, partial row blocks
+    sc = g.synth.gen_points(N, M, overlap=0.6, extent=(90, 90, 18), noise=0.04, seed=23)
+    ft = {"none": g.FT_NONE, "bsc": g.FT_BSC}[Ft]
+    ct = {"nn": g.CT_NN, "nnr": g.CT_NNR}[Ct]
+    if Ft == "bsc":
+        g.synth.add_bsc(sc, bits=441, V=4)
+    fast = g.registration.from_scene(sc, ft, ct)
+    slow = g.registration.from_scene(sc, ft, ct, force_exact=True)
+    n_fallback = 0
+    for it in range(8):
+        a, b = fast.iterate(), slow.iterate()
+        n_fallback += a.exact_fallback
+        assert b.exact_fallback == 0
+        sp, tp = fast.pairs()
+        osp, otp = slow.pairs()
+        assert np.array_equal(sp, osp) and np.array_equal(tp, otp), f"iteration {it}"
+        assert a.cd_mean == pytest.approx(b.cd_mean, rel=2e-6)
+        assert a.penalty == pytest.approx(b.penalty, rel=1e-5)
+        assert np.array_equal(np.array(a.Rt), np.array(b.Rt))  # same pairs -> bit-identical solve
+        if a.converged:
+            break
+    assert n_fallback <= 2
+
+
+def test_streaming_path_km_candidates(g):
+    N, M = 3000, 3300
+    sc = g.synth.add_bsc(g.synth.gen_points(N, M, overlap=0.6, extent=(80, 80, 16), noise=0.04, seed=29), bits=441, V=4)
+    fast = g.registration.from_scene(sc, g.FT_BSC, g.CT_KM)
+    slow = g.registration.from_scene(sc, g.FT_BSC, g.CT_KM, force_exact=True)
+    for it in range(5):
+        a, b = fast.iterate(), slow.iterate()
+        assert a.penalty == pytest.approx(b.penalty, rel=1e-5)
+        assert abs(a.nnz - b.nnz) <= max(2, 1e-4 * b.nnz)   # gate flips only inside the statistics error band
+        assert abs(a.km_energy - b.km_energy) <= max(N, M) * 0.01 + 1e-6 * abs(b.km_energy)
+        # keep the trajectories together (eps-optimal matchings are not unique)
+        slow.set_keypoints(fast.source(), sc.T)
+        slow.set_state(a.iteration + 1, a.rmse, a.fdm, a.fdstd, a.para1, a.para2)
+
+
 # ---- KM -----------------------------------------------------------------------------------------------
 def test_km_golden_g1_g2(g, orc):
     from golden_vectors import G1_W, G2_CD
