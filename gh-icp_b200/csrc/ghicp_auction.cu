@@ -14,6 +14,7 @@
 // All tie-breaks are explicit (value, then smaller index), so the result does not depend on the
 // order in which atomics land.
 #include <climits>
+#include <cooperative_groups.h>
 #include <cstdio>
 
 #include "ghicp_internal.h"
@@ -274,6 +275,249 @@ __global__ void __launch_bounds__(AUC_BLOCK) k_rev_reset(AucArgs a, const int *l
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Persistent cooperative versions of the bidding rounds.  One launch runs a whole forward (or
+// reverse) phase: rounds with many active bidders use the whole grid with grid-wide barriers between
+// bid / resolve / commit; once the active set is small (the long price-war tail) CTA 0 runs the rounds
+// alone with __syncthreads, which removes the launch / grid-barrier latency from ~all of the rounds.
+// All mutable state is read with ld.global.cg (L2) so no stale L1 line is ever consumed.
+// ---------------------------------------------------------------------------------------------
+namespace cg = cooperative_groups;
+constexpr int PA_THREADS = 512;
+constexpr int PA_SMALL = 2048;  // active-set size below which CTA 0 iterates alone
+
+__device__ __forceinline__ int ldcg_i(const int *p) { return __ldcg(p); }
+__device__ __forceinline__ double ldcg_d(const double *p) { return __ldcg(p); }
+
+// one person bids (warp-cooperative). Returns nothing; writes bid slots / dummy assignment.
+__device__ __forceinline__ void fwd_bid_one(const AucArgs &a, int i, int lane) {
+  const long long b = a.rowptr[(size_t)i * a.n_chunks], e = a.rowptr[(size_t)(i + 1) * a.n_chunks];
+  Top2 t{-1e300, -1e300, -1};
+  double bgain = 0.0;
+  for (long long k = b + lane; k < e; k += 32) {
+    const int j = a.csr_col[k];
+    const double g = a.csr_gain[k];
+    const double v = g - ldcg_d(&a.price[j]);
+    if (v > t.best || (v == t.best && j < t.idx)) bgain = g;
+    top2_push(t, v, j);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double ob = __shfl_xor_sync(0xffffffffu, t.best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, t.idx, o);
+    double os = __shfl_xor_sync(0xffffffffu, t.second, o);
+    double og = __shfl_xor_sync(0xffffffffu, bgain, o);
+    if (oi >= 0) {
+      if (ob > t.best || (ob == t.best && oi < t.idx) || t.idx < 0) bgain = og;
+      if (t.idx < 0) { t.best = ob; t.idx = oi; t.second = os; }
+      else top2_merge(t, ob, oi, os);
+    }
+  }
+  if (lane == 0) {
+    if (t.idx < 0 || t.best <= 0.0) {
+      __stcg(&a.assign[i], DUMMY);
+      __stcg(&a.profit[i], 0.0);
+    } else {
+      const double wv = fmax(t.second, 0.0);
+      const double newprice = ldcg_d(&a.price[t.idx]) + (t.best - wv) + a.eps;
+      __stcg(&a.bid_obj[i], t.idx);
+      __stcg(&a.bid_val[i], newprice);
+      __stcg(&a.bid_aux[i], bgain);
+      atomicMax(&a.bidmax[t.idx], d2ull(newprice));
+    }
+  }
+}
+__device__ __forceinline__ void fwd_resolve_one(const AucArgs &a, int i) {
+  if (ldcg_i(&a.assign[i]) != UNASSIGNED) return;
+  const int j = ldcg_i(&a.bid_obj[i]);
+  if (d2ull(ldcg_d(&a.bid_val[i])) == __ldcg(&a.bidmax[j])) atomicMin(&a.bidwin[j], i);
+}
+// returns via append(): persons that stay / become unassigned
+template <typename Append>
+__device__ __forceinline__ void fwd_commit_one(const AucArgs &a, int i, Append append) {
+  if (ldcg_i(&a.assign[i]) != UNASSIGNED) return;
+  const int j = ldcg_i(&a.bid_obj[i]);
+  if (ldcg_i(&a.bidwin[j]) == i) {
+    const int prev = ldcg_i(&a.owner[j]);
+    const double bv = ldcg_d(&a.bid_val[i]);
+    __stcg(&a.owner[j], i);
+    __stcg(&a.price[j], bv);
+    __stcg(&a.assign[i], j);
+    __stcg(&a.profit[i], ldcg_d(&a.bid_aux[i]) - bv);
+    if (prev >= 0) { __stcg(&a.assign[prev], UNASSIGNED); append(prev); }
+  } else {
+    append(i);
+  }
+}
+__device__ __forceinline__ void fwd_reset_one(const AucArgs &a, int i) {
+  const int j = ldcg_i(&a.bid_obj[i]);
+  if (j >= 0) { __stcg(&a.bidmax[j], 0ull); __stcg(&a.bidwin[j], INT_MAX); }
+}
+
+__device__ __forceinline__ void rev_offer_one(const AucArgs &a, int j, int lane) {
+  const long long b = a.colptr[j], e = a.colptr[j + 1];
+  Top2 t{-1e300, -1e300, -1};
+  for (long long k = b + lane; k < e; k += 32) {
+    const int i = a.csc_row[k];
+    const double v = a.csc_gain[k] - ldcg_d(&a.profit[i]);
+    top2_push(t, v, i);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double ob = __shfl_xor_sync(0xffffffffu, t.best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, t.idx, o);
+    double os = __shfl_xor_sync(0xffffffffu, t.second, o);
+    if (oi >= 0) {
+      if (t.idx < 0) { t.best = ob; t.idx = oi; t.second = os; }
+      else top2_merge(t, ob, oi, os);
+    }
+  }
+  if (lane == 0) {
+    if (t.idx < 0 || t.best <= a.eps) {
+      __stcg(&a.price[j], 0.0);
+      __stcg(&a.bid_obj[j], -1);
+    } else {
+      const double delta = fmin(t.best, (t.best - t.second) + a.eps);
+      __stcg(&a.bid_obj[j], t.idx);
+      __stcg(&a.bid_val[j], delta);
+      __stcg(&a.bid_aux[j], t.best);
+      atomicMax(&a.bidmax[t.idx], d2ull(delta));
+    }
+  }
+}
+__device__ __forceinline__ void rev_resolve_one(const AucArgs &a, int j) {
+  const int i = ldcg_i(&a.bid_obj[j]);
+  if (i < 0) return;
+  if (d2ull(ldcg_d(&a.bid_val[j])) == __ldcg(&a.bidmax[i])) atomicMin(&a.bidwin[i], j);
+}
+template <typename Append>
+__device__ __forceinline__ void rev_commit_one(const AucArgs &a, int j, Append append) {
+  const int i = ldcg_i(&a.bid_obj[j]);
+  if (i < 0) return;
+  if (ldcg_i(&a.bidwin[i]) == j) {
+    const int old = ldcg_i(&a.assign[i]);
+    const double dl = ldcg_d(&a.bid_val[j]);
+    __stcg(&a.assign[i], j);
+    __stcg(&a.owner[j], i);
+    __stcg(&a.price[j], ldcg_d(&a.bid_aux[j]) - dl);
+    __stcg(&a.profit[i], ldcg_d(&a.profit[i]) + dl);
+    if (old >= 0) {
+      __stcg(&a.owner[old], -1);
+      if (ldcg_d(&a.price[old]) > 0.0) append(old);
+    }
+  } else {
+    append(j);
+  }
+}
+__device__ __forceinline__ void rev_reset_one(const AucArgs &a, int j) {
+  const int i = ldcg_i(&a.bid_obj[j]);
+  if (i >= 0) { __stcg(&a.bidmax[i], 0ull); __stcg(&a.bidwin[i], INT_MAX); }
+}
+
+// counters: [0],[1] list sizes, [2] base list size, [4] cur after the kernel, [5] rounds executed
+template <bool REVERSE>
+__global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a, int *list0, int *list1, int max_rounds) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ int s_n, s_next;
+  int *lists[2] = {list0, list1};
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int gwarps = (gridDim.x * blockDim.x) >> 5;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int gthreads = gridDim.x * blockDim.x;
+  int cur = 0, rounds = 0;
+  while (true) {
+    const int n = ldcg_i(&a.counters[cur]);
+    if (n == 0 || rounds >= max_rounds) break;
+    if (n <= PA_SMALL) {
+      // ---- tail: CTA 0 alone, block-level barriers only
+      if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) s_n = n;
+        __syncthreads();
+        while (true) {
+          const int m = s_n;
+          if (m == 0 || m > PA_SMALL || rounds >= max_rounds) break;
+          const int *list = lists[cur];
+          int *next = lists[cur ^ 1];
+          if (threadIdx.x == 0) s_next = 0;
+          for (int w = threadIdx.x >> 5; w < m; w += PA_THREADS / 32) {
+            const int e = ldcg_i(&list[w]);
+            if (REVERSE) rev_offer_one(a, e, lane); else fwd_bid_one(a, e, lane);
+          }
+          __syncthreads();
+          for (int w = threadIdx.x; w < m; w += PA_THREADS) {
+            const int e = ldcg_i(&list[w]);
+            if (REVERSE) rev_resolve_one(a, e); else fwd_resolve_one(a, e);
+          }
+          __syncthreads();
+          for (int w = threadIdx.x; w < m; w += PA_THREADS) {
+            const int e = ldcg_i(&list[w]);
+            auto app = [&](int x) { __stcg(&next[atomicAdd(&s_next, 1)], x); };
+            if (REVERSE) rev_commit_one(a, e, app); else fwd_commit_one(a, e, app);
+          }
+          __syncthreads();
+          for (int w = threadIdx.x; w < m; w += PA_THREADS) {
+            const int e = ldcg_i(&list[w]);
+            if (REVERSE) rev_reset_one(a, e); else fwd_reset_one(a, e);
+          }
+          __syncthreads();
+          cur ^= 1;
+          ++rounds;
+          if (threadIdx.x == 0) s_n = s_next;
+          __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+          __stcg(&a.counters[cur], s_n);
+          __stcg(&a.counters[4], cur);
+          __stcg(&a.counters[5], rounds);
+        }
+      }
+      __threadfence();
+      grid.sync();
+      cur = ldcg_i(&a.counters[4]);
+      rounds = ldcg_i(&a.counters[5]);
+      continue;
+    }
+    // ---- full-grid round
+    const int *list = lists[cur];
+    int *next = lists[cur ^ 1];
+    if (gtid == 0) __stcg(&a.counters[cur ^ 1], 0);
+    for (int w = gwarp; w < n; w += gwarps) {
+      const int e = ldcg_i(&list[w]);
+      if (REVERSE) rev_offer_one(a, e, lane); else fwd_bid_one(a, e, lane);
+    }
+    __threadfence();
+    grid.sync();
+    for (int w = gtid; w < n; w += gthreads) {
+      const int e = ldcg_i(&list[w]);
+      if (REVERSE) rev_resolve_one(a, e); else fwd_resolve_one(a, e);
+    }
+    __threadfence();
+    grid.sync();
+    for (int w = gtid; w < n; w += gthreads) {
+      const int e = ldcg_i(&list[w]);
+      auto app = [&](int x) { __stcg(&next[atomicAdd(&a.counters[cur ^ 1], 1)], x); };
+      if (REVERSE) rev_commit_one(a, e, app); else fwd_commit_one(a, e, app);
+    }
+    __threadfence();
+    grid.sync();
+    for (int w = gtid; w < n; w += gthreads) {
+      const int e = ldcg_i(&list[w]);
+      if (REVERSE) rev_reset_one(a, e); else fwd_reset_one(a, e);
+    }
+    __threadfence();
+    grid.sync();
+    cur ^= 1;
+    ++rounds;
+  }
+  if (gtid == 0) {
+    __stcg(&a.counters[4], cur);
+    __stcg(&a.counters[6], ldcg_i(&a.counters[6]) + rounds);  // accumulated rounds of the whole solve
+    if (ldcg_i(&a.counters[cur]) != 0) __stcg(&a.counters[3], 1);  // sticky: a phase hit the round limit
+  }
+}
+
 // ---- CSC build ---------------------------------------------------------------------------------
 __global__ void k_col_count(const int *__restrict__ csr_col, long long nnz, int *__restrict__ colcnt) {
   const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -383,59 +627,55 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
 
   int rounds = 0;
   const int max_rounds = 4000000;
+  // persistent cooperative launch geometry (all CTAs must be co-resident)
+  static int coop_blocks_per_sm[2] = {0, 0};
+  int n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device);
+  if (coop_blocks_per_sm[0] == 0) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&coop_blocks_per_sm[0], k_auction_persistent<false>, PA_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&coop_blocks_per_sm[1], k_auction_persistent<true>, PA_THREADS, 0);
+    if (coop_blocks_per_sm[0] < 1) coop_blocks_per_sm[0] = 1;
+    if (coop_blocks_per_sm[1] < 1) coop_blocks_per_sm[1] = 1;
+  }
   for (size_t ph = 0; ph < eps_list.size(); ++ph) {
     a.eps = eps_list[ph];
     k_auc_phase_start<<<gmax, 256, 0, st>>>(n_rows, n_cols, c->d_rowptr, c->n_chunks, c->d_assign, c->d_owner,
                                             c->d_profit);
     c->launches++;
-    // active list 0 = base list
     cudaMemcpyAsync(c->d_list[0], base_list, sizeof(int) * (size_t)n_rows, cudaMemcpyDeviceToDevice, st);
     cudaMemcpyAsync(&c->d_counters[0], &c->d_counters[2], sizeof(int), cudaMemcpyDeviceToDevice, st);
-    int cur = 0;
-    // ---- forward rounds
-    int check_every = 1;
-    while (true) {
-      for (int r = 0; r < check_every; ++r) {
-        k_fwd_bid<<<AUC_GRID, AUC_BLOCK, 0, st>>>(a, c->d_list[cur], cur);
-        k_fwd_resolve<<<AUC_GRID, AUC_BLOCK, 0, st>>>(a, c->d_list[cur], cur);
-        k_fwd_commit<<<AUC_GRID, AUC_BLOCK, 0, st>>>(a, c->d_list[cur], c->d_list[cur ^ 1], cur);
-        k_fwd_reset<<<AUC_GRID, AUC_BLOCK, 0, st>>>(a, c->d_list[cur], cur);
-        c->launches += 4;
-        cur ^= 1;
-        ++rounds;
-      }
-      cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, st);
-      cudaError_t e = cudaStreamSynchronize(st);
-      if (e != cudaSuccess) { set_error(c, std::string("auction forward: ") + cudaGetErrorString(e)); return GHICP_E_CUDA; }
-      if (c->h_counters[cur] == 0) break;
-      if (rounds > max_rounds) { set_error(c, "auction: round limit exceeded"); return GHICP_E_NOCONV; }
-      check_every = check_every < 8 ? check_every * 2 : 8;
+    cudaMemsetAsync(&c->d_counters[1], 0, sizeof(int), st);
+    {
+      int *l0 = c->d_list[0], *l1 = c->d_list[1];
+      int mr = max_rounds;
+      void *args[] = {(void *)&a, (void *)&l0, (void *)&l1, (void *)&mr};
+      cudaError_t e = cudaLaunchCooperativeKernel((void *)k_auction_persistent<false>, dim3(n_sm * coop_blocks_per_sm[0]),
+                                                  dim3(PA_THREADS), args, 0, st);
+      if (e != cudaSuccess) { set_error(c, std::string("auction forward launch: ") + cudaGetErrorString(e)); return GHICP_E_CUDA; }
+      c->launches++;
     }
-    // ---- reverse rounds: objects left free with a positive price
+    // reverse: objects left free with a positive price
     cudaMemsetAsync(&c->d_counters[0], 0, sizeof(int) * 2, st);
-    cur = 0;
-    k_rev_collect<<<gmax, 256, 0, st>>>(n_cols, c->d_owner, c->d_price, c->d_list[cur], c->d_counters, cur);
+    k_rev_collect<<<gmax, 256, 0, st>>>(n_cols, c->d_owner, c->d_price, c->d_list[0], c->d_counters, 0);
     c->launches++;
     cudaMemsetAsync(c->d_bid_obj, 0xff, sizeof(int) * (size_t)nmax, st);
-    check_every = 1;
-    while (true) {
-      cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, st);
-      cudaError_t e = cudaStreamSynchronize(st);
-      if (e != cudaSuccess) { set_error(c, std::string("auction reverse: ") + cudaGetErrorString(e)); return GHICP_E_CUDA; }
-      if (c->h_counters[cur] == 0) break;
-      if (rounds > max_rounds) { set_error(c, "auction: round limit exceeded"); return GHICP_E_NOCONV; }
-      for (int r = 0; r < check_every; ++r) {
-        k_rev_offer<<<AUC_GRID, AUC_BLOCK, 0, st>>>(a, c->d_list[cur], cur);
-        k_rev_resolve<<<AUC_GRID, AUC_BLOCK, 0, st>>>(a, c->d_list[cur], cur);
-        k_rev_commit<<<AUC_GRID, AUC_BLOCK, 0, st>>>(a, c->d_list[cur], c->d_list[cur ^ 1], cur);
-        k_rev_reset<<<AUC_GRID, AUC_BLOCK, 0, st>>>(a, c->d_list[cur], cur);
-        c->launches += 4;
-        cur ^= 1;
-        ++rounds;
-      }
-      check_every = check_every < 8 ? check_every * 2 : 8;
+    {
+      int *l0 = c->d_list[0], *l1 = c->d_list[1];
+      int mr = max_rounds;
+      void *args[] = {(void *)&a, (void *)&l0, (void *)&l1, (void *)&mr};
+      cudaError_t e = cudaLaunchCooperativeKernel((void *)k_auction_persistent<true>, dim3(n_sm * coop_blocks_per_sm[1]),
+                                                  dim3(PA_THREADS), args, 0, st);
+      if (e != cudaSuccess) { set_error(c, std::string("auction reverse launch: ") + cudaGetErrorString(e)); return GHICP_E_CUDA; }
+      c->launches++;
     }
     cudaMemsetAsync(c->d_bid_obj, 0xff, sizeof(int) * (size_t)nmax, st);
+  }
+  {
+    cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(int) * 8, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { set_error(c, std::string("auction: ") + cudaGetErrorString(e)); return GHICP_E_CUDA; }
+    rounds = c->h_counters[6];
+    if (c->h_counters[3] != 0) { set_error(c, "auction: round limit exceeded"); return GHICP_E_NOCONV; }
   }
   if (res) { res->rounds = rounds; res->phases = (int)eps_list.size(); }
   cudaError_t e = cudaGetLastError();

@@ -236,24 +236,36 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
   const int ft = c->cfg.feature_type, ct = c->cfg.corr_type;
   const bool fast = c->use_fast && (ft == GHICP_FT_NONE || ft == GHICP_FT_BSC);
   bool exact_fallback = !fast;
-  bool ev1_done = false;
+  bool ev1_done = false, timed_stream = false;
+  int stream_passes = 0;
   if (fast && ct != GHICP_CT_KM) {
     // ---- streaming path, NN / NNR: one pass = calED + calCD + row (and column) scans + statistics
     const bool cols = (ct == GHICP_CT_NNR);
+    // a seed pass (FP32 minima only) keeps the refinement cheap whenever last iteration's partners are not
+    // a tight bound: the first iterations (the metric mix changes fastest) or when many candidates were seen
+    const long long cand_budget = 6ll * ((long long)c->N + (cols ? c->M : 0));
+    const bool prepass = !c->have_prev || c->iteration <= 2 || c->last_cands > cand_budget;
     CK(c, launch_stream_prep(c, cp, 0));
     CK(c, launch_stream_seed(c, cp, cols));
-    CK(c, launch_stream(c, cp, cols ? 1 : 0, true));
+    if (prepass) { CK(c, launch_stream(c, cp, cols ? 5 : 4, true)); ++stream_passes; }
+    CK(c, cudaEventRecord(c->ev[4], st));
+    CK(c, launch_stream(c, cp, cols ? 1 : 0, !prepass));
+    CK(c, cudaEventRecord(c->ev[5], st));
+    ++stream_passes; timed_stream = true;
     CK(c, launch_finalize_fast(c, ls));
     CK(c, launch_stream_resolve(c, cp, cols));
     CK(c, cudaEventRecord(c->ev[1], st));
     ev1_done = true;
+    // the NN gate depends on this iteration's statistics only for Ft=None and for BSC iterations 0-1
+    const bool stats_dependent = (ft == GHICP_FT_NONE) || (c->iteration <= 1);
     if (cols) CK(c, launch_select_nnr(c));
-    else CK(c, launch_select_nn(c, 1e-5));
+    else CK(c, launch_select_nn(c, stats_dependent ? 1e-5 : 0.0));
     CK(c, cudaMemcpyAsync(c->h_sdev, c->d_sdev, sizeof(StreamDev), cudaMemcpyDeviceToHost, st));
     CK(c, cudaMemcpyAsync(c->h_iter, c->d_iter, sizeof(DevIter), cudaMemcpyDeviceToHost, st));
     CK(c, cudaStreamSynchronize(st));
     // candidate buffer overflow, or an NN gate decision inside the error band of the fast statistics:
     // redo this iteration's cost stage with the all-double kernels (rare)
+    c->last_cands = (long long)c->h_sdev->cand_count[0] + (cols ? c->h_sdev->cand_count[1] : 0);
     if (c->h_sdev->overflow || (!cols && c->h_iter->ambiguous > 0)) exact_fallback = true;
     else c->have_prev = true;
     c->fallbacks += exact_fallback ? 1 : 0;
@@ -263,18 +275,25 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
     CK(c, launch_stream_prep(c, cp, 0));
     CK(c, cudaMemsetAsync(c->d_cnt, 0, sizeof(int) * ((size_t)c->N + 2), st));
     if (stats_first) {
+      CK(c, cudaEventRecord(c->ev[4], st));
       CK(c, launch_stream(c, cp, 2, true));   // gate disabled (thr = -1): statistics only
+      CK(c, cudaEventRecord(c->ev[5], st));
       CK(c, launch_finalize_fast(c, ls));
       CK(c, launch_stream_gate(c, cp));
       CK(c, cudaEventRecord(c->ev[1], st));
       CK(c, launch_stream(c, cp, 2, false));
+      stream_passes += 2;
     } else {
       CK(c, launch_penalty_only(c, ls));      // src/ghicp_reg.cpp:279-282: independent of this iteration's CD
       CK(c, launch_stream_gate(c, cp));
+      CK(c, cudaEventRecord(c->ev[4], st));
       CK(c, launch_stream(c, cp, 2, true));
+      CK(c, cudaEventRecord(c->ev[5], st));
       CK(c, launch_finalize_fast(c, ls));
       CK(c, cudaEventRecord(c->ev[1], st));
+      stream_passes += 1;
     }
+    timed_stream = true;
     ev1_done = true;
     CK(c, launch_scan_rows(c));
     CK(c, cudaMemcpyAsync(c->h_iter, c->d_iter, sizeof(DevIter), cudaMemcpyDeviceToHost, st));
@@ -283,6 +302,7 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
     const double penalty = c->h_iter->penalty;
     if ((rc = ensure_edges(c, nnz_super))) return rc;
     if (nnz_super > 0) {
+      ++stream_passes;
       CK(c, launch_stream(c, cp, 3, false));
       CK(c, launch_csr_check(c, cp));
     }
@@ -392,6 +412,8 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
     cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); out->ms_corr = ms;
     cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]); out->ms_solve = ms;
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]); out->ms_total = ms;
+    if (timed_stream) { cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]); out->ms_stream = ms; }
+    out->stream_passes = stream_passes;
   }
   c->iteration++;
   return warnings;

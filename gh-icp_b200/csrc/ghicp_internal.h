@@ -74,7 +74,7 @@ struct Ctx {
   ghicp_config cfg{};
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::string err;
 
   int N = 0, M = 0;
@@ -132,6 +132,7 @@ struct Ctx {
 
   // streaming path
   bool use_fast = true;
+  long long last_cands = 0;  // candidates the filter passed to exact evaluation last iteration
   int fallbacks = 0;         // iterations that fell back to the all-double cost kernels
   bool have_prev = false;    // d_row_idx / d_col_idx hold last iteration's partners
   double center[3] = {0, 0, 0};

@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int *__restrict__ cn
 // kind 0: NN   keep row i iff row_cd[i] < penalty          (src/ghicp_reg.cpp:725-730)
 // kind 1: NNR  keep row i iff col_idx[row_idx[i]] == i     (src/ghicp_reg.cpp:652-662)
 // kind 2: KM   keep column j iff owner[j] >= 0; pairs ordered by target index (src/km.cpp:157-167)
-__global__ void __launch_bounds__(1024) k_select(int kind, int n, const double *__restrict__ row_cd,
+__global__ void __launch_bounds__(1024) k_select(int kind, int n, int n_cols, const double *__restrict__ row_cd,
                                                  const int *__restrict__ row_idx, const int *__restrict__ col_idx,
                                                  const int *__restrict__ owner, int *__restrict__ sp,
                                                  int *__restrict__ tp, DevIter *iter, double amb_rel) {
@@ -547,7 +547,7 @@ __global__ void __launch_bounds__(1024) k_select(int kind, int n, const double *
   const int e = min(b + seg, n);
   auto keep = [&](int k) -> bool {
     if (kind == 0) return row_cd[k] < penalty;
-    if (kind == 1) return col_idx[row_idx[k]] == k;
+    if (kind == 1) { const int j = row_idx[k]; return (j >= 0 && j < n_cols) ? (col_idx[j] == k) : false; }
     return owner[k] >= 0;
   };
   long long s = 0;
@@ -934,17 +934,17 @@ cudaError_t launch_scan_counts(Ctx *c) {
 }
 
 cudaError_t launch_select_nn(Ctx *c, double amb_rel) {
-  k_select<<<1, 1024, 0, c->stream>>>(0, c->N, c->d_row_cd, c->d_row_idx, nullptr, nullptr, c->d_sp, c->d_tp, c->d_iter, amb_rel);
+  k_select<<<1, 1024, 0, c->stream>>>(0, c->N, c->M, c->d_row_cd, c->d_row_idx, nullptr, nullptr, c->d_sp, c->d_tp, c->d_iter, amb_rel);
   c->launches++;
   return cudaGetLastError();
 }
 cudaError_t launch_select_nnr(Ctx *c) {
-  k_select<<<1, 1024, 0, c->stream>>>(1, c->N, c->d_row_cd, c->d_row_idx, c->d_col_idx, nullptr, c->d_sp, c->d_tp, c->d_iter, 0.0);
+  k_select<<<1, 1024, 0, c->stream>>>(1, c->N, c->M, c->d_row_cd, c->d_row_idx, c->d_col_idx, nullptr, c->d_sp, c->d_tp, c->d_iter, 0.0);
   c->launches++;
   return cudaGetLastError();
 }
 cudaError_t launch_select_km(Ctx *c) {
-  k_select<<<1, 1024, 0, c->stream>>>(2, c->M, nullptr, nullptr, nullptr, c->d_owner, c->d_sp, c->d_tp, c->d_iter, 0.0);
+  k_select<<<1, 1024, 0, c->stream>>>(2, c->M, c->M, nullptr, nullptr, nullptr, c->d_owner, c->d_sp, c->d_tp, c->d_iter, 0.0);
   c->launches++;
   return cudaGetLastError();
 }

@@ -34,7 +34,7 @@ constexpr int ST_RB = 128;                        // source rows per CTA
 constexpr int ST_UNROLL = 4;
 constexpr unsigned INF_BITS = 0x7f800000u;
 
-enum { SM_NN = 0, SM_NNR = 1, SM_COUNT = 2, SM_FILL = 3 };
+enum { SM_NN = 0, SM_NNR = 1, SM_COUNT = 2, SM_FILL = 3, SM_PRE = 4, SM_PRE_COLS = 5 };
 
 __device__ __forceinline__ float sqrt_approx(float x) {
   float r;
@@ -183,11 +183,11 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, u
     if (FULL || j < a.M) {
       const float4 T = a.T4[j];
       Tx[c] = T.x; Ty[c] = T.y; Tz[c] = T.z; Tw[c] = T.w;
-      colrun[c] = (MODE == SM_NNR) ? __uint_as_float(a.col_thr_init[j]) : 0.f;
+      colrun[c] = (MODE == SM_NNR || MODE == SM_PRE_COLS) ? __uint_as_float(a.col_thr_init[j]) : 0.f;
     } else {
       Tx[c] = Ty[c] = Tz[c] = 0.f;
       Tw[c] = __uint_as_float(INF_BITS);  // cd = +inf: never a minimum, never below a threshold
-      colrun[c] = -1.f;                    // never triggers the column filter
+      colrun[c] = (MODE == SM_PRE_COLS) ? __uint_as_float(INF_BITS) : -1.f;  // never triggers / never written
     }
   }
   const float margin = a.dev->margin;
@@ -235,12 +235,22 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, u
             }
           }
         }
-        if (MODE == SM_NN || MODE == SM_NNR) {
+        if (MODE == SM_PRE || MODE == SM_PRE_COLS) {
+          // seed pass: FP32 row (and column) minima only, no decisions
+          float m8 = fminf(fminf(fminf(cd[0], cd[1]), fminf(cd[2], cd[3])), fminf(fminf(cd[4], cd[5]), fminf(cd[6], cd[7])));
+          const unsigned wmin = __reduce_min_sync(0xffffffffu, __float_as_uint(m8));
+          if (lane == 0 && wmin < s_thr[r]) atomicMin(&s_thr[r], wmin);
+          if (MODE == SM_PRE_COLS) {
+#pragma unroll
+            for (int c = 0; c < ST_CPL; ++c) colrun[c] = fminf(colrun[c], cd[c]);
+          }
+        } else if (MODE == SM_NN || MODE == SM_NNR) {
           float m8 = fminf(fminf(fminf(cd[0], cd[1]), fminf(cd[2], cd[3])), fminf(fminf(cd[4], cd[5]), fminf(cd[6], cd[7])));
           const unsigned wmin = __reduce_min_sync(0xffffffffu, __float_as_uint(m8));
           const float run = __uint_as_float(s_thr[r]);
           if (__uint_as_float(wmin) <= run + m2) {  // warp-uniform, rare once the running minimum is tight
-            const float lim = run + m2;
+            // the row argmin is within 2*margin of the smallest value of ANY set that contains it
+            const float lim = fminf(run, __uint_as_float(wmin)) + m2;
 #pragma unroll
             for (int c = 0; c < ST_CPL; ++c) slow_row(a, r0 + r, j0 + c, cd[c], lim);
             if (lane == 0) atomicMin(&s_thr[r], wmin);
@@ -289,6 +299,11 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, u
       dsq += (double)psq;
     }
   }
+  if (MODE == SM_PRE_COLS) {
+#pragma unroll
+    for (int c = 0; c < ST_CPL; ++c)
+      if (FULL || (j0 + c < a.M)) atomicMin(&a.col_thr_init[j0 + c], __float_as_uint(colrun[c]));
+  }
 }
 
 template <int MODE, bool HAS_FD, bool STATS>
@@ -302,7 +317,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) k_stream(const StreamArgs a) {
   const int nrows = min(ST_RB, a.N - r0);
   for (int r = tid; r < ST_RB; r += ST_THREADS) {
     s_S4[r] = (r < nrows) ? a.S4[r0 + r] : make_float4(0.f, 0.f, 0.f, 0.f);
-    s_thr[r] = ((MODE == SM_NN || MODE == SM_NNR) && r < nrows) ? a.row_thr_init[r0 + r] : INF_BITS;
+    s_thr[r] = ((MODE == SM_NN || MODE == SM_NNR || MODE == SM_PRE || MODE == SM_PRE_COLS) && r < nrows) ? a.row_thr_init[r0 + r] : INF_BITS;
     s_cnt[r] = 0;
   }
   __syncthreads();
@@ -334,6 +349,9 @@ __global__ void __launch_bounds__(ST_THREADS, 2) k_stream(const StreamArgs a) {
   if (MODE == SM_COUNT) {
     for (int r = tid; r < nrows; r += ST_THREADS)
       if (s_cnt[r]) atomicAdd(&a.cnt[r0 + r], s_cnt[r]);
+  }
+  if (MODE == SM_PRE || MODE == SM_PRE_COLS) {
+    for (int r = tid; r < nrows; r += ST_THREADS) atomicMin(&a.row_thr_init[r0 + r], s_thr[r]);
   }
 }
 
@@ -521,10 +539,11 @@ cudaError_t launch_stream_seed(Ctx *c, const CostParams &cp, bool with_cols) {
   return cudaGetLastError();
 }
 
-// mode: 0 NN, 1 NNR, 2 KM count, 3 KM fill;  stats: accumulate sum / sumsq of CD
+// mode: 0 NN, 1 NNR, 2 KM count, 3 KM fill, 4 seed pass (rows), 5 seed pass (rows + columns);
+// stats: accumulate sum / sumsq of CD
 cudaError_t launch_stream(Ctx *c, const CostParams &cp, int mode, bool stats) {
   StreamArgs a = make_args(c, cp);
-  if (mode == SM_NNR) a.col_thr_init = c->d_col_thr;
+  if (mode == SM_NNR || mode == SM_PRE_COLS) a.col_thr_init = c->d_col_thr;
   const dim3 grid = stream_grid(c);
   const bool fd = a.fd != nullptr;
 #define LAUNCH(MODE, FD, ST) k_stream<MODE, FD, ST><<<grid, ST_THREADS, 0, c->stream>>>(a)
@@ -537,6 +556,8 @@ cudaError_t launch_stream(Ctx *c, const CostParams &cp, int mode, bool stats) {
     case SM_NN: PICK(SM_NN); break;
     case SM_NNR: PICK(SM_NNR); break;
     case SM_COUNT: PICK(SM_COUNT); break;
+    case SM_PRE: PICK(SM_PRE); break;
+    case SM_PRE_COLS: PICK(SM_PRE_COLS); break;
     default:
       if (fd) LAUNCH(SM_FILL, true, false); else LAUNCH(SM_FILL, false, false);
       break;

@@ -84,6 +84,8 @@ typedef struct ghicp_iter_stats {
   int gpu_launches;     /* kernels launched by this call */
   int exact_fallback;   /* 1 = this iteration re-ran its cost stage with the all-double kernels */
   float ms_cost, ms_corr, ms_solve, ms_total; /* CUDA-event stage times on the ctx stream */
+  float ms_stream;      /* CUDA-event time of ONE streaming pass over the FD plane (the dominant kernel) */
+  int stream_passes;    /* passes over the FD plane this iteration (1 NN/NNR, +1 seed pass, 2-3 KM) */
 } ghicp_iter_stats;
 
 typedef struct ghicp_ctx ghicp_ctx;
