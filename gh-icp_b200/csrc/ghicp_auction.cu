@@ -16,6 +16,7 @@
 #include <climits>
 #include <cooperative_groups.h>
 #include <cstdio>
+#include <cstdlib>
 
 #include "ghicp_internal.h"
 
@@ -35,6 +36,37 @@ struct Top2 {
   double best, second;
   int idx;
 };
+// Tie-break among equally valued options: a fixed pseudo-random order per bidder instead of "smallest
+// index".  With integer costs (BSC iteration 0: CD = Hamming distance) whole groups of bidders are exactly
+// indifferent between the same objects; index order would send them all to the same object and resolve
+// one bidder per round, a hashed order spreads them and resolves the group in O(log) rounds.  The order
+// is a pure function of (bidder, option), so results stay independent of thread scheduling.
+__device__ __forceinline__ unsigned tie_key(int who, int idx) {
+  unsigned h = (unsigned)idx * 0x9E3779B1u ^ ((unsigned)who * 0x85EBCA77u + 0xC2B2AE3Du);
+  h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
+  return h;
+}
+__device__ __forceinline__ bool tie_less(int who, int a, int b) {  // a before b ?
+  const unsigned ka = tie_key(who, a), kb = tie_key(who, b);
+  return ka < kb || (ka == kb && a < b);
+}
+__device__ __forceinline__ void top2_push_h(Top2 &t, double v, int idx, int who) {
+  if (v > t.best || (v == t.best && t.idx >= 0 && tie_less(who, idx, t.idx))) {
+    t.second = t.best;
+    t.best = v;
+    t.idx = idx;
+  } else if (v > t.second) {
+    t.second = v;
+  }
+}
+__device__ __forceinline__ void top2_merge_h(Top2 &a, double ob, int oi, double os, int who) {
+  if (ob > a.best || (ob == a.best && tie_less(who, oi, a.idx))) {
+    double nb2 = fmax(a.best, os);
+    a.best = ob; a.idx = oi; a.second = nb2;
+  } else {
+    a.second = fmax(a.second, ob);
+  }
+}
 __device__ __forceinline__ void top2_push(Top2 &t, double v, int idx) {
   if (v > t.best || (v == t.best && idx < t.idx)) {
     t.second = t.best;
@@ -288,6 +320,10 @@ constexpr int PA_THREADS = 512;
 constexpr int PA_SMALL = 2048;  // active-set size below which CTA 0 iterates alone
 
 __device__ __forceinline__ int ldcg_i(const int *p) { return __ldcg(p); }
+__device__ __forceinline__ unsigned long long pack_key(float v, int who) {  // v > 0
+  return ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)(who + 1);
+}
+__device__ __forceinline__ int key_who(unsigned long long k) { return (int)(unsigned)(k & 0xffffffffull) - 1; }
 __device__ __forceinline__ double ldcg_d(const double *p) { return __ldcg(p); }
 
 // one person bids (warp-cooperative). Returns nothing; writes bid slots / dummy assignment.
@@ -295,12 +331,27 @@ __device__ __forceinline__ void fwd_bid_one(const AucArgs &a, int i, int lane) {
   const long long b = a.rowptr[(size_t)i * a.n_chunks], e = a.rowptr[(size_t)(i + 1) * a.n_chunks];
   Top2 t{-1e300, -1e300, -1};
   double bgain = 0.0;
-  for (long long k = b + lane; k < e; k += 32) {
+  long long k = b + lane;
+  // 4 independent edge loads in flight per lane (the tail rounds are latency-bound)
+  for (; k + 96 < e; k += 128) {
+    int j[4]; double g[4], p[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { j[u] = a.csr_col[k + 32 * u]; g[u] = a.csr_gain[k + 32 * u]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) p[u] = ldcg_d(&a.price[j[u]]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const double v = g[u] - p[u];
+      if (v > t.best || (v == t.best && t.idx >= 0 && tie_less(i, j[u], t.idx))) bgain = g[u];
+      top2_push_h(t, v, j[u], i);
+    }
+  }
+  for (; k < e; k += 32) {
     const int j = a.csr_col[k];
     const double g = a.csr_gain[k];
     const double v = g - ldcg_d(&a.price[j]);
-    if (v > t.best || (v == t.best && j < t.idx)) bgain = g;
-    top2_push(t, v, j);
+    if (v > t.best || (v == t.best && t.idx >= 0 && tie_less(i, j, t.idx))) bgain = g;
+    top2_push_h(t, v, j, i);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -309,9 +360,11 @@ __device__ __forceinline__ void fwd_bid_one(const AucArgs &a, int i, int lane) {
     double os = __shfl_xor_sync(0xffffffffu, t.second, o);
     double og = __shfl_xor_sync(0xffffffffu, bgain, o);
     if (oi >= 0) {
-      if (ob > t.best || (ob == t.best && oi < t.idx) || t.idx < 0) bgain = og;
-      if (t.idx < 0) { t.best = ob; t.idx = oi; t.second = os; }
-      else top2_merge(t, ob, oi, os);
+      if (t.idx < 0) { t.best = ob; t.idx = oi; t.second = os; bgain = og; }
+      else {
+        if (ob > t.best || (ob == t.best && tie_less(i, oi, t.idx))) bgain = og;
+        top2_merge_h(t, ob, oi, os, i);
+      }
     }
   }
   if (lane == 0) {
@@ -324,7 +377,10 @@ __device__ __forceinline__ void fwd_bid_one(const AucArgs &a, int i, int lane) {
       __stcg(&a.bid_obj[i], t.idx);
       __stcg(&a.bid_val[i], newprice);
       __stcg(&a.bid_aux[i], bgain);
-      atomicMax(&a.bidmax[t.idx], d2ull(newprice));
+      // One atomic decides the round's winner: the key orders bidders by their bid rounded to float32, then
+      // by id.  ANY bidder may win a round as long as the price becomes its own (exact, double) bid: that is
+      // a valid auction step (price rises by >= eps, the winner is eps-happy), so float32 ordering is enough.
+      atomicMax(&a.bidmax[t.idx], pack_key((float)newprice, i));
     }
   }
 }
@@ -338,7 +394,7 @@ template <typename Append>
 __device__ __forceinline__ void fwd_commit_one(const AucArgs &a, int i, Append append) {
   if (ldcg_i(&a.assign[i]) != UNASSIGNED) return;
   const int j = ldcg_i(&a.bid_obj[i]);
-  if (ldcg_i(&a.bidwin[j]) == i) {
+  if (key_who(__ldcg(&a.bidmax[j])) == i) {
     const int prev = ldcg_i(&a.owner[j]);
     const double bv = ldcg_d(&a.bid_val[i]);
     __stcg(&a.owner[j], i);
@@ -352,7 +408,7 @@ __device__ __forceinline__ void fwd_commit_one(const AucArgs &a, int i, Append a
 }
 __device__ __forceinline__ void fwd_reset_one(const AucArgs &a, int i) {
   const int j = ldcg_i(&a.bid_obj[i]);
-  if (j >= 0) { __stcg(&a.bidmax[j], 0ull); __stcg(&a.bidwin[j], INT_MAX); }
+  if (j >= 0) __stcg(&a.bidmax[j], 0ull);
 }
 
 __device__ __forceinline__ void rev_offer_one(const AucArgs &a, int j, int lane) {
@@ -361,7 +417,7 @@ __device__ __forceinline__ void rev_offer_one(const AucArgs &a, int j, int lane)
   for (long long k = b + lane; k < e; k += 32) {
     const int i = a.csc_row[k];
     const double v = a.csc_gain[k] - ldcg_d(&a.profit[i]);
-    top2_push(t, v, i);
+    top2_push_h(t, v, i, j);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -370,7 +426,7 @@ __device__ __forceinline__ void rev_offer_one(const AucArgs &a, int j, int lane)
     double os = __shfl_xor_sync(0xffffffffu, t.second, o);
     if (oi >= 0) {
       if (t.idx < 0) { t.best = ob; t.idx = oi; t.second = os; }
-      else top2_merge(t, ob, oi, os);
+      else top2_merge_h(t, ob, oi, os, j);
     }
   }
   if (lane == 0) {
@@ -382,7 +438,7 @@ __device__ __forceinline__ void rev_offer_one(const AucArgs &a, int j, int lane)
       __stcg(&a.bid_obj[j], t.idx);
       __stcg(&a.bid_val[j], delta);
       __stcg(&a.bid_aux[j], t.best);
-      atomicMax(&a.bidmax[t.idx], d2ull(delta));
+      atomicMax(&a.bidmax[t.idx], pack_key((float)delta, j));
     }
   }
 }
@@ -395,7 +451,7 @@ template <typename Append>
 __device__ __forceinline__ void rev_commit_one(const AucArgs &a, int j, Append append) {
   const int i = ldcg_i(&a.bid_obj[j]);
   if (i < 0) return;
-  if (ldcg_i(&a.bidwin[i]) == j) {
+  if (key_who(__ldcg(&a.bidmax[i])) == j) {
     const int old = ldcg_i(&a.assign[i]);
     const double dl = ldcg_d(&a.bid_val[j]);
     __stcg(&a.assign[i], j);
@@ -412,12 +468,13 @@ __device__ __forceinline__ void rev_commit_one(const AucArgs &a, int j, Append a
 }
 __device__ __forceinline__ void rev_reset_one(const AucArgs &a, int j) {
   const int i = ldcg_i(&a.bid_obj[j]);
-  if (i >= 0) { __stcg(&a.bidmax[i], 0ull); __stcg(&a.bidwin[i], INT_MAX); }
+  if (i >= 0) __stcg(&a.bidmax[i], 0ull);
 }
 
 // counters: [0],[1] list sizes, [2] base list size, [4] cur after the kernel, [5] rounds executed
 template <bool REVERSE>
-__global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a, int *list0, int *list1, int max_rounds) {
+__global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a, int *list0, int *list1, int max_rounds,
+                                                                      int small_n) {
   cg::grid_group grid = cg::this_grid();
   __shared__ int s_n, s_next;
   int *lists[2] = {list0, list1};
@@ -430,25 +487,20 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
   while (true) {
     const int n = ldcg_i(&a.counters[cur]);
     if (n == 0 || rounds >= max_rounds) break;
-    if (n <= PA_SMALL) {
+    if (n <= small_n) {
       // ---- tail: CTA 0 alone, block-level barriers only
       if (blockIdx.x == 0) {
         if (threadIdx.x == 0) s_n = n;
         __syncthreads();
         while (true) {
           const int m = s_n;
-          if (m == 0 || m > PA_SMALL || rounds >= max_rounds) break;
+          if (m == 0 || m > small_n || rounds >= max_rounds) break;
           const int *list = lists[cur];
           int *next = lists[cur ^ 1];
           if (threadIdx.x == 0) s_next = 0;
           for (int w = threadIdx.x >> 5; w < m; w += PA_THREADS / 32) {
             const int e = ldcg_i(&list[w]);
             if (REVERSE) rev_offer_one(a, e, lane); else fwd_bid_one(a, e, lane);
-          }
-          __syncthreads();
-          for (int w = threadIdx.x; w < m; w += PA_THREADS) {
-            const int e = ldcg_i(&list[w]);
-            if (REVERSE) rev_resolve_one(a, e); else fwd_resolve_one(a, e);
           }
           __syncthreads();
           for (int w = threadIdx.x; w < m; w += PA_THREADS) {
@@ -486,12 +538,6 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
     for (int w = gwarp; w < n; w += gwarps) {
       const int e = ldcg_i(&list[w]);
       if (REVERSE) rev_offer_one(a, e, lane); else fwd_bid_one(a, e, lane);
-    }
-    __threadfence();
-    grid.sync();
-    for (int w = gtid; w < n; w += gthreads) {
-      const int e = ldcg_i(&list[w]);
-      if (REVERSE) rev_resolve_one(a, e); else fwd_resolve_one(a, e);
     }
     __threadfence();
     grid.sync();
@@ -637,6 +683,15 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
     if (coop_blocks_per_sm[0] < 1) coop_blocks_per_sm[0] = 1;
     if (coop_blocks_per_sm[1] < 1) coop_blocks_per_sm[1] = 1;
   }
+  // CTA 0 takes over the rounds alone once the expected work of a round (active bidders x average
+  // adjacency length) is small enough that grid-wide barriers would dominate
+  const double avg_row = (double)nnz / (n_rows > 0 ? n_rows : 1), avg_col = (double)nnz / (n_cols > 0 ? n_cols : 1);
+  int small_fwd = (int)(16384.0 / (avg_row > 1.0 ? avg_row : 1.0));
+  int small_rev = (int)(16384.0 / (avg_col > 1.0 ? avg_col : 1.0));
+  small_fwd = small_fwd < 16 ? 16 : (small_fwd > PA_SMALL ? PA_SMALL : small_fwd);
+  small_rev = small_rev < 16 ? 16 : (small_rev > PA_SMALL ? PA_SMALL : small_rev);
+  const bool debug = getenv("GHICP_AUCTION_DEBUG") != nullptr;
+  int last_rounds = 0;
   for (size_t ph = 0; ph < eps_list.size(); ++ph) {
     a.eps = eps_list[ph];
     k_auc_phase_start<<<gmax, 256, 0, st>>>(n_rows, n_cols, c->d_rowptr, c->n_chunks, c->d_assign, c->d_owner,
@@ -648,7 +703,8 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
     {
       int *l0 = c->d_list[0], *l1 = c->d_list[1];
       int mr = max_rounds;
-      void *args[] = {(void *)&a, (void *)&l0, (void *)&l1, (void *)&mr};
+      int sn = small_fwd;
+      void *args[] = {(void *)&a, (void *)&l0, (void *)&l1, (void *)&mr, (void *)&sn};
       cudaError_t e = cudaLaunchCooperativeKernel((void *)k_auction_persistent<false>, dim3(n_sm * coop_blocks_per_sm[0]),
                                                   dim3(PA_THREADS), args, 0, st);
       if (e != cudaSuccess) { set_error(c, std::string("auction forward launch: ") + cudaGetErrorString(e)); return GHICP_E_CUDA; }
@@ -662,13 +718,21 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
     {
       int *l0 = c->d_list[0], *l1 = c->d_list[1];
       int mr = max_rounds;
-      void *args[] = {(void *)&a, (void *)&l0, (void *)&l1, (void *)&mr};
+      int sn = small_rev;
+      void *args[] = {(void *)&a, (void *)&l0, (void *)&l1, (void *)&mr, (void *)&sn};
       cudaError_t e = cudaLaunchCooperativeKernel((void *)k_auction_persistent<true>, dim3(n_sm * coop_blocks_per_sm[1]),
                                                   dim3(PA_THREADS), args, 0, st);
       if (e != cudaSuccess) { set_error(c, std::string("auction reverse launch: ") + cudaGetErrorString(e)); return GHICP_E_CUDA; }
       c->launches++;
     }
     cudaMemsetAsync(c->d_bid_obj, 0xff, sizeof(int) * (size_t)nmax, st);
+    if (debug) {
+      cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(int) * 8, cudaMemcpyDeviceToHost, st);
+      cudaStreamSynchronize(st);
+      fprintf(stderr, "[auction] phase %zu eps %.5f rounds %d (cum %d) small_fwd %d small_rev %d\n", ph, a.eps,
+              c->h_counters[6] - last_rounds, c->h_counters[6], small_fwd, small_rev);
+      last_rounds = c->h_counters[6];
+    }
   }
   {
     cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(int) * 8, cudaMemcpyDeviceToHost, st);
