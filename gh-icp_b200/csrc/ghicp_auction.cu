@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
           if (m == 0 || m > small_n || rounds >= max_rounds) break;
           const int *list = lists[cur];
           int *next = lists[cur ^ 1];
-          if (threadIdx.x == 0) s_next = 0;
+          if (threadIdx.x == 0) { s_next = 0; atomicAdd((unsigned long long *)&a.counters[8], (unsigned long long)m); }
           for (int w = threadIdx.x >> 5; w < m; w += PA_THREADS / 32) {
             const int e = ldcg_i(&list[w]);
             if (REVERSE) rev_offer_one(a, e, lane); else fwd_bid_one(a, e, lane);
@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
     // ---- full-grid round
     const int *list = lists[cur];
     int *next = lists[cur ^ 1];
-    if (gtid == 0) __stcg(&a.counters[cur ^ 1], 0);
+    if (gtid == 0) { __stcg(&a.counters[cur ^ 1], 0); atomicAdd((unsigned long long *)&a.counters[8], (unsigned long long)n); __stcg(&a.counters[10], ldcg_i(&a.counters[10]) + 1); }
     for (int w = gwarp; w < n; w += gwarps) {
       const int e = ldcg_i(&list[w]);
       if (REVERSE) rev_offer_one(a, e, lane); else fwd_bid_one(a, e, lane);
@@ -656,7 +656,7 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
   const int gmax = (nmax + 255) / 256;
   int *base_list = c->d_flags;  // free during KM
 
-  cudaMemsetAsync(c->d_counters, 0, sizeof(int) * 8, st);
+  cudaMemsetAsync(c->d_counters, 0, sizeof(int) * 16, st);
   k_auc_init<<<gmax, 256, 0, st>>>(n_rows, n_cols, c->d_rowptr, c->n_chunks, c->d_price, base_list, c->d_counters,
                                    c->d_bidmax, c->d_bidwin, nmax);
   c->launches++;
@@ -727,10 +727,11 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
     }
     cudaMemsetAsync(c->d_bid_obj, 0xff, sizeof(int) * (size_t)nmax, st);
     if (debug) {
-      cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(int) * 8, cudaMemcpyDeviceToHost, st);
+      cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(int) * 16, cudaMemcpyDeviceToHost, st);
       cudaStreamSynchronize(st);
-      fprintf(stderr, "[auction] phase %zu eps %.5f rounds %d (cum %d) small_fwd %d small_rev %d\n", ph, a.eps,
-              c->h_counters[6] - last_rounds, c->h_counters[6], small_fwd, small_rev);
+      fprintf(stderr, "[auction] phase %zu eps %.5f rounds %d (cum %d, grid rounds %d) bids(cum) %llu small_fwd %d\n", ph, a.eps,
+              c->h_counters[6] - last_rounds, c->h_counters[6], c->h_counters[10],
+              *(unsigned long long *)&c->h_counters[8], small_fwd);
       last_rounds = c->h_counters[6];
     }
   }

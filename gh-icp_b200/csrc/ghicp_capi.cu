@@ -140,7 +140,7 @@ static int alloc_workspaces(Ctx *c) {
   if ((rc = dev_alloc(c, &c->d_tp, (size_t)nmax))) return rc;
   if ((rc = dev_alloc(c, &c->d_iter, 1))) return rc;
   if (!c->h_iter && cudaMallocHost((void **)&c->h_iter, sizeof(DevIter)) != cudaSuccess) return GHICP_E_NOMEM;
-  if (!c->h_counters && cudaMallocHost((void **)&c->h_counters, sizeof(int) * 8) != cudaSuccess) return GHICP_E_NOMEM;
+  if (!c->h_counters && cudaMallocHost((void **)&c->h_counters, sizeof(int) * 16) != cudaSuccess) return GHICP_E_NOMEM;
   if (c->cfg.corr_type == GHICP_CT_KM) {
     if ((rc = dev_alloc(c, &c->d_cnt, L + 2))) return rc;
     if ((rc = dev_alloc(c, &c->d_rowptr, L + 1))) return rc;
@@ -158,7 +158,7 @@ static int alloc_workspaces(Ctx *c) {
     if ((rc = dev_alloc(c, &c->d_bid_aux, (size_t)nmax))) return rc;
     if ((rc = dev_alloc(c, &c->d_list[0], (size_t)nmax))) return rc;
     if ((rc = dev_alloc(c, &c->d_list[1], (size_t)nmax))) return rc;
-    if ((rc = dev_alloc(c, &c->d_counters, 8))) return rc;
+    if ((rc = dev_alloc(c, &c->d_counters, 16))) return rc;
   }
   return GHICP_OK;
 }

@@ -17,6 +17,7 @@
 // registers) and sweeps ST_RB source rows; per row a lane issues one 16-byte load of the FD plane
 // (512 contiguous bytes per warp and row).  Row minima are warp-reduced with one REDUX per row.
 #include <climits>
+#include <cstdlib>
 #include <cuda_fp16.h>
 
 #include "ghicp_internal.h"
@@ -30,9 +31,36 @@ constexpr int ST_WARPS = ST_THREADS / 32;
 constexpr int ST_CPL = 8;                         // columns per lane
 constexpr int ST_PANEL = 32 * ST_CPL;             // columns per warp
 constexpr int ST_CTA_COLS = ST_WARPS * ST_PANEL;  // 2048
-constexpr int ST_RB = 128;                        // source rows per CTA
+constexpr int ST_RB = 256;                        // source rows per CTA
 constexpr int ST_UNROLL = 4;
 constexpr unsigned INF_BITS = 0x7f800000u;
+// TMA staging of the FD plane: every warp runs its own ring of ST_STAGES stages; a stage holds ST_UNROLL
+// row segments of the warp's 256-column panel (512 B each), brought in by cp.async.bulk (TMA engine,
+// UBLKCP) and signalled on one mbarrier per stage.  No registers are tied up by loads in flight.
+constexpr int ST_STAGES = 6;
+constexpr int ST_SEG_BYTES = ST_PANEL * 2;                   // 512
+constexpr int ST_STAGE_BYTES = ST_UNROLL * ST_SEG_BYTES;     // 2048
+constexpr int ST_RING_BYTES = ST_STAGES * ST_STAGE_BYTES;    // per warp
+constexpr int ST_DYN_SMEM = ST_WARPS * ST_RING_BYTES;
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 enum { SM_NN = 0, SM_NNR = 1, SM_COUNT = 2, SM_FILL = 3, SM_PRE = 4, SM_PRE_COLS = 5 };
 
@@ -172,9 +200,10 @@ __device__ __noinline__ void slow_col(const StreamArgs &a, int i, int j, float c
   }
 }
 
-template <int MODE, bool HAS_FD, bool STATS, bool FULL>
+template <int MODE, bool HAS_FD, bool STATS, bool FULL, bool TMA>
 __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, unsigned *s_thr, int *s_cnt,
-                                      int r0, int nrows, int j0, int lane, double &dsum, double &dsq) {
+                                      int r0, int nrows, int j0, int lane, double &dsum, double &dsq,
+                                      unsigned char *ring, unsigned long long *bars) {
   float Tx[ST_CPL], Ty[ST_CPL], Tz[ST_CPL], Tw[ST_CPL];
   float colrun[ST_CPL];
 #pragma unroll
@@ -196,10 +225,40 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, u
   const float b = a.b;
   const bool lane_loads = FULL || (j0 < a.M);
   const unsigned short *fdp = HAS_FD ? a.fd + (size_t)r0 * a.ldM + j0 : nullptr;
+  // ---- TMA ring bookkeeping (warp-private) ----
+  const int panel = j0 - lane * ST_CPL;
+  const unsigned seg_bytes = (HAS_FD && TMA) ? (unsigned)min((size_t)ST_SEG_BYTES, (a.ldM - (size_t)panel) * 2) : 0u;
+  const unsigned short *panel_base = (HAS_FD && TMA) ? a.fd + (size_t)r0 * a.ldM + panel : nullptr;
+  const int nbatch = (nrows + ST_UNROLL - 1) / ST_UNROLL;
+  auto issue = [&](int k) {  // lane 0 only
+    const int stage = k % ST_STAGES;
+    const int rows = min(ST_UNROLL, nrows - k * ST_UNROLL);
+    mbar_expect_tx(&bars[stage], (unsigned)rows * seg_bytes);
+    for (int u = 0; u < rows; ++u)
+      bulk_g2s(ring + stage * ST_STAGE_BYTES + u * ST_SEG_BYTES, panel_base + (size_t)(k * ST_UNROLL + u) * a.ldM, seg_bytes,
+               &bars[stage]);
+  };
+  if (HAS_FD && TMA) {
+    if (lane == 0)
+      for (int k = 0; k < min(ST_STAGES, nbatch); ++k) issue(k);
+  }
 
   for (int rb = 0; rb < nrows; rb += ST_UNROLL) {
     uint4 q[ST_UNROLL];
-    if (HAS_FD) {
+    if (HAS_FD && TMA) {
+      const int k = rb / ST_UNROLL;
+      const int stage = k % ST_STAGES;
+      mbar_wait(&bars[stage], (unsigned)((k / ST_STAGES) & 1));
+#pragma unroll
+      for (int u = 0; u < ST_UNROLL; ++u)
+        q[u] = *reinterpret_cast<const uint4 *>(ring + stage * ST_STAGE_BYTES + u * ST_SEG_BYTES + lane * 16);
+      // the values are in registers: hand the stage back to the TMA engine for batch k + ST_STAGES
+      __syncwarp();
+      if (lane == 0 && k + ST_STAGES < nbatch) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(k + ST_STAGES);
+      }
+    } else if (HAS_FD) {
 #pragma unroll
       for (int u = 0; u < ST_UNROLL; ++u) {
         const int r = min(rb + u, nrows - 1);
@@ -306,8 +365,10 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, u
   }
 }
 
-template <int MODE, bool HAS_FD, bool STATS>
+template <int MODE, bool HAS_FD, bool STATS, bool TMA>
 __global__ void __launch_bounds__(ST_THREADS, 2) k_stream(const StreamArgs a) {
+  extern __shared__ __align__(128) unsigned char s_ring[];   // [ST_WARPS][ST_RING_BYTES] when TMA
+  __shared__ __align__(8) unsigned long long s_bar[ST_WARPS][ST_STAGES];
   __shared__ float4 s_S4[ST_RB];
   __shared__ unsigned s_thr[ST_RB];
   __shared__ int s_cnt[ST_RB];
@@ -320,15 +381,20 @@ __global__ void __launch_bounds__(ST_THREADS, 2) k_stream(const StreamArgs a) {
     s_thr[r] = ((MODE == SM_NN || MODE == SM_NNR || MODE == SM_PRE || MODE == SM_PRE_COLS) && r < nrows) ? a.row_thr_init[r0 + r] : INF_BITS;
     s_cnt[r] = 0;
   }
+  if (TMA && lane == 0) {
+    for (int st = 0; st < ST_STAGES; ++st) mbar_init(&s_bar[warp][st], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
+  unsigned char *ring = TMA ? s_ring + warp * ST_RING_BYTES : nullptr;
   const int panel = blockIdx.x * ST_CTA_COLS + warp * ST_PANEL;
   const int j0 = panel + lane * ST_CPL;
   double dsum = 0.0, dsq = 0.0;
   if (panel < a.M) {
     if (panel + ST_PANEL <= a.M)
-      sweep<MODE, HAS_FD, STATS, true>(a, s_S4, s_thr, s_cnt, r0, nrows, j0, lane, dsum, dsq);
+      sweep<MODE, HAS_FD, STATS, true, TMA>(a, s_S4, s_thr, s_cnt, r0, nrows, j0, lane, dsum, dsq, ring, s_bar[warp]);
     else
-      sweep<MODE, HAS_FD, STATS, false>(a, s_S4, s_thr, s_cnt, r0, nrows, j0, lane, dsum, dsq);
+      sweep<MODE, HAS_FD, STATS, false, TMA>(a, s_S4, s_thr, s_cnt, r0, nrows, j0, lane, dsum, dsq, ring, s_bar[warp]);
   }
   if (STATS) {
 #pragma unroll
@@ -546,7 +612,16 @@ cudaError_t launch_stream(Ctx *c, const CostParams &cp, int mode, bool stats) {
   if (mode == SM_NNR || mode == SM_PRE_COLS) a.col_thr_init = c->d_col_thr;
   const dim3 grid = stream_grid(c);
   const bool fd = a.fd != nullptr;
-#define LAUNCH(MODE, FD, ST) k_stream<MODE, FD, ST><<<grid, ST_THREADS, 0, c->stream>>>(a)
+  static const bool use_tma = getenv("GHICP_STREAM_LDG") == nullptr;
+#define LAUNCH(MODE, FD, ST)                                                                                   \
+  do {                                                                                                         \
+    if (FD && use_tma) {                                                                                       \
+      cudaFuncSetAttribute(k_stream<MODE, FD, ST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_DYN_SMEM); \
+      k_stream<MODE, FD, ST, true><<<grid, ST_THREADS, ST_DYN_SMEM, c->stream>>>(a);                          \
+    } else {                                                                                                   \
+      k_stream<MODE, FD, ST, false><<<grid, ST_THREADS, 0, c->stream>>>(a);                                   \
+    }                                                                                                          \
+  } while (0)
 #define PICK(MODE)                                      \
   do {                                                  \
     if (fd) { if (stats) LAUNCH(MODE, true, true); else LAUNCH(MODE, true, false); }   \

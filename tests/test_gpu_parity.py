@@ -217,7 +217,9 @@ def test_km_golden_g1_g2(g, orc):
     G = orc.km_graph(G2_CD, 30.0)
     m, e, _ = g.km_solve(G, sp=7, tp=6, eps=0.01, penalty=30.0)
     kept = [(int(m[y]), y) for y in range(7) if m[y] >= 0]
-    assert kept == [(0, 0), (1, 1), (6, 2), (4, 3), (2, 4)]
+    # E_min = 106 is attained by exactly two matchings (brute force): the figure's / the reference DFS's
+    # {S6-T2, S2-T4} and its mirror {S2-T2, S6-T4}; an eps-optimal solver may return either.
+    assert kept in ([(0, 0), (1, 1), (6, 2), (4, 3), (2, 4)], [(0, 0), (1, 1), (2, 2), (4, 3), (6, 4)])
     assert e == 106.0
 
 
