@@ -327,26 +327,27 @@ __device__ __forceinline__ int key_who(unsigned long long k) { return (int)(unsi
 __device__ __forceinline__ double ldcg_d(const double *p) { return __ldcg(p); }
 
 // one person bids (warp-cooperative). Returns nothing; writes bid slots / dummy assignment.
-__device__ __forceinline__ void fwd_bid_one(const AucArgs &a, int i, int lane) {
-  const long long b = a.rowptr[(size_t)i * a.n_chunks], e = a.rowptr[(size_t)(i + 1) * a.n_chunks];
-  Top2 t{-1e300, -1e300, -1};
-  double bgain = 0.0;
-  long long k = b + lane;
-  // 4 independent edge loads in flight per lane (the tail rounds are latency-bound)
-  for (; k + 96 < e; k += 128) {
-    int j[4]; double g[4], p[4];
+// scan edges [kb, ke) of person i: best / second-best value (and the gain of the best edge), warp-reduced
+__device__ __forceinline__ void fwd_scan(const AucArgs &a, int i, int lane, long long kb, long long ke, Top2 &t,
+                                         double &bgain) {
+  t.best = -1e300; t.second = -1e300; t.idx = -1;
+  bgain = 0.0;
+  long long k = kb + lane;
+  // 8 independent edge loads in flight per lane (the tail rounds are latency-bound)
+  for (; k + 7 * 32 < ke; k += 8 * 32) {
+    int j[8]; double g[8], p[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { j[u] = a.csr_col[k + 32 * u]; g[u] = a.csr_gain[k + 32 * u]; }
+    for (int u = 0; u < 8; ++u) { j[u] = a.csr_col[k + 32 * u]; g[u] = a.csr_gain[k + 32 * u]; }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) p[u] = ldcg_d(&a.price[j[u]]);
+    for (int u = 0; u < 8; ++u) p[u] = ldcg_d(&a.price[j[u]]);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       const double v = g[u] - p[u];
       if (v > t.best || (v == t.best && t.idx >= 0 && tie_less(i, j[u], t.idx))) bgain = g[u];
       top2_push_h(t, v, j[u], i);
     }
   }
-  for (; k < e; k += 32) {
+  for (; k < ke; k += 32) {
     const int j = a.csr_col[k];
     const double g = a.csr_gain[k];
     const double v = g - ldcg_d(&a.price[j]);
@@ -367,22 +368,30 @@ __device__ __forceinline__ void fwd_bid_one(const AucArgs &a, int i, int lane) {
       }
     }
   }
-  if (lane == 0) {
-    if (t.idx < 0 || t.best <= 0.0) {
-      __stcg(&a.assign[i], DUMMY);
-      __stcg(&a.profit[i], 0.0);
-    } else {
-      const double wv = fmax(t.second, 0.0);
-      const double newprice = ldcg_d(&a.price[t.idx]) + (t.best - wv) + a.eps;
-      __stcg(&a.bid_obj[i], t.idx);
-      __stcg(&a.bid_val[i], newprice);
-      __stcg(&a.bid_aux[i], bgain);
-      // One atomic decides the round's winner: the key orders bidders by their bid rounded to float32, then
-      // by id.  ANY bidder may win a round as long as the price becomes its own (exact, double) bid: that is
-      // a valid auction step (price rises by >= eps, the winner is eps-happy), so float32 ordering is enough.
-      atomicMax(&a.bidmax[t.idx], pack_key((float)newprice, i));
-    }
+}
+// one thread: turn (best, second) into a bid or retire to the private dummy
+__device__ __forceinline__ void fwd_finish(const AucArgs &a, int i, const Top2 &t, double bgain) {
+  if (t.idx < 0 || t.best <= 0.0) {
+    __stcg(&a.assign[i], DUMMY);
+    __stcg(&a.profit[i], 0.0);
+  } else {
+    const double wv = fmax(t.second, 0.0);
+    const double newprice = ldcg_d(&a.price[t.idx]) + (t.best - wv) + a.eps;
+    __stcg(&a.bid_obj[i], t.idx);
+    __stcg(&a.bid_val[i], newprice);
+    __stcg(&a.bid_aux[i], bgain);
+    // One atomic decides the round's winner: the key orders bidders by their bid rounded to float32, then
+    // by id.  ANY bidder may win a round as long as the price becomes its own (exact, double) bid: that is
+    // a valid auction step (price rises by >= eps, the winner is eps-happy), so float32 ordering is enough.
+    atomicMax(&a.bidmax[t.idx], pack_key((float)newprice, i));
   }
+}
+__device__ __forceinline__ void fwd_bid_one(const AucArgs &a, int i, int lane) {
+  const long long b = a.rowptr[(size_t)i * a.n_chunks], e = a.rowptr[(size_t)(i + 1) * a.n_chunks];
+  Top2 t;
+  double bgain;
+  fwd_scan(a, i, lane, b, e, t, bgain);
+  if (lane == 0) fwd_finish(a, i, t, bgain);
 }
 __device__ __forceinline__ void fwd_resolve_one(const AucArgs &a, int i) {
   if (ldcg_i(&a.assign[i]) != UNASSIGNED) return;
@@ -401,6 +410,7 @@ __device__ __forceinline__ void fwd_commit_one(const AucArgs &a, int i, Append a
     __stcg(&a.price[j], bv);
     __stcg(&a.assign[i], j);
     __stcg(&a.profit[i], ldcg_d(&a.bid_aux[i]) - bv);
+    __stcg(&a.bidmax[j], 0ull);  // slot back to "no bid" (a loser reading 0 or the key sees "not me" either way)
     if (prev >= 0) { __stcg(&a.assign[prev], UNASSIGNED); append(prev); }
   } else {
     append(i);
@@ -411,13 +421,21 @@ __device__ __forceinline__ void fwd_reset_one(const AucArgs &a, int i) {
   if (j >= 0) __stcg(&a.bidmax[j], 0ull);
 }
 
-__device__ __forceinline__ void rev_offer_one(const AucArgs &a, int j, int lane) {
-  const long long b = a.colptr[j], e = a.colptr[j + 1];
-  Top2 t{-1e300, -1e300, -1};
-  for (long long k = b + lane; k < e; k += 32) {
+__device__ __forceinline__ void rev_scan(const AucArgs &a, int j, int lane, long long kb, long long ke, Top2 &t) {
+  t.best = -1e300; t.second = -1e300; t.idx = -1;
+  long long k = kb + lane;
+  for (; k + 7 * 32 < ke; k += 8 * 32) {
+    int i[8]; double g[8], pr[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { i[u] = a.csc_row[k + 32 * u]; g[u] = a.csc_gain[k + 32 * u]; }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) pr[u] = ldcg_d(&a.profit[i[u]]);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) top2_push_h(t, g[u] - pr[u], i[u], j);
+  }
+  for (; k < ke; k += 32) {
     const int i = a.csc_row[k];
-    const double v = a.csc_gain[k] - ldcg_d(&a.profit[i]);
-    top2_push_h(t, v, i, j);
+    top2_push_h(t, a.csc_gain[k] - ldcg_d(&a.profit[i]), i, j);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -429,18 +447,23 @@ __device__ __forceinline__ void rev_offer_one(const AucArgs &a, int j, int lane)
       else top2_merge_h(t, ob, oi, os, j);
     }
   }
-  if (lane == 0) {
-    if (t.idx < 0 || t.best <= a.eps) {
-      __stcg(&a.price[j], 0.0);
-      __stcg(&a.bid_obj[j], -1);
-    } else {
-      const double delta = fmin(t.best, (t.best - t.second) + a.eps);
-      __stcg(&a.bid_obj[j], t.idx);
-      __stcg(&a.bid_val[j], delta);
-      __stcg(&a.bid_aux[j], t.best);
-      atomicMax(&a.bidmax[t.idx], pack_key((float)delta, j));
-    }
+}
+__device__ __forceinline__ void rev_finish(const AucArgs &a, int j, const Top2 &t) {
+  if (t.idx < 0 || t.best <= a.eps) {
+    __stcg(&a.price[j], 0.0);   // nobody is worth attracting: price falls to the floor, object stays free
+    __stcg(&a.bid_obj[j], -1);
+  } else {
+    const double delta = fmin(t.best, (t.best - t.second) + a.eps);
+    __stcg(&a.bid_obj[j], t.idx);
+    __stcg(&a.bid_val[j], delta);
+    __stcg(&a.bid_aux[j], t.best);
+    atomicMax(&a.bidmax[t.idx], pack_key((float)delta, j));
   }
+}
+__device__ __forceinline__ void rev_offer_one(const AucArgs &a, int j, int lane) {
+  Top2 t;
+  rev_scan(a, j, lane, a.colptr[j], a.colptr[j + 1], t);
+  if (lane == 0) rev_finish(a, j, t);
 }
 __device__ __forceinline__ void rev_resolve_one(const AucArgs &a, int j) {
   const int i = ldcg_i(&a.bid_obj[j]);
@@ -458,6 +481,7 @@ __device__ __forceinline__ void rev_commit_one(const AucArgs &a, int j, Append a
     __stcg(&a.owner[j], i);
     __stcg(&a.price[j], ldcg_d(&a.bid_aux[j]) - dl);
     __stcg(&a.profit[i], ldcg_d(&a.profit[i]) + dl);
+    __stcg(&a.bidmax[i], 0ull);
     if (old >= 0) {
       __stcg(&a.owner[old], -1);
       if (ldcg_d(&a.price[old]) > 0.0) append(old);
@@ -477,6 +501,8 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
                                                                       int small_n) {
   cg::grid_group grid = cg::this_grid();
   __shared__ int s_n, s_next;
+  __shared__ Top2 s_pt[PA_THREADS / 32];
+  __shared__ double s_pg[PA_THREADS / 32];
   int *lists[2] = {list0, list1};
   const int lane = threadIdx.x & 31;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -484,9 +510,12 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const int gthreads = gridDim.x * blockDim.x;
   int cur = 0, rounds = 0;
+  unsigned long long t_mark = 0;
+  auto now_ns = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
   while (true) {
     const int n = ldcg_i(&a.counters[cur]);
     if (n == 0 || rounds >= max_rounds) break;
+    if (gtid == 0) t_mark = now_ns();
     if (n <= small_n) {
       // ---- tail: CTA 0 alone, block-level barriers only
       if (blockIdx.x == 0) {
@@ -498,20 +527,46 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
           const int *list = lists[cur];
           int *next = lists[cur ^ 1];
           if (threadIdx.x == 0) { s_next = 0; atomicAdd((unsigned long long *)&a.counters[8], (unsigned long long)m); }
-          for (int w = threadIdx.x >> 5; w < m; w += PA_THREADS / 32) {
-            const int e = ldcg_i(&list[w]);
-            if (REVERSE) rev_offer_one(a, e, lane); else fwd_bid_one(a, e, lane);
+          constexpr int NW = PA_THREADS / 32;
+          if (m <= NW / 2) {
+            // very few bidders: split every adjacency list over G warps so one round costs one short scan
+            const int G = NW / m;
+            const int warp = threadIdx.x >> 5, bidder = warp / G, slice = warp % G;
+            if (bidder < m) {
+              const int i = ldcg_i(&list[bidder]);
+              long long b, e;
+              if (REVERSE) { b = a.colptr[i]; e = a.colptr[i + 1]; }
+              else { b = a.rowptr[(size_t)i * a.n_chunks]; e = a.rowptr[(size_t)(i + 1) * a.n_chunks]; }
+              const long long len = e - b;
+              Top2 t; double bg = 0.0;
+              if (REVERSE) rev_scan(a, i, lane, b + len * slice / G, b + len * (slice + 1) / G, t);
+              else fwd_scan(a, i, lane, b + len * slice / G, b + len * (slice + 1) / G, t, bg);
+              if (lane == 0) { s_pt[warp] = t; s_pg[warp] = bg; }
+            }
+            __syncthreads();
+            if (bidder < m && slice == 0 && lane == 0) {
+              const int i = ldcg_i(&list[bidder]);
+              Top2 t = s_pt[warp]; double bg = s_pg[warp];
+              for (int q = 1; q < G; ++q) {
+                const Top2 o = s_pt[warp + q];
+                if (o.idx < 0) continue;
+                if (t.idx < 0) { t = o; bg = s_pg[warp + q]; continue; }
+                if (o.best > t.best || (o.best == t.best && tie_less(i, o.idx, t.idx))) bg = s_pg[warp + q];
+                top2_merge_h(t, o.best, o.idx, o.second, i);
+              }
+              if (REVERSE) rev_finish(a, i, t); else fwd_finish(a, i, t, bg);
+            }
+          } else {
+            for (int w = threadIdx.x >> 5; w < m; w += NW) {
+              const int e = ldcg_i(&list[w]);
+              if (REVERSE) rev_offer_one(a, e, lane); else fwd_bid_one(a, e, lane);
+            }
           }
           __syncthreads();
           for (int w = threadIdx.x; w < m; w += PA_THREADS) {
             const int e = ldcg_i(&list[w]);
             auto app = [&](int x) { __stcg(&next[atomicAdd(&s_next, 1)], x); };
             if (REVERSE) rev_commit_one(a, e, app); else fwd_commit_one(a, e, app);
-          }
-          __syncthreads();
-          for (int w = threadIdx.x; w < m; w += PA_THREADS) {
-            const int e = ldcg_i(&list[w]);
-            if (REVERSE) rev_reset_one(a, e); else fwd_reset_one(a, e);
           }
           __syncthreads();
           cur ^= 1;
@@ -527,6 +582,7 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
       }
       __threadfence();
       grid.sync();
+      if (gtid == 0) atomicAdd((unsigned long long *)&a.counters[12], now_ns() - t_mark);  // ns in tail mode
       cur = ldcg_i(&a.counters[4]);
       rounds = ldcg_i(&a.counters[5]);
       continue;
@@ -548,12 +604,7 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
     }
     __threadfence();
     grid.sync();
-    for (int w = gtid; w < n; w += gthreads) {
-      const int e = ldcg_i(&list[w]);
-      if (REVERSE) rev_reset_one(a, e); else fwd_reset_one(a, e);
-    }
-    __threadfence();
-    grid.sync();
+    if (gtid == 0) atomicAdd((unsigned long long *)&a.counters[14], now_ns() - t_mark);  // ns in full-grid rounds
     cur ^= 1;
     ++rounds;
   }
@@ -686,8 +737,8 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
   // CTA 0 takes over the rounds alone once the expected work of a round (active bidders x average
   // adjacency length) is small enough that grid-wide barriers would dominate
   const double avg_row = (double)nnz / (n_rows > 0 ? n_rows : 1), avg_col = (double)nnz / (n_cols > 0 ? n_cols : 1);
-  int small_fwd = (int)(16384.0 / (avg_row > 1.0 ? avg_row : 1.0));
-  int small_rev = (int)(16384.0 / (avg_col > 1.0 ? avg_col : 1.0));
+  int small_fwd = (int)(65536.0 / (avg_row > 1.0 ? avg_row : 1.0));
+  int small_rev = (int)(65536.0 / (avg_col > 1.0 ? avg_col : 1.0));
   small_fwd = small_fwd < 16 ? 16 : (small_fwd > PA_SMALL ? PA_SMALL : small_fwd);
   small_rev = small_rev < 16 ? 16 : (small_rev > PA_SMALL ? PA_SMALL : small_rev);
   const bool debug = getenv("GHICP_AUCTION_DEBUG") != nullptr;
@@ -710,7 +761,10 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
       if (e != cudaSuccess) { set_error(c, std::string("auction forward launch: ") + cudaGetErrorString(e)); return GHICP_E_CUDA; }
       c->launches++;
     }
-    // reverse: objects left free with a positive price
+    // reverse: objects left free with a positive price.  Complementary slackness for free objects only
+    // matters for the final optimality bound, so intermediate phases skip it (their leftover prices are
+    // just the next phase's starting prices).
+    if (ph + 1 == eps_list.size()) {
     cudaMemsetAsync(&c->d_counters[0], 0, sizeof(int) * 2, st);
     k_rev_collect<<<gmax, 256, 0, st>>>(n_cols, c->d_owner, c->d_price, c->d_list[0], c->d_counters, 0);
     c->launches++;
@@ -726,12 +780,14 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
       c->launches++;
     }
     cudaMemsetAsync(c->d_bid_obj, 0xff, sizeof(int) * (size_t)nmax, st);
+    }
     if (debug) {
       cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(int) * 16, cudaMemcpyDeviceToHost, st);
       cudaStreamSynchronize(st);
-      fprintf(stderr, "[auction] phase %zu eps %.5f rounds %d (cum %d, grid rounds %d) bids(cum) %llu small_fwd %d\n", ph, a.eps,
+      fprintf(stderr, "[auction] phase %zu eps %.5f rounds %d (cum %d, grid rounds %d) bids(cum) %llu small_fwd %d  tail %.2f ms grid %.2f ms (cum)\n", ph, a.eps,
               c->h_counters[6] - last_rounds, c->h_counters[6], c->h_counters[10],
-              *(unsigned long long *)&c->h_counters[8], small_fwd);
+              *(unsigned long long *)&c->h_counters[8], small_fwd, *(unsigned long long *)&c->h_counters[12] * 1e-6,
+              *(unsigned long long *)&c->h_counters[14] * 1e-6);
       last_rounds = c->h_counters[6];
     }
   }

@@ -188,14 +188,17 @@ static int build_fd(Ctx *c) {
     const int Vneed = (c->cfg.dof == 6) ? 4 : 2;
     if (c->V < Vneed) { set_error(c, "build_fd: not enough BSC source variants for dof"); return GHICP_E_ARG; }
     if (c->bits > 2048) { set_error(c, "build_fd: BSC descriptors longer than 2048 bits are not supported (fp16 FD plane)"); return GHICP_E_ARG; }
-    int rc = dev_alloc(c, &c->d_fd16, (size_t)c->N * c->ldM);
+    c->fd_rows = (size_t)c->N;
+    int rc = dev_alloc(c, &c->d_fd16, fd_elems(c->fd_rows, c->M));
     if (rc) return rc;
-    CK(c, cudaMemsetAsync(c->d_fd16, 0, (size_t)c->N * c->ldM * sizeof(uint16_t), c->stream));  // zero the pitch padding
+    CK(c, cudaMemsetAsync(c->d_fd16, 0, fd_elems(c->fd_rows, c->M) * sizeof(uint16_t), c->stream));  // zero the panel padding
     CK(c, launch_fd_bsc(c));
   } else if (c->cfg.feature_type == GHICP_FT_FPFH) {
     if (!c->have_fpfh) { set_error(c, "build_fd: FPFH descriptors not set"); return GHICP_E_ARG; }
-    int rc = dev_alloc(c, &c->d_fdf, (size_t)c->N * c->ldM);
+    c->fd_rows = (size_t)c->N;
+    int rc = dev_alloc(c, &c->d_fdf, fd_elems(c->fd_rows, c->M));
     if (rc) return rc;
+    CK(c, cudaMemsetAsync(c->d_fdf, 0, fd_elems(c->fd_rows, c->M) * sizeof(float), c->stream));
     CK(c, launch_fd_fpfh(c));
   }
   c->fd_built = true;

@@ -10,6 +10,15 @@
 
 namespace ghicp_b200 {
 
+// Feature-distance plane layout: PANEL-MAJOR.  The N x M plane is stored as ceil(M/256) column panels, each
+// a dense row-major [rows][256] block, so the 256-column panel a warp sweeps down the source rows is one
+// perfectly sequential HBM stream (512 B per row back to back) instead of 512 B reads at a 2*M-byte stride.
+constexpr int FD_PANEL = 256;
+__host__ __device__ inline size_t fd_index(size_t rows, int i, int j) {
+  return ((size_t)(j >> 8) * rows + (size_t)i) * FD_PANEL + (size_t)(j & (FD_PANEL - 1));
+}
+__host__ __device__ inline size_t fd_elems(size_t rows, int M) { return (size_t)((M + FD_PANEL - 1) / FD_PANEL) * rows * FD_PANEL; }
+
 // ---- small device-side structs -----------------------------------------------------------------
 // Parameters of one cost evaluation CD(i,j) (src/ghicp_reg.cpp:122, 224, 259, 308).
 struct CostParams {
@@ -54,8 +63,8 @@ struct StreamDev {  // device-resident scalars of the streaming path
   unsigned long long nnz_valid;
 };
 struct StreamArgs {
-  const unsigned short *fd;  // fp16 FD plane or nullptr (no feature)
-  size_t ldM;
+  const unsigned short *fd;  // fp16 FD plane (panel-major) or nullptr (no feature)
+  size_t fd_rows;            // rows of the plane held by this context
   int N, M;
   const float4 *S4, *T4;
   const double *s, *t;
@@ -78,7 +87,8 @@ struct Ctx {
   std::string err;
 
   int N = 0, M = 0;
-  size_t ldM = 0;  // FD pitch in elements
+  size_t ldM = 0;  // (legacy pitch, unused by the panel-major plane)
+  size_t fd_rows = 0;  // rows of the FD plane held by this context
   // coordinates, SoA doubles
   double *d_s = nullptr;  // [3][N]
   double *d_t = nullptr;  // [3][M]

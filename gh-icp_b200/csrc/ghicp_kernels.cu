@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(FDB_THREADS) k_fd_bsc(const uint64_t *__restri
         int m = acc[r][0];
 #pragma unroll
         for (int v = 1; v < V; ++v) m = min(m, acc[r][v]);
-        fd[(size_t)i * ldM + j] = __half_as_ushort(__int2half_rn(m));
+        fd[fd_index(ldM, i, j)] = __half_as_ushort(__int2half_rn(m));
       }
     }
   }
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(FPT *FPT) k_fd_fpfh(const float *__restrict__ 
 #pragma unroll
   for (int k = 0; k < 33; ++k) up += s_s[ty][k] * s_t[tx][k];
   float d = up / sqrtf(s_s[ty][33] * s_t[tx][33]);
-  fd[(size_t)i * ldM + j] = fabsf(d);
+  fd[fd_index(ldM, i, j)] = fabsf(d);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -272,11 +272,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_rowsweep(const SweepArgs a) {
         const double sx = s_src[0][r], sy = s_src[1][r], sz = s_src[2][r];
         double fdv[COLS_PER_THREAD];
         if (FT == GHICP_FT_BSC) {
-          const uint2 q = *reinterpret_cast<const uint2 *>(a.fd16 + (size_t)(i0 + r) * a.ldM + j);
+          const uint2 q = *reinterpret_cast<const uint2 *>(a.fd16 + fd_index(a.ldM, i0 + r, j));
           fdv[0] = h2d(q.x & 0xffffu); fdv[1] = h2d(q.x >> 16);
           fdv[2] = h2d(q.y & 0xffffu); fdv[3] = h2d(q.y >> 16);
         } else if (FT == GHICP_FT_FPFH) {
-          const float4 q = *reinterpret_cast<const float4 *>(a.fdf + (size_t)(i0 + r) * a.ldM + j);
+          const float4 q = *reinterpret_cast<const float4 *>(a.fdf + fd_index(a.ldM, i0 + r, j));
           fdv[0] = (double)q.x; fdv[1] = (double)q.y; fdv[2] = (double)q.z; fdv[3] = (double)q.w;
         } else {
           fdv[0] = fdv[1] = fdv[2] = fdv[3] = 0.0;
@@ -383,14 +383,14 @@ __global__ void __launch_bounds__(COL_THREADS) k_colsweep(const ColArgs a) {
     const double sx = sxp[i], sy = syp[i], sz = szp[i];
     double fdv[CT];
     if (FT == GHICP_FT_BSC) {
-      const uint4 q = *reinterpret_cast<const uint4 *>(a.fd16 + (size_t)i * a.ldM + j0);
+      const uint4 q = *reinterpret_cast<const uint4 *>(a.fd16 + fd_index(a.ldM, i, j0));
       fdv[0] = h2d(q.x & 0xffffu); fdv[1] = h2d(q.x >> 16);
       fdv[2] = h2d(q.y & 0xffffu); fdv[3] = h2d(q.y >> 16);
       fdv[4] = h2d(q.z & 0xffffu); fdv[5] = h2d(q.z >> 16);
       fdv[6] = h2d(q.w & 0xffffu); fdv[7] = h2d(q.w >> 16);
     } else if (FT == GHICP_FT_FPFH) {
-      const float4 q0 = *reinterpret_cast<const float4 *>(a.fdf + (size_t)i * a.ldM + j0);
-      const float4 q1 = *reinterpret_cast<const float4 *>(a.fdf + (size_t)i * a.ldM + j0 + 4);
+      const float4 q0 = *reinterpret_cast<const float4 *>(a.fdf + fd_index(a.ldM, i, j0));
+      const float4 q1 = *reinterpret_cast<const float4 *>(a.fdf + fd_index(a.ldM, i, j0 + 4));
       fdv[0] = q0.x; fdv[1] = q0.y; fdv[2] = q0.z; fdv[3] = q0.w;
       fdv[4] = q1.x; fdv[5] = q1.y; fdv[6] = q1.z; fdv[7] = q1.w;
     } else {
@@ -717,8 +717,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(const SolveArgs a) {
       const int i = a.sp[p], j = a.tp[p];
       sx = a.s[i]; sy = a.s[(size_t)a.N + i]; sz = a.s[2 * (size_t)a.N + i];
       tx = a.t[j]; ty = a.t[(size_t)a.M + j]; tz = a.t[2 * (size_t)a.M + j];
-      if (a.feature_type == GHICP_FT_BSC && a.fd16) fd = h2d(a.fd16[(size_t)i * a.ldM + j]);
-      else if (a.feature_type == GHICP_FT_FPFH && a.fdf) fd = (double)a.fdf[(size_t)i * a.ldM + j];
+      if (a.feature_type == GHICP_FT_BSC && a.fd16) fd = h2d(a.fd16[fd_index(a.ldM, i, j)]);
+      else if (a.feature_type == GHICP_FT_FPFH && a.fdf) fd = (double)a.fdf[fd_index(a.ldM, i, j)];
       else fd = 0.0;
     }
   };
@@ -822,7 +822,7 @@ __global__ void k_fd_to_double(const uint16_t *__restrict__ fd16, const float *_
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)N * M) return;
   const size_t i = idx / M, j = idx % M;
-  out[idx] = fd16 ? h2d(fd16[i * ldM + j]) : (fdf ? (double)fdf[i * ldM + j] : 0.0);
+  out[idx] = fd16 ? h2d(fd16[fd_index(ldM, (int)i, (int)j)]) : (fdf ? (double)fdf[fd_index(ldM, (int)i, (int)j)] : 0.0);
 }
 
 template <typename F>
@@ -858,9 +858,9 @@ cudaError_t launch_fd_bsc(Ctx *c) {
   dim3 grid((c->M + FDB_THREADS - 1) / FDB_THREADS, (c->N + FDB_ROWS - 1) / FDB_ROWS);
   size_t smem = (size_t)V * c->W64 * FDB_ROWS * sizeof(uint64_t);
   if (V == 4)
-    k_fd_bsc<4><<<grid, FDB_THREADS, smem, c->stream>>>(c->d_bs, c->d_bt, c->d_fd16, c->N, c->M, c->ldM, c->W64);
+    k_fd_bsc<4><<<grid, FDB_THREADS, smem, c->stream>>>(c->d_bs, c->d_bt, c->d_fd16, c->N, c->M, c->fd_rows, c->W64);
   else
-    k_fd_bsc<2><<<grid, FDB_THREADS, smem, c->stream>>>(c->d_bs, c->d_bt, c->d_fd16, c->N, c->M, c->ldM, c->W64);
+    k_fd_bsc<2><<<grid, FDB_THREADS, smem, c->stream>>>(c->d_bs, c->d_bt, c->d_fd16, c->N, c->M, c->fd_rows, c->W64);
   c->launches++;
   return cudaGetLastError();
 }
@@ -873,7 +873,7 @@ cudaError_t launch_fd_fpfh(Ctx *c) {
   k_fpfh_center<<<(c->N + 127) / 128, 128, 0, c->stream>>>(c->d_fs, sc, c->N);
   k_fpfh_center<<<(c->M + 127) / 128, 128, 0, c->stream>>>(c->d_ft, tc, c->M);
   dim3 grid((c->M + FPT - 1) / FPT, (c->N + FPT - 1) / FPT);
-  k_fd_fpfh<<<grid, FPT * FPT, 0, c->stream>>>(sc, tc, c->d_fdf, c->N, c->M, c->ldM);
+  k_fd_fpfh<<<grid, FPT * FPT, 0, c->stream>>>(sc, tc, c->d_fdf, c->N, c->M, c->fd_rows);
   c->launches += 3;
   cudaFreeAsync(sc, c->stream);
   cudaFreeAsync(tc, c->stream);
@@ -882,7 +882,7 @@ cudaError_t launch_fd_fpfh(Ctx *c) {
 
 cudaError_t launch_rowsweep(Ctx *c, int mode, const CostParams &cp) {
   SweepArgs a{};
-  a.s = c->d_s; a.t = c->d_t; a.fd16 = c->d_fd16; a.fdf = c->d_fdf; a.ldM = c->ldM;
+  a.s = c->d_s; a.t = c->d_t; a.fd16 = c->d_fd16; a.fdf = c->d_fdf; a.ldM = c->fd_rows;
   a.N = c->N; a.M = c->M; a.n_chunks = c->n_chunks;
   int cpc = (c->M + c->n_chunks - 1) / c->n_chunks;
   cpc = (cpc + COLS_PER_THREAD - 1) / COLS_PER_THREAD * COLS_PER_THREAD;
@@ -905,7 +905,7 @@ cudaError_t launch_rowsweep(Ctx *c, int mode, const CostParams &cp) {
 
 cudaError_t launch_colsweep(Ctx *c, const CostParams &cp) {
   ColArgs a{};
-  a.s = c->d_s; a.t = c->d_t; a.fd16 = c->d_fd16; a.fdf = c->d_fdf; a.ldM = c->ldM;
+  a.s = c->d_s; a.t = c->d_t; a.fd16 = c->d_fd16; a.fdf = c->d_fdf; a.ldM = c->fd_rows;
   a.N = c->N; a.M = c->M; a.cp = cp; a.col_cd = c->d_col_cd; a.col_idx = c->d_col_idx;
   dim3 grid((c->M + CT - 1) / CT);
   cudaError_t e = dispatch_ft(c->cfg.feature_type, [&](auto ft) {
@@ -952,7 +952,7 @@ cudaError_t launch_select_km(Ctx *c) {
 cudaError_t launch_solve(Ctx *c, const CostParams &cp) {
   SolveArgs a{};
   a.cp = cp;
-  a.s = c->d_s; a.t = c->d_t; a.fd16 = c->d_fd16; a.fdf = c->d_fdf; a.ldM = c->ldM;
+  a.s = c->d_s; a.t = c->d_t; a.fd16 = c->d_fd16; a.fdf = c->d_fdf; a.ldM = c->fd_rows;
   a.N = c->N; a.M = c->M; a.feature_type = c->cfg.feature_type;
   a.sp = c->d_sp; a.tp = c->d_tp; a.sxyz_pairs = nullptr; a.txyz_pairs = nullptr; a.n_explicit = 0;
   a.iter = c->d_iter;
@@ -977,7 +977,7 @@ cudaError_t launch_apply(Ctx *c) {
 
 cudaError_t launch_get_fd(Ctx *c, double *d_out) {
   const size_t total = (size_t)c->N * c->M;
-  k_fd_to_double<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(c->d_fd16, c->d_fdf, c->ldM, c->N, c->M, d_out);
+  k_fd_to_double<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(c->d_fd16, c->d_fdf, c->fd_rows, c->N, c->M, d_out);
   c->launches++;
   return cudaGetLastError();
 }

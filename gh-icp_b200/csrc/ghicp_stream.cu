@@ -37,7 +37,7 @@ constexpr unsigned INF_BITS = 0x7f800000u;
 // TMA staging of the FD plane: every warp runs its own ring of ST_STAGES stages; a stage holds ST_UNROLL
 // row segments of the warp's 256-column panel (512 B each), brought in by cp.async.bulk (TMA engine,
 // UBLKCP) and signalled on one mbarrier per stage.  No registers are tied up by loads in flight.
-constexpr int ST_STAGES = 6;
+constexpr int ST_STAGES = 4;
 constexpr int ST_SEG_BYTES = ST_PANEL * 2;                   // 512
 constexpr int ST_STAGE_BYTES = ST_UNROLL * ST_SEG_BYTES;     // 2048
 constexpr int ST_RING_BYTES = ST_STAGES * ST_STAGE_BYTES;    // per warp
@@ -89,7 +89,7 @@ __device__ __noinline__ double exact_cd(const StreamArgs &a, int i, int j) {
   const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
   const double ed = __dmul_rn(a.scale, __dsqrt_rn(d2));
   if (a.fd) {
-    const double fd = (double)__half2float(__ushort_as_half(a.fd[(size_t)i * a.ldM + j]));
+    const double fd = (double)__half2float(__ushort_as_half(a.fd[fd_index(a.fd_rows, i, j)]));
     return __dadd_rn(__dmul_rn(a.WED, ed), __dmul_rn(a.WFD, fd));
   }
   return ed;
@@ -223,20 +223,19 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, u
   const float m2 = 2.f * margin;
   const float thr_hi = a.dev->thr_hi;
   const float b = a.b;
-  const bool lane_loads = FULL || (j0 < a.M);
-  const unsigned short *fdp = HAS_FD ? a.fd + (size_t)r0 * a.ldM + j0 : nullptr;
+  const bool lane_loads = true;  // the panel-major plane is allocated in whole panels (zero padded)
+  const unsigned short *fdp = HAS_FD ? a.fd + fd_index(a.fd_rows, r0, j0) : nullptr;
   // ---- TMA ring bookkeeping (warp-private) ----
   const int panel = j0 - lane * ST_CPL;
-  const unsigned seg_bytes = (HAS_FD && TMA) ? (unsigned)min((size_t)ST_SEG_BYTES, (a.ldM - (size_t)panel) * 2) : 0u;
-  const unsigned short *panel_base = (HAS_FD && TMA) ? a.fd + (size_t)r0 * a.ldM + panel : nullptr;
+  const unsigned short *panel_base = (HAS_FD && TMA) ? a.fd + fd_index(a.fd_rows, r0, panel) : nullptr;
   const int nbatch = (nrows + ST_UNROLL - 1) / ST_UNROLL;
   auto issue = [&](int k) {  // lane 0 only
     const int stage = k % ST_STAGES;
     const int rows = min(ST_UNROLL, nrows - k * ST_UNROLL);
-    mbar_expect_tx(&bars[stage], (unsigned)rows * seg_bytes);
-    for (int u = 0; u < rows; ++u)
-      bulk_g2s(ring + stage * ST_STAGE_BYTES + u * ST_SEG_BYTES, panel_base + (size_t)(k * ST_UNROLL + u) * a.ldM, seg_bytes,
-               &bars[stage]);
+    // panel-major plane: the ST_UNROLL row segments of a stage are contiguous -> ONE bulk copy
+    mbar_expect_tx(&bars[stage], (unsigned)rows * ST_SEG_BYTES);
+    bulk_g2s(ring + stage * ST_STAGE_BYTES, panel_base + (size_t)(k * ST_UNROLL) * FD_PANEL, (unsigned)rows * ST_SEG_BYTES,
+             &bars[stage]);
   };
   if (HAS_FD && TMA) {
     if (lane == 0)
@@ -249,20 +248,11 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, u
       const int k = rb / ST_UNROLL;
       const int stage = k % ST_STAGES;
       mbar_wait(&bars[stage], (unsigned)((k / ST_STAGES) & 1));
-#pragma unroll
-      for (int u = 0; u < ST_UNROLL; ++u)
-        q[u] = *reinterpret_cast<const uint4 *>(ring + stage * ST_STAGE_BYTES + u * ST_SEG_BYTES + lane * 16);
-      // the values are in registers: hand the stage back to the TMA engine for batch k + ST_STAGES
-      __syncwarp();
-      if (lane == 0 && k + ST_STAGES < nbatch) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        issue(k + ST_STAGES);
-      }
     } else if (HAS_FD) {
 #pragma unroll
       for (int u = 0; u < ST_UNROLL; ++u) {
         const int r = min(rb + u, nrows - 1);
-        q[u] = lane_loads ? ldg_stream(reinterpret_cast<const uint4 *>(fdp + (size_t)r * a.ldM)) : make_uint4(0, 0, 0, 0);
+        q[u] = lane_loads ? ldg_stream(reinterpret_cast<const uint4 *>(fdp + (size_t)r * FD_PANEL)) : make_uint4(0, 0, 0, 0);
       }
     }
     float psum = 0.f, psq = 0.f;
@@ -271,6 +261,8 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, u
       const int r = rb + u;
       if (r < nrows) {
         const float4 S = s_S4[r];
+        if (HAS_FD && TMA)  // just-in-time read of this row's 8 values from the staged segment
+          q[u] = *reinterpret_cast<const uint4 *>(ring + ((rb / ST_UNROLL) % ST_STAGES) * ST_STAGE_BYTES + u * ST_SEG_BYTES + lane * 16);
         float cd[ST_CPL];
 #pragma unroll
         for (int c = 0; c < ST_CPL; ++c) {
@@ -353,6 +345,15 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, u
         }
       }
     }
+    if (HAS_FD && TMA) {
+      // every lane has consumed its values: hand the stage back to the TMA engine for batch k + ST_STAGES
+      const int k = rb / ST_UNROLL;
+      __syncwarp();
+      if (lane == 0 && k + ST_STAGES < nbatch) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(k + ST_STAGES);
+      }
+    }
     if (STATS) {
       dsum += (double)psum;
       dsq += (double)psq;
@@ -366,7 +367,7 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, u
 }
 
 template <int MODE, bool HAS_FD, bool STATS, bool TMA>
-__global__ void __launch_bounds__(ST_THREADS, 2) k_stream(const StreamArgs a) {
+__global__ void __launch_bounds__(ST_THREADS, TMA ? 3 : 2) k_stream(const StreamArgs a) {
   extern __shared__ __align__(128) unsigned char s_ring[];   // [ST_WARPS][ST_RING_BYTES] when TMA
   __shared__ __align__(8) unsigned long long s_bar[ST_WARPS][ST_STAGES];
   __shared__ float4 s_S4[ST_RB];
@@ -551,7 +552,7 @@ __global__ void __launch_bounds__(1024) k_scan_rows(const int *__restrict__ cnt,
 static StreamArgs make_args(Ctx *c, const CostParams &cp) {
   StreamArgs a{};
   a.fd = (c->cfg.feature_type == GHICP_FT_BSC) ? c->d_fd16 : nullptr;
-  a.ldM = c->ldM; a.N = c->N; a.M = c->M;
+  a.fd_rows = c->fd_rows; a.N = c->N; a.M = c->M;
   a.S4 = reinterpret_cast<const float4 *>(c->d_S4); a.T4 = reinterpret_cast<const float4 *>(c->d_T4);
   a.s = c->d_s; a.t = c->d_t;
   a.scale = cp.scale; a.WED = cp.WED; a.WFD = cp.WFD;
