@@ -123,6 +123,13 @@ def _ip(a):
     return a.ctypes.data_as(C.POINTER(C.c_int))
 
 
+def comm_unique_id():
+    """128-byte NCCL unique id (rank 0 creates it, the host runtime broadcasts it)."""
+    buf = (C.c_char * 128)()
+    check(lib().ghicp_comm_unique_id(buf))
+    return bytes(buf)
+
+
 def km_solve(W, sp=None, tp=None, eps=0.01, penalty=1000.0, device=0):
     """Stand-alone Km replacement on a dense weight matrix (include/km.h:38-53)."""
     W = np.ascontiguousarray(W, dtype=np.float64)

@@ -72,6 +72,9 @@ static void free_all(Ctx *c) {
   dev_free(&c->d_price); dev_free(&c->d_profit); dev_free(&c->d_assign); dev_free(&c->d_owner);
   dev_free(&c->d_bidmax); dev_free(&c->d_bidwin); dev_free(&c->d_bid_obj); dev_free(&c->d_bid_val);
   dev_free(&c->d_bid_aux); dev_free(&c->d_list[0]); dev_free(&c->d_list[1]); dev_free(&c->d_counters);
+  dev_free(&c->d_row_fd); dev_free(&c->d_pair_fd); dev_free(&c->d_csr_fd); dev_free(&c->d_xstats);
+  dev_free(&c->d_colg_cd); dev_free(&c->d_colg_idx);
+  if (c->h_rowptr_cut) { cudaFreeHost(c->h_rowptr_cut); c->h_rowptr_cut = nullptr; }
   dev_free(&c->d_S4); dev_free(&c->d_T4); dev_free(&c->d_sdev); dev_free(&c->d_row_thr); dev_free(&c->d_col_thr);
   dev_free(&c->d_rowbest); dev_free(&c->d_colbest); dev_free(&c->d_rowidx2); dev_free(&c->d_colidx2);
   dev_free(&c->d_cand[0]); dev_free(&c->d_cand[1]);
@@ -102,28 +105,34 @@ static void reset_loop_state(Ctx *c) {
 // workspaces that depend on (N, M)
 static int alloc_workspaces(Ctx *c) {
   const int N = c->N, M = c->M;
-  const int nmax = std::max(N, M);
+  // contiguous blocks of source rows per rank; Npad = arrays that get all-gathered
+  c->shard = (N + c->world - 1) / c->world;
+  c->Npad = c->shard * c->world;
+  c->r0 = std::min(N, c->rank * c->shard);
+  c->nloc = std::max(0, std::min(N, c->r0 + c->shard) - c->r0);
+  if (c->world > 1 && c->n_chunks != 1) c->n_chunks = 1;
+  const int nmax = std::max(c->Npad, M);
   const int row_ctas = (N + 7) / 8;
   int want = (148 * 4 + row_ctas - 1) / row_ctas;
   int lim = std::max(1, M / 2048);
   c->n_chunks = std::max(1, std::min(want, lim));
-  if (c->cfg.corr_type == GHICP_CT_KM) c->n_chunks = 1;  // the streaming path keeps one CSR segment per row
+  if (c->cfg.corr_type == GHICP_CT_KM || c->world > 1) c->n_chunks = 1;  // one CSR / result segment per row
   int rc;
-  const size_t L = (size_t)N * c->n_chunks;
+  const size_t L = (size_t)c->Npad * c->n_chunks;
   if ((rc = dev_alloc(c, &c->d_part_cd, L))) return rc;
   if ((rc = dev_alloc(c, &c->d_part_idx, L))) return rc;
   c->part_stats_cap = std::max((size_t)row_ctas * c->n_chunks * 2, (size_t)stream_num_parts(c) * 2);
   if ((rc = dev_alloc(c, &c->d_part_stats, c->part_stats_cap))) return rc;
   // streaming path
-  if ((rc = dev_alloc(c, &c->d_S4, 4 * (size_t)N))) return rc;
+  if ((rc = dev_alloc(c, &c->d_S4, 4 * (size_t)c->Npad))) return rc;
   if ((rc = dev_alloc(c, &c->d_T4, 4 * (size_t)M))) return rc;
   if ((rc = dev_alloc(c, &c->d_sdev, 1))) return rc;
   if (!c->h_sdev && cudaMallocHost((void **)&c->h_sdev, sizeof(StreamDev)) != cudaSuccess) return GHICP_E_NOMEM;
-  if ((rc = dev_alloc(c, &c->d_row_thr, (size_t)N))) return rc;
+  if ((rc = dev_alloc(c, &c->d_row_thr, (size_t)c->Npad))) return rc;
   if ((rc = dev_alloc(c, &c->d_col_thr, (size_t)M))) return rc;
-  if ((rc = dev_alloc(c, &c->d_rowbest, (size_t)N))) return rc;
+  if ((rc = dev_alloc(c, &c->d_rowbest, (size_t)c->Npad))) return rc;
   if ((rc = dev_alloc(c, &c->d_colbest, (size_t)M))) return rc;
-  if ((rc = dev_alloc(c, &c->d_rowidx2, (size_t)N))) return rc;
+  if ((rc = dev_alloc(c, &c->d_rowidx2, (size_t)c->Npad))) return rc;
   if ((rc = dev_alloc(c, &c->d_colidx2, (size_t)M))) return rc;
   if (c->cfg.corr_type != GHICP_CT_KM) {
     c->cand_cap = (int)std::min<size_t>((size_t)96 * nmax + (1u << 20), (size_t)1 << 28);
@@ -131,8 +140,18 @@ static int alloc_workspaces(Ctx *c) {
     if (c->cfg.corr_type == GHICP_CT_NNR) { if ((rc = dev_alloc(c, &c->d_cand[1], (size_t)c->cand_cap))) return rc; }
   }
   CK(c, cudaMemset(c->d_sdev, 0, sizeof(StreamDev)));
-  if ((rc = dev_alloc(c, &c->d_row_cd, (size_t)N))) return rc;
-  if ((rc = dev_alloc(c, &c->d_row_idx, (size_t)N))) return rc;
+  if ((rc = dev_alloc(c, &c->d_row_cd, (size_t)c->Npad))) return rc;
+  if ((rc = dev_alloc(c, &c->d_row_idx, (size_t)c->Npad))) return rc;
+  if ((rc = dev_alloc(c, &c->d_row_fd, (size_t)c->Npad))) return rc;
+  if ((rc = dev_alloc(c, &c->d_pair_fd, (size_t)nmax))) return rc;
+  if ((rc = dev_alloc(c, &c->d_xstats, (size_t)4 * c->world))) return rc;
+  CK(c, cudaMemset(c->d_xstats, 0, sizeof(double) * 4 * c->world));
+  CK(c, cudaMemset(c->d_row_idx, 0, sizeof(int) * (size_t)c->Npad));
+  if (c->world > 1 && c->cfg.corr_type == GHICP_CT_NNR) {
+    if ((rc = dev_alloc(c, &c->d_colg_cd, (size_t)c->world * M))) return rc;
+    if ((rc = dev_alloc(c, &c->d_colg_idx, (size_t)c->world * M))) return rc;
+  }
+  if (!c->h_rowptr_cut && cudaMallocHost((void **)&c->h_rowptr_cut, sizeof(long long) * (c->world + 1)) != cudaSuccess) return GHICP_E_NOMEM;
   if ((rc = dev_alloc(c, &c->d_col_cd, (size_t)M))) return rc;
   if ((rc = dev_alloc(c, &c->d_col_idx, (size_t)M))) return rc;
   if ((rc = dev_alloc(c, &c->d_flags, (size_t)nmax))) return rc;
@@ -148,8 +167,8 @@ static int alloc_workspaces(Ctx *c) {
     if ((rc = dev_alloc(c, &c->d_colptr, (size_t)M + 1))) return rc;
     if ((rc = dev_alloc(c, &c->d_colcnt, (size_t)M + 1))) return rc;
     if ((rc = dev_alloc(c, &c->d_price, (size_t)M))) return rc;
-    if ((rc = dev_alloc(c, &c->d_profit, (size_t)N))) return rc;
-    if ((rc = dev_alloc(c, &c->d_assign, (size_t)N))) return rc;
+    if ((rc = dev_alloc(c, &c->d_profit, (size_t)c->Npad))) return rc;
+    if ((rc = dev_alloc(c, &c->d_assign, (size_t)c->Npad))) return rc;
     if ((rc = dev_alloc(c, &c->d_owner, (size_t)M))) return rc;
     if ((rc = dev_alloc(c, &c->d_bidmax, (size_t)nmax))) return rc;
     if ((rc = dev_alloc(c, &c->d_bidwin, (size_t)nmax))) return rc;
@@ -170,6 +189,7 @@ static int ensure_edges(Ctx *c, long long nnz) {
     size_t cap = need + need / 8 + 1024;
     if ((rc = dev_alloc(c, &c->d_csr_col, cap))) return rc;
     if ((rc = dev_alloc(c, &c->d_csr_gain, cap))) return rc;
+    if ((rc = dev_alloc(c, &c->d_csr_fd, cap))) return rc;
     c->csr_cap = cap;
   }
   if (need > c->csc_cap) {
@@ -188,14 +208,14 @@ static int build_fd(Ctx *c) {
     const int Vneed = (c->cfg.dof == 6) ? 4 : 2;
     if (c->V < Vneed) { set_error(c, "build_fd: not enough BSC source variants for dof"); return GHICP_E_ARG; }
     if (c->bits > 2048) { set_error(c, "build_fd: BSC descriptors longer than 2048 bits are not supported (fp16 FD plane)"); return GHICP_E_ARG; }
-    c->fd_rows = (size_t)c->N;
+    c->fd_rows = (size_t)std::max(c->nloc, 1);
     int rc = dev_alloc(c, &c->d_fd16, fd_elems(c->fd_rows, c->M));
     if (rc) return rc;
     CK(c, cudaMemsetAsync(c->d_fd16, 0, fd_elems(c->fd_rows, c->M) * sizeof(uint16_t), c->stream));  // zero the panel padding
     CK(c, launch_fd_bsc(c));
   } else if (c->cfg.feature_type == GHICP_FT_FPFH) {
     if (!c->have_fpfh) { set_error(c, "build_fd: FPFH descriptors not set"); return GHICP_E_ARG; }
-    c->fd_rows = (size_t)c->N;
+    c->fd_rows = (size_t)std::max(c->nloc, 1);
     int rc = dev_alloc(c, &c->d_fdf, fd_elems(c->fd_rows, c->M));
     if (rc) return rc;
     CK(c, cudaMemsetAsync(c->d_fdf, 0, fd_elems(c->fd_rows, c->M) * sizeof(float), c->stream));
@@ -241,12 +261,17 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
   bool exact_fallback = !fast;
   bool ev1_done = false, timed_stream = false;
   int stream_passes = 0;
+  const bool sharded = c->world > 1;
+  if (sharded && ct == GHICP_CT_KM && !fast) {
+    set_error(c, "multi-GPU KM needs the streaming path (BSC / no feature, force_exact = 0)");
+    return GHICP_E_ARG;
+  }
   if (fast && ct != GHICP_CT_KM) {
     // ---- streaming path, NN / NNR: one pass = calED + calCD + row (and column) scans + statistics
     const bool cols = (ct == GHICP_CT_NNR);
     // a seed pass (FP32 minima only) keeps the refinement cheap whenever last iteration's partners are not
     // a tight bound: the first iterations (the metric mix changes fastest) or when many candidates were seen
-    const long long cand_budget = 6ll * ((long long)c->N + (cols ? c->M : 0));
+    const long long cand_budget = 6ll * ((long long)c->nloc + (cols ? c->M : 0));
     const bool prepass = !c->have_prev || c->iteration <= 2 || c->last_cands > cand_budget;
     CK(c, launch_stream_prep(c, cp, 0));
     CK(c, launch_stream_seed(c, cp, cols));
@@ -257,6 +282,9 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
     ++stream_passes; timed_stream = true;
     CK(c, launch_finalize_fast(c, ls));
     CK(c, launch_stream_resolve(c, cp, cols));
+    if ((rc = comm_exchange(c, 1 | 2 | (cols ? 4 : 0)))) return rc;   // the single exchange of the iteration
+    CK(c, launch_penalty(c, 0.0, ls));
+    if (cols && sharded) CK(c, launch_colmerge(c));
     CK(c, cudaEventRecord(c->ev[1], st));
     ev1_done = true;
     // the NN gate depends on this iteration's statistics only for Ft=None and for BSC iterations 0-1
@@ -266,22 +294,24 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
     CK(c, cudaMemcpyAsync(c->h_sdev, c->d_sdev, sizeof(StreamDev), cudaMemcpyDeviceToHost, st));
     CK(c, cudaMemcpyAsync(c->h_iter, c->d_iter, sizeof(DevIter), cudaMemcpyDeviceToHost, st));
     CK(c, cudaStreamSynchronize(st));
-    // candidate buffer overflow, or an NN gate decision inside the error band of the fast statistics:
-    // redo this iteration's cost stage with the all-double kernels (rare)
+    // candidate buffer overflow (on any rank), or an NN gate decision inside the error band of the fast
+    // statistics: redo this iteration's cost stage with the all-double kernels (rare)
     c->last_cands = (long long)c->h_sdev->cand_count[0] + (cols ? c->h_sdev->cand_count[1] : 0);
-    if (c->h_sdev->overflow || (!cols && c->h_iter->ambiguous > 0)) exact_fallback = true;
+    if (c->h_iter->overflow_any || (!cols && c->h_iter->ambiguous > 0)) exact_fallback = true;
     else c->have_prev = true;
     c->fallbacks += exact_fallback ? 1 : 0;
   } else if (fast) {
     // ---- streaming path, KM: [statistics pass] + count pass + fill pass over the FD plane
     const bool stats_first = (ft == GHICP_FT_NONE) || (c->iteration <= 1);
     CK(c, launch_stream_prep(c, cp, 0));
-    CK(c, cudaMemsetAsync(c->d_cnt, 0, sizeof(int) * ((size_t)c->N + 2), st));
+    CK(c, cudaMemsetAsync(c->d_cnt, 0, sizeof(int) * ((size_t)c->Npad + 2), st));
     if (stats_first) {
       CK(c, cudaEventRecord(c->ev[4], st));
       CK(c, launch_stream(c, cp, 2, true));   // gate disabled (thr = -1): statistics only
       CK(c, cudaEventRecord(c->ev[5], st));
       CK(c, launch_finalize_fast(c, ls));
+      if ((rc = comm_exchange(c, 1))) return rc;
+      CK(c, launch_penalty(c, 0.0, ls));
       CK(c, launch_stream_gate(c, cp));
       CK(c, cudaEventRecord(c->ev[1], st));
       CK(c, launch_stream(c, cp, 2, false));
@@ -293,13 +323,20 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
       CK(c, launch_stream(c, cp, 2, true));
       CK(c, cudaEventRecord(c->ev[5], st));
       CK(c, launch_finalize_fast(c, ls));
+      if ((rc = comm_exchange(c, 1))) return rc;
+      CK(c, launch_penalty(c, 0.0, ls));
       CK(c, cudaEventRecord(c->ev[1], st));
       stream_passes += 1;
     }
     timed_stream = true;
     ev1_done = true;
+    if ((rc = comm_gather_counts(c))) return rc;
     CK(c, launch_scan_rows(c));
     CK(c, cudaMemcpyAsync(c->h_iter, c->d_iter, sizeof(DevIter), cudaMemcpyDeviceToHost, st));
+    if (sharded)
+      for (int r = 0; r <= c->world; ++r)
+        CK(c, cudaMemcpyAsync(&c->h_rowptr_cut[r], c->d_rowptr + std::min(c->N, r * c->shard), sizeof(long long),
+                              cudaMemcpyDeviceToHost, st));
     CK(c, cudaStreamSynchronize(st));
     const long long nnz_super = c->h_iter->nnz;
     const double penalty = c->h_iter->penalty;
@@ -308,22 +345,31 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
       ++stream_passes;
       CK(c, launch_stream(c, cp, 3, false));
       CK(c, launch_csr_check(c, cp));
+      if (sharded) {
+        if ((rc = comm_gather_edges(c, c->h_rowptr_cut))) return rc;
+        CK(c, launch_count_valid(c, nnz_super));
+      }
     }
     CK(c, launch_build_csc(c, c->N, c->M, nnz_super));
     if ((rc = km_auction(c, c->N, c->M, nnz_super, c->KM_eps, std::max(penalty, c->KM_eps), &kres))) return rc;
     CK(c, launch_select_km(c));
+    CK(c, launch_pair_fd_km(c));
     CK(c, cudaMemcpyAsync(c->h_sdev, c->d_sdev, sizeof(StreamDev), cudaMemcpyDeviceToHost, st));
     nnz = -1;  // filled from h_sdev after the final synchronize
   }
   if (exact_fallback) {
     // ---- all-double path (FPFH; forced; or fallback): calED + calCD_* (+ the row scan of NN / NNR)
+    if (sharded && ct == GHICP_CT_KM) { set_error(c, "multi-GPU KM: all-double fallback not supported"); return GHICP_E_ARG; }
     CK(c, launch_rowsweep(c, 0, cp));
     CK(c, launch_finalize_stats(c, cp, ls));
+    if (ct == GHICP_CT_NNR) CK(c, launch_colsweep(c, cp));
+    if ((rc = comm_exchange(c, 1 | 2 | (ct == GHICP_CT_NNR ? 4 : 0)))) return rc;
+    CK(c, launch_penalty(c, cp.pivot, ls));
+    if (ct == GHICP_CT_NNR && sharded) CK(c, launch_colmerge(c));
     if (!ev1_done) CK(c, cudaEventRecord(c->ev[1], st));
     if (ct == GHICP_CT_NN) {
       CK(c, launch_select_nn(c));
     } else if (ct == GHICP_CT_NNR) {
-      CK(c, launch_colsweep(c, cp));
       CK(c, launch_select_nnr(c));
     } else {
       CK(c, launch_rowsweep(c, 1, cp));
@@ -337,6 +383,7 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
       CK(c, launch_build_csc(c, c->N, c->M, nnz));
       if ((rc = km_auction(c, c->N, c->M, nnz, c->KM_eps, std::max(penalty, c->KM_eps), &kres))) return rc;
       CK(c, launch_select_km(c));
+      CK(c, launch_pair_fd_km(c));
     }
     if (ct != GHICP_CT_KM) c->have_prev = true;
   }
@@ -473,6 +520,7 @@ int ghicp_destroy(ghicp_ctx *ctx) {
   if (!c) return GHICP_OK;
   use_device(c);
   cudaStreamSynchronize(c->stream);
+  comm_destroy(c);
   free_all(c);
   for (auto &e : c->ev) if (e) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -649,6 +697,8 @@ int ghicp_probe_rowmin(ghicp_ctx *ctx, int *idx, double *cd, double *cd_mean, do
   const LoopScalars ls = make_loop_scalars(c, cp);
   CK(c, launch_rowsweep(c, 0, cp));
   CK(c, launch_finalize_stats(c, cp, ls));
+  if ((rc = comm_exchange(c, 1 | 2))) return rc;
+  CK(c, launch_penalty(c, cp.pivot, ls));
   CK(c, cudaMemcpyAsync(c->h_iter, c->d_iter, sizeof(DevIter), cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
   if (idx) CK(c, cudaMemcpy(idx, c->d_row_idx, sizeof(int) * (size_t)c->N, cudaMemcpyDeviceToHost));
@@ -753,13 +803,16 @@ int ghicp_rigid_fit(int device, const double *s, const double *t, int n, double 
   return GHICP_OK;
 }
 
-int ghicp_comm_unique_id(void *) {
-  set_error(nullptr, "multi-GPU exchange not built in this revision");
-  return GHICP_E_NCCL;
+int ghicp_comm_unique_id(void *id128) {
+  if (!id128) return GHICP_E_ARG;
+  return comm_unique_id(id128);
 }
-int ghicp_comm_init(ghicp_ctx *, const void *, int, int) {
-  set_error(nullptr, "multi-GPU exchange not built in this revision");
-  return GHICP_E_NCCL;
+int ghicp_comm_init(ghicp_ctx *ctx, const void *id128, int rank, int world) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || (!id128 && world > 1)) return GHICP_E_ARG;
+  int rc;
+  if ((rc = use_device(c))) return rc;
+  return comm_init(c, id128, rank, world);
 }
 
 }  // extern "C"

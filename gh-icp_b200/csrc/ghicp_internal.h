@@ -40,7 +40,7 @@ struct DevIter {
   double cd_sum_shift, cd_sumsq_shift;  // sums of (cd - pivot), (cd - pivot)^2
   double cd_mean, cd_std, penalty;
   int cor;
-  int pad0;
+  int overflow_any;     // some rank's candidate buffer overflowed (streaming path)
   double rmse, fdm, fdstd, rmse_after;
   double km_cd_sum;     // sum of CD over kept pairs
   double Rt[16];        // column-major
@@ -66,6 +66,7 @@ struct StreamArgs {
   const unsigned short *fd;  // fp16 FD plane (panel-major) or nullptr (no feature)
   size_t fd_rows;            // rows of the plane held by this context
   int N, M;
+  int row0, nloc;            // source rows [row0, row0 + nloc) streamed by this context
   const float4 *S4, *T4;
   const double *s, *t;
   double scale, WED, WFD;
@@ -76,6 +77,8 @@ struct StreamArgs {
   Cand *cand[2]; int cand_cap;
   double *part_stats;
   int *cnt; const long long *rowptr; int *cursor; int *csr_col;
+  float *row_fd;   // FD of (row, its partner)
+  float *csr_fd;   // FD of every CSR entry
 };
 
 // ---- the context ----------------------------------------------------------------------------------
@@ -168,9 +171,18 @@ struct Ctx {
   int launches = 0;
   int last_cor = 0;
 
-  // multi-GPU
+  // multi-GPU: source rows [r0, r0 + nloc) live here; target replicated; one exchange per iteration
   void *nccl_comm = nullptr;
   int rank = 0, world = 1;
+  int r0 = 0, nloc = 0, shard = 0, Npad = 0;
+  float *d_row_fd = nullptr;    // [Npad]
+  float *d_pair_fd = nullptr;   // [max(N,M)]
+  float *d_csr_fd = nullptr;    // [csr_cap]
+  double *d_xstats = nullptr;   // [world][2] partial CD sums
+  unsigned long long *d_colg_cd = nullptr;  // [world][M] gathered column minima (ordered-double bits)
+  int *d_colg_idx = nullptr;                // [world][M]
+  long long *h_rowptr_cut = nullptr;        // pinned [world + 1] CSR offsets at the shard boundaries
+  int exchanges = 0;
 };
 
 struct KmResult {
@@ -193,6 +205,10 @@ cudaError_t launch_apply(Ctx *c);
 cudaError_t launch_solve_explicit(cudaStream_t stream, const double *d_s, const double *d_t, int n, DevIter *d_iter);
 cudaError_t launch_get_fd(Ctx *c, double *d_out);
 cudaError_t launch_scan_counts(Ctx *c);  // d_cnt → d_rowptr, nnz → d_iter->nnz
+cudaError_t launch_penalty(Ctx *c, double pivot, const LoopScalars &ls);
+cudaError_t launch_pair_fd_km(Ctx *c);
+cudaError_t launch_colmerge(Ctx *c);
+cudaError_t launch_count_valid(Ctx *c, long long nnz);
 
 // ---- streaming path (ghicp_stream.cu) -----------------------------------------------------------
 cudaError_t launch_stream_prep(Ctx *c, const CostParams &cp, int for_km_gate);
@@ -211,6 +227,14 @@ int stream_num_parts(const Ctx *c);
 int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, double max_gain,
                KmResult *res);
 cudaError_t launch_build_csc(Ctx *c, int n_rows, int n_cols, long long nnz);
+
+// ---- multi-GPU exchange (ghicp_comm.cu) ------------------------------------------------------------
+int comm_unique_id(void *id128);
+int comm_init(Ctx *c, const void *id128, int rank, int world);
+void comm_destroy(Ctx *c);
+int comm_exchange(Ctx *c, int what);         // bit0 stats, bit1 rows, bit2 columns
+int comm_gather_counts(Ctx *c);
+int comm_gather_edges(Ctx *c, const long long *cut);
 
 // misc
 int ensure_capacity(Ctx *c, void **ptr, size_t *cap, size_t need_bytes);

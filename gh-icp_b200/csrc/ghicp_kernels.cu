@@ -120,15 +120,16 @@ template <int V>
 __global__ void __launch_bounds__(FDB_THREADS) k_fd_bsc(const uint64_t *__restrict__ bs,
                                                          const uint64_t *__restrict__ bt,
                                                          uint16_t *__restrict__ fd, int N, int M, size_t ldM,
-                                                         int W64) {
+                                                         int W64, int row0, int nloc) {
   extern __shared__ uint64_t s_words[];  // [V][W64][FDB_ROWS]
-  const int i0 = blockIdx.y * FDB_ROWS;
+  const int i0 = row0 + blockIdx.y * FDB_ROWS;
+  const int iend = row0 + nloc;
   const int j = blockIdx.x * FDB_THREADS + threadIdx.x;
   for (int k = threadIdx.x; k < V * W64 * FDB_ROWS; k += FDB_THREADS) {
     int r = k % FDB_ROWS;
     int vw = k / FDB_ROWS;  // v*W64 + w
     int i = i0 + r;
-    s_words[k] = (i < N) ? bs[(size_t)vw * N + i] : 0ull;
+    s_words[k] = (i < iend) ? bs[(size_t)vw * N + i] : 0ull;
   }
   __syncthreads();
   if (j >= M) return;
@@ -150,11 +151,11 @@ __global__ void __launch_bounds__(FDB_THREADS) k_fd_bsc(const uint64_t *__restri
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       int i = i0 + rc + r;
-      if (i < N) {
+      if (i < iend) {
         int m = acc[r][0];
 #pragma unroll
         for (int v = 1; v < V; ++v) m = min(m, acc[r][v]);
-        fd[fd_index(ldM, i, j)] = __half_as_ushort(__int2half_rn(m));
+        fd[fd_index(ldM, i - row0, j)] = __half_as_ushort(__int2half_rn(m));
       }
     }
   }
@@ -186,11 +187,13 @@ __global__ void k_fpfh_center(const float *__restrict__ h, float *__restrict__ h
 
 constexpr int FPT = 16;  // tile edge
 __global__ void __launch_bounds__(FPT *FPT) k_fd_fpfh(const float *__restrict__ sc, const float *__restrict__ tc,
-                                                       float *__restrict__ fd, int N, int M, size_t ldM) {
+                                                       float *__restrict__ fd, int N, int M, size_t ldM, int row0,
+                                                       int nloc) {
   __shared__ float s_s[FPT][37];
   __shared__ float s_t[FPT][37];
   const int tx = threadIdx.x % FPT, ty = threadIdx.x / FPT;
-  const int i0 = blockIdx.y * FPT, j0 = blockIdx.x * FPT;
+  const int i0 = row0 + blockIdx.y * FPT, j0 = blockIdx.x * FPT;
+  N = row0 + nloc;  // rows of this shard end here
   for (int k = threadIdx.x; k < FPT * 36; k += FPT * FPT) {
     int r = k / 36, q = k % 36;
     s_s[r][q] = (i0 + r < N) ? sc[(size_t)(i0 + r) * 36 + q] : 0.f;
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(FPT *FPT) k_fd_fpfh(const float *__restrict__ 
 #pragma unroll
   for (int k = 0; k < 33; ++k) up += s_s[ty][k] * s_t[tx][k];
   float d = up / sqrtf(s_s[ty][33] * s_t[tx][33]);
-  fd[fd_index(ldM, i, j)] = fabsf(d);
+  fd[fd_index(ldM, i - row0, j)] = fabsf(d);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -220,6 +223,7 @@ struct SweepArgs {
   const float *fdf;
   size_t ldM;
   int N, M, n_chunks, cols_per_chunk;
+  int row0, nloc;  // source rows [row0, row0 + nloc) held by this context
   CostParams cp;
   // mode 0
   double *part_cd; int *part_idx; double *part_stats;
@@ -238,9 +242,9 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_rowsweep(const SweepArgs a) {
   __shared__ double s_bv[TR][SWEEP_THREADS / 32];
   __shared__ int s_bi[TR][SWEEP_THREADS / 32];
   const int tid = threadIdx.x;
-  const int i0 = blockIdx.x * TR;
+  const int i0 = a.row0 + blockIdx.x * TR;
   const int chunk = blockIdx.y;
-  const int nrows = min(TR, a.N - i0);
+  const int nrows = min(TR, a.row0 + a.nloc - i0);
   const int c0 = chunk * a.cols_per_chunk;
   const int c1 = min(a.M, c0 + a.cols_per_chunk);
   if (tid < 3 * TR) {
@@ -272,11 +276,11 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_rowsweep(const SweepArgs a) {
         const double sx = s_src[0][r], sy = s_src[1][r], sz = s_src[2][r];
         double fdv[COLS_PER_THREAD];
         if (FT == GHICP_FT_BSC) {
-          const uint2 q = *reinterpret_cast<const uint2 *>(a.fd16 + fd_index(a.ldM, i0 + r, j));
+          const uint2 q = *reinterpret_cast<const uint2 *>(a.fd16 + fd_index(a.ldM, i0 + r - a.row0, j));
           fdv[0] = h2d(q.x & 0xffffu); fdv[1] = h2d(q.x >> 16);
           fdv[2] = h2d(q.y & 0xffffu); fdv[3] = h2d(q.y >> 16);
         } else if (FT == GHICP_FT_FPFH) {
-          const float4 q = *reinterpret_cast<const float4 *>(a.fdf + fd_index(a.ldM, i0 + r, j));
+          const float4 q = *reinterpret_cast<const float4 *>(a.fdf + fd_index(a.ldM, i0 + r - a.row0, j));
           fdv[0] = (double)q.x; fdv[1] = (double)q.y; fdv[2] = (double)q.z; fdv[3] = (double)q.w;
         } else {
           fdv[0] = fdv[1] = fdv[2] = fdv[3] = 0.0;
@@ -358,6 +362,7 @@ struct ColArgs {
   const float *fdf;
   size_t ldM;
   int N, M;
+  int row0, nloc;
   CostParams cp;
   double *col_cd; int *col_idx;
 };
@@ -379,18 +384,18 @@ __global__ void __launch_bounds__(COL_THREADS) k_colsweep(const ColArgs a) {
 #pragma unroll
   for (int c = 0; c < CT; ++c) { best[c] = MAXVALIUE; bidx[c] = 0; }
   const double *sxp = a.s, *syp = a.s + a.N, *szp = a.s + 2 * (size_t)a.N;
-  for (int i = tid; i < a.N; i += COL_THREADS) {
+  for (int i = a.row0 + tid; i < a.row0 + a.nloc; i += COL_THREADS) {
     const double sx = sxp[i], sy = syp[i], sz = szp[i];
     double fdv[CT];
     if (FT == GHICP_FT_BSC) {
-      const uint4 q = *reinterpret_cast<const uint4 *>(a.fd16 + fd_index(a.ldM, i, j0));
+      const uint4 q = *reinterpret_cast<const uint4 *>(a.fd16 + fd_index(a.ldM, i - a.row0, j0));
       fdv[0] = h2d(q.x & 0xffffu); fdv[1] = h2d(q.x >> 16);
       fdv[2] = h2d(q.y & 0xffffu); fdv[3] = h2d(q.y >> 16);
       fdv[4] = h2d(q.z & 0xffffu); fdv[5] = h2d(q.z >> 16);
       fdv[6] = h2d(q.w & 0xffffu); fdv[7] = h2d(q.w >> 16);
     } else if (FT == GHICP_FT_FPFH) {
-      const float4 q0 = *reinterpret_cast<const float4 *>(a.fdf + fd_index(a.ldM, i, j0));
-      const float4 q1 = *reinterpret_cast<const float4 *>(a.fdf + fd_index(a.ldM, i, j0 + 4));
+      const float4 q0 = *reinterpret_cast<const float4 *>(a.fdf + fd_index(a.ldM, i - a.row0, j0));
+      const float4 q1 = *reinterpret_cast<const float4 *>(a.fdf + fd_index(a.ldM, i - a.row0, j0 + 4));
       fdv[0] = q0.x; fdv[1] = q0.y; fdv[2] = q0.z; fdv[3] = q0.w;
       fdv[4] = q1.x; fdv[5] = q1.y; fdv[6] = q1.z; fdv[7] = q1.w;
     } else {
@@ -427,18 +432,20 @@ __global__ void __launch_bounds__(COL_THREADS) k_colsweep(const ColArgs a) {
 // (src/ghicp_reg.cpp:228-239, 264-287, 317-335).  One CTA.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_finalize(const double *__restrict__ part_cd,
-                                                   const int *__restrict__ part_idx, int n_chunks, int N, int M,
+                                                   const int *__restrict__ part_idx, int n_chunks, int row0, int nloc,
                                                    const double *__restrict__ part_stats, int n_parts,
                                                    double *__restrict__ row_cd, int *__restrict__ row_idx,
-                                                   int feature_type, double pivot, LoopScalars ls,
-                                                   DevIter *iter) {
+                                                   float *__restrict__ row_fd, const uint16_t *__restrict__ fd16,
+                                                   const float *__restrict__ fdf, size_t fd_rows,
+                                                   double *__restrict__ xstats /* [world][2] */, int rank) {
   __shared__ double smem[2 * 32];
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+  for (int i = row0 + threadIdx.x; i < row0 + nloc; i += blockDim.x) {
     double v = part_cd[(size_t)i * n_chunks];
     int ix = part_idx[(size_t)i * n_chunks];
     for (int c = 1; c < n_chunks; ++c) lexmin(v, ix, part_cd[(size_t)i * n_chunks + c], part_idx[(size_t)i * n_chunks + c]);
     row_cd[i] = v;
     row_idx[i] = ix;
+    row_fd[i] = fd16 ? (float)h2d(fd16[fd_index(fd_rows, i - row0, ix)]) : (fdf ? fdf[fd_index(fd_rows, i - row0, ix)] : 0.f);
   }
   double acc[2] = {0.0, 0.0};
   for (int p = threadIdx.x; p < n_parts; p += blockDim.x) {
@@ -447,33 +454,45 @@ __global__ void __launch_bounds__(1024) k_finalize(const double *__restrict__ pa
   }
   block_sum<2, 1024>(acc, smem);
   if (threadIdx.x == 0) {
-    const double S1 = acc[0], S2 = acc[1];
-    const double n = (double)N * (double)M;
-    const double CDmean = pivot + S1 / M / N;
-    double var = (S2 - S1 * S1 / n) / n;
-    if (var < 0.0) var = 0.0;
-    const double CDstd = sqrt(var);
-    double penalty;
-    if (feature_type == GHICP_FT_BSC) {
-      if (ls.iteration > 1)
-        penalty = ls.RMS * ls.para1 * ls.scale * ls.WED + (ls.FDM + ls.para2 * ls.FDstd) * ls.WFD;
-      else
-        penalty = (CDmean - ls.penalty_initial * CDstd);
-      penalty = fmax(penalty, 5.0);
-    } else if (feature_type == GHICP_FT_FPFH) {
-      if (ls.iteration > 1)
-        penalty = ls.RMS * ls.para1 * ls.scale * ls.para2;
-      else
-        penalty = (CDmean / ls.penalty_initial);
-    } else {
-      penalty = fmax(CDmean, 1.0);
-    }
-    iter->cd_sum_shift = S1;
-    iter->cd_sumsq_shift = S2;
-    iter->cd_mean = CDmean;
-    iter->cd_std = (feature_type == GHICP_FT_BSC) ? CDstd : 0.0;
-    iter->penalty = penalty;
+    xstats[4 * rank] = acc[0];
+    xstats[4 * rank + 1] = acc[1];
+    xstats[4 * rank + 2] = 0.0;
   }
+}
+
+// CD mean / std over the whole N x M matrix from the per-rank partial sums (fixed rank order: every rank
+// computes bit-identical values) and the penalty rule (src/ghicp_reg.cpp:228-239, 264-287, 317-335).
+__global__ void k_penalty(const double *__restrict__ xstats, int world, double pivot, int N, int M, int feature_type,
+                          LoopScalars ls, DevIter *iter) {
+  double S1 = 0.0, S2 = 0.0;
+  double ovf = 0.0;
+  for (int r = 0; r < world; ++r) { S1 += xstats[4 * r]; S2 += xstats[4 * r + 1]; ovf += xstats[4 * r + 2]; }
+  iter->overflow_any = ovf > 0.0 ? 1 : 0;
+  const double n = (double)N * (double)M;
+  const double CDmean = pivot + S1 / M / N;
+  double var = (S2 - S1 * S1 / n) / n;
+  if (var < 0.0) var = 0.0;
+  const double CDstd = sqrt(var);
+  double penalty;
+  if (feature_type == GHICP_FT_BSC) {
+    if (ls.iteration > 1)
+      penalty = ls.RMS * ls.para1 * ls.scale * ls.WED + (ls.FDM + ls.para2 * ls.FDstd) * ls.WFD;
+    else
+      penalty = (CDmean - ls.penalty_initial * CDstd);
+    penalty = fmax(penalty, 5.0);
+  } else if (feature_type == GHICP_FT_FPFH) {
+    if (ls.iteration > 1)
+      penalty = ls.RMS * ls.para1 * ls.scale * ls.para2;
+    else
+      penalty = (CDmean / ls.penalty_initial);
+  } else {
+    penalty = fmax(CDmean, 1.0);
+  }
+  iter->cd_sum_shift = S1;
+  iter->cd_sumsq_shift = S2;
+  iter->cd_mean = CDmean;
+  iter->cd_std = (feature_type == GHICP_FT_BSC) ? CDstd : 0.0;
+  iter->penalty = penalty;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -536,7 +555,8 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int *__restrict__ cn
 __global__ void __launch_bounds__(1024) k_select(int kind, int n, int n_cols, const double *__restrict__ row_cd,
                                                  const int *__restrict__ row_idx, const int *__restrict__ col_idx,
                                                  const int *__restrict__ owner, int *__restrict__ sp,
-                                                 int *__restrict__ tp, DevIter *iter, double amb_rel) {
+                                                 int *__restrict__ tp, const float *__restrict__ row_fd,
+                                                 float *__restrict__ pair_fd, DevIter *iter, double amb_rel) {
   __shared__ long long smem[33];
   const double penalty = iter->penalty;
   if (threadIdx.x == 0) iter->ambiguous = 0;
@@ -562,7 +582,7 @@ __global__ void __launch_bounds__(1024) k_select(int kind, int n, int n_cols, co
   for (int k = b; k < e; ++k) {
     if (keep(k)) {
       if (kind == 2) { sp[off] = owner[k]; tp[off] = k; }
-      else { sp[off] = k; tp[off] = row_idx[k]; }
+      else { sp[off] = k; tp[off] = row_idx[k]; pair_fd[off] = row_fd[k]; }
       ++off;
     }
   }
@@ -691,8 +711,7 @@ __device__ void umeyama_from_moments_f32(const float mu_s[3], const float mu_d[3
 // ---------------------------------------------------------------------------------------------
 struct SolveArgs {
   const double *s, *t;
-  const uint16_t *fd16;
-  const float *fdf;
+  const float *pair_fd;  // FD of every pair (gathered by the selection step), or nullptr
   size_t ldM;
   int N, M, feature_type;
   const int *sp, *tp;
@@ -717,9 +736,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(const SolveArgs a) {
       const int i = a.sp[p], j = a.tp[p];
       sx = a.s[i]; sy = a.s[(size_t)a.N + i]; sz = a.s[2 * (size_t)a.N + i];
       tx = a.t[j]; ty = a.t[(size_t)a.M + j]; tz = a.t[2 * (size_t)a.M + j];
-      if (a.feature_type == GHICP_FT_BSC && a.fd16) fd = h2d(a.fd16[fd_index(a.ldM, i, j)]);
-      else if (a.feature_type == GHICP_FT_FPFH && a.fdf) fd = (double)a.fdf[fd_index(a.ldM, i, j)];
-      else fd = 0.0;
+      fd = (a.pair_fd && a.feature_type != GHICP_FT_NONE) ? (double)a.pair_fd[p] : 0.0;
     }
   };
   // pass 1
@@ -818,11 +835,27 @@ __global__ void k_apply(double *__restrict__ s, int N, const DevIter *__restrict
 }
 
 __global__ void k_fd_to_double(const uint16_t *__restrict__ fd16, const float *__restrict__ fdf, size_t ldM,
-                               int N, int M, double *__restrict__ out) {
+                               int N, int M, int row0, int nloc, double *__restrict__ out) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)N * M) return;
-  const size_t i = idx / M, j = idx % M;
-  out[idx] = fd16 ? h2d(fd16[fd_index(ldM, (int)i, (int)j)]) : (fdf ? (double)fdf[fd_index(ldM, (int)i, (int)j)] : 0.0);
+  const int i = (int)(idx / M), j = (int)(idx % M);
+  if (i < row0 || i >= row0 + nloc) { out[idx] = 0.0; return; }  // rows held by another rank
+  out[idx] = fd16 ? h2d(fd16[fd_index(ldM, i - row0, j)]) : (fdf ? (double)fdf[fd_index(ldM, i - row0, j)] : 0.0);
+}
+
+// KM: FD of every kept pair, looked up in the candidate CSR (every rank holds the full CSR, not the full plane)
+__global__ void k_pair_fd_km(const int *__restrict__ sp, const int *__restrict__ tp, const DevIter *iter,
+                             const long long *__restrict__ rowptr, const int *__restrict__ csr_col,
+                             const float *__restrict__ csr_fd, float *__restrict__ pair_fd) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int cor = iter->cor;
+  for (int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < cor; p += warps) {
+    const int i = sp[p], j = tp[p];
+    const long long b = rowptr[i], e = rowptr[i + 1];
+    for (long long k = b + lane; k < e; k += 32)
+      if (csr_col[k] == j) pair_fd[p] = csr_fd[k];
+  }
 }
 
 template <typename F>
@@ -855,12 +888,12 @@ cudaError_t launch_pack_bsc(Ctx *c, const uint8_t *d_raw_s, const uint8_t *d_raw
 
 cudaError_t launch_fd_bsc(Ctx *c) {
   const int V = (c->cfg.dof == 6) ? 4 : 2;  // src/ghicp_reg.cpp:178-182
-  dim3 grid((c->M + FDB_THREADS - 1) / FDB_THREADS, (c->N + FDB_ROWS - 1) / FDB_ROWS);
+  dim3 grid((c->M + FDB_THREADS - 1) / FDB_THREADS, (c->nloc + FDB_ROWS - 1) / FDB_ROWS);
   size_t smem = (size_t)V * c->W64 * FDB_ROWS * sizeof(uint64_t);
   if (V == 4)
-    k_fd_bsc<4><<<grid, FDB_THREADS, smem, c->stream>>>(c->d_bs, c->d_bt, c->d_fd16, c->N, c->M, c->fd_rows, c->W64);
+    k_fd_bsc<4><<<grid, FDB_THREADS, smem, c->stream>>>(c->d_bs, c->d_bt, c->d_fd16, c->N, c->M, c->fd_rows, c->W64, c->r0, c->nloc);
   else
-    k_fd_bsc<2><<<grid, FDB_THREADS, smem, c->stream>>>(c->d_bs, c->d_bt, c->d_fd16, c->N, c->M, c->fd_rows, c->W64);
+    k_fd_bsc<2><<<grid, FDB_THREADS, smem, c->stream>>>(c->d_bs, c->d_bt, c->d_fd16, c->N, c->M, c->fd_rows, c->W64, c->r0, c->nloc);
   c->launches++;
   return cudaGetLastError();
 }
@@ -872,8 +905,8 @@ cudaError_t launch_fd_fpfh(Ctx *c) {
   if ((e = cudaMallocAsync(&tc, (size_t)c->M * 36 * sizeof(float), c->stream)) != cudaSuccess) return e;
   k_fpfh_center<<<(c->N + 127) / 128, 128, 0, c->stream>>>(c->d_fs, sc, c->N);
   k_fpfh_center<<<(c->M + 127) / 128, 128, 0, c->stream>>>(c->d_ft, tc, c->M);
-  dim3 grid((c->M + FPT - 1) / FPT, (c->N + FPT - 1) / FPT);
-  k_fd_fpfh<<<grid, FPT * FPT, 0, c->stream>>>(sc, tc, c->d_fdf, c->N, c->M, c->fd_rows);
+  dim3 grid((c->M + FPT - 1) / FPT, (c->nloc + FPT - 1) / FPT);
+  k_fd_fpfh<<<grid, FPT * FPT, 0, c->stream>>>(sc, tc, c->d_fdf, c->N, c->M, c->fd_rows, c->r0, c->nloc);
   c->launches += 3;
   cudaFreeAsync(sc, c->stream);
   cudaFreeAsync(tc, c->stream);
@@ -884,6 +917,7 @@ cudaError_t launch_rowsweep(Ctx *c, int mode, const CostParams &cp) {
   SweepArgs a{};
   a.s = c->d_s; a.t = c->d_t; a.fd16 = c->d_fd16; a.fdf = c->d_fdf; a.ldM = c->fd_rows;
   a.N = c->N; a.M = c->M; a.n_chunks = c->n_chunks;
+  a.row0 = c->r0; a.nloc = c->nloc;
   int cpc = (c->M + c->n_chunks - 1) / c->n_chunks;
   cpc = (cpc + COLS_PER_THREAD - 1) / COLS_PER_THREAD * COLS_PER_THREAD;
   a.cols_per_chunk = cpc;
@@ -891,7 +925,7 @@ cudaError_t launch_rowsweep(Ctx *c, int mode, const CostParams &cp) {
   a.part_cd = c->d_part_cd; a.part_idx = c->d_part_idx; a.part_stats = c->d_part_stats;
   a.iter = c->d_iter; a.cnt = c->d_cnt; a.rowptr = c->d_rowptr; a.cursor = c->d_cursor;
   a.csr_col = c->d_csr_col; a.csr_gain = c->d_csr_gain;
-  dim3 grid((c->N + TR - 1) / TR, c->n_chunks);
+  dim3 grid((c->nloc + TR - 1) / TR, c->n_chunks);
   cudaError_t e = dispatch_ft(c->cfg.feature_type, [&](auto ft) {
     constexpr int FT = decltype(ft)::value;
     if (mode == 0) k_rowsweep<FT, 0><<<grid, SWEEP_THREADS, 0, c->stream>>>(a);
@@ -906,7 +940,7 @@ cudaError_t launch_rowsweep(Ctx *c, int mode, const CostParams &cp) {
 cudaError_t launch_colsweep(Ctx *c, const CostParams &cp) {
   ColArgs a{};
   a.s = c->d_s; a.t = c->d_t; a.fd16 = c->d_fd16; a.fdf = c->d_fdf; a.ldM = c->fd_rows;
-  a.N = c->N; a.M = c->M; a.cp = cp; a.col_cd = c->d_col_cd; a.col_idx = c->d_col_idx;
+  a.N = c->N; a.M = c->M; a.row0 = c->r0; a.nloc = c->nloc; a.cp = cp; a.col_cd = c->d_col_cd; a.col_idx = c->d_col_idx;
   dim3 grid((c->M + CT - 1) / CT);
   cudaError_t e = dispatch_ft(c->cfg.feature_type, [&](auto ft) {
     constexpr int FT = decltype(ft)::value;
@@ -918,10 +952,23 @@ cudaError_t launch_colsweep(Ctx *c, const CostParams &cp) {
 }
 
 cudaError_t launch_finalize_stats(Ctx *c, const CostParams &cp, const LoopScalars &ls) {
-  const int n_parts = ((c->N + TR - 1) / TR) * c->n_chunks;
-  k_finalize<<<1, 1024, 0, c->stream>>>(c->d_part_cd, c->d_part_idx, c->n_chunks, c->N, c->M, c->d_part_stats,
-                                        n_parts, c->d_row_cd, c->d_row_idx, c->cfg.feature_type, cp.pivot, ls,
-                                        c->d_iter);
+  (void)cp; (void)ls;
+  const int n_parts = ((c->nloc + TR - 1) / TR) * c->n_chunks;
+  k_finalize<<<1, 1024, 0, c->stream>>>(c->d_part_cd, c->d_part_idx, c->n_chunks, c->r0, c->nloc, c->d_part_stats,
+                                        n_parts, c->d_row_cd, c->d_row_idx, c->d_row_fd, c->d_fd16, c->d_fdf,
+                                        c->fd_rows, c->d_xstats, c->rank);
+  c->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_penalty(Ctx *c, double pivot, const LoopScalars &ls) {
+  k_penalty<<<1, 1, 0, c->stream>>>(c->d_xstats, c->world, pivot, c->N, c->M, c->cfg.feature_type, ls, c->d_iter);
+  c->launches++;
+  return cudaGetLastError();
+}
+cudaError_t launch_pair_fd_km(Ctx *c) {
+  k_pair_fd_km<<<148 * 2, 256, 0, c->stream>>>(c->d_sp, c->d_tp, c->d_iter, c->d_rowptr, c->d_csr_col, c->d_csr_fd,
+                                               c->d_pair_fd);
   c->launches++;
   return cudaGetLastError();
 }
@@ -934,17 +981,17 @@ cudaError_t launch_scan_counts(Ctx *c) {
 }
 
 cudaError_t launch_select_nn(Ctx *c, double amb_rel) {
-  k_select<<<1, 1024, 0, c->stream>>>(0, c->N, c->M, c->d_row_cd, c->d_row_idx, nullptr, nullptr, c->d_sp, c->d_tp, c->d_iter, amb_rel);
+  k_select<<<1, 1024, 0, c->stream>>>(0, c->N, c->M, c->d_row_cd, c->d_row_idx, nullptr, nullptr, c->d_sp, c->d_tp, c->d_row_fd, c->d_pair_fd, c->d_iter, amb_rel);
   c->launches++;
   return cudaGetLastError();
 }
 cudaError_t launch_select_nnr(Ctx *c) {
-  k_select<<<1, 1024, 0, c->stream>>>(1, c->N, c->M, c->d_row_cd, c->d_row_idx, c->d_col_idx, nullptr, c->d_sp, c->d_tp, c->d_iter, 0.0);
+  k_select<<<1, 1024, 0, c->stream>>>(1, c->N, c->M, c->d_row_cd, c->d_row_idx, c->d_col_idx, nullptr, c->d_sp, c->d_tp, c->d_row_fd, c->d_pair_fd, c->d_iter, 0.0);
   c->launches++;
   return cudaGetLastError();
 }
 cudaError_t launch_select_km(Ctx *c) {
-  k_select<<<1, 1024, 0, c->stream>>>(2, c->M, c->M, nullptr, nullptr, nullptr, c->d_owner, c->d_sp, c->d_tp, c->d_iter, 0.0);
+  k_select<<<1, 1024, 0, c->stream>>>(2, c->M, c->M, nullptr, nullptr, nullptr, c->d_owner, c->d_sp, c->d_tp, nullptr, nullptr, c->d_iter, 0.0);
   c->launches++;
   return cudaGetLastError();
 }
@@ -952,7 +999,7 @@ cudaError_t launch_select_km(Ctx *c) {
 cudaError_t launch_solve(Ctx *c, const CostParams &cp) {
   SolveArgs a{};
   a.cp = cp;
-  a.s = c->d_s; a.t = c->d_t; a.fd16 = c->d_fd16; a.fdf = c->d_fdf; a.ldM = c->fd_rows;
+  a.s = c->d_s; a.t = c->d_t; a.pair_fd = c->d_pair_fd; a.ldM = c->fd_rows;
   a.N = c->N; a.M = c->M; a.feature_type = c->cfg.feature_type;
   a.sp = c->d_sp; a.tp = c->d_tp; a.sxyz_pairs = nullptr; a.txyz_pairs = nullptr; a.n_explicit = 0;
   a.iter = c->d_iter;
@@ -977,7 +1024,7 @@ cudaError_t launch_apply(Ctx *c) {
 
 cudaError_t launch_get_fd(Ctx *c, double *d_out) {
   const size_t total = (size_t)c->N * c->M;
-  k_fd_to_double<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(c->d_fd16, c->d_fdf, c->fd_rows, c->N, c->M, d_out);
+  k_fd_to_double<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(c->d_fd16, c->d_fdf, c->fd_rows, c->N, c->M, c->r0, c->nloc, d_out);
   c->launches++;
   return cudaGetLastError();
 }

@@ -89,7 +89,7 @@ __device__ __noinline__ double exact_cd(const StreamArgs &a, int i, int j) {
   const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
   const double ed = __dmul_rn(a.scale, __dsqrt_rn(d2));
   if (a.fd) {
-    const double fd = (double)__half2float(__ushort_as_half(a.fd[fd_index(a.fd_rows, i, j)]));
+    const double fd = (double)__half2float(__ushort_as_half(a.fd[fd_index(a.fd_rows, i - a.row0, j)]));
     return __dadd_rn(__dmul_rn(a.WED, ed), __dmul_rn(a.WFD, fd));
   }
   return ed;
@@ -148,7 +148,7 @@ __global__ void k_margin(StreamDev *dev, double A, double a, double b, double fd
 __global__ void k_seed(StreamArgs a, const int *__restrict__ prev_row_idx, const int *__restrict__ prev_col_idx,
                        int have_prev) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < a.N) {
+  if (k >= a.row0 && k < a.row0 + a.nloc) {
     unsigned bits = INF_BITS;
     if (have_prev) {
       int j = prev_row_idx[k];
@@ -162,7 +162,7 @@ __global__ void k_seed(StreamArgs a, const int *__restrict__ prev_row_idx, const
     unsigned bits = INF_BITS;
     if (have_prev) {
       int i = prev_col_idx[k];
-      if (i >= 0 && i < a.N) bits = __float_as_uint(__double2float_ru(exact_cd(a, i, k)));
+      if (i >= a.row0 && i < a.row0 + a.nloc) bits = __float_as_uint(__double2float_ru(exact_cd(a, i, k)));
     }
     a.col_thr_init[k] = bits;
     a.colbest[k] = ~0ull;
@@ -224,10 +224,10 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, u
   const float thr_hi = a.dev->thr_hi;
   const float b = a.b;
   const bool lane_loads = true;  // the panel-major plane is allocated in whole panels (zero padded)
-  const unsigned short *fdp = HAS_FD ? a.fd + fd_index(a.fd_rows, r0, j0) : nullptr;
+  const unsigned short *fdp = HAS_FD ? a.fd + fd_index(a.fd_rows, r0 - a.row0, j0) : nullptr;
   // ---- TMA ring bookkeeping (warp-private) ----
   const int panel = j0 - lane * ST_CPL;
-  const unsigned short *panel_base = (HAS_FD && TMA) ? a.fd + fd_index(a.fd_rows, r0, panel) : nullptr;
+  const unsigned short *panel_base = (HAS_FD && TMA) ? a.fd + fd_index(a.fd_rows, r0 - a.row0, panel) : nullptr;
   const int nbatch = (nrows + ST_UNROLL - 1) / ST_UNROLL;
   auto issue = [&](int k) {  // lane 0 only
     const int stage = k % ST_STAGES;
@@ -375,8 +375,8 @@ __global__ void __launch_bounds__(ST_THREADS, TMA ? 3 : 2) k_stream(const Stream
   __shared__ int s_cnt[ST_RB];
   __shared__ double s_red[2][ST_WARPS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int r0 = blockIdx.y * ST_RB;
-  const int nrows = min(ST_RB, a.N - r0);
+  const int r0 = a.row0 + blockIdx.y * ST_RB;
+  const int nrows = min(ST_RB, a.row0 + a.nloc - r0);
   for (int r = tid; r < ST_RB; r += ST_THREADS) {
     s_S4[r] = (r < nrows) ? a.S4[r0 + r] : make_float4(0.f, 0.f, 0.f, 0.f);
     s_thr[r] = ((MODE == SM_NN || MODE == SM_NNR || MODE == SM_PRE || MODE == SM_PRE_COLS) && r < nrows) ? a.row_thr_init[r0 + r] : INF_BITS;
@@ -435,11 +435,15 @@ __global__ void k_resolve(const StreamArgs a, int which) {
     }
   }
 }
-__global__ void k_publish(const StreamArgs a, double *row_cd, int *row_idx, double *col_cd, int *col_idx) {
+__global__ void k_publish(const StreamArgs a, double *row_cd, int *row_idx, double *col_cd, int *col_idx,
+                          double *xstats, int rank) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < a.N) {
+  if (k == 0) xstats[4 * rank + 2] = a.dev->overflow ? 1.0 : 0.0;  // travels with the statistics
+  if (k >= a.row0 && k < a.row0 + a.nloc) {
     row_cd[k] = __longlong_as_double((long long)a.rowbest[k]);
-    row_idx[k] = a.rowidx[k];
+    const int j = a.rowidx[k];
+    row_idx[k] = j;
+    a.row_fd[k] = (a.fd && j >= 0 && j < a.M) ? __half2float(__ushort_as_half(a.fd[fd_index(a.fd_rows, k - a.row0, j)])) : 0.f;
   }
   if (col_cd && k < a.M) {
     col_cd[k] = __longlong_as_double((long long)a.colbest[k]);
@@ -447,9 +451,9 @@ __global__ void k_publish(const StreamArgs a, double *row_cd, int *row_idx, doub
   }
 }
 
-// fast statistics → mean / std / penalty (src/ghicp_reg.cpp:228-239, 264-287)
-__global__ void __launch_bounds__(1024) k_finalize_fast(const double *__restrict__ part_stats, int n_parts, int N,
-                                                        int M, int feature_type, LoopScalars ls, DevIter *iter) {
+// fast statistics: this rank's partial sums of CD and CD^2 (the penalty rule runs in k_penalty)
+__global__ void __launch_bounds__(1024) k_finalize_fast(const double *__restrict__ part_stats, int n_parts,
+                                                        double *__restrict__ xstats, int rank) {
   __shared__ double sm[2][32];
   double a0 = 0.0, a1 = 0.0;
   for (int p = threadIdx.x; p < n_parts; p += blockDim.x) { a0 += part_stats[2 * p]; a1 += part_stats[2 * p + 1]; }
@@ -461,24 +465,9 @@ __global__ void __launch_bounds__(1024) k_finalize_fast(const double *__restrict
   if (threadIdx.x == 0) {
     double S1 = 0.0, S2 = 0.0;
     for (int w = 0; w < 32; ++w) { S1 += sm[0][w]; S2 += sm[1][w]; }
-    const double n = (double)N * (double)M;
-    const double CDmean = S1 / M / N;
-    double var = (S2 - S1 * S1 / n) / n;
-    if (var < 0.0) var = 0.0;
-    const double CDstd = sqrt(var);
-    double penalty;
-    if (feature_type == GHICP_FT_BSC) {
-      if (ls.iteration > 1) penalty = ls.RMS * ls.para1 * ls.scale * ls.WED + (ls.FDM + ls.para2 * ls.FDstd) * ls.WFD;
-      else penalty = (CDmean - ls.penalty_initial * CDstd);
-      penalty = fmax(penalty, 5.0);
-    } else {
-      penalty = fmax(CDmean, 1.0);
-    }
-    iter->cd_sum_shift = S1;
-    iter->cd_sumsq_shift = S2;
-    iter->cd_mean = CDmean;
-    iter->cd_std = (feature_type == GHICP_FT_BSC) ? CDstd : 0.0;
-    iter->penalty = penalty;
+    xstats[4 * rank] = S1;
+    xstats[4 * rank + 1] = S2;
+    xstats[4 * rank + 2] = 0.0;
   }
 }
 // BSC iterations > 1: the penalty does not depend on this iteration's statistics (src/ghicp_reg.cpp:279-282)
@@ -494,11 +483,12 @@ __global__ void __launch_bounds__(256) k_csr_check(const StreamArgs a, const Dev
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const double penalty = iter->penalty;
   int valid = 0;
-  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < a.N; i += warps) {
+  for (int i = a.row0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); i < a.row0 + a.nloc; i += warps) {
     const long long b = a.rowptr[i], e = a.rowptr[i + 1];
     for (long long k = b + lane; k < e; k += 32) {
       const int j = a.csr_col[k];
       const double cd = exact_cd(a, i, j);
+      a.csr_fd[k] = a.fd ? __half2float(__ushort_as_half(a.fd[fd_index(a.fd_rows, i - a.row0, j)])) : 0.f;
       if (cd < penalty) { csr_gain[k] = penalty - cd; ++valid; }
       else csr_gain[k] = -1e300;
     }
@@ -553,6 +543,8 @@ static StreamArgs make_args(Ctx *c, const CostParams &cp) {
   StreamArgs a{};
   a.fd = (c->cfg.feature_type == GHICP_FT_BSC) ? c->d_fd16 : nullptr;
   a.fd_rows = c->fd_rows; a.N = c->N; a.M = c->M;
+  a.row0 = c->r0; a.nloc = c->nloc;
+  a.row_fd = c->d_row_fd; a.csr_fd = c->d_csr_fd;
   a.S4 = reinterpret_cast<const float4 *>(c->d_S4); a.T4 = reinterpret_cast<const float4 *>(c->d_T4);
   a.s = c->d_s; a.t = c->d_t;
   a.scale = cp.scale; a.WED = cp.WED; a.WFD = cp.WFD;
@@ -567,7 +559,7 @@ static StreamArgs make_args(Ctx *c, const CostParams &cp) {
 }
 
 static dim3 stream_grid(const Ctx *c) {
-  return dim3((c->M + ST_CTA_COLS - 1) / ST_CTA_COLS, (c->N + ST_RB - 1) / ST_RB);
+  return dim3((c->M + ST_CTA_COLS - 1) / ST_CTA_COLS, (c->nloc + ST_RB - 1) / ST_RB);
 }
 int stream_num_parts(const Ctx *c) {
   dim3 g = stream_grid(c);
@@ -650,19 +642,54 @@ cudaError_t launch_stream_resolve(Ctx *c, const CostParams &cp, bool with_cols) 
   if (with_cols) k_resolve<<<148 * 4, 256, 0, c->stream>>>(a, 1);
   const int n = c->N > c->M ? c->N : c->M;
   k_publish<<<(n + 255) / 256, 256, 0, c->stream>>>(a, c->d_row_cd, c->d_row_idx, with_cols ? c->d_col_cd : nullptr,
-                                                    with_cols ? c->d_col_idx : nullptr);
+                                                    with_cols ? c->d_col_idx : nullptr, c->d_xstats, c->rank);
   c->launches += with_cols ? 3 : 2;
   return cudaGetLastError();
 }
 
 cudaError_t launch_finalize_fast(Ctx *c, const LoopScalars &ls) {
-  k_finalize_fast<<<1, 1024, 0, c->stream>>>(c->d_part_stats, stream_num_parts(c), c->N, c->M, c->cfg.feature_type, ls,
-                                             c->d_iter);
+  (void)ls;
+  k_finalize_fast<<<1, 1024, 0, c->stream>>>(c->d_part_stats, stream_num_parts(c), c->d_xstats, c->rank);
   c->launches++;
   return cudaGetLastError();
 }
 cudaError_t launch_penalty_only(Ctx *c, const LoopScalars &ls) {
   k_penalty_only<<<1, 1, 0, c->stream>>>(ls, c->d_iter);
+  c->launches++;
+  return cudaGetLastError();
+}
+// NNR with sharded rows: per-rank column minima (ordered-double bits, row index) gathered as [world][M];
+// keep the lexicographic minimum (ranks own ascending row ranges, so equal values keep the smaller row).
+__global__ void k_colmerge(const unsigned long long *__restrict__ g_cd, const int *__restrict__ g_idx, int world, int M,
+                           double *__restrict__ col_cd, int *__restrict__ col_idx) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= M) return;
+  unsigned long long best = g_cd[j];
+  int bi = g_idx[j];
+  for (int r = 1; r < world; ++r) {
+    const unsigned long long v = g_cd[(size_t)r * M + j];
+    const int i = g_idx[(size_t)r * M + j];
+    if (v < best || (v == best && i < bi)) { best = v; bi = i; }
+  }
+  col_cd[j] = __longlong_as_double((long long)best);
+  col_idx[j] = bi;
+}
+cudaError_t launch_colmerge(Ctx *c) {
+  k_colmerge<<<(c->M + 255) / 256, 256, 0, c->stream>>>(c->d_colg_cd, c->d_colg_idx, c->world, c->M, c->d_col_cd, c->d_col_idx);
+  c->launches++;
+  return cudaGetLastError();
+}
+__global__ void k_count_valid(const double *__restrict__ gain, long long nnz, StreamDev *dev) {
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int v = 0;
+  for (; k < nnz; k += (long long)gridDim.x * blockDim.x) v += gain[k] > 0.0 ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0 && v) atomicAdd(&dev->nnz_valid, (unsigned long long)v);
+}
+cudaError_t launch_count_valid(Ctx *c, long long nnz) {
+  cudaMemsetAsync(&c->d_sdev->nnz_valid, 0, sizeof(unsigned long long), c->stream);
+  k_count_valid<<<148 * 4, 256, 0, c->stream>>>(c->d_csr_gain, nnz, c->d_sdev);
   c->launches++;
   return cudaGetLastError();
 }

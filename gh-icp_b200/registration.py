@@ -57,7 +57,8 @@ class GHRegistration:
 
     def __init__(self, Kp, Ef, Ft, Ct, radiusNonMax=1.0, weight_adjustment_ratio=1.1,
                  weight_adjustment_step=0.1, dof_type=6, estimated_IoU=0.5,
-                 converge_tran=0.02, converge_rot=0.02, max_iter=0, device=0, km_eps=0.0, force_exact=False):
+                 converge_tran=0.02, converge_rot=0.02, max_iter=0, device=0, km_eps=0.0, force_exact=False,
+                 comm=None):
         self.L = capi.lib()
         cfg = capi.Config()
         cfg.feature_type, cfg.corr_type, cfg.dof = Ft, Ct, dof_type
@@ -70,6 +71,10 @@ class GHRegistration:
         cfg.force_exact = 1 if force_exact else 0
         self.ctx = C.c_void_p()
         capi.check(self.L.ghicp_create(C.byref(cfg), C.byref(self.ctx)))
+        if comm is not None:  # (unique_id bytes, rank, world): one process per GPU, source rows sharded
+            uid, rank, world = comm
+            buf = (C.c_char * 128).from_buffer_copy(uid) if world > 1 else None
+            capi.check(self.L.ghicp_comm_init(self.ctx, buf, rank, world), self.ctx)
         self.N, self.M = Kp.kps_num, Kp.kpt_num
         self.Ft, self.Ct = Ft, Ct
         self.upload(Kp)

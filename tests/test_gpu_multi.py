@@ -1,0 +1,72 @@
+"""Multi-GPU path (one process per GPU, source rows sharded, NCCL exchange): every rank must reproduce the
+single-GPU result exactly (NN / NNR: identical pair lists and bit-identical transforms; KM: same candidate
+graph, identical replicated auction).  Needs >= 2 GPUs: run with `gpurun --gpus 2`."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys, pickle
+import numpy as np
+sys.path.insert(0, %(root)r)
+import torch, torch.distributed as dist
+import ghicp_b200 as g
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("gloo")          # rendezvous only: the data path uses NCCL inside the library
+uid = [g.comm_unique_id() if rank == 0 else None]
+dist.broadcast_object_list(uid, src=0)
+mode = sys.argv[1]
+ft = {"none": g.FT_NONE, "bsc": g.FT_BSC}[mode.split("-")[0]]
+ct = {"nn": g.CT_NN, "nnr": g.CT_NNR, "km": g.CT_KM}[mode.split("-")[1]]
+sc = g.synth.gen_points(3001, 2750, overlap=0.6, extent=(80, 80, 16), noise=0.04, seed=31)
+if ft == g.FT_BSC: g.synth.add_bsc(sc, bits=441, V=4)
+reg = g.registration.from_scene(sc, ft, ct, device=rank, comm=(uid[0], rank, world))
+out = []
+for it in range(6):
+    st = reg.iterate()
+    sp, tp = reg.pairs()
+    out.append(dict(cor=st.cor, penalty=st.penalty, mean=st.cd_mean, Rt=np.array(st.Rt), sp=sp, tp=tp,
+                    energy=st.km_energy, nnz=st.nnz, fb=st.exact_fallback))
+pickle.dump(out, open(os.path.join(sys.argv[2], "rank%%d.pkl" %% rank), "wb"))
+dist.barrier()
+'''
+
+
+@pytest.mark.parametrize("mode", ["none-nn", "bsc-nn", "bsc-nnr", "bsc-km"])
+def test_sharded_equals_single_gpu(g, tmp_path, mode):
+    import pickle
+    if g.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % dict(root=ROOT))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29671", str(script), mode, str(tmp_path)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    ranks = [pickle.load(open(tmp_path / f"rank{k}.pkl", "rb")) for k in range(world)]
+    # single-GPU reference run in this process
+    ft = {"none": g.FT_NONE, "bsc": g.FT_BSC}[mode.split("-")[0]]
+    ct = {"nn": g.CT_NN, "nnr": g.CT_NNR, "km": g.CT_KM}[mode.split("-")[1]]
+    sc = g.synth.gen_points(3001, 2750, overlap=0.6, extent=(80, 80, 16), noise=0.04, seed=31)
+    if ft == g.FT_BSC:
+        g.synth.add_bsc(sc, bits=441, V=4)
+    reg = g.registration.from_scene(sc, ft, ct)
+    for it in range(6):
+        st = reg.iterate()
+        sp, tp = reg.pairs()
+        for k in range(world):
+            o = ranks[k][it]
+            assert o["cor"] == st.cor, (it, k)
+            assert np.array_equal(o["sp"], sp) and np.array_equal(o["tp"], tp), (it, k)
+            assert o["penalty"] == pytest.approx(st.penalty, rel=1e-9)
+            if ct != g.CT_KM:
+                assert np.array_equal(o["Rt"], np.array(st.Rt)), (it, k)
+        assert np.array_equal(ranks[0][it]["Rt"], ranks[1][it]["Rt"])  # ranks stay in lock step
