@@ -70,7 +70,9 @@ struct StreamArgs {
   const float4 *S4, *T4;
   const double *s, *t;
   double scale, WED, WFD;
-  float b;
+  float b;               // feature weight in the filter's (kappa-scaled) domain
+  unsigned short bh;     // the same weight as fp16 bits (FHFMA operand)
+  double kappa;          // scale of the filter domain relative to CD
   StreamDev *dev;
   unsigned *row_thr_init; unsigned long long *rowbest; int *rowidx;
   unsigned *col_thr_init; unsigned long long *colbest; int *colidx;
@@ -145,6 +147,10 @@ struct Ctx {
 
   // streaming path
   bool use_fast = true;
+  bool x2_ok = true;         // packed-FP32 / FHFMA variant usable this iteration
+  double kappa = 1.0;
+  float b_eff = 0.f;
+  unsigned short bh_bits = 0;
   long long last_cands = 0;  // candidates the filter passed to exact evaluation last iteration
   int fallbacks = 0;         // iterations that fell back to the all-double cost kernels
   bool have_prev = false;    // d_row_idx / d_col_idx hold last iteration's partners

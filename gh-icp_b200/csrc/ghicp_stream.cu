@@ -69,6 +69,18 @@ __device__ __forceinline__ float sqrt_approx(float x) {
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
+// packed FP32 pairs (FFMA2 / FADD2 on sm_100a): two columns per instruction, half the issue slots
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(u64 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+// cd = fd(fp16) * weight(fp16) + dist : one FHFMA (the half product is exact in fp32)
+__device__ __forceinline__ float fhfma(unsigned short h, unsigned short w, float c) {
+  float r;
+  asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(r) : "h"(h), "h"(w), "f"(c));
+  return r;
+}
 __device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
@@ -124,7 +136,7 @@ __global__ void k_prep(const double *__restrict__ s, const double *__restrict__ 
 // S, T + 1 add + 3 fma on magnitudes <= 4*A*R^2, R = max centred norm), so |sqrt(d2'_32) - a*dist| <=
 // sqrt(that); sqrt.approx, the fd FFMA and the float weight add 2^-21-relative terms.
 __global__ void k_margin(StreamDev *dev, double A, double a, double b, double fdmax, const DevIter *iter,
-                         int use_iter_penalty, double rel_slack) {
+                         int use_iter_penalty, double rel_slack, double kappa) {
   const double R2 = (double)__uint_as_float(dev->r2max_bits);
   const double E = 32.0 * 5.9604644775390625e-08 * A * R2;
   const double R = sqrt(R2);
@@ -136,7 +148,7 @@ __global__ void k_margin(StreamDev *dev, double A, double a, double b, double fd
   dev->nnz_valid = 0;
   if (use_iter_penalty) {
     // KM gate: superset threshold = penalty*(1+slack) + margin, rounded up
-    const double p = iter->penalty;
+    const double p = iter->penalty * kappa;   // thresholds live in the scaled domain
     dev->thr_hi = __double2float_ru(p + fabs(p) * rel_slack + m);
   } else {
     dev->thr_hi = -1.f;
@@ -152,7 +164,7 @@ __global__ void k_seed(StreamArgs a, const int *__restrict__ prev_row_idx, const
     unsigned bits = INF_BITS;
     if (have_prev) {
       int j = prev_row_idx[k];
-      if (j >= 0 && j < a.M) bits = __float_as_uint(__double2float_ru(exact_cd(a, k, j)));
+      if (j >= 0 && j < a.M) bits = __float_as_uint(__double2float_ru(a.kappa * exact_cd(a, k, j) * 1.0000001));
     }
     a.row_thr_init[k] = bits;
     a.rowbest[k] = ~0ull;
@@ -162,7 +174,7 @@ __global__ void k_seed(StreamArgs a, const int *__restrict__ prev_row_idx, const
     unsigned bits = INF_BITS;
     if (have_prev) {
       int i = prev_col_idx[k];
-      if (i >= a.row0 && i < a.row0 + a.nloc) bits = __float_as_uint(__double2float_ru(exact_cd(a, i, k)));
+      if (i >= a.row0 && i < a.row0 + a.nloc) bits = __float_as_uint(__double2float_ru(a.kappa * exact_cd(a, i, k) * 1.0000001));
     }
     a.col_thr_init[k] = bits;
     a.colbest[k] = ~0ull;
@@ -200,8 +212,8 @@ __device__ __noinline__ void slow_col(const StreamArgs &a, int i, int j, float c
   }
 }
 
-template <int MODE, bool HAS_FD, bool STATS, bool FULL, bool TMA>
-__device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, unsigned *s_thr, int *s_cnt,
+template <int MODE, bool HAS_FD, bool STATS, bool FULL, bool TMA, bool X2>
+__device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, const float *s_S8, unsigned *s_thr, int *s_cnt,
                                       int r0, int nrows, int j0, int lane, double &dsum, double &dsq,
                                       unsigned char *ring, unsigned long long *bars) {
   float Tx[ST_CPL], Ty[ST_CPL], Tz[ST_CPL], Tw[ST_CPL];
@@ -219,6 +231,16 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, u
       colrun[c] = (MODE == SM_PRE_COLS) ? __uint_as_float(INF_BITS) : -1.f;  // never triggers / never written
     }
   }
+  u64 Tx2[ST_CPL / 2], Ty2[ST_CPL / 2], Tz2[ST_CPL / 2], Tw2[ST_CPL / 2];
+  if (X2) {
+#pragma unroll
+    for (int p = 0; p < ST_CPL / 2; ++p) {
+      Tx2[p] = pack2(Tx[2 * p], Tx[2 * p + 1]); Ty2[p] = pack2(Ty[2 * p], Ty[2 * p + 1]);
+      Tz2[p] = pack2(Tz[2 * p], Tz[2 * p + 1]); Tw2[p] = pack2(Tw[2 * p], Tw[2 * p + 1]);
+    }
+  }
+  unsigned short bh = a.bh;
+  asm volatile("mov.b16 %0, %0;" : "+h"(bh));  // keep the weight in a vector register (FHFMA takes no uniform operand)
   const float margin = a.dev->margin;
   const float m2 = 2.f * margin;
   const float thr_hi = a.dev->thr_hi;
@@ -256,6 +278,7 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, u
       }
     }
     float psum = 0.f, psq = 0.f;
+    u64 psum2 = 0ull, psq2 = 0ull;
 #pragma unroll
     for (int u = 0; u < ST_UNROLL; ++u) {
       const int r = rb + u;
@@ -264,6 +287,39 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, u
         if (HAS_FD && TMA)  // just-in-time read of this row's 8 values from the staged segment
           q[u] = *reinterpret_cast<const uint4 *>(ring + ((rb / ST_UNROLL) % ST_STAGES) * ST_STAGE_BYTES + u * ST_SEG_BYTES + lane * 16);
         float cd[ST_CPL];
+        if (X2) {
+          const ulonglong2 sA = *reinterpret_cast<const ulonglong2 *>(s_S8 + r * 8);      // (sx,sx) (sy,sy)
+          const ulonglong2 sB = *reinterpret_cast<const ulonglong2 *>(s_S8 + r * 8 + 4);  // (sz,sz) (sw,sw)
+#pragma unroll
+          for (int p = 0; p < ST_CPL / 2; ++p) {
+            u64 acc = add2(Tw2[p], sB.y);
+            acc = fma2(sB.x, Tz2[p], acc);
+            acc = fma2(sA.y, Ty2[p], acc);
+            acc = fma2(sA.x, Tx2[p], acc);
+            float d0, d1;
+            unpack2(acc, d0, d1);
+            d0 = sqrt_approx(fabsf(d0));   // |.|: a slightly negative d2' (cancellation) stays inside the margin
+            d1 = sqrt_approx(fabsf(d1));
+            if (HAS_FD) {
+              const unsigned w = (p == 0) ? q[u].x : (p == 1) ? q[u].y : (p == 2) ? q[u].z : q[u].w;
+              cd[2 * p] = fhfma((unsigned short)(w & 0xffffu), bh, d0);
+              cd[2 * p + 1] = fhfma((unsigned short)(w >> 16), bh, d1);
+            } else {
+              cd[2 * p] = d0;
+              cd[2 * p + 1] = d1;
+            }
+            if (STATS && FULL) {
+              const u64 c2 = pack2(cd[2 * p], cd[2 * p + 1]);
+              psum2 = add2(psum2, c2);
+              psq2 = fma2(c2, c2, psq2);
+            }
+          }
+          if (STATS && !FULL) {
+#pragma unroll
+            for (int c = 0; c < ST_CPL; ++c)
+              if (j0 + c < a.M) { psum += cd[c]; psq = fmaf(cd[c], cd[c], psq); }
+          }
+        } else {
 #pragma unroll
         for (int c = 0; c < ST_CPL; ++c) {
           float d2 = fmaf(S.x, Tx[c], fmaf(S.y, Ty[c], fmaf(S.z, Tz[c], Tw[c] + S.w)));
@@ -285,6 +341,7 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, u
               psq = fmaf(cd[c], cd[c], psq);
             }
           }
+        }
         }
         if (MODE == SM_PRE || MODE == SM_PRE_COLS) {
           // seed pass: FP32 row (and column) minima only, no decisions
@@ -355,6 +412,13 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, u
       }
     }
     if (STATS) {
+      if (X2 && FULL) {
+        float a0, a1, b0, b1;
+        unpack2(psum2, a0, a1);
+        unpack2(psq2, b0, b1);
+        dsum += (double)a0 + (double)a1;
+        dsq += (double)b0 + (double)b1;
+      }
       dsum += (double)psum;
       dsq += (double)psq;
     }
@@ -366,8 +430,9 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, u
   }
 }
 
-template <int MODE, bool HAS_FD, bool STATS, bool TMA>
+template <int MODE, bool HAS_FD, bool STATS, bool TMA, bool X2>
 __global__ void __launch_bounds__(ST_THREADS, TMA ? 3 : 2) k_stream(const StreamArgs a) {
+  __shared__ __align__(16) float s_S8[X2 ? ST_RB * 8 : 8];
   extern __shared__ __align__(128) unsigned char s_ring[];   // [ST_WARPS][ST_RING_BYTES] when TMA
   __shared__ __align__(8) unsigned long long s_bar[ST_WARPS][ST_STAGES];
   __shared__ float4 s_S4[ST_RB];
@@ -378,7 +443,12 @@ __global__ void __launch_bounds__(ST_THREADS, TMA ? 3 : 2) k_stream(const Stream
   const int r0 = a.row0 + blockIdx.y * ST_RB;
   const int nrows = min(ST_RB, a.row0 + a.nloc - r0);
   for (int r = tid; r < ST_RB; r += ST_THREADS) {
-    s_S4[r] = (r < nrows) ? a.S4[r0 + r] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 Sv = (r < nrows) ? a.S4[r0 + r] : make_float4(0.f, 0.f, 0.f, 0.f);
+    s_S4[r] = Sv;
+    if (X2) {
+      float *d = s_S8 + r * 8;
+      d[0] = d[1] = Sv.x; d[2] = d[3] = Sv.y; d[4] = d[5] = Sv.z; d[6] = d[7] = Sv.w;
+    }
     s_thr[r] = ((MODE == SM_NN || MODE == SM_NNR || MODE == SM_PRE || MODE == SM_PRE_COLS) && r < nrows) ? a.row_thr_init[r0 + r] : INF_BITS;
     s_cnt[r] = 0;
   }
@@ -393,9 +463,9 @@ __global__ void __launch_bounds__(ST_THREADS, TMA ? 3 : 2) k_stream(const Stream
   double dsum = 0.0, dsq = 0.0;
   if (panel < a.M) {
     if (panel + ST_PANEL <= a.M)
-      sweep<MODE, HAS_FD, STATS, true, TMA>(a, s_S4, s_thr, s_cnt, r0, nrows, j0, lane, dsum, dsq, ring, s_bar[warp]);
+      sweep<MODE, HAS_FD, STATS, true, TMA, X2>(a, s_S4, s_S8, s_thr, s_cnt, r0, nrows, j0, lane, dsum, dsq, ring, s_bar[warp]);
     else
-      sweep<MODE, HAS_FD, STATS, false, TMA>(a, s_S4, s_thr, s_cnt, r0, nrows, j0, lane, dsum, dsq, ring, s_bar[warp]);
+      sweep<MODE, HAS_FD, STATS, false, TMA, X2>(a, s_S4, s_S8, s_thr, s_cnt, r0, nrows, j0, lane, dsum, dsq, ring, s_bar[warp]);
   }
   if (STATS) {
 #pragma unroll
@@ -453,7 +523,7 @@ __global__ void k_publish(const StreamArgs a, double *row_cd, int *row_idx, doub
 
 // fast statistics: this rank's partial sums of CD and CD^2 (the penalty rule runs in k_penalty)
 __global__ void __launch_bounds__(1024) k_finalize_fast(const double *__restrict__ part_stats, int n_parts,
-                                                        double *__restrict__ xstats, int rank) {
+                                                        double *__restrict__ xstats, int rank, double kappa) {
   __shared__ double sm[2][32];
   double a0 = 0.0, a1 = 0.0;
   for (int p = threadIdx.x; p < n_parts; p += blockDim.x) { a0 += part_stats[2 * p]; a1 += part_stats[2 * p + 1]; }
@@ -465,8 +535,8 @@ __global__ void __launch_bounds__(1024) k_finalize_fast(const double *__restrict
   if (threadIdx.x == 0) {
     double S1 = 0.0, S2 = 0.0;
     for (int w = 0; w < 32; ++w) { S1 += sm[0][w]; S2 += sm[1][w]; }
-    xstats[4 * rank] = S1;
-    xstats[4 * rank + 1] = S2;
+    xstats[4 * rank] = S1 / kappa;               // back from the filter's scaled domain
+    xstats[4 * rank + 1] = S2 / (kappa * kappa);
     xstats[4 * rank + 2] = 0.0;
   }
 }
@@ -548,7 +618,7 @@ static StreamArgs make_args(Ctx *c, const CostParams &cp) {
   a.S4 = reinterpret_cast<const float4 *>(c->d_S4); a.T4 = reinterpret_cast<const float4 *>(c->d_T4);
   a.s = c->d_s; a.t = c->d_t;
   a.scale = cp.scale; a.WED = cp.WED; a.WFD = cp.WFD;
-  a.b = (c->cfg.feature_type == GHICP_FT_BSC) ? (float)cp.WFD : 0.f;
+  a.b = c->b_eff; a.bh = c->bh_bits; a.kappa = c->kappa;
   a.dev = c->d_sdev;
   a.row_thr_init = c->d_row_thr; a.rowbest = c->d_rowbest; a.rowidx = c->d_rowidx2;
   a.col_thr_init = nullptr; a.colbest = c->d_colbest; a.colidx = c->d_colidx2;
@@ -568,23 +638,44 @@ int stream_num_parts(const Ctx *c) {
 
 cudaError_t launch_stream_prep(Ctx *c, const CostParams &cp, int for_km_gate) {
   const bool bsc = c->cfg.feature_type == GHICP_FT_BSC;
-  const double a = bsc ? cp.scale * cp.WED : cp.scale;
+  // The filter works in a domain scaled by kappa = half(WFD)/WFD (|kappa - 1| <= 2^-11) so that the feature
+  // weight is exactly representable in fp16 and cd32 = FHFMA(fd, w_h, dist): argmin and threshold tests are
+  // invariant under the positive scaling; sums are scaled back in k_finalize_fast.
+  double kappa = 1.0;
+  c->x2_ok = true;
+  c->bh_bits = 0;
+  c->b_eff = 0.f;
+  if (bsc) {
+    const __half wh = __float2half_rn((float)cp.WFD);
+    const float whf = __half2float(wh);
+    if (cp.WFD >= 6.2e-5 && whf > 0.f) {
+      kappa = (double)whf / cp.WFD;
+      c->bh_bits = __half_as_ushort(wh);
+      c->b_eff = whf;
+    } else {           // weight below the fp16 normal range: scalar FFMA path with the float weight
+      c->x2_ok = false;
+      c->b_eff = (float)cp.WFD;
+    }
+  }
+  c->kappa = kappa;
+  const double a = (bsc ? cp.scale * cp.WED : cp.scale) * kappa;
   const double A = a * a;
-  const double b = bsc ? cp.WFD : 0.0;
+  const double b = bsc ? (double)c->b_eff : 0.0;
   const int n = c->N > c->M ? c->N : c->M;
   cudaMemsetAsync(&c->d_sdev->r2max_bits, 0, sizeof(unsigned), c->stream);
   k_prep<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_s, c->d_t, c->N, c->M, c->center[0], c->center[1], c->center[2], A,
                                                  reinterpret_cast<float4 *>(c->d_S4), reinterpret_cast<float4 *>(c->d_T4),
                                                  c->d_sdev);
-  k_margin<<<1, 1, 0, c->stream>>>(c->d_sdev, A, a, b, (double)c->bits, c->d_iter, for_km_gate, 1e-5);
+  k_margin<<<1, 1, 0, c->stream>>>(c->d_sdev, A, a, b, (double)c->bits, c->d_iter, for_km_gate, 1e-5, kappa);
   c->launches += 2;
   return cudaGetLastError();
 }
 // refresh only the KM superset threshold (penalty has been (re)computed on the device)
 cudaError_t launch_stream_gate(Ctx *c, const CostParams &cp) {
   const bool bsc = c->cfg.feature_type == GHICP_FT_BSC;
-  const double a = bsc ? cp.scale * cp.WED : cp.scale;
-  k_margin<<<1, 1, 0, c->stream>>>(c->d_sdev, a * a, a, bsc ? cp.WFD : 0.0, (double)c->bits, c->d_iter, 1, 1e-5);
+  const double a = (bsc ? cp.scale * cp.WED : cp.scale) * c->kappa;
+  k_margin<<<1, 1, 0, c->stream>>>(c->d_sdev, a * a, a, bsc ? (double)c->b_eff : 0.0, (double)c->bits, c->d_iter, 1, 1e-5,
+                                   c->kappa);
   c->launches++;
   return cudaGetLastError();
 }
@@ -608,11 +699,16 @@ cudaError_t launch_stream(Ctx *c, const CostParams &cp, int mode, bool stats) {
   static const bool use_tma = getenv("GHICP_STREAM_LDG") == nullptr;
 #define LAUNCH(MODE, FD, ST)                                                                                   \
   do {                                                                                                         \
-    if (FD && use_tma) {                                                                                       \
-      cudaFuncSetAttribute(k_stream<MODE, FD, ST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_DYN_SMEM); \
-      k_stream<MODE, FD, ST, true><<<grid, ST_THREADS, ST_DYN_SMEM, c->stream>>>(a);                          \
+    if (FD && use_tma && c->x2_ok) {                                                                           \
+      cudaFuncSetAttribute(k_stream<MODE, FD, ST, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_DYN_SMEM); \
+      k_stream<MODE, FD, ST, true, true><<<grid, ST_THREADS, ST_DYN_SMEM, c->stream>>>(a);                    \
+    } else if (FD && use_tma) {                                                                                \
+      cudaFuncSetAttribute(k_stream<MODE, FD, ST, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_DYN_SMEM); \
+      k_stream<MODE, FD, ST, true, false><<<grid, ST_THREADS, ST_DYN_SMEM, c->stream>>>(a);                   \
+    } else if (c->x2_ok) {                                                                                     \
+      k_stream<MODE, FD, ST, false, true><<<grid, ST_THREADS, 0, c->stream>>>(a);                             \
     } else {                                                                                                   \
-      k_stream<MODE, FD, ST, false><<<grid, ST_THREADS, 0, c->stream>>>(a);                                   \
+      k_stream<MODE, FD, ST, false, false><<<grid, ST_THREADS, 0, c->stream>>>(a);                            \
     }                                                                                                          \
   } while (0)
 #define PICK(MODE)                                      \
@@ -649,7 +745,7 @@ cudaError_t launch_stream_resolve(Ctx *c, const CostParams &cp, bool with_cols) 
 
 cudaError_t launch_finalize_fast(Ctx *c, const LoopScalars &ls) {
   (void)ls;
-  k_finalize_fast<<<1, 1024, 0, c->stream>>>(c->d_part_stats, stream_num_parts(c), c->d_xstats, c->rank);
+  k_finalize_fast<<<1, 1024, 0, c->stream>>>(c->d_part_stats, stream_num_parts(c), c->d_xstats, c->rank, c->kappa);
   c->launches++;
   return cudaGetLastError();
 }

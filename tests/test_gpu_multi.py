@@ -66,7 +66,7 @@ def test_sharded_equals_single_gpu(g, tmp_path, mode):
             o = ranks[k][it]
             assert o["cor"] == st.cor, (it, k)
             assert np.array_equal(o["sp"], sp) and np.array_equal(o["tp"], tp), (it, k)
-            assert o["penalty"] == pytest.approx(st.penalty, rel=1e-9)
+            assert o["penalty"] == pytest.approx(st.penalty, rel=1e-6)  # FP32-filter statistics: partition-dependent at ~1e-8
             if ct != g.CT_KM:
                 assert np.array_equal(o["Rt"], np.array(st.Rt)), (it, k)
         assert np.array_equal(ranks[0][it]["Rt"], ranks[1][it]["Rt"])  # ranks stay in lock step
