@@ -232,7 +232,7 @@ struct SweepArgs {
   int *cnt;
   const long long *rowptr;
   int *cursor;
-  int *csr_col; double *csr_gain;
+  int *csr_col; double *csr_gain; float *csr_fd;
 };
 
 template <int FT, int MODE>
@@ -303,6 +303,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_rowsweep(const SweepArgs a) {
                 const long long pos = a.rowptr[slot] + atomicAdd(&a.cursor[slot], 1);
                 a.csr_col[pos] = j + c;
                 a.csr_gain[pos] = penalty - cd;
+                a.csr_fd[pos] = (float)fdv[c];
               }
             }
           }
@@ -924,7 +925,7 @@ cudaError_t launch_rowsweep(Ctx *c, int mode, const CostParams &cp) {
   a.cp = cp;
   a.part_cd = c->d_part_cd; a.part_idx = c->d_part_idx; a.part_stats = c->d_part_stats;
   a.iter = c->d_iter; a.cnt = c->d_cnt; a.rowptr = c->d_rowptr; a.cursor = c->d_cursor;
-  a.csr_col = c->d_csr_col; a.csr_gain = c->d_csr_gain;
+  a.csr_col = c->d_csr_col; a.csr_gain = c->d_csr_gain; a.csr_fd = c->d_csr_fd;
   dim3 grid((c->nloc + TR - 1) / TR, c->n_chunks);
   cudaError_t e = dispatch_ft(c->cfg.feature_type, [&](auto ft) {
     constexpr int FT = decltype(ft)::value;

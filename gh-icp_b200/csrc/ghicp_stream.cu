@@ -37,7 +37,7 @@ constexpr unsigned INF_BITS = 0x7f800000u;
 // TMA staging of the FD plane: every warp runs its own ring of ST_STAGES stages; a stage holds ST_UNROLL
 // row segments of the warp's 256-column panel (512 B each), brought in by cp.async.bulk (TMA engine,
 // UBLKCP) and signalled on one mbarrier per stage.  No registers are tied up by loads in flight.
-constexpr int ST_STAGES = 4;
+constexpr int ST_STAGES = 6;
 constexpr int ST_SEG_BYTES = ST_PANEL * 2;                   // 512
 constexpr int ST_STAGE_BYTES = ST_UNROLL * ST_SEG_BYTES;     // 2048
 constexpr int ST_RING_BYTES = ST_STAGES * ST_STAGE_BYTES;    // per warp
@@ -239,8 +239,10 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, c
       Tz2[p] = pack2(Tz[2 * p], Tz[2 * p + 1]); Tw2[p] = pack2(Tw[2 * p], Tw[2 * p + 1]);
     }
   }
-  unsigned short bh = a.bh;
-  asm volatile("mov.b16 %0, %0;" : "+h"(bh));  // keep the weight in a vector register (FHFMA takes no uniform operand)
+  // keep the fp16 weight in a per-thread (vector) register: FHFMA takes no uniform-register operand, and a
+  // value the compiler can prove warp-uniform would be re-materialised from the constant bank per use
+  // (bit 31 of a running-minimum word is always 0 — a positive float — but only known at run time)
+  const unsigned short bh = (unsigned short)(a.bh | (unsigned short)(s_thr[0] >> 31));
   const float margin = a.dev->margin;
   const float m2 = 2.f * margin;
   const float thr_hi = a.dev->thr_hi;
@@ -279,17 +281,22 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, c
     }
     float psum = 0.f, psq = 0.f;
     u64 psum2 = 0ull, psq2 = 0ull;
+    // per-batch base addresses: everything inside the unrolled rows is base + immediate
+    const unsigned char *qbase = (HAS_FD && TMA) ? ring + ((rb / ST_UNROLL) % ST_STAGES) * ST_STAGE_BYTES + lane * 16 : nullptr;
+    const float *s8base = s_S8 + rb * 8;
+    const float4 *s4base = s_S4 + rb;
+    unsigned *thrbase = s_thr + rb;
 #pragma unroll
     for (int u = 0; u < ST_UNROLL; ++u) {
       const int r = rb + u;
       if (r < nrows) {
-        const float4 S = s_S4[r];
+        const float4 S = X2 ? make_float4(0.f, 0.f, 0.f, 0.f) : s4base[u];
         if (HAS_FD && TMA)  // just-in-time read of this row's 8 values from the staged segment
-          q[u] = *reinterpret_cast<const uint4 *>(ring + ((rb / ST_UNROLL) % ST_STAGES) * ST_STAGE_BYTES + u * ST_SEG_BYTES + lane * 16);
+          q[u] = *reinterpret_cast<const uint4 *>(qbase + u * ST_SEG_BYTES);
         float cd[ST_CPL];
         if (X2) {
-          const ulonglong2 sA = *reinterpret_cast<const ulonglong2 *>(s_S8 + r * 8);      // (sx,sx) (sy,sy)
-          const ulonglong2 sB = *reinterpret_cast<const ulonglong2 *>(s_S8 + r * 8 + 4);  // (sz,sz) (sw,sw)
+          const ulonglong2 sA = *reinterpret_cast<const ulonglong2 *>(s8base + u * 8);      // (sx,sx) (sy,sy)
+          const ulonglong2 sB = *reinterpret_cast<const ulonglong2 *>(s8base + u * 8 + 4);  // (sz,sz) (sw,sw)
 #pragma unroll
           for (int p = 0; p < ST_CPL / 2; ++p) {
             u64 acc = add2(Tw2[p], sB.y);
@@ -347,7 +354,7 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, c
           // seed pass: FP32 row (and column) minima only, no decisions
           float m8 = fminf(fminf(fminf(cd[0], cd[1]), fminf(cd[2], cd[3])), fminf(fminf(cd[4], cd[5]), fminf(cd[6], cd[7])));
           const unsigned wmin = __reduce_min_sync(0xffffffffu, __float_as_uint(m8));
-          if (lane == 0 && wmin < s_thr[r]) atomicMin(&s_thr[r], wmin);
+          if (lane == 0 && wmin < thrbase[u]) atomicMin(&thrbase[u], wmin);
           if (MODE == SM_PRE_COLS) {
 #pragma unroll
             for (int c = 0; c < ST_CPL; ++c) colrun[c] = fminf(colrun[c], cd[c]);
@@ -355,7 +362,7 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, c
         } else if (MODE == SM_NN || MODE == SM_NNR) {
           float m8 = fminf(fminf(fminf(cd[0], cd[1]), fminf(cd[2], cd[3])), fminf(fminf(cd[4], cd[5]), fminf(cd[6], cd[7])));
           const unsigned wmin = __reduce_min_sync(0xffffffffu, __float_as_uint(m8));
-          const float run = __uint_as_float(s_thr[r]);
+          const float run = __uint_as_float(thrbase[u]);
           if (__uint_as_float(wmin) <= run + m2) {  // warp-uniform, rare once the running minimum is tight
             // the row argmin is within 2*margin of the smallest value of ANY set that contains it
             const float lim = fminf(run, __uint_as_float(wmin)) + m2;
@@ -431,7 +438,7 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, c
 }
 
 template <int MODE, bool HAS_FD, bool STATS, bool TMA, bool X2>
-__global__ void __launch_bounds__(ST_THREADS, TMA ? 3 : 2) k_stream(const StreamArgs a) {
+__global__ void __launch_bounds__(ST_THREADS, (TMA && !X2) ? 3 : 2) k_stream(const StreamArgs a) {
   __shared__ __align__(16) float s_S8[X2 ? ST_RB * 8 : 8];
   extern __shared__ __align__(128) unsigned char s_ring[];   // [ST_WARPS][ST_RING_BYTES] when TMA
   __shared__ __align__(8) unsigned long long s_bar[ST_WARPS][ST_STAGES];
