@@ -286,15 +286,11 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, c
     const float *s8base = s_S8 + rb * 8;
     const float4 *s4base = s_S4 + rb;
     unsigned *thrbase = s_thr + rb;
-#pragma unroll
-    for (int u = 0; u < ST_UNROLL; ++u) {
-      const int r = rb + u;
-      if (r < nrows) {
+    auto compute_row = [&](const int u, float (&cd)[ST_CPL]) {
         const float4 S = X2 ? make_float4(0.f, 0.f, 0.f, 0.f) : s4base[u];
         if (HAS_FD && TMA)  // just-in-time read of this row's 8 values from the staged segment
           q[u] = *reinterpret_cast<const uint4 *>(qbase + u * ST_SEG_BYTES);
-        float cd[ST_CPL];
-        if (X2) {
+                if (X2) {
           const ulonglong2 sA = *reinterpret_cast<const ulonglong2 *>(s8base + u * 8);      // (sx,sx) (sy,sy)
           const ulonglong2 sB = *reinterpret_cast<const ulonglong2 *>(s8base + u * 8 + 4);  // (sz,sz) (sw,sw)
 #pragma unroll
@@ -350,6 +346,9 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, c
           }
         }
         }
+    };
+    auto decide_row = [&](const int u, const float (&cd)[ST_CPL]) {
+      const int r = rb + u;
         if (MODE == SM_PRE || MODE == SM_PRE_COLS) {
           // seed pass: FP32 row (and column) minima only, no decisions
           float m8 = fminf(fminf(fminf(cd[0], cd[1]), fminf(cd[2], cd[3])), fminf(fminf(cd[4], cd[5]), fminf(cd[6], cd[7])));
@@ -406,6 +405,23 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, c
                 if (cd[c] < thr_hi) a.csr_col[pos++] = j0 + c;
             }
           }
+        }
+          };
+    if (rb + ST_UNROLL <= nrows) {
+      // full batch: all arithmetic of the ST_UNROLL rows first (4 x 8 independent chains in flight), then
+      // the per-row reductions / rare branches
+      float cdm[ST_UNROLL][ST_CPL];
+#pragma unroll
+      for (int u = 0; u < ST_UNROLL; ++u) compute_row(u, cdm[u]);
+#pragma unroll
+      for (int u = 0; u < ST_UNROLL; ++u) decide_row(u, cdm[u]);
+    } else {
+#pragma unroll
+      for (int u = 0; u < ST_UNROLL; ++u) {
+        if (rb + u < nrows) {
+          float cd1[ST_CPL];
+          compute_row(u, cd1);
+          decide_row(u, cd1);
         }
       }
     }
