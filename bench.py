@@ -45,24 +45,45 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region (NVML, every 5 ms; nvidia-smi fallback)."""
 
     def __init__(self, dev=0):
         self.rows, self.stop, self.dev = [], threading.Event(), dev
         self.t = None
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(dev)
+        except Exception:
+            self.nv = None
 
     def _run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+        nv = self.nv
         while not self.stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.dev}", f"--query-gpu={q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([x.strip() for x in out.strip().split(",")])
+                if nv is not None:
+                    sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                    mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                        else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    self.rows.append((sm, mx, rs))
+                    self.stop.wait(0.005)
+                else:
+                    q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+                    out = subprocess.run(["nvidia-smi", f"--id={self.dev}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout
+                    r = [x.strip() for x in out.strip().split(",")]
+                    bits = 0
+                    for k, v in enumerate(r[2:6]):
+                        if v.lower().startswith("active"):
+                            bits |= [0x8, 0x40, 0x20, 0x4][k]
+                    self.rows.append((float(r[0]), float(r[1]), bits))
+                    self.stop.wait(0.1)
             except Exception:
-                pass
-            self.stop.wait(0.2)
+                self.stop.wait(0.05)
 
     def __enter__(self):
         self.t = threading.Thread(target=self._run, daemon=True)
@@ -74,17 +95,15 @@ class ClockSampler:
         self.t.join(timeout=6)
 
     def summary(self):
-        sm, mx, reasons = [], 0, set()
+        sm = [r[0] for r in self.rows]
+        mx = max([r[1] for r in self.rows], default=0)
+        bits = 0
         for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx = max(mx, float(r[1]))
-                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            bits |= int(r[2])
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        reasons = sorted(n for b, n in names.items() if bits & b)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(mx) or None,
+                "reasons": reasons, "samples": len(sm)}
 
 
 def make_scene(g, wl, n_override=None, seed=2):
@@ -101,6 +120,10 @@ def make_scene(g, wl, n_override=None, seed=2):
     return sc
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_stream launch, from the committed `ncu --set full` captures
+# (profiles/r01_summary.md); algorithmic bytes are 5.002e9
+NCU_TRAFFIC = {"config2": 5.0386e9, "config2-nn": 5.311e9}
+
 FT = {"none": 3, "bsc": 0, "fpfh": 2}
 CT = {"nn": 0, "nnr": 1, "km": 2}
 
@@ -108,16 +131,14 @@ CT = {"nn": 0, "nnr": 1, "km": 2}
 # --------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle (restated reference loop) + the reference's own km.cpp when compiled.
 # --------------------------------------------------------------------------------------------------
-def cpu_baseline(g, wl, threads, n_sample, iters=2):
+def _oracle_run(g, wl, ct, threads, n, iters, use_ref):
     import oracle
-    oracle.build()
-    use_ref = oracle.ref_km_lib() is not None and wl["ct"] == "km"
-    sc = make_scene(g, wl, n_override=n_sample)
-    cwd = os.getcwd()
     import tempfile
+    sc = make_scene(g, wl, n_override=n)
+    cwd = os.getcwd()
     os.chdir(tempfile.mkdtemp())  # Km::output writes Corres.txt (src/km.cpp:148)
     try:
-        o = oracle.Oracle(FT[wl["ft"]], CT[wl["ct"]], bbx_magnitude=sc.bbx_magnitude, solve_mode=0,
+        o = oracle.Oracle(FT[wl["ft"]], CT[ct], bbx_magnitude=sc.bbx_magnitude, solve_mode=0,
                           use_ref_km=use_ref, num_threads=threads)
         o.set_keypoints(sc.S, sc.T)
         if wl["ft"] == "bsc":
@@ -131,27 +152,44 @@ def cpu_baseline(g, wl, threads, n_sample, iters=2):
             t_cost.append(st.t_cost_ms); t_corr.append(st.t_corr_ms); t_solve.append(st.t_solve_ms)
     finally:
         os.chdir(cwd)
-    n = n_sample
+    return float(np.median(t_cost)), float(np.median(t_corr)), float(np.median(t_solve)), t_fd
+
+
+def cpu_baseline(g, wl, threads, n_sample, iters=2):
+    """The reference's CPU path on a bounded sample: O(N*M) stages (calED/calCD/scans) timed at n_cost
+    (threads as given), KM timed at n_sample with the reference's own single-threaded src/km.cpp when
+    oracle/_ref is built; both extrapolated to the workload size (cost ~ N*M, KM ~ n^3, solve ~ n)."""
+    import oracle
+    oracle.build()
+    km = wl["ct"] == "km"
+    use_ref = oracle.ref_km_lib() is not None and km
     N = wl["N"]
-    cost = float(np.median(t_cost)); corr = float(np.median(t_corr)); solve = float(np.median(t_solve))
-    # extrapolation laws: cost/NN/NNR ~ N*M, KM ~ n^3, solve ~ n
-    sc2 = (N / n) ** 2
-    sc3 = (N / n) ** 3
-    full_ms = cost * sc2 + (corr * sc3 if wl["ct"] == "km" else corr * sc2) + solve * (N / n)
+    n_cost = min(N, 6000)
+    cost, scan, solve, t_fd = _oracle_run(g, wl, "nn" if km else wl["ct"], threads, n_cost, iters, False)
+    parts = [f"cost stage (calED+calCD) {cost:.1f} ms at {n_cost}x{n_cost} on {threads} thread(s)"]
+    full_ms = cost * (N / n_cost) ** 2 + solve * (N / n_cost)
+    if km:
+        n_km = min(n_sample, N)
+        _, corr, _, _ = _oracle_run(g, wl, "km", 1, n_km, iters, use_ref)
+        full_ms += corr * (N / n_km) ** 3
+        parts.append(f"KM ({'reference src/km.cpp' if use_ref else 'restated km.cpp'}, 1 thread: it is sequential) "
+                     f"{corr:.1f} ms at {n_km}x{n_km}")
+    else:
+        full_ms += scan * (N / n_cost) ** 2
+        parts.append(f"{wl['ct'].upper()} scan {scan:.1f} ms at {n_cost}x{n_cost}")
+    sample = ("; ".join(parts) + f"; solve {solve:.2f} ms; one-time FD {t_fd * 1e3:.0f} ms; median of {iters} iterations; "
+              f"extrapolated to {N}x{wl['M']} with cost/scan ~ N*M, KM ~ n^3, solve ~ n "
+              f"(the reference cannot run {N}x{wl['M']}: 24*N*M B of doubles + O(n^3) KM, SURVEY.md §6)")
     return dict(value=1000.0 / full_ms, unit="iterations/s", cores=threads,
-                kind="reference" if use_ref else "port",
-                sample=(f"{n}x{n} subsample of the workload, {iters} iterations, median stage times "
-                        f"cost={cost:.1f} ms corr={corr:.1f} ms solve={solve:.2f} ms (one-time FD {t_fd*1e3:.0f} ms); "
-                        f"extrapolated to {N}x{wl['M']} with cost~N*M, {'KM~n^3' if wl['ct']=='km' else 'scan~N*M'}, solve~n "
-                        f"(the reference cannot run {N}x{wl['M']}: 24*N*M B of doubles + O(n^3) KM, SURVEY.md §6)"),
-                ms_per_step_sample=cost + corr + solve, ms_per_step_extrapolated=full_ms)
+                kind="reference" if use_ref else "port", sample=sample,
+                ms_per_step_sample=cost + (scan if not km else 0.0) + solve, ms_per_step_extrapolated=full_ms)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--n", type=int, default=0, help="override N=M (debug; makes the number non-headline)")
@@ -180,7 +218,7 @@ def main():
             return
         n_s = args.cpu_sample or (1500 if wl["ct"] == "km" else min(wl["N"], 6000))
         t0 = time.perf_counter()
-        cb = cpu_baseline(g, wl, threads=ncores, n_sample=min(n_s, wl["N"]), iters=max(1, min(args.steps, 2)))
+        cb = cpu_baseline(g, wl, threads=min(ncores, 32), n_sample=min(n_s, wl["N"]), iters=max(1, min(args.steps, 2)))
         line = {"impl": "reference", "metric": "ICP iterations/sec", "value": cb["value"], "unit": "iterations/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": cb["ms_per_step_extrapolated"], "higher_is_better": True, "scaling": "strong",
@@ -297,7 +335,7 @@ def main():
         "roofline": {"kernel": "k_stream (calED+calCD+scan/gate+stats fused over the fp16 FD plane)", "bound": "hbm",
                      "kernel_ms": stream_ms,
                      "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": NCU_TRAFFIC.get(args.workload) if not args.n else None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "sweeps_per_step": n_sweeps},
     }
     if not args.no_cpu:

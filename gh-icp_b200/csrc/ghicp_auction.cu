@@ -121,9 +121,17 @@ __global__ void k_auc_init(int n_rows, int n_cols, const long long *rowptr, int 
 }
 
 __global__ void k_auc_phase_start(int n_rows, int n_cols, const long long *rowptr, int n_chunks, int *assign,
-                                  int *owner, double *profit) {
+                                  int *owner, double *profit, double *price, double relax) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_cols) owner[i] = -1;
+  if (i < n_cols) {
+    owner[i] = -1;
+    // Warm start: prices of the previous (coarser) phase sit up to eps_prev above the level at which their
+    // last owner is indifferent to staying unmatched; carried over unchanged those owners would all retire to
+    // their dummy at once and the (sequential) reverse auction would have to re-attract them one chain at a
+    // time.  Relaxing every price by eps_prev lets the parallel forward rounds redo that matching instead.
+    // Any non-negative starting prices are valid for the auction.
+    if (relax > 0.0) price[i] = fmax(0.0, price[i] - relax);
+  }
   if (i < n_rows) {
     const bool has = rowptr[(size_t)(i + 1) * n_chunks] > rowptr[(size_t)i * n_chunks];
     assign[i] = has ? UNASSIGNED : DUMMY;
@@ -223,6 +231,16 @@ __global__ void __launch_bounds__(AUC_BLOCK) k_fwd_reset(AucArgs a, const int *l
 }
 
 // ---- reverse round -------------------------------------------------------------------------------
+// D = sum of the prices of objects left free: the exact amount by which complementary slackness is violated,
+// i.e. the extra term of the optimality bound  OPT - ours <= |M*| * eps + D
+__global__ void k_free_price_sum(int n_cols, const int *owner, const double *price, double *out) {
+  double v = 0.0;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_cols; j += gridDim.x * blockDim.x)
+    if (owner[j] < 0) v += price[j];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(out, v);
+}
 __global__ void k_rev_collect(int n_cols, const int *owner, const double *price, int *list, int *counters, int cur) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < n_cols && owner[j] < 0 && price[j] > 0.0) list[atomicAdd(&counters[cur], 1)] = j;
@@ -716,11 +734,15 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
   // epsilon schedule
   std::vector<double> eps_list;
   {
+    // Optimality bound at termination: OPT - ours <= n*eps_last + D  (D = prices of objects left free).
+    // eps_last = eps_final/2 leaves a budget of n*eps_final/2 for D, so the reverse auction (whose rounds are
+    // long sequential displacement chains) only runs when D exceeds that budget.
+    const double eps_last = 0.5 * eps_final;
     double e0 = max_gain / 4.0;
-    while (e0 > eps_final * 1.0000001) { eps_list.push_back(e0); e0 /= 5.0; }
-    eps_list.push_back(eps_final);
+    while (e0 > eps_last * 1.0000001) { eps_list.push_back(e0); e0 /= 5.0; }
+    eps_list.push_back(eps_last);
   }
-  if (nnz == 0) eps_list.assign(1, eps_final);
+  if (nnz == 0) eps_list.assign(1, 0.5 * eps_final);
 
   int rounds = 0;
   const int max_rounds = 4000000;
@@ -742,11 +764,12 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
   small_fwd = small_fwd < 16 ? 16 : (small_fwd > PA_SMALL ? PA_SMALL : small_fwd);
   small_rev = small_rev < 16 ? 16 : (small_rev > PA_SMALL ? PA_SMALL : small_rev);
   const bool debug = getenv("GHICP_AUCTION_DEBUG") != nullptr;
+  const double relax_factor = getenv("GHICP_AUCTION_RELAX") ? atof(getenv("GHICP_AUCTION_RELAX")) : 0.0;
   int last_rounds = 0;
   for (size_t ph = 0; ph < eps_list.size(); ++ph) {
     a.eps = eps_list[ph];
     k_auc_phase_start<<<gmax, 256, 0, st>>>(n_rows, n_cols, c->d_rowptr, c->n_chunks, c->d_assign, c->d_owner,
-                                            c->d_profit);
+                                            c->d_profit, c->d_price, ph > 0 ? relax_factor * eps_list[ph - 1] : 0.0);
     c->launches++;
     cudaMemcpyAsync(c->d_list[0], base_list, sizeof(int) * (size_t)n_rows, cudaMemcpyDeviceToDevice, st);
     cudaMemcpyAsync(&c->d_counters[0], &c->d_counters[2], sizeof(int), cudaMemcpyDeviceToDevice, st);
@@ -764,7 +787,20 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
     // reverse: objects left free with a positive price.  Complementary slackness for free objects only
     // matters for the final optimality bound, so intermediate phases skip it (their leftover prices are
     // just the next phase's starting prices).
+    bool need_reverse = false;
     if (ph + 1 == eps_list.size()) {
+      double *d_D = reinterpret_cast<double *>(c->d_bid_aux);  // free scratch between rounds
+      cudaMemsetAsync(d_D, 0, sizeof(double), st);
+      k_free_price_sum<<<148, 256, 0, st>>>(n_cols, c->d_owner, c->d_price, d_D);
+      c->launches++;
+      double D = 0.0;
+      cudaMemcpyAsync(&D, d_D, sizeof(double), cudaMemcpyDeviceToHost, st);
+      cudaStreamSynchronize(st);
+      const double budget = 0.5 * eps_final * (double)(n_rows > n_cols ? n_rows : n_cols);
+      need_reverse = D > budget;
+      if (debug) fprintf(stderr, "[auction] free-object price sum D = %.4f, budget %.4f -> reverse %s\n", D, budget, need_reverse ? "yes" : "skipped");
+    }
+    if (need_reverse) {
     cudaMemsetAsync(&c->d_counters[0], 0, sizeof(int) * 2, st);
     k_rev_collect<<<gmax, 256, 0, st>>>(n_cols, c->d_owner, c->d_price, c->d_list[0], c->d_counters, 0);
     c->launches++;
