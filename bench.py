@@ -273,7 +273,7 @@ def main():
             st = reg.iterate()  # ends with a stream synchronize
             dev_ms.append(st.ms_total)
             stage.append((st.ms_cost, st.ms_corr, st.ms_solve, st.nnz, st.km_rounds, st.cor, st.ms_stream,
-                          st.stream_passes, st.exact_fallback))
+                          st.stream_passes, st.exact_fallback, st.candidates))
             launches += st.gpu_launches
         wall = time.perf_counter() - t0
     barrier()
@@ -331,7 +331,7 @@ def main():
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
         "clocks": clocks,
-        "exact_fallbacks": int(stage[:, 8].sum()),
+        "exact_fallbacks": int(stage[:, 8].sum()), "filter_candidates_per_step": int(np.median(stage[:, 9])),
         "roofline": {"kernel": "k_stream (calED+calCD+scan/gate+stats fused over the fp16 FD plane)", "bound": "hbm",
                      "kernel_ms": stream_ms,
                      "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,

@@ -37,7 +37,7 @@ class IterStats(C.Structure):
                 ("ax", C.c_double), ("ay", C.c_double), ("az", C.c_double),
                 ("nnz", C.c_longlong), ("km_rounds", C.c_int), ("km_phases", C.c_int), ("gpu_launches", C.c_int), ("exact_fallback", C.c_int),
                 ("ms_cost", C.c_float), ("ms_corr", C.c_float), ("ms_solve", C.c_float), ("ms_total", C.c_float),
-                ("ms_stream", C.c_float), ("stream_passes", C.c_int)]
+                ("ms_stream", C.c_float), ("stream_passes", C.c_int), ("candidates", C.c_longlong)]
 
     def Rt_np(self):
         return np.array(self.Rt).reshape(4, 4).T.copy()

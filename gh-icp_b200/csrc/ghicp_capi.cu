@@ -464,6 +464,7 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]); out->ms_total = ms;
     if (timed_stream) { cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]); out->ms_stream = ms; }
     out->stream_passes = stream_passes;
+    out->candidates = (fast && ct != GHICP_CT_KM) ? c->last_cands : 0;
   }
   c->iteration++;
   return warnings;
