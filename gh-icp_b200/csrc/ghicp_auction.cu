@@ -572,7 +572,50 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
                 if (o.best > t.best || (o.best == t.best && tie_less(i, o.idx, t.idx))) bg = s_pg[warp + q];
                 top2_merge_h(t, o.best, o.idx, o.second, i);
               }
-              if (REVERSE) rev_finish(a, i, t); else fwd_finish(a, i, t, bg);
+              if (m == 1) {
+                // a single bidder cannot lose: bid and commit in one step (no key atomics, no second pass).
+                // This is the common case of the tail: one displacement chain advancing one step per round.
+                if (!REVERSE) {
+                  if (t.idx < 0 || t.best <= 0.0) {
+                    __stcg(&a.assign[i], DUMMY);
+                    __stcg(&a.profit[i], 0.0);
+                  } else {
+                    const int j = t.idx;
+                    const double newprice = ldcg_d(&a.price[j]) + (t.best - fmax(t.second, 0.0)) + a.eps;
+                    const int prev = ldcg_i(&a.owner[j]);
+                    __stcg(&a.owner[j], i);
+                    __stcg(&a.price[j], newprice);
+                    __stcg(&a.assign[i], j);
+                    __stcg(&a.profit[i], bg - newprice);
+                    if (prev >= 0) { __stcg(&a.assign[prev], UNASSIGNED); __stcg(&next[0], prev); s_next = 1; }
+                  }
+                } else {
+                  const int j = i;  // the list holds objects in the reverse phase
+                  if (t.idx < 0 || t.best <= a.eps) {
+                    __stcg(&a.price[j], 0.0);
+                  } else {
+                    const int who = t.idx;
+                    const double delta = fmin(t.best, (t.best - t.second) + a.eps);
+                    const int old = ldcg_i(&a.assign[who]);
+                    __stcg(&a.assign[who], j);
+                    __stcg(&a.owner[j], who);
+                    __stcg(&a.price[j], t.best - delta);
+                    __stcg(&a.profit[who], ldcg_d(&a.profit[who]) + delta);
+                    if (old >= 0) {
+                      __stcg(&a.owner[old], -1);
+                      if (ldcg_d(&a.price[old]) > 0.0) { __stcg(&next[0], old); s_next = 1; }
+                    }
+                  }
+                }
+              } else if (REVERSE) rev_finish(a, i, t); else fwd_finish(a, i, t, bg);
+            }
+            if (m == 1) {   // committed above
+              __syncthreads();
+              cur ^= 1;
+              ++rounds;
+              if (threadIdx.x == 0) s_n = s_next;
+              __syncthreads();
+              continue;
             }
           } else {
             for (int w = threadIdx.x >> 5; w < m; w += NW) {

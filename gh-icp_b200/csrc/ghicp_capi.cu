@@ -212,7 +212,12 @@ static int build_fd(Ctx *c) {
     int rc = dev_alloc(c, &c->d_fd16, fd_elems(c->fd_rows, c->M));
     if (rc) return rc;
     CK(c, cudaMemsetAsync(c->d_fd16, 0, fd_elems(c->fd_rows, c->M) * sizeof(uint16_t), c->stream));  // zero the panel padding
-    CK(c, launch_fd_bsc(c));
+    {
+      // tensor-core build (tcgen05 kind::i8) when the descriptor fits its shared-memory tiling, else POPC
+      cudaError_t e = (getenv("GHICP_FD_POPC") != nullptr) ? cudaErrorNotSupported : launch_fd_bsc_tc(c);
+      if (e == cudaErrorNotSupported) { cudaGetLastError(); CK(c, launch_fd_bsc(c)); c->fd_tensor = false; }
+      else { CK(c, e); c->fd_tensor = true; }
+    }
   } else if (c->cfg.feature_type == GHICP_FT_FPFH) {
     if (!c->have_fpfh) { set_error(c, "build_fd: FPFH descriptors not set"); return GHICP_E_ARG; }
     c->fd_rows = (size_t)std::max(c->nloc, 1);

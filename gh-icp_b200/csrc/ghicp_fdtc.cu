@@ -1,0 +1,245 @@
+// ghicp_fdtc.cu — one-time BSC feature-distance build on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// calFD_BSC (src/ghicp_reg.cpp:143-200): FD[i][j] = min_v Hamming(bscS[v][i], bscT[0][j]).
+// With descriptor bits mapped to +/-1 int8 (padding = 0) the Hamming distance is an integer GEMM:
+//      dot(a, b) = (#equal bits) - (#different bits) = bits - 2 * Hamming   =>   Hamming = (bits - dot) / 2
+// exactly (int32 accumulation of +/-1 products).  One CTA keeps a B tile = 256 (source, variant) rows
+// resident in shared memory and streams 128-row target tiles (A) through a double buffer; a single thread
+// issues tcgen05.mma.kind::i8 (M=128, N=256, K=32 per instruction) into one of two 256-column TMEM
+// accumulators while four warps drain the other one (tcgen05.ld), take the min over the V variants
+// (adjacent accumulator columns, in registers) and store fp16 into the panel-major FD plane.
+// Operands sit in shared memory in the canonical K-major no-swizzle layout [k-chunk(16 B)][row][16 B]
+// (8-row x 16-byte core matrices back to back: SBO = 128 B, LBO = rows * 16 B).
+#include <cstdlib>
+#include <cuda_fp16.h>
+
+#include "ghicp_internal.h"
+
+namespace ghicp_b200 {
+
+namespace {
+
+constexpr int TC_TM = 128;   // target rows per A tile  (UMMA M)
+constexpr int TC_TN = 256;   // (source, variant) rows per B tile (UMMA N)
+constexpr int TC_THREADS = 256;
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// bits -> +/-1 int8, written directly in the TILE-CANONICAL layout the MMA reads from shared memory:
+//   out[tile][k-chunk (16 B)][R rows][16 B]      (R = rows per tile; padding rows / bits are 0)
+// so that a whole operand tile is ONE contiguous block = one cp.async.bulk.  Logical row = (i - i0) * V + v.
+// words: [Vw][W64][n] word-major planes.
+__global__ void k_unpack_pm1(const uint64_t *__restrict__ words, int V, int n, int W64, int bits, int KP, int R,
+                             int i0, int n_rows_logical, int8_t *__restrict__ out) {
+  const int chunks = KP / 16;
+  const int n_tiles = (n_rows_logical + R - 1) / R;
+  const long long total = (long long)n_tiles * R * chunks;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int r = (int)(idx % R);
+  const int c = (int)((idx / R) % chunks);
+  const int tile = (int)(idx / ((long long)R * chunks));
+  const long long row = (long long)tile * R + r;
+  uint32_t o[4] = {0, 0, 0, 0};
+  if (row < n_rows_logical) {
+    const int i = i0 + (int)(row / V), v = (int)(row % V);
+    const int k0 = c * 16;
+    const int w = k0 >> 6;
+    const uint64_t word = (w < W64) ? words[((size_t)v * W64 + w) * n + i] : 0ull;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t pack = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int k = k0 + q * 4 + b;
+        int8_t val = 0;
+        if (k < bits) val = ((word >> (k & 63)) & 1ull) ? 1 : -1;
+        pack |= (uint32_t)(uint8_t)val << (8 * b);
+      }
+      o[q] = pack;
+    }
+  }
+  *reinterpret_cast<uint4 *>(out + idx * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+__device__ __forceinline__ void mbar_init1(unsigned long long *b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait_parity(unsigned long long *b, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+  } while (!ok);
+}
+// One logical tile copy = many 2-4 KB bulk copies in flight (a single large cp.async.bulk is serviced with
+// little memory-level parallelism; measured 13 GB/s per SM for one 56 KB copy), all completing on one mbarrier.
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  constexpr unsigned PIECE = 4096;
+  for (unsigned off = 0; off < bytes; off += PIECE) {
+    const unsigned n = (bytes - off < PIECE) ? (bytes - off) : PIECE;
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32((unsigned char *)dst + off)), "l"((const unsigned char *)src + off), "r"(n), "r"(smem_u32(bar)) : "memory");
+  }
+}
+
+__device__ __forceinline__ uint64_t make_desc(unsigned smem_addr, unsigned lbo_bytes, unsigned sbo_bytes) {
+  // SM100 shared-memory matrix descriptor: start address [0,14) (>>4), leading byte offset [16,30) (>>4),
+  // stride byte offset [32,46) (>>4), version = 1 at [46,48), layout type [61,64) = 0 (no swizzle)
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+
+template <int V>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_fd_bsc_tc(const int8_t *__restrict__ T8c, const int8_t *__restrict__ S8c, unsigned short *__restrict__ fd, int N, int M,
+            size_t fd_rows, int row0, int nloc, int bits, int KP, int dbg) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  // barriers: [0,1] A tile landed, [2,3] MMA of tile done, [4,5] TMEM accumulator drained, [6] B tile landed
+  __shared__ __align__(8) unsigned long long s_bar[7];
+  __shared__ unsigned s_tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int SRC_PER_TILE = TC_TN / V;
+  const unsigned b_bytes = (unsigned)TC_TN * KP, a_bytes = (unsigned)TC_TM * KP;
+  unsigned char *Bs = smem;
+  unsigned char *As[2] = {smem + b_bytes, smem + b_bytes + a_bytes};
+  const int src_base = row0 + blockIdx.x * SRC_PER_TILE;   // first source row of this CTA's B tile
+  const int n_ttiles = (M + TC_TM - 1) / TC_TM;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&s_tmem_base)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    mbar_init1(&s_bar[0], 1); mbar_init1(&s_bar[1], 1);
+    mbar_init1(&s_bar[2], 1); mbar_init1(&s_bar[3], 1);
+    mbar_init1(&s_bar[4], 128); mbar_init1(&s_bar[5], 128);
+    mbar_init1(&s_bar[6], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const unsigned tmem_base = s_tmem_base;
+
+  if (warp == 4 && lane == 0) {
+    // ===== producer + MMA issuer (one thread) =====
+    bulk_load(Bs, S8c + (size_t)blockIdx.x * b_bytes, b_bytes, &s_bar[6]);
+    // instruction descriptor (kind::i8): D = s32 [4,6)=2, A = s8 [7,10)=1, B = s8 [10,13)=1, K-major A and B,
+    // N>>3 at [17,23), M>>4 at [24,29)
+    const unsigned idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(TC_TN >> 3) << 17) | ((unsigned)(TC_TM >> 4) << 24);
+    const int ksteps = KP / 32;
+    const unsigned b_addr = smem_u32(Bs);
+    bulk_load(As[0], T8c, a_bytes, &s_bar[0]);                      // A(0)
+    for (int t = 0; t < n_ttiles; ++t) {
+      const int s = t & 1;
+      const unsigned ph = (unsigned)((t >> 1) & 1);
+      if (t >= 2) mbar_wait_parity(&s_bar[4 + s], ph ^ 1);      // epilogue(t-2) drained TMEM buffer s
+      if (t == 0) mbar_wait_parity(&s_bar[6], 0);                // B landed
+      mbar_wait_parity(&s_bar[s], ph);                           // A(t) landed
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const unsigned a_addr = smem_u32(As[s]);
+      const unsigned d_tmem = tmem_base + (unsigned)(s * TC_TN);
+      for (int k = 0; k < ((dbg & 2) ? 1 : ksteps); ++k) {
+        const uint64_t adesc = make_desc(a_addr + (unsigned)k * 2u * TC_TM * 16u, TC_TM * 16u, 128u);
+        const uint64_t bdesc = make_desc(b_addr + (unsigned)k * 2u * TC_TN * 16u, TC_TN * 16u, 128u);
+        const unsigned accumulate = k > 0 ? 1u : 0u;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s_bar[2 + s])) : "memory");
+      // prefetch A(t+1) into the other buffer as soon as MMA(t-1) has finished reading it: the copy then
+      // overlaps MMA(t)
+      if (t + 1 < n_ttiles) {
+        const int s1 = (t + 1) & 1;
+        if (t >= 1) mbar_wait_parity(&s_bar[2 + s1], (unsigned)(((t - 1) >> 1) & 1));
+        bulk_load(As[s1], T8c + (size_t)(t + 1) * a_bytes, a_bytes, &s_bar[s1]);
+      }
+    }
+  } else if (warp < 4) {
+    // ===== epilogue warps: TMEM -> registers -> min over variants -> fp16 -> FD plane =====
+    for (int t = 0; t < n_ttiles; ++t) {
+      const int s = t & 1;
+      const unsigned ph = (unsigned)((t >> 1) & 1);
+      mbar_wait_parity(&s_bar[2 + s], ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int j = t * TC_TM + warp * 32 + lane;  // target column owned by this thread (TMEM lane)
+      const unsigned taddr0 = tmem_base + ((unsigned)(warp * 32) << 16) + (unsigned)(s * TC_TN);
+#pragma unroll 1
+      for (int cb = 0; cb < TC_TN; cb += 32) {
+        unsigned r[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr0 + (unsigned)cb));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (j < M && !(dbg & 1)) {
+#pragma unroll
+          for (int q = 0; q < 32 / V; ++q) {
+            int best = (int)r[q * V];
+#pragma unroll
+            for (int v = 1; v < V; ++v) best = max(best, (int)r[q * V + v]);   // max dot = min Hamming
+            const int i = src_base + (cb / V) + q;
+            if (i < row0 + nloc) {
+              const int ham = (bits - best) >> 1;
+              fd[fd_index(fd_rows, i - row0, j)] = __half_as_ushort(__int2half_rn(ham));
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_bar[4 + s])) : "memory");
+    }
+  }
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+}
+
+}  // namespace
+
+// Returns cudaErrorNotSupported when the shape does not fit this kernel (caller falls back to k_fd_bsc).
+cudaError_t launch_fd_bsc_tc(Ctx *c) {
+  const int V = (c->cfg.dof == 6) ? 4 : 2;
+  const int KP = (c->bits + 31) / 32 * 32;
+  const size_t smem = (size_t)TC_TN * KP + 2 * (size_t)TC_TM * KP;
+  if (smem > 227 * 1024 || c->V < V || c->nloc <= 0) return cudaErrorNotSupported;
+  int8_t *T8 = nullptr, *S8 = nullptr;
+  cudaError_t e;
+  const int dbg = getenv("GHICP_FDTC_DBG") ? atoi(getenv("GHICP_FDTC_DBG")) : 0;
+  const int src_per_tile = TC_TN / V;
+  const int grid = (c->nloc + src_per_tile - 1) / src_per_tile;
+  const int n_ttiles = (c->M + TC_TM - 1) / TC_TM;
+  const size_t t_bytes = (size_t)n_ttiles * TC_TM * KP, s_bytes = (size_t)grid * TC_TN * KP;
+  if ((e = cudaMallocAsync((void **)&T8, t_bytes, c->stream)) != cudaSuccess) return e;
+  if ((e = cudaMallocAsync((void **)&S8, s_bytes, c->stream)) != cudaSuccess) { cudaFreeAsync(T8, c->stream); return e; }
+  {
+    const long long tot = (long long)(t_bytes / 16);
+    k_unpack_pm1<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(c->d_bt, 1, c->M, c->W64, c->bits, KP, TC_TM, 0, c->M, T8);
+    const long long tos = (long long)(s_bytes / 16);
+    k_unpack_pm1<<<(unsigned)((tos + 255) / 256), 256, 0, c->stream>>>(c->d_bs, V, c->N, c->W64, c->bits, KP, TC_TN, c->r0,
+                                                                         c->nloc * V, S8);
+    c->launches += 2;
+  }
+  if (V == 4) {
+    cudaFuncSetAttribute(k_fd_bsc_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_fd_bsc_tc<4><<<grid, TC_THREADS, smem, c->stream>>>(T8, S8, c->d_fd16, c->N, c->M, c->fd_rows, c->r0, c->nloc, c->bits, KP, dbg);
+  } else {
+    cudaFuncSetAttribute(k_fd_bsc_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_fd_bsc_tc<2><<<grid, TC_THREADS, smem, c->stream>>>(T8, S8, c->d_fd16, c->N, c->M, c->fd_rows, c->r0, c->nloc, c->bits, KP, dbg);
+  }
+  c->launches++;
+  e = cudaGetLastError();
+  cudaFreeAsync(T8, c->stream);
+  cudaFreeAsync(S8, c->stream);
+  return e;
+}
+
+}  // namespace ghicp_b200

@@ -106,6 +106,7 @@ struct Ctx {
   float *d_fs = nullptr, *d_ft = nullptr;  // raw [N][33], [M][33]
   float *d_fdf = nullptr;                  // [N][ldM] float FD
   bool have_bsc = false, have_fpfh = false, fd_built = false;
+  bool fd_tensor = false;  // FD plane built by the tcgen05 kernel
 
   // per-iteration workspaces
   int rows_per_cta = 8, n_chunks = 1;
@@ -198,6 +199,7 @@ struct KmResult {
 // ---- launchers (ghicp_kernels.cu) ---------------------------------------------------------------
 cudaError_t launch_pack_bsc(Ctx *c, const uint8_t *d_raw_s, const uint8_t *d_raw_t);
 cudaError_t launch_fd_bsc(Ctx *c);
+cudaError_t launch_fd_bsc_tc(Ctx *c);  // tcgen05 path; cudaErrorNotSupported when the shape does not fit
 cudaError_t launch_fd_fpfh(Ctx *c);
 // mode: 0 rowmin+stats, 1 count (needs penalty in d_iter), 2 fill
 cudaError_t launch_rowsweep(Ctx *c, int mode, const CostParams &cp);

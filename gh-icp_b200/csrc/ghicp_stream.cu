@@ -261,10 +261,7 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, c
     bulk_g2s(ring + stage * ST_STAGE_BYTES, panel_base + (size_t)(k * ST_UNROLL) * FD_PANEL, (unsigned)rows * ST_SEG_BYTES,
              &bars[stage]);
   };
-  if (HAS_FD && TMA) {
-    if (lane == 0)
-      for (int k = 0; k < min(ST_STAGES, nbatch); ++k) issue(k);
-  }
+  // (the first ST_STAGES batches were issued by the kernel prologue, before the operand staging)
 
   for (int rb = 0; rb < nrows; rb += ST_UNROLL) {
     uint4 q[ST_UNROLL];
@@ -465,6 +462,25 @@ __global__ void __launch_bounds__(ST_THREADS, (TMA && !X2) ? 3 : 2) k_stream(con
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r0 = a.row0 + blockIdx.y * ST_RB;
   const int nrows = min(ST_RB, a.row0 + a.nloc - r0);
+  if (TMA && HAS_FD) {
+    // start the FD stream first: the operand staging below overlaps with the first bulk copies in flight
+    const int panel0 = blockIdx.x * ST_CTA_COLS + warp * ST_PANEL;
+    if (lane == 0) {
+      for (int st = 0; st < ST_STAGES; ++st) mbar_init(&s_bar[warp][st], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      if (panel0 < a.M) {
+        const unsigned short *pb = a.fd + fd_index(a.fd_rows, r0 - a.row0, panel0);
+        const int nbatch = (nrows + ST_UNROLL - 1) / ST_UNROLL;
+        for (int k = 0; k < min(ST_STAGES, nbatch); ++k) {
+          const int rows = min(ST_UNROLL, nrows - k * ST_UNROLL);
+          mbar_expect_tx(&s_bar[warp][k], (unsigned)rows * ST_SEG_BYTES);
+          bulk_g2s(s_ring + warp * ST_RING_BYTES + k * ST_STAGE_BYTES, pb + (size_t)(k * ST_UNROLL) * FD_PANEL,
+                   (unsigned)rows * ST_SEG_BYTES, &s_bar[warp][k]);
+        }
+      }
+    }
+    __syncwarp();
+  }
   for (int r = tid; r < ST_RB; r += ST_THREADS) {
     const float4 Sv = (r < nrows) ? a.S4[r0 + r] : make_float4(0.f, 0.f, 0.f, 0.f);
     s_S4[r] = Sv;
@@ -474,10 +490,6 @@ __global__ void __launch_bounds__(ST_THREADS, (TMA && !X2) ? 3 : 2) k_stream(con
     }
     s_thr[r] = ((MODE == SM_NN || MODE == SM_NNR || MODE == SM_PRE || MODE == SM_PRE_COLS) && r < nrows) ? a.row_thr_init[r0 + r] : INF_BITS;
     s_cnt[r] = 0;
-  }
-  if (TMA && lane == 0) {
-    for (int st = 0; st < ST_STAGES; ++st) mbar_init(&s_bar[warp][st], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   unsigned char *ring = TMA ? s_ring + warp * ST_RING_BYTES : nullptr;
