@@ -290,6 +290,8 @@ def main():
     # coordinates, one iteration, device -> host read of the stats, the pair lists and the updated source.
     S_host = reg.source()
     T_host = sc.T
+    # time the same iteration range as the device-resident region (the weight schedule depends on the index)
+    reg.set_state(args.warmup, st.rmse, st.fdm, st.fdstd, st.para1, st.para2)
     barrier()
     t0 = time.perf_counter()
     e2e_steps = args.steps

@@ -84,16 +84,6 @@ __device__ __forceinline__ void top2_merge(Top2 &a, double ob, int oi, double os
     a.second = fmax(a.second, ob);
   }
 }
-__device__ __forceinline__ void warp_top2(Top2 &t) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    double ob = __shfl_xor_sync(0xffffffffu, t.best, o);
-    int oi = __shfl_xor_sync(0xffffffffu, t.idx, o);
-    double os = __shfl_xor_sync(0xffffffffu, t.second, o);
-    // a real entry (oi >= 0) merges; empty lanes carry -inf
-    if (oi >= 0) top2_merge(t, ob, oi, os);
-  }
-}
 
 struct AucArgs {
   const long long *rowptr; int n_chunks;  // row i spans rowptr[i*n_chunks] .. rowptr[(i+1)*n_chunks]
@@ -139,97 +129,6 @@ __global__ void k_auc_phase_start(int n_rows, int n_cols, const long long *rowpt
   }
 }
 
-// ---- forward round -----------------------------------------------------------------------------
-__global__ void __launch_bounds__(AUC_BLOCK) k_fwd_bid(AucArgs a, const int *list, int cur) {
-  const int n_active = a.counters[cur];
-  const int lane = threadIdx.x & 31;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  if (blockIdx.x == 0 && threadIdx.x == 0) a.counters[cur ^ 1] = 0;
-  for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_active; w += warps) {
-    const int i = list[w];
-    const long long b = a.rowptr[(size_t)i * a.n_chunks], e = a.rowptr[(size_t)(i + 1) * a.n_chunks];
-    Top2 t{-1e300, -1e300, -1};
-    double bgain = 0.0;
-    for (long long k = b + lane; k < e; k += 32) {
-      const int j = a.csr_col[k];
-      const double g = a.csr_gain[k];
-      const double v = g - a.price[j];
-      if (v > t.best || (v == t.best && j < t.idx)) bgain = g;
-      top2_push(t, v, j);
-    }
-    // reduce; carry the gain of the best edge along
-    {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        double ob = __shfl_xor_sync(0xffffffffu, t.best, o);
-        int oi = __shfl_xor_sync(0xffffffffu, t.idx, o);
-        double os = __shfl_xor_sync(0xffffffffu, t.second, o);
-        double og = __shfl_xor_sync(0xffffffffu, bgain, o);
-        if (oi >= 0) {
-          if (ob > t.best || (ob == t.best && oi < t.idx) || t.idx < 0) bgain = og;
-          if (t.idx < 0) { t.best = ob; t.idx = oi; t.second = os; }
-          else top2_merge(t, ob, oi, os);
-        }
-      }
-    }
-    if (lane == 0) {
-      if (t.idx < 0 || t.best <= 0.0) {
-        // the private zero-gain dummy is at least as good: stay unmatched
-        a.assign[i] = DUMMY;
-        a.profit[i] = 0.0;
-      } else {
-        const double wv = fmax(t.second, 0.0);
-        const double newprice = a.price[t.idx] + (t.best - wv) + a.eps;
-        a.bid_obj[i] = t.idx;
-        a.bid_val[i] = newprice;
-        a.bid_aux[i] = bgain;
-        atomicMax(&a.bidmax[t.idx], d2ull(newprice));
-      }
-    }
-  }
-}
-
-__global__ void __launch_bounds__(AUC_BLOCK) k_fwd_resolve(AucArgs a, const int *list, int cur) {
-  const int n_active = a.counters[cur];
-  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_active; w += gridDim.x * blockDim.x) {
-    const int i = list[w];
-    if (a.assign[i] != UNASSIGNED) continue;
-    const int j = a.bid_obj[i];
-    if (d2ull(a.bid_val[i]) == a.bidmax[j]) atomicMin(&a.bidwin[j], i);
-  }
-}
-
-__global__ void __launch_bounds__(AUC_BLOCK) k_fwd_commit(AucArgs a, const int *list, int *next, int cur) {
-  const int n_active = a.counters[cur];
-  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_active; w += gridDim.x * blockDim.x) {
-    const int i = list[w];
-    if (a.assign[i] != UNASSIGNED) continue;  // went to its dummy
-    const int j = a.bid_obj[i];
-    if (a.bidwin[j] == i) {
-      const int prev = a.owner[j];
-      a.owner[j] = i;
-      a.price[j] = a.bid_val[i];
-      a.assign[i] = j;
-      a.profit[i] = a.bid_aux[i] - a.bid_val[i];
-      if (prev >= 0) {
-        a.assign[prev] = UNASSIGNED;
-        next[atomicAdd(&a.counters[cur ^ 1], 1)] = prev;
-      }
-    } else {
-      next[atomicAdd(&a.counters[cur ^ 1], 1)] = i;
-    }
-  }
-}
-// reset the per-object bid slots touched this round (separate pass: no read/write race with commit)
-__global__ void __launch_bounds__(AUC_BLOCK) k_fwd_reset(AucArgs a, const int *list, int cur) {
-  const int n_active = a.counters[cur];
-  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_active; w += gridDim.x * blockDim.x) {
-    const int i = list[w];
-    const int j = a.bid_obj[i];
-    if (j >= 0) { a.bidmax[j] = 0ull; a.bidwin[j] = INT_MAX; }
-  }
-}
-
 // ---- reverse round -------------------------------------------------------------------------------
 // D = sum of the prices of objects left free: the exact amount by which complementary slackness is violated,
 // i.e. the extra term of the optimality bound  OPT - ours <= |M*| * eps + D
@@ -246,88 +145,9 @@ __global__ void k_rev_collect(int n_cols, const int *owner, const double *price,
   if (j < n_cols && owner[j] < 0 && price[j] > 0.0) list[atomicAdd(&counters[cur], 1)] = j;
 }
 
-__global__ void __launch_bounds__(AUC_BLOCK) k_rev_offer(AucArgs a, const int *list, int cur) {
-  const int n_active = a.counters[cur];
-  const int lane = threadIdx.x & 31;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  if (blockIdx.x == 0 && threadIdx.x == 0) a.counters[cur ^ 1] = 0;
-  for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_active; w += warps) {
-    const int j = list[w];
-    const long long b = a.colptr[j], e = a.colptr[j + 1];
-    Top2 t{-1e300, -1e300, -1};
-    for (long long k = b + lane; k < e; k += 32) {
-      const int i = a.csc_row[k];
-      const double v = a.csc_gain[k] - a.profit[i];
-      top2_push(t, v, i);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      double ob = __shfl_xor_sync(0xffffffffu, t.best, o);
-      int oi = __shfl_xor_sync(0xffffffffu, t.idx, o);
-      double os = __shfl_xor_sync(0xffffffffu, t.second, o);
-      if (oi >= 0) {
-        if (t.idx < 0) { t.best = ob; t.idx = oi; t.second = os; }
-        else top2_merge(t, ob, oi, os);
-      }
-    }
-    if (lane == 0) {
-      if (t.idx < 0 || t.best <= a.eps) {
-        a.price[j] = 0.0;   // nobody is worth attracting: price falls to the floor, object stays free
-        a.bid_obj[j] = -1;
-      } else {
-        const double delta = fmin(t.best, (t.best - t.second) + a.eps);
-        a.bid_obj[j] = t.idx;   // person attracted
-        a.bid_val[j] = delta;
-        a.bid_aux[j] = t.best;
-        atomicMax(&a.bidmax[t.idx], d2ull(delta));
-      }
-    }
-  }
-}
-
-__global__ void __launch_bounds__(AUC_BLOCK) k_rev_resolve(AucArgs a, const int *list, int cur) {
-  const int n_active = a.counters[cur];
-  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_active; w += gridDim.x * blockDim.x) {
-    const int j = list[w];
-    const int i = a.bid_obj[j];
-    if (i < 0) continue;
-    if (d2ull(a.bid_val[j]) == a.bidmax[i]) atomicMin(&a.bidwin[i], j);
-  }
-}
-
-__global__ void __launch_bounds__(AUC_BLOCK) k_rev_commit(AucArgs a, const int *list, int *next, int cur) {
-  const int n_active = a.counters[cur];
-  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_active; w += gridDim.x * blockDim.x) {
-    const int j = list[w];
-    const int i = a.bid_obj[j];
-    if (i < 0) continue;
-    if (a.bidwin[i] == j) {
-      const int old = a.assign[i];
-      a.assign[i] = j;
-      a.owner[j] = i;
-      a.price[j] = a.bid_aux[j] - a.bid_val[j];
-      a.profit[i] += a.bid_val[j];
-      if (old >= 0) {
-        a.owner[old] = -1;
-        if (a.price[old] > 0.0) next[atomicAdd(&a.counters[cur ^ 1], 1)] = old;
-      }
-    } else {
-      next[atomicAdd(&a.counters[cur ^ 1], 1)] = j;
-    }
-  }
-}
-__global__ void __launch_bounds__(AUC_BLOCK) k_rev_reset(AucArgs a, const int *list, int cur) {
-  const int n_active = a.counters[cur];
-  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_active; w += gridDim.x * blockDim.x) {
-    const int j = list[w];
-    const int i = a.bid_obj[j];
-    if (i >= 0) { a.bidmax[i] = 0ull; a.bidwin[i] = INT_MAX; }
-  }
-}
-
 
 // ---------------------------------------------------------------------------------------------
-// Persistent cooperative versions of the bidding rounds.  One launch runs a whole forward (or
+// Persistent cooperative bidding rounds.  One launch runs a whole forward (or
 // reverse) phase: rounds with many active bidders use the whole grid with grid-wide barriers between
 // bid / resolve / commit; once the active set is small (the long price-war tail) CTA 0 runs the rounds
 // alone with __syncthreads, which removes the launch / grid-barrier latency from ~all of the rounds.
@@ -411,11 +231,6 @@ __device__ __forceinline__ void fwd_bid_one(const AucArgs &a, int i, int lane) {
   fwd_scan(a, i, lane, b, e, t, bgain);
   if (lane == 0) fwd_finish(a, i, t, bgain);
 }
-__device__ __forceinline__ void fwd_resolve_one(const AucArgs &a, int i) {
-  if (ldcg_i(&a.assign[i]) != UNASSIGNED) return;
-  const int j = ldcg_i(&a.bid_obj[i]);
-  if (d2ull(ldcg_d(&a.bid_val[i])) == __ldcg(&a.bidmax[j])) atomicMin(&a.bidwin[j], i);
-}
 // returns via append(): persons that stay / become unassigned
 template <typename Append>
 __device__ __forceinline__ void fwd_commit_one(const AucArgs &a, int i, Append append) {
@@ -433,10 +248,6 @@ __device__ __forceinline__ void fwd_commit_one(const AucArgs &a, int i, Append a
   } else {
     append(i);
   }
-}
-__device__ __forceinline__ void fwd_reset_one(const AucArgs &a, int i) {
-  const int j = ldcg_i(&a.bid_obj[i]);
-  if (j >= 0) __stcg(&a.bidmax[j], 0ull);
 }
 
 __device__ __forceinline__ void rev_scan(const AucArgs &a, int j, int lane, long long kb, long long ke, Top2 &t) {
@@ -483,11 +294,6 @@ __device__ __forceinline__ void rev_offer_one(const AucArgs &a, int j, int lane)
   rev_scan(a, j, lane, a.colptr[j], a.colptr[j + 1], t);
   if (lane == 0) rev_finish(a, j, t);
 }
-__device__ __forceinline__ void rev_resolve_one(const AucArgs &a, int j) {
-  const int i = ldcg_i(&a.bid_obj[j]);
-  if (i < 0) return;
-  if (d2ull(ldcg_d(&a.bid_val[j])) == __ldcg(&a.bidmax[i])) atomicMin(&a.bidwin[i], j);
-}
 template <typename Append>
 __device__ __forceinline__ void rev_commit_one(const AucArgs &a, int j, Append append) {
   const int i = ldcg_i(&a.bid_obj[j]);
@@ -507,10 +313,6 @@ __device__ __forceinline__ void rev_commit_one(const AucArgs &a, int j, Append a
   } else {
     append(j);
   }
-}
-__device__ __forceinline__ void rev_reset_one(const AucArgs &a, int j) {
-  const int i = ldcg_i(&a.bid_obj[j]);
-  if (i >= 0) __stcg(&a.bidmax[i], 0ull);
 }
 
 // counters: [0],[1] list sizes, [2] base list size, [4] cur after the kernel, [5] rounds executed

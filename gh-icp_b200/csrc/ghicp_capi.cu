@@ -140,6 +140,7 @@ static int alloc_workspaces(Ctx *c) {
     if (c->cfg.corr_type == GHICP_CT_NNR) { if ((rc = dev_alloc(c, &c->d_cand[1], (size_t)c->cand_cap))) return rc; }
   }
   CK(c, cudaMemset(c->d_sdev, 0, sizeof(StreamDev)));
+  if ((rc = comm_warmup(c))) return rc;
   if ((rc = dev_alloc(c, &c->d_row_cd, (size_t)c->Npad))) return rc;
   if ((rc = dev_alloc(c, &c->d_row_idx, (size_t)c->Npad))) return rc;
   if ((rc = dev_alloc(c, &c->d_row_fd, (size_t)c->Npad))) return rc;

@@ -114,6 +114,15 @@ int comm_exchange(Ctx *c, int what) {
   return GHICP_OK;
 }
 
+// First use of a communicator sets up its channels (hundreds of ms): do it once when the workspaces are
+// allocated instead of inside the first iteration.
+int comm_warmup(Ctx *c) {
+  if (c->world == 1 || !c->d_xstats) return GHICP_OK;
+  NCK(c, g_nccl.AllGather(c->d_xstats + 4 * c->rank, c->d_xstats, 4, ncclDouble, (ncclComm_t)c->nccl_comm, c->stream));
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess) { set_error(c, "comm warm-up failed"); return GHICP_E_NCCL; }
+  return GHICP_OK;
+}
+
 // KM: per-row candidate counts of the rank's rows → all ranks
 int comm_gather_counts(Ctx *c) {
   if (c->world == 1) return GHICP_OK;

@@ -240,6 +240,7 @@ cudaError_t launch_build_csc(Ctx *c, int n_rows, int n_cols, long long nnz);
 int comm_unique_id(void *id128);
 int comm_init(Ctx *c, const void *id128, int rank, int world);
 void comm_destroy(Ctx *c);
+int comm_warmup(Ctx *c);
 int comm_exchange(Ctx *c, int what);         // bit0 stats, bit1 rows, bit2 columns
 int comm_gather_counts(Ctx *c);
 int comm_gather_edges(Ctx *c, const long long *cut);

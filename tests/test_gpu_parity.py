@@ -291,3 +291,55 @@ def test_error_paths(g):
     Ef = g.Energyfunction().init(50, 40, sc.bbx_magnitude)
     with pytest.raises(g.GhicpError):
         g.GHRegistration(Kp, Ef, 1, g.CT_NN)  # RoPS: "Not passed yet" in the reference
+
+
+# ---- ragged / tiny shapes (partial column panels, partial row blocks, fewer than 3 pairs) ----------------
+@pytest.mark.parametrize("N,M", [(1, 1), (2, 5), (3, 700), (700, 3), (257, 255), (513, 2049)])
+@pytest.mark.parametrize("Ft,Ct", [("none", "nn"), ("bsc", "nn"), ("bsc", "nnr"), ("bsc", "km")])
+def test_ragged_and_tiny_shapes(g, orc, scratch_cwd, N, M, Ft, Ct):
+    sc = g.synth.gen_points(N, M, overlap=0.7, extent=(20, 20, 4), noise=0.02, seed=N * 7 + M)
+    ft = {"none": g.FT_NONE, "bsc": g.FT_BSC}[Ft]
+    ct = {"nn": g.CT_NN, "nnr": g.CT_NNR, "km": g.CT_KM}[Ct]
+    if Ft == "bsc":
+        g.synth.add_bsc(sc, bits=441, V=4)
+    reg, o = make_pair(g, orc, sc, ft, ct, solve_mode=1)
+    for it in range(3):
+        a, b = reg.iterate(), o.iterate()
+        assert a.penalty == pytest.approx(b.penalty, rel=1e-6, nan_ok=True)
+        if ct != g.CT_KM:
+            sp, tp = reg.pairs()
+            osp, otp = o.pairs()
+            assert np.array_equal(sp, osp) and np.array_equal(tp, otp), (it, N, M)
+            assert np.allclose(np.array(a.Rt), np.array(b.Rt), atol=1e-5)
+        else:
+            assert abs(a.km_energy - b.km_energy) <= max(N, M) * 0.01 + 1e-6 * abs(b.km_energy)
+            o.set_keypoints(reg.source(), sc.T)
+            o.set_bsc(sc.bsc_s, sc.bsc_t, sc.bits)
+            o.build_fd()
+            o.set_state(a.iteration + 1, a.rmse, a.fdm, a.fdstd, a.para1, a.para2)
+        if a.converged or b.converged:
+            break
+
+
+def test_dof4_two_variants_loop(g, orc):
+    """dof != 6 uses only the first two BSC source variants (src/ghicp_reg.cpp:181-182)."""
+    sc = g.synth.add_bsc(g.synth.gen_points(500, 450, overlap=0.7, extent=(50, 50, 10), noise=0.03, seed=77), bits=441, V=4)
+    reg, o = make_pair(g, orc, sc, g.FT_BSC, g.CT_NN, dof=4, solve_mode=1)
+    assert np.array_equal(reg.fd(), o.fd())
+    for _ in range(4):
+        a, b = reg.iterate(), o.iterate()
+        sp, tp = reg.pairs()
+        osp, otp = o.pairs()
+        assert np.array_equal(sp, osp) and np.array_equal(tp, otp)
+
+
+def test_bsc_672_bits_loop(g, orc):
+    """BASELINE.json names 672-bit BSC; 672 bits take the POPC FD kernel (the tcgen05 tiling holds <= 448)."""
+    sc = g.synth.add_bsc(g.synth.gen_points(400, 420, overlap=0.7, extent=(50, 50, 10), noise=0.03, seed=78), bits=672, V=4)
+    reg, o = make_pair(g, orc, sc, g.FT_BSC, g.CT_NNR, solve_mode=1)
+    assert np.array_equal(reg.fd(), o.fd())
+    for _ in range(4):
+        a, b = reg.iterate(), o.iterate()
+        sp, tp = reg.pairs()
+        osp, otp = o.pairs()
+        assert np.array_equal(sp, osp) and np.array_equal(tp, otp)
