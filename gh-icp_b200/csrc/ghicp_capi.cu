@@ -78,6 +78,7 @@ static void free_all(Ctx *c) {
   dev_free(&c->d_S4); dev_free(&c->d_T4); dev_free(&c->d_sdev); dev_free(&c->d_row_thr); dev_free(&c->d_col_thr);
   dev_free(&c->d_rowbest); dev_free(&c->d_colbest); dev_free(&c->d_rowidx2); dev_free(&c->d_colidx2);
   dev_free(&c->d_cand[0]); dev_free(&c->d_cand[1]);
+  dev_free(&c->d_emit); c->emit_cap = 0;
   if (c->h_sdev) { cudaFreeHost(c->h_sdev); c->h_sdev = nullptr; }
   if (c->h_iter) { cudaFreeHost(c->h_iter); c->h_iter = nullptr; }
   if (c->h_counters) { cudaFreeHost(c->h_counters); c->h_counters = nullptr; }
@@ -179,6 +180,10 @@ static int alloc_workspaces(Ctx *c) {
     if ((rc = dev_alloc(c, &c->d_list[0], (size_t)nmax))) return rc;
     if ((rc = dev_alloc(c, &c->d_list[1], (size_t)nmax))) return rc;
     if ((rc = dev_alloc(c, &c->d_counters, 16))) return rc;
+    // edge list of the KM count pass: generous for a settled loop (a few edges per keypoint), grown on demand
+    const size_t plane = (size_t)std::max(c->nloc, 1) * (size_t)M;
+    c->emit_cap = std::min(plane, std::max((size_t)1 << 21, (size_t)32 * (size_t)(c->nloc + M)));
+    if ((rc = dev_alloc(c, &c->d_emit, c->emit_cap))) return rc;
   }
   return GHICP_OK;
 }
@@ -339,6 +344,7 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
     if ((rc = comm_gather_counts(c))) return rc;
     CK(c, launch_scan_rows(c));
     CK(c, cudaMemcpyAsync(c->h_iter, c->d_iter, sizeof(DevIter), cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(c->h_sdev, c->d_sdev, sizeof(StreamDev), cudaMemcpyDeviceToHost, st));
     if (sharded)
       for (int r = 0; r <= c->world; ++r)
         CK(c, cudaMemcpyAsync(&c->h_rowptr_cut[r], c->d_rowptr + std::min(c->N, r * c->shard), sizeof(long long),
@@ -348,8 +354,23 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
     const double penalty = c->h_iter->penalty;
     if ((rc = ensure_edges(c, nnz_super))) return rc;
     if (nnz_super > 0) {
-      ++stream_passes;
-      CK(c, launch_stream(c, cp, 3, false));
+      // this rank's gate hits were appended to the edge list by the count pass; only when the list
+      // overflowed is the plane streamed a second time (fill pass), and the list grown for the next iteration
+      const unsigned long long emitted = c->h_sdev->emit_count;
+      const bool force_fill = getenv("GHICP_KM_FILL") != nullptr;  // test hook: always take the fill pass
+      if (emitted <= (unsigned long long)c->emit_cap && !force_fill) {
+        if (emitted > 0) CK(c, launch_emit_scatter(c, cp, emitted));
+      } else {
+        ++stream_passes;
+        CK(c, launch_stream(c, cp, 3, false));
+        const size_t plane = (size_t)std::max(c->nloc, 1) * (size_t)c->M;
+        const size_t want = std::min(plane, (size_t)emitted * 2);
+        if (want > c->emit_cap && want <= ((size_t)1 << 27)) {
+          CK(c, cudaStreamSynchronize(st));
+          if ((rc = dev_alloc(c, &c->d_emit, want))) return rc;
+          c->emit_cap = want;
+        }
+      }
       CK(c, launch_csr_check(c, cp));
       if (sharded) {
         if ((rc = comm_gather_edges(c, c->h_rowptr_cut))) return rc;

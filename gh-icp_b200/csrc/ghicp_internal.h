@@ -61,6 +61,7 @@ struct StreamDev {  // device-resident scalars of the streaming path
   int cand_count[2];     // row / column candidates
   int overflow;
   unsigned long long nnz_valid;
+  unsigned long long emit_count;  // KM: gate hits appended to the edge list by the count pass (may exceed its capacity)
 };
 struct StreamArgs {
   const unsigned short *fd;  // fp16 FD plane (panel-major) or nullptr (no feature)
@@ -81,6 +82,7 @@ struct StreamArgs {
   int *cnt; const long long *rowptr; int *cursor; int *csr_col;
   float *row_fd;   // FD of (row, its partner)
   float *csr_fd;   // FD of every CSR entry
+  unsigned long long *emit; unsigned long long emit_cap;  // KM edge list: (row << 32 | col) per gate hit
 };
 
 // ---- the context ----------------------------------------------------------------------------------
@@ -164,6 +166,8 @@ struct Ctx {
   int *d_rowidx2 = nullptr, *d_colidx2 = nullptr;
   Cand *d_cand[2] = {nullptr, nullptr};
   int cand_cap = 0;
+  unsigned long long *d_emit = nullptr;     // KM edge list of the count pass
+  size_t emit_cap = 0;
 
   // host loop state (include/ghicp_reg.h:173-202)
   int iteration = 0;
@@ -227,6 +231,7 @@ cudaError_t launch_stream_resolve(Ctx *c, const CostParams &cp, bool with_cols);
 cudaError_t launch_finalize_fast(Ctx *c, const LoopScalars &ls);
 cudaError_t launch_penalty_only(Ctx *c, const LoopScalars &ls);
 cudaError_t launch_scan_rows(Ctx *c);
+cudaError_t launch_emit_scatter(Ctx *c, const CostParams &cp, unsigned long long n_emitted);
 cudaError_t launch_csr_check(Ctx *c, const CostParams &cp);
 int stream_num_parts(const Ctx *c);
 

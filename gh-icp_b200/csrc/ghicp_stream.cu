@@ -146,6 +146,7 @@ __global__ void k_margin(StreamDev *dev, double A, double a, double b, double fd
   dev->cand_count[1] = 0;
   dev->overflow = 0;
   dev->nnz_valid = 0;
+  dev->emit_count = 0;
   if (use_iter_penalty) {
     // KM gate: superset threshold = penalty*(1+slack) + margin, rounded up
     const double p = iter->penalty * kappa;   // thresholds live in the scaled domain
@@ -209,6 +210,33 @@ __device__ __noinline__ void slow_col(const StreamArgs &a, int i, int j, float c
     const double e = exact_cd(a, i, j);
     atomicMin(&a.colbest[j], ord64(e));
     push_candidate(a, 1, i, j, e);
+  }
+}
+
+// KM count pass, rare path: a warp-row with `total` gate hits (bit c of mask8 = column j0 + c of this lane).
+// Besides the per-row count the hits are appended to a global edge list, so that the CSR can be scattered
+// from the list instead of streaming the plane a second time (the fill pass stays as the overflow fallback).
+__device__ __noinline__ void emit_hits(const StreamArgs &a, int *s_cnt_r, int row, int j0, unsigned mask8, int total,
+                                       int lane) {
+  unsigned long long base = 0;
+  if (lane == 0) {
+    atomicAdd(s_cnt_r, total);
+    base = atomicAdd(&a.dev->emit_count, (unsigned long long)total);
+  }
+  base = __shfl_sync(0xffffffffu, base, 0);
+  const int c8 = __popc(mask8);
+  int incl = c8;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  unsigned long long pos = base + (unsigned long long)(incl - c8);
+  while (mask8) {
+    const int c = __ffs(mask8) - 1;
+    mask8 &= mask8 - 1;
+    if (pos < a.emit_cap) a.emit[pos] = ((unsigned long long)(unsigned)row << 32) | (unsigned)(j0 + c);
+    ++pos;
   }
 }
 
@@ -344,22 +372,25 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, c
         }
         }
     };
-    auto decide_row = [&](const int u, const float (&cd)[ST_CPL]) {
+    // do_rows = false: the batch-level test has shown that no row of the batch can touch its running minimum
+    auto decide_row = [&](const int u, const float (&cd)[ST_CPL], const bool do_rows) {
       const int r = rb + u;
         if (MODE == SM_PRE || MODE == SM_PRE_COLS) {
           // seed pass: FP32 row (and column) minima only, no decisions
-          float m8 = fminf(fminf(fminf(cd[0], cd[1]), fminf(cd[2], cd[3])), fminf(fminf(cd[4], cd[5]), fminf(cd[6], cd[7])));
-          const unsigned wmin = __reduce_min_sync(0xffffffffu, __float_as_uint(m8));
-          if (lane == 0 && wmin < thrbase[u]) atomicMin(&thrbase[u], wmin);
+          if (do_rows) {
+            float m8 = fminf(fminf(fminf(cd[0], cd[1]), fminf(cd[2], cd[3])), fminf(fminf(cd[4], cd[5]), fminf(cd[6], cd[7])));
+            const unsigned wmin = __reduce_min_sync(0xffffffffu, __float_as_uint(m8));
+            if (lane == 0 && wmin < thrbase[u]) atomicMin(&thrbase[u], wmin);
+          }
           if (MODE == SM_PRE_COLS) {
 #pragma unroll
             for (int c = 0; c < ST_CPL; ++c) colrun[c] = fminf(colrun[c], cd[c]);
           }
         } else if (MODE == SM_NN || MODE == SM_NNR) {
           float m8 = fminf(fminf(fminf(cd[0], cd[1]), fminf(cd[2], cd[3])), fminf(fminf(cd[4], cd[5]), fminf(cd[6], cd[7])));
-          const unsigned wmin = __reduce_min_sync(0xffffffffu, __float_as_uint(m8));
+          const unsigned wmin = do_rows ? __reduce_min_sync(0xffffffffu, __float_as_uint(m8)) : INF_BITS;
           const float run = __uint_as_float(thrbase[u]);
-          if (__uint_as_float(wmin) <= run + m2) {  // warp-uniform, rare once the running minimum is tight
+          if (do_rows && __uint_as_float(wmin) <= run + m2) {  // warp-uniform, rare once the running minimum is tight
             // the row argmin is within 2*margin of the smallest value of ANY set that contains it
             const float lim = fminf(run, __uint_as_float(wmin)) + m2;
 #pragma unroll
@@ -379,13 +410,14 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, c
           }
         } else {
           // KM gate on the superset threshold (exactly re-checked per CSR entry afterwards)
-          int c8 = 0;
+          unsigned mask8 = 0;
 #pragma unroll
-          for (int c = 0; c < ST_CPL; ++c) c8 += (cd[c] < thr_hi) ? 1 : 0;
+          for (int c = 0; c < ST_CPL; ++c) mask8 |= (cd[c] < thr_hi) ? (1u << c) : 0u;
+          const int c8 = __popc(mask8);
           const int total = __reduce_add_sync(0xffffffffu, c8);
           if (total) {
             if (MODE == SM_COUNT) {
-              if (lane == 0) atomicAdd(&s_cnt[r], total);
+              emit_hits(a, &s_cnt[r], r0 + r, j0, mask8, total, lane);
             } else {
               int base = 0;
               if (lane == 0) base = atomicAdd(&a.cursor[r0 + r], total);
@@ -410,15 +442,43 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, c
       float cdm[ST_UNROLL][ST_CPL];
 #pragma unroll
       for (int u = 0; u < ST_UNROLL; ++u) compute_row(u, cdm[u]);
+      if (MODE == SM_COUNT || MODE == SM_FILL) {
+        // one gate test per batch: the minimum of the ST_UNROLL x ST_CPL values against the threshold
+        // (hits are a few 1e-5 of the plane once the loop has settled)
+        float bm[ST_CPL];
 #pragma unroll
-      for (int u = 0; u < ST_UNROLL; ++u) decide_row(u, cdm[u]);
+        for (int cc = 0; cc < ST_CPL; ++cc) {
+          bm[cc] = cdm[0][cc];
+#pragma unroll
+          for (int u = 1; u < ST_UNROLL; ++u) bm[cc] = fminf(bm[cc], cdm[u][cc]);
+        }
+        const float m8 = fminf(fminf(fminf(bm[0], bm[1]), fminf(bm[2], bm[3])), fminf(fminf(bm[4], bm[5]), fminf(bm[6], bm[7])));
+        if (__any_sync(0xffffffffu, m8 < thr_hi)) {
+#pragma unroll
+          for (int u = 0; u < ST_UNROLL; ++u) decide_row(u, cdm[u], true);
+        }
+      } else {
+        // one vote per batch: does any lane hold a value that can touch the running minimum of its row?
+        // (for the seed passes: strictly below it)
+        bool touch = false;
+#pragma unroll
+        for (int u = 0; u < ST_UNROLL; ++u) {
+          const float (&cd)[ST_CPL] = cdm[u];
+          const float m8 = fminf(fminf(fminf(cd[0], cd[1]), fminf(cd[2], cd[3])), fminf(fminf(cd[4], cd[5]), fminf(cd[6], cd[7])));
+          const float run = __uint_as_float(thrbase[u]);
+          touch |= (MODE == SM_PRE || MODE == SM_PRE_COLS) ? (m8 < run) : (m8 <= run + m2);
+        }
+        const bool do_rows = __any_sync(0xffffffffu, touch);
+#pragma unroll
+        for (int u = 0; u < ST_UNROLL; ++u) decide_row(u, cdm[u], do_rows);
+      }
     } else {
 #pragma unroll
       for (int u = 0; u < ST_UNROLL; ++u) {
         if (rb + u < nrows) {
           float cd1[ST_CPL];
           compute_row(u, cd1);
-          decide_row(u, cd1);
+          decide_row(u, cd1, true);
         }
       }
     }
@@ -603,6 +663,18 @@ __global__ void __launch_bounds__(256) k_csr_check(const StreamArgs a, const Dev
   if (lane == 0 && valid) atomicAdd(&a.dev->nnz_valid, (unsigned long long)valid);
 }
 
+// CSR columns from the edge list of the count pass (order inside a row is arbitrary, as with the fill pass:
+// the auction breaks ties by a hash of (row, col), not by position)
+__global__ void k_emit_scatter(const StreamArgs a, unsigned long long n) {
+  for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < n;
+       k += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long e = a.emit[k];
+    const int row = (int)(e >> 32), col = (int)(unsigned)e;
+    const long long pos = a.rowptr[row] + atomicAdd(&a.cursor[row], 1);
+    a.csr_col[pos] = col;
+  }
+}
+
 __global__ void __launch_bounds__(1024) k_scan_rows(const int *__restrict__ cnt, long long *__restrict__ rowptr,
                                                     int *__restrict__ cursor, int L, DevIter *iter) {
   __shared__ long long smem[33];
@@ -660,6 +732,7 @@ static StreamArgs make_args(Ctx *c, const CostParams &cp) {
   a.cand[0] = c->d_cand[0]; a.cand[1] = c->d_cand[1]; a.cand_cap = c->cand_cap;
   a.part_stats = c->d_part_stats;
   a.cnt = c->d_cnt; a.rowptr = c->d_rowptr; a.cursor = c->d_cursor; a.csr_col = c->d_csr_col;
+  a.emit = c->d_emit; a.emit_cap = c->d_emit ? (unsigned long long)c->emit_cap : 0ull;
   return a;
 }
 
@@ -826,6 +899,14 @@ cudaError_t launch_count_valid(Ctx *c, long long nnz) {
 }
 cudaError_t launch_scan_rows(Ctx *c) {
   k_scan_rows<<<1, 1024, 0, c->stream>>>(c->d_cnt, c->d_rowptr, c->d_cursor, c->N, c->d_iter);
+  c->launches++;
+  return cudaGetLastError();
+}
+cudaError_t launch_emit_scatter(Ctx *c, const CostParams &cp, unsigned long long n_emitted) {
+  StreamArgs a = make_args(c, cp);
+  const unsigned long long want = (n_emitted + 255) / 256;
+  const int blocks = (int)std::min<unsigned long long>(std::max<unsigned long long>(want, 1), 148ull * 8);
+  k_emit_scatter<<<blocks, 256, 0, c->stream>>>(a, n_emitted);
   c->launches++;
   return cudaGetLastError();
 }

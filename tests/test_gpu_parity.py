@@ -209,6 +209,27 @@ def test_streaming_path_km_candidates(g):
         slow.set_state(a.iteration + 1, a.rmse, a.fdm, a.fdstd, a.para1, a.para2)
 
 
+def test_km_edge_list_equals_fill_pass(g, monkeypatch):
+    """The KM count pass appends its gate hits to an edge list (one stream over the plane); the two-pass
+    count + fill route is the overflow fallback.  Both must give the same graph and the same matching."""
+    N, M = 2500, 2100
+    sc = g.synth.add_bsc(g.synth.gen_points(N, M, overlap=0.6, extent=(70, 70, 14), noise=0.04, seed=31), bits=441, V=4)
+    one = g.registration.from_scene(sc, g.FT_BSC, g.CT_KM)
+    monkeypatch.setenv("GHICP_KM_FILL", "1")
+    two = g.registration.from_scene(sc, g.FT_BSC, g.CT_KM)
+    for it in range(6):
+        monkeypatch.delenv("GHICP_KM_FILL", raising=False)
+        a = one.iterate()
+        monkeypatch.setenv("GHICP_KM_FILL", "1")
+        b = two.iterate()
+        assert a.stream_passes + 1 == b.stream_passes
+        assert (a.nnz, a.cor, a.penalty) == (b.nnz, b.cor, b.penalty)
+        assert a.km_energy == b.km_energy
+        pa, pb = one.pairs(), two.pairs()
+        assert np.array_equal(pa[0], pb[0]) and np.array_equal(pa[1], pb[1])
+        assert np.array_equal(one.source(), two.source())
+
+
 # ---- KM -----------------------------------------------------------------------------------------------
 def test_km_golden_g1_g2(g, orc):
     from golden_vectors import G1_W, G2_CD
