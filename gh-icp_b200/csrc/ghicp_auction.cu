@@ -483,44 +483,6 @@ __global__ void k_col_count(const int *__restrict__ csr_col, long long nnz, int 
   const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k < nnz) atomicAdd(&colcnt[csr_col[k]], 1);
 }
-__global__ void __launch_bounds__(1024) k_scan_i32(const int *__restrict__ cnt, long long *__restrict__ ptr,
-                                                   int *__restrict__ cursor, int L) {
-  __shared__ long long smem[33];
-  const int seg = (L + 1023) / 1024;
-  const int b = threadIdx.x * seg;
-  const int e = min(b + seg, L);
-  long long s = 0;
-  for (int k = b; k < e; ++k) s += cnt[k];
-  // block exclusive scan
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  long long x = s;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    long long y = __shfl_up_sync(0xffffffffu, x, o);
-    if (lane >= o) x += y;
-  }
-  if (lane == 31) smem[warp] = x;
-  __syncthreads();
-  if (warp == 0) {
-    long long w = smem[lane];
-    long long xs = w;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      long long y = __shfl_up_sync(0xffffffffu, xs, o);
-      if (lane >= o) xs += y;
-    }
-    smem[lane] = xs - w;
-    if (lane == 31) smem[32] = xs;
-  }
-  __syncthreads();
-  long long off = smem[warp] + x - s;
-  for (int k = b; k < e; ++k) {
-    ptr[k] = off;
-    off += cnt[k];
-    cursor[k] = 0;
-  }
-  if (threadIdx.x == 0) ptr[L] = smem[32];
-}
 __global__ void __launch_bounds__(AUC_BLOCK) k_csc_fill(int n_rows, const long long *rowptr, int n_chunks,
                                                          const int *csr_col, const double *csr_gain,
                                                          const long long *colptr, int *cursor, int *csc_row,
@@ -548,8 +510,10 @@ cudaError_t launch_build_csc(Ctx *c, int n_rows, int n_cols, long long nnz) {
     c->launches++;
   }
   // cursor reuse: d_bid_obj is free before the auction starts
-  k_scan_i32<<<1, 1024, 0, c->stream>>>(c->d_colcnt, c->d_colptr, c->d_bid_obj, n_cols);
-  c->launches++;
+  {
+    cudaError_t e = launch_scan_i32(c, c->d_colcnt, c->d_colptr, c->d_bid_obj, n_cols, nullptr);
+    if (e != cudaSuccess) return e;
+  }
   if (nnz > 0) {
     k_csc_fill<<<AUC_GRID, AUC_BLOCK, 0, c->stream>>>(n_rows, c->d_rowptr, c->n_chunks, c->d_csr_col, c->d_csr_gain,
                                                        c->d_colptr, c->d_bid_obj, c->d_csc_row, c->d_csc_gain);
@@ -587,7 +551,11 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
     while (e0 > eps_last * 1.0000001) { eps_list.push_back(e0); e0 /= 5.0; }
     eps_list.push_back(eps_last);
   }
-  if (nnz == 0) eps_list.assign(1, 0.5 * eps_final);
+  // Sparse candidate graphs (a settled loop: about one candidate per keypoint) need no epsilon scaling:
+  // price wars are bounded by the few alternatives a person has, and a single forward phase from zero
+  // prices leaves every free object at price zero (D = 0, no reverse auction).
+  const bool single_phase = nnz <= (long long)(1.5 * (double)nmax) && getenv("GHICP_AUCTION_SCALING") == nullptr;
+  if (nnz == 0 || single_phase) eps_list.assign(1, 0.5 * eps_final);
 
   int rounds = 0;
   const int max_rounds = 4000000;
@@ -611,6 +579,7 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
   const bool debug = getenv("GHICP_AUCTION_DEBUG") != nullptr;
   const double relax_factor = getenv("GHICP_AUCTION_RELAX") ? atof(getenv("GHICP_AUCTION_RELAX")) : 0.0;
   int last_rounds = 0;
+  bool ran_reverse = false;
   for (size_t ph = 0; ph < eps_list.size(); ++ph) {
     a.eps = eps_list[ph];
     k_auc_phase_start<<<gmax, 256, 0, st>>>(n_rows, n_cols, c->d_rowptr, c->n_chunks, c->d_assign, c->d_owner,
@@ -640,12 +609,14 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
       c->launches++;
       double D = 0.0;
       cudaMemcpyAsync(&D, d_D, sizeof(double), cudaMemcpyDeviceToHost, st);
+      cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(int) * 8, cudaMemcpyDeviceToHost, st);  // final, unless the reverse runs
       cudaStreamSynchronize(st);
       const double budget = 0.5 * eps_final * (double)(n_rows > n_cols ? n_rows : n_cols);
       need_reverse = D > budget;
       if (debug) fprintf(stderr, "[auction] free-object price sum D = %.4f, budget %.4f -> reverse %s\n", D, budget, need_reverse ? "yes" : "skipped");
     }
     if (need_reverse) {
+    ran_reverse = true;
     cudaMemsetAsync(&c->d_counters[0], 0, sizeof(int) * 2, st);
     k_rev_collect<<<gmax, 256, 0, st>>>(n_cols, c->d_owner, c->d_price, c->d_list[0], c->d_counters, 0);
     c->launches++;
@@ -673,8 +644,11 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
     }
   }
   {
-    cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(int) * 8, cudaMemcpyDeviceToHost, st);
-    cudaError_t e = cudaStreamSynchronize(st);
+    cudaError_t e = cudaSuccess;
+    if (ran_reverse || debug) {
+      cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(int) * 8, cudaMemcpyDeviceToHost, st);
+      e = cudaStreamSynchronize(st);
+    }
     if (e != cudaSuccess) { set_error(c, std::string("auction: ") + cudaGetErrorString(e)); return GHICP_E_CUDA; }
     rounds = c->h_counters[6];
     if (c->h_counters[3] != 0) { set_error(c, "auction: round limit exceeded"); return GHICP_E_NOCONV; }

@@ -79,6 +79,7 @@ static void free_all(Ctx *c) {
   dev_free(&c->d_rowbest); dev_free(&c->d_colbest); dev_free(&c->d_rowidx2); dev_free(&c->d_colidx2);
   dev_free(&c->d_cand[0]); dev_free(&c->d_cand[1]);
   dev_free(&c->d_emit); c->emit_cap = 0;
+  dev_free(&c->d_tile_sum); c->tile_cap = 0; dev_free(&c->d_solve_part);
   if (c->h_sdev) { cudaFreeHost(c->h_sdev); c->h_sdev = nullptr; }
   if (c->h_iter) { cudaFreeHost(c->h_iter); c->h_iter = nullptr; }
   if (c->h_counters) { cudaFreeHost(c->h_counters); c->h_counters = nullptr; }
@@ -140,6 +141,9 @@ static int alloc_workspaces(Ctx *c) {
     if ((rc = dev_alloc(c, &c->d_cand[0], (size_t)c->cand_cap))) return rc;
     if (c->cfg.corr_type == GHICP_CT_NNR) { if ((rc = dev_alloc(c, &c->d_cand[1], (size_t)c->cand_cap))) return rc; }
   }
+  c->tile_cap = 2 * ((std::max(L, (size_t)nmax) + 1023) / 1024 + 1);
+  if ((rc = dev_alloc(c, &c->d_tile_sum, c->tile_cap))) return rc;
+  if ((rc = dev_alloc(c, &c->d_solve_part, (size_t)3 * 64 * 12))) return rc;
   CK(c, cudaMemset(c->d_sdev, 0, sizeof(StreamDev)));
   if ((rc = comm_warmup(c))) return rc;
   if ((rc = dev_alloc(c, &c->d_row_cd, (size_t)c->Npad))) return rc;

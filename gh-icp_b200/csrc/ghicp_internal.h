@@ -166,6 +166,9 @@ struct Ctx {
   int *d_rowidx2 = nullptr, *d_colidx2 = nullptr;
   Cand *d_cand[2] = {nullptr, nullptr};
   int cand_cap = 0;
+  long long *d_tile_sum = nullptr;          // per-tile sums of the tiled scan / selection kernels
+  size_t tile_cap = 0;
+  double *d_solve_part = nullptr;           // per-CTA partial sums of the cooperative solve kernel
   unsigned long long *d_emit = nullptr;     // KM edge list of the count pass
   size_t emit_cap = 0;
 
@@ -217,6 +220,8 @@ cudaError_t launch_apply(Ctx *c);
 cudaError_t launch_solve_explicit(cudaStream_t stream, const double *d_s, const double *d_t, int n, DevIter *d_iter);
 cudaError_t launch_get_fd(Ctx *c, double *d_out);
 cudaError_t launch_scan_counts(Ctx *c);  // d_cnt → d_rowptr, nnz → d_iter->nnz
+// counts[L] → ptr[L + 1] (exclusive scan), cursor[L] zeroed, total → *total_out (device pointer, may be null)
+cudaError_t launch_scan_i32(Ctx *c, const int *cnt, long long *ptr, int *cursor, long long L, long long *total_out);
 cudaError_t launch_penalty(Ctx *c, double pivot, const LoopScalars &ls);
 cudaError_t launch_pair_fd_km(Ctx *c);
 cudaError_t launch_colmerge(Ctx *c);

@@ -2,14 +2,17 @@
 // of the GH-ICP inner loop for sm_100a.  Compiled with --fmad=false: every arithmetic operation on
 // the exact path is a separately rounded IEEE operation, in the reference's evaluation order, so
 // CD(i,j) is bit-identical to the reference's double arithmetic (src/ghicp_reg.cpp:122,259,308).
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <cooperative_groups.h>
 #include <cuda_fp16.h>
 
 #include "ghicp_internal.h"
 
 namespace ghicp_b200 {
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -497,10 +500,13 @@ __global__ void k_penalty(const double *__restrict__ xstats, int world, double p
 }
 
 // ---------------------------------------------------------------------------------------------
-// Single-CTA ordered compaction / exclusive scan helpers.
+// Tiled ordered scan / compaction: every CTA owns TILE consecutive items (4 per thread); a first kernel
+// leaves one sum per tile, the second adds up the tiles before its own (a few dozen values) and scans
+// inside the tile.  Two short launches instead of one CTA walking the whole array.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ long long block_exclusive_scan_1024(long long v, long long *smem /*[33]*/,
-                                                               long long *total) {
+constexpr int TILE_THREADS = 256, TILE_ITEMS = 4, TILE = TILE_THREADS * TILE_ITEMS;
+
+__device__ __forceinline__ long long block_exclusive_scan_256(long long v, long long *smem /*[9]*/, long long *total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   long long x = v;
 #pragma unroll
@@ -510,84 +516,137 @@ __device__ __forceinline__ long long block_exclusive_scan_1024(long long v, long
   }
   if (lane == 31) smem[warp] = x;
   __syncthreads();
-  if (warp == 0) {
-    long long w = smem[lane];
-    long long xs = w;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      long long y = __shfl_up_sync(0xffffffffu, xs, o);
-      if (lane >= o) xs += y;
-    }
-    smem[lane] = xs - w;  // exclusive warp offsets
-    if (lane == 31) smem[32] = xs;
+  if (threadIdx.x == 0) {
+    long long run = 0;
+    for (int w = 0; w < TILE_THREADS / 32; ++w) { const long long t = smem[w]; smem[w] = run; run += t; }
+    smem[TILE_THREADS / 32] = run;
   }
   __syncthreads();
-  long long excl = smem[warp] + x - v;
-  *total = smem[32];
+  const long long excl = smem[warp] + x - v;
+  *total = smem[TILE_THREADS / 32];
   __syncthreads();
   return excl;
 }
+// sum of tile_sum[stride * b], b < nb (every thread gets it)
+__device__ __forceinline__ long long tiles_before(const long long *tile_sum, int stride, int nb, long long *smem) {
+  long long p = 0;
+  for (int b = threadIdx.x; b < nb; b += TILE_THREADS) p += tile_sum[(size_t)stride * b];
+  long long tot;
+  block_exclusive_scan_256(p, smem, &tot);
+  return tot;
+}
 
-// counts[L] → rowptr[L+1] (exclusive), nnz → iter->nnz; cursor zeroed.
-__global__ void __launch_bounds__(1024) k_scan_counts(const int *__restrict__ cnt, long long *__restrict__ rowptr,
-                                                      int *__restrict__ cursor, long long L, DevIter *iter) {
-  __shared__ long long smem[33];
-  const long long seg = (L + 1023) / 1024;
-  const long long b = (long long)threadIdx.x * seg;
-  const long long e = (b + seg < L) ? b + seg : L;
-  long long s = 0;
-  for (long long k = b; k < e; ++k) s += cnt[k];
-  long long total;
-  long long off = block_exclusive_scan_1024(s, smem, &total);
-  for (long long k = b; k < e; ++k) {
-    rowptr[k] = off;
-    off += cnt[k];
-    cursor[k] = 0;
+__global__ void __launch_bounds__(TILE_THREADS) k_tile_sum_i32(const int *__restrict__ cnt, long long L,
+                                                               long long *__restrict__ tile_sum) {
+  __shared__ long long smem[TILE_THREADS / 32 + 1];
+  const long long base = (long long)blockIdx.x * TILE + threadIdx.x * TILE_ITEMS;
+  long long v = 0;
+#pragma unroll
+  for (int q = 0; q < TILE_ITEMS; ++q)
+    if (base + q < L) v += cnt[base + q];
+  long long tot;
+  block_exclusive_scan_256(v, smem, &tot);
+  if (threadIdx.x == 0) tile_sum[blockIdx.x] = tot;
+}
+// counts[L] → ptr[L+1] (exclusive), total → *total_out (optional); cursor zeroed.
+__global__ void __launch_bounds__(TILE_THREADS) k_tile_scan_i32(const int *__restrict__ cnt, long long L,
+                                                                const long long *__restrict__ tile_sum,
+                                                                long long *__restrict__ ptr, int *__restrict__ cursor,
+                                                                long long *total_out) {
+  __shared__ long long smem[TILE_THREADS / 32 + 1];
+  const long long pre = tiles_before(tile_sum, 1, blockIdx.x, smem);
+  const long long base = (long long)blockIdx.x * TILE + threadIdx.x * TILE_ITEMS;
+  int cq[TILE_ITEMS];
+  long long v = 0;
+#pragma unroll
+  for (int q = 0; q < TILE_ITEMS; ++q) {
+    cq[q] = (base + q < L) ? cnt[base + q] : 0;
+    v += cq[q];
   }
-  if (threadIdx.x == 0) {
-    rowptr[L] = total;
-    iter->nnz = total;
+  long long tot;
+  long long off = pre + block_exclusive_scan_256(v, smem, &tot);
+#pragma unroll
+  for (int q = 0; q < TILE_ITEMS; ++q) {
+    if (base + q < L) {
+      ptr[base + q] = off;
+      cursor[base + q] = 0;
+      off += cq[q];
+    }
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+    ptr[L] = pre + tot;
+    if (total_out) *total_out = pre + tot;
   }
 }
 
 // kind 0: NN   keep row i iff row_cd[i] < penalty          (src/ghicp_reg.cpp:725-730)
 // kind 1: NNR  keep row i iff col_idx[row_idx[i]] == i     (src/ghicp_reg.cpp:652-662)
 // kind 2: KM   keep column j iff owner[j] >= 0; pairs ordered by target index (src/km.cpp:157-167)
-__global__ void __launch_bounds__(1024) k_select(int kind, int n, int n_cols, const double *__restrict__ row_cd,
-                                                 const int *__restrict__ row_idx, const int *__restrict__ col_idx,
-                                                 const int *__restrict__ owner, int *__restrict__ sp,
-                                                 int *__restrict__ tp, const float *__restrict__ row_fd,
-                                                 float *__restrict__ pair_fd, DevIter *iter, double amb_rel) {
-  __shared__ long long smem[33];
-  const double penalty = iter->penalty;
-  if (threadIdx.x == 0) iter->ambiguous = 0;
-  __syncthreads();
-  const double band = amb_rel * fmax(1.0, fabs(penalty));
-  const int seg = (n + 1023) / 1024;
-  const int b = threadIdx.x * seg;
-  const int e = min(b + seg, n);
-  auto keep = [&](int k) -> bool {
-    if (kind == 0) return row_cd[k] < penalty;
-    if (kind == 1) { const int j = row_idx[k]; return (j >= 0 && j < n_cols) ? (col_idx[j] == k) : false; }
-    return owner[k] >= 0;
-  };
-  long long s = 0;
-  int amb = 0;
-  for (int k = b; k < e; ++k) {
-    s += keep(k) ? 1 : 0;
-    if (kind == 0 && amb_rel > 0.0 && fabs(row_cd[k] - penalty) <= band) ++amb;
+struct SelArgs {
+  int kind, n, n_cols;
+  const double *row_cd;
+  const int *row_idx, *col_idx, *owner;
+  int *sp, *tp;
+  const float *row_fd;
+  float *pair_fd;
+  DevIter *iter;
+  double amb_rel;
+  long long *tile_sum;  // [2][tiles]: kept, ambiguous
+};
+__device__ __forceinline__ bool sel_keep(const SelArgs &a, int k, double penalty) {
+  if (a.kind == 0) return a.row_cd[k] < penalty;
+  if (a.kind == 1) { const int j = a.row_idx[k]; return (j >= 0 && j < a.n_cols) ? (a.col_idx[j] == k) : false; }
+  return a.owner[k] >= 0;
+}
+__global__ void __launch_bounds__(TILE_THREADS) k_select_count(const SelArgs a) {
+  __shared__ long long smem[TILE_THREADS / 32 + 1];
+  const double penalty = a.iter->penalty;
+  const double band = a.amb_rel * fmax(1.0, fabs(penalty));
+  const int base = blockIdx.x * TILE + threadIdx.x * TILE_ITEMS;
+  long long v = 0;  // kept | ambiguous << 32
+#pragma unroll
+  for (int q = 0; q < TILE_ITEMS; ++q) {
+    const int k = base + q;
+    if (k < a.n) {
+      v += sel_keep(a, k, penalty) ? 1 : 0;
+      if (a.kind == 0 && a.amb_rel > 0.0 && fabs(a.row_cd[k] - penalty) <= band) v += 1ll << 32;
+    }
   }
-  if (amb) atomicAdd(&iter->ambiguous, amb);
-  long long total;
-  long long off = block_exclusive_scan_1024(s, smem, &total);
-  for (int k = b; k < e; ++k) {
-    if (keep(k)) {
-      if (kind == 2) { sp[off] = owner[k]; tp[off] = k; }
-      else { sp[off] = k; tp[off] = row_idx[k]; pair_fd[off] = row_fd[k]; }
+  long long tot;
+  block_exclusive_scan_256(v, smem, &tot);
+  if (threadIdx.x == 0) {
+    a.tile_sum[2 * blockIdx.x] = tot & 0xffffffffll;
+    a.tile_sum[2 * blockIdx.x + 1] = tot >> 32;
+  }
+}
+__global__ void __launch_bounds__(TILE_THREADS) k_select_write(const SelArgs a) {
+  __shared__ long long smem[TILE_THREADS / 32 + 1];
+  const double penalty = a.iter->penalty;
+  const long long pre = tiles_before(a.tile_sum, 2, blockIdx.x, smem);
+  const int base = blockIdx.x * TILE + threadIdx.x * TILE_ITEMS;
+  bool kq[TILE_ITEMS];
+  long long v = 0;
+#pragma unroll
+  for (int q = 0; q < TILE_ITEMS; ++q) {
+    kq[q] = (base + q < a.n) ? sel_keep(a, base + q, penalty) : false;
+    v += kq[q] ? 1 : 0;
+  }
+  long long tot;
+  long long off = pre + block_exclusive_scan_256(v, smem, &tot);
+#pragma unroll
+  for (int q = 0; q < TILE_ITEMS; ++q) {
+    const int k = base + q;
+    if (kq[q]) {
+      if (a.kind == 2) { a.sp[off] = a.owner[k]; a.tp[off] = k; }
+      else { a.sp[off] = k; a.tp[off] = a.row_idx[k]; a.pair_fd[off] = a.row_fd[k]; }
       ++off;
     }
   }
-  if (threadIdx.x == 0) iter->cor = (int)total;
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) a.iter->cor = (int)(pre + tot);
+  if (blockIdx.x == 0) {
+    const long long amb = tiles_before(a.tile_sum + 1, 2, gridDim.x, smem);
+    if (threadIdx.x == 0) a.iter->ambiguous = (int)amb;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -720,12 +779,42 @@ struct SolveArgs {
   int n_explicit;
   CostParams cp;
   DevIter *iter;
+  double *part;  // [3][SOLVE_GRID_MAX][SOLVE_K] per-CTA partial sums of the cooperative variant
 };
-constexpr int SOLVE_THREADS = 1024;
-__global__ void __launch_bounds__(SOLVE_THREADS) k_solve(const SolveArgs a) {
-  __shared__ double smem[12 * (SOLVE_THREADS / 32)];
-  static_assert(12 >= 10, "smem sized for the widest block_sum");
+// COOP = false: one CTA of 1024 threads (stand-alone rigid fit).  COOP = true: a cooperative grid of
+// SOLVE_GRID_MAX x 256 threads for the loop — per-CTA partial sums, grid barrier, then EVERY CTA adds the
+// partials in CTA order (fixed tree: deterministic, identical on every rank) and carries on redundantly.
+constexpr int SOLVE_GRID_MAX = 64;
+constexpr int SOLVE_K = 12;  // widest reduction (10) rounded up
+template <int K, int THREADS, bool COOP>
+__device__ __forceinline__ void solve_sum(double (&v)[K], double *smem, double *part, double *s_tot) {
+  block_sum<K, THREADS>(v, smem);
+  if (COOP) {
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) part[blockIdx.x * SOLVE_K + k] = v[k];
+      __threadfence();
+    }
+    cg::this_grid().sync();
+    if (threadIdx.x < K) {
+      double t = 0.0;
+      for (int b = 0; b < (int)gridDim.x; ++b) t += __ldcg(&part[b * SOLVE_K + threadIdx.x]);
+      s_tot[threadIdx.x] = t;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = s_tot[k];
+    __syncthreads();
+  }
+}
+template <bool COOP>
+__global__ void __launch_bounds__(COOP ? 256 : 1024) k_solve(const SolveArgs a) {
+  constexpr int SOLVE_THREADS = COOP ? 256 : 1024;
+  __shared__ double smem[SOLVE_K * (SOLVE_THREADS / 32)];
   __shared__ double s_b[16];
+  __shared__ double s_tot[SOLVE_K];
+  const bool lead = blockIdx.x == 0 && threadIdx.x == 0;  // the one thread that publishes results
+  const int p0 = blockIdx.x * SOLVE_THREADS + threadIdx.x, pstep = gridDim.x * SOLVE_THREADS;
   const bool explicit_pts = a.sxyz_pairs != nullptr;
   const int cor = explicit_pts ? a.n_explicit : a.iter->cor;
   auto load = [&](int p, double &sx, double &sy, double &sz, double &tx, double &ty, double &tz, double &fd) {
@@ -742,7 +831,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(const SolveArgs a) {
   };
   // pass 1
   double acc1[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  for (int p = threadIdx.x; p < cor; p += SOLVE_THREADS) {
+  for (int p = p0; p < cor; p += pstep) {
     double sx, sy, sz, tx, ty, tz, fd;
     load(p, sx, sy, sz, tx, ty, tz, fd);
     const double dx = sx - tx, dy = sy - ty, dz = sz - tz;
@@ -759,9 +848,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(const SolveArgs a) {
     else cd = ed;
     acc1[8] += cd;
   }
-  block_sum<9, SOLVE_THREADS>(acc1, smem);
+  solve_sum<9, SOLVE_THREADS, COOP>(acc1, smem, a.part, s_tot);
   if (threadIdx.x == 0) {
-    a.iter->km_cd_sum = acc1[8];
+    if (lead) a.iter->km_cd_sum = acc1[8];
     s_b[0] = acc1[0];               // sum of squared distances
     s_b[1] = acc1[1] / cor;         // FDM (NaN when cor == 0, as the reference)
     for (int k = 0; k < 6; ++k) s_b[2 + k] = acc1[2 + k] / cor;  // centroids
@@ -771,7 +860,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(const SolveArgs a) {
   const double mus[3] = {s_b[2], s_b[3], s_b[4]}, mud[3] = {s_b[5], s_b[6], s_b[7]};
   // pass 2
   double acc2[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  for (int p = threadIdx.x; p < cor; p += SOLVE_THREADS) {
+  for (int p = p0; p < cor; p += pstep) {
     double sx, sy, sz, tx, ty, tz, fd;
     load(p, sx, sy, sz, tx, ty, tz, fd);
     const double ds[3] = {sx - mus[0], sy - mus[1], sz - mus[2]};
@@ -783,26 +872,26 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(const SolveArgs a) {
     const double e = fd - FDM;
     acc2[9] += e * e;
   }
-  block_sum<10, SOLVE_THREADS>(acc2, smem);
+  solve_sum<10, SOLVE_THREADS, COOP>(acc2, smem, a.part + SOLVE_GRID_MAX * SOLVE_K, s_tot);
   __shared__ double s_Rt[16];
   if (threadIdx.x == 0) {
     DevIter *it = a.iter;
     double RMSE = s_b[0] / cor;
-    it->rmse = sqrt(RMSE);
-    it->fdm = FDM;
-    it->fdstd = sqrt(acc2[9] / cor);
+    if (lead) {
+      it->rmse = sqrt(RMSE);
+      it->fdm = FDM;
+      it->fdstd = sqrt(acc2[9] / cor);
+      it->solve_degenerate = (cor >= 3) ? 0 : 1;
+    }
     double Rt[16];
     for (int i = 0; i < 16; ++i) Rt[i] = (i % 5 == 0) ? 1.0 : 0.0;
-    it->solve_degenerate = 0;
     if (cor >= 3) {
       float mu_s[3], mu_d[3], sigma[9];
       for (int k = 0; k < 3; ++k) { mu_s[k] = (float)mus[k]; mu_d[k] = (float)mud[k]; }
       for (int k = 0; k < 9; ++k) sigma[k] = (float)(acc2[k] / cor);
       umeyama_from_moments_f32(mu_s, mu_d, sigma, Rt);
-    } else {
-      it->solve_degenerate = 1;
     }
-    for (int i = 0; i < 16; ++i) { it->Rt[i] = Rt[i]; s_Rt[i] = Rt[i]; }
+    for (int i = 0; i < 16; ++i) { if (lead) it->Rt[i] = Rt[i]; s_Rt[i] = Rt[i]; }
   }
   __syncthreads();
   // pass 3: RMSE after the update; R*v evaluated as ((R0*x + R1*y) + R2*z) + t like Eigen
@@ -810,7 +899,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(const SolveArgs a) {
   {
     const double R00 = s_Rt[0], R10 = s_Rt[1], R20 = s_Rt[2], R01 = s_Rt[4], R11 = s_Rt[5], R21 = s_Rt[6],
                  R02 = s_Rt[8], R12 = s_Rt[9], R22 = s_Rt[10], t0 = s_Rt[12], t1 = s_Rt[13], t2 = s_Rt[14];
-    for (int p = threadIdx.x; p < cor; p += SOLVE_THREADS) {
+    for (int p = p0; p < cor; p += pstep) {
       double sx, sy, sz, tx, ty, tz, fd;
       load(p, sx, sy, sz, tx, ty, tz, fd);
       const double nx = ((R00 * sx + R01 * sy) + R02 * sz) + t0;
@@ -820,8 +909,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(const SolveArgs a) {
       acc3[0] += (dx * dx + dy * dy) + dz * dz;
     }
   }
-  block_sum<1, SOLVE_THREADS>(acc3, smem);
-  if (threadIdx.x == 0) a.iter->rmse_after = sqrt(acc3[0] / cor);
+  solve_sum<1, SOLVE_THREADS, COOP>(acc3, smem, a.part + 2 * SOLVE_GRID_MAX * SOLVE_K, s_tot);
+  if (lead) a.iter->rmse_after = sqrt(acc3[0] / cor);
 }
 
 // KP.kpSXYZ.row(i) = (R * row^T + t)^T for ALL source keypoints (src/ghicp_reg.cpp:891-894)
@@ -974,27 +1063,43 @@ cudaError_t launch_pair_fd_km(Ctx *c) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_scan_counts(Ctx *c) {
-  const long long L = (long long)c->N * c->n_chunks;
-  k_scan_counts<<<1, 1024, 0, c->stream>>>(c->d_cnt, c->d_rowptr, c->d_cursor, L, c->d_iter);
-  c->launches++;
+cudaError_t launch_scan_i32(Ctx *c, const int *cnt, long long *ptr, int *cursor, long long L, long long *total_out) {
+  const int tiles = (int)std::max<long long>(1, (L + TILE - 1) / TILE);
+  if ((size_t)tiles > c->tile_cap) return cudaErrorInvalidValue;
+  k_tile_sum_i32<<<tiles, TILE_THREADS, 0, c->stream>>>(cnt, L, c->d_tile_sum);
+  k_tile_scan_i32<<<tiles, TILE_THREADS, 0, c->stream>>>(cnt, L, c->d_tile_sum, ptr, cursor, total_out);
+  c->launches += 2;
   return cudaGetLastError();
+}
+cudaError_t launch_scan_counts(Ctx *c) {
+  return launch_scan_i32(c, c->d_cnt, c->d_rowptr, c->d_cursor, (long long)c->N * c->n_chunks, &c->d_iter->nnz);
 }
 
-cudaError_t launch_select_nn(Ctx *c, double amb_rel) {
-  k_select<<<1, 1024, 0, c->stream>>>(0, c->N, c->M, c->d_row_cd, c->d_row_idx, nullptr, nullptr, c->d_sp, c->d_tp, c->d_row_fd, c->d_pair_fd, c->d_iter, amb_rel);
-  c->launches++;
+static cudaError_t launch_select(Ctx *c, SelArgs a) {
+  const int tiles = std::max(1, (a.n + TILE - 1) / TILE);
+  if ((size_t)tiles * 2 > c->tile_cap) return cudaErrorInvalidValue;
+  a.iter = c->d_iter; a.sp = c->d_sp; a.tp = c->d_tp; a.tile_sum = c->d_tile_sum;
+  k_select_count<<<tiles, TILE_THREADS, 0, c->stream>>>(a);
+  k_select_write<<<tiles, TILE_THREADS, 0, c->stream>>>(a);
+  c->launches += 2;
   return cudaGetLastError();
+}
+cudaError_t launch_select_nn(Ctx *c, double amb_rel) {
+  SelArgs a{};
+  a.kind = 0; a.n = c->N; a.n_cols = c->M; a.row_cd = c->d_row_cd; a.row_idx = c->d_row_idx;
+  a.row_fd = c->d_row_fd; a.pair_fd = c->d_pair_fd; a.amb_rel = amb_rel;
+  return launch_select(c, a);
 }
 cudaError_t launch_select_nnr(Ctx *c) {
-  k_select<<<1, 1024, 0, c->stream>>>(1, c->N, c->M, c->d_row_cd, c->d_row_idx, c->d_col_idx, nullptr, c->d_sp, c->d_tp, c->d_row_fd, c->d_pair_fd, c->d_iter, 0.0);
-  c->launches++;
-  return cudaGetLastError();
+  SelArgs a{};
+  a.kind = 1; a.n = c->N; a.n_cols = c->M; a.row_cd = c->d_row_cd; a.row_idx = c->d_row_idx; a.col_idx = c->d_col_idx;
+  a.row_fd = c->d_row_fd; a.pair_fd = c->d_pair_fd;
+  return launch_select(c, a);
 }
 cudaError_t launch_select_km(Ctx *c) {
-  k_select<<<1, 1024, 0, c->stream>>>(2, c->M, c->M, nullptr, nullptr, nullptr, c->d_owner, c->d_sp, c->d_tp, nullptr, nullptr, c->d_iter, 0.0);
-  c->launches++;
-  return cudaGetLastError();
+  SelArgs a{};
+  a.kind = 2; a.n = c->M; a.n_cols = c->M; a.owner = c->d_owner;
+  return launch_select(c, a);
 }
 
 cudaError_t launch_solve(Ctx *c, const CostParams &cp) {
@@ -1004,16 +1109,20 @@ cudaError_t launch_solve(Ctx *c, const CostParams &cp) {
   a.N = c->N; a.M = c->M; a.feature_type = c->cfg.feature_type;
   a.sp = c->d_sp; a.tp = c->d_tp; a.sxyz_pairs = nullptr; a.txyz_pairs = nullptr; a.n_explicit = 0;
   a.iter = c->d_iter;
-  k_solve<<<1, SOLVE_THREADS, 0, c->stream>>>(a);
+  a.part = c->d_solve_part;
+  const int nmax = std::max(c->N, c->M);
+  const int grid = std::min(SOLVE_GRID_MAX, std::max(1, (nmax + 1023) / 1024));
+  void *args[] = {(void *)&a};
+  cudaError_t e = cudaLaunchCooperativeKernel((void *)k_solve<true>, dim3(grid), dim3(256), args, 0, c->stream);
   c->launches++;
-  return cudaGetLastError();
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t launch_solve_explicit(cudaStream_t stream, const double *d_s, const double *d_t, int n, DevIter *d_iter) {
   SolveArgs a{};
   a.sxyz_pairs = d_s; a.txyz_pairs = d_t; a.n_explicit = n; a.iter = d_iter;
   a.feature_type = GHICP_FT_NONE;
-  k_solve<<<1, SOLVE_THREADS, 0, stream>>>(a);
+  k_solve<false><<<1, 1024, 0, stream>>>(a);
   return cudaGetLastError();
 }
 

@@ -675,44 +675,6 @@ __global__ void k_emit_scatter(const StreamArgs a, unsigned long long n) {
   }
 }
 
-__global__ void __launch_bounds__(1024) k_scan_rows(const int *__restrict__ cnt, long long *__restrict__ rowptr,
-                                                    int *__restrict__ cursor, int L, DevIter *iter) {
-  __shared__ long long smem[33];
-  const int seg = (L + 1023) / 1024;
-  const int b = threadIdx.x * seg;
-  const int e = min(b + seg, L);
-  long long s = 0;
-  for (int k = b; k < e; ++k) s += cnt[k];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  long long x = s;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    long long y = __shfl_up_sync(0xffffffffu, x, o);
-    if (lane >= o) x += y;
-  }
-  if (lane == 31) smem[warp] = x;
-  __syncthreads();
-  if (warp == 0) {
-    long long w = smem[lane];
-    long long xs = w;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      long long y = __shfl_up_sync(0xffffffffu, xs, o);
-      if (lane >= o) xs += y;
-    }
-    smem[lane] = xs - w;
-    if (lane == 31) smem[32] = xs;
-  }
-  __syncthreads();
-  long long off = smem[warp] + x - s;
-  for (int k = b; k < e; ++k) {
-    rowptr[k] = off;
-    off += cnt[k];
-    cursor[k] = 0;
-  }
-  if (threadIdx.x == 0) { rowptr[L] = smem[32]; iter->nnz = smem[32]; }
-}
-
 }  // namespace
 
 // =============================================================================================
@@ -898,9 +860,7 @@ cudaError_t launch_count_valid(Ctx *c, long long nnz) {
   return cudaGetLastError();
 }
 cudaError_t launch_scan_rows(Ctx *c) {
-  k_scan_rows<<<1, 1024, 0, c->stream>>>(c->d_cnt, c->d_rowptr, c->d_cursor, c->N, c->d_iter);
-  c->launches++;
-  return cudaGetLastError();
+  return launch_scan_i32(c, c->d_cnt, c->d_rowptr, c->d_cursor, c->N, &c->d_iter->nnz);
 }
 cudaError_t launch_emit_scatter(Ctx *c, const CostParams &cp, unsigned long long n_emitted) {
   StreamArgs a = make_args(c, cp);
