@@ -289,7 +289,7 @@ def main():
     # every step: host (pinned inside the library) -> device copy of the current source + target
     # coordinates, one iteration, device -> host read of the stats, the pair lists and the updated source.
     S_host = reg.source()
-    T_host = sc.T
+    T_host = np.asfortranarray(sc.T, dtype=np.float64)  # the reference holds kpTXYZ column-major (Eigen::MatrixX3d)
     # time the same iteration range as the device-resident region (the weight schedule depends on the index)
     reg.set_state(args.warmup, st.rmse, st.fdm, st.fdstd, st.para1, st.para2)
     barrier()

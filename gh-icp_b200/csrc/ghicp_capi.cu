@@ -318,6 +318,9 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
   } else if (fast) {
     // ---- streaming path, KM: [statistics pass] + count pass + fill pass over the FD plane
     const bool stats_first = (ft == GHICP_FT_NONE) || (c->iteration <= 1);
+    // the edge list pays off on sparse candidate graphs; on a dense one (first iterations) its single append
+    // counter would serialise millions of hits, so it is switched on from last iteration's count
+    c->emit_on = c->last_local_nnz >= 0 && (size_t)c->last_local_nnz + (size_t)c->last_local_nnz / 2 <= c->emit_cap;
     CK(c, launch_stream_prep(c, cp, 0));
     CK(c, cudaMemsetAsync(c->d_cnt, 0, sizeof(int) * ((size_t)c->Npad + 2), st));
     if (stats_first) {
@@ -357,23 +360,26 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
     const long long nnz_super = c->h_iter->nnz;
     const double penalty = c->h_iter->penalty;
     if ((rc = ensure_edges(c, nnz_super))) return rc;
+    if (nnz_super == 0) c->last_local_nnz = 0;
     if (nnz_super > 0) {
-      // this rank's gate hits were appended to the edge list by the count pass; only when the list
-      // overflowed is the plane streamed a second time (fill pass), and the list grown for the next iteration
+      // this rank's gate hits were appended to the edge list by the count pass (when the list was on and did
+      // not overflow): scatter them; otherwise stream the plane a second time (fill pass)
+      const long long local_nnz = sharded ? c->h_rowptr_cut[c->rank + 1] - c->h_rowptr_cut[c->rank] : nnz_super;
       const unsigned long long emitted = c->h_sdev->emit_count;
       const bool force_fill = getenv("GHICP_KM_FILL") != nullptr;  // test hook: always take the fill pass
-      if (emitted <= (unsigned long long)c->emit_cap && !force_fill) {
+      if (c->emit_on && emitted <= (unsigned long long)c->emit_cap && !force_fill) {
         if (emitted > 0) CK(c, launch_emit_scatter(c, cp, emitted));
       } else {
         ++stream_passes;
         CK(c, launch_stream(c, cp, 3, false));
-        const size_t plane = (size_t)std::max(c->nloc, 1) * (size_t)c->M;
-        const size_t want = std::min(plane, (size_t)emitted * 2);
-        if (want > c->emit_cap && want <= ((size_t)1 << 27)) {
-          CK(c, cudaStreamSynchronize(st));
-          if ((rc = dev_alloc(c, &c->d_emit, want))) return rc;
-          c->emit_cap = want;
-        }
+      }
+      c->last_local_nnz = local_nnz;
+      const size_t plane = (size_t)std::max(c->nloc, 1) * (size_t)c->M;
+      const size_t want = std::min(plane, (size_t)local_nnz * 2);
+      if (want > c->emit_cap && want <= ((size_t)1 << 27)) {   // make room for next iteration's list
+        CK(c, cudaStreamSynchronize(st));
+        if ((rc = dev_alloc(c, &c->d_emit, want))) return rc;
+        c->emit_cap = want;
       }
       CK(c, launch_csr_check(c, cp));
       if (sharded) {
@@ -574,12 +580,8 @@ int ghicp_set_keypoints(ghicp_ctx *ctx, const double *sxyz, int N, const double 
     if ((rc = alloc_workspaces(c))) return rc;
     c->have_bsc = c->have_fpfh = c->fd_built = false;
     c->have_prev = false;
+    c->last_local_nnz = -1;
     reset_loop_state(c);
-  }
-  {  // centre of the FP32 filter coordinates: target centroid
-    double cx = 0, cy = 0, cz = 0;
-    for (int j = 0; j < M; ++j) { cx += txyz[j]; cy += txyz[(size_t)M + j]; cz += txyz[2 * (size_t)M + j]; }
-    c->center[0] = cx / M; c->center[1] = cy / M; c->center[2] = cz / M;
   }
   const size_t need = 3 * ((size_t)N + M) * sizeof(double);
   if (need > c->h_stage_cap) {
@@ -587,10 +589,18 @@ int ghicp_set_keypoints(ghicp_ctx *ctx, const double *sxyz, int N, const double 
     if (cudaMallocHost((void **)&c->h_stage, need) != cudaSuccess) { c->h_stage = nullptr; c->h_stage_cap = 0; return GHICP_E_NOMEM; }
     c->h_stage_cap = need;
   }
-  std::memcpy(c->h_stage, sxyz, 3 * (size_t)N * sizeof(double));
-  std::memcpy(c->h_stage + 3 * (size_t)N, txyz, 3 * (size_t)M * sizeof(double));
-  CK(c, cudaMemcpyAsync(c->d_s, c->h_stage, 3 * (size_t)N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  CK(c, cudaMemcpyAsync(c->d_t, c->h_stage + 3 * (size_t)N, 3 * (size_t)M * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  // pageable -> pinned staging, pipelined with the DMA: the target is staged while the source is in flight,
+  // and the centroid is taken from the staged copy while the target is in flight
+  double *hs = c->h_stage, *ht = c->h_stage + 3 * (size_t)N;
+  std::memcpy(hs, sxyz, 3 * (size_t)N * sizeof(double));
+  CK(c, cudaMemcpyAsync(c->d_s, hs, 3 * (size_t)N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  std::memcpy(ht, txyz, 3 * (size_t)M * sizeof(double));
+  CK(c, cudaMemcpyAsync(c->d_t, ht, 3 * (size_t)M * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  {  // centre of the FP32 filter coordinates: target centroid
+    double cx = 0, cy = 0, cz = 0;
+    for (int j = 0; j < M; ++j) { cx += ht[j]; cy += ht[(size_t)M + j]; cz += ht[2 * (size_t)M + j]; }
+    c->center[0] = cx / M; c->center[1] = cy / M; c->center[2] = cz / M;
+  }
   CK(c, cudaStreamSynchronize(c->stream));
   return GHICP_OK;
 }

@@ -171,6 +171,8 @@ struct Ctx {
   double *d_solve_part = nullptr;           // per-CTA partial sums of the cooperative solve kernel
   unsigned long long *d_emit = nullptr;     // KM edge list of the count pass
   size_t emit_cap = 0;
+  bool emit_on = false;                     // this iteration's count pass appends to the list
+  long long last_local_nnz = -1;            // gate hits in this context's rows last iteration (-1: no history)
 
   // host loop state (include/ghicp_reg.h:173-202)
   int iteration = 0;

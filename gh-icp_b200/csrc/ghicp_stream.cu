@@ -218,11 +218,10 @@ __device__ __noinline__ void slow_col(const StreamArgs &a, int i, int j, float c
 // from the list instead of streaming the plane a second time (the fill pass stays as the overflow fallback).
 __device__ __noinline__ void emit_hits(const StreamArgs &a, int *s_cnt_r, int row, int j0, unsigned mask8, int total,
                                        int lane) {
+  if (lane == 0) atomicAdd(s_cnt_r, total);
+  if (a.emit_cap == 0) return;  // list switched off (dense graph expected): count only, the fill pass follows
   unsigned long long base = 0;
-  if (lane == 0) {
-    atomicAdd(s_cnt_r, total);
-    base = atomicAdd(&a.dev->emit_count, (unsigned long long)total);
-  }
+  if (lane == 0) base = atomicAdd(&a.dev->emit_count, (unsigned long long)total);
   base = __shfl_sync(0xffffffffu, base, 0);
   const int c8 = __popc(mask8);
   int incl = c8;
@@ -457,6 +456,11 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, c
 #pragma unroll
           for (int u = 0; u < ST_UNROLL; ++u) decide_row(u, cdm[u], true);
         }
+      } else if (MODE == SM_NNR) {
+        // (batch-level votes push this variant, with its eight running column minima, into register spills:
+        // measured slower than the per-row form)
+#pragma unroll
+        for (int u = 0; u < ST_UNROLL; ++u) decide_row(u, cdm[u], true);
       } else {
         // one vote per batch: does any lane hold a value that can touch the running minimum of its row?
         // (for the seed passes: strictly below it)
@@ -694,7 +698,7 @@ static StreamArgs make_args(Ctx *c, const CostParams &cp) {
   a.cand[0] = c->d_cand[0]; a.cand[1] = c->d_cand[1]; a.cand_cap = c->cand_cap;
   a.part_stats = c->d_part_stats;
   a.cnt = c->d_cnt; a.rowptr = c->d_rowptr; a.cursor = c->d_cursor; a.csr_col = c->d_csr_col;
-  a.emit = c->d_emit; a.emit_cap = c->d_emit ? (unsigned long long)c->emit_cap : 0ull;
+  a.emit = c->d_emit; a.emit_cap = (c->d_emit && c->emit_on) ? (unsigned long long)c->emit_cap : 0ull;
   return a;
 }
 

@@ -222,12 +222,15 @@ def test_km_edge_list_equals_fill_pass(g, monkeypatch):
         a = one.iterate()
         monkeypatch.setenv("GHICP_KM_FILL", "1")
         b = two.iterate()
-        assert a.stream_passes + 1 == b.stream_passes
+        # the list is switched on from the previous iteration's edge count (off while the graph is dense)
+        assert b.stream_passes - a.stream_passes in (0, 1)
+        saved = b.stream_passes - a.stream_passes
         assert (a.nnz, a.cor, a.penalty) == (b.nnz, b.cor, b.penalty)
         assert a.km_energy == b.km_energy
         pa, pb = one.pairs(), two.pairs()
         assert np.array_equal(pa[0], pb[0]) and np.array_equal(pa[1], pb[1])
         assert np.array_equal(one.source(), two.source())
+    assert saved == 1   # a settled loop streams the plane once per iteration
 
 
 # ---- KM -----------------------------------------------------------------------------------------------
