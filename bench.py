@@ -234,6 +234,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
     dist = None
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own banner / debug output goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch
         import torch.distributed as dist_mod
         torch.cuda.set_device(local_rank)

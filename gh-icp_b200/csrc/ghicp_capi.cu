@@ -184,7 +184,8 @@ static int alloc_workspaces(Ctx *c) {
     if ((rc = dev_alloc(c, &c->d_list[0], (size_t)nmax))) return rc;
     if ((rc = dev_alloc(c, &c->d_list[1], (size_t)nmax))) return rc;
     if ((rc = dev_alloc(c, &c->d_counters, 16))) return rc;
-    // edge list of the KM count pass: generous for a settled loop (a few edges per keypoint), grown on demand
+    // edge list of the KM count pass: generous for a settled loop (a few edges per keypoint); denser graphs
+    // take the two-pass count + fill route (their time is the auction's anyway)
     const size_t plane = (size_t)std::max(c->nloc, 1) * (size_t)M;
     c->emit_cap = std::min(plane, std::max((size_t)1 << 21, (size_t)32 * (size_t)(c->nloc + M)));
     if ((rc = dev_alloc(c, &c->d_emit, c->emit_cap))) return rc;
@@ -374,13 +375,6 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
         CK(c, launch_stream(c, cp, 3, false));
       }
       c->last_local_nnz = local_nnz;
-      const size_t plane = (size_t)std::max(c->nloc, 1) * (size_t)c->M;
-      const size_t want = std::min(plane, (size_t)local_nnz * 2);
-      if (want > c->emit_cap && want <= ((size_t)1 << 27)) {   // make room for next iteration's list
-        CK(c, cudaStreamSynchronize(st));
-        if ((rc = dev_alloc(c, &c->d_emit, want))) return rc;
-        c->emit_cap = want;
-      }
       CK(c, launch_csr_check(c, cp));
       if (sharded) {
         if ((rc = comm_gather_edges(c, c->h_rowptr_cut))) return rc;
