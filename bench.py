@@ -259,7 +259,8 @@ def main():
     first_iters = []
     for _ in range(args.warmup):
         st = reg.iterate()
-        first_iters.append(dict(it=st.iteration, ms=st.ms_total, cor=st.cor, nnz=st.nnz, rounds=st.km_rounds))
+        first_iters.append(dict(it=st.iteration, ms=st.ms_total, cor=st.cor, nnz=st.nnz, rounds=st.km_rounds,
+                                km_energy=st.km_energy))
 
     def barrier():
         if dist is not None:

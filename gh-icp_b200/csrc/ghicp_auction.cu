@@ -548,6 +548,7 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
     // long sequential displacement chains) only runs when D exceeds that budget.
     const double eps_last = 0.5 * eps_final;
     double e0 = max_gain / 4.0;
+    if (const char *ov = getenv("GHICP_AUCTION_EPS0")) e0 = atof(ov);  // experiment hook: first epsilon (0 = single phase)
     while (e0 > eps_last * 1.0000001) { eps_list.push_back(e0); e0 /= 5.0; }
     eps_list.push_back(eps_last);
   }
