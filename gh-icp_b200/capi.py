@@ -12,6 +12,8 @@ FT_BSC, FT_ROPS, FT_FPFH, FT_NONE = 0, 1, 2, 3   # include/utility.h:51-57
 CT_NN, CT_NNR, CT_KM = 0, 1, 2                   # include/utility.h:59-64
 
 GHICP_W_FEW_PAIRS = 1
+# ghicp_solver_type (include/ghicp_b200.h): SVD is the reference's estimator, the others are opt-in extensions
+SOLVER_SVD, SOLVER_WEIGHTED_SVD, SOLVER_POINT_TO_PLANE, SOLVER_YAW_4DOF = 0, 1, 2, 3
 
 
 class GhicpError(RuntimeError):
@@ -25,7 +27,8 @@ class Config(C.Structure):
                 ("bbx_magnitude", C.c_float), ("nonmax", C.c_float), ("adjust_ratio", C.c_float),
                 ("adjust_step", C.c_float), ("estimated_iou", C.c_float), ("converge_t", C.c_float),
                 ("converge_r", C.c_float), ("max_iter", C.c_int), ("device", C.c_int),
-                ("km_eps", C.c_double), ("verbose", C.c_int), ("force_exact", C.c_int), ("reserved", C.c_int * 6)]
+                ("km_eps", C.c_double), ("verbose", C.c_int), ("force_exact", C.c_int),
+                ("fpfh_matrix_free", C.c_int), ("solver", C.c_int), ("reserved", C.c_int * 4)]
 
 
 class IterStats(C.Structure):
@@ -64,8 +67,8 @@ _lib = None
 EXPORTS = ["ghicp_abi_version", "ghicp_device_count", "ghicp_last_error", "ghicp_create", "ghicp_destroy",
            "ghicp_set_keypoints", "ghicp_set_bsc", "ghicp_set_fpfh", "ghicp_build_fd", "ghicp_iterate",
            "ghicp_run", "ghicp_get_pairs", "ghicp_get_source", "ghicp_get_rt", "ghicp_get_fd",
-           "ghicp_probe_rowmin", "ghicp_set_state", "ghicp_km_solve", "ghicp_rigid_fit",
-           "ghicp_comm_unique_id", "ghicp_comm_init"]
+           "ghicp_probe_rowmin", "ghicp_set_state", "ghicp_km_solve", "ghicp_rigid_fit", "ghicp_rigid_fit_ex",
+           "ghicp_set_target_normals", "ghicp_set_solver", "ghicp_comm_unique_id", "ghicp_comm_init"]
 
 
 def lib():
@@ -98,6 +101,9 @@ def lib():
     L.ghicp_set_state.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]
     L.ghicp_km_solve.argtypes = [C.c_int, dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, ip, dp, ip]
     L.ghicp_rigid_fit.argtypes = [C.c_int, dp, dp, C.c_int, dp]
+    L.ghicp_rigid_fit_ex.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, C.c_int, dp]
+    L.ghicp_set_target_normals.argtypes = [vp, dp]
+    L.ghicp_set_solver.argtypes = [vp, C.c_int]
     L.ghicp_comm_unique_id.argtypes = [vp]
     L.ghicp_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
     _lib = L
@@ -141,6 +147,19 @@ def km_solve(W, sp=None, tp=None, eps=0.01, penalty=1000.0, device=0):
     r = C.c_int(0)
     check(lib().ghicp_km_solve(device, _dp(W), n, sp, tp, eps, penalty, _ip(match), C.byref(e), C.byref(r)))
     return match, e.value, r.value
+
+
+def rigid_fit_ex(S, T, solver=SOLVER_SVD, normals=None, weights=None, device=0):
+    """Opt-in estimators (ghicp_solver_type): weighted point-to-point, point-to-plane LLS, yaw-only 4-DoF.
+    Returns (Rt 4x4, warning bits)."""
+    S = np.asfortranarray(S, dtype=np.float64)
+    T = np.asfortranarray(T, dtype=np.float64)
+    Nn = None if normals is None else np.asfortranarray(normals, dtype=np.float64)
+    W = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+    Rt = np.zeros(16)
+    rc = check(lib().ghicp_rigid_fit_ex(device, solver, _dp(S), _dp(T), None if Nn is None else _dp(Nn),
+                                        None if W is None else _dp(W), S.shape[0], _dp(Rt)))
+    return Rt.reshape(4, 4).T.copy(), rc
 
 
 def rigid_fit(S, T, device=0):

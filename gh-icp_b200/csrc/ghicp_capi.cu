@@ -63,6 +63,7 @@ static void free_all(Ctx *c) {
   dev_free(&c->d_s); dev_free(&c->d_t);
   dev_free(&c->d_bs); dev_free(&c->d_bt); dev_free(&c->d_fd16);
   dev_free(&c->d_fs); dev_free(&c->d_ft); dev_free(&c->d_fdf);
+  dev_free(&c->d_fsc); dev_free(&c->d_fscT); dev_free(&c->d_ftc); dev_free(&c->d_ftcT); dev_free(&c->d_tn);
   dev_free(&c->d_part_cd); dev_free(&c->d_part_idx); dev_free(&c->d_part_stats);
   dev_free(&c->d_row_cd); dev_free(&c->d_row_idx); dev_free(&c->d_col_cd); dev_free(&c->d_col_idx);
   dev_free(&c->d_flags); dev_free(&c->d_sp); dev_free(&c->d_tp); dev_free(&c->d_iter);
@@ -232,10 +233,29 @@ static int build_fd(Ctx *c) {
   } else if (c->cfg.feature_type == GHICP_FT_FPFH) {
     if (!c->have_fpfh) { set_error(c, "build_fd: FPFH descriptors not set"); return GHICP_E_ARG; }
     c->fd_rows = (size_t)std::max(c->nloc, 1);
-    int rc = dev_alloc(c, &c->d_fdf, fd_elems(c->fd_rows, c->M));
-    if (rc) return rc;
-    CK(c, cudaMemsetAsync(c->d_fdf, 0, fd_elems(c->fd_rows, c->M) * sizeof(float), c->stream));
-    CK(c, launch_fd_fpfh(c));
+    // Stored float plane (4*N*M bytes) or matrix-free (ghicp_fpfh.cu: FD recomputed inside the sweeps, O(N+M) memory).
+    // Both give bit-identical FD / CD values; auto mode stores the plane only while it is a modest share of the HBM.
+    const size_t plane_bytes = fd_elems(c->fd_rows, c->M) * sizeof(float);
+    bool mf = c->cfg.fpfh_matrix_free > 0 || getenv("GHICP_FPFH_MATRIX_FREE") != nullptr;
+    if (!mf && c->cfg.fpfh_matrix_free == 0) {
+      size_t free_b = 0, total_b = 0;
+      CK(c, cudaMemGetInfo(&free_b, &total_b));
+      mf = (double)plane_bytes > 0.4 * (double)free_b;
+    }
+    c->fpfh_mf = mf;
+    int rc;
+    if (mf) {
+      dev_free(&c->d_fdf);
+      if ((rc = dev_alloc(c, &c->d_fsc, (size_t)c->N * 36))) return rc;
+      if ((rc = dev_alloc(c, &c->d_fscT, (size_t)c->N * 36))) return rc;
+      if ((rc = dev_alloc(c, &c->d_ftc, (size_t)c->M * 36))) return rc;
+      if ((rc = dev_alloc(c, &c->d_ftcT, (size_t)c->M * 36))) return rc;
+      CK(c, launch_fpfh_prepare(c));
+    } else {
+      if ((rc = dev_alloc(c, &c->d_fdf, fd_elems(c->fd_rows, c->M)))) return rc;
+      CK(c, cudaMemsetAsync(c->d_fdf, 0, plane_bytes, c->stream));
+      CK(c, launch_fd_fpfh(c));
+    }
   }
   c->fd_built = true;
   return GHICP_OK;
@@ -262,6 +282,10 @@ static LoopScalars make_loop_scalars(const Ctx *c, const CostParams &cp) {
 
 static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
   if (c->N <= 0 || c->M <= 0) { set_error(c, "iterate: keypoints not set"); return GHICP_E_ARG; }
+  if (c->cfg.solver == GHICP_SOLVER_POINT_TO_PLANE && !c->have_normals) {
+    set_error(c, "iterate: GHICP_SOLVER_POINT_TO_PLANE needs ghicp_set_target_normals");
+    return GHICP_E_ARG;
+  }
   int rc;
   if ((rc = build_fd(c))) return rc;
   c->launches = 0;
@@ -391,9 +415,11 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
   if (exact_fallback) {
     // ---- all-double path (FPFH; forced; or fallback): calED + calCD_* (+ the row scan of NN / NNR)
     if (sharded && ct == GHICP_CT_KM) { set_error(c, "multi-GPU KM: all-double fallback not supported"); return GHICP_E_ARG; }
-    CK(c, launch_rowsweep(c, 0, cp));
+    const bool mf = (ft == GHICP_FT_FPFH) && c->fpfh_mf;   // matrix-free FPFH: FD recomputed inside the sweeps
+    CK(c, mf ? launch_rowsweep_mf(c, 0, cp) : launch_rowsweep(c, 0, cp));
     CK(c, launch_finalize_stats(c, cp, ls));
-    if (ct == GHICP_CT_NNR) CK(c, launch_colsweep(c, cp));
+    if (mf) CK(c, launch_rowfd_mf(c));
+    if (ct == GHICP_CT_NNR) CK(c, mf ? launch_colsweep_mf(c, cp) : launch_colsweep(c, cp));
     if ((rc = comm_exchange(c, 1 | 2 | (ct == GHICP_CT_NNR ? 4 : 0)))) return rc;
     CK(c, launch_penalty(c, cp.pivot, ls));
     if (ct == GHICP_CT_NNR && sharded) CK(c, launch_colmerge(c));
@@ -403,14 +429,14 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
     } else if (ct == GHICP_CT_NNR) {
       CK(c, launch_select_nnr(c));
     } else {
-      CK(c, launch_rowsweep(c, 1, cp));
+      CK(c, mf ? launch_rowsweep_mf(c, 1, cp) : launch_rowsweep(c, 1, cp));
       CK(c, launch_scan_counts(c));
       CK(c, cudaMemcpyAsync(c->h_iter, c->d_iter, sizeof(DevIter), cudaMemcpyDeviceToHost, st));
       CK(c, cudaStreamSynchronize(st));
       nnz = c->h_iter->nnz;
       const double penalty = c->h_iter->penalty;
       if ((rc = ensure_edges(c, nnz))) return rc;
-      if (nnz > 0) CK(c, launch_rowsweep(c, 2, cp));
+      if (nnz > 0) CK(c, mf ? launch_rowsweep_mf(c, 2, cp) : launch_rowsweep(c, 2, cp));
       CK(c, launch_build_csc(c, c->N, c->M, nnz));
       if ((rc = km_auction(c, c->N, c->M, nnz, c->KM_eps, std::max(penalty, c->KM_eps), &kres))) return rc;
       CK(c, launch_select_km(c));
@@ -421,6 +447,8 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
   CK(c, cudaEventRecord(c->ev[2], st));
   // transformestimation (numeric core) + update of all source keypoints
   CK(c, launch_solve(c, cp));
+  // opt-in estimators replace the transform (and the RMSE after it); the pair statistics stay k_solve's
+  if (c->cfg.solver != GHICP_SOLVER_SVD) CK(c, launch_solve_alt(c, c->cfg.solver));
   CK(c, launch_apply(c));
   CK(c, cudaEventRecord(c->ev[3], st));
   CK(c, cudaMemcpyAsync(c->h_iter, c->d_iter, sizeof(DevIter), cudaMemcpyDeviceToHost, st));
@@ -534,6 +562,10 @@ int ghicp_create(const ghicp_config *cfg, ghicp_ctx **out) {
     set_error(nullptr, "ghicp_create: feature_type must be BSC, FPFH or None (RoPS is 'Not passed yet' in the reference, test/ghicp_main.cpp:130-134)");
     return GHICP_E_ARG;
   }
+  if (cfg->solver != GHICP_SOLVER_SVD && cfg->solver != GHICP_SOLVER_POINT_TO_PLANE && cfg->solver != GHICP_SOLVER_YAW_4DOF) {
+    set_error(nullptr, "ghicp_create: solver must be SVD (reference), POINT_TO_PLANE or YAW_4DOF (WEIGHTED_SVD is stand-alone: ghicp_rigid_fit_ex)");
+    return GHICP_E_ARG;
+  }
   Ctx *c = new Ctx();
   c->cfg = *cfg;
   c->device = cfg->device;
@@ -573,6 +605,7 @@ int ghicp_set_keypoints(ghicp_ctx *ctx, const double *sxyz, int N, const double 
     if ((rc = dev_alloc(c, &c->d_t, 3 * (size_t)M))) return rc;
     if ((rc = alloc_workspaces(c))) return rc;
     c->have_bsc = c->have_fpfh = c->fd_built = false;
+    c->have_normals = false;
     c->have_prev = false;
     c->last_local_nnz = -1;
     reset_loop_state(c);
@@ -639,6 +672,28 @@ int ghicp_set_fpfh(ghicp_ctx *ctx, const float *s, const float *t) {
   CK(c, cudaStreamSynchronize(c->stream));
   c->have_fpfh = true;
   c->fd_built = false;
+  return GHICP_OK;
+}
+
+int ghicp_set_target_normals(ghicp_ctx *ctx, const double *nxyz) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !nxyz || c->M <= 0) { set_error(c, "set_target_normals: bad argument or keypoints not set"); return GHICP_E_ARG; }
+  int rc;
+  if ((rc = use_device(c))) return rc;
+  if ((rc = dev_alloc(c, &c->d_tn, 3 * (size_t)c->M))) return rc;
+  CK(c, cudaMemcpyAsync(c->d_tn, nxyz, 3 * (size_t)c->M * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  c->have_normals = true;
+  return GHICP_OK;
+}
+
+int ghicp_set_solver(ghicp_ctx *ctx, int solver) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || (solver != GHICP_SOLVER_SVD && solver != GHICP_SOLVER_POINT_TO_PLANE && solver != GHICP_SOLVER_YAW_4DOF)) {
+    set_error(c, "set_solver: solver must be SVD (reference), POINT_TO_PLANE or YAW_4DOF");
+    return GHICP_E_ARG;
+  }
+  c->cfg.solver = solver;
   return GHICP_OK;
 }
 
@@ -715,7 +770,8 @@ int ghicp_get_fd(ghicp_ctx *ctx, double *fd) {
   if ((rc = build_fd(c))) return rc;
   double *d_out = nullptr;
   if ((rc = dev_alloc(c, &d_out, (size_t)c->N * c->M))) return rc;
-  cudaError_t e = launch_get_fd(c, d_out);
+  const bool mf = c->cfg.feature_type == GHICP_FT_FPFH && c->fpfh_mf;
+  cudaError_t e = mf ? launch_get_fd_mf(c, d_out) : launch_get_fd(c, d_out);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   if (e == cudaSuccess) e = cudaMemcpy(fd, d_out, (size_t)c->N * c->M * sizeof(double), cudaMemcpyDeviceToHost);
   dev_free(&d_out);
@@ -731,8 +787,10 @@ int ghicp_probe_rowmin(ghicp_ctx *ctx, int *idx, double *cd, double *cd_mean, do
   if ((rc = build_fd(c))) return rc;
   const CostParams cp = make_cost_params(c);
   const LoopScalars ls = make_loop_scalars(c, cp);
-  CK(c, launch_rowsweep(c, 0, cp));
+  const bool mf = c->cfg.feature_type == GHICP_FT_FPFH && c->fpfh_mf;
+  CK(c, mf ? launch_rowsweep_mf(c, 0, cp) : launch_rowsweep(c, 0, cp));
   CK(c, launch_finalize_stats(c, cp, ls));
+  if (mf) CK(c, launch_rowfd_mf(c));
   if ((rc = comm_exchange(c, 1 | 2))) return rc;
   CK(c, launch_penalty(c, cp.pivot, ls));
   CK(c, cudaMemcpyAsync(c->h_iter, c->d_iter, sizeof(DevIter), cudaMemcpyDeviceToHost, c->stream));
@@ -837,6 +895,41 @@ int ghicp_rigid_fit(int device, const double *s, const double *t, int n, double 
   if (e != cudaSuccess) { set_error(nullptr, std::string("rigid_fit: ") + cudaGetErrorString(e)); return GHICP_E_CUDA; }
   std::memcpy(Rt, h.Rt, sizeof(double) * 16);
   return GHICP_OK;
+}
+
+int ghicp_rigid_fit_ex(int device, int solver, const double *s, const double *t, const double *tn, const double *w,
+                       int n, double Rt[16]) {
+  if (!s || !t || !Rt || n <= 0 || solver < GHICP_SOLVER_SVD || solver > GHICP_SOLVER_YAW_4DOF) {
+    set_error(nullptr, "rigid_fit_ex: bad argument");
+    return GHICP_E_ARG;
+  }
+  if (solver == GHICP_SOLVER_POINT_TO_PLANE && !tn) { set_error(nullptr, "rigid_fit_ex: point-to-plane needs target normals"); return GHICP_E_ARG; }
+  if (ghicp_device_count() <= 0) { set_error(nullptr, "rigid_fit_ex: no CUDA device"); return GHICP_E_NODEV; }
+  if (cudaSetDevice(device) != cudaSuccess) return GHICP_E_CUDA;
+  double *d_s = nullptr, *d_t = nullptr, *d_n = nullptr, *d_w = nullptr;
+  DevIter *d_iter = nullptr;
+  DevIter h;
+  const size_t b3 = 3 * (size_t)n * sizeof(double);
+  cudaError_t e = cudaMalloc((void **)&d_s, b3);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&d_t, b3);
+  if (e == cudaSuccess && tn) e = cudaMalloc((void **)&d_n, b3);
+  if (e == cudaSuccess && w) e = cudaMalloc((void **)&d_w, (size_t)n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&d_iter, sizeof(DevIter));
+  if (e == cudaSuccess) e = cudaMemcpy(d_s, s, b3, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_t, t, b3, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && tn) e = cudaMemcpy(d_n, tn, b3, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && w) e = cudaMemcpy(d_w, w, (size_t)n * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(d_iter, 0, sizeof(DevIter));
+  if (e == cudaSuccess) e = launch_solve_alt_explicit(0, solver, d_s, d_t, d_n, d_w, n, d_iter);
+  if (e == cudaSuccess) e = cudaMemcpy(&h, d_iter, sizeof(DevIter), cudaMemcpyDeviceToHost);
+  if (d_s) cudaFree(d_s);
+  if (d_t) cudaFree(d_t);
+  if (d_n) cudaFree(d_n);
+  if (d_w) cudaFree(d_w);
+  if (d_iter) cudaFree(d_iter);
+  if (e != cudaSuccess) { set_error(nullptr, std::string("rigid_fit_ex: ") + cudaGetErrorString(e)); return GHICP_E_CUDA; }
+  std::memcpy(Rt, h.Rt, sizeof(double) * 16);
+  return h.solve_degenerate ? GHICP_W_FEW_PAIRS : GHICP_OK;
 }
 
 int ghicp_comm_unique_id(void *id128) {

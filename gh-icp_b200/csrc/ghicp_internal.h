@@ -107,6 +107,12 @@ struct Ctx {
   // FPFH
   float *d_fs = nullptr, *d_ft = nullptr;  // raw [N][33], [M][33]
   float *d_fdf = nullptr;                  // [N][ldM] float FD
+  // matrix-free FPFH (ghicp_fpfh.cu): centred histograms, row-major [n][36] and transposed [36][n]; no N x M array
+  bool fpfh_mf = false;
+  float *d_fsc = nullptr, *d_fscT = nullptr, *d_ftc = nullptr, *d_ftcT = nullptr;
+  // opt-in solvers (ghicp_solvers.cu)
+  double *d_tn = nullptr;  // target normals [3][M]
+  bool have_normals = false;
   bool have_bsc = false, have_fpfh = false, fd_built = false;
   bool fd_tensor = false;  // FD plane built by the tcgen05 kernel
 
@@ -228,6 +234,20 @@ cudaError_t launch_penalty(Ctx *c, double pivot, const LoopScalars &ls);
 cudaError_t launch_pair_fd_km(Ctx *c);
 cudaError_t launch_colmerge(Ctx *c);
 cudaError_t launch_count_valid(Ctx *c, long long nnz);
+
+// ---- matrix-free FPFH (ghicp_fpfh.cu): same contracts as launch_rowsweep / launch_colsweep, FD recomputed on the fly
+cudaError_t launch_fpfh_prepare(Ctx *c);   // centred histograms in both layouts
+cudaError_t launch_rowsweep_mf(Ctx *c, int mode, const CostParams &cp);
+cudaError_t launch_colsweep_mf(Ctx *c, const CostParams &cp);
+cudaError_t launch_rowfd_mf(Ctx *c);       // d_row_fd[i] = FD(i, d_row_idx[i]) for this context's rows
+cudaError_t launch_get_fd_mf(Ctx *c, double *d_out);
+
+// ---- opt-in solvers (ghicp_solvers.cu) -------------------------------------------------------------
+// Overwrites iter->Rt and iter->rmse_after from the pair list in the ctx (after launch_solve produced the statistics)
+cudaError_t launch_solve_alt(Ctx *c, int solver);
+// stand-alone: explicit column-major n x 3 point lists (+ normals, + weights, either may be null)
+cudaError_t launch_solve_alt_explicit(cudaStream_t stream, int solver, const double *d_s, const double *d_t,
+                                      const double *d_tn, const double *d_w, int n, DevIter *d_iter);
 
 // ---- streaming path (ghicp_stream.cu) -----------------------------------------------------------
 cudaError_t launch_stream_prep(Ctx *c, const CostParams &cp, int for_km_gate);

@@ -90,6 +90,13 @@ class GHRegistration {
   void set_viewer(bool launch_viewer) { launch_viewer_ = launch_viewer; }
   void set_max_iterations(int n) { max_iterations_ = n; }
   void set_verbose(bool v) { verbose_ = v; }
+  // Extensions (not in the reference's class): opt-in estimators of include/ghicp_b200.h ghicp_solver_type.
+  // GHICP_SOLVER_SVD (default) is what src/ghicp_reg.cpp:857-859 always runs.
+  void set_solver(int solver) { check(ghicp_set_solver(ctx_, solver), "ghicp_set_solver"); }
+  void set_target_normals(MatrixX3d &normals) {  // unit normals of the target keypoints, for POINT_TO_PLANE
+    if ((int)normals.rows() != KP.kpt_num) throw std::runtime_error("set_target_normals: one normal per target keypoint");
+    check(ghicp_set_target_normals(ctx_, normals.data()), "ghicp_set_target_normals");
+  }
 
   // Main entrance (src/ghicp_reg.cpp:24-112)
   bool ghicp_reg(Matrix4d &Rt_final) {

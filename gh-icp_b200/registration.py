@@ -58,7 +58,7 @@ class GHRegistration:
     def __init__(self, Kp, Ef, Ft, Ct, radiusNonMax=1.0, weight_adjustment_ratio=1.1,
                  weight_adjustment_step=0.1, dof_type=6, estimated_IoU=0.5,
                  converge_tran=0.02, converge_rot=0.02, max_iter=0, device=0, km_eps=0.0, force_exact=False,
-                 comm=None):
+                 comm=None, fpfh_matrix_free=0, solver=capi.SOLVER_SVD, target_normals=None):
         self.L = capi.lib()
         cfg = capi.Config()
         cfg.feature_type, cfg.corr_type, cfg.dof = Ft, Ct, dof_type
@@ -69,6 +69,8 @@ class GHRegistration:
         cfg.converge_t, cfg.converge_r = converge_tran, converge_rot
         cfg.max_iter, cfg.device, cfg.km_eps = max_iter, device, km_eps
         cfg.force_exact = 1 if force_exact else 0
+        cfg.fpfh_matrix_free = int(fpfh_matrix_free)   # extension: 1 = never store the N x M FPFH distance plane
+        cfg.solver = int(solver)                       # extension: opt-in estimators, 0 = the reference's SVD
         self.ctx = C.c_void_p()
         capi.check(self.L.ghicp_create(C.byref(cfg), C.byref(self.ctx)))
         if comm is not None:  # (unique_id bytes, rank, world): one process per GPU, source rows sharded
@@ -78,6 +80,8 @@ class GHRegistration:
         self.N, self.M = Kp.kps_num, Kp.kpt_num
         self.Ft, self.Ct = Ft, Ct
         self.upload(Kp)
+        if target_normals is not None:
+            self.set_target_normals(target_normals)
         self.history = []
 
     def upload(self, Kp):
@@ -95,6 +99,14 @@ class GHRegistration:
         kpt = np.asfortranarray(kpt, dtype=np.float64)
         capi.check(self.L.ghicp_set_keypoints(self.ctx, capi._dp(kps), kps.shape[0], capi._dp(kpt),
                                               kpt.shape[0]), self.ctx)
+
+    def set_target_normals(self, normals):
+        """Unit normals of the target keypoints (M, 3): only read by SOLVER_POINT_TO_PLANE."""
+        n = np.asfortranarray(normals, dtype=np.float64)
+        capi.check(self.L.ghicp_set_target_normals(self.ctx, capi._dp(n)), self.ctx)
+
+    def set_solver(self, solver):
+        capi.check(self.L.ghicp_set_solver(self.ctx, int(solver)), self.ctx)
 
     def close(self):
         if getattr(self, "ctx", None):

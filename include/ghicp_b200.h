@@ -26,11 +26,26 @@
 extern "C" {
 #endif
 
-#define GHICP_ABI_VERSION 1
+#define GHICP_ABI_VERSION 2
 
 /* enum values follow include/utility.h:51-64 */
 enum ghicp_feature_type { GHICP_FT_BSC = 0, GHICP_FT_ROPS = 1, GHICP_FT_FPFH = 2, GHICP_FT_NONE = 3 };
 enum ghicp_corr_type { GHICP_CT_NN = 0, GHICP_CT_NNR = 1, GHICP_CT_KM = 2 };
+/* Transform estimation.  The reference loop always runs GHICP_SOLVER_SVD (unweighted point-to-point, PCL
+ * TransformationEstimationSVD, src/ghicp_reg.cpp:857-859).  The others are OPT-IN extensions named by
+ * BASELINE.json's north_star / configs 3 and 5; the reference holds them only as code the
+ * loop never calls, so their parity is pinned by restatement + analytic tests only:
+ *   WEIGHTED_SVD    per-pair weights w_k >= 0 in the centroids and the cross-covariance (w = 1 reproduces SVD)
+ *   POINT_TO_PLANE  linearised point-to-plane least squares, rows [s x n, n], rhs n.(t - s), 6x6 normal equations,
+ *                   R = Rz(gamma) Ry(beta) Rx(alpha)  (PCL TransformationEstimationPointToPlaneLLS, the estimator
+ *                   behind IterativeClosestPointWithNormals in src/common_reg.cpp:123-199)
+ *   YAW_4DOF        Gauss-Newton on (yaw, tx, ty, tz), CRegistration::LLS_4DOF (src/common_reg.cpp:623-775) */
+enum ghicp_solver_type {
+  GHICP_SOLVER_SVD = 0,
+  GHICP_SOLVER_WEIGHTED_SVD = 1,
+  GHICP_SOLVER_POINT_TO_PLANE = 2,
+  GHICP_SOLVER_YAW_4DOF = 3
+};
 
 enum ghicp_status {
   GHICP_OK = 0,
@@ -61,7 +76,13 @@ typedef struct ghicp_config {
   double km_eps;        /* 0 → Energyfunction::KM_eps = 0.01 (ghicp_reg.h:38) */
   int verbose;          /* 0 = silent (the reference prints every iteration; we do not by default) */
   int force_exact;      /* 1 = all-double cost kernels only (no FP32 filter); results are identical, slower */
-  int reserved[6];
+  int fpfh_matrix_free; /* FPFH only: 0 = auto (stored float FD plane while it fits in 40 % of the free device
+                           memory, matrix-free beyond: config 3's 200k x 200k plane would be 160 GB), 1 = always
+                           recompute FD on the fly (no N x M array at all), -1 = always store the plane.  Results are
+                           bit-identical either way. */
+  int solver;           /* ghicp_solver_type used by ghicp_iterate; 0 = the reference's SVD.  POINT_TO_PLANE needs
+                           ghicp_set_target_normals.  WEIGHTED_SVD is stand-alone only (ghicp_rigid_fit_ex). */
+  int reserved[4];
 } ghicp_config;
 
 /* Everything one loop body of GHRegistration::ghicp_reg (src/ghicp_reg.cpp:49-103) reports. */
@@ -107,6 +128,12 @@ int ghicp_set_bsc(ghicp_ctx *ctx, const uint8_t *s_bits, int V, const uint8_t *t
 /* Keypoints::setFPFHfeature (include/ghicp_reg.h:68-72). s [N][33], t [M][33]. */
 int ghicp_set_fpfh(ghicp_ctx *ctx, const float *s, const float *t);
 
+/* Unit normals of the target keypoints, column-major M x 3 (only read by GHICP_SOLVER_POINT_TO_PLANE; the
+ * reference estimates them by k-NN PCA inside PCL, src/common_reg.cpp:149-150 — here the caller supplies them). */
+int ghicp_set_target_normals(ghicp_ctx *ctx, const double *nxyz);
+/* Change the in-loop estimator of an existing context (same values / rules as ghicp_config.solver). */
+int ghicp_set_solver(ghicp_ctx *ctx, int solver);
+
 /* calFD_BSC / calFD_FPFH (src/ghicp_reg.cpp:143-214): one-time feature-distance build. */
 int ghicp_build_fd(ghicp_ctx *ctx);
 
@@ -141,6 +168,12 @@ int ghicp_km_solve(int device, const double *W, int n, int sp, int tp, double ep
 /* pcl TransformationEstimationSVD::estimateRigidTransformation as called at src/ghicp_reg.cpp:857-866.
  * s, t column-major n x 3 (Spoint / Tpoint). */
 int ghicp_rigid_fit(int device, const double *s, const double *t, int n, double Rt[16]);
+/* Opt-in estimators (see ghicp_solver_type).  s, t column-major n x 3; tn = target normals, column-major n x 3
+ * (POINT_TO_PLANE, else may be NULL); w = n weights or NULL (all ones).  solver = SVD with w == NULL is
+ * ghicp_rigid_fit.  YAW_4DOF starts from yaw0 = 0 like a leveled scan pair (src/common_reg.cpp:646 takes the
+ * initial guess from the caller). */
+int ghicp_rigid_fit_ex(int device, int solver, const double *s, const double *t, const double *tn, const double *w,
+                       int n, double Rt[16]);
 
 /* ---- multi-GPU (one process per GPU; source rows sharded, target replicated) ---------------- */
 /* 128-byte NCCL unique id; rank 0 creates it, the host runtime broadcasts it (torch.distributed,

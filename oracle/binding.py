@@ -81,6 +81,9 @@ def lib(omp=False):
                                 C.POINTER(C.c_int), C.POINTER(C.c_double)]
     L.orc_rigid_fit.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_int,
                                 C.POINTER(C.c_double)]
+    L.orc_rigid_fit_ex.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                   C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double)]
+    L.orc_set_solver.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
     L.orc_set_km_backend.argtypes = [C.c_void_p]
     _libs[key] = L
     return L
@@ -150,6 +153,18 @@ def rigid_fit(S, T, solve_mode=0):
     Rt = np.zeros(16, np.float64)
     lib().orc_rigid_fit(_dp(S), _dp(T), S.shape[0], solve_mode, _dp(Rt))
     return Rt.reshape(4, 4).T.copy()
+
+
+def rigid_fit_ex(S, T, solver, normals=None, weights=None):
+    """Opt-in estimators (extensions, parity unpinned): solver 0/1 (weighted) point-to-point, 2 point-to-plane
+    LLS, 3 yaw-only LLS_4DOF.  Returns (4x4, rc) with rc != 0 for degenerate input."""
+    S = np.asfortranarray(S, dtype=np.float64); T = np.asfortranarray(T, dtype=np.float64)
+    Nn = None if normals is None else np.asfortranarray(normals, dtype=np.float64)
+    W = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+    Rt = np.zeros(16, np.float64)
+    rc = lib().orc_rigid_fit_ex(solver, _dp(S), _dp(T), None if Nn is None else _dp(Nn),
+                                None if W is None else _dp(W), S.shape[0], _dp(Rt))
+    return Rt.reshape(4, 4).T.copy(), rc
 
 
 class Oracle:
@@ -223,6 +238,12 @@ class Oracle:
     def cd(self):
         p = self.L.orc_cd(self.ctx)
         return np.ctypeslib.as_array(p, shape=(self.N, self.M)).copy()
+
+    def set_solver(self, solver, target_normals=None):
+        n = None if target_normals is None else np.asfortranarray(target_normals, dtype=np.float64)
+        rc = self.L.orc_set_solver(self.ctx, solver, None if n is None else _dp(n))
+        if rc:
+            raise ValueError("orc_set_solver: bad solver / missing normals")
 
     def set_state(self, iteration, rms, fdm, fdstd, para1, para2):
         self.L.orc_set_state(self.ctx, iteration, rms, fdm, fdstd, para1, para2)

@@ -213,6 +213,140 @@ static int rigid_fit_impl(const double *s, const double *t, int n, int solve_mod
 }
 
 // ---------------------------------------------------------------------------------------------
+// OPT-IN estimators (extensions: the reference loop never calls them).
+//   1 weighted point-to-point: weighted means / cross-covariance + the float32 Umeyama core above
+//   2 point-to-plane LLS     : PCL TransformationEstimationPointToPlaneLLS (estimator of
+//                              IterativeClosestPointWithNormals, src/common_reg.cpp:123-199); PCL is not in
+//                              /root/reference: published algorithm restated, PARITY UNPINNED
+//   3 yaw-only 4-DoF         : CRegistration::LLS_4DOF, src/common_reg.cpp:623-775, restated row by row:
+//                              the 3n x 4 system is assembled EXPLICITLY every Gauss-Newton step like :661-685
+//                              and solved through the normal equations (:689) — on purpose not the moment
+//                              form the GPU kernel uses, so the two derivations check each other.
+// ---------------------------------------------------------------------------------------------
+static bool gauss_solve(int n, std::vector<double> A /* n x n row-major */, std::vector<double> b, double *x) {
+  for (int c = 0; c < n; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < n; ++r) if (std::fabs(A[(size_t)r * n + c]) > std::fabs(A[(size_t)piv * n + c])) piv = r;
+    if (!(std::fabs(A[(size_t)piv * n + c]) > 0.0)) return false;
+    if (piv != c) { for (int k = 0; k < n; ++k) std::swap(A[(size_t)piv * n + k], A[(size_t)c * n + k]); std::swap(b[piv], b[c]); }
+    for (int r = c + 1; r < n; ++r) {
+      const double f = A[(size_t)r * n + c] / A[(size_t)c * n + c];
+      for (int k = c; k < n; ++k) A[(size_t)r * n + k] -= f * A[(size_t)c * n + k];
+      b[r] -= f * b[c];
+    }
+  }
+  for (int r = n - 1; r >= 0; --r) {
+    double v = b[r];
+    for (int k = r + 1; k < n; ++k) v -= A[(size_t)r * n + k] * x[k];
+    x[r] = v / A[(size_t)r * n + r];
+  }
+  return true;
+}
+
+static int rigid_fit_ex_impl(int solver, const double *s, const double *t, const double *tn, const double *w, int n,
+                             double Rt[16]) {
+  for (int i = 0; i < 16; ++i) Rt[i] = (i % 5 == 0) ? 1.0 : 0.0;
+  const double *sx = s, *sy = s + n, *sz = s + 2 * (size_t)n;
+  const double *tx = t, *ty = t + n, *tz = t + 2 * (size_t)n;
+  auto W = [&](int i) { return w ? w[i] : 1.0; };
+  if (solver == 0 || solver == 1) {
+    if (n < 3) return 1;
+    double sw = 0, ms[3] = {0, 0, 0}, md[3] = {0, 0, 0};
+    for (int i = 0; i < n; ++i) {
+      sw += W(i);
+      ms[0] += W(i) * sx[i]; ms[1] += W(i) * sy[i]; ms[2] += W(i) * sz[i];
+      md[0] += W(i) * tx[i]; md[1] += W(i) * ty[i]; md[2] += W(i) * tz[i];
+    }
+    if (!(sw > 0.0)) return 1;
+    double mus[3], mud[3];
+    for (int k = 0; k < 3; ++k) { mus[k] = ms[k] / sw; mud[k] = md[k] / sw; }
+    double acc[9] = {0};
+    for (int i = 0; i < n; ++i) {
+      const double ds[3] = {sx[i] - mus[0], sy[i] - mus[1], sz[i] - mus[2]};
+      const double dd[3] = {tx[i] - mud[0], ty[i] - mud[1], tz[i] - mud[2]};
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) acc[r * 3 + c] += W(i) * (dd[r] * ds[c]);
+    }
+    float mu_s[3], mu_d[3], sigma[9];
+    for (int k = 0; k < 3; ++k) { mu_s[k] = (float)mus[k]; mu_d[k] = (float)mud[k]; }
+    for (int k = 0; k < 9; ++k) sigma[k] = (float)(acc[k] / sw);
+    umeyama_from_moments_f32(mu_s, mu_d, sigma, Rt);
+    return 0;
+  }
+  if (solver == 2) {
+    if (n < 6 || !tn) return 1;
+    const double *nx = tn, *ny = tn + n, *nz = tn + 2 * (size_t)n;
+    std::vector<double> ATA(36, 0.0), ATb(6, 0.0);
+    for (int i = 0; i < n; ++i) {
+      const double row[6] = {nz[i] * sy[i] - ny[i] * sz[i], nx[i] * sz[i] - nz[i] * sx[i], ny[i] * sx[i] - nx[i] * sy[i],
+                             nx[i], ny[i], nz[i]};
+      const double d = nx[i] * tx[i] + ny[i] * ty[i] + nz[i] * tz[i] - nx[i] * sx[i] - ny[i] * sy[i] - nz[i] * sz[i];
+      for (int r = 0; r < 6; ++r) {
+        for (int c = 0; c < 6; ++c) ATA[r * 6 + c] += W(i) * (row[r] * row[c]);
+        ATb[r] += W(i) * (row[r] * d);
+      }
+    }
+    double x[6];
+    double tr = 0; for (int k = 0; k < 6; ++k) tr += ATA[k * 7];
+    // rank check through the smallest pivot of an LDL^T-free elimination: compare against the trace scale
+    if (!gauss_solve(6, ATA, ATb, x)) return 1;
+    for (int k = 0; k < 6; ++k) if (!std::isfinite(x[k])) return 1;
+    (void)tr;
+    const double al = x[0], be = x[1], ga = x[2];
+    // PCL constructTransformationMatrix(alpha, beta, gamma, tx, ty, tz): R = Rz(gamma) Ry(beta) Rx(alpha)
+    double R[3][3];
+    R[0][0] = std::cos(ga) * std::cos(be);
+    R[0][1] = -std::sin(ga) * std::cos(al) + std::cos(ga) * std::sin(be) * std::sin(al);
+    R[0][2] = std::sin(ga) * std::sin(al) + std::cos(ga) * std::sin(be) * std::cos(al);
+    R[1][0] = std::sin(ga) * std::cos(be);
+    R[1][1] = std::cos(ga) * std::cos(al) + std::sin(ga) * std::sin(be) * std::sin(al);
+    R[1][2] = -std::cos(ga) * std::sin(al) + std::sin(ga) * std::sin(be) * std::cos(al);
+    R[2][0] = -std::sin(be);
+    R[2][1] = std::cos(be) * std::sin(al);
+    R[2][2] = std::cos(be) * std::cos(al);
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) Rt[j * 4 + i] = R[i][j];
+      Rt[12 + i] = x[3 + i];
+    }
+    return 0;
+  }
+  if (solver == 3) {
+    if (n < 2) return 1;  // src/common_reg.cpp:648 "Not enough control point number"
+    double theta0 = 0.0, dtheta = 9999, eps = 1e-9;  // :643-646 (initial guess 0 deg)
+    double sol[4] = {0, 0, 0, 0};
+    int iter_num = 0;
+    while (std::abs(dtheta) > eps && iter_num < 200) {  // :654 (the 200 cap is ours)
+      std::vector<double> ATA(16, 0.0), ATb(4, 0.0);
+      for (int j = 0; j < n; ++j) {
+        const double A0[4] = {-sx[j] * std::sin(theta0) - sy[j] * std::cos(theta0), 1, 0, 0};   // :663-666
+        const double A1[4] = {sx[j] * std::cos(theta0) - sy[j] * std::sin(theta0), 0, 1, 0};    // :668-671
+        const double A2[4] = {0, 0, 0, 1};                                                      // :673-676
+        const double b0 = tx[j] - sx[j] * std::cos(theta0) + sy[j] * std::sin(theta0);          // :679
+        const double b1 = ty[j] - sx[j] * std::sin(theta0) - sy[j] * std::cos(theta0);          // :680
+        const double b2 = tz[j] - sz[j];                                                        // :681
+        const double *rows[3] = {A0, A1, A2};
+        const double bb[3] = {b0, b1, b2};
+        for (int q = 0; q < 3; ++q)
+          for (int r = 0; r < 4; ++r) {
+            for (int c = 0; c < 4; ++c) ATA[r * 4 + c] += W(j) * (rows[q][r] * rows[q][c]);
+            ATb[r] += W(j) * (rows[q][r] * bb[q]);
+          }
+      }
+      if (!gauss_solve(4, ATA, ATb, sol)) return 1;   // x = (A^T A)^-1 A^T b, :689
+      dtheta = sol[0];
+      theta0 += dtheta;
+      ++iter_num;
+    }
+    const double theta = theta0;
+    Rt[0] = std::cos(theta); Rt[4] = -std::sin(theta); Rt[12] = sol[1];   // :719-737
+    Rt[1] = std::sin(theta); Rt[5] = std::cos(theta);  Rt[13] = sol[2];
+    Rt[10] = 1.0;                                       Rt[14] = sol[3];
+    return 0;
+  }
+  return -1;
+}
+
+// ---------------------------------------------------------------------------------------------
 // KM restatement (src/km.cpp:13-126).  Same traversal order, same eps-tight test, slack reset once
 // per x, recursive DFS (run orc from a thread with a large stack for big n).
 // ---------------------------------------------------------------------------------------------
@@ -334,6 +468,9 @@ struct orc_ctx {
   std::vector<int> SP, TP;
   std::vector<double> Spoint, Tpoint;     // column-major cor x 3
   double last_cd_mean = 0, last_cd_std = 0, last_energy = 0;
+  // opt-in estimators (extension; 0 = the reference's SVD)
+  int solver = 0;
+  std::vector<double> tn;                 // target normals, column-major M x 3
 };
 
 extern "C" {
@@ -464,6 +601,19 @@ int orc_km_output(const double *W, int n, int sp, int tp, double penalty, const 
   if (nSPout) *nSPout = (int)spo.size();
   if (nTPout) *nTPout = (int)tpo.size();
   return cor;
+}
+
+int orc_rigid_fit_ex(int solver, const double *s, const double *t, const double *tn, const double *w, int n,
+                     double Rt[16]) {
+  return rigid_fit_ex_impl(solver, s, t, tn, w, n, Rt);
+}
+
+int orc_set_solver(orc_ctx *c, int solver, const double *target_normals) {
+  if (solver < 0 || solver > 3 || solver == 1) return -1;
+  if (solver == 2 && !target_normals) return -1;
+  c->solver = solver;
+  if (target_normals) c->tn.assign(target_normals, target_normals + 3 * (size_t)c->M);
+  return 0;
 }
 
 int orc_rigid_fit(const double *s, const double *t, int n, int solve_mode, double Rt[16]) {
@@ -650,7 +800,18 @@ static void transformestimation(orc_ctx *c, double Rt[16], orc_iter_stats *st) {
   int cor_number = (int)c->SP.size();
   if (cor_number < c->min_cor) c->converge = 1;
   c->IoU = 1.0 * cor_number / (N + M - cor_number);
-  rigid_fit_impl(c->Spoint.data(), c->Tpoint.data(), cor_number, c->cfg.solve_mode, Rt);
+  if (c->solver == 0) {
+    rigid_fit_impl(c->Spoint.data(), c->Tpoint.data(), cor_number, c->cfg.solve_mode, Rt);
+  } else {
+    std::vector<double> npair;
+    if (c->solver == 2) {
+      npair.assign(3 * (size_t)cor_number, 0.0);
+      for (int i = 0; i < cor_number; ++i)
+        for (int k = 0; k < 3; ++k) npair[(size_t)k * cor_number + i] = c->tn[(size_t)k * M + c->TP[i]];
+    }
+    rigid_fit_ex_impl(c->solver, c->Spoint.data(), c->Tpoint.data(), npair.empty() ? nullptr : npair.data(), nullptr,
+                      cor_number, Rt);
+  }
   double R[3][3], t[3];
   for (int i = 0; i < 3; ++i) {
     for (int j = 0; j < 3; ++j) R[i][j] = Rt[j * 4 + i];

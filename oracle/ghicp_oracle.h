@@ -120,6 +120,14 @@ int orc_km_output(const double *W, int n, int sp, int tp, double penalty, const 
    s, t: column-major n x 3 doubles (Spoint/Tpoint); Rt column-major 4x4 double (cast of float). */
 int orc_rigid_fit(const double *s, const double *t, int n, int solve_mode, double Rt[16]);
 
+/* OPT-IN estimators (extensions, PARITY UNPINNED — see the block comment in ghicp_oracle.cpp):
+   solver 0/1 = (weighted) point-to-point, 2 = point-to-plane LLS (PCL), 3 = yaw-only LLS_4DOF
+   (src/common_reg.cpp:623-775).  tn = target normals (column-major n x 3), w = weights; either may be NULL. */
+int orc_rigid_fit_ex(int solver, const double *s, const double *t, const double *tn, const double *w, int n,
+                     double Rt[16]);
+/* in-loop estimator of a context (0, 2 or 3); target_normals column-major M x 3 (solver 2) */
+int orc_set_solver(orc_ctx *c, int solver, const double *target_normals);
+
 typedef int (*orc_km_backend_fn)(const double *W, int n, double eps, int *match);
 void orc_set_km_backend(orc_km_backend_fn fn);
 

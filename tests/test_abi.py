@@ -24,11 +24,11 @@ def test_header_symbols_all_exported(g):
 
 
 def test_abi_version(g):
-    assert g.lib().ghicp_abi_version() == 1
+    assert g.lib().ghicp_abi_version() == 2
 
 
 def test_struct_sizes_match_header(g):
-    # ghicp_config: 3 int + 7 float + 2 int + double + 2 int + 6 int (with natural alignment)
+    # ghicp_config: 3 int + 7 float + 2 int + double + 2 int + fpfh_matrix_free + solver + 4 reserved (natural alignment)
     assert C.sizeof(g.Config) == 88
     assert C.sizeof(g.IterStats) % 8 == 0
 
