@@ -277,8 +277,8 @@ __global__ void k_fd_to_double_mf(const float *__restrict__ sc, const float *__r
 }  // namespace
 
 cudaError_t launch_fpfh_prepare(Ctx *c) {
-  k_fpfh_center2<<<(c->N + 127) / 128, 128, 0, c->stream>>>(c->d_fs, c->d_fsc, c->d_fscT, c->N);
-  k_fpfh_center2<<<(c->M + 127) / 128, 128, 0, c->stream>>>(c->d_ft, c->d_ftc, c->d_ftcT, c->M);
+  GHICP_LAUNCH(k_fpfh_center2, (c->N + 127) / 128, 128, 0, c->stream, c->d_fs, c->d_fsc, c->d_fscT, c->N);
+  GHICP_LAUNCH(k_fpfh_center2, (c->M + 127) / 128, 128, 0, c->stream, c->d_ft, c->d_ftc, c->d_ftcT, c->M);
   c->launches += 2;
   return cudaGetLastError();
 }
@@ -294,9 +294,9 @@ cudaError_t launch_rowsweep_mf(Ctx *c, int mode, const CostParams &cp) {
   a.iter = c->d_iter; a.cnt = c->d_cnt; a.rowptr = c->d_rowptr; a.cursor = c->d_cursor;
   a.csr_col = c->d_csr_col; a.csr_gain = c->d_csr_gain; a.csr_fd = c->d_csr_fd;
   const dim3 grid((c->nloc + TR - 1) / TR, c->n_chunks);
-  if (mode == 0) k_rowsweep_mf<0><<<grid, MF_THREADS, 0, c->stream>>>(a);
-  else if (mode == 1) k_rowsweep_mf<1><<<grid, MF_THREADS, 0, c->stream>>>(a);
-  else k_rowsweep_mf<2><<<grid, MF_THREADS, 0, c->stream>>>(a);
+  if (mode == 0) GHICP_LAUNCH(k_rowsweep_mf<0>, grid, MF_THREADS, 0, c->stream, a);
+  else if (mode == 1) GHICP_LAUNCH(k_rowsweep_mf<1>, grid, MF_THREADS, 0, c->stream, a);
+  else GHICP_LAUNCH(k_rowsweep_mf<2>, grid, MF_THREADS, 0, c->stream, a);
   c->launches++;
   return cudaGetLastError();
 }
@@ -306,21 +306,21 @@ cudaError_t launch_colsweep_mf(Ctx *c, const CostParams &cp) {
   a.s = c->d_s; a.t = c->d_t; a.scT = c->d_fscT; a.tc = c->d_ftc;
   a.N = c->N; a.M = c->M; a.row0 = c->r0; a.nloc = c->nloc; a.cp = cp;
   a.col_cd = c->d_col_cd; a.col_idx = c->d_col_idx;
-  k_colsweep_mf<<<(c->M + MF_CT - 1) / MF_CT, MF_THREADS, 0, c->stream>>>(a);
+  GHICP_LAUNCH(k_colsweep_mf, (c->M + MF_CT - 1) / MF_CT, MF_THREADS, 0, c->stream, a);
   c->launches++;
   return cudaGetLastError();
 }
 
 cudaError_t launch_rowfd_mf(Ctx *c) {
   if (c->nloc <= 0) return cudaSuccess;
-  k_rowfd_mf<<<(c->nloc + 255) / 256, 256, 0, c->stream>>>(c->d_fsc, c->d_ftc, c->d_row_idx, c->r0, c->nloc, c->d_row_fd);
+  GHICP_LAUNCH(k_rowfd_mf, (c->nloc + 255) / 256, 256, 0, c->stream, c->d_fsc, c->d_ftc, c->d_row_idx, c->r0, c->nloc, c->d_row_fd);
   c->launches++;
   return cudaGetLastError();
 }
 
 cudaError_t launch_get_fd_mf(Ctx *c, double *d_out) {
   const size_t total = (size_t)c->N * c->M;
-  k_fd_to_double_mf<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(c->d_fsc, c->d_ftc, c->N, c->M, c->r0, c->nloc, d_out);
+  GHICP_LAUNCH(k_fd_to_double_mf, (unsigned)((total + 255) / 256), 256, 0, c->stream, c->d_fsc, c->d_ftc, c->N, c->M, c->r0, c->nloc, d_out);
   c->launches++;
   return cudaGetLastError();
 }

@@ -8,6 +8,15 @@
 
 #include "../../include/ghicp_b200.h"
 
+// Kernel launch: the <<< >>> syntax under nvcc.  The kernel-LOGIC harness (tests/harness, g++ -DGHICP_EMU_HOST with the
+// host emulation shim of tests/harness/cuda_emu) compiles a few .cu files as plain C++ and runs every CUDA thread as a
+// fiber on the CPU; those files launch through this macro.  The product is always built by nvcc.
+#if defined(GHICP_EMU_HOST)
+#define GHICP_LAUNCH(kernel, grid, block, smem, stream, ...) emu::launch((grid), (block), [&] { kernel(__VA_ARGS__); })
+#else
+#define GHICP_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
 namespace ghicp_b200 {
 
 // Feature-distance plane layout: PANEL-MAJOR.  The N x M plane is stored as ceil(M/256) column panels, each

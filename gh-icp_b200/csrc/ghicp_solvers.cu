@@ -186,7 +186,7 @@ cudaError_t launch_solve_alt(Ctx *c, int solver) {
   AltArgs a{};
   a.s = c->d_s; a.t = c->d_t; a.tn = c->d_tn; a.sp = c->d_sp; a.tp = c->d_tp; a.N = c->N; a.M = c->M;
   a.solver = solver; a.iter = c->d_iter;
-  k_solve_alt<<<1, ALT_THREADS, 0, c->stream>>>(a);
+  GHICP_LAUNCH(k_solve_alt, 1, ALT_THREADS, 0, c->stream, a);
   c->launches++;
   return cudaGetLastError();
 }
@@ -195,7 +195,7 @@ cudaError_t launch_solve_alt_explicit(cudaStream_t stream, int solver, const dou
                                       const double *d_tn, const double *d_w, int n, DevIter *d_iter) {
   AltArgs a{};
   a.ps = d_s; a.pt = d_t; a.pn = d_tn; a.pw = d_w; a.n_explicit = n; a.solver = solver; a.iter = d_iter;
-  k_solve_alt<<<1, ALT_THREADS, 0, stream>>>(a);
+  GHICP_LAUNCH(k_solve_alt, 1, ALT_THREADS, 0, stream, a);
   return cudaGetLastError();
 }
 

@@ -1,0 +1,53 @@
+// cuda_runtime.h — HOST EMULATION SHIM (tests/harness/cuda_emu), found before the real CUDA header only by the
+// kernel-logic harness builds (g++ -Itests/harness/cuda_emu -DGHICP_EMU_HOST).  It lets a .cu translation unit of
+// the product compile as plain C++ and run its kernels on the CPU: every CUDA thread of a block is a ucontext fiber,
+// __syncthreads() and the warp shuffles are rendezvous points between fibers (emu.h).  What this checks is the
+// kernels' LOGIC (indexing, reductions, tie-breaks, arithmetic order) against the oracle without a GPU; code
+// generation, memory ordering and performance are only checked by the -m gpu tests.  Test infrastructure only.
+#pragma once
+#include <math.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "emu.h"
+
+#define __host__
+#define __device__
+#define __global__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
+
+typedef int cudaError_t;
+enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2, cudaErrorNotSupported = 801 };
+typedef void *cudaStream_t;
+typedef void *cudaEvent_t;
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
+
+struct float4 { float x, y, z, w; };
+struct uint2 { unsigned x, y; };
+struct uint4 { unsigned x, y, z, w; };
+
+#define threadIdx (emu::cur()->tidx)
+#define blockIdx (emu::g_block)
+#define blockDim (emu::g_bdim)
+#define gridDim (emu::g_gdim)
+
+inline void __syncthreads() { emu::syncthreads(); }
+template <typename T>
+inline T __shfl_xor_sync(unsigned, T v, int lane_mask) { return emu::shfl<T>(v, (emu::cur()->tidx.x & 31) ^ lane_mask); }
+template <typename T>
+inline T __shfl_up_sync(unsigned, T v, int delta) {
+  const int lane = emu::cur()->tidx.x & 31;
+  return emu::shfl<T>(v, lane >= delta ? lane - delta : lane);
+}
+template <typename T>
+inline T atomicAdd(T *p, T v) { T old = *p; *p = old + v; return old; }   // one OS thread: fibers never preempt
+
+inline int min(int a, int b) { return a < b ? a : b; }
+inline int max(int a, int b) { return a > b ? a : b; }
+inline long long min(long long a, long long b) { return a < b ? a : b; }
+inline long long max(long long a, long long b) { return a > b ? a : b; }

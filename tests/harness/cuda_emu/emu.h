@@ -1,0 +1,124 @@
+// emu.h — a very small CUDA execution model on the CPU (test infrastructure, see cuda_runtime.h next to it).
+// One thread block at a time; each CUDA thread is a ucontext fiber scheduled round-robin on ONE OS thread, so plain
+// memory accesses need no synchronisation.  Rendezvous points:
+//   syncthreads()  all live fibers of the block
+//   shfl<T>()      the 32 fibers of a warp (full-warp, convergent shuffles only — what the product's kernels use)
+// A fiber that returns from the kernel leaves every later rendezvous (like an exited CUDA thread).
+#pragma once
+#include <ucontext.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <vector>
+
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+
+namespace emu {
+
+struct Fiber {
+  ucontext_t ctx;
+  dim3 tidx;
+  bool done = false;
+  char *stack = nullptr;
+};
+struct Warp {
+  unsigned long long in[32], out[32];
+  int count = 0, gen = 0, live = 0;
+};
+
+inline dim3 g_block, g_bdim, g_gdim;
+inline std::vector<Fiber> g_fibers;
+inline std::vector<Warp> g_warps;
+inline int g_cur_index = 0, g_live = 0, g_bar_count = 0, g_bar_gen = 0;
+inline ucontext_t g_sched;
+inline const std::function<void()> *g_body = nullptr;
+constexpr size_t STACK = 256 * 1024;
+
+inline Fiber *cur() { return &g_fibers[g_cur_index]; }
+inline void yield() { swapcontext(&cur()->ctx, &g_sched); }
+
+inline void syncthreads() {
+  const int my = g_bar_gen;
+  if (++g_bar_count == g_live) { g_bar_count = 0; ++g_bar_gen; return; }
+  while (g_bar_gen == my) yield();
+}
+
+template <typename T>
+inline T shfl(T v, int src_lane) {
+  static_assert(sizeof(T) <= 8, "shfl: at most 64-bit values");
+  Warp &w = g_warps[cur()->tidx.x >> 5];
+  const int lane = cur()->tidx.x & 31;
+  unsigned long long raw = 0;
+  memcpy(&raw, &v, sizeof(T));
+  w.in[lane] = raw;
+  const int my = w.gen;
+  if (++w.count == w.live) {
+    memcpy(w.out, w.in, sizeof(w.out));
+    w.count = 0;
+    ++w.gen;
+  } else {
+    while (w.gen == my) yield();
+  }
+  T r;
+  memcpy(&r, &w.out[src_lane & 31], sizeof(T));
+  return r;
+}
+
+inline void fiber_entry() {
+  (*g_body)();
+  Fiber *f = cur();
+  f->done = true;
+  --g_live;
+  Warp &w = g_warps[f->tidx.x >> 5];
+  --w.live;
+  // an exiting thread may complete a rendezvous the others are waiting in
+  if (g_live > 0 && g_bar_count == g_live) { g_bar_count = 0; ++g_bar_gen; }
+  if (w.live > 0 && w.count == w.live) { memcpy(w.out, w.in, sizeof(w.out)); w.count = 0; ++w.gen; }
+  swapcontext(&f->ctx, &g_sched);
+}
+
+// run `body` (a call of the kernel function) for every thread of every block of the grid (1-D blocks)
+inline void launch(dim3 grid, dim3 block, const std::function<void()> &body) {
+  const int nt = (int)block.x;
+  if (block.y != 1 || block.z != 1) { fprintf(stderr, "emu: 1-D blocks only\n"); abort(); }
+  if ((int)g_fibers.size() < nt) {
+    const size_t old = g_fibers.size();
+    g_fibers.resize(nt);
+    for (size_t i = old; i < g_fibers.size(); ++i) g_fibers[i].stack = (char *)malloc(STACK);
+  }
+  g_bdim = block; g_gdim = grid; g_body = &body;
+  for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+      for (unsigned bx = 0; bx < grid.x; ++bx) {
+        g_block = dim3(bx, by, bz);
+        g_warps.assign((nt + 31) / 32, Warp());
+        g_live = nt; g_bar_count = 0; g_bar_gen = 0;
+        for (int t = 0; t < nt; ++t) {
+          Fiber &f = g_fibers[t];
+          f.done = false;
+          f.tidx = dim3(t, 0, 0);
+          g_warps[t >> 5].live++;
+          getcontext(&f.ctx);
+          f.ctx.uc_stack.ss_sp = f.stack;
+          f.ctx.uc_stack.ss_size = STACK;
+          f.ctx.uc_link = nullptr;
+          makecontext(&f.ctx, fiber_entry, 0);
+        }
+        long spins = 0;
+        while (g_live > 0) {
+          for (int t = 0; t < nt; ++t) {
+            if (g_fibers[t].done) continue;
+            g_cur_index = t;
+            swapcontext(&g_sched, &g_fibers[t].ctx);
+          }
+          if (++spins > 100000000L) { fprintf(stderr, "emu: deadlock (divergent barrier / shuffle?)\n"); abort(); }
+        }
+      }
+}
+
+}  // namespace emu

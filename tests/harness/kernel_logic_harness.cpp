@@ -1,0 +1,147 @@
+// kernel_logic_harness.cpp — runs the product's matrix-free FPFH and opt-in estimator KERNELS on the CPU through the
+// host emulation shim (tests/harness/cuda_emu): the .cu files are compiled as plain C++, every CUDA thread is a fiber.
+// Built and driven by tests/test_kernel_logic_host.py; checks kernel logic against the oracle without a GPU.
+// Test infrastructure only — the product is always the nvcc build.
+#define GHICP_EMU_HOST 1
+#include "../../gh-icp_b200/csrc/ghicp_fpfh.cu"
+#include "../../gh-icp_b200/csrc/ghicp_solvers.cu"
+
+#include <vector>
+
+using namespace ghicp_b200;
+
+namespace {
+struct Host {
+  Ctx c;
+  std::vector<float> fsc, fscT, ftc, ftcT, row_fd, csr_fd;
+  std::vector<double> part_cd, part_stats, col_cd, csr_gain;
+  std::vector<int> part_idx, row_idx, col_idx, cnt, cursor, csr_col;
+  std::vector<long long> rowptr;
+  DevIter iter;
+};
+void setup(Host &h, const double *S, const double *T, const float *fs, const float *ft, int N, int M, int n_chunks,
+           int row0, int nloc) {
+  Ctx &c = h.c;
+  c.N = N; c.M = M; c.n_chunks = n_chunks; c.r0 = row0; c.nloc = nloc;
+  c.d_s = const_cast<double *>(S); c.d_t = const_cast<double *>(T);
+  c.d_fs = const_cast<float *>(fs); c.d_ft = const_cast<float *>(ft);
+  h.fsc.assign((size_t)N * 36, 0.f); h.fscT.assign((size_t)N * 36, 0.f);
+  h.ftc.assign((size_t)M * 36, 0.f); h.ftcT.assign((size_t)M * 36, 0.f);
+  c.d_fsc = h.fsc.data(); c.d_fscT = h.fscT.data(); c.d_ftc = h.ftc.data(); c.d_ftcT = h.ftcT.data();
+  const size_t L = (size_t)N * n_chunks;
+  h.part_cd.assign(L, -1.0); h.part_idx.assign(L, -1);
+  h.part_stats.assign((size_t)2 * ((N + 7) / 8) * n_chunks, 0.0);
+  h.row_idx.assign(N, 0); h.row_fd.assign(N, 0.f); h.col_cd.assign(M, 0.0); h.col_idx.assign(M, 0);
+  h.cnt.assign(L + 2, 0); h.cursor.assign(L + 1, 0); h.rowptr.assign(L + 1, 0);
+  c.d_part_cd = h.part_cd.data(); c.d_part_idx = h.part_idx.data(); c.d_part_stats = h.part_stats.data();
+  c.d_row_idx = h.row_idx.data(); c.d_row_fd = h.row_fd.data(); c.d_col_cd = h.col_cd.data(); c.d_col_idx = h.col_idx.data();
+  c.d_cnt = h.cnt.data(); c.d_cursor = h.cursor.data(); c.d_rowptr = h.rowptr.data();
+  memset(&h.iter, 0, sizeof(h.iter));
+  c.d_iter = &h.iter;
+  launch_fpfh_prepare(&c);
+}
+CostParams cost(float bbx, int iteration, double pivot) {
+  CostParams cp;
+  const float scale_f = 0.005 * bbx;   // double product rounded to float, include/ghicp_reg.h:40
+  cp.scale = (double)scale_f;
+  cp.WFD = 1.0; cp.WED = 0.0;
+  cp.ex = 1.0 / (iteration + 1);
+  cp.pivot = pivot;
+  return cp;
+}
+}  // namespace
+
+extern "C" {
+
+// row sweep mode 0 + the chunk merge of k_finalize + k_rowfd_mf
+int emu_fpfh_rowmin(const double *S, const double *T, const float *fs, const float *ft, int N, int M, int n_chunks,
+                    int row0, int nloc, float bbx, int iteration, double pivot, double *row_cd, int *row_idx,
+                    float *row_fd, double *stats2) {
+  Host h;
+  setup(h, S, T, fs, ft, N, M, n_chunks, row0, nloc);
+  const CostParams cp = cost(bbx, iteration, pivot);
+  launch_rowsweep_mf(&h.c, 0, cp);
+  for (int i = row0; i < row0 + nloc; ++i) {
+    double v = h.part_cd[(size_t)i * n_chunks];
+    int ix = h.part_idx[(size_t)i * n_chunks];
+    for (int k = 1; k < n_chunks; ++k) {
+      const double ov = h.part_cd[(size_t)i * n_chunks + k];
+      const int oi = h.part_idx[(size_t)i * n_chunks + k];
+      if (ov < v || (ov == v && oi < ix)) { v = ov; ix = oi; }
+    }
+    row_cd[i] = v; row_idx[i] = ix; h.row_idx[i] = ix;
+  }
+  const int n_parts = ((nloc + 7) / 8) * n_chunks;
+  stats2[0] = stats2[1] = 0.0;
+  for (int p = 0; p < n_parts; ++p) { stats2[0] += h.part_stats[2 * p]; stats2[1] += h.part_stats[2 * p + 1]; }
+  launch_rowfd_mf(&h.c);
+  for (int i = row0; i < row0 + nloc; ++i) row_fd[i] = h.row_fd[i];
+  return 0;
+}
+
+int emu_fpfh_colmin(const double *S, const double *T, const float *fs, const float *ft, int N, int M, int row0,
+                    int nloc, float bbx, int iteration, double *col_cd, int *col_idx) {
+  Host h;
+  setup(h, S, T, fs, ft, N, M, 1, row0, nloc);
+  launch_colsweep_mf(&h.c, cost(bbx, iteration, 0.0));
+  for (int j = 0; j < M; ++j) { col_cd[j] = h.col_cd[j]; col_idx[j] = h.col_idx[j]; }
+  return 0;
+}
+
+// KM graph build: count (mode 1) -> exclusive scan on the host -> fill (mode 2).  Returns nnz; arrays sized by caller.
+long long emu_fpfh_csr(const double *S, const double *T, const float *fs, const float *ft, int N, int M, float bbx,
+                       int iteration, double penalty, long long *rowptr, int *col, double *gain, float *fd,
+                       long long cap) {
+  Host h;
+  setup(h, S, T, fs, ft, N, M, 1, 0, N);
+  const CostParams cp = cost(bbx, iteration, 0.0);
+  h.iter.penalty = penalty;
+  launch_rowsweep_mf(&h.c, 1, cp);
+  long long run = 0;
+  for (int i = 0; i < N; ++i) { h.rowptr[i] = run; run += h.cnt[i]; }
+  h.rowptr[N] = run;
+  if (run > cap) return -run;
+  h.csr_col.assign((size_t)run + 1, -1); h.csr_gain.assign((size_t)run + 1, 0.0); h.csr_fd.assign((size_t)run + 1, 0.f);
+  h.c.d_csr_col = h.csr_col.data(); h.c.d_csr_gain = h.csr_gain.data(); h.c.d_csr_fd = h.csr_fd.data();
+  launch_rowsweep_mf(&h.c, 2, cp);
+  for (int i = 0; i <= N; ++i) rowptr[i] = h.rowptr[i];
+  for (long long k = 0; k < run; ++k) { col[k] = h.csr_col[k]; gain[k] = h.csr_gain[k]; fd[k] = h.csr_fd[k]; }
+  return run;
+}
+
+int emu_fpfh_fd(const float *fs, const float *ft, int N, int M, double *out) {
+  Host h;
+  std::vector<double> S(3 * (size_t)N, 0.0), T(3 * (size_t)M, 0.0);
+  setup(h, S.data(), T.data(), fs, ft, N, M, 1, 0, N);
+  launch_get_fd_mf(&h.c, out);
+  return 0;
+}
+
+// stand-alone estimator kernel on explicit lists
+int emu_solve_alt(int solver, const double *s, const double *t, const double *tn, const double *w, int n, double *Rt,
+                  double *rmse_after, int *degenerate) {
+  DevIter it;
+  memset(&it, 0, sizeof(it));
+  launch_solve_alt_explicit(nullptr, solver, s, t, tn, w, n, &it);
+  memcpy(Rt, it.Rt, sizeof(double) * 16);
+  *rmse_after = it.rmse_after;
+  *degenerate = it.solve_degenerate;
+  return 0;
+}
+
+// in-loop form: pair lists into the keypoint arrays
+int emu_solve_alt_pairs(int solver, const double *S, const double *T, const double *TN, int N, int M, const int *sp,
+                        const int *tp, int cor, double *Rt, double *rmse_after) {
+  Ctx c;
+  DevIter it;
+  memset(&it, 0, sizeof(it));
+  it.cor = cor;
+  c.N = N; c.M = M; c.d_s = const_cast<double *>(S); c.d_t = const_cast<double *>(T); c.d_tn = const_cast<double *>(TN);
+  c.d_sp = const_cast<int *>(sp); c.d_tp = const_cast<int *>(tp); c.d_iter = &it;
+  launch_solve_alt(&c, solver);
+  memcpy(Rt, it.Rt, sizeof(double) * 16);
+  *rmse_after = it.rmse_after;
+  return 0;
+}
+
+}  // extern "C"
