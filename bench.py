@@ -334,12 +334,22 @@ def main():
                 "traffic": NCU_TRAFFIC.get(args.workload) if not args.n else None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "sweeps_per_step": n_sweeps}
     if wl["ft"] == "fpfh":
-        # matrix-free FPFH: O(N+M) bytes for N*M pair evaluations -> FP pipes, not HBM, bound the sweeps; no HBM
-        # roofline is claimed for this workload (not yet profiled: written after round 1's GPU budget was spent)
-        pairs = float(wl["N"]) * wl["M"] * (2 if wl["ct"] == "nnr" else 1)
-        roofline = {"kernel": "k_rowsweep_mf / k_colsweep_mf (FD recomputed on the fly, exact FP64 cost)", "bound": "fp-pipe",
-                    "kernel_ms": cost_ms, "achieved": pairs / (cost_ms * 1e-3) / 1e9 if cost_ms > 0 else 0.0,
-                    "unit": "Gpair/s", "peak": None, "frac": None, "traffic": None}
+        # matrix-free FPFH: O(N+M) bytes for N*M pair evaluations -> the FP32 pipe, not HBM, bounds the sweep.
+        # Dominant kernel = k_ff_sweep<MAIN> (FP32 filter; ms_stream is its CUDA-event time).  Algorithmic work per pair
+        # (DESIGN.md §3.5): 33 FFMA (histogram dot) + 12 (hi/lo coordinate differences, d2) + 8 (cost, bound, sum) = 53
+        # FP32-pipe instructions; peak = 148 SMs x 128 lanes x SM clock.
+        pairs = float(wl["N"]) * wl["M"]
+        fast = stream_ms > 0
+        t_ms = stream_ms if fast else cost_ms
+        sm_mhz = (clocks.get("sm_mhz") or 1965.0)
+        peak_ginstr = 148 * 128 * sm_mhz * 1e6 / 1e9
+        ach = 53.0 * pairs / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0
+        roofline = {"kernel": "k_ff_sweep (FP32 filter over on-the-fly FPFH distances + exact FP64 refinement)" if fast
+                    else "k_rowsweep_mf / k_colsweep_mf (exact all-double matrix-free sweeps)",
+                    "bound": "fp32-pipe", "kernel_ms": t_ms, "achieved": ach if fast else None, "peak": peak_ginstr,
+                    "unit": "Ginstr/s", "frac": (ach / peak_ginstr) if fast else None, "traffic": None,
+                    "pairs_per_s": pairs / (t_ms * 1e-3) if t_ms > 0 else 0.0, "sweeps_per_step": n_sweeps,
+                    "algorithmic_instr_per_pair": 53}
     line = {
         "metric": "ICP iterations/sec", "value": 1000.0 / ms_per_step,
         "unit": "iterations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,

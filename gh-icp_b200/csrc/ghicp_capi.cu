@@ -64,6 +64,8 @@ static void free_all(Ctx *c) {
   dev_free(&c->d_bs); dev_free(&c->d_bt); dev_free(&c->d_fd16);
   dev_free(&c->d_fs); dev_free(&c->d_ft); dev_free(&c->d_fdf);
   dev_free(&c->d_fsc); dev_free(&c->d_fscT); dev_free(&c->d_ftc); dev_free(&c->d_ftcT); dev_free(&c->d_tn);
+  dev_free(&c->d_ff_srec); dev_free(&c->d_ff_tnT); dev_free(&c->d_ff_tco); dev_free(&c->d_ff_part);
+  dev_free(&c->d_ff_rowguess); dev_free(&c->d_ff_colguess); c->fpfh_fast_ready = false;
   dev_free(&c->d_part_cd); dev_free(&c->d_part_idx); dev_free(&c->d_part_stats);
   dev_free(&c->d_row_cd); dev_free(&c->d_row_idx); dev_free(&c->d_col_cd); dev_free(&c->d_col_idx);
   dev_free(&c->d_flags); dev_free(&c->d_sp); dev_free(&c->d_tp); dev_free(&c->d_iter);
@@ -251,6 +253,20 @@ static int build_fd(Ctx *c) {
       if ((rc = dev_alloc(c, &c->d_ftc, (size_t)c->M * 36))) return rc;
       if ((rc = dev_alloc(c, &c->d_ftcT, (size_t)c->M * 36))) return rc;
       CK(c, launch_fpfh_prepare(c));
+      // operands of the FP32 filter (fast NN / NNR path); KM keeps the exact sweeps
+      c->fpfh_fast_ready = false;
+      if (c->cfg.corr_type != GHICP_CT_KM) {
+        if ((rc = dev_alloc(c, &c->d_ff_srec, (size_t)c->N * fpfh_fast_rec_floats()))) return rc;
+        if ((rc = dev_alloc(c, &c->d_ff_tnT, (size_t)c->M * 36))) return rc;
+        if ((rc = dev_alloc(c, &c->d_ff_tco, (size_t)c->M * 6))) return rc;
+        if ((rc = dev_alloc(c, &c->d_ff_part, fpfh_fast_parts(c)))) return rc;
+        if ((rc = dev_alloc(c, &c->d_ff_rowguess, (size_t)c->Npad))) return rc;
+        if ((rc = dev_alloc(c, &c->d_ff_colguess, (size_t)c->M))) return rc;
+        CK(c, cudaMemsetAsync(c->d_ff_rowguess, 0xff, sizeof(unsigned long long) * (size_t)c->Npad, c->stream));
+        CK(c, cudaMemsetAsync(c->d_ff_colguess, 0xff, sizeof(unsigned long long) * (size_t)c->M, c->stream));
+        CK(c, launch_fpfh_fast_build(c));
+        c->fpfh_fast_ready = true;
+      }
     } else {
       if ((rc = dev_alloc(c, &c->d_fdf, fd_elems(c->fd_rows, c->M)))) return rc;
       CK(c, cudaMemsetAsync(c->d_fdf, 0, plane_bytes, c->stream));
@@ -298,7 +314,12 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
   CK(c, cudaEventRecord(c->ev[0], st));
   const int ft = c->cfg.feature_type, ct = c->cfg.corr_type;
   const bool fast = c->use_fast && (ft == GHICP_FT_NONE || ft == GHICP_FT_BSC);
-  bool exact_fallback = !fast;
+  // FPFH: FP32 filter over on-the-fly feature distances + exact refinement (ghicp_fpfh.cu).  Taken when no decision
+  // depends on the CD mean, which a filter cannot reproduce in FPFH mode (heavy-tailed ED / FD^ex): NNR has no gate,
+  // NN's penalty is RMS*para1*scale*para2 from iteration 2 on (src/ghicp_reg.cpp:327-330).
+  const bool fpfh_fast = c->use_fast && ft == GHICP_FT_FPFH && c->fpfh_mf && c->fpfh_fast_ready && ct != GHICP_CT_KM &&
+                         (ct == GHICP_CT_NNR || c->iteration >= 2) && getenv("GHICP_FPFH_EXACT") == nullptr;
+  bool exact_fallback = !fast && !fpfh_fast;
   bool ev1_done = false, timed_stream = false;
   int stream_passes = 0;
   const bool sharded = c->world > 1;
@@ -306,7 +327,35 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
     set_error(c, "multi-GPU KM needs the streaming path (BSC / no feature, force_exact = 0)");
     return GHICP_E_ARG;
   }
-  if (fast && ct != GHICP_CT_KM) {
+  if (fpfh_fast) {
+    const bool cols = (ct == GHICP_CT_NNR);
+    // guesses for the thresholds: last iteration's partners once the loop has settled, else an FP32 argmin pre-pass
+    const long long cand_budget = 6ll * ((long long)c->nloc + (cols ? c->M : 0));
+    const bool prepass = !c->have_prev || c->iteration <= 2 || c->last_cands > cand_budget;
+    CK(c, launch_fpfh_fast_prep(c));
+    if (prepass) { CK(c, launch_fpfh_fast_sweep(c, cp, true, cols)); ++stream_passes; }
+    CK(c, launch_fpfh_fast_seed(c, cp, cols, prepass));
+    CK(c, cudaEventRecord(c->ev[4], st));
+    CK(c, launch_fpfh_fast_sweep(c, cp, false, cols));
+    CK(c, cudaEventRecord(c->ev[5], st));
+    ++stream_passes; timed_stream = true;
+    CK(c, launch_fpfh_fast_finish(c, cp, cols));
+    CK(c, launch_rowfd_mf(c));
+    if ((rc = comm_exchange(c, 1 | 2 | (cols ? 4 : 0)))) return rc;
+    CK(c, launch_penalty(c, 0.0, ls));
+    if (cols && sharded) CK(c, launch_colmerge(c));
+    CK(c, cudaEventRecord(c->ev[1], st));
+    ev1_done = true;
+    if (cols) CK(c, launch_select_nnr(c));
+    else CK(c, launch_select_nn(c, 0.0));
+    CK(c, cudaMemcpyAsync(c->h_sdev, c->d_sdev, sizeof(StreamDev), cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(c->h_iter, c->d_iter, sizeof(DevIter), cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    c->last_cands = (long long)c->h_sdev->cand_count[0] + (cols ? c->h_sdev->cand_count[1] : 0);
+    if (c->h_iter->overflow_any) exact_fallback = true;   // candidate buffer overflow (on any rank): exact sweeps
+    else c->have_prev = true;
+    c->fallbacks += exact_fallback ? 1 : 0;
+  } else if (fast && ct != GHICP_CT_KM) {
     // ---- streaming path, NN / NNR: one pass = calED + calCD + row (and column) scans + statistics
     const bool cols = (ct == GHICP_CT_NNR);
     // a seed pass (FP32 minima only) keeps the refinement cheap whenever last iteration's partners are not
@@ -515,7 +564,7 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
     out->ax = ax; out->ay = ay; out->az = az;
     out->nnz = nnz; out->km_rounds = kres.rounds; out->km_phases = kres.phases;
     out->gpu_launches = c->launches;
-    out->exact_fallback = (fast && exact_fallback) ? 1 : 0;
+    out->exact_fallback = ((fast || fpfh_fast) && exact_fallback) ? 1 : 0;
     float ms;
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); out->ms_cost = ms;
     cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); out->ms_corr = ms;
@@ -523,7 +572,7 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[3]); out->ms_total = ms;
     if (timed_stream) { cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]); out->ms_stream = ms; }
     out->stream_passes = stream_passes;
-    out->candidates = (fast && ct != GHICP_CT_KM) ? c->last_cands : 0;
+    out->candidates = ((fast || fpfh_fast) && ct != GHICP_CT_KM) ? c->last_cands : 0;
   }
   c->iteration++;
   return warnings;

@@ -15,6 +15,7 @@
 // Per iteration algorithmic work: 33 multiply-adds + ~12 FP64 operations + one pow() per pair; bytes are O(N + M)
 // per CTA row block (the 5.3 KB/keypoint-pair tiles stay in L2), i.e. the path is FP-pipe bound, not HBM bound.
 #include <algorithm>
+#include <climits>
 #include <cmath>
 
 #include "ghicp_internal.h"
@@ -274,6 +275,320 @@ __global__ void k_fd_to_double_mf(const float *__restrict__ sc, const float *__r
   out[idx] = (double)fpfh_fd_pair(sc + (size_t)i * HP, tc + (size_t)j * HP);
 }
 
+
+// =====================================================================================================================
+// FAST path: FP32 filter + exact FP64 refinement (the scheme of ghicp_stream.cu with FD recomputed on the fly).
+//
+// Every decision the reference takes on doubles (row / column argmin with the first-minimum tie-break) is taken on the
+// exactly evaluated CD of the few pairs an FP32 filter cannot rule out:
+//   filter   cd32 = scale * dist32 * fd32^(-ex) dist32 from hi/lo-split centred coordinates (relative error ~2^-22),
+//                                              fd32 = |<h_s, h_t>| of the L2-normalised centred histograms (33 FFMA),
+//                                              fd^(-ex) = ex2(-ex * lg2(fd))  (MUFU)
+//   bound    |fd32 - FD_reference| <= FF_G     (both are 33-term float dot products of vectors of norm <= 1; the
+//                                              reference's own float evaluation carries the same kind of error)
+//            => CD_exact >= LB = cd32 * (1 - FF_D0 - 1.5 * ex * FF_G / fd32)      while FF_G / fd32 <= 1/8;
+//            below that (|correlation| < 6.4e-5, CD astronomically large) the rare path re-derives a bound from fd32 + FF_G
+//   refine   every pair with LB <= thr(row) (or thr(column)) is evaluated EXACTLY (reference operation order), its CD
+//            goes to atomicMin(rowbest / colbest) and to the candidate list; k_ff_resolve keeps the smallest index among
+//            the candidates equal to the minimum.  thr = exact CD of a guess pair (last iteration's partner, or the FP32
+//            argmin found by the PRE pass), so the true minimum always passes.
+// Statistics: only the CD SUM is kept (FP32 values, FP64 accumulation).  In FPFH mode the mean is dominated by pairs of
+// near-zero correlation (CD = ED / FD^ex is heavy-tailed) and cannot be reproduced by a filter, so the host only takes
+// this path when no decision depends on it (NNR: no gate; NN from iteration 2 on: penalty = RMS*para1*scale*para2,
+// src/ghicp_reg.cpp:327-330) and reports the estimate.
+// =====================================================================================================================
+constexpr int FF_THREADS = 256;
+constexpr int FF_RB = 32;        // source rows staged in shared memory per step
+constexpr int FF_ROWS = 1024;    // source rows per CTA
+constexpr int FF_REC = 40;       // floats per source record: 33 normalised bins, hi xyz, lo xyz, row threshold
+constexpr float FF_D0 = 3e-5f;   // relative slack: sqrt / lg2 / ex2 approximations, coordinate split, normalisation
+constexpr float FF_G = 8e-6f;    // absolute bound on |fd32 - FD_reference|
+typedef unsigned long long ffu64;
+
+__device__ __forceinline__ float ff_lg2(float x) {
+#if defined(GHICP_EMU_HOST)
+  return log2f(x);
+#else
+  float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#endif
+}
+__device__ __forceinline__ float ff_ex2(float x) {
+#if defined(GHICP_EMU_HOST)
+  return exp2f(x);
+#else
+  float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#endif
+}
+__device__ __forceinline__ float ff_sqrt(float x) {
+#if defined(GHICP_EMU_HOST)
+  return sqrtf(x);
+#else
+  float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#endif
+}
+__device__ __forceinline__ ffu64 ff_ord64(double v) { return (ffu64)__double_as_longlong(v); }  // CD >= 0: monotone bits
+
+struct FfArgs {
+  const double *s, *t;          // exact coordinates [3][N], [3][M]
+  const float *sc, *tc;         // exact path: centred histograms, row-major [n][36]
+  const float *srec;            // filter: source records [N][FF_REC]
+  const float *tnT;             // filter: normalised target histograms, transposed [36][M]
+  const float *tco;             // filter: target coordinates hi xyz, lo xyz, transposed [6][M]
+  int N, M, row0, nloc;
+  CostParams cp;
+  float scalef;                 // (float) cp.scale
+  float exf;                    // (float) cp.ex
+  float c1;                     // 1.5 * ex * FF_G
+  float *thr_row, *thr_col;     // upper bounds of the exact minima (rounded up)
+  ffu64 *rowguess, *colguess;   // PRE pass: packed (cd32 bits << 32 | index)
+  ffu64 *rowbest, *colbest;     // exact minima, ordered-double bits
+  int *rowidx, *colidx;
+  Cand *cand[2]; int cand_cap;
+  StreamDev *dev;
+  double *part;                 // [grid] CD sums
+};
+
+// exact CD(i,j): reference operation order (include/fpfh.hpp:135-165, src/ghicp_reg.cpp:122, 308)
+__device__ GHICP_NOINLINE double ff_exact_cd(const FfArgs &a, int i, int j) {
+  const float fdf = fpfh_fd_pair(a.sc + (size_t)i * HP, a.tc + (size_t)j * HP);
+  const double ed = ed_exact(a.s[i], a.s[(size_t)a.N + i], a.s[2 * (size_t)a.N + i], a.t[j], a.t[(size_t)a.M + j],
+                             a.t[2 * (size_t)a.M + j], a.cp.scale);
+  return cd_exact<GHICP_FT_FPFH>(ed, (double)fdf, a.cp);
+}
+__device__ __forceinline__ void ff_push(const FfArgs &a, int which, int i, int j, double cd) {
+  const int slot = atomicAdd(&a.dev->cand_count[which], 1);
+  if (slot < a.cand_cap) {
+    Cand c;
+    c.i = i; c.j = j; c.cd = cd;
+    a.cand[which][slot] = c;
+  } else {
+    a.dev->overflow = 1;
+  }
+}
+// rare path: the filter could not rule the pair out.  fd32 so small that the first-order bound does not apply
+// (FF_G / fd32 > 1/8) gets a bound from fd32 + FF_G >= FD_reference first.
+__device__ GHICP_NOINLINE void ff_slow(const FfArgs &a, int which, int i, int j, float dist, float fd, float thr) {
+  if (FF_G > 0.125f * fd) {
+    const float lb2 = dist * ff_ex2(-a.exf * ff_lg2(fd + FF_G)) * (1.f - FF_D0);
+    if (lb2 > thr) return;
+  }
+  const double e = ff_exact_cd(a, i, j);
+  if (!(e == e)) return;  // NaN (degenerate histogram): never a minimum in the reference's '<' scans either
+  if (which == 0) atomicMin(&a.rowbest[i], ff_ord64(e)); else atomicMin(&a.colbest[j], ff_ord64(e));
+  ff_push(a, which, i, j, e);
+}
+
+// Per-iteration operands: centred coordinates split into hi + lo floats (their difference then carries a RELATIVE
+// error of ~2^-23 even for nearly coincident points), written into the source records / the target SoA array.
+__global__ void k_ff_prep(const double *__restrict__ s, const double *__restrict__ t, int N, int M, double cx, double cy,
+                          double cz, float *__restrict__ srec, float *__restrict__ tco) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < N) {
+    const double x = s[k] - cx, y = s[(size_t)N + k] - cy, z = s[2 * (size_t)N + k] - cz;
+    const float xh = (float)x, yh = (float)y, zh = (float)z;
+    float *r = srec + (size_t)k * FF_REC;
+    r[33] = xh; r[34] = yh; r[35] = zh;
+    r[36] = (float)(x - (double)xh); r[37] = (float)(y - (double)yh); r[38] = (float)(z - (double)zh);
+  }
+  if (k < M) {
+    const double x = t[k] - cx, y = t[(size_t)M + k] - cy, z = t[2 * (size_t)M + k] - cz;
+    const float xh = (float)x, yh = (float)y, zh = (float)z;
+    tco[k] = xh; tco[(size_t)M + k] = yh; tco[2 * (size_t)M + k] = zh;
+    tco[3 * (size_t)M + k] = (float)(x - (double)xh);
+    tco[4 * (size_t)M + k] = (float)(y - (double)yh);
+    tco[5 * (size_t)M + k] = (float)(z - (double)zh);
+  }
+}
+// One-time: L2-normalised centred histograms for the filter (source: into the records; target: transposed)
+__global__ void k_ff_normalise(const float *__restrict__ sc, const float *__restrict__ tc, int N, int M,
+                               float *__restrict__ srec, float *__restrict__ tnT) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < N) {
+    const float *h = sc + (size_t)k * HP;
+    const float inv = h[33] > 0.f ? 1.0f / sqrtf(h[33]) : 0.f;
+    float *r = srec + (size_t)k * FF_REC;
+    for (int q = 0; q < 33; ++q) r[q] = h[q] * inv;
+    for (int q = 33; q < FF_REC; ++q) r[q] = 0.f;
+  }
+  if (k < M) {
+    const float *h = tc + (size_t)k * HP;
+    const float inv = h[33] > 0.f ? 1.0f / sqrtf(h[33]) : 0.f;
+    for (int q = 0; q < 33; ++q) tnT[(size_t)q * M + k] = h[q] * inv;
+    for (int q = 33; q < HP; ++q) tnT[(size_t)q * M + k] = 0.f;
+  }
+}
+
+// Thresholds: exact CD of the guess pairs (PRE pass argmin and / or last iteration's partner), rounded up.
+__global__ void k_ff_seed(FfArgs a, const int *__restrict__ prev_row_idx, const int *__restrict__ prev_col_idx,
+                          int have_prev, int use_guess, int with_cols, float *__restrict__ srec) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const float INF = __uint_as_float(0x7f800000u);
+  if (k >= a.row0 && k < a.row0 + a.nloc) {
+    double best = 1e300;
+    bool any = false;
+    if (use_guess && a.rowguess[k] != ~0ull) {
+      const int j = (int)(unsigned)(a.rowguess[k] & 0xffffffffull);
+      const double e = ff_exact_cd(a, k, j);
+      if (e == e && e < best) { best = e; any = true; }
+    }
+    if (have_prev) {
+      const int j = prev_row_idx[k];
+      if (j >= 0 && j < a.M) { const double e = ff_exact_cd(a, k, j); if (e == e && e < best) { best = e; any = true; } }
+    }
+    const float thr = any ? __double2float_ru(best * 1.0000001) : INF;
+    a.thr_row[k] = thr;
+    srec[(size_t)k * FF_REC + 39] = thr;
+    a.rowbest[k] = ~0ull;
+    a.rowidx[k] = INT_MAX;
+    a.rowguess[k] = ~0ull;
+  }
+  if (with_cols && k < a.M) {
+    double best = 1e300;
+    bool any = false;
+    if (use_guess && a.colguess[k] != ~0ull) {
+      const int i = (int)(unsigned)(a.colguess[k] & 0xffffffffull);
+      const double e = ff_exact_cd(a, i, k);
+      if (e == e && e < best) { best = e; any = true; }
+    }
+    if (have_prev) {
+      const int i = prev_col_idx[k];
+      if (i >= a.row0 && i < a.row0 + a.nloc) { const double e = ff_exact_cd(a, i, k); if (e == e && e < best) { best = e; any = true; } }
+    }
+    a.thr_col[k] = any ? __double2float_ru(best * 1.0000001) : INF;
+    a.colbest[k] = ~0ull;
+    a.colidx[k] = INT_MAX;
+    a.colguess[k] = ~0ull;
+  }
+}
+
+// The sweep.  PRE = true: FP32 argmin per row (and column) -> guess pairs.  PRE = false: candidate gate + statistics.
+// A thread owns one target column (its normalised histogram and split coordinates stay in registers); the CTA walks
+// FF_ROWS source rows, FF_RB at a time through shared memory.
+template <bool PRE, bool COLS>
+__global__ void __launch_bounds__(FF_THREADS) k_ff_sweep(const FfArgs a) {
+  __shared__ __align__(16) float s_rec[FF_RB][FF_REC];
+  __shared__ ffu64 s_guess[FF_RB];
+  __shared__ double s_red[FF_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int jraw = blockIdx.x * FF_THREADS + tid;
+  const bool valid = jraw < a.M;
+  const int j = valid ? jraw : a.M - 1;
+  const int i_begin = a.row0 + blockIdx.y * FF_ROWS;
+  const int i_end = min(a.row0 + a.nloc, i_begin + FF_ROWS);
+  const float INF = __uint_as_float(0x7f800000u);
+
+  float ht[33];
+#pragma unroll
+  for (int k = 0; k < 33; ++k) ht[k] = a.tnT[(size_t)k * a.M + j];
+  const float txh = a.tco[j], tyh = a.tco[(size_t)a.M + j], tzh = a.tco[2 * (size_t)a.M + j];
+  const float txl = a.tco[3 * (size_t)a.M + j], tyl = a.tco[4 * (size_t)a.M + j], tzl = a.tco[5 * (size_t)a.M + j];
+  const float thr_c = (!PRE && COLS && valid) ? a.thr_col[j] : -INF;
+  float cmin = INF;   // PRE: running column minimum over this CTA's rows
+  int carg = 0;
+  double dsum = 0.0;
+
+  for (int ib = i_begin; ib < i_end; ib += FF_RB) {
+    const int nb = min(FF_RB, i_end - ib);
+    __syncthreads();
+    for (int k = tid; k < nb * FF_REC; k += FF_THREADS) s_rec[k / FF_REC][k % FF_REC] = a.srec[(size_t)ib * FF_REC + k];
+    if (PRE && tid < FF_RB) s_guess[tid] = ~0ull;
+    __syncthreads();
+    float fsum = 0.f;
+    for (int r = 0; r < nb; ++r) {
+      asm volatile("" ::: "memory");   // keep the records in shared memory (no hoisting into registers / local memory)
+      const float *rec = s_rec[r];
+      const float dx = (rec[33] - txh) + (rec[36] - txl);
+      const float dy = (rec[34] - tyh) + (rec[37] - tyl);
+      const float dz = (rec[35] - tzh) + (rec[38] - tzl);
+      const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+      float dot = 0.f;
+#pragma unroll
+      for (int k = 0; k < 33; ++k) dot = fmaf(rec[k], ht[k], dot);
+      const float fd = fmaxf(fabsf(dot), 1e-30f);
+      const float dist = a.scalef * ff_sqrt(d2);   // ED (src/ghicp_reg.cpp:122) in FP32
+      const float l = ff_lg2(fd);
+      float cd32 = dist * ff_ex2(-a.exf * l);
+      if (!valid) cd32 = INF;
+      if (PRE) {
+        // warp argmin of the row: REDUX on the (non-negative) float bits, first lane holding the minimum
+        const unsigned bits = __float_as_uint(cd32);
+        const unsigned m = __reduce_min_sync(0xffffffffu, bits);
+        const unsigned who = __ballot_sync(0xffffffffu, bits == m);
+        if (lane == __ffs(who) - 1 && m < 0x7f800000u) atomicMin(&s_guess[r], ((ffu64)m << 32) | (unsigned)j);
+        if (COLS && cd32 < cmin) { cmin = cd32; carg = ib + r; }
+      } else {
+        fsum += valid ? cd32 : 0.f;
+        const float rinv = ff_ex2(-l);                         // ~ 1 / fd32
+        // <= exact CD.  The first-order term only holds while FF_G / fd32 <= 1/8: below that the pair always takes the
+        // rare path, which bounds it through fd32 + FF_G instead.
+        const float lb = fd < 8.f * FF_G ? -INF : cd32 * (1.f - FF_D0 - a.c1 * rinv);
+        if (valid && lb <= rec[39]) ff_slow(a, 0, ib + r, j, dist, fd, rec[39]);
+        if (COLS && valid && lb <= thr_c) ff_slow(a, 1, ib + r, j, dist, fd, thr_c);
+      }
+    }
+    if (PRE) {
+      __syncthreads();
+      if (tid < nb && s_guess[tid] != ~0ull) atomicMin(&a.rowguess[ib + tid], s_guess[tid]);
+    } else {
+      dsum += (double)fsum;   // at most FF_RB FP32 values per partial
+    }
+  }
+  if (PRE) {
+    if (COLS && valid && cmin < INF) atomicMin(&a.colguess[j], ((ffu64)__float_as_uint(cmin) << 32) | (unsigned)carg);
+  } else {
+    double v[1] = {dsum};
+    block_sum<1, FF_THREADS>(v, s_red);
+    if (tid == 0) a.part[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = v[0];
+  }
+}
+
+// this rank's CD sum -> xstats (the penalty rule runs in k_penalty); fixed order: deterministic
+__global__ void __launch_bounds__(1024) k_ff_stats(const double *__restrict__ part, int n_parts, double *__restrict__ xstats,
+                                                   int rank) {
+  __shared__ double sm[32];
+  double v[1] = {0.0};
+  for (int p = threadIdx.x; p < n_parts; p += blockDim.x) v[0] += part[p];
+  block_sum<1, 1024>(v, sm);
+  if (threadIdx.x == 0) {
+    xstats[4 * rank] = v[0];
+    xstats[4 * rank + 1] = 0.0;   // the CD variance is not defined for FPFH (src/ghicp_reg.cpp:317-335 uses the mean only)
+    xstats[4 * rank + 2] = 0.0;
+  }
+}
+// first-minimum tie-break: among the candidates whose exact CD equals the minimum keep the smallest index
+// (src/ghicp_reg.cpp:626, 641, 719)
+__global__ void k_ff_resolve(const FfArgs a, int which) {
+  const int n = min(a.dev->cand_count[which], a.cand_cap);
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const Cand c = a.cand[which][k];
+    if (which == 0) {
+      if (ff_ord64(c.cd) == a.rowbest[c.i]) atomicMin(&a.rowidx[c.i], c.j);
+    } else {
+      if (ff_ord64(c.cd) == a.colbest[c.j]) atomicMin(&a.colidx[c.j], c.i);
+    }
+  }
+}
+__global__ void k_ff_publish(const FfArgs a, double *row_cd, int *row_idx, double *col_cd, int *col_idx, double *xstats,
+                             int rank) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k == 0) xstats[4 * rank + 2] = a.dev->overflow ? 1.0 : 0.0;   // travels with the statistics
+  if (k >= a.row0 && k < a.row0 + a.nloc) {
+    const int j = a.rowidx[k];
+    const bool found = j != INT_MAX;   // not found: every CD of the row is NaN -> the reference scan keeps (9e20, 0)
+    row_cd[k] = found ? __longlong_as_double((long long)a.rowbest[k]) : MAXVALIUE;
+    row_idx[k] = found ? j : 0;
+  }
+  if (col_cd && k < a.M) {
+    const int i = a.colidx[k];
+    const bool found = i != INT_MAX;
+    col_cd[k] = found ? __longlong_as_double((long long)a.colbest[k]) : MAXVALIUE;
+    col_idx[k] = found ? i : 0;
+  }
+}
+__global__ void k_ff_reset(StreamDev *dev) {
+  dev->cand_count[0] = 0; dev->cand_count[1] = 0; dev->overflow = 0;
+}
+
 }  // namespace
 
 cudaError_t launch_fpfh_prepare(Ctx *c) {
@@ -322,6 +637,75 @@ cudaError_t launch_get_fd_mf(Ctx *c, double *d_out) {
   const size_t total = (size_t)c->N * c->M;
   GHICP_LAUNCH(k_fd_to_double_mf, (unsigned)((total + 255) / 256), 256, 0, c->stream, c->d_fsc, c->d_ftc, c->N, c->M, c->r0, c->nloc, d_out);
   c->launches++;
+  return cudaGetLastError();
+}
+
+
+// ---- fast path launchers ---------------------------------------------------------------------------------------------
+static FfArgs ff_args(Ctx *c, const CostParams &cp) {
+  FfArgs a{};
+  a.s = c->d_s; a.t = c->d_t; a.sc = c->d_fsc; a.tc = c->d_ftc;
+  a.srec = c->d_ff_srec; a.tnT = c->d_ff_tnT; a.tco = c->d_ff_tco;
+  a.N = c->N; a.M = c->M; a.row0 = c->r0; a.nloc = c->nloc;
+  a.cp = cp;
+  a.scalef = (float)cp.scale;
+  a.exf = (float)cp.ex;
+  a.c1 = 1.5f * (float)cp.ex * FF_G;
+  a.thr_row = reinterpret_cast<float *>(c->d_row_thr); a.thr_col = reinterpret_cast<float *>(c->d_col_thr);
+  a.rowguess = c->d_ff_rowguess; a.colguess = c->d_ff_colguess;
+  a.rowbest = c->d_rowbest; a.colbest = c->d_colbest; a.rowidx = c->d_rowidx2; a.colidx = c->d_colidx2;
+  a.cand[0] = c->d_cand[0]; a.cand[1] = c->d_cand[1]; a.cand_cap = c->cand_cap;
+  a.dev = c->d_sdev;
+  a.part = c->d_ff_part;
+  return a;
+}
+static dim3 ff_grid(const Ctx *c) { return dim3((c->M + FF_THREADS - 1) / FF_THREADS, (c->nloc + FF_ROWS - 1) / FF_ROWS); }
+size_t fpfh_fast_parts(const Ctx *c) { const dim3 g = ff_grid(c); return (size_t)g.x * g.y; }
+size_t fpfh_fast_rec_floats() { return FF_REC; }
+
+// one-time (after launch_fpfh_prepare): normalised histograms for the filter; guesses cleared
+cudaError_t launch_fpfh_fast_build(Ctx *c) {
+  const int n = c->N > c->M ? c->N : c->M;
+  GHICP_LAUNCH(k_ff_normalise, (n + 127) / 128, 128, 0, c->stream, c->d_fsc, c->d_ftc, c->N, c->M, c->d_ff_srec, c->d_ff_tnT);
+  c->launches++;
+  return cudaGetLastError();
+}
+// per iteration: split coordinates, counters
+cudaError_t launch_fpfh_fast_prep(Ctx *c) {
+  const int n = c->N > c->M ? c->N : c->M;
+  GHICP_LAUNCH(k_ff_prep, (n + 255) / 256, 256, 0, c->stream, c->d_s, c->d_t, c->N, c->M, c->center[0], c->center[1],
+               c->center[2], c->d_ff_srec, c->d_ff_tco);
+  GHICP_LAUNCH(k_ff_reset, 1, 1, 0, c->stream, c->d_sdev);
+  c->launches += 2;
+  return cudaGetLastError();
+}
+cudaError_t launch_fpfh_fast_seed(Ctx *c, const CostParams &cp, bool with_cols, bool use_guess) {
+  const FfArgs a = ff_args(c, cp);
+  const int n = c->N > c->M ? c->N : c->M;
+  GHICP_LAUNCH(k_ff_seed, (n + 255) / 256, 256, 0, c->stream, a, c->d_row_idx, c->d_col_idx, c->have_prev ? 1 : 0,
+               use_guess ? 1 : 0, with_cols ? 1 : 0, c->d_ff_srec);
+  c->launches++;
+  return cudaGetLastError();
+}
+cudaError_t launch_fpfh_fast_sweep(Ctx *c, const CostParams &cp, bool pre, bool with_cols) {
+  const FfArgs a = ff_args(c, cp);
+  const dim3 grid = ff_grid(c);
+  void (*kern)(const FfArgs) = pre ? (with_cols ? k_ff_sweep<true, true> : k_ff_sweep<true, false>)
+                                   : (with_cols ? k_ff_sweep<false, true> : k_ff_sweep<false, false>);
+  GHICP_LAUNCH(kern, grid, FF_THREADS, 0, c->stream, a);
+  c->launches++;
+  return cudaGetLastError();
+}
+// statistics -> xstats, exact index resolution, publication into d_row_cd / d_row_idx (/ d_col_*)
+cudaError_t launch_fpfh_fast_finish(Ctx *c, const CostParams &cp, bool with_cols) {
+  const FfArgs a = ff_args(c, cp);
+  GHICP_LAUNCH(k_ff_stats, 1, 1024, 0, c->stream, c->d_ff_part, (int)fpfh_fast_parts(c), c->d_xstats, c->rank);
+  GHICP_LAUNCH(k_ff_resolve, 148 * 4, 256, 0, c->stream, a, 0);
+  if (with_cols) GHICP_LAUNCH(k_ff_resolve, 148 * 4, 256, 0, c->stream, a, 1);
+  const int n = c->N > c->M ? c->N : c->M;
+  GHICP_LAUNCH(k_ff_publish, (n + 255) / 256, 256, 0, c->stream, a, c->d_row_cd, c->d_row_idx,
+               with_cols ? c->d_col_cd : (double *)nullptr, with_cols ? c->d_col_idx : (int *)nullptr, c->d_xstats, c->rank);
+  c->launches += with_cols ? 4 : 3;
   return cudaGetLastError();
 }
 

@@ -13,7 +13,9 @@
 // fiber on the CPU; those files launch through this macro.  The product is always built by nvcc.
 #if defined(GHICP_EMU_HOST)
 #define GHICP_LAUNCH(kernel, grid, block, smem, stream, ...) emu::launch((grid), (block), [&] { kernel(__VA_ARGS__); })
+#define GHICP_NOINLINE __attribute__((noinline))
 #else
+#define GHICP_NOINLINE __noinline__
 #define GHICP_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #endif
 
@@ -119,6 +121,12 @@ struct Ctx {
   // matrix-free FPFH (ghicp_fpfh.cu): centred histograms, row-major [n][36] and transposed [36][n]; no N x M array
   bool fpfh_mf = false;
   float *d_fsc = nullptr, *d_fscT = nullptr, *d_ftc = nullptr, *d_ftcT = nullptr;
+  // FPFH fast path (FP32 filter + exact refinement): source records [N][40], normalised target histograms [36][M],
+  // split target coordinates [6][M], per-CTA CD sums, PRE-pass guesses
+  bool fpfh_fast_ready = false;
+  float *d_ff_srec = nullptr, *d_ff_tnT = nullptr, *d_ff_tco = nullptr;
+  double *d_ff_part = nullptr;
+  unsigned long long *d_ff_rowguess = nullptr, *d_ff_colguess = nullptr;
   // opt-in solvers (ghicp_solvers.cu)
   double *d_tn = nullptr;  // target normals [3][M]
   bool have_normals = false;
@@ -250,6 +258,14 @@ cudaError_t launch_rowsweep_mf(Ctx *c, int mode, const CostParams &cp);
 cudaError_t launch_colsweep_mf(Ctx *c, const CostParams &cp);
 cudaError_t launch_rowfd_mf(Ctx *c);       // d_row_fd[i] = FD(i, d_row_idx[i]) for this context's rows
 cudaError_t launch_get_fd_mf(Ctx *c, double *d_out);
+// FPFH fast path: FP32 filter over on-the-fly FD + exact FP64 refinement of the candidates (NN / NNR)
+size_t fpfh_fast_parts(const Ctx *c);      // per-CTA partial sums the sweep writes
+size_t fpfh_fast_rec_floats();             // floats per source record
+cudaError_t launch_fpfh_fast_build(Ctx *c);                                   // once, after launch_fpfh_prepare
+cudaError_t launch_fpfh_fast_prep(Ctx *c);                                    // per iteration
+cudaError_t launch_fpfh_fast_seed(Ctx *c, const CostParams &cp, bool with_cols, bool use_guess);
+cudaError_t launch_fpfh_fast_sweep(Ctx *c, const CostParams &cp, bool pre, bool with_cols);
+cudaError_t launch_fpfh_fast_finish(Ctx *c, const CostParams &cp, bool with_cols);
 
 // ---- opt-in solvers (ghicp_solvers.cu) -------------------------------------------------------------
 // Overwrites iter->Rt and iter->rmse_after from the pair list in the ctx (after launch_solve produced the statistics)

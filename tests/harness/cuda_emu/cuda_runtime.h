@@ -47,6 +47,34 @@ inline T __shfl_up_sync(unsigned, T v, int delta) {
 template <typename T>
 inline T atomicAdd(T *p, T v) { T old = *p; *p = old + v; return old; }   // one OS thread: fibers never preempt
 
+template <typename T>
+inline T atomicMin(T *p, T v) { T old = *p; if (v < old) *p = v; return old; }
+template <typename T>
+inline T atomicMax(T *p, T v) { T old = *p; if (v > old) *p = v; return old; }
+inline unsigned __reduce_min_sync(unsigned, unsigned v) {
+  unsigned all[32];
+  emu::warp_all<unsigned>(v, all);
+  unsigned m = all[0];
+  for (int l = 1; l < 32; ++l) m = all[l] < m ? all[l] : m;
+  return m;
+}
+inline unsigned __ballot_sync(unsigned, int pred) {
+  unsigned all[32], m = 0;
+  emu::warp_all<unsigned>(pred ? 1u : 0u, all);
+  for (int l = 0; l < 32; ++l) m |= (all[l] & 1u) << l;
+  return m;
+}
+inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
+inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+inline long long __double_as_longlong(double d) { long long l; memcpy(&l, &d, 8); return l; }
+inline double __longlong_as_double(long long l) { double d; memcpy(&d, &l, 8); return d; }
+inline float __double2float_ru(double x) {
+  float f = (float)x;
+  if ((double)f < x) f = nextafterf(f, INFINITY);
+  return f;
+}
+
 inline int min(int a, int b) { return a < b ? a : b; }
 inline int max(int a, int b) { return a > b ? a : b; }
 inline long long min(long long a, long long b) { return a < b ? a : b; }

@@ -69,6 +69,25 @@ inline T shfl(T v, int src_lane) {
   return r;
 }
 
+// all 32 lane values of a convergent warp-wide operation (ballot / redux)
+template <typename T>
+inline void warp_all(T v, T out[32]) {
+  Warp &w = g_warps[cur()->tidx.x >> 5];
+  const int lane = cur()->tidx.x & 31;
+  unsigned long long raw = 0;
+  memcpy(&raw, &v, sizeof(T));
+  w.in[lane] = raw;
+  const int my = w.gen;
+  if (++w.count == w.live) {
+    memcpy(w.out, w.in, sizeof(w.out));
+    w.count = 0;
+    ++w.gen;
+  } else {
+    while (w.gen == my) yield();
+  }
+  for (int l = 0; l < 32; ++l) memcpy(&out[l], &w.out[l], sizeof(T));
+}
+
 inline void fiber_entry() {
   (*g_body)();
   Fiber *f = cur();

@@ -117,6 +117,53 @@ int emu_fpfh_fd(const float *fs, const float *ft, int N, int M, double *out) {
   return 0;
 }
 
+// FPFH fast path (FP32 filter + exact refinement) in the order ghicp_capi.cu drives it: prep, [PRE sweep], seed, MAIN
+// sweep, finish (+ row FD).  prev_* = last iteration's partners (may be null).  Returns the candidate counts.
+int emu_fpfh_fast(const double *S, const double *T, const float *fs, const float *ft, int N, int M, int row0, int nloc,
+                  float bbx, int iteration, int cols, const int *prev_row, const int *prev_col, int prepass,
+                  double *row_cd, int *row_idx, float *row_fd, double *col_cd, int *col_idx, int *cand_counts,
+                  double *cd_sum) {
+  Host h;
+  setup(h, S, T, fs, ft, N, M, 1, row0, nloc);
+  Ctx &c = h.c;
+  const CostParams cp = cost(bbx, iteration, 0.0);
+  std::vector<float> srec((size_t)N * fpfh_fast_rec_floats()), tnT((size_t)M * 36), tco((size_t)M * 6);
+  std::vector<unsigned long long> rowguess(N, ~0ull), colguess(M, ~0ull), rowbest(N), colbest(M);
+  std::vector<unsigned> row_thr(N), col_thr(M);
+  std::vector<int> rowidx2(N), colidx2(M);
+  std::vector<double> part(fpfh_fast_parts(&c)), xstats(4, 0.0), rcd(N, -1.0);
+  std::vector<Cand> cand0((size_t)1 << 20), cand1((size_t)1 << 20);
+  StreamDev sdev;
+  memset(&sdev, 0, sizeof(sdev));
+  c.d_ff_srec = srec.data(); c.d_ff_tnT = tnT.data(); c.d_ff_tco = tco.data(); c.d_ff_part = part.data();
+  c.d_ff_rowguess = rowguess.data(); c.d_ff_colguess = colguess.data();
+  c.d_rowbest = rowbest.data(); c.d_colbest = colbest.data(); c.d_rowidx2 = rowidx2.data(); c.d_colidx2 = colidx2.data();
+  c.d_row_thr = row_thr.data(); c.d_col_thr = col_thr.data();
+  c.d_cand[0] = cand0.data(); c.d_cand[1] = cand1.data(); c.cand_cap = 1 << 20;
+  c.d_sdev = &sdev; c.d_xstats = xstats.data(); c.rank = 0;
+  c.d_row_cd = rcd.data();
+  double cx = 0, cy = 0, cz = 0;   // the library centres the filter operands on the target centroid
+  for (int j = 0; j < M; ++j) { cx += T[j]; cy += T[(size_t)M + j]; cz += T[2 * (size_t)M + j]; }
+  c.center[0] = cx / M; c.center[1] = cy / M; c.center[2] = cz / M;
+  c.have_prev = prev_row != nullptr;
+  if (prev_row) for (int i = 0; i < N; ++i) h.row_idx[i] = prev_row[i];
+  if (prev_col) for (int j = 0; j < M; ++j) h.col_idx[j] = prev_col[j];
+  launch_fpfh_fast_build(&c);
+  launch_fpfh_fast_prep(&c);
+  if (prepass) launch_fpfh_fast_sweep(&c, cp, true, cols != 0);
+  if (getenv("EMU_DEBUG")) for (int i = 0; i < 4; ++i) fprintf(stderr, "rowguess[%d] = %llx\n", i, rowguess[i]);
+  launch_fpfh_fast_seed(&c, cp, cols != 0, prepass != 0);
+  if (getenv("EMU_DEBUG")) for (int i = 0; i < 4; ++i) fprintf(stderr, "thr[%d] = %g  rec: %g %g %g | %g\n", i, srec[(size_t)i * 40 + 39], srec[(size_t)i*40], srec[(size_t)i*40+33], srec[(size_t)i*40+36], tnT[i]);
+  launch_fpfh_fast_sweep(&c, cp, false, cols != 0);
+  launch_fpfh_fast_finish(&c, cp, cols != 0);
+  launch_rowfd_mf(&c);
+  for (int i = row0; i < row0 + nloc; ++i) { row_cd[i] = rcd[i]; row_idx[i] = h.row_idx[i]; row_fd[i] = h.row_fd[i]; }
+  if (cols) for (int j = 0; j < M; ++j) { col_cd[j] = h.col_cd[j]; col_idx[j] = h.col_idx[j]; }
+  cand_counts[0] = sdev.cand_count[0]; cand_counts[1] = sdev.cand_count[1]; cand_counts[2] = sdev.overflow;
+  *cd_sum = xstats[0];
+  return 0;
+}
+
 // stand-alone estimator kernel on explicit lists
 int emu_solve_alt(int solver, const double *s, const double *t, const double *tn, const double *w, int n, double *Rt,
                   double *rmse_after, int *degenerate) {

@@ -35,6 +35,8 @@ def emu(tmp_path_factory):
     L.emu_fpfh_csr.restype = C.c_longlong
     L.emu_fpfh_csr.argtypes = [dp, dp, fp, fp, C.c_int, C.c_int, C.c_float, C.c_int, C.c_double, lp, ip, dp, fp, C.c_longlong]
     L.emu_fpfh_fd.argtypes = [fp, fp, C.c_int, C.c_int, dp]
+    L.emu_fpfh_fast.argtypes = [dp, dp, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, ip, ip, C.c_int,
+                                dp, ip, fp, dp, ip, ip, dp]
     L.emu_solve_alt.argtypes = [C.c_int, dp, dp, dp, dp, C.c_int, dp, dp, ip]
     L.emu_solve_alt_pairs.argtypes = [C.c_int, dp, dp, dp, C.c_int, C.c_int, ip, ip, C.c_int, dp, dp]
     return L
@@ -131,6 +133,114 @@ def test_emulated_km_graph_build_matches_oracle(g, orc, emu):
         assert np.array_equal(col[b:e][order], np.nonzero(mask[i])[0].astype(np.int32))
         assert np.array_equal(gain[b:e][order], penalty - CD[i, mask[i]])
         assert np.array_equal(fd[b:e][order], FD[i, mask[i]].astype(np.float32))
+
+
+# ---- FPFH fast path: FP32 filter + exact refinement ------------------------------------------------------------------
+def run_fast(emu, sc, it, cols, prev_row=None, prev_col=None, prepass=True, row0=0, nloc=None):
+    N, M = sc.S.shape[0], sc.T.shape[0]
+    nloc = N if nloc is None else nloc
+    S, T = np.asfortranarray(sc.S), np.asfortranarray(sc.T)
+    row_cd, row_idx, row_fd = np.full(N, -1.0), np.full(N, -1, np.int32), np.zeros(N, np.float32)
+    col_cd, col_idx = np.full(M, -1.0), np.full(M, -1, np.int32)
+    counts, cd_sum = np.zeros(3, np.int32), C.c_double(0)
+    emu.emu_fpfh_fast(P(S, dp), P(T, dp), P(sc.fpfh_s, fp), P(sc.fpfh_t, fp), N, M, row0, nloc, C.c_float(sc.bbx_magnitude), it,
+                      1 if cols else 0, P(prev_row, ip), P(prev_col, ip), 1 if prepass else 0,
+                      P(row_cd, dp), P(row_idx, ip), P(row_fd, fp), P(col_cd, dp), P(col_idx, ip), P(counts, ip), C.byref(cd_sum))
+    return row_cd, row_idx, row_fd, col_cd, col_idx, counts, cd_sum.value
+
+
+@pytest.mark.parametrize("N,M,it", [(300, 420, 0), (257, 300, 1), (64, 1000, 4), (5, 3, 0)])
+def test_fast_path_with_prepass_equals_exact_argmins(g, orc, emu, N, M, it):
+    sc = scene(g, N, M, 11 * N + M + it)
+    FD, CD = oracle_cd(orc, sc, it)
+    row_cd, row_idx, row_fd, col_cd, col_idx, counts, cd_sum = run_fast(emu, sc, it, cols=True)
+    ri, ci = np.argmin(CD, axis=1), np.argmin(CD, axis=0)
+    assert counts[2] == 0
+    assert np.array_equal(row_idx, ri.astype(np.int32)) and np.array_equal(row_cd, CD[np.arange(N), ri])
+    assert np.array_equal(col_idx, ci.astype(np.int32)) and np.array_equal(col_cd, CD[ci, np.arange(M)])
+    assert np.array_equal(row_fd, FD[np.arange(N), ri].astype(np.float32))
+    # the filter passes only a few pairs per row / column to exact evaluation
+    assert N <= counts[0] <= 4 * N + 16 and M <= counts[1] <= 4 * M + 16
+    # the CD sum is the FP32 filter's estimate (heavy-tailed in FPFH mode: dominated by near-zero correlations)
+    assert cd_sum == pytest.approx(float(CD.sum()), rel=0.2)
+
+
+def test_fast_path_seeded_by_stale_partners_without_prepass(g, orc, emu):
+    N, M, it = 200, 260, 3
+    sc = scene(g, N, M, 77)
+    _, CD = oracle_cd(orc, sc, it)
+    ri, ci = np.argmin(CD, axis=1), np.argmin(CD, axis=0)
+    rng = np.random.default_rng(1)
+    prev_row = ri.astype(np.int32).copy()
+    prev_col = ci.astype(np.int32).copy()
+    prev_row[::3] = rng.integers(0, M, size=len(prev_row[::3]))      # a third of the partners are stale (loose bounds)
+    prev_col[::4] = rng.integers(0, N, size=len(prev_col[::4]))
+    row_cd, row_idx, _, col_cd, col_idx, counts, _ = run_fast(emu, sc, it, cols=True, prev_row=prev_row, prev_col=prev_col,
+                                                              prepass=False)
+    assert np.array_equal(row_idx, ri.astype(np.int32)) and np.array_equal(row_cd, CD[np.arange(N), ri])
+    assert np.array_equal(col_idx, ci.astype(np.int32)) and np.array_equal(col_cd, CD[ci, np.arange(M)])
+    assert counts[0] > N                                              # loose thresholds cost extra exact evaluations
+
+
+def test_fast_path_first_minimum_tie_break(g, orc, emu):
+    # duplicated target keypoints (same coordinates and histogram): the reference keeps the FIRST minimum (:719)
+    N, M, it = 120, 150, 2
+    sc = scene(g, N, M, 5)
+    T = np.array(sc.T); ft = np.array(sc.fpfh_t)
+    T[100:150] = T[0:50]; ft[100:150] = ft[0:50]
+    sc.T = np.asfortranarray(T); sc.fpfh_t = np.ascontiguousarray(ft)
+    _, CD = oracle_cd(orc, sc, it)
+    row_cd, row_idx, _, col_cd, col_idx, counts, _ = run_fast(emu, sc, it, cols=True)
+    ri, ci = np.argmin(CD, axis=1), np.argmin(CD, axis=0)
+    assert np.array_equal(row_idx, ri.astype(np.int32))
+    assert np.array_equal(col_idx, ci.astype(np.int32))
+    assert (ri < 100).all() or (CD[np.arange(N), ri] < CD[np.arange(N), np.minimum(ri + 100, M - 1)]).any()
+
+
+def test_fast_path_near_zero_correlation_pairs_are_not_lost(g, orc, emu):
+    """Adversarial: the row / column minimum is a pair whose correlation is ~1e-5 (where the first-order error bound of
+    the filter does not hold) because the two keypoints almost coincide.  The rare path must still catch it."""
+    N, M, it = 80, 90, 0
+    sc = scene(g, N, M, 13)
+    S, T = np.array(sc.S), np.array(sc.T)
+    fs, ft = np.array(sc.fpfh_s, dtype=np.float64), np.array(sc.fpfh_t, dtype=np.float64)
+    rng = np.random.default_rng(3)
+    for i, j, eps in ((3, 7, 1e-5), (40, 41, -3e-6), (66, 2, 4e-5)):
+        a = fs[i] - fs[i].mean()
+        v = rng.random(33); v -= v.mean(); v -= a * (v @ a) / (a @ a)          # orthogonal to the centred source histogram
+        h = 3.0 + v / np.abs(v).max() + eps * a / np.linalg.norm(a) * np.linalg.norm(v / np.abs(v).max())
+        ft[j] = h
+        T[j] = S[i] + 1e-7                                                     # (almost) the same place
+    sc.S, sc.T = np.asfortranarray(S), np.asfortranarray(T.astype(np.float32).astype(np.float64))
+    sc.fpfh_s, sc.fpfh_t = np.ascontiguousarray(fs, dtype=np.float32), np.ascontiguousarray(ft, dtype=np.float32)
+    FD, CD = oracle_cd(orc, sc, it)
+    assert FD[3, 7] < 1e-4 and FD[40, 41] < 1e-4                               # really in the uncertain regime
+    row_cd, row_idx, _, col_cd, col_idx, counts, _ = run_fast(emu, sc, it, cols=True)
+    ri, ci = np.argmin(CD, axis=1), np.argmin(CD, axis=0)
+    assert np.array_equal(row_idx, ri.astype(np.int32)) and np.array_equal(row_cd, CD[np.arange(N), ri])
+    assert np.array_equal(col_idx, ci.astype(np.int32)) and np.array_equal(col_cd, CD[ci, np.arange(M)])
+
+
+def test_fast_path_on_a_row_shard_only_touches_its_rows(g, orc, emu):
+    N, M, it = 90, 333, 1
+    sc = scene(g, N, M, 9)
+    _, CD = oracle_cd(orc, sc, it)
+    row0, nloc = 30, 41
+    row_cd, row_idx, _, col_cd, col_idx, counts, _ = run_fast(emu, sc, it, cols=True, row0=row0, nloc=nloc)
+    sl = slice(row0, row0 + nloc)
+    assert np.array_equal(row_idx[sl], np.argmin(CD[sl], axis=1).astype(np.int32))
+    assert np.all(row_idx[:row0] == -1) and np.all(row_idx[row0 + nloc:] == -1)
+    assert np.array_equal(col_idx, (np.argmin(CD[sl], axis=0) + row0).astype(np.int32))   # column minima over the shard
+
+
+def test_fast_path_rows_only_mode(g, orc, emu):
+    N, M, it = 150, 700, 2
+    sc = scene(g, N, M, 41)
+    _, CD = oracle_cd(orc, sc, it)
+    row_cd, row_idx, _, _, _, counts, _ = run_fast(emu, sc, it, cols=False)
+    ri = np.argmin(CD, axis=1)
+    assert np.array_equal(row_idx, ri.astype(np.int32)) and np.array_equal(row_cd, CD[np.arange(N), ri])
+    assert counts[1] == 0
 
 
 # ---- the estimator kernel -----------------------------------------------------------------------------------------

@@ -46,11 +46,12 @@ def test_fpfh_matrix_free_rowmin_identical(g, N, M):
 
 
 @pytest.mark.parametrize("Ct", ["nn", "nnr", "km"])
-def test_fpfh_matrix_free_loop_identical(g, Ct):
+def test_fpfh_matrix_free_exact_loop_identical(g, Ct):
+    """force_exact: the matrix-free sweeps with the all-double arithmetic == the stored-plane kernels, bit for bit."""
     N, M = (600, 500) if Ct != "km" else (220, 260)
     sc = fpfh_scene(g, N, M, 17)
     ct = {"nn": g.CT_NN, "nnr": g.CT_NNR, "km": g.CT_KM}[Ct]
-    mf = g.registration.from_scene(sc, g.FT_FPFH, ct, fpfh_matrix_free=1)
+    mf = g.registration.from_scene(sc, g.FT_FPFH, ct, fpfh_matrix_free=1, force_exact=True)
     pl = g.registration.from_scene(sc, g.FT_FPFH, ct, fpfh_matrix_free=-1)
     for it in range(12):
         a, b = mf.iterate(), pl.iterate()
@@ -60,10 +61,44 @@ def test_fpfh_matrix_free_loop_identical(g, Ct):
         assert np.array_equal(np.array(a.Rt), np.array(b.Rt))          # same pairs -> bit-identical solve
         assert a.fdm == b.fdm and a.fdstd == b.fdstd                   # FD of the pairs recomputed identically
         assert a.cd_mean == pytest.approx(b.cd_mean, rel=1e-12)
+        assert a.stream_passes == 0
         if Ct == "km":
             assert a.nnz == b.nnz
         if a.converged:
             break
+
+
+@pytest.mark.parametrize("Ct,N,M", [("nn", 600, 500), ("nnr", 600, 500), ("nnr", 2300, 1700), ("nnr", 40, 1500)])
+def test_fpfh_fast_path_equals_exact_path(g, Ct, N, M):
+    """FP32 filter + exact refinement (the default with fpfh_matrix_free=1) against the all-double stored-plane path:
+    identical correspondence sets and transforms every iteration.  NN only takes the fast path from iteration 2 on (its
+    penalty depends on the CD mean before that); the CD mean itself is the filter's estimate on fast iterations."""
+    sc = fpfh_scene(g, N, M, 23)
+    ct = {"nn": g.CT_NN, "nnr": g.CT_NNR}[Ct]
+    fast = g.registration.from_scene(sc, g.FT_FPFH, ct, fpfh_matrix_free=1)
+    slow = g.registration.from_scene(sc, g.FT_FPFH, ct, fpfh_matrix_free=-1)
+    n_fast = 0
+    for it in range(14):
+        a, b = fast.iterate(), slow.iterate()
+        sp, tp = fast.pairs()
+        osp, otp = slow.pairs()
+        assert np.array_equal(sp, osp) and np.array_equal(tp, otp), f"iteration {it}"
+        assert np.array_equal(np.array(a.Rt), np.array(b.Rt))
+        assert a.fdm == b.fdm and a.rmse == b.rmse
+        assert a.exact_fallback == 0
+        on_fast = Ct == "nnr" or it >= 2
+        assert (a.stream_passes >= 1) == on_fast
+        if on_fast:
+            n_fast += 1
+            assert a.candidates >= N                                   # at least the minimum of every row is refined
+            assert a.candidates <= 8 * (N + M) + 64                    # ... and not much more than that
+            assert a.cd_mean == pytest.approx(b.cd_mean, rel=0.05)     # estimate (heavy-tailed statistic)
+        else:
+            assert a.cd_mean == pytest.approx(b.cd_mean, rel=1e-12)
+            assert a.penalty == pytest.approx(b.penalty, rel=1e-12)
+        if a.converged:
+            break
+    assert n_fast >= 1
 
 
 def test_fpfh_env_override_selects_matrix_free(g, monkeypatch):
