@@ -238,11 +238,13 @@ static int build_fd(Ctx *c) {
     // Stored float plane (4*N*M bytes) or matrix-free (ghicp_fpfh.cu: FD recomputed inside the sweeps, O(N+M) memory).
     // Both give bit-identical FD / CD values; auto mode stores the plane only while it is a modest share of the HBM.
     const size_t plane_bytes = fd_elems(c->fd_rows, c->M) * sizeof(float);
+    // auto: NN / NNR always go matrix-free (their sweeps then run the FP32-filter fast path, ~9x the all-double
+    // kernels at 200k x 200k on a B200, same correspondences); KM keeps the plane while it is a modest share of the HBM.
     bool mf = c->cfg.fpfh_matrix_free > 0 || getenv("GHICP_FPFH_MATRIX_FREE") != nullptr;
     if (!mf && c->cfg.fpfh_matrix_free == 0) {
       size_t free_b = 0, total_b = 0;
       CK(c, cudaMemGetInfo(&free_b, &total_b));
-      mf = (double)plane_bytes > 0.4 * (double)free_b;
+      mf = c->cfg.corr_type != GHICP_CT_KM || (double)plane_bytes > 0.4 * (double)free_b;
     }
     c->fpfh_mf = mf;
     int rc;

@@ -76,10 +76,10 @@ typedef struct ghicp_config {
   double km_eps;        /* 0 → Energyfunction::KM_eps = 0.01 (ghicp_reg.h:38) */
   int verbose;          /* 0 = silent (the reference prints every iteration; we do not by default) */
   int force_exact;      /* 1 = all-double cost kernels only (no FP32 filter); results are identical, slower */
-  int fpfh_matrix_free; /* FPFH only: 0 = auto (stored float FD plane while it fits in 40 % of the free device
-                           memory, matrix-free beyond: config 3's 200k x 200k plane would be 160 GB), 1 = always
-                           recompute FD on the fly (no N x M array at all), -1 = always store the plane.  Results are
-                           bit-identical either way. */
+  int fpfh_matrix_free; /* FPFH only: 0 = auto (NN / NNR: matrix-free, no N x M array at all — the sweeps recompute the
+                           feature distance and run the FP32-filter + exact-refinement fast path; KM: stored float plane
+                           while it fits in 40 % of the free device memory), 1 = always matrix-free, -1 = always store
+                           the plane (all-double sweeps).  Correspondences and transforms are identical either way. */
   int solver;           /* ghicp_solver_type used by ghicp_iterate; 0 = the reference's SVD.  POINT_TO_PLANE needs
                            ghicp_set_target_normals.  WEIGHTED_SVD is stand-alone only (ghicp_rigid_fit_ex). */
   int reserved[4];
@@ -93,7 +93,9 @@ typedef struct ghicp_iter_stats {
   int warnings;         /* GHICP_W_* bits */
   double Rt[16];        /* this iteration's transform (Rt_temp), column-major */
   double Rt_tillnow[16];/* accumulated transform */
-  double cd_mean, cd_std, penalty;          /* calCD_* outputs */
+  double cd_mean, cd_std, penalty;          /* calCD_* outputs.  FPFH fast path (stream_passes > 0): cd_mean is the FP32
+                                               filter's ESTIMATE — the statistic is heavy-tailed (ED / FD^ex with FD near
+                                               0) and no decision depends on it on the iterations that take that path */
   double rmse, rmse_after, fdm, fdstd, iou; /* findcorrespondence* / transformestimation outputs */
   double para1, para2;                      /* after adjustweight */
   double km_energy;                         /* Km::Calenergy equivalent (KM mode) */

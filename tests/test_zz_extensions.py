@@ -92,7 +92,9 @@ def test_fpfh_fast_path_equals_exact_path(g, Ct, N, M):
             n_fast += 1
             assert a.candidates >= N                                   # at least the minimum of every row is refined
             assert a.candidates <= 8 * (N + M) + 64                    # ... and not much more than that
-            assert a.cd_mean == pytest.approx(b.cd_mean, rel=0.05)     # estimate (heavy-tailed statistic)
+            # the CD mean is only an ESTIMATE here: ED / FD^ex is heavy-tailed (a handful of near-zero correlations carry
+            # most of the sum) and no decision depends on it on these iterations
+            assert 0.3 * b.cd_mean < a.cd_mean < 3.0 * b.cd_mean
         else:
             assert a.cd_mean == pytest.approx(b.cd_mean, rel=1e-12)
             assert a.penalty == pytest.approx(b.penalty, rel=1e-12)
@@ -101,15 +103,25 @@ def test_fpfh_fast_path_equals_exact_path(g, Ct, N, M):
     assert n_fast >= 1
 
 
-def test_fpfh_env_override_selects_matrix_free(g, monkeypatch):
+def test_fpfh_auto_mode_and_overrides(g, monkeypatch):
     sc = fpfh_scene(g, 64, 80, 5)
+    auto = g.registration.from_scene(sc, g.FT_FPFH, g.CT_NNR)         # auto: NN / NNR go matrix-free + fast path
+    plane = g.registration.from_scene(sc, g.FT_FPFH, g.CT_NNR, fpfh_matrix_free=-1)
+    monkeypatch.setenv("GHICP_FPFH_EXACT", "1")                       # matrix-free, but the all-double sweeps
+    exact = g.registration.from_scene(sc, g.FT_FPFH, g.CT_NNR)
+    e = exact.iterate()
+    monkeypatch.delenv("GHICP_FPFH_EXACT")
+    a, b = auto.iterate(), plane.iterate()
+    assert a.stream_passes >= 1 and b.stream_passes == 0 and e.stream_passes == 0
+    for r in (auto, exact):
+        assert np.array_equal(r.pairs()[0], plane.pairs()[0]) and np.array_equal(r.pairs()[1], plane.pairs()[1])
+    assert np.array_equal(np.array(a.Rt), np.array(b.Rt)) and np.array_equal(np.array(e.Rt), np.array(b.Rt))
+    assert e.cd_mean == pytest.approx(b.cd_mean, rel=1e-12)
+    km = g.registration.from_scene(sc, g.FT_FPFH, g.CT_KM)            # KM keeps the stored plane in auto mode
     monkeypatch.setenv("GHICP_FPFH_MATRIX_FREE", "1")
-    mf = g.registration.from_scene(sc, g.FT_FPFH, g.CT_NN)           # auto mode, forced by the environment
-    mf.build_fd()                                                    # the variable is read when the FD stage is set up
-    monkeypatch.delenv("GHICP_FPFH_MATRIX_FREE")
-    pl = g.registration.from_scene(sc, g.FT_FPFH, g.CT_NN)
-    a, b = mf.iterate(), pl.iterate()
-    assert np.array_equal(mf.pairs()[0], pl.pairs()[0]) and np.array_equal(np.array(a.Rt), np.array(b.Rt))
+    km_mf = g.registration.from_scene(sc, g.FT_FPFH, g.CT_KM)
+    x, y = km_mf.iterate(), km.iterate()
+    assert x.nnz == y.nnz and abs(x.km_energy - y.km_energy) <= 80 * 0.01 + 1e-9 * abs(y.km_energy)
 
 
 # ---- opt-in estimators --------------------------------------------------------------------------------------------
