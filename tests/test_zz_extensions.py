@@ -118,6 +118,7 @@ def test_fpfh_auto_mode_and_overrides(g, monkeypatch):
     assert np.array_equal(np.array(a.Rt), np.array(b.Rt)) and np.array_equal(np.array(e.Rt), np.array(b.Rt))
     assert e.cd_mean == pytest.approx(b.cd_mean, rel=1e-12)
     km = g.registration.from_scene(sc, g.FT_FPFH, g.CT_KM)            # KM keeps the stored plane in auto mode
+    km.build_fd()                                                     # (the FD stage is set up lazily: do it before the override)
     monkeypatch.setenv("GHICP_FPFH_MATRIX_FREE", "1")
     km_mf = g.registration.from_scene(sc, g.FT_FPFH, g.CT_KM)
     x, y = km_mf.iterate(), km.iterate()
