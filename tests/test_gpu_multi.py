@@ -23,10 +23,11 @@ dist.init_process_group("gloo")          # rendezvous only: the data path uses N
 uid = [g.comm_unique_id() if rank == 0 else None]
 dist.broadcast_object_list(uid, src=0)
 mode = sys.argv[1]
-ft = {"none": g.FT_NONE, "bsc": g.FT_BSC}[mode.split("-")[0]]
+ft = {"none": g.FT_NONE, "bsc": g.FT_BSC, "fpfh": g.FT_FPFH}[mode.split("-")[0]]
 ct = {"nn": g.CT_NN, "nnr": g.CT_NNR, "km": g.CT_KM}[mode.split("-")[1]]
 sc = g.synth.gen_points(3001, 2750, overlap=0.6, extent=(80, 80, 16), noise=0.04, seed=31)
 if ft == g.FT_BSC: g.synth.add_bsc(sc, bits=441, V=4)
+if ft == g.FT_FPFH: g.synth.add_fpfh(sc)
 reg = g.registration.from_scene(sc, ft, ct, device=rank, comm=(uid[0], rank, world))
 out = []
 for it in range(6):
@@ -39,7 +40,7 @@ dist.barrier()
 '''
 
 
-@pytest.mark.parametrize("mode", ["none-nn", "bsc-nn", "bsc-nnr", "bsc-km"])
+@pytest.mark.parametrize("mode", ["none-nn", "bsc-nn", "bsc-nnr", "bsc-km", "fpfh-nnr", "fpfh-nn"])
 def test_sharded_equals_single_gpu(g, tmp_path, mode):
     import pickle
     if g.device_count() < 2:
@@ -53,11 +54,13 @@ def test_sharded_equals_single_gpu(g, tmp_path, mode):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     ranks = [pickle.load(open(tmp_path / f"rank{k}.pkl", "rb")) for k in range(world)]
     # single-GPU reference run in this process
-    ft = {"none": g.FT_NONE, "bsc": g.FT_BSC}[mode.split("-")[0]]
+    ft = {"none": g.FT_NONE, "bsc": g.FT_BSC, "fpfh": g.FT_FPFH}[mode.split("-")[0]]
     ct = {"nn": g.CT_NN, "nnr": g.CT_NNR, "km": g.CT_KM}[mode.split("-")[1]]
     sc = g.synth.gen_points(3001, 2750, overlap=0.6, extent=(80, 80, 16), noise=0.04, seed=31)
     if ft == g.FT_BSC:
         g.synth.add_bsc(sc, bits=441, V=4)
+    if ft == g.FT_FPFH:
+        g.synth.add_fpfh(sc)   # matrix-free: each rank sweeps its block of source rows, column minima merged (§3.5)
     reg = g.registration.from_scene(sc, ft, ct)
     for it in range(6):
         st = reg.iterate()
