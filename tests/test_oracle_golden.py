@@ -148,3 +148,37 @@ def test_loop_converges_to_ground_truth(orc):
     assert rc == 0 and it < 60
     assert synth.rot_angle(Rt[:3, :3], sc.R_gt) < 2e-3
     assert np.linalg.norm(Rt[:3, 3] - sc.t_gt) < 0.5  # plain ICP with 10 % outliers: near, not exact
+
+
+# ---- loop-level fixtures (tests/golden/loop_golden.npz, generated by tests/golden/make_loop_golden.py) --------------
+LOOP_CASES = ["none_nn", "none_nnr", "bsc_nn", "bsc_nnr", "bsc_km", "bsc_nn_dof4", "fpfh_nn", "fpfh_nnr"]
+
+
+def load_loop_case(name):
+    z = np.load(os.path.join(GOLD, "loop_golden.npz"))
+    pre = name + "/"
+    return {k[len(pre):]: z[k] for k in z.files if k.startswith(pre)}
+
+
+@pytest.mark.parametrize("name", LOOP_CASES)
+def test_oracle_reproduces_loop_fixture(orc, scratch_cwd, name):
+    """Guards the oracle against drift: the committed loops (inputs, per-iteration pair lists, transforms) replay."""
+    c = load_loop_case(name)
+    ft, ct, dof, max_it, n_it = (int(v) for v in c["meta"])
+    o = orc.Oracle(ft, ct, dof=dof, bbx_magnitude=float(c["bbx"]), solve_mode=1, max_iter=max_it,
+                   use_ref_km=(ct == orc.CT_KM and orc.ref_km_lib() is not None))
+    o.set_keypoints(c["S"], c["T"])
+    if "bsc_s" in c:
+        o.set_bsc(c["bsc_s"], c["bsc_t"], 441)
+    if "fpfh_s" in c:
+        o.set_fpfh(c["fpfh_s"], c["fpfh_t"])
+    o.build_fd()
+    for it in range(n_it):
+        st = o.iterate()
+        sp, tp = o.pairs()
+        b, e = c["off"][it], c["off"][it + 1]
+        assert np.array_equal(sp, c["sp"][b:e]) and np.array_equal(tp, c["tp"][b:e]), (name, it)
+        assert np.allclose(np.array(st.Rt), c["Rt"][it], atol=1e-12)
+        assert st.penalty == pytest.approx(float(c["penalty"][it]), rel=1e-12)
+    assert st.converged == 1
+    assert np.allclose(np.array(st.Rt_tillnow), c["Rt_final"], atol=1e-12)
