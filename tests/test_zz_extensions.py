@@ -253,7 +253,7 @@ def test_cuda_path_reproduces_committed_loop_fixture(g, scratch_cwd, name):
             continue
         assert same, (name, it)
         assert np.allclose(np.array(st.Rt), c["Rt"][it], atol=1e-5)
-    assert mismatched <= 1
+    assert mismatched <= 1   # none observed on the stored-plane path (tests/test_gpu_parity.py allows the same)
     if ct != g.CT_KM and mismatched == 0:
         Ra, Rb = reg.Rt_tillnow(), np.array(c["Rt_final"]).reshape(4, 4).T
         assert g.synth.rot_angle(Ra[:3, :3], Rb[:3, :3]) < 1e-4 and np.linalg.norm(Ra[:3, 3] - Rb[:3, 3]) < 1e-3
