@@ -68,7 +68,8 @@ EXPORTS = ["ghicp_abi_version", "ghicp_device_count", "ghicp_last_error", "ghicp
            "ghicp_set_keypoints", "ghicp_set_bsc", "ghicp_set_fpfh", "ghicp_build_fd", "ghicp_iterate",
            "ghicp_run", "ghicp_get_pairs", "ghicp_get_source", "ghicp_get_rt", "ghicp_get_fd",
            "ghicp_probe_rowmin", "ghicp_set_state", "ghicp_km_solve", "ghicp_rigid_fit", "ghicp_rigid_fit_ex",
-           "ghicp_set_target_normals", "ghicp_set_solver", "ghicp_comm_unique_id", "ghicp_comm_init"]
+           "ghicp_set_target_normals", "ghicp_set_solver", "ghicp_voxel_downsample", "ghicp_detect_keypoints",
+           "ghicp_comm_unique_id", "ghicp_comm_init"]
 
 
 def lib():
@@ -104,6 +105,9 @@ def lib():
     L.ghicp_rigid_fit_ex.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, C.c_int, dp]
     L.ghicp_set_target_normals.argtypes = [vp, dp]
     L.ghicp_set_solver.argtypes = [vp, C.c_int]
+    fpp = C.POINTER(C.c_float)
+    L.ghicp_voxel_downsample.argtypes = [C.c_int, fpp, C.c_int, C.c_float, ip, ip]
+    L.ghicp_detect_keypoints.argtypes = [C.c_int, fpp, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, ip, ip, fpp, dp, ip]
     L.ghicp_comm_unique_id.argtypes = [vp]
     L.ghicp_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
     _lib = L
@@ -147,6 +151,29 @@ def km_solve(W, sp=None, tp=None, eps=0.01, penalty=1000.0, device=0):
     r = C.c_int(0)
     check(lib().ghicp_km_solve(device, _dp(W), n, sp, tp, eps, penalty, _ip(match), C.byref(e), C.byref(r)))
     return match, e.value, r.value
+
+
+def voxel_downsample(xyz, voxel_size, device=0):
+    """CFilter::voxelfilter (include/filter.hpp:28-88) on the GPU: indices of the kept points, in output order."""
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+    out = np.zeros(len(xyz) + 1, np.int32)
+    m = C.c_int(0)
+    check(lib().ghicp_voxel_downsample(device, xyz.ctypes.data_as(C.POINTER(C.c_float)), len(xyz), voxel_size, _ip(out),
+                                       C.byref(m)))
+    return out[:m.value].copy()
+
+
+def detect_keypoints(xyz, radius, ratio_max=0.65, min_pts=20, nms_radius=None, device=0):
+    """CKeypointDetect::keypointDetectionBasedOnCurvature (include/keypoint_detect.hpp:27-51) on the GPU.
+    Returns (keypoint indices in the reference's output order, eigenvalues [n][3], curvature [n], neighbour counts)."""
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+    n = len(xyz)
+    kp, m = np.zeros(n, np.int32), C.c_int(0)
+    lam, curv, cnt = np.zeros((n, 3), np.float32), np.zeros(n), np.zeros(n, np.int32)
+    check(lib().ghicp_detect_keypoints(device, xyz.ctypes.data_as(C.POINTER(C.c_float)), n, radius, ratio_max, min_pts,
+                                       nms_radius if nms_radius is not None else radius, _ip(kp), C.byref(m),
+                                       lam.ctypes.data_as(C.POINTER(C.c_float)), _dp(curv), _ip(cnt)))
+    return kp[:m.value].copy(), lam, curv, cnt
 
 
 def rigid_fit_ex(S, T, solver=SOLVER_SVD, normals=None, weights=None, device=0):

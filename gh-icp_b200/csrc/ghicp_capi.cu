@@ -983,6 +983,53 @@ int ghicp_rigid_fit_ex(int device, int solver, const double *s, const double *t,
   return h.solve_degenerate ? GHICP_W_FEW_PAIRS : GHICP_OK;
 }
 
+// ---- pre-processing ----------------------------------------------------------------------------------------------
+int ghicp_voxel_downsample(int device, const float *xyz, int n, float voxel_size, int *out_idx, int *n_out) {
+  if (!xyz || !out_idx || !n_out || n <= 0 || !(voxel_size > 0.f)) { set_error(nullptr, "voxel_downsample: bad argument"); return GHICP_E_ARG; }
+  if (ghicp_device_count() <= 0) { set_error(nullptr, "voxel_downsample: no CUDA device"); return GHICP_E_NODEV; }
+  if (cudaSetDevice(device) != cudaSuccess) return GHICP_E_CUDA;
+  float *d_xyz = nullptr; int *d_out = nullptr;
+  cudaError_t e = cudaMalloc((void **)&d_xyz, 3 * (size_t)n * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&d_out, ((size_t)n + 1) * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemcpy(d_xyz, xyz, 3 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice);
+  int m = 0;
+  if (e == cudaSuccess) e = prep_voxel_downsample(0, d_xyz, n, voxel_size, d_out, &m);
+  if (e == cudaSuccess && m > 0) e = cudaMemcpy(out_idx, d_out, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost);
+  if (d_xyz) cudaFree(d_xyz);
+  if (d_out) cudaFree(d_out);
+  if (e != cudaSuccess) { set_error(nullptr, std::string("voxel_downsample: ") + cudaGetErrorString(e)); cudaGetLastError(); return e == cudaErrorMemoryAllocation ? GHICP_E_NOMEM : GHICP_E_CUDA; }
+  *n_out = m;
+  return GHICP_OK;
+}
+
+int ghicp_detect_keypoints(int device, const float *xyz, int n, float radius, float ratio_max, int min_pts, float nms_radius,
+                           int *kp_idx, int *n_kp, float *lam, double *curvature, int *pt_num) {
+  if (!xyz || !kp_idx || !n_kp || n <= 0 || !(radius > 0.f) || !(nms_radius > 0.f)) { set_error(nullptr, "detect_keypoints: bad argument"); return GHICP_E_ARG; }
+  if (ghicp_device_count() <= 0) { set_error(nullptr, "detect_keypoints: no CUDA device"); return GHICP_E_NODEV; }
+  if (cudaSetDevice(device) != cudaSuccess) return GHICP_E_CUDA;
+  float *d_xyz = nullptr, *d_lam = nullptr; double *d_curv = nullptr; int *d_cnt = nullptr, *d_kp = nullptr;
+  cudaError_t e = cudaMalloc((void **)&d_xyz, 3 * (size_t)n * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&d_lam, 3 * (size_t)n * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&d_curv, (size_t)n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&d_cnt, (size_t)n * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&d_kp, (size_t)n * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemcpy(d_xyz, xyz, 3 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice);
+  int m = 0, rounds = 0;
+  if (e == cudaSuccess) e = prep_detect_keypoints(0, d_xyz, n, radius, ratio_max, min_pts, nms_radius, d_lam, d_curv, d_cnt, d_kp, &m, &rounds);
+  if (e == cudaSuccess && m > 0) e = cudaMemcpy(kp_idx, d_kp, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && lam) e = cudaMemcpy(lam, d_lam, 3 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && curvature) e = cudaMemcpy(curvature, d_curv, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && pt_num) e = cudaMemcpy(pt_num, d_cnt, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost);
+  if (d_xyz) cudaFree(d_xyz);
+  if (d_lam) cudaFree(d_lam);
+  if (d_curv) cudaFree(d_curv);
+  if (d_cnt) cudaFree(d_cnt);
+  if (d_kp) cudaFree(d_kp);
+  if (e != cudaSuccess) { set_error(nullptr, std::string("detect_keypoints: ") + cudaGetErrorString(e)); cudaGetLastError(); return e == cudaErrorMemoryAllocation ? GHICP_E_NOMEM : GHICP_E_CUDA; }
+  *n_kp = m;
+  return GHICP_OK;
+}
+
 int ghicp_comm_unique_id(void *id128) {
   if (!id128) return GHICP_E_ARG;
   return comm_unique_id(id128);

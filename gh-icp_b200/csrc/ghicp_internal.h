@@ -274,6 +274,12 @@ cudaError_t launch_solve_alt(Ctx *c, int solver);
 cudaError_t launch_solve_alt_explicit(cudaStream_t stream, int solver, const double *d_s, const double *d_t,
                                       const double *d_tn, const double *d_w, int n, DevIter *d_iter);
 
+// ---- pre-processing (ghicp_prep.cu): voxel filter, radius PCA / curvature, keypoint pruning + NMS, on device arrays ----
+cudaError_t prep_voxel_downsample(cudaStream_t st, const float *d_xyz, int n, float voxel_size, int *d_out, int *n_out);
+cudaError_t prep_detect_keypoints(cudaStream_t st, const float *d_xyz, int n, float radius, float ratio_max, int min_pts,
+                                  float nms_radius, float *d_lam, double *d_curv, int *d_cnt, int *d_kp, int *n_kp,
+                                  int *nms_rounds);
+
 // ---- streaming path (ghicp_stream.cu) -----------------------------------------------------------
 cudaError_t launch_stream_prep(Ctx *c, const CostParams &cp, int for_km_gate);
 cudaError_t launch_stream_gate(Ctx *c, const CostParams &cp);

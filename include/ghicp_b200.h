@@ -177,6 +177,21 @@ int ghicp_rigid_fit(int device, const double *s, const double *t, int n, double 
 int ghicp_rigid_fit_ex(int device, int solver, const double *s, const double *t, const double *tn, const double *w,
                        int n, double Rt[16]);
 
+/* ---- pre-processing on the GPU (BASELINE.json configs 4 / 5) ------------------------------
+ * The steps of test/ghicp_main.cpp:86-100 that produce the keypoints the loop consumes.  xyz = [n][3] float32 (PCL
+ * points are float32).  Where the reference's result is implementation-defined (unstable std::sort) or delegated to PCL,
+ * the canonical definitions documented in oracle/ghicp_prep_oracle.cpp apply. */
+/* CFilter::voxelfilter (include/filter.hpp:28-88): one point per occupied voxel — the one with the smallest index — in
+ * ascending voxel-id order, preceded by point 0 (the reference's phantom voxel-0 entries, :52 + :66).
+ * out_idx: capacity n + 1. */
+int ghicp_voxel_downsample(int device, const float *xyz, int n, float voxel_size, int *out_idx, int *n_out);
+/* CKeypointDetect::keypointDetectionBasedOnCurvature (include/keypoint_detect.hpp:27-51): radius PCA of every point
+ * (include/pca.h:133-250), pruneUnstablePoints (:132-147, ratio_max = 0.65 and min_pts = 20 in ghicp_main.cpp:96-97),
+ * non-maximum suppression by curvature (:149-191).  kp_idx (capacity n): keypoint indices in the reference's output order
+ * (descending curvature).  lam [n][3] (eigenvalues, descending), curvature [n], pt_num [n] may be NULL. */
+int ghicp_detect_keypoints(int device, const float *xyz, int n, float radius, float ratio_max, int min_pts, float nms_radius,
+                           int *kp_idx, int *n_kp, float *lam, double *curvature, int *pt_num);
+
 /* ---- multi-GPU (one process per GPU; source rows sharded, target replicated) ---------------- */
 /* 128-byte NCCL unique id; rank 0 creates it, the host runtime broadcasts it (torch.distributed,
  * MPI, a file ...). No NCCL symbol is touched unless these are called (world == 1 → never). */

@@ -84,6 +84,11 @@ def lib(omp=False):
     L.orc_rigid_fit_ex.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                    C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double)]
     L.orc_set_solver.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+    fpp = C.POINTER(C.c_float)
+    L.orc_voxel_downsample.argtypes = [fpp, C.c_int, C.c_float, C.POINTER(C.c_int)]
+    L.orc_pca_curvature.argtypes = [fpp, C.c_int, C.c_float, fpp, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    L.orc_detect_keypoints.argtypes = [fpp, C.c_int, fpp, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_float, C.c_int,
+                                       C.c_float, C.POINTER(C.c_int)]
     L.orc_set_km_backend.argtypes = [C.c_void_p]
     _libs[key] = L
     return L
@@ -153,6 +158,38 @@ def rigid_fit(S, T, solve_mode=0):
     Rt = np.zeros(16, np.float64)
     lib().orc_rigid_fit(_dp(S), _dp(T), S.shape[0], solve_mode, _dp(Rt))
     return Rt.reshape(4, 4).T.copy()
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def voxel_downsample(xyz, voxel_size):
+    """CFilter::voxelfilter (include/filter.hpp:28-88): indices of the kept points, in output order."""
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+    out = np.zeros(len(xyz) + 1, np.int32)
+    m = lib().orc_voxel_downsample(_fp(xyz), len(xyz), voxel_size, _ip(out))
+    return out[:m].copy()
+
+
+def pca_curvature(xyz, radius):
+    """Radius PCA (include/pca.h:133-250): (eigenvalues [n][3] float32 descending, curvature [n], neighbour counts)."""
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+    n = len(xyz)
+    lam, curv, cnt = np.zeros((n, 3), np.float32), np.zeros(n), np.zeros(n, np.int32)
+    lib().orc_pca_curvature(_fp(xyz), n, radius, _fp(lam), _dp(curv), _ip(cnt))
+    return lam, curv, cnt
+
+
+def detect_keypoints(xyz, radius, ratio_max=0.65, min_pts=20, nms_radius=None):
+    """CKeypointDetect::keypointDetectionBasedOnCurvature (include/keypoint_detect.hpp:27-51): keypoint indices in the
+    reference's output order (descending curvature), plus the per-point PCA results."""
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+    lam, curv, cnt = pca_curvature(xyz, radius)
+    kp = np.zeros(len(xyz), np.int32)
+    m = lib().orc_detect_keypoints(_fp(xyz), len(xyz), _fp(lam), _dp(curv), _ip(cnt), ratio_max, min_pts,
+                                   nms_radius if nms_radius is not None else radius, _ip(kp))
+    return kp[:m].copy(), lam, curv, cnt
 
 
 def rigid_fit_ex(S, T, solver, normals=None, weights=None):

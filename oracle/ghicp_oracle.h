@@ -128,6 +128,14 @@ int orc_rigid_fit_ex(int solver, const double *s, const double *t, const double 
 /* in-loop estimator of a context (0, 2 or 3); target_normals column-major M x 3 (solver 2) */
 int orc_set_solver(orc_ctx *c, int solver, const double *target_normals);
 
+/* Pre-processing ("next" row N1 of SURVEY.md §8f; ghicp_prep_oracle.cpp): voxel filter (include/filter.hpp:28-88),
+   radius PCA / curvature (include/pca.h:133-250), keypoint pruning + non-maximum suppression
+   (include/keypoint_detect.hpp:132-191).  xyz [n][3] float32.  PARITY UNPINNED (PCL absent), see the file header. */
+int orc_voxel_downsample(const float *xyz, int n, float voxel_size, int *out_idx /* cap n + 1 */);
+int orc_pca_curvature(const float *xyz, int n, float radius, float *lam /*[n][3]*/, double *curvature, int *pt_num);
+int orc_detect_keypoints(const float *xyz, int n, const float *lam, const double *curvature, const int *pt_num,
+                         float ratio_max, int min_pts, float nms_radius, int *kp_idx /* cap n */);
+
 typedef int (*orc_km_backend_fn)(const double *W, int n, double eps, int *match);
 void orc_set_km_backend(orc_km_backend_fn fn);
 

@@ -5,6 +5,7 @@
 #define GHICP_EMU_HOST 1
 #include "../../gh-icp_b200/csrc/ghicp_fpfh.cu"
 #include "../../gh-icp_b200/csrc/ghicp_solvers.cu"
+#include "../../gh-icp_b200/csrc/ghicp_prep.cu"
 
 #include <vector>
 
@@ -189,6 +190,16 @@ int emu_solve_alt_pairs(int solver, const double *S, const double *T, const doub
   memcpy(Rt, it.Rt, sizeof(double) * 16);
   *rmse_after = it.rmse_after;
   return 0;
+}
+
+// pre-processing pipelines on host arrays (the sort / scan plumbing is the C++ library here, CUB on the GPU)
+int emu_voxel_downsample(const float *xyz, int n, float voxel_size, int *out_idx, int *n_out) {
+  return (int)prep_voxel_downsample(nullptr, xyz, n, voxel_size, out_idx, n_out);
+}
+int emu_detect_keypoints(const float *xyz, int n, float radius, float ratio_max, int min_pts, float nms_radius, int *kp_idx,
+                         int *n_kp, float *lam, double *curvature, int *pt_num, int *nms_rounds) {
+  return (int)prep_detect_keypoints(nullptr, xyz, n, radius, ratio_max, min_pts, nms_radius, lam, curvature, pt_num, kp_idx, n_kp,
+                                    nms_rounds);
 }
 
 }  // extern "C"

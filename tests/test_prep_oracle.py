@@ -1,0 +1,132 @@
+"""CPU checks of the pre-processing oracle (oracle/ghicp_prep_oracle.cpp: voxel filter, radius PCA, keypoint pruning +
+non-maximum suppression) against independent numpy formulations, and of the product's pre-processing KERNELS run on the
+CPU through the host emulation shim (tests/harness) against that oracle — bit for bit."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+fp, ip, dp = C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_double)
+
+
+def scan_like_cloud(n, seed, extent=(20.0, 20.0, 5.0)):
+    """A crude 'scan': a ground plane, two walls, a box edge and clutter (float32 like PCL points)."""
+    rng = np.random.default_rng(seed)
+    P = rng.random((n, 3)) * np.asarray(extent)
+    q = n // 8
+    P[:3 * q, 2] = 0.02 * rng.standard_normal(3 * q)                        # ground
+    P[3 * q:5 * q, 0] = extent[0] * 0.5 + 0.02 * rng.standard_normal(2 * q)  # wall x = const
+    P[5 * q:6 * q, 1] = extent[1] * 0.25 + 0.02 * rng.standard_normal(q)     # wall y = const
+    P[6 * q:7 * q, 0] = 3.0 + 0.01 * rng.standard_normal(q)                  # a pole-like edge
+    P[6 * q:7 * q, 1] = 4.0 + 0.01 * rng.standard_normal(q)
+    return P.astype(np.float32)
+
+
+# ---- oracle vs independent numpy ---------------------------------------------------------------------------------------
+def test_voxel_filter_one_point_per_voxel_smallest_index_plus_phantom(orc):
+    P = scan_like_cloud(6000, 1)
+    v = np.float32(0.4)
+    idx = orc.voxel_downsample(P, float(v))
+    inv = np.float32(1.0) / v
+    mn = P.min(axis=0)
+    vox = np.floor((P - mn) * inv).astype(np.int64)                       # float32 arithmetic like include/filter.hpp:56-58
+    gap = P.max(axis=0) - mn
+    my, mz = int(np.ceil(gap[1] * inv) + 1), int(np.ceil(gap[2] * inv) + 1)
+    key = vox[:, 0] * (my * mz) + vox[:, 1] * mz + vox[:, 2]
+    assert idx[0] == 0                                                    # the reference's phantom voxel-0 entry
+    rest = idx[1:]
+    uk, first = np.unique(key, return_index=True)                         # np.unique: first occurrence = smallest index
+    keep = uk != 0
+    assert np.array_equal(rest, first[keep].astype(np.int32))             # ascending voxel id, smallest index per voxel
+    assert np.all(np.diff(key[rest]) > 0)
+
+
+def test_pca_eigenvalues_and_counts_match_numpy(orc):
+    P = scan_like_cloud(3000, 2)
+    r = 0.9
+    lam, curv, cnt = orc.pca_curvature(P, r)
+    Pd = P.astype(np.float64)
+    rng = np.random.default_rng(0)
+    for i in rng.integers(0, len(P), 60):
+        d = P - P[i]                                                       # float32 differences, like the KD-tree's metric
+        d2 = d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2]
+        nb = np.nonzero(d2 < np.float32(r) * np.float32(r))[0]
+        assert cnt[i] == len(nb)
+        if len(nb) >= 3:
+            w = np.linalg.eigvalsh(np.cov(Pd[nb].T))[::-1]
+            assert np.allclose(lam[i], w, rtol=2e-4, atol=2e-6)
+            assert curv[i] == pytest.approx(w[2] / w.sum(), rel=2e-3, abs=2e-6)
+
+
+def test_keypoints_satisfy_the_greedy_nms_definition(orc):
+    P = scan_like_cloud(5000, 3)
+    kp, lam, curv, cnt = orc.detect_keypoints(P, 1.0, 0.65, 20, 1.5)
+    assert len(kp) > 10
+    with np.errstate(invalid="ignore", divide="ignore"):
+        ok = (lam[:, 1] / lam[:, 0] < 0.65) & (lam[:, 2] / lam[:, 1] < 0.65) & (cnt > 20)
+    assert ok[kp].all()
+    assert np.all(np.diff(curv[kp]) <= 0)                                  # emitted best first
+    K = P[kp].astype(np.float64)
+    D = np.linalg.norm(K[:, None] - K[None], axis=2) + 10 * np.eye(len(kp))
+    assert D.min() >= 1.5 - 1e-5                                           # no two keypoints within the NMS radius
+    cand = np.nonzero(ok)[0]
+    rest = np.setdiff1d(cand, kp)
+    for i in rest[:300]:                                                   # every rejected candidate lost to a better keypoint
+        d = np.linalg.norm(P[kp].astype(np.float64) - P[i].astype(np.float64), axis=1)
+        near = kp[d < 1.5 + 1e-6]
+        assert len(near) and curv[near].max() >= curv[i]
+
+
+# ---- product kernels on the CPU (emulation) vs the oracle: bit for bit -----------------------------------------------------
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    out = tmp_path_factory.mktemp("emu_prep") / "libkernel_logic_harness.so"
+    src = os.path.join(ROOT, "tests", "harness", "kernel_logic_harness.cpp")
+    r = subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-DGHICP_EMU_HOST",
+                        "-I" + os.path.join(ROOT, "tests", "harness", "cuda_emu"), "-x", "c++", "-shared", "-o", str(out), src],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    L = C.CDLL(str(out))
+    L.emu_voxel_downsample.argtypes = [fp, C.c_int, C.c_float, ip, ip]
+    L.emu_detect_keypoints.argtypes = [fp, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, ip, ip, fp, dp, ip, ip]
+    return L
+
+
+@pytest.mark.parametrize("n,voxel,seed", [(5000, 0.4, 4), (777, 0.05, 5), (1, 1.0, 6), (300, 50.0, 7)])
+def test_emulated_voxel_filter_equals_oracle(orc, emu, n, voxel, seed):
+    P = scan_like_cloud(max(n, 8), seed)[:n]
+    out, m = np.zeros(n + 1, np.int32), C.c_int(0)
+    assert emu.emu_voxel_downsample(P.ctypes.data_as(fp), n, voxel, out.ctypes.data_as(ip), C.byref(m)) == 0
+    assert np.array_equal(out[:m.value], orc.voxel_downsample(P, voxel))
+
+
+@pytest.mark.parametrize("n,radius,nms,seed", [(4000, 1.0, 1.5, 8), (1500, 0.6, 0.6, 9), (600, 3.0, 0.3, 10)])
+def test_emulated_keypoint_detection_equals_oracle(orc, emu, n, radius, nms, seed):
+    P = scan_like_cloud(n, seed)
+    kp, m, rounds = np.zeros(n, np.int32), C.c_int(0), C.c_int(0)
+    lam, curv, cnt = np.zeros((n, 3), np.float32), np.zeros(n), np.zeros(n, np.int32)
+    rc = emu.emu_detect_keypoints(P.ctypes.data_as(fp), n, radius, 0.65, 20, nms, kp.ctypes.data_as(ip), C.byref(m),
+                                  lam.ctypes.data_as(fp), curv.ctypes.data_as(dp), cnt.ctypes.data_as(ip), C.byref(rounds))
+    assert rc == 0
+    okp, olam, ocurv, ocnt = orc.detect_keypoints(P, radius, 0.65, 20, nms)
+    assert np.array_equal(cnt, ocnt)
+    assert np.array_equal(lam, olam) and np.array_equal(curv, ocurv)      # same sums, same Jacobi: identical bits
+    assert np.array_equal(kp[:m.value], okp)
+    assert 1 <= rounds.value <= 64
+
+
+def test_emulated_pipeline_downsample_then_keypoints(orc, emu):
+    P = scan_like_cloud(20000, 11)
+    out, m = np.zeros(len(P) + 1, np.int32), C.c_int(0)
+    emu.emu_voxel_downsample(P.ctypes.data_as(fp), len(P), 0.3, out.ctypes.data_as(ip), C.byref(m))
+    D = np.ascontiguousarray(P[out[:m.value]])
+    n = len(D)
+    kp, k, rounds = np.zeros(n, np.int32), C.c_int(0), C.c_int(0)
+    lam, curv, cnt = np.zeros((n, 3), np.float32), np.zeros(n), np.zeros(n, np.int32)
+    emu.emu_detect_keypoints(D.ctypes.data_as(fp), n, 1.0, 0.65, 20, 1.5, kp.ctypes.data_as(ip), C.byref(k),
+                             lam.ctypes.data_as(fp), curv.ctypes.data_as(dp), cnt.ctypes.data_as(ip), C.byref(rounds))
+    okp, _, _, _ = orc.detect_keypoints(D, 1.0, 0.65, 20, 1.5)
+    assert np.array_equal(kp[:k.value], okp) and len(okp) > 20

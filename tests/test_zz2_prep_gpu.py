@@ -1,0 +1,64 @@
+"""GPU tests of the pre-processing kernels (gh-icp_b200/csrc/ghicp_prep.cu: voxel filter, radius PCA, keypoint pruning +
+non-maximum suppression) through the C ABI against the oracle — bit for bit, the canonical definitions of
+oracle/ghicp_prep_oracle.cpp on both sides.  Written after round 1's GPU budget was spent (kernel logic verified on the CPU
+through the emulation shim, tests/test_prep_oracle.py); the file name sorts last so that a failure here cannot mask the
+verified suites under `pytest -x`."""
+import numpy as np
+import pytest
+
+from test_prep_oracle import scan_like_cloud
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n,voxel,seed", [(5000, 0.4, 4), (777, 0.05, 5), (1, 1.0, 6), (300, 50.0, 7), (200000, 0.1, 8)])
+def test_voxel_filter_equals_oracle(g, orc, n, voxel, seed):
+    P = scan_like_cloud(max(n, 8), seed)[:n]
+    assert np.array_equal(g.voxel_downsample(P, voxel), orc.voxel_downsample(P, voxel))
+
+
+@pytest.mark.parametrize("n,radius,nms,seed", [(4000, 1.0, 1.5, 8), (1500, 0.6, 0.6, 9), (600, 3.0, 0.3, 10), (60000, 0.5, 0.8, 11)])
+def test_keypoint_detection_equals_oracle(g, orc, n, radius, nms, seed):
+    P = scan_like_cloud(n, seed)
+    kp, lam, curv, cnt = g.detect_keypoints(P, radius, 0.65, 20, nms)
+    okp, olam, ocurv, ocnt = orc.detect_keypoints(P, radius, 0.65, 20, nms)
+    assert np.array_equal(cnt, ocnt)
+    assert np.array_equal(lam, olam) and np.array_equal(curv, ocurv)
+    assert np.array_equal(kp, okp)
+
+
+def test_pipeline_raw_cloud_to_registration(g, orc):
+    """test/ghicp_main.cpp:86-151 end to end on the GPU: downsample both clouds, detect keypoints, register the
+    keypoints (no feature, NN) — every stage equal to the oracle's."""
+    T = scan_like_cloud(40000, 21)
+    R = g.synth.rot_xyz_deg(0.5, -0.3, 1.5)
+    S = ((T.astype(np.float64) - [0.3, -0.2, 0.1]) @ R).astype(np.float32)      # R (s) + t = target
+    clouds = {}
+    for name, P in (("T", T), ("S", S)):
+        idx = g.voxel_downsample(P, 0.25)
+        assert np.array_equal(idx, orc.voxel_downsample(P, 0.25))
+        D = np.ascontiguousarray(P[idx])
+        kp, _, _, _ = g.detect_keypoints(D, 1.0, 0.65, 20, 1.2)
+        okp, _, _, _ = orc.detect_keypoints(D, 1.0, 0.65, 20, 1.2)
+        assert np.array_equal(kp, okp) and len(kp) >= 10
+        clouds[name] = (D, D[kp].astype(np.float64))
+    KS, KT = clouds["S"][1], clouds["T"][1]
+    ext = clouds["S"][0].max(axis=0) - clouds["S"][0].min(axis=0)              # bbx of the down-sampled source (:91-93)
+    bbx = float(np.float32(ext[0] + ext[1] + ext[2]))
+    Kp = g.Keypoints().setCoordinate(KS, KT)
+    Ef = g.Energyfunction().init(Kp.kps_num, Kp.kpt_num, bbx)
+    reg = g.GHRegistration(Kp, Ef, g.FT_NONE, g.CT_NN, max_iter=50)
+    o = orc.Oracle(orc.FT_NONE, orc.CT_NN, bbx_magnitude=bbx, solve_mode=1, max_iter=50)
+    o.set_keypoints(KS, KT)
+    for it in range(50):
+        a, b = reg.iterate(), o.iterate()
+        assert np.array_equal(reg.pairs()[0], o.pairs()[0]) and np.array_equal(reg.pairs()[1], o.pairs()[1]), it
+        if a.converged or b.converged:
+            break
+
+
+def test_prep_error_paths(g):
+    with pytest.raises(g.GhicpError):
+        g.voxel_downsample(np.zeros((10, 3), np.float32), 0.0)
+    with pytest.raises(g.GhicpError):
+        g.detect_keypoints(np.zeros((10, 3), np.float32), -1.0)
