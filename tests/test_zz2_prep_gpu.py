@@ -62,3 +62,36 @@ def test_prep_error_paths(g):
         g.voxel_downsample(np.zeros((10, 3), np.float32), 0.0)
     with pytest.raises(g.GhicpError):
         g.detect_keypoints(np.zeros((10, 3), np.float32), -1.0)
+
+
+def test_command_line_driver_registers_two_files(g, orc, tmp_path):
+    """gh-icp_b200/cxx/ghicp_cli with the reference's argument list (test/ghicp_main.cpp:56-79) on two .pcd files,
+    feature N, correspondence N: the transform equals the one of the same pipeline driven through Python + the oracle."""
+    import os
+    import subprocess
+    from test_cli_io import CLI, ROOT, read_pcd_binary, write_pcd
+    assert subprocess.run(["make", "-C", os.path.join(ROOT, "gh-icp_b200", "cxx"), "ghicp_cli"], capture_output=True).returncode == 0
+    T = scan_like_cloud(40000, 21)
+    R = g.synth.rot_xyz_deg(0.5, -0.3, 1.5)
+    S = ((T.astype(np.float64) - [0.3, -0.2, 0.1]) @ R).astype(np.float32)
+    ft, fs, fr = str(tmp_path / "t.pcd"), str(tmp_path / "s.pcd"), str(tmp_path / "reg.pcd")
+    write_pcd(ft, T, True); write_pcd(fs, S, True)
+    r = subprocess.run([CLI, ft, fs, fr, "N", "N", "0.25", "1.0", "1.2", "1.1", "0.1", "6", "0.5", "0"], capture_output=True, text=True,
+                       env=dict(os.environ, GHICP_MAX_ITER="50"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    Rt = np.loadtxt(fr + ".Rt.txt")
+    # the same pipeline through the oracle
+    K = {}
+    for name, P in (("T", T), ("S", S)):
+        D = np.ascontiguousarray(P[orc.voxel_downsample(P, 0.25)])
+        kp, _, _, _ = orc.detect_keypoints(D, 1.0, 0.65, 20, 1.2)
+        K[name] = (D, D[kp].astype(np.float64))
+    ext = K["S"][0].max(axis=0) - K["S"][0].min(axis=0)
+    o = orc.Oracle(orc.FT_NONE, orc.CT_NN, bbx_magnitude=float(np.float32(ext[0] + ext[1] + ext[2])), solve_mode=1, max_iter=50)
+    o.set_keypoints(K["S"][1], K["T"][1])
+    Ro, _, rc = o.run()
+    assert rc == 0
+    assert g.synth.rot_angle(Rt[:3, :3], Ro[:3, :3]) < 1e-4 and np.linalg.norm(Rt[:3, 3] - Ro[:3, 3]) < 1e-3
+    reg = read_pcd_binary(fr)
+    Rf, tf = Rt[:3, :3].astype(np.float32), Rt[:3, 3].astype(np.float32)
+    assert np.allclose(reg, S @ Rf.T + tf, atol=1e-4)       # pcl::transformPointCloud with the float32 matrix (:153)
