@@ -494,21 +494,26 @@ __global__ void __launch_bounds__(FF_THREADS) k_ff_sweep(const FfArgs a) {
     if (PRE && tid < FF_RB) s_guess[tid] = ~0ull;
     __syncthreads();
     float fsum = 0.f;
-    for (int r = 0; r < nb; ++r) {
-      asm volatile("" ::: "memory");   // keep the records in shared memory (no hoisting into registers / local memory)
-      const float *rec = s_rec[r];
+    // one pair: the filter value and what the rare path needs
+    auto eval = [&](const float *rec, float &cd32, float &dist, float &fd, float &l) {
       const float dx = (rec[33] - txh) + (rec[36] - txl);
       const float dy = (rec[34] - tyh) + (rec[37] - tyl);
       const float dz = (rec[35] - tzh) + (rec[38] - tzl);
       const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-      float dot = 0.f;
+      // three independent partial sums: the 33-term FFMA chain would otherwise be one 33-deep dependency per row
+      float d0 = 0.f, d1 = 0.f, d2s = 0.f;
 #pragma unroll
-      for (int k = 0; k < 33; ++k) dot = fmaf(rec[k], ht[k], dot);
-      const float fd = fmaxf(fabsf(dot), 1e-30f);
-      const float dist = a.scalef * ff_sqrt(d2);   // ED (src/ghicp_reg.cpp:122) in FP32
-      const float l = ff_lg2(fd);
-      float cd32 = dist * ff_ex2(-a.exf * l);
-      if (!valid) cd32 = INF;
+      for (int k = 0; k < 11; ++k) {
+        d0 = fmaf(rec[k], ht[k], d0);
+        d1 = fmaf(rec[11 + k], ht[11 + k], d1);
+        d2s = fmaf(rec[22 + k], ht[22 + k], d2s);
+      }
+      fd = fmaxf(fabsf((d0 + d1) + d2s), 1e-30f);
+      dist = a.scalef * ff_sqrt(d2);   // ED (src/ghicp_reg.cpp:122) in FP32
+      l = ff_lg2(fd);
+      cd32 = valid ? dist * ff_ex2(-a.exf * l) : INF;
+    };
+    auto process = [&](int r, const float *rec, float cd32, float dist, float fd, float l) {
       if (PRE) {
         // warp argmin of the row: REDUX on the (non-negative) float bits, first lane holding the minimum
         const unsigned bits = __float_as_uint(cd32);
@@ -525,6 +530,17 @@ __global__ void __launch_bounds__(FF_THREADS) k_ff_sweep(const FfArgs a) {
         if (valid && lb <= rec[39]) ff_slow(a, 0, ib + r, j, dist, fd, rec[39]);
         if (COLS && valid && lb <= thr_c) ff_slow(a, 1, ib + r, j, dist, fd, thr_c);
       }
+    };
+    // two rows per step: two independent instruction streams for the scheduler (nb is uniform across the CTA)
+    for (int r = 0; r < nb; r += 2) {
+      asm volatile("" ::: "memory");   // keep the records in shared memory (no hoisting into registers / local memory)
+      const bool has_b = r + 1 < nb;
+      const float *rec_a = s_rec[r], *rec_b = s_rec[has_b ? r + 1 : r];
+      float cd_a, dist_a, fd_a, l_a, cd_b, dist_b, fd_b, l_b;
+      eval(rec_a, cd_a, dist_a, fd_a, l_a);
+      eval(rec_b, cd_b, dist_b, fd_b, l_b);
+      process(r, rec_a, cd_a, dist_a, fd_a, l_a);
+      if (has_b) process(r + 1, rec_b, cd_b, dist_b, fd_b, l_b);
     }
     if (PRE) {
       __syncthreads();
