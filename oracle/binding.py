@@ -34,7 +34,8 @@ def build(force=False):
     need = force or not os.path.exists(os.path.join(_HERE, "liboracle.so")) \
         or not os.path.exists(os.path.join(_HERE, "liboracle_omp.so"))
     if need or (os.path.isdir("/root/reference") and
-                not os.path.exists(os.path.join(_HERE, "_ref", "libkm_ref.so"))):
+                not (os.path.exists(os.path.join(_HERE, "_ref", "libkm_ref.so")) and
+                     os.path.exists(os.path.join(_HERE, "_ref", "libfeat_ref.so")))):
         subprocess.run(["make", "-C", _HERE, "all"], check=True, capture_output=True)
 
 
@@ -111,6 +112,37 @@ def ref_km_lib():
                                      C.POINTER(C.c_int), C.POINTER(C.c_double)]
     _libs["ref"] = R
     return R
+
+
+def ref_feat_lib():
+    """oracle/_ref/libfeat_ref.so = the reference's own src/stereo_binary_feature.cpp + include/fpfh.hpp, or None."""
+    if "feat" in _libs:
+        return _libs["feat"]
+    build()
+    p = os.path.join(_HERE, "_ref", "libfeat_ref.so")
+    if not os.path.exists(p):
+        _libs["feat"] = None
+        return None
+    R = C.CDLL(p)
+    R.featref_hamming.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    R.featref_set_bits.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_int, C.c_void_p]
+    R.featref_get_bit.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    R.featref_fpfh_distance.restype = C.c_float
+    R.featref_fpfh_distance.argtypes = [C.c_void_p, C.c_void_p]
+    _libs["feat"] = R
+    return R
+
+
+def hamming(a, b):
+    """The oracle's restatement of StereoBinaryFeature::hammingDistance (src/stereo_binary_feature.cpp:87-104)."""
+    a = np.ascontiguousarray(a, dtype=np.uint8); b = np.ascontiguousarray(b, dtype=np.uint8)
+    return lib().orc_hamming(a.ctypes.data, b.ctypes.data, len(a))
+
+
+def fpfh_distance(h1, h2):
+    """The oracle's restatement of FPFHfeature::compute_fpfh_distance (include/fpfh.hpp:135-165)."""
+    h1 = np.ascontiguousarray(h1, dtype=np.float32); h2 = np.ascontiguousarray(h2, dtype=np.float32)
+    return float(lib().orc_fpfh_distance(h1.ctypes.data, h2.ctypes.data))
 
 
 def km_solve(W, eps=0.01, backend="port"):

@@ -32,8 +32,14 @@
  *     algorithm is restated (orc_rigid_fit).  PARITY UNPINNED for this stage: no golden vector
  *     exists in the reference; it is cross-checked against an independent numpy float64 Kabsch in
  *     tests/.
- *   - ED/FD/CD/NN/NNR: no golden vectors exist in the reference (it has no tests); these are short
- *     scalar loops restated verbatim.  PARITY UNPINNED beyond restatement.
+ *   - FD (calFD_BSC / calFD_FPFH per-pair kernels): PINNED.  StereoBinaryFeature::hammingDistance / byteBitsLookUp /
+ *     setNthBitValue (src/stereo_binary_feature.cpp:16-104, include/stereo_binary_feature.h:130-146) and
+ *     FPFHfeature::compute_fpfh_distance (include/fpfh.hpp:135-165) are compiled VERBATIM from /root/reference into
+ *     oracle/_ref/libfeat_ref.so (PCL / boost / Eigen replaced by declaration-only stubs, oracle/stub); orc_hamming and
+ *     orc_fpfh_distance are checked against them bit for bit, live and through tests/golden/feat_golden.npz.
+ *   - ED/CD/NN/NNR and the loop glue: no golden vectors exist in the reference (it has no tests) and these live inside
+ *     GHRegistration, which needs PCL to compile; they are short scalar loops restated verbatim.  PARITY UNPINNED beyond
+ *     restatement (tests/golden/loop_golden.npz pins the restatement against drift only).
  *
  * Build: oracle/Makefile  (g++ -O3 -std=c++17 -ffp-contract=off, no -march: IEEE double, no FMA).
  */

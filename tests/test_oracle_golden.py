@@ -182,3 +182,66 @@ def test_oracle_reproduces_loop_fixture(orc, scratch_cwd, name):
         assert st.penalty == pytest.approx(float(c["penalty"][it]), rel=1e-12)
     assert st.converged == 1
     assert np.allclose(np.array(st.Rt_tillnow), c["Rt_final"], atol=1e-12)
+
+
+# ---- the reference's own per-pair feature-distance code (oracle/_ref/libfeat_ref.so) and its committed outputs ---------------
+def load_feat_golden():
+    return np.load(os.path.join(GOLD, "feat_golden.npz"))
+
+
+@pytest.mark.parametrize("bits", [441, 672, 9, 64, 2048])
+def test_oracle_fd_bsc_equals_reference_hamming_fixture(orc, bits):
+    """calFD_BSC (src/ghicp_reg.cpp:143-200) of the oracle == min over variants of the Hamming distances the REFERENCE's own
+    StereoBinaryFeature::hammingDistance produced (fixture generated by tests/golden/make_feat_golden.py)."""
+    z = load_feat_golden()
+    S, T, H = z[f"bsc{bits}/S"], z[f"bsc{bits}/T"], z[f"bsc{bits}/H"]
+    _, V, N, M = (int(v) for v in z[f"bsc{bits}/meta"])
+    for i in range(N):
+        for j in range(M):
+            for v in range(V):
+                assert orc.hamming(S[v, i], T[j]) == H[v, i, j]
+    for dof, nv in ((6, min(V, 4)), (4, 2)):
+        if V < (4 if dof == 6 else 2):
+            continue
+        o = orc.Oracle(orc.FT_BSC, orc.CT_NN, dof=dof, bbx_magnitude=10.0)
+        o.set_keypoints(np.zeros((N, 3)), np.zeros((M, 3)))
+        o.set_bsc(S, T, bits)
+        o.build_fd()
+        assert np.array_equal(o.fd(), H[:nv].min(axis=0).astype(np.float64))
+
+
+def test_oracle_fd_fpfh_equals_reference_fixture(orc):
+    z = load_feat_golden()
+    fs, ft, D = z["fpfh/S"], z["fpfh/T"], z["fpfh/D"]
+    o = orc.Oracle(orc.FT_FPFH, orc.CT_NN, bbx_magnitude=10.0)
+    o.set_keypoints(np.zeros((len(fs), 3)), np.zeros((len(ft), 3)))
+    o.set_fpfh(fs, ft)
+    o.build_fd()
+    assert np.array_equal(o.fd().astype(np.float32), D, equal_nan=True)     # bit-identical floats, NaN where the reference gives 0/0
+    assert np.isnan(D[:, 12]).all() and D[10, 11] == pytest.approx(1.0, abs=1e-6)
+
+
+def test_reference_feature_code_live(orc):
+    """When /root/reference is present (build container): the oracle against the reference's own functions on fresh random
+    inputs, and the descriptor bit layout (setNthBitValue: bit k -> byte k/8, bit k%8) the synthetic generator assumes."""
+    R = orc.ref_feat_lib()
+    if R is None:
+        pytest.skip("oracle/_ref/libfeat_ref.so not built (no /root/reference here)")
+    import ctypes as C
+    import ghicp_b200 as g
+    rng = np.random.default_rng(5)
+    for bits in (441, 672, 13):
+        B = (bits + 7) // 8
+        for _ in range(50):
+            a = rng.integers(0, 256, B, dtype=np.uint8); b = rng.integers(0, 256, B, dtype=np.uint8)
+            assert orc.hamming(a, b) == R.featref_hamming(a.ctypes.data, b.ctypes.data, bits)
+        bits01 = rng.random(bits) < 0.4
+        pos = np.nonzero(bits01)[0].astype(np.int32)
+        out = np.zeros(B, np.uint8)
+        R.featref_set_bits(bits, pos.ctypes.data_as(C.POINTER(C.c_int)), len(pos), out.ctypes.data)
+        assert np.array_equal(out, g.synth.pack_bits(bits01))
+        assert all(R.featref_get_bit(out.ctypes.data, bits, int(k)) == int(bits01[k]) for k in range(bits))
+    for _ in range(200):
+        h1 = (rng.gamma(0.6, 1.0, 33) * 20).astype(np.float32); h2 = (rng.gamma(0.6, 1.0, 33) * 20).astype(np.float32)
+        a = np.float32(orc.fpfh_distance(h1, h2)); b = np.float32(R.featref_fpfh_distance(h1.ctypes.data, h2.ctypes.data))
+        assert a == b

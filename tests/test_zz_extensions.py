@@ -257,3 +257,30 @@ def test_cuda_path_reproduces_committed_loop_fixture(g, scratch_cwd, name):
     if ct != g.CT_KM and mismatched == 0:
         Ra, Rb = reg.Rt_tillnow(), np.array(c["Rt_final"]).reshape(4, 4).T
         assert g.synth.rot_angle(Ra[:3, :3], Rb[:3, :3]) < 1e-4 and np.linalg.norm(Ra[:3, 3] - Rb[:3, 3]) < 1e-3
+
+
+# ---- the reference's own per-pair feature distances (tests/golden/feat_golden.npz) -------------------------------------
+@pytest.mark.parametrize("bits", [441, 672, 9, 64, 2048])
+def test_fd_bsc_equals_reference_hamming_fixture(g, bits):
+    """The FD build (tcgen05 / POPC) against Hamming distances produced by the REFERENCE's own
+    StereoBinaryFeature::hammingDistance (compiled verbatim in the build container, outputs committed)."""
+    from test_oracle_golden import load_feat_golden
+    z = load_feat_golden()
+    S, T, H = z[f"bsc{bits}/S"], z[f"bsc{bits}/T"], z[f"bsc{bits}/H"]
+    _, V, N, M = (int(v) for v in z[f"bsc{bits}/meta"])
+    for dof, nv in ((6, 4), (4, 2)):
+        if V < nv:
+            continue
+        Kp = g.Keypoints().setCoordinate(np.zeros((N, 3)), np.zeros((M, 3))).setBSCfeature(S, T, bits)
+        reg = g.GHRegistration(Kp, g.Energyfunction().init(N, M, 10.0), g.FT_BSC, g.CT_NN, dof_type=dof)
+        assert np.array_equal(reg.fd(), H[:nv].min(axis=0).astype(np.float64))
+
+
+@pytest.mark.parametrize("mf", [1, -1])
+def test_fd_fpfh_equals_reference_fixture(g, mf):
+    from test_oracle_golden import load_feat_golden
+    z = load_feat_golden()
+    fs, ft, D = z["fpfh/S"], z["fpfh/T"], z["fpfh/D"]
+    Kp = g.Keypoints().setCoordinate(np.zeros((len(fs), 3)), np.zeros((len(ft), 3))).setFPFHfeature(fs, ft)
+    reg = g.GHRegistration(Kp, g.Energyfunction().init(len(fs), len(ft), 10.0), g.FT_FPFH, g.CT_NN, fpfh_matrix_free=mf)
+    assert np.array_equal(reg.fd().astype(np.float32), D, equal_nan=True)
