@@ -162,15 +162,62 @@ def _oracle_run(g, wl, ct, threads, n, iters, use_ref):
     return float(np.median(t_cost)), float(np.median(t_corr)), float(np.median(t_solve)), t_fd
 
 
+def _reference_run(g, wl, ct, n, iters):
+    """The REFERENCE's own GHRegistration loop (src/ghicp_reg.cpp + km.cpp + stereo_binary_feature.cpp compiled verbatim into
+    oracle/_ref/libghreg_ref.so; single-threaded like the reference) on an n x n sample: (median ms per iteration, FD build s)."""
+    import oracle
+    import tempfile
+    sc = make_scene(g, wl, n_override=n)
+    cwd = os.getcwd()
+    os.chdir(tempfile.mkdtemp())  # Km::output writes Corres.txt (src/km.cpp:148)
+    try:
+        r = oracle.Reference(FT[wl["ft"]], CT[ct], bbx_magnitude=sc.bbx_magnitude, solve_mode=0)
+        r.set_keypoints(sc.S, sc.T)
+        if wl["ft"] == "bsc":
+            r.set_bsc(sc.bsc_s, sc.bsc_t, sc.bits)
+        elif wl["ft"] == "fpfh":
+            r.set_fpfh(sc.fpfh_s, sc.fpfh_t)
+        t0 = time.perf_counter()
+        r.build_fd()
+        t_fd = time.perf_counter() - t0
+        ts = []
+        for _ in range(iters):
+            t0 = time.perf_counter()
+            r.iterate()
+            ts.append((time.perf_counter() - t0) * 1e3)
+    finally:
+        os.chdir(cwd)
+    return float(np.median(ts)), t_fd
+
+
 def cpu_baseline(g, wl, threads, n_sample, iters=2):
-    """The reference's CPU path on a bounded sample: O(N*M) stages (calED/calCD/scans) timed at n_cost
-    (threads as given), KM timed at n_sample with the reference's own single-threaded src/km.cpp when
-    oracle/_ref is built; both extrapolated to the workload size (cost ~ N*M, KM ~ n^3, solve ~ n)."""
+    """The reference's CPU path on a bounded sample, extrapolated to the workload size (cost / scans ~ N*M, KM ~ n^3, solve ~ n;
+    the reference cannot run 50k x 50k: 24*N*M B of doubles + O(n^3) KM).
+    kind "reference": the reference's OWN compiled loop (oracle/_ref/libghreg_ref.so, one thread — it is single-threaded);
+    kind "port": the oracle restatement (+ OpenMP on the O(N*M) loops when threads > 1) where oracle/_ref is not available."""
     import oracle
     oracle.build()
     km = wl["ct"] == "km"
-    use_ref = oracle.ref_km_lib() is not None and km
     N = wl["N"]
+    if oracle.ref_ghreg_lib() is not None:
+        n_cost = min(N, 4000)
+        nn_ct = "nn" if km else wl["ct"]
+        t_iter, t_fd = _reference_run(g, wl, nn_ct, n_cost, iters)
+        parts = [f"reference loop ({nn_ct.upper()}: calED + calCD + scan + solve) {t_iter:.1f} ms / iteration at {n_cost}x{n_cost}"]
+        full_ms = t_iter * (N / n_cost) ** 2
+        if km:
+            n_km = min(n_sample, N)
+            t_km, _ = _reference_run(g, wl, "km", n_km, iters)
+            t_nn_small, _ = _reference_run(g, wl, "nn", n_km, iters)
+            corr = max(t_km - t_nn_small, 0.0)
+            full_ms += corr * (N / n_km) ** 3
+            parts.append(f"findcorrespondenceKM (graph copies + src/km.cpp) {corr:.1f} ms at {n_km}x{n_km}")
+        sample = ("; ".join(parts) + f"; one-time calFD {t_fd:.2f} s at {n_cost}x{n_cost}; median of {iters} iterations; the "
+                  f"reference's own src/ghicp_reg.cpp + km.cpp compiled verbatim (1 thread: it is single-threaded; PCL's SVD "
+                  f"call delegated to the oracle); extrapolated to {N}x{wl['M']} with cost/scan ~ N*M, KM ~ n^3")
+        return dict(value=1000.0 / full_ms, unit="iterations/s", cores=1, kind="reference", sample=sample,
+                    ms_per_step_sample=t_iter, ms_per_step_extrapolated=full_ms)
+    use_ref = oracle.ref_km_lib() is not None and km
     n_cost = min(N, 6000)
     cost, scan, solve, t_fd = _oracle_run(g, wl, "nn" if km else wl["ct"], threads, n_cost, iters, False)
     parts = [f"cost stage (calED+calCD) {cost:.1f} ms at {n_cost}x{n_cost} on {threads} thread(s)"]
@@ -223,7 +270,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        n_s = args.cpu_sample or (1500 if wl["ct"] == "km" else min(wl["N"], 6000))
+        n_s = args.cpu_sample or (2000 if wl["ct"] == "km" else min(wl["N"], 6000))
         t0 = time.perf_counter()
         cb = cpu_baseline(g, wl, threads=min(ncores, 32), n_sample=min(n_s, wl["N"]), iters=max(1, min(args.steps, 2)))
         line = {"impl": "reference", "metric": "ICP iterations/sec", "value": cb["value"], "unit": "iterations/s",
@@ -369,7 +416,7 @@ def main():
         "roofline": roofline,
     }
     if not args.no_cpu:
-        n_s = args.cpu_sample or (1500 if wl["ct"] == "km" else min(wl["N"], 6000))
+        n_s = args.cpu_sample or (2000 if wl["ct"] == "km" else min(wl["N"], 6000))
         cb = cpu_baseline(g, wl, threads=1, n_sample=min(n_s, wl["N"]))
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line))

@@ -34,8 +34,8 @@ def build(force=False):
     need = force or not os.path.exists(os.path.join(_HERE, "liboracle.so")) \
         or not os.path.exists(os.path.join(_HERE, "liboracle_omp.so"))
     if need or (os.path.isdir("/root/reference") and
-                not (os.path.exists(os.path.join(_HERE, "_ref", "libkm_ref.so")) and
-                     os.path.exists(os.path.join(_HERE, "_ref", "libfeat_ref.so")))):
+                not all(os.path.exists(os.path.join(_HERE, "_ref", f))
+                        for f in ("libkm_ref.so", "libfeat_ref.so", "libghreg_ref.so"))):
         subprocess.run(["make", "-C", _HERE, "all"], check=True, capture_output=True)
 
 
@@ -131,6 +131,120 @@ def ref_feat_lib():
     R.featref_fpfh_distance.argtypes = [C.c_void_p, C.c_void_p]
     _libs["feat"] = R
     return R
+
+
+class GhrefStats(C.Structure):
+    _fields_ = [("iteration", C.c_int), ("cor", C.c_int), ("converged", C.c_int), ("penalty", C.c_double), ("rmse", C.c_double),
+                ("rmse_after", C.c_double), ("fdm", C.c_double), ("fdstd", C.c_double), ("iou", C.c_double),
+                ("para1", C.c_double), ("para2", C.c_double), ("energy", C.c_double), ("Rt", C.c_double * 16),
+                ("Rt_tillnow", C.c_double * 16)]
+
+
+def ref_ghreg_lib():
+    """oracle/_ref/libghreg_ref.so = the reference's own src/ghicp_reg.cpp (+ km.cpp, stereo_binary_feature.cpp), or None."""
+    if "ghreg" in _libs:
+        return _libs["ghreg"]
+    build()
+    p = os.path.join(_HERE, "_ref", "libghreg_ref.so")
+    if not os.path.exists(p):
+        _libs["ghreg"] = None
+        return None
+    R = C.CDLL(p)
+    dp, fp = C.POINTER(C.c_double), C.POINTER(C.c_float)
+    R.ghref_create.restype = C.c_void_p
+    R.ghref_create.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_float] * 7 + [dp, C.c_int, dp, C.c_int, C.c_void_p, C.c_int,
+                                                                                C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    R.ghref_destroy.argtypes = [C.c_void_p]
+    R.ghref_build_fd.argtypes = [C.c_void_p]
+    R.ghref_iterate.argtypes = [C.c_void_p, C.POINTER(GhrefStats)]
+    R.ghref_get_pairs_xyz.argtypes = [C.c_void_p, dp, dp]
+    R.ghref_get_source.argtypes = [C.c_void_p, dp]
+    R.ghref_fd_row.restype = dp; R.ghref_fd_row.argtypes = [C.c_void_p, C.c_int]
+    R.ghref_cd_row.restype = dp; R.ghref_cd_row.argtypes = [C.c_void_p, C.c_int]
+    R.ghref_run.argtypes = [C.c_void_p, dp]
+    R.ghref_set_solve_mode.argtypes = [C.c_int]
+    _libs["ghreg"] = R
+    return R
+
+
+class Reference:
+    """The REFERENCE's own GHRegistration (src/ghicp_reg.cpp compiled verbatim, see oracle/ghreg_ref_shim.cpp), stepped one
+    loop body at a time.  Same interface as Oracle where it matters for tests.  solve_mode selects which of the oracle's
+    summation modes stands in for PCL's TransformationEstimationSVD (0 = PCL-like float32 sums)."""
+
+    def __init__(self, feature_type, corr_type, dof=6, bbx_magnitude=1.0, nonmax=1.0, adjust_ratio=1.1, adjust_step=0.1,
+                 estimated_iou=0.5, converge_t=0.02, converge_r=0.02, solve_mode=0):
+        self.R = ref_ghreg_lib()
+        if self.R is None:
+            raise RuntimeError("oracle/_ref/libghreg_ref.so not built (needs /root/reference)")
+        self.args = (feature_type, corr_type, dof, bbx_magnitude, nonmax, adjust_ratio, adjust_step, estimated_iou, converge_t,
+                     converge_r)
+        self.solve_mode = solve_mode
+        self.ctx = None
+        self.S = self.T = self.bsc = self.fpfh = None
+
+    def set_keypoints(self, S, T):
+        self.S = np.asfortranarray(S, dtype=np.float64); self.T = np.asfortranarray(T, dtype=np.float64)
+        self.N, self.M = self.S.shape[0], self.T.shape[0]
+
+    def set_bsc(self, s_bits, t_bits, bits):
+        self.bsc = (np.ascontiguousarray(s_bits, dtype=np.uint8), np.ascontiguousarray(t_bits, dtype=np.uint8), bits)
+
+    def set_fpfh(self, s, t):
+        self.fpfh = (np.ascontiguousarray(s, dtype=np.float32), np.ascontiguousarray(t, dtype=np.float32))
+
+    def build_fd(self):
+        ft, ct, dof, bbx, nonmax, ratio, step, iou, ct_, cr = self.args
+        bs = self.bsc
+        fp = self.fpfh
+        self.R.ghref_set_solve_mode(self.solve_mode)
+        self.ctx = C.c_void_p(self.R.ghref_create(ft, ct, dof, bbx, nonmax, ratio, step, iou, ct_, cr, _dp(self.S), self.N,
+                                                  _dp(self.T), self.M, bs[0].ctypes.data if bs else None,
+                                                  bs[0].shape[0] if bs else 0, bs[1].ctypes.data if bs else None,
+                                                  bs[2] if bs else 0, fp[0].ctypes.data if fp else None,
+                                                  fp[1].ctypes.data if fp else None))
+        self.R.ghref_build_fd(self.ctx)
+
+    def iterate(self):
+        if self.ctx is None:
+            self.build_fd()
+        self.R.ghref_set_solve_mode(self.solve_mode)
+        st = GhrefStats()
+        self.R.ghref_iterate(self.ctx, C.byref(st))
+        return st
+
+    def pairs_xyz(self):
+        cap = max(self.N, self.M)
+        sp = np.zeros(3 * cap); tp = np.zeros(3 * cap)
+        n = self.R.ghref_get_pairs_xyz(self.ctx, _dp(sp), _dp(tp))
+        return sp[:3 * n].reshape(3, n).T.copy(), tp[:3 * n].reshape(3, n).T.copy()
+
+    def source(self):
+        out = np.zeros((self.N, 3), dtype=np.float64, order="F")
+        self.R.ghref_get_source(self.ctx, _dp(out))
+        return out
+
+    def fd(self):
+        return np.array([np.ctypeslib.as_array(self.R.ghref_fd_row(self.ctx, i), shape=(self.M,)).copy() for i in range(self.N)])
+
+    def cd(self):
+        return np.array([np.ctypeslib.as_array(self.R.ghref_cd_row(self.ctx, i), shape=(self.M,)).copy() for i in range(self.N)])
+
+    def run(self):
+        if self.ctx is None:
+            self.build_fd()
+        self.R.ghref_set_solve_mode(self.solve_mode)
+        Rt = np.zeros(16)
+        its = self.R.ghref_run(self.ctx, _dp(Rt))
+        return Rt.reshape(4, 4).T.copy(), its
+
+    def __del__(self):
+        try:
+            if self.ctx:
+                self.R.ghref_destroy(self.ctx)
+                self.ctx = None
+        except Exception:
+            pass
 
 
 def hamming(a, b):

@@ -911,6 +911,7 @@ int orc_iterate(orc_ctx *c, orc_iter_stats *st) {
 int orc_run(orc_ctx *c, double Rt_final[16], int *iterations) {
   int it = 0;
   orc_iter_stats st;
+  orc_build_fd(c);  // calFD_BSC / calFD_FPFH at the top of ghicp_reg (src/ghicp_reg.cpp:33-44)
   while (!c->converge) {
     orc_iterate(c, &st);
     ++it;

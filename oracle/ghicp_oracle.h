@@ -25,7 +25,7 @@
  *   - KM (Km::kmsolve/output): PINNED.  Checked against golden vectors G1 (src/km.cpp:237-260) and
  *     G2 (img/GH-ICPworkflow.jpg panels (e),(f), E_min = 106) and, bit for bit, against the
  *     reference's own src/km.cpp compiled verbatim into oracle/_ref/libkm_ref.so (oracle/Makefile).
- *   - Rigid solve: the reference delegates to PCL's TransformationEstimationSVD<PointXYZ,PointXYZ>
+ *   - Rigid solve (the ONLY unpinned piece): the reference delegates to PCL's TransformationEstimationSVD<PointXYZ,PointXYZ>
  *     (src/ghicp_reg.cpp:857-859), i.e. Eigen::umeyama in float32.  PCL/Eigen are NOT in
  *     /root/reference and not installed here; version unpinned by the reference
  *     (CMakeLists.txt:13 "FIND_PACKAGE(PCL REQUIRED)", README.md:52 "PCL(>=1.7)").  The published
@@ -37,9 +37,15 @@
  *     FPFHfeature::compute_fpfh_distance (include/fpfh.hpp:135-165) are compiled VERBATIM from /root/reference into
  *     oracle/_ref/libfeat_ref.so (PCL / boost / Eigen replaced by declaration-only stubs, oracle/stub); orc_hamming and
  *     orc_fpfh_distance are checked against them bit for bit, live and through tests/golden/feat_golden.npz.
- *   - ED/CD/NN/NNR and the loop glue: no golden vectors exist in the reference (it has no tests) and these live inside
- *     GHRegistration, which needs PCL to compile; they are short scalar loops restated verbatim.  PARITY UNPINNED beyond
- *     restatement (tests/golden/loop_golden.npz pins the restatement against drift only).
+ *   - ED / CD / penalty rules / NN / NNR / KM glue / pair statistics / update / convergence / adjustweight / the loop: PINNED.
+ *     The reference's own src/ghicp_reg.cpp (GHRegistration, lines 24-927) is compiled VERBATIM from /root/reference,
+ *     together with its src/km.cpp and src/stereo_binary_feature.cpp, into oracle/_ref/libghreg_ref.so
+ *     (oracle/ghreg_ref_shim.cpp; Eigen / PCL / VTK replaced by the declaration-level stubs of oracle/stub: a minimal
+ *     matrix type, empty viewer classes).  The oracle agrees with it BIT FOR BIT — FD and CD matrices, penalties, pair
+ *     lists, statistics, per-iteration and accumulated transforms, updated keypoints, convergence — for every
+ *     feature x correspondence x dof combination (tests/test_reference_loop.py) and for GHRegistration::ghicp_reg as a whole.
+ *     tests/golden/loop_golden.npz carries that behaviour to machines without /root/reference.
+ *     The single exception is the call into PCL (next item).
  *
  * Build: oracle/Makefile  (g++ -O3 -std=c++17 -ffp-contract=off, no -march: IEEE double, no FMA).
  */

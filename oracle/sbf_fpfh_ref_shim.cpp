@@ -7,13 +7,7 @@
 // i.e. the per-pair kernels of calFD_BSC / calFD_FPFH (src/ghicp_reg.cpp:143-214).  TEST INFRASTRUCTURE ONLY; contains no
 // reference source, only calls it.
 #include "stereo_binary_feature.h"
-// include/utility.h (pulled in by fpfh.hpp:23) needs real Eigen matrices for helpers this path never touches: its guard is
-// pre-defined and only the four typedefs fpfh.hpp uses (utility.h:41-48) are supplied
-#define _INCLUDE_UTILITY_H
-typedef pcl::PointCloud<pcl::Normal>::Ptr NormalsPtr;
-typedef pcl::PointCloud<pcl::Normal> Normals;
-typedef pcl::PointCloud<pcl::FPFHSignature33>::Ptr fpfhFeaturePtr;
-typedef pcl::PointCloud<pcl::FPFHSignature33> fpfhFeature;
+// (include/utility.h is guarded out; oracle/stub/ghicp_utility_names.h is force-included instead)
 #include "fpfh.hpp"
 
 extern "C" {

@@ -29,4 +29,6 @@ template <typename A, typename B> class NormalEstimation;
 template <typename A, typename B, typename C> class FPFHEstimationOMP;
 template <typename A, typename B, typename C> class SampleConsensusInitialAlignment;
 namespace search { template <typename T> struct KdTree { typedef std::shared_ptr<KdTree<T>> Ptr; }; }
+template <typename P, typename M> void transformPointCloud(const PointCloud<P> &in, PointCloud<P> &out, const M &) { out = in; }
 }  // namespace pcl
+namespace boost { namespace filesystem {} }   // `using namespace boost::filesystem;` at src/ghicp_reg.cpp:18

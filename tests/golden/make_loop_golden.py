@@ -1,8 +1,14 @@
 """Regenerates tests/golden/loop_golden.npz: small complete registration loops (inputs + per-iteration correspondence
-lists + transforms) produced by the CPU ORACLE (oracle/, the line-by-line restatement of src/ghicp_reg.cpp; KM through
-the reference's own src/km.cpp when oracle/_ref is built).  The reference has no loop-level golden data;
-these fixtures pin (a) the oracle against drift (tests/test_oracle_golden.py) and (b) the CUDA path against committed
-vectors on the GPU box, where /root/reference does not exist (tests/test_zz_extensions.py).
+lists + transforms).  Every loop is run TWICE and must agree bit for bit before it is written:
+  * through the REFERENCE's own GHRegistration (src/ghicp_reg.cpp + km.cpp + stereo_binary_feature.cpp compiled verbatim
+    into oracle/_ref/libghreg_ref.so; needs /root/reference, i.e. the build container) — pair coordinates, penalties and
+    transforms come from the reference's own statements (PCL's SVD call delegated to the oracle's PCL-like float32
+    Umeyama, solve_mode 0) and must equal the oracle run in the same mode;
+  * through the CPU oracle with double-moment sums (solve_mode 1, what the CUDA path computes), whose pair INDEX lists
+    (the reference keeps them in locals) must be the ones of the reference run in every iteration; its transforms are
+    what the fixture stores (they differ from the float32-sum ones by ~1e-7).
+The reference has no loop-level golden data; these fixtures carry its behaviour to the GPU box, where
+/root/reference does not exist (tests/test_oracle_golden.py on the CPU, tests/test_zz_extensions.py on the GPU).
 
     python tests/golden/make_loop_golden.py
 """
@@ -50,10 +56,29 @@ def main():
         if ft == "fpfh":
             o.set_fpfh(sc.fpfh_s, sc.fpfh_t)
         o.build_fd()
+        ref = oracle.Reference(FT[ft], CT[ct], dof=dof, bbx_magnitude=sc.bbx_magnitude, solve_mode=0)
+        o0 = oracle.Oracle(FT[ft], CT[ct], dof=dof, bbx_magnitude=sc.bbx_magnitude, solve_mode=0, max_iter=max_it,
+                           use_ref_km=(use_ref and ct == "km"))
+        for x in (ref, o0):
+            x.set_keypoints(sc.S, sc.T)
+            if ft == "bsc":
+                x.set_bsc(sc.bsc_s, sc.bsc_t, sc.bits)
+            if ft == "fpfh":
+                x.set_fpfh(sc.fpfh_s, sc.fpfh_t)
+            x.build_fd()
         sps, tps, offs, rts, pens, energies = [], [], [0], [], [], []
         for _ in range(max_it):
             st = o.iterate()
             sp, tp = o.pairs()
+            rst, st0 = ref.iterate(), o0.iterate()   # the reference's own loop body and the oracle in the same solve mode
+            rs, rt = ref.pairs_xyz()
+            assert rst.cor == st0.cor and rst.penalty == st0.penalty and rst.converged == st0.converged, name
+            assert np.array_equal(np.array(rst.Rt), np.array(st0.Rt)), name
+            assert np.array_equal(np.array(rst.Rt_tillnow), np.array(st0.Rt_tillnow)), name
+            sp0, tp0 = o0.pairs()
+            assert np.array_equal(rt, np.asarray(sc.T)[tp0]), name
+            # the stored lists (double-moment solve) are the reference run's lists
+            assert np.array_equal(sp, sp0) and np.array_equal(tp, tp0) and st.converged == st0.converged, name
             sps.append(sp); tps.append(tp); offs.append(offs[-1] + len(sp))
             rts.append(np.array(st.Rt)); pens.append(st.penalty); energies.append(st.km_energy)
             if st.converged:
