@@ -35,7 +35,7 @@ def build(force=False):
         or not os.path.exists(os.path.join(_HERE, "liboracle_omp.so"))
     if need or (os.path.isdir("/root/reference") and
                 not all(os.path.exists(os.path.join(_HERE, "_ref", f))
-                        for f in ("libkm_ref.so", "libfeat_ref.so", "libghreg_ref.so"))):
+                        for f in ("libkm_ref.so", "libfeat_ref.so", "libghreg_ref.so", "libprep_ref.so"))):
         subprocess.run(["make", "-C", _HERE, "all"], check=True, capture_output=True)
 
 
@@ -131,6 +131,24 @@ def ref_feat_lib():
     R.featref_fpfh_distance.argtypes = [C.c_void_p, C.c_void_p]
     _libs["feat"] = R
     return R
+
+
+def ref_voxelfilter(xyz, voxel_size):
+    """The REFERENCE's own CFilter::voxelfilter (include/filter.hpp:28-88 compiled verbatim, oracle/_ref/libprep_ref.so):
+    the output cloud [m][3], or None when the library is not built."""
+    p = os.path.join(_HERE, "_ref", "libprep_ref.so")
+    if "prep" not in _libs:
+        build()
+        _libs["prep"] = C.CDLL(p) if os.path.exists(p) else None
+        if _libs["prep"] is not None:
+            _libs["prep"].prepref_voxelfilter.argtypes = [C.POINTER(C.c_float), C.c_int, C.c_float, C.POINTER(C.c_float)]
+    R = _libs["prep"]
+    if R is None:
+        return None
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+    out = np.zeros((len(xyz) + 1, 3), np.float32)
+    m = R.prepref_voxelfilter(_fp(xyz), len(xyz), voxel_size, _fp(out))
+    return out[:m].copy()
 
 
 class GhrefStats(C.Structure):

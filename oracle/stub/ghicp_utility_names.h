@@ -17,4 +17,8 @@ typedef pcl::PointCloud<pcl::FPFHSignature33> fpfhFeature;
 namespace ghicp {
 enum FeatureType { BSC, RoPS, FPFH, None };
 enum CorrespondenceType { NN, NNR, KM };
+// named in signatures of include/filter.hpp (utility.h:66-90, 131-...): declarations only, nothing here is called
+struct CenterPoint { double x, y, z; };
+struct Bounds { double min_x, min_y, min_z, max_x, max_y, max_z; };
+template <typename PointT> class CloudUtility {};
 }

@@ -44,6 +44,25 @@ def test_voxel_filter_one_point_per_voxel_smallest_index_plus_phantom(orc):
     assert np.all(np.diff(key[rest]) > 0)
 
 
+@pytest.mark.parametrize("n,voxel,seed", [(6000, 0.4, 1), (20000, 0.1, 2), (500, 5.0, 3), (3000, 0.02, 4)])
+def test_voxel_filter_against_the_reference_build(orc, n, voxel, seed):
+    """The REFERENCE's own CFilter::voxelfilter (include/filter.hpp compiled verbatim, build container only): same number of
+    output points, the phantom point 0 first, the same voxel at every output position.  WHICH point of a voxel is kept is
+    implementation-defined there (an unstable std::sort on the voxel id alone, :71); the oracle / CUDA path keep the smallest
+    index."""
+    P = scan_like_cloud(n, seed)
+    ref = orc.ref_voxelfilter(P, voxel)
+    if ref is None:
+        pytest.skip("oracle/_ref/libprep_ref.so not built (no /root/reference here)")
+    mine = P[orc.voxel_downsample(P, voxel)]
+    assert len(ref) == len(mine)
+    assert np.array_equal(ref[0], P[0]) and np.array_equal(mine[0], P[0])
+    inv = np.float32(1.0) / np.float32(voxel)
+    mn = P.min(axis=0)
+    vr, vm = np.floor((ref - mn) * inv), np.floor((mine - mn) * inv)
+    assert np.array_equal(vr[1:], vm[1:])                      # same voxel, position by position (position 0 is the phantom)
+
+
 def test_pca_eigenvalues_and_counts_match_numpy(orc):
     P = scan_like_cloud(3000, 2)
     r = 0.9
