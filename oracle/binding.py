@@ -151,6 +151,21 @@ def ref_voxelfilter(xyz, voxel_size):
     return out[:m].copy()
 
 
+def ref_detect_keypoints(xyz, radius, ratio_max=0.65, min_pts=20, nms_radius=None):
+    """The REFERENCE's own CKeypointDetect::keypointDetectionBasedOnCurvature (include/keypoint_detect.hpp + include/pca.h
+    compiled verbatim; KD-tree / PCA numerics from the stand-ins of oracle/stub): keypoint indices, or None."""
+    if ref_voxelfilter(np.zeros((1, 3), np.float32), 1.0) is None:
+        return None
+    R = _libs["prep"]
+    R.prepref_detect_keypoints.argtypes = [C.POINTER(C.c_float), C.c_int, C.c_float, C.c_float, C.c_int, C.c_float,
+                                           C.POINTER(C.c_int)]
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+    kp = np.zeros(len(xyz), np.int32)
+    m = R.prepref_detect_keypoints(_fp(xyz), len(xyz), radius, ratio_max, min_pts,
+                                   nms_radius if nms_radius is not None else radius, _ip(kp))
+    return kp[:m].copy()
+
+
 class GhrefStats(C.Structure):
     _fields_ = [("iteration", C.c_int), ("cor", C.c_int), ("converged", C.c_int), ("penalty", C.c_double), ("rmse", C.c_double),
                 ("rmse_after", C.c_double), ("fdm", C.c_double), ("fdstd", C.c_double), ("iou", C.c_double),

@@ -8,6 +8,7 @@
 #include <Eigen/Core>
 #include <iostream>
 #include <memory>
+#include <set>
 #include <vector>
 namespace pcl {
 struct PointXYZ { float x, y, z; };
@@ -32,7 +33,10 @@ template <typename T> struct PointCloud {
 };
 struct PointIndices { std::vector<int> indices; };
 typedef std::shared_ptr<PointIndices> PointIndicesPtr;
+template <typename P> bool isFinite(const P &) { return true; }
 template <typename A> class StatisticalOutlierRemoval;
+template <typename A, typename B> class NormalEstimationOMP;
+template <typename A, typename B, typename C> void concatenateFields(const A &, const B &, C &);
 template <typename A, typename B> class NormalEstimation;
 template <typename A, typename B, typename C> class FPFHEstimationOMP;
 template <typename A, typename B, typename C> class SampleConsensusInitialAlignment;

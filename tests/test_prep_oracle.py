@@ -63,6 +63,25 @@ def test_voxel_filter_against_the_reference_build(orc, n, voxel, seed):
     assert np.array_equal(vr[1:], vm[1:])                      # same voxel, position by position (position 0 is the phantom)
 
 
+@pytest.mark.parametrize("n,radius,nms,seed", [(4000, 1.0, 1.5, 8), (1500, 0.6, 0.6, 9), (600, 3.0, 0.3, 10), (6000, 0.8, 1.0, 12)])
+def test_keypoint_detection_against_the_reference_build(orc, n, radius, nms, seed):
+    """The REFERENCE's own keypointDetectionBasedOnCurvature (keypoint_detect.hpp + pca.h compiled verbatim: its PCA driver,
+    pruneUnstablePoints, the curvature sort and the std::set based greedy suppression; KD-tree / PCA numerics from the
+    stand-ins): same number of keypoints, the same curvature at every output position.  Indices may differ only between
+    points of EXACTLY equal curvature that suppress each other — the reference orders such ties through an unstable
+    std::sort (:151), the oracle / CUDA path by index."""
+    P = scan_like_cloud(n, seed)
+    ref = orc.ref_detect_keypoints(P, radius, 0.65, 20, nms)
+    if ref is None:
+        pytest.skip("oracle/_ref/libprep_ref.so not built (no /root/reference here)")
+    kp, lam, curv, cnt = orc.detect_keypoints(P, radius, 0.65, 20, nms)
+    assert len(ref) == len(kp) and len(kp) > 0
+    assert np.array_equal(curv[ref], curv[kp])
+    for a, b in zip(ref, kp):
+        if a != b:
+            assert curv[a] == curv[b] and np.linalg.norm(P[a].astype(np.float64) - P[b].astype(np.float64)) < nms
+
+
 def test_pca_eigenvalues_and_counts_match_numpy(orc):
     P = scan_like_cloud(3000, 2)
     r = 0.9
