@@ -15,3 +15,4 @@ from .capi import (  # noqa: F401
 )
 from .registration import GHRegistration, Keypoints, Energyfunction  # noqa: F401
 from . import synth  # noqa: F401
+from . import pipeline  # noqa: F401

@@ -1,0 +1,51 @@
+"""Raw clouds -> transform: the steps of the reference's driver (test/ghicp_main.cpp:86-155) over the C ABI, in Python.
+
+    Rt, info = register_clouds(target_xyz, source_xyz, resolution=0.1, neighborhood_radius=0.5,
+                               curvature_non_max_radius=1.0)
+
+Voxel down-sampling of both clouds (CFilter::voxelfilter), curvature keypoints (0.65 / 20 neighbours, :96-97), the
+bounding-box magnitude of the down-sampled source (:91-93), GHRegistration on the keypoints.  Descriptors are optional:
+`features(target_down, target_kp_idx, source_down, source_kp_idx) -> Keypoints` may attach BSC / FPFH descriptors computed
+elsewhere (the encoders are not part of this library); without it the registration runs on coordinates
+only (Ft = None), which GHRegistration supports (src/ghicp_reg.cpp:66-68) although the reference's own main() rejects it.
+"""
+import numpy as np
+
+from . import capi
+from .registration import Energyfunction, GHRegistration, Keypoints
+
+
+def register_clouds(target_xyz, source_xyz, resolution, neighborhood_radius, curvature_non_max_radius, corr_type=capi.CT_NN,
+                    feature_type=capi.FT_NONE, features=None, weight_adjustment_ratio=1.1, weight_adjustment_step=0.1,
+                    dof_type=6, estimated_IoU=0.5, max_iter=0, device=0, **reg_kw):
+    T = np.ascontiguousarray(target_xyz, dtype=np.float32)
+    S = np.ascontiguousarray(source_xyz, dtype=np.float32)
+    down, kp_idx = {}, {}
+    for name, P in (("T", T), ("S", S)):
+        keep = capi.voxel_downsample(P, resolution, device=device)                       # :89-90
+        D = np.ascontiguousarray(P[keep])
+        kp, _, _, _ = capi.detect_keypoints(D, neighborhood_radius, 0.65, 20, curvature_non_max_radius, device=device)   # :96-100
+        if len(kp) == 0:
+            raise capi.GhicpError(-1, f"no keypoints in the {'target' if name == 'T' else 'source'} cloud: check the radii")
+        down[name], kp_idx[name] = D, kp
+    ext = down["S"].max(axis=0) - down["S"].min(axis=0)                                   # getCloudBound, :91-93
+    bbx = float(np.float32(ext[0] + ext[1] + ext[2]))
+    if features is not None:
+        Kp = features(down["T"], kp_idx["T"], down["S"], kp_idx["S"])
+    else:
+        Kp = Keypoints().setCoordinate(down["S"][kp_idx["S"]].astype(np.float64), down["T"][kp_idx["T"]].astype(np.float64))
+    Ef = Energyfunction().init(Kp.kps_num, Kp.kpt_num, bbx)
+    reg = GHRegistration(Kp, Ef, feature_type, corr_type, curvature_non_max_radius, weight_adjustment_ratio,
+                         weight_adjustment_step, dof_type, estimated_IoU, max_iter=max_iter, device=device, **reg_kw)
+    Rt, iterations = reg.ghicp_reg()
+    info = dict(iterations=iterations, n_target_down=len(down["T"]), n_source_down=len(down["S"]), n_target_kp=len(kp_idx["T"]),
+                n_source_kp=len(kp_idx["S"]), bbx_magnitude=bbx, cor=len(reg.pairs()[0]))
+    reg.close()
+    return Rt, info
+
+
+def transform_cloud(xyz, Rt):
+    """pcl::transformPointCloud with the float32 matrix (test/ghicp_main.cpp:153)."""
+    P = np.ascontiguousarray(xyz, dtype=np.float32)
+    R, t = Rt[:3, :3].astype(np.float32), Rt[:3, 3].astype(np.float32)
+    return P @ R.T + t

@@ -95,3 +95,24 @@ def test_command_line_driver_registers_two_files(g, orc, tmp_path):
     reg = read_pcd_binary(fr)
     Rf, tf = Rt[:3, :3].astype(np.float32), Rt[:3, 3].astype(np.float32)
     assert np.allclose(reg, S @ Rf.T + tf, atol=1e-4)       # pcl::transformPointCloud with the float32 matrix (:153)
+
+
+def test_python_pipeline_helper(g, orc):
+    """ghicp_b200.pipeline.register_clouds = the CLI's pipeline from Python."""
+    T = scan_like_cloud(30000, 33)
+    R = g.synth.rot_xyz_deg(0.4, 0.2, -1.0)
+    S = ((T.astype(np.float64) - [0.2, 0.1, -0.05]) @ R).astype(np.float32)
+    Rt, info = g.pipeline.register_clouds(T, S, 0.25, 1.0, 1.2, max_iter=50)
+    assert info["n_source_kp"] >= 10 and info["iterations"] >= 1
+    K = {}
+    for name, P in (("T", T), ("S", S)):
+        D = np.ascontiguousarray(P[orc.voxel_downsample(P, 0.25)])
+        kp, _, _, _ = orc.detect_keypoints(D, 1.0, 0.65, 20, 1.2)
+        K[name] = (D, D[kp].astype(np.float64))
+    ext = K["S"][0].max(axis=0) - K["S"][0].min(axis=0)
+    o = orc.Oracle(orc.FT_NONE, orc.CT_NN, bbx_magnitude=float(np.float32(ext[0] + ext[1] + ext[2])), solve_mode=1, max_iter=50)
+    o.set_keypoints(K["S"][1], K["T"][1])
+    Ro, _, _ = o.run()
+    assert g.synth.rot_angle(Rt[:3, :3], Ro[:3, :3]) < 1e-4 and np.linalg.norm(Rt[:3, 3] - Ro[:3, 3]) < 1e-3
+    moved = g.pipeline.transform_cloud(S, Rt)
+    assert moved.shape == S.shape and moved.dtype == np.float32
