@@ -12,7 +12,7 @@
 // host emulation shim of tests/harness/cuda_emu) compiles a few .cu files as plain C++ and runs every CUDA thread as a
 // fiber on the CPU; those files launch through this macro.  The product is always built by nvcc.
 #if defined(GHICP_EMU_HOST)
-#define GHICP_LAUNCH(kernel, grid, block, smem, stream, ...) emu::launch((grid), (block), [&] { kernel(__VA_ARGS__); })
+#define GHICP_LAUNCH(kernel, grid, block, smem, stream, ...) emu::launch((grid), (block), [&] { kernel(__VA_ARGS__); }, (smem))
 #define GHICP_NOINLINE __attribute__((noinline))
 #else
 #define GHICP_NOINLINE __noinline__

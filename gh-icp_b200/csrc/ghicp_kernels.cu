@@ -53,7 +53,11 @@ __global__ void __launch_bounds__(FDB_THREADS) k_fd_bsc(const uint64_t *__restri
                                                          const uint64_t *__restrict__ bt,
                                                          uint16_t *__restrict__ fd, int N, int M, size_t ldM,
                                                          int W64, int row0, int nloc) {
+#if defined(GHICP_EMU_HOST)
+  uint64_t *s_words = reinterpret_cast<uint64_t *>(emu::dyn_smem());  // host emulation: the launch's dynamic shared memory
+#else
   extern __shared__ uint64_t s_words[];  // [V][W64][FDB_ROWS]
+#endif
   const int i0 = row0 + blockIdx.y * FDB_ROWS;
   const int iend = row0 + nloc;
   const int j = blockIdx.x * FDB_THREADS + threadIdx.x;
@@ -784,12 +788,12 @@ cudaError_t dispatch_ft(int ft, F &&f) {
 cudaError_t launch_pack_bsc(Ctx *c, const uint8_t *d_raw_s, const uint8_t *d_raw_t) {
   {
     long long total = (long long)c->V * c->W64 * c->N;
-    k_pack_bsc<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(d_raw_s, c->d_bs, c->V, c->N, c->Bbytes, c->W64);
+    GHICP_LAUNCH(k_pack_bsc, (unsigned)((total + 255) / 256), 256, 0, c->stream, d_raw_s, c->d_bs, c->V, c->N, c->Bbytes, c->W64);
     c->launches++;
   }
   {
     long long total = (long long)c->W64 * c->M;
-    k_pack_bsc<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(d_raw_t, c->d_bt, 1, c->M, c->Bbytes, c->W64);
+    GHICP_LAUNCH(k_pack_bsc, (unsigned)((total + 255) / 256), 256, 0, c->stream, d_raw_t, c->d_bt, 1, c->M, c->Bbytes, c->W64);
     c->launches++;
   }
   return cudaGetLastError();
@@ -800,9 +804,9 @@ cudaError_t launch_fd_bsc(Ctx *c) {
   dim3 grid((c->M + FDB_THREADS - 1) / FDB_THREADS, (c->nloc + FDB_ROWS - 1) / FDB_ROWS);
   size_t smem = (size_t)V * c->W64 * FDB_ROWS * sizeof(uint64_t);
   if (V == 4)
-    k_fd_bsc<4><<<grid, FDB_THREADS, smem, c->stream>>>(c->d_bs, c->d_bt, c->d_fd16, c->N, c->M, c->fd_rows, c->W64, c->r0, c->nloc);
+    GHICP_LAUNCH(k_fd_bsc<4>, grid, FDB_THREADS, smem, c->stream, c->d_bs, c->d_bt, c->d_fd16, c->N, c->M, c->fd_rows, c->W64, c->r0, c->nloc);
   else
-    k_fd_bsc<2><<<grid, FDB_THREADS, smem, c->stream>>>(c->d_bs, c->d_bt, c->d_fd16, c->N, c->M, c->fd_rows, c->W64, c->r0, c->nloc);
+    GHICP_LAUNCH(k_fd_bsc<2>, grid, FDB_THREADS, smem, c->stream, c->d_bs, c->d_bt, c->d_fd16, c->N, c->M, c->fd_rows, c->W64, c->r0, c->nloc);
   c->launches++;
   return cudaGetLastError();
 }
@@ -812,10 +816,10 @@ cudaError_t launch_fd_fpfh(Ctx *c) {
   cudaError_t e;
   if ((e = cudaMallocAsync(&sc, (size_t)c->N * 36 * sizeof(float), c->stream)) != cudaSuccess) return e;
   if ((e = cudaMallocAsync(&tc, (size_t)c->M * 36 * sizeof(float), c->stream)) != cudaSuccess) return e;
-  k_fpfh_center<<<(c->N + 127) / 128, 128, 0, c->stream>>>(c->d_fs, sc, c->N);
-  k_fpfh_center<<<(c->M + 127) / 128, 128, 0, c->stream>>>(c->d_ft, tc, c->M);
+  GHICP_LAUNCH(k_fpfh_center, (c->N + 127) / 128, 128, 0, c->stream, c->d_fs, sc, c->N);
+  GHICP_LAUNCH(k_fpfh_center, (c->M + 127) / 128, 128, 0, c->stream, c->d_ft, tc, c->M);
   dim3 grid((c->M + FPT - 1) / FPT, (c->nloc + FPT - 1) / FPT);
-  k_fd_fpfh<<<grid, FPT * FPT, 0, c->stream>>>(sc, tc, c->d_fdf, c->N, c->M, c->fd_rows, c->r0, c->nloc);
+  GHICP_LAUNCH(k_fd_fpfh, grid, FPT * FPT, 0, c->stream, sc, tc, c->d_fdf, c->N, c->M, c->fd_rows, c->r0, c->nloc);
   c->launches += 3;
   cudaFreeAsync(sc, c->stream);
   cudaFreeAsync(tc, c->stream);
@@ -837,9 +841,8 @@ cudaError_t launch_rowsweep(Ctx *c, int mode, const CostParams &cp) {
   dim3 grid((c->nloc + TR - 1) / TR, c->n_chunks);
   cudaError_t e = dispatch_ft(c->cfg.feature_type, [&](auto ft) {
     constexpr int FT = decltype(ft)::value;
-    if (mode == 0) k_rowsweep<FT, 0><<<grid, SWEEP_THREADS, 0, c->stream>>>(a);
-    else if (mode == 1) k_rowsweep<FT, 1><<<grid, SWEEP_THREADS, 0, c->stream>>>(a);
-    else k_rowsweep<FT, 2><<<grid, SWEEP_THREADS, 0, c->stream>>>(a);
+    void (*kern)(const SweepArgs) = mode == 0 ? k_rowsweep<FT, 0> : (mode == 1 ? k_rowsweep<FT, 1> : k_rowsweep<FT, 2>);
+    GHICP_LAUNCH(kern, grid, SWEEP_THREADS, 0, c->stream, a);
     return cudaGetLastError();
   });
   c->launches++;
@@ -853,7 +856,8 @@ cudaError_t launch_colsweep(Ctx *c, const CostParams &cp) {
   dim3 grid((c->M + CT - 1) / CT);
   cudaError_t e = dispatch_ft(c->cfg.feature_type, [&](auto ft) {
     constexpr int FT = decltype(ft)::value;
-    k_colsweep<FT><<<grid, COL_THREADS, 0, c->stream>>>(a);
+    void (*kern)(const ColArgs) = k_colsweep<FT>;
+    GHICP_LAUNCH(kern, grid, COL_THREADS, 0, c->stream, a);
     return cudaGetLastError();
   });
   c->launches++;
@@ -863,7 +867,7 @@ cudaError_t launch_colsweep(Ctx *c, const CostParams &cp) {
 cudaError_t launch_finalize_stats(Ctx *c, const CostParams &cp, const LoopScalars &ls) {
   (void)cp; (void)ls;
   const int n_parts = ((c->nloc + TR - 1) / TR) * c->n_chunks;
-  k_finalize<<<1, 1024, 0, c->stream>>>(c->d_part_cd, c->d_part_idx, c->n_chunks, c->r0, c->nloc, c->d_part_stats,
+  GHICP_LAUNCH(k_finalize, 1, 1024, 0, c->stream, c->d_part_cd, c->d_part_idx, c->n_chunks, c->r0, c->nloc, c->d_part_stats,
                                         n_parts, c->d_row_cd, c->d_row_idx, c->d_row_fd, c->d_fd16, c->d_fdf,
                                         c->fd_rows, c->d_xstats, c->rank);
   c->launches++;
@@ -871,12 +875,12 @@ cudaError_t launch_finalize_stats(Ctx *c, const CostParams &cp, const LoopScalar
 }
 
 cudaError_t launch_penalty(Ctx *c, double pivot, const LoopScalars &ls) {
-  k_penalty<<<1, 1, 0, c->stream>>>(c->d_xstats, c->world, pivot, c->N, c->M, c->cfg.feature_type, ls, c->d_iter);
+  GHICP_LAUNCH(k_penalty, 1, 1, 0, c->stream, c->d_xstats, c->world, pivot, c->N, c->M, c->cfg.feature_type, ls, c->d_iter);
   c->launches++;
   return cudaGetLastError();
 }
 cudaError_t launch_pair_fd_km(Ctx *c) {
-  k_pair_fd_km<<<148 * 2, 256, 0, c->stream>>>(c->d_sp, c->d_tp, c->d_iter, c->d_rowptr, c->d_csr_col, c->d_csr_fd,
+  GHICP_LAUNCH(k_pair_fd_km, 148 * 2, 256, 0, c->stream, c->d_sp, c->d_tp, c->d_iter, c->d_rowptr, c->d_csr_col, c->d_csr_fd,
                                                c->d_pair_fd);
   c->launches++;
   return cudaGetLastError();
@@ -885,8 +889,8 @@ cudaError_t launch_pair_fd_km(Ctx *c) {
 cudaError_t launch_scan_i32(Ctx *c, const int *cnt, long long *ptr, int *cursor, long long L, long long *total_out) {
   const int tiles = (int)std::max<long long>(1, (L + TILE - 1) / TILE);
   if ((size_t)tiles > c->tile_cap) return cudaErrorInvalidValue;
-  k_tile_sum_i32<<<tiles, TILE_THREADS, 0, c->stream>>>(cnt, L, c->d_tile_sum);
-  k_tile_scan_i32<<<tiles, TILE_THREADS, 0, c->stream>>>(cnt, L, c->d_tile_sum, ptr, cursor, total_out);
+  GHICP_LAUNCH(k_tile_sum_i32, tiles, TILE_THREADS, 0, c->stream, cnt, L, c->d_tile_sum);
+  GHICP_LAUNCH(k_tile_scan_i32, tiles, TILE_THREADS, 0, c->stream, cnt, L, c->d_tile_sum, ptr, cursor, total_out);
   c->launches += 2;
   return cudaGetLastError();
 }
@@ -898,8 +902,8 @@ static cudaError_t launch_select(Ctx *c, SelArgs a) {
   const int tiles = std::max(1, (a.n + TILE - 1) / TILE);
   if ((size_t)tiles * 2 > c->tile_cap) return cudaErrorInvalidValue;
   a.iter = c->d_iter; a.sp = c->d_sp; a.tp = c->d_tp; a.tile_sum = c->d_tile_sum;
-  k_select_count<<<tiles, TILE_THREADS, 0, c->stream>>>(a);
-  k_select_write<<<tiles, TILE_THREADS, 0, c->stream>>>(a);
+  GHICP_LAUNCH(k_select_count, tiles, TILE_THREADS, 0, c->stream, a);
+  GHICP_LAUNCH(k_select_write, tiles, TILE_THREADS, 0, c->stream, a);
   c->launches += 2;
   return cudaGetLastError();
 }
@@ -932,7 +936,14 @@ cudaError_t launch_solve(Ctx *c, const CostParams &cp) {
   const int nmax = std::max(c->N, c->M);
   const int grid = std::min(SOLVE_GRID_MAX, std::max(1, (nmax + 1023) / 1024));
   void *args[] = {(void *)&a};
+#if defined(GHICP_EMU_HOST)
+  (void)args;   // host emulation: one block only (its grid barrier is then a block barrier), see tests/harness/cuda_emu
+  void (*kern)(const SolveArgs) = k_solve<true>;
+  GHICP_LAUNCH(kern, 1, 256, 0, c->stream, a);
+  cudaError_t e = cudaSuccess;
+#else
   cudaError_t e = cudaLaunchCooperativeKernel((void *)k_solve<true>, dim3(grid), dim3(256), args, 0, c->stream);
+#endif
   c->launches++;
   return e != cudaSuccess ? e : cudaGetLastError();
 }
@@ -941,19 +952,20 @@ cudaError_t launch_solve_explicit(cudaStream_t stream, const double *d_s, const 
   SolveArgs a{};
   a.sxyz_pairs = d_s; a.txyz_pairs = d_t; a.n_explicit = n; a.iter = d_iter;
   a.feature_type = GHICP_FT_NONE;
-  k_solve<false><<<1, 1024, 0, stream>>>(a);
+  void (*kern)(const SolveArgs) = k_solve<false>;
+  GHICP_LAUNCH(kern, 1, 1024, 0, stream, a);
   return cudaGetLastError();
 }
 
 cudaError_t launch_apply(Ctx *c) {
-  k_apply<<<(c->N + 255) / 256, 256, 0, c->stream>>>(c->d_s, c->N, c->d_iter);
+  GHICP_LAUNCH(k_apply, (c->N + 255) / 256, 256, 0, c->stream, c->d_s, c->N, c->d_iter);
   c->launches++;
   return cudaGetLastError();
 }
 
 cudaError_t launch_get_fd(Ctx *c, double *d_out) {
   const size_t total = (size_t)c->N * c->M;
-  k_fd_to_double<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(c->d_fd16, c->d_fdf, c->fd_rows, c->N, c->M, c->r0, c->nloc, d_out);
+  GHICP_LAUNCH(k_fd_to_double, (unsigned)((total + 255) / 256), 256, 0, c->stream, c->d_fd16, c->d_fdf, c->fd_rows, c->N, c->M, c->r0, c->nloc, d_out);
   c->launches++;
   return cudaGetLastError();
 }

@@ -14,3 +14,22 @@ inline float __half2float(__half h) {
   else out = (s << 31) | ((e + 112u) << 23) | (m << 13);
   float f; memcpy(&f, &out, 4); return f;
 }
+inline unsigned short __half_as_ushort(__half h) { return h.bits; }
+inline __half __int2half_rn(int v) {   // exact for |v| <= 2048 (the BSC Hamming distances); round-to-nearest-even beyond
+  __half h; h.bits = 0;
+  if (v == 0) return h;
+  const unsigned s = v < 0 ? 1u : 0u;
+  unsigned a = (unsigned)(v < 0 ? -v : v);
+  int e = 31 - __builtin_clz(a);                  // a = 1.xxx * 2^e
+  unsigned m;
+  if (e <= 10) m = (a << (10 - e)) & 1023u;
+  else {
+    const unsigned sh = (unsigned)(e - 10), rem = a & ((1u << sh) - 1u), half = 1u << (sh - 1);
+    unsigned q = a >> sh;
+    if (rem > half || (rem == half && (q & 1u))) ++q;
+    if (q >> 11) { q >>= 1; ++e; }
+    m = q & 1023u;
+  }
+  h.bits = (unsigned short)((s << 15) | ((unsigned)(e + 15) << 10) | m);
+  return h;
+}

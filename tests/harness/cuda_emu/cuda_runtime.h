@@ -6,6 +6,7 @@
 // generation, memory ordering and performance are only checked by the -m gpu tests.  Test infrastructure only.
 #pragma once
 #include <math.h>
+#include <stdlib.h>
 #include <stddef.h>
 #include <stdint.h>
 #include <string.h>
@@ -25,6 +26,8 @@ enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2
 typedef void *cudaStream_t;
 typedef void *cudaEvent_t;
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+template <typename T> inline cudaError_t cudaMallocAsync(T **p, size_t bytes, cudaStream_t) { *p = (T *)malloc(bytes ? bytes : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+inline cudaError_t cudaFreeAsync(void *p, cudaStream_t) { free(p); return cudaSuccess; }
 inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
 
 struct float4 { float x, y, z, w; };
@@ -37,6 +40,7 @@ struct uint4 { unsigned x, y, z, w; };
 #define gridDim (emu::g_gdim)
 
 inline void __syncthreads() { emu::syncthreads(); }
+inline void __threadfence() {}   // one OS thread: program order is memory order
 template <typename T>
 inline T __shfl_xor_sync(unsigned, T v, int lane_mask) { return emu::shfl<T>(v, (emu::cur()->tidx.x & 31) ^ lane_mask); }
 template <typename T>
@@ -64,6 +68,8 @@ inline unsigned __ballot_sync(unsigned, int pred) {
   for (int l = 0; l < 32; ++l) m |= (all[l] & 1u) << l;
   return m;
 }
+inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
+template <typename T> inline T __ldcg(const T *p) { return *p; }
 inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
 inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }

@@ -37,6 +37,8 @@ inline std::vector<Warp> g_warps;
 inline int g_cur_index = 0, g_live = 0, g_bar_count = 0, g_bar_gen = 0;
 inline ucontext_t g_sched;
 inline const std::function<void()> *g_body = nullptr;
+inline std::vector<unsigned long long> g_dyn;   // dynamic shared memory of the running launch (8-byte aligned)
+inline void *dyn_smem() { return g_dyn.data(); }
 constexpr size_t STACK = 256 * 1024;
 
 inline Fiber *cur() { return &g_fibers[g_cur_index]; }
@@ -102,8 +104,9 @@ inline void fiber_entry() {
 }
 
 // run `body` (a call of the kernel function) for every thread of every block of the grid (1-D blocks)
-inline void launch(dim3 grid, dim3 block, const std::function<void()> &body) {
+inline void launch(dim3 grid, dim3 block, const std::function<void()> &body, size_t dyn_smem_bytes = 0) {
   const int nt = (int)block.x;
+  g_dyn.assign(dyn_smem_bytes / 8 + 1, 0ull);
   if (block.y != 1 || block.z != 1) { fprintf(stderr, "emu: 1-D blocks only\n"); abort(); }
   if ((int)g_fibers.size() < nt) {
     const size_t old = g_fibers.size();

@@ -3,6 +3,7 @@
 // Built and driven by tests/test_kernel_logic_host.py; checks kernel logic against the oracle without a GPU.
 // Test infrastructure only — the product is always the nvcc build.
 #define GHICP_EMU_HOST 1
+#include "../../gh-icp_b200/csrc/ghicp_kernels.cu"
 #include "../../gh-icp_b200/csrc/ghicp_fpfh.cu"
 #include "../../gh-icp_b200/csrc/ghicp_solvers.cu"
 #include "../../gh-icp_b200/csrc/ghicp_prep.cu"
@@ -200,6 +201,104 @@ int emu_detect_keypoints(const float *xyz, int n, float radius, float ratio_max,
                          int *n_kp, float *lam, double *curvature, int *pt_num, int *nms_rounds) {
   return (int)prep_detect_keypoints(nullptr, xyz, n, radius, ratio_max, min_pts, nms_radius, lam, curvature, pt_num, kp_idx, n_kp,
                                     nms_rounds);
+}
+
+// ---- the all-double path of ghicp_kernels.cu: FD build + one loop body, driven in the order of ghicp_capi.cu's exact branch ----
+struct emu_iter_out {
+  int cor; long long nnz;
+  double cd_mean, cd_std, penalty, rmse, rmse_after, fdm, fdstd;
+  double Rt[16];
+};
+// ft: 0 BSC, 2 FPFH, 3 None; ct: 0 NN, 1 NNR, 2 KM (graph build only: rowptr / col / gain returned, no auction).
+// N, M <= 1024 (the cooperative solve is emulated with one block).  Arrays are caller-allocated.
+int emu_exact_iteration(int ft, int ct, int dof, const double *S, const double *T, int N, int M, const uint8_t *bsc_s, int V,
+                        const uint8_t *bsc_t, int bits, const float *fs, const float *fth, float bbx, int iteration, double RMS,
+                        double FDM, double FDstd, double para1, double para2, double pivot, int n_chunks, double *fd_out /*N*M*/,
+                        double *row_cd, int *row_idx, double *col_cd, int *col_idx, int *sp, int *tp, double *S_after,
+                        long long *rowptr, int *csr_col, double *csr_gain, emu_iter_out *out) {
+  Ctx c;
+  c.cfg.feature_type = ft; c.cfg.corr_type = ct; c.cfg.dof = dof;
+  c.N = N; c.M = M; c.n_chunks = n_chunks; c.r0 = 0; c.nloc = N; c.world = 1; c.rank = 0; c.shard = N; c.Npad = N;
+  std::vector<double> s(S, S + 3 * (size_t)N), t(T, T + 3 * (size_t)M);
+  c.d_s = s.data(); c.d_t = t.data();
+  const size_t L = (size_t)N * n_chunks;
+  const int nmax = N > M ? N : M;
+  std::vector<double> part_cd(L), part_stats(2 * (size_t)((N + 7) / 8) * n_chunks + 2), xstats(4, 0.0), rcd(N), ccd(M), solve_part(3 * 64 * 12);
+  std::vector<int> part_idx(L), ridx(N, 0), cidx(M, 0), vsp(nmax), vtp(nmax), cnt(L + 2, 0), cursor(L + 1, 0);
+  std::vector<long long> vrowptr(L + 1, 0), tile_sum(2 * ((std::max(L, (size_t)nmax) + 1023) / 1024 + 1) + 2);
+  std::vector<float> row_fd(N, 0.f), pair_fd(nmax, 0.f);
+  DevIter it; memset(&it, 0, sizeof(it));
+  c.d_part_cd = part_cd.data(); c.d_part_idx = part_idx.data(); c.d_part_stats = part_stats.data(); c.part_stats_cap = part_stats.size();
+  c.d_xstats = xstats.data(); c.d_row_cd = rcd.data(); c.d_row_idx = ridx.data(); c.d_col_cd = ccd.data(); c.d_col_idx = cidx.data();
+  c.d_row_fd = row_fd.data(); c.d_pair_fd = pair_fd.data(); c.d_sp = vsp.data(); c.d_tp = vtp.data(); c.d_iter = &it;
+  c.d_cnt = cnt.data(); c.d_cursor = cursor.data(); c.d_rowptr = vrowptr.data();
+  c.d_tile_sum = tile_sum.data(); c.tile_cap = tile_sum.size(); c.d_solve_part = solve_part.data();
+  // one-time FD build (calFD_BSC via the POPC kernel / calFD_FPFH into the stored plane)
+  std::vector<uint64_t> bs, bt; std::vector<uint16_t> fd16; std::vector<float> fdf, hfs, hft;
+  c.fd_rows = (size_t)N;
+  if (ft == GHICP_FT_BSC) {
+    c.V = V; c.bits = bits; c.Bbytes = (bits + 7) / 8; c.W64 = (c.Bbytes + 7) / 8;
+    bs.assign((size_t)V * c.W64 * N, 0); bt.assign((size_t)c.W64 * M, 0);
+    c.d_bs = bs.data(); c.d_bt = bt.data();
+    launch_pack_bsc(&c, bsc_s, bsc_t);
+    fd16.assign(fd_elems(c.fd_rows, M), 0);
+    c.d_fd16 = fd16.data();
+    launch_fd_bsc(&c);
+  } else if (ft == GHICP_FT_FPFH) {
+    hfs.assign(fs, fs + (size_t)N * 33); hft.assign(fth, fth + (size_t)M * 33);
+    c.d_fs = hfs.data(); c.d_ft = hft.data();
+    fdf.assign(fd_elems(c.fd_rows, M), 0.f);
+    c.d_fdf = fdf.data();
+    launch_fd_fpfh(&c);
+  }
+  if (fd_out) launch_get_fd(&c, fd_out);
+  // loop scalars as ghicp_capi.cu builds them
+  CostParams cp;
+  const float scale_f = 0.005 * bbx;
+  cp.scale = (double)scale_f;
+  cp.WFD = exp(-1.0 * iteration / 6);
+  cp.WED = 1.0 - cp.WFD;
+  cp.ex = 1.0 / (iteration + 1);
+  cp.pivot = pivot;
+  LoopScalars ls;
+  ls.iteration = iteration; ls.RMS = RMS; ls.FDM = FDM; ls.FDstd = FDstd; ls.para1 = para1; ls.para2 = para2;
+  ls.scale = cp.scale; ls.WED = cp.WED; ls.WFD = cp.WFD; ls.penalty_initial = 2.0;
+  launch_rowsweep(&c, 0, cp);
+  launch_finalize_stats(&c, cp, ls);
+  if (ct == GHICP_CT_NNR) launch_colsweep(&c, cp);
+  launch_penalty(&c, cp.pivot, ls);
+  if (ct == GHICP_CT_NN) launch_select_nn(&c, 0.0);
+  else if (ct == GHICP_CT_NNR) launch_select_nnr(&c);
+  else {
+    launch_rowsweep(&c, 1, cp);
+    launch_scan_counts(&c);
+    const long long nnz = it.nnz;
+    std::vector<int> vcol((size_t)nnz + 1); std::vector<double> vgain((size_t)nnz + 1); std::vector<float> vfd((size_t)nnz + 1);
+    c.d_csr_col = vcol.data(); c.d_csr_gain = vgain.data(); c.d_csr_fd = vfd.data();
+    if (nnz > 0) launch_rowsweep(&c, 2, cp);
+    for (int i = 0; i <= N; ++i) rowptr[i] = vrowptr[(size_t)i * n_chunks];
+    for (long long k = 0; k < nnz; ++k) { csr_col[k] = vcol[k]; csr_gain[k] = vgain[k]; }
+    out->nnz = nnz; out->cd_mean = it.cd_mean; out->cd_std = it.cd_std; out->penalty = it.penalty;
+    for (int i = 0; i < N; ++i) { row_cd[i] = rcd[i]; row_idx[i] = ridx[i]; }
+    return 0;
+  }
+  launch_solve(&c, cp);
+  launch_apply(&c);
+  for (int i = 0; i < N; ++i) { row_cd[i] = rcd[i]; row_idx[i] = ridx[i]; }
+  if (ct == GHICP_CT_NNR) for (int j = 0; j < M; ++j) { col_cd[j] = ccd[j]; col_idx[j] = cidx[j]; }
+  for (int k = 0; k < it.cor; ++k) { sp[k] = vsp[k]; tp[k] = vtp[k]; }
+  memcpy(S_after, s.data(), sizeof(double) * 3 * (size_t)N);
+  out->cor = it.cor; out->nnz = 0; out->cd_mean = it.cd_mean; out->cd_std = it.cd_std; out->penalty = it.penalty;
+  out->rmse = it.rmse; out->rmse_after = it.rmse_after; out->fdm = it.fdm; out->fdstd = it.fdstd;
+  memcpy(out->Rt, it.Rt, sizeof(it.Rt));
+  return 0;
+}
+// stand-alone rigid fit kernel (ghicp_rigid_fit)
+int emu_rigid_fit(const double *s, const double *t, int n, double *Rt) {
+  DevIter it; memset(&it, 0, sizeof(it));
+  launch_solve_explicit(nullptr, s, t, n, &it);
+  memcpy(Rt, it.Rt, sizeof(it.Rt));
+  return 0;
 }
 
 }  // extern "C"
