@@ -22,15 +22,8 @@ class IterOut(C.Structure):
 
 
 @pytest.fixture(scope="module")
-def emu(tmp_path_factory):
-    out = tmp_path_factory.mktemp("emu_core") / "libkernel_logic_harness.so"
-    src = os.path.join(ROOT, "tests", "harness", "kernel_logic_harness.cpp")
-    extra = os.environ.get("GHICP_EMU_CXXFLAGS", "").split()
-    r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-DGHICP_EMU_HOST"] + extra +
-                       ["-I" + os.path.join(ROOT, "tests", "harness", "cuda_emu"), "-x", "c++", "-shared", "-o", str(out), src],
-                       capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr[-3000:]
-    L = C.CDLL(str(out))
+def emu(emu_harness_path):
+    L = C.CDLL(emu_harness_path)
     L.emu_exact_iteration.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                       C.c_void_p, C.c_void_p, C.c_float, C.c_int] + [C.c_double] * 6 + [C.c_int, dp, dp, ip, dp, ip,
                                       ip, ip, dp, lp, ip, dp, C.POINTER(IterOut)]

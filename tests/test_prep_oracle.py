@@ -127,17 +127,8 @@ def test_keypoints_satisfy_the_greedy_nms_definition(orc):
 
 # ---- product kernels on the CPU (emulation) vs the oracle: bit for bit -----------------------------------------------------
 @pytest.fixture(scope="module")
-def emu(tmp_path_factory):
-    out = tmp_path_factory.mktemp("emu_prep") / "libkernel_logic_harness.so"
-    src = os.path.join(ROOT, "tests", "harness", "kernel_logic_harness.cpp")
-    # GHICP_EMU_CXXFLAGS="-fsanitize=address,undefined -fno-omit-frame-pointer" (with LD_PRELOAD=libasan.so) runs the
-    # emulated kernels under the sanitizers: out-of-bounds accesses of a kernel show up on the CPU
-    extra = os.environ.get("GHICP_EMU_CXXFLAGS", "").split()
-    r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-DGHICP_EMU_HOST"] + extra +
-                       ["-I" + os.path.join(ROOT, "tests", "harness", "cuda_emu"), "-x", "c++", "-shared", "-o", str(out), src],
-                       capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr[-3000:]
-    L = C.CDLL(str(out))
+def emu(emu_harness_path):
+    L = C.CDLL(emu_harness_path)
     L.emu_voxel_downsample.argtypes = [fp, C.c_int, C.c_float, ip, ip]
     L.emu_detect_keypoints.argtypes = [fp, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, ip, ip, fp, dp, ip, ip]
     return L
