@@ -331,7 +331,11 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
   const int gthreads = gridDim.x * blockDim.x;
   int cur = 0, rounds = 0;
   unsigned long long t_mark = 0;
+#if defined(GHICP_EMU_HOST)
+  auto now_ns = []() { return 0ull; };   // host emulation: no device timer
+#else
   auto now_ns = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+#endif
   while (true) {
     const int n = ldcg_i(&a.counters[cur]);
     if (n == 0 || rounds >= max_rounds) break;
@@ -506,7 +510,7 @@ cudaError_t launch_build_csc(Ctx *c, int n_rows, int n_cols, long long nnz) {
   cudaError_t e;
   if ((e = cudaMemsetAsync(c->d_colcnt, 0, sizeof(int) * (size_t)(n_cols + 1), c->stream)) != cudaSuccess) return e;
   if (nnz > 0) {
-    k_col_count<<<(unsigned)((nnz + 255) / 256), 256, 0, c->stream>>>(c->d_csr_col, nnz, c->d_colcnt);
+    GHICP_LAUNCH(k_col_count, (unsigned)((nnz + 255) / 256), 256, 0, c->stream, c->d_csr_col, nnz, c->d_colcnt);
     c->launches++;
   }
   // cursor reuse: d_bid_obj is free before the auction starts
@@ -515,7 +519,7 @@ cudaError_t launch_build_csc(Ctx *c, int n_rows, int n_cols, long long nnz) {
     if (e != cudaSuccess) return e;
   }
   if (nnz > 0) {
-    k_csc_fill<<<AUC_GRID, AUC_BLOCK, 0, c->stream>>>(n_rows, c->d_rowptr, c->n_chunks, c->d_csr_col, c->d_csr_gain,
+    GHICP_LAUNCH(k_csc_fill, AUC_GRID, AUC_BLOCK, 0, c->stream, n_rows, c->d_rowptr, c->n_chunks, c->d_csr_col, c->d_csr_gain,
                                                        c->d_colptr, c->d_bid_obj, c->d_csc_row, c->d_csc_gain);
     c->launches++;
   }
@@ -535,7 +539,7 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
   int *base_list = c->d_flags;  // free during KM
 
   cudaMemsetAsync(c->d_counters, 0, sizeof(int) * 16, st);
-  k_auc_init<<<gmax, 256, 0, st>>>(n_rows, n_cols, c->d_rowptr, c->n_chunks, c->d_price, base_list, c->d_counters,
+  GHICP_LAUNCH(k_auc_init, gmax, 256, 0, st, n_rows, n_cols, c->d_rowptr, c->n_chunks, c->d_price, base_list, c->d_counters,
                                    c->d_bidmax, c->d_bidwin, nmax);
   c->launches++;
   cudaMemsetAsync(c->d_bid_obj, 0xff, sizeof(int) * (size_t)nmax, st);  // -1
@@ -577,13 +581,14 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
   int small_rev = (int)(65536.0 / (avg_col > 1.0 ? avg_col : 1.0));
   small_fwd = small_fwd < 16 ? 16 : (small_fwd > PA_SMALL ? PA_SMALL : small_fwd);
   small_rev = small_rev < 16 ? 16 : (small_rev > PA_SMALL ? PA_SMALL : small_rev);
+  if (const char *ov = getenv("GHICP_AUCTION_SMALL")) small_fwd = small_rev = atoi(ov);  // experiment / test hook: 0 = grid rounds only
   const bool debug = getenv("GHICP_AUCTION_DEBUG") != nullptr;
   const double relax_factor = getenv("GHICP_AUCTION_RELAX") ? atof(getenv("GHICP_AUCTION_RELAX")) : 0.0;
   int last_rounds = 0;
   bool ran_reverse = false;
   for (size_t ph = 0; ph < eps_list.size(); ++ph) {
     a.eps = eps_list[ph];
-    k_auc_phase_start<<<gmax, 256, 0, st>>>(n_rows, n_cols, c->d_rowptr, c->n_chunks, c->d_assign, c->d_owner,
+    GHICP_LAUNCH(k_auc_phase_start, gmax, 256, 0, st, n_rows, n_cols, c->d_rowptr, c->n_chunks, c->d_assign, c->d_owner,
                                             c->d_profit, c->d_price, ph > 0 ? relax_factor * eps_list[ph - 1] : 0.0);
     c->launches++;
     cudaMemcpyAsync(c->d_list[0], base_list, sizeof(int) * (size_t)n_rows, cudaMemcpyDeviceToDevice, st);
@@ -594,8 +599,14 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
       int mr = max_rounds;
       int sn = small_fwd;
       void *args[] = {(void *)&a, (void *)&l0, (void *)&l1, (void *)&mr, (void *)&sn};
+#if defined(GHICP_EMU_HOST)
+      (void)args;   // host emulation: all blocks of the (small) grid run as fibers, the grid barrier is a rendezvous
+      emu::launch_cooperative(dim3(n_sm * coop_blocks_per_sm[0]), dim3(PA_THREADS), [&] { k_auction_persistent<false>(a, l0, l1, mr, sn); });
+      cudaError_t e = cudaSuccess;
+#else
       cudaError_t e = cudaLaunchCooperativeKernel((void *)k_auction_persistent<false>, dim3(n_sm * coop_blocks_per_sm[0]),
                                                   dim3(PA_THREADS), args, 0, st);
+#endif
       if (e != cudaSuccess) { set_error(c, std::string("auction forward launch: ") + cudaGetErrorString(e)); return GHICP_E_CUDA; }
       c->launches++;
     }
@@ -606,7 +617,7 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
     if (ph + 1 == eps_list.size()) {
       double *d_D = reinterpret_cast<double *>(c->d_bid_aux);  // free scratch between rounds
       cudaMemsetAsync(d_D, 0, sizeof(double), st);
-      k_free_price_sum<<<148, 256, 0, st>>>(n_cols, c->d_owner, c->d_price, d_D);
+      GHICP_LAUNCH(k_free_price_sum, 148, 256, 0, st, n_cols, c->d_owner, c->d_price, d_D);
       c->launches++;
       double D = 0.0;
       cudaMemcpyAsync(&D, d_D, sizeof(double), cudaMemcpyDeviceToHost, st);
@@ -619,7 +630,7 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
     if (need_reverse) {
     ran_reverse = true;
     cudaMemsetAsync(&c->d_counters[0], 0, sizeof(int) * 2, st);
-    k_rev_collect<<<gmax, 256, 0, st>>>(n_cols, c->d_owner, c->d_price, c->d_list[0], c->d_counters, 0);
+    GHICP_LAUNCH(k_rev_collect, gmax, 256, 0, st, n_cols, c->d_owner, c->d_price, c->d_list[0], c->d_counters, 0);
     c->launches++;
     cudaMemsetAsync(c->d_bid_obj, 0xff, sizeof(int) * (size_t)nmax, st);
     {
@@ -627,8 +638,14 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
       int mr = max_rounds;
       int sn = small_rev;
       void *args[] = {(void *)&a, (void *)&l0, (void *)&l1, (void *)&mr, (void *)&sn};
+#if defined(GHICP_EMU_HOST)
+      (void)args;
+      emu::launch_cooperative(dim3(n_sm * coop_blocks_per_sm[1]), dim3(PA_THREADS), [&] { k_auction_persistent<true>(a, l0, l1, mr, sn); });
+      cudaError_t e = cudaSuccess;
+#else
       cudaError_t e = cudaLaunchCooperativeKernel((void *)k_auction_persistent<true>, dim3(n_sm * coop_blocks_per_sm[1]),
                                                   dim3(PA_THREADS), args, 0, st);
+#endif
       if (e != cudaSuccess) { set_error(c, std::string("auction reverse launch: ") + cudaGetErrorString(e)); return GHICP_E_CUDA; }
       c->launches++;
     }

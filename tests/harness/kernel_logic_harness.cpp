@@ -4,6 +4,7 @@
 // Test infrastructure only — the product is always the nvcc build.
 #define GHICP_EMU_HOST 1
 #include "../../gh-icp_b200/csrc/ghicp_kernels.cu"
+#include "../../gh-icp_b200/csrc/ghicp_auction.cu"
 #include "../../gh-icp_b200/csrc/ghicp_fpfh.cu"
 #include "../../gh-icp_b200/csrc/ghicp_solvers.cu"
 #include "../../gh-icp_b200/csrc/ghicp_prep.cu"
@@ -11,6 +12,11 @@
 #include <vector>
 
 using namespace ghicp_b200;
+
+// the product's set_error lives in ghicp_capi.cu (not part of this harness)
+namespace ghicp_b200 {
+void set_error(Ctx *c, const std::string &msg) { if (c) c->err = msg; fprintf(stderr, "emu set_error: %s\n", msg.c_str()); }
+}
 
 namespace {
 struct Host {
@@ -291,6 +297,38 @@ int emu_exact_iteration(int ft, int ct, int dof, const double *S, const double *
   out->cor = it.cor; out->nnz = 0; out->cd_mean = it.cd_mean; out->cd_std = it.cd_std; out->penalty = it.penalty;
   out->rmse = it.rmse; out->rmse_after = it.rmse_after; out->fdm = it.fdm; out->fdstd = it.fdstd;
   memcpy(out->Rt, it.Rt, sizeof(it.Rt));
+  return 0;
+}
+// ---- ghicp_auction.cu: CSC build + the whole epsilon-scaled forward/reverse auction, driven by km_auction itself ----
+// CSR input like ghicp_km_solve builds it (n_chunks = 1).  The persistent kernels run as an emulated cooperative launch of
+// "2 SMs x 1 CTA".  owner[M] / assign[N] = the matching, rounds/phases = what the driver reports.
+int emu_km_auction(int N, int M, const long long *rowptr, const int *col, const double *gain, double eps, double max_gain,
+                   int *owner, int *assign, double *price, int *rounds, int *phases) {
+  Ctx c;
+  c.N = N; c.M = M; c.n_chunks = 1; c.Npad = N; c.device = 0;
+  const int nmax = N > M ? N : M;
+  const long long nnz = rowptr[N];
+  std::vector<long long> vrowptr(rowptr, rowptr + N + 1), colptr((size_t)M + 2, 0), tile_sum(2 * ((size_t)(nmax + 1023) / 1024 + 1) + 2);
+  std::vector<int> vcol(col, col + nnz), colcnt((size_t)M + 2, 0), csc_row((size_t)nnz + 1), vassign(nmax), vowner(nmax), bidwin(nmax),
+      bid_obj(nmax), l0(nmax), l1(nmax), counters(16, 0), hcount(16, 0), flags(nmax);
+  std::vector<double> vgain(gain, gain + nnz), csc_gain((size_t)nnz + 1), vprice(nmax, 0.0), profit(nmax, 0.0), bid_val(nmax), bid_aux((size_t)nmax + 2);
+  std::vector<unsigned long long> bidmax(nmax, 0ull);
+  vcol.resize((size_t)nnz + 1); vgain.resize((size_t)nnz + 1);
+  c.d_rowptr = vrowptr.data(); c.d_csr_col = vcol.data(); c.d_csr_gain = vgain.data();
+  c.d_colptr = colptr.data(); c.d_colcnt = colcnt.data(); c.d_csc_row = csc_row.data(); c.d_csc_gain = csc_gain.data();
+  c.d_price = vprice.data(); c.d_profit = profit.data(); c.d_assign = vassign.data(); c.d_owner = vowner.data();
+  c.d_bidmax = bidmax.data(); c.d_bidwin = bidwin.data(); c.d_bid_obj = bid_obj.data();
+  c.d_bid_val = bid_val.data(); c.d_bid_aux = bid_aux.data();
+  c.d_list[0] = l0.data(); c.d_list[1] = l1.data(); c.d_counters = counters.data(); c.h_counters = hcount.data();
+  c.d_flags = flags.data(); c.d_tile_sum = tile_sum.data(); c.tile_cap = tile_sum.size();
+  if (launch_build_csc(&c, N, M, nnz) != cudaSuccess) return -1;
+  KmResult kres;
+  const int rc = km_auction(&c, N, M, nnz, eps, max_gain, &kres);
+  c.h_counters = nullptr;   // not ours to free
+  if (rc) return rc;
+  for (int j = 0; j < M; ++j) { owner[j] = vowner[j]; price[j] = vprice[j]; }
+  for (int i = 0; i < N; ++i) assign[i] = vassign[i];
+  *rounds = kres.rounds; *phases = kres.phases;
   return 0;
 }
 // stand-alone rigid fit kernel (ghicp_rigid_fit)
