@@ -108,6 +108,8 @@ def lib():
     fpp = C.POINTER(C.c_float)
     L.ghicp_voxel_downsample.argtypes = [C.c_int, fpp, C.c_int, C.c_float, ip, ip]
     L.ghicp_detect_keypoints.argtypes = [C.c_int, fpp, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, ip, ip, fpp, dp, ip]
+    L.ghicp_bsc_extract.argtypes = [C.c_int, fpp, C.c_int, ip, C.c_int, C.c_float, C.c_int, ip, C.c_int, vp, ip, fpp, ip]
+    L.ghicp_bsc_default_pattern.argtypes = [C.c_int, ip]
     L.ghicp_comm_unique_id.argtypes = [vp]
     L.ghicp_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
     _lib = L
@@ -174,6 +176,41 @@ def detect_keypoints(xyz, radius, ratio_max=0.65, min_pts=20, nms_radius=None, d
                                        nms_radius if nms_radius is not None else radius, _ip(kp), C.byref(m),
                                        lam.ctypes.data_as(C.POINTER(C.c_float)), _dp(curv), _ip(cnt)))
     return kp[:m.value].copy(), lam, curv, cnt
+
+
+def bsc_default_pattern(side=7):
+    """The grid-pair sampling pattern of the reference's BSCEncoder constructor (binary_feature_extraction.hpp:75-103) in a
+    fresh process = the sample_pattern.txt its users generate.  [side*side][2] int32; only side 7 is shipped."""
+    pairs = np.zeros((side * side, 2), np.int32)
+    check(lib().ghicp_bsc_default_pattern(side, _ip(pairs)))
+    return pairs
+
+
+def read_sample_pattern(path, side=7):
+    """sample_pattern.txt as the reference reads it (:107-116): side*side lines of two cell indices."""
+    vals = np.loadtxt(path, dtype=np.int64).reshape(-1, 2)
+    if len(vals) < side * side:
+        raise GhicpError(-1, f"{path}: expected {side * side} pairs, found {len(vals)}")
+    return np.ascontiguousarray(vals[:side * side], dtype=np.int32)
+
+
+def bsc_extract(xyz, kp_idx, extract_radius, dof_type=6, side=7, pairs=None, device=0):
+    """BSCEncoder::extractBinaryFeatures (include/binary_feature_extraction.hpp:603-676) on the GPU.
+    Returns (features [V][nkp][ceil(9 side^2 / 8)] uint8, lrf [nkp][12] float32, status [nkp]); V = 1 / 2 / 4 for
+    dof_type 0 / 1..4 / > 4, the layout Keypoints.setBSCfeature / ghicp_set_bsc take (bits = 9 side^2)."""
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+    kp_idx = np.ascontiguousarray(kp_idx, dtype=np.int32)
+    pairs = bsc_default_pattern(side) if pairs is None else np.ascontiguousarray(pairs, dtype=np.int32)
+    nkp = len(kp_idx)
+    nbytes = (9 * side * side + 7) // 8
+    feats = np.zeros((4, nkp, nbytes), np.uint8)
+    lrf, status, V = np.zeros((nkp, 12), np.float32), np.zeros(nkp, np.int32), C.c_int(0)
+    check(lib().ghicp_bsc_extract(device, xyz.ctypes.data_as(C.POINTER(C.c_float)), len(xyz), _ip(kp_idx), nkp, extract_radius,
+                                  side, _ip(pairs), dof_type, feats.ctypes.data, C.byref(V),
+                                  lrf.ctypes.data_as(C.POINTER(C.c_float)), _ip(status)))
+    # the ABI writes [V][nkp][bytes] contiguously: re-view the first V * nkp * bytes bytes with that shape
+    out = feats.reshape(-1)[:V.value * nkp * nbytes].reshape(V.value, nkp, nbytes).copy()
+    return out, lrf, status
 
 
 def rigid_fit_ex(S, T, solver=SOLVER_SVD, normals=None, weights=None, device=0):

@@ -1030,6 +1030,64 @@ int ghicp_detect_keypoints(int device, const float *xyz, int n, float radius, fl
   return GHICP_OK;
 }
 
+int ghicp_bsc_extract(int device, const float *xyz, int n, const int *kp_idx, int nkp, float extract_radius, int voxel_side_num,
+                      const int *pairs, int dof_type, unsigned char *features, int *n_variants, float *lrf, int *status) {
+  if (!xyz || !kp_idx || !pairs || !features || n <= 0 || nkp <= 0 || !(extract_radius > 0.f) || voxel_side_num < 1 ||
+      voxel_side_num > 9) {
+    set_error(nullptr, "bsc_extract: bad argument");
+    return GHICP_E_ARG;
+  }
+  const int S2 = voxel_side_num * voxel_side_num;
+  for (int i = 0; i < nkp; ++i) if (kp_idx[i] < 0 || kp_idx[i] >= n) { set_error(nullptr, "bsc_extract: keypoint index out of range"); return GHICP_E_ARG; }
+  for (int i = 0; i < 2 * S2; ++i) if (pairs[i] < 0 || pairs[i] >= S2) { set_error(nullptr, "bsc_extract: sampling pair out of range"); return GHICP_E_ARG; }
+  if (ghicp_device_count() <= 0) { set_error(nullptr, "bsc_extract: no CUDA device"); return GHICP_E_NODEV; }
+  if (cudaSetDevice(device) != cudaSuccess) return GHICP_E_CUDA;
+  const int V = dof_type > 4 ? 4 : (dof_type > 0 ? 2 : 1);
+  const size_t nbytes = (size_t)(9 * S2 + 7) / 8, out_bytes = (size_t)V * nkp * nbytes;
+  float *d_xyz = nullptr, *d_lrf = nullptr; int *d_kp = nullptr, *d_pairs = nullptr, *d_status = nullptr; unsigned char *d_bits = nullptr;
+  cudaError_t e = cudaMalloc((void **)&d_xyz, 3 * (size_t)n * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&d_kp, (size_t)nkp * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&d_pairs, 2 * (size_t)S2 * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&d_bits, out_bytes);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&d_lrf, 12 * (size_t)nkp * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&d_status, (size_t)nkp * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemcpy(d_xyz, xyz, 3 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_kp, kp_idx, (size_t)nkp * sizeof(int), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_pairs, pairs, 2 * (size_t)S2 * sizeof(int), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = prep_bsc_extract(0, d_xyz, n, d_kp, nkp, extract_radius, voxel_side_num, d_pairs, dof_type, d_bits, d_lrf, d_status);
+  if (e == cudaSuccess) e = cudaMemcpy(features, d_bits, out_bytes, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && lrf) e = cudaMemcpy(lrf, d_lrf, 12 * (size_t)nkp * sizeof(float), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && status) e = cudaMemcpy(status, d_status, (size_t)nkp * sizeof(int), cudaMemcpyDeviceToHost);
+  if (d_xyz) cudaFree(d_xyz);
+  if (d_kp) cudaFree(d_kp);
+  if (d_pairs) cudaFree(d_pairs);
+  if (d_bits) cudaFree(d_bits);
+  if (d_lrf) cudaFree(d_lrf);
+  if (d_status) cudaFree(d_status);
+  if (e != cudaSuccess) { set_error(nullptr, std::string("bsc_extract: ") + cudaGetErrorString(e)); cudaGetLastError(); return e == cudaErrorMemoryAllocation ? GHICP_E_NOMEM : GHICP_E_CUDA; }
+  if (n_variants) *n_variants = V;
+  return GHICP_OK;
+}
+
+// The sampling pattern of the grid-pair comparisons for voxel_side_num = 7: what the reference's BSCEncoder constructor
+// generates with build_sample_pattern = true (include/binary_feature_extraction.hpp:75-103) in a process that has not called
+// srand — glibc's rand() sequence for seed 1 — i.e. the sample_pattern.txt a user of the reference produces; the reference
+// itself ships none.  Generated by tests/golden/make_bsc_golden.py through the reference's own constructor.
+static const int kBscPattern7[49][2] = {
+    {15, 39}, {37, 5}, {29, 10}, {24, 23}, {8, 17}, {9, 47}, {6, 18},
+    {20, 21}, {17, 22}, {3, 21}, {30, 47}, {33, 48}, {29, 5}, {5, 0},
+    {45, 47}, {10, 30}, {8, 35}, {9, 16}, {8, 18}, {19, 14}, {41, 45},
+    {41, 9}, {23, 15}, {38, 26}, {42, 43}, {46, 4}, {22, 31}, {9, 27},
+    {32, 5}, {31, 47}, {40, 39}, {38, 0}, {12, 3}, {23, 31}, {17, 16},
+    {32, 14}, {30, 7}, {35, 24}, {33, 28}, {18, 4}, {7, 16}, {8, 29},
+    {47, 18}, {12, 35}, {28, 43}, {39, 20}, {39, 28}, {25, 7}, {31, 0},
+};
+int ghicp_bsc_default_pattern(int voxel_side_num, int *pairs) {
+  if (!pairs || voxel_side_num != 7) { set_error(nullptr, "bsc_default_pattern: only voxel_side_num = 7 has a shipped pattern"); return GHICP_E_ARG; }
+  for (int i = 0; i < 49; ++i) { pairs[2 * i] = kBscPattern7[i][0]; pairs[2 * i + 1] = kBscPattern7[i][1]; }
+  return GHICP_OK;
+}
+
 int ghicp_comm_unique_id(void *id128) {
   if (!id128) return GHICP_E_ARG;
   return comm_unique_id(id128);

@@ -279,6 +279,9 @@ cudaError_t prep_voxel_downsample(cudaStream_t st, const float *d_xyz, int n, fl
 cudaError_t prep_detect_keypoints(cudaStream_t st, const float *d_xyz, int n, float radius, float ratio_max, int min_pts,
                                   float nms_radius, float *d_lam, double *d_curv, int *d_cnt, int *d_kp, int *n_kp,
                                   int *nms_rounds);
+// BSCEncoder::extractBinaryFeatures (include/binary_feature_extraction.hpp:603-676) on device arrays, see ghicp_prep.cu
+cudaError_t prep_bsc_extract(cudaStream_t st, const float *d_xyz, int n, const int *d_kp, int nkp, float R, int side,
+                             const int *d_pairs, int dof_type, unsigned char *d_bits, float *d_lrf, int *d_status);
 
 // ---- streaming path (ghicp_stream.cu) -----------------------------------------------------------
 cudaError_t launch_stream_prep(Ctx *c, const CostParams &cp, int for_km_gate);

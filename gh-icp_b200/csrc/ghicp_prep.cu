@@ -21,6 +21,7 @@
 #include <cstring>
 
 #include "ghicp_internal.h"
+#include "ghicp_device.cuh"
 
 #if !defined(GHICP_EMU_HOST)
 #include <cub/cub.cuh>
@@ -437,6 +438,361 @@ cudaError_t prep_detect_keypoints(cudaStream_t st, const float *d_xyz, int n, fl
 done:
   pfree(order); pfree(ucell); pfree(cstart); pfree(order2); pfree(ucell2); pfree(cstart2);
   pfree(d_flags); pfree(d_pos); pfree(d_cand); pfree(d_state); pfree(d_und); pfree(d_keys);
+  return err;
+}
+
+
+// =====================================================================================================================
+// BSC descriptor encoder: BSCEncoder::extractBinaryFeatures, include/binary_feature_extraction.hpp
+// :603-676 — per keypoint the weighted-PCA local frame (:940-1035, :123-160), the change of frame (:163-196, :1085-1138),
+// the three projected Gaussian-weighted side x side grids (:197-373), the 9 side^2-bit descriptor (:464-565) and its
+// re-arranged variants (:678-837).  The reference walks three KD-trees per keypoint on one thread; here one CTA per
+// keypoint walks the 27 cells of a uniform grid (edge = search radius sqrt(3) R) three times:
+//   pass A  neighbour count, centroid and the weight sum            (double sums)
+//   pass B  weighted covariance about the centroid                  (double sums, rounded once to float32)
+//   thread 0: eigenvectors (cyclic Jacobi in double, sign "largest component positive"), the frame, the float32
+//            Umeyama fit of the unit axes onto it and its inverse — the reference's own roundabout route to the rotation
+//   pass C  every neighbour, moved to the frame in float32, adds exp(-d^2 / 2 delta^2) to the cells whose centre lies
+//            within 1.5 cell edges in each projection.  The sums are FIXED-POINT integer atomics in shared memory
+//            (weights are float32 in (2^-7, 1]: w * 2^40 is an exact integer), so the result does not depend on the order
+//            in which threads arrive: the descriptor is deterministic run to run.
+// Where the reference accumulates in float32 in KD-tree result order (covariance, depth sums) this kernel holds the exact
+// sum instead; the two differ by float32 accumulation error (~1e-7 relative), which moves a descriptor bit only when a
+// comparison is that close to its threshold — tests/ state the tolerance.  Variants 1..3 reproduce the reference's
+// ReArrangeGrid quirk: the re-arranged grid is APPENDED to 3 side^2 empty cells (:693-695 after :788), so those
+// descriptors carry the occupancy bits of the re-arranged grid at bit offset 3 side^2 and nothing else.
+// =====================================================================================================================
+namespace {
+
+constexpr int BSC_T = 128;          // threads per keypoint
+constexpr int BSC_MAX_SIDE = 9;     // grids up to 9 x 9 (the reference uses 7)
+constexpr int BSC_MAX_CELLS = 3 * BSC_MAX_SIDE * BSC_MAX_SIDE;
+
+struct BscArgs {
+  GridArgs g;
+  const int *kp; int nkp;
+  float R; int side; const int *pairs; int V;
+  unsigned char *bits; int nbytes; float *lrf; int *status;
+};
+
+// symmetric 3x3 eigen-decomposition in double (the convention of oracle/stub/Eigen/Eigenvalues, substitution S1)
+__device__ void bsc_jacobi3(double a[3][3], double V[3][3], double w[3]) {
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 64; ++sweep) {
+    double off = 0.0;
+    for (int p = 0; p < 3; ++p) for (int q = p + 1; q < 3; ++q) off += a[p][q] * a[p][q];
+    if (off == 0.0) break;
+    for (int p = 0; p < 3; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        if (a[p][q] == 0.0) continue;
+        const double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < 3; ++k) { const double x = a[k][p], y = a[k][q]; a[k][p] = c * x - s * y; a[k][q] = s * x + c * y; }
+        for (int k = 0; k < 3; ++k) { const double x = a[p][k], y = a[q][k]; a[p][k] = c * x - s * y; a[q][k] = s * x + c * y; }
+        for (int k = 0; k < 3; ++k) { const double x = V[k][p], y = V[k][q]; V[k][p] = c * x - s * y; V[k][q] = s * x + c * y; }
+      }
+  }
+  for (int j = 0; j < 3; ++j) {
+    w[j] = a[j][j];
+    int big = 0;
+    for (int i = 1; i < 3; ++i) if (fabs(V[i][j]) > fabs(V[big][j])) big = i;
+    if (V[big][j] < 0.0) for (int i = 0; i < 3; ++i) V[i][j] = -V[i][j];
+  }
+}
+// inverse of a 4x4 float matrix (column-major) through double Gauss-Jordan, rounded to float (substitution S2)
+__device__ void bsc_inverse4(const float m[16], float out[16]) {
+  double a[4][8];
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { a[i][j] = (double)m[j * 4 + i]; a[i][4 + j] = (i == j) ? 1.0 : 0.0; }
+  for (int c = 0; c < 4; ++c) {
+    int p = c;
+    for (int i = c + 1; i < 4; ++i) if (fabs(a[i][c]) > fabs(a[p][c])) p = i;
+    for (int j = 0; j < 8; ++j) { const double t = a[c][j]; a[c][j] = a[p][j]; a[p][j] = t; }
+    const double d = a[c][c];
+    for (int j = 0; j < 8; ++j) a[c][j] /= d;
+    for (int i = 0; i < 4; ++i) if (i != c) { const double f = a[i][c]; for (int j = 0; j < 8; ++j) a[i][j] -= f * a[c][j]; }
+  }
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) out[j * 4 + i] = (float)a[i][4 + j];
+}
+__device__ __forceinline__ void bsc_cross(const float a[3], const float b[3], float o[3]) {
+  o[0] = a[1] * b[2] - a[2] * b[1];
+  o[1] = a[2] * b[0] - a[0] * b[2];
+  o[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ void bsc_normalize(float a[3]) {
+  float z = a[0] * a[0];
+  z = z + a[1] * a[1];
+  z = z + a[2] * a[2];
+  if (z > 0.f) { const float n = sqrtf(z); a[0] = a[0] / n; a[1] = a[1] / n; a[2] = a[2] / n; }
+}
+// index of the source cell of re-arranged cell k of one plane (ReArrange_2D :701-757)
+__device__ __forceinline__ int bsc_rearranged(int tr, int k, int side) {
+  const int i = k / side, j = k % side;
+  return tr == 1 ? side * side - 1 - k : (tr == 2 ? (side - 1 - i) * side + j : i * side + side - 1 - j);
+}
+
+__global__ void __launch_bounds__(BSC_T) k_bsc(const BscArgs a) {
+  __shared__ int s_lo[27], s_hi[27];
+  __shared__ unsigned long long s_num[BSC_MAX_CELLS];
+  __shared__ long long s_dep[BSC_MAX_CELLS];
+  __shared__ float s_depth[BSC_MAX_CELLS], s_npw[BSC_MAX_CELLS];
+  __shared__ double s_red[10 * (BSC_T / 32)];
+  __shared__ double s_c[4];            // centroid, weight sum
+  __shared__ float s_M[12];            // rows of the change of frame: x' = M[0..2].p + M[3] ...
+  __shared__ double s_stat[3][4];      // per plane: mean / sd of the depth and of the density differences
+  __shared__ int s_cnt;
+  const GridArgs &g = a.g;
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const int p = a.kp[q];
+  const int side = a.side, S2 = side * side, cells = 3 * S2, nbits = 9 * S2;
+  const float qx = g.xyz[3 * (size_t)p], qy = g.xyz[3 * (size_t)p + 1], qz = g.xyz[3 * (size_t)p + 2];
+  if (tid < 27) {
+    const int cx = cell_coord(qx, g.mnx, g.inv) + tid / 9 - 1, cy = cell_coord(qy, g.mny, g.inv) + (tid / 3) % 3 - 1,
+              cz = cell_coord(qz, g.mnz, g.inv) + tid % 3 - 1;
+    int lo = 0, hi = 0;
+    if (cx >= 0 && cy >= 0 && cz >= 0) {
+      const int u = find_cell(g.ucell, g.nu, cell_key(cx, cy, cz));
+      if (u >= 0) { lo = g.cstart[u]; hi = g.cstart[u + 1]; }
+    }
+    s_lo[tid] = lo; s_hi[tid] = hi;
+  }
+  for (int c = tid; c < cells; c += BSC_T) { s_num[c] = 0ull; s_dep[c] = 0ll; }
+  __syncthreads();
+  const double radius = sqrt(2.0) * (double)a.R;   // :956
+  // ---- pass A: count, centroid sums, weight sum (:956-966) ----
+  {
+    double v[5] = {0, 0, 0, 0, 0};
+    for (int c = 0; c < 27; ++c)
+      for (int s = s_lo[c] + tid; s < s_hi[c]; s += BSC_T) {
+        const int k = g.order[s];
+        const float x = g.xyz[3 * (size_t)k], y = g.xyz[3 * (size_t)k + 1], z = g.xyz[3 * (size_t)k + 2];
+        const float ex = x - qx, ey = y - qy, ez = z - qz;
+        const float d2 = ex * ex + ey * ey + ez * ez;
+        if (!(d2 < g.r2)) continue;
+        v[0] += 1.0; v[1] += (double)x; v[2] += (double)y; v[3] += (double)z;
+        v[4] += radius - (double)sqrtf(d2);
+      }
+    block_sum<5, BSC_T>(v, s_red);
+    if (tid == 0) {
+      s_cnt = (int)v[0];
+      s_c[0] = v[1] / v[0]; s_c[1] = v[2] / v[0]; s_c[2] = v[3] / v[0]; s_c[3] = v[4];
+    }
+    __syncthreads();
+  }
+  const int cnt = s_cnt;
+  if (cnt < 3) {   // the reference reads uninitialised axes here (:952): descriptor left zero, status 1
+    for (int b = tid; b < a.V * a.nbytes; b += BSC_T) a.bits[((size_t)(b / a.nbytes) * a.nkp + q) * a.nbytes + b % a.nbytes] = 0;
+    if (tid == 0) {
+      if (a.status) a.status[q] = 1;
+      if (a.lrf) { for (int c = 0; c < 9; ++c) a.lrf[12 * (size_t)q + c] = 0.f; a.lrf[12 * (size_t)q + 9] = qx; a.lrf[12 * (size_t)q + 10] = qy; a.lrf[12 * (size_t)q + 11] = qz; }
+    }
+    return;
+  }
+  // ---- pass B: weighted covariance about the centroid (:972-990) ----
+  {
+    double v[6] = {0, 0, 0, 0, 0, 0};
+    const double cx = s_c[0], cy = s_c[1], cz = s_c[2];
+    for (int c = 0; c < 27; ++c)
+      for (int s = s_lo[c] + tid; s < s_hi[c]; s += BSC_T) {
+        const int k = g.order[s];
+        const float x = g.xyz[3 * (size_t)k], y = g.xyz[3 * (size_t)k + 1], z = g.xyz[3 * (size_t)k + 2];
+        const float ex = x - qx, ey = y - qy, ez = z - qz;
+        const float d2 = ex * ex + ey * ey + ez * ez;
+        if (!(d2 < g.r2)) continue;
+        const float weight = (float)(radius - (double)sqrtf(d2));
+        const double dx = (double)x - cx, dy = (double)y - cy, dz = (double)z - cz, w = (double)weight;
+        v[0] += w * dx * dx; v[1] += w * dx * dy; v[2] += w * dx * dz; v[3] += w * dy * dy; v[4] += w * dy * dz; v[5] += w * dz * dz;
+      }
+    block_sum<6, BSC_T>(v, s_red);
+    if (tid == 0) {
+      const float da = (float)s_c[3];
+      const float c00 = (float)v[0] / da, c01 = (float)v[1] / da, c02 = (float)v[2] / da, c11 = (float)v[3] / da,
+                  c12 = (float)v[4] / da, c22 = (float)v[5] / da;
+      double A[3][3] = {{c00, c01, c02}, {c01, c11, c12}, {c02, c12, c22}}, Vv[3][3], w[3];
+      bsc_jacobi3(A, Vv, w);
+      const float ev[3] = {(float)w[0], (float)w[1], (float)w[2]};
+      int imax = 0, imin = 0;
+      float vmax = ev[0], vmin = ev[0];
+      for (int i = 0; i < 3; ++i) {   // :998-1012
+        if (ev[i] > vmax) { imax = i; vmax = ev[i]; }
+        if (ev[i] < vmin) { imin = i; vmin = ev[i]; }
+      }
+      float principal[3], normal[3], ax[3], ay[3], az[3];
+      for (int i = 0; i < 3; ++i) { principal[i] = (float)Vv[i][imax]; normal[i] = (float)Vv[i][imin]; }
+      bsc_cross(principal, normal, ay);                 // middle direction :1022
+      for (int i = 0; i < 3; ++i) ax[i] = principal[i];
+      bsc_cross(ax, ay, az);                            // :148, before the normalisation
+      bsc_normalize(ax); bsc_normalize(ay);             // :155-156
+      if (a.lrf) {
+        float *o = a.lrf + 12 * (size_t)q;
+        for (int c = 0; c < 3; ++c) { o[c] = ax[c]; o[3 + c] = ay[c]; o[6 + c] = az[c]; }
+        o[9] = qx; o[10] = qy; o[11] = qz;
+      }
+      if (a.status) a.status[q] = 0;
+      // :1085-1138 — PCL's float32 Umeyama of the unit axes onto (ax, ay, az), the way the hot path's solve does it
+      // (points (1,0,0), (0,1,0), (0,0,1) -> ax, ay, az; float32 means, demeaned products, 1/n), then the inverse
+      const float third = 1.0f / 3.0f;
+      float mu_s[3], mu_d[3], sigma[9];
+      {
+        float ms[3] = {0.f, 0.f, 0.f}, md[3] = {0.f, 0.f, 0.f};
+        const float S[3][3] = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
+        const float *D[3] = {ax, ay, az};
+        for (int i = 0; i < 3; ++i) for (int c = 0; c < 3; ++c) { ms[c] += S[i][c]; md[c] += D[i][c]; }
+        for (int c = 0; c < 3; ++c) { mu_s[c] = ms[c] * third; mu_d[c] = md[c] * third; }
+        float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int i = 0; i < 3; ++i) {
+          const float ds[3] = {S[i][0] - mu_s[0], S[i][1] - mu_s[1], S[i][2] - mu_s[2]};
+          const float dd[3] = {D[i][0] - mu_d[0], D[i][1] - mu_d[1], D[i][2] - mu_d[2]};
+          for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) acc[r * 3 + c] += dd[r] * ds[c];
+        }
+        for (int k = 0; k < 9; ++k) sigma[k] = third * acc[k];
+      }
+      double Rt[16];
+      umeyama_from_moments_f32(mu_s, mu_d, sigma, Rt);
+      float M[16], Mi[16];
+      for (int k = 0; k < 16; ++k) M[k] = (float)Rt[k];
+      bsc_inverse4(M, Mi);
+      for (int r = 0; r < 3; ++r) { s_M[4 * r] = Mi[r]; s_M[4 * r + 1] = Mi[4 + r]; s_M[4 * r + 2] = Mi[8 + r]; s_M[4 * r + 3] = Mi[12 + r]; }
+    }
+    __syncthreads();
+  }
+  // ---- pass C: the three projected grids (:197-310) ----
+  const float R = a.R;
+  const float unit = 2 * R / side;                                  // :72
+  const float delta = (float)(unit * 0.5);                          // :205
+  const float two_dd = 2 * delta * delta;
+  const float rc = (float)(1.5 * unit), rc2 = rc * rc;              // search radius of a cell centre, squared like S4
+  const double dep_scale = 1099511627776.0 / (double)R;             // 2^40 / R: depth * w / R in fixed point
+  {
+    const float m00 = s_M[0], m01 = s_M[1], m02 = s_M[2], m03 = s_M[3], m10 = s_M[4], m11 = s_M[5], m12 = s_M[6], m13 = s_M[7],
+                m20 = s_M[8], m21 = s_M[9], m22 = s_M[10], m23 = s_M[11];
+    for (int c = 0; c < 27; ++c)
+      for (int s = s_lo[c] + tid; s < s_hi[c]; s += BSC_T) {
+        const int k = g.order[s];
+        const float ex = g.xyz[3 * (size_t)k] - qx, ey = g.xyz[3 * (size_t)k + 1] - qy, ez = g.xyz[3 * (size_t)k + 2] - qz;
+        const float d2 = ex * ex + ey * ey + ez * ez;
+        if (!(d2 < g.r2)) continue;
+        float loc[3];
+        loc[0] = m00 * ex + m01 * ey + m02 * ez + m03;              // :193, rows summed left to right
+        loc[1] = m10 * ex + m11 * ey + m12 * ez + m13;
+        loc[2] = m20 * ex + m21 * ey + m22 * ez + m23;
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) {
+          const float u = loc[pl == 2 ? 1 : 0], v = loc[pl == 0 ? 1 : 2];
+          const float depth = loc[pl == 0 ? 2 : (pl == 1 ? 1 : 0)] + R;   // :240, :274, :308
+          const int iu = (int)floorf((u + R) / unit), iv = (int)floorf((v + R) / unit);
+          for (int i = iu - 2; i <= iu + 2; ++i) {
+            if (i < 0 || i >= side) continue;
+            const float cu = (float)((i + 0.5) * unit - R);          // :226
+            const float du = u - cu;
+            for (int j = iv - 2; j <= iv + 2; ++j) {
+              if (j < 0 || j >= side) continue;
+              const float cv = (float)((j + 0.5) * unit - R);
+              const float dv = v - cv;
+              const float dd = du * du + dv * dv;
+              if (!(dd < rc2)) continue;
+              const float wgt = (float)exp((double)(-dd / two_dd));  // :238 exp(float): rounded-to-nearest float32 exponential
+              const int cell = i + j * side + pl * S2;
+              atomicAdd(&s_num[cell], (unsigned long long)((double)wgt * 1099511627776.0));
+              atomicAdd((unsigned long long *)&s_dep[cell], (unsigned long long)__double2ll_rn((double)depth * (double)wgt * dep_scale));
+            }
+          }
+        }
+      }
+  }
+  __syncthreads();
+  // ---- cells (:341-373) ----
+  {
+    const float area_n = (float)(3.14159265358979323846 * R * R);    // :346
+    const float dens_n = (float)cnt / area_n;                        // :347
+    const float area_g = unit * unit;
+    for (int c = tid; c < cells; c += BSC_T) {
+      const double num = (double)s_num[c] * (1.0 / 1099511627776.0);
+      float depth = 0.f;
+      if (num != 0.0) depth = (float)(((double)s_dep[c] / dep_scale) / num);
+      const float dens_g = (float)(num / (double)area_g);
+      s_depth[c] = depth;
+      s_npw[c] = (dens_n != 0.0f) ? dens_g / dens_n : 0.f;
+    }
+  }
+  __syncthreads();
+  // ---- per plane statistics of the pair differences (:498-527), one thread per plane, the reference's summation order ----
+  if (tid < 3) {
+    const int off = tid * S2;
+    double mean_dep = 0.0, mean_den = 0.0, var_dep = 0.0, var_den = 0.0;
+    for (int i = 0; i < S2; ++i) {
+      mean_dep += (double)(s_depth[a.pairs[2 * i] + off] - s_depth[a.pairs[2 * i + 1] + off]);
+      mean_den += (double)(s_npw[a.pairs[2 * i] + off] - s_npw[a.pairs[2 * i + 1] + off]);
+    }
+    mean_dep /= S2; mean_den /= S2;
+    for (int i = 0; i < S2; ++i) {
+      const double dep = (double)(s_depth[a.pairs[2 * i] + off] - s_depth[a.pairs[2 * i + 1] + off]);
+      const double den = (double)(s_npw[a.pairs[2 * i] + off] - s_npw[a.pairs[2 * i + 1] + off]);
+      var_dep += (dep - mean_dep) * (dep - mean_dep);
+      var_den += (den - mean_den) * (den - mean_den);
+    }
+    s_stat[tid][0] = mean_dep; s_stat[tid][1] = sqrt(var_dep / S2); s_stat[tid][2] = mean_den; s_stat[tid][3] = sqrt(var_den / S2);
+  }
+  __syncthreads();
+  // ---- bits: one thread per output byte ----
+  const float T = 0.1f;
+  for (int b = tid; b < a.V * a.nbytes; b += BSC_T) {
+    const int v = b / a.nbytes, byte = b % a.nbytes;
+    unsigned out = 0;
+    for (int bit = 0; bit < 8; ++bit) {
+      const int k = 8 * byte + bit;
+      if (k >= nbits) break;
+      bool on = false;
+      if (v == 0) {
+        if (k < cells) on = s_npw[k] > T;
+        else {
+          const int kk = k - cells, pl = kk / (2 * S2), r = kk % (2 * S2), i = r >> 1, off = pl * S2;
+          const int pa = a.pairs[2 * i], pb = a.pairs[2 * i + 1];
+          if ((r & 1) == 0) {
+            const double dep = (double)(s_depth[pa + off] - s_depth[pb + off]);
+            on = fabs(dep - s_stat[pl][0]) > s_stat[pl][1];          // :531
+          } else if (!(s_npw[pa] < T && s_npw[pb] < T)) {             // :544 looks at the first plane whatever the plane
+            const double den = (double)(s_npw[pa + off] - s_npw[pb + off]);
+            on = fabs(den - s_stat[pl][2]) > s_stat[pl][3];          // :551
+          }
+        }
+      } else if (k >= cells && k < 2 * cells) {                       // the appended re-arranged grid's occupancy bits
+        const int kk = k - cells, pl = kk / S2;
+        const int tr = (v == 1) ? (pl == 0 ? 1 : 2) : (v == 2 ? (pl == 0 ? 3 : (pl == 1 ? 2 : 1)) : (pl == 0 ? 2 : (pl == 1 ? 1 : 3)));   // :789, :804, :813
+        on = s_npw[pl * S2 + bsc_rearranged(tr, kk % S2, side)] > T;
+      }
+      if (on) out |= 1u << bit;
+    }
+    a.bits[((size_t)v * a.nkp + q) * a.nbytes + byte] = (unsigned char)out;
+  }
+}
+
+}  // namespace
+
+// BSCEncoder::extractBinaryFeatures on device arrays.  d_kp [nkp] keypoint indices into d_xyz [n][3]; d_pairs [side^2][2];
+// d_bits [V][nkp][ceil(9 side^2 / 8)] with V = 1 (dof_type 0), 2 (1..4), 4 (> 4); d_lrf [nkp][12] and d_status [nkp] may be null.
+cudaError_t prep_bsc_extract(cudaStream_t st, const float *d_xyz, int n, const int *d_kp, int nkp, float R, int side,
+                             const int *d_pairs, int dof_type, unsigned char *d_bits, float *d_lrf, int *d_status) {
+  cudaError_t err = cudaSuccess;
+  GridArgs g{};
+  int *order = nullptr, *cstart = nullptr; pu64 *ucell = nullptr;
+  if (n <= 0 || nkp <= 0) return cudaSuccess;
+  if (side < 1 || side > BSC_MAX_SIDE) return cudaErrorInvalidValue;
+  {
+    const float search = (float)(sqrt(3.0) * (double)R);            // :643; squared in float32 like the radius of S4
+    PCK(build_grid(st, d_xyz, nullptr, n, search, &g, &order, &ucell, &cstart));
+    BscArgs a{};
+    a.g = g; a.kp = d_kp; a.nkp = nkp; a.R = R; a.side = side; a.pairs = d_pairs;
+    a.V = dof_type > 4 ? 4 : (dof_type > 0 ? 2 : 1);
+    a.bits = d_bits; a.nbytes = (9 * side * side + 7) / 8; a.lrf = d_lrf; a.status = d_status;
+    GHICP_LAUNCH(k_bsc, nkp, BSC_T, 0, st, a);
+    PCK(psync(st));
+#if !defined(GHICP_EMU_HOST)
+    PCK(cudaGetLastError());
+#endif
+  }
+done:
+  pfree(order); pfree(ucell); pfree(cstart);
   return err;
 }
 

@@ -8,6 +8,9 @@ bounding-box magnitude of the down-sampled source (:91-93), GHRegistration on th
 `features(target_down, target_kp_idx, source_down, source_kp_idx) -> Keypoints` may attach BSC / FPFH descriptors computed
 elsewhere (the encoders are not part of this library); without it the registration runs on coordinates
 only (Ft = None), which GHRegistration supports (src/ghicp_reg.cpp:66-68) although the reference's own main() rejects it.
+With feature_type = FT_BSC and no `features` callback the BSC descriptors are encoded on the GPU like :113-116
+(capi.bsc_extract: radius = curvature_non_max_radius, 7 x 7 grids, dof_type 0 for the target, `dof_type` for the source;
+`bsc_pattern` = the sampling pairs, default = the pattern the reference's constructor generates).
 """
 import numpy as np
 
@@ -17,7 +20,7 @@ from .registration import Energyfunction, GHRegistration, Keypoints
 
 def register_clouds(target_xyz, source_xyz, resolution, neighborhood_radius, curvature_non_max_radius, corr_type=capi.CT_NN,
                     feature_type=capi.FT_NONE, features=None, weight_adjustment_ratio=1.1, weight_adjustment_step=0.1,
-                    dof_type=6, estimated_IoU=0.5, max_iter=0, device=0, **reg_kw):
+                    dof_type=6, estimated_IoU=0.5, max_iter=0, device=0, bsc_pattern=None, **reg_kw):
     T = np.ascontiguousarray(target_xyz, dtype=np.float32)
     S = np.ascontiguousarray(source_xyz, dtype=np.float32)
     down, kp_idx = {}, {}
@@ -32,6 +35,11 @@ def register_clouds(target_xyz, source_xyz, resolution, neighborhood_radius, cur
     bbx = float(np.float32(ext[0] + ext[1] + ext[2]))
     if features is not None:
         Kp = features(down["T"], kp_idx["T"], down["S"], kp_idx["S"])
+    elif feature_type == capi.FT_BSC:
+        bscT, _, _ = capi.bsc_extract(down["T"], kp_idx["T"], curvature_non_max_radius, 0, 7, bsc_pattern, device)        # :115
+        bscS, _, _ = capi.bsc_extract(down["S"], kp_idx["S"], curvature_non_max_radius, dof_type, 7, bsc_pattern, device)  # :116
+        Kp = Keypoints().setCoordinate(down["S"][kp_idx["S"]].astype(np.float64), down["T"][kp_idx["T"]].astype(np.float64))
+        Kp.setBSCfeature(bscS, bscT[0], 9 * 49)
     else:
         Kp = Keypoints().setCoordinate(down["S"][kp_idx["S"]].astype(np.float64), down["T"][kp_idx["T"]].astype(np.float64))
     Ef = Energyfunction().init(Kp.kps_num, Kp.kpt_num, bbx)

@@ -192,6 +192,22 @@ int ghicp_voxel_downsample(int device, const float *xyz, int n, float voxel_size
 int ghicp_detect_keypoints(int device, const float *xyz, int n, float radius, float ratio_max, int min_pts, float nms_radius,
                            int *kp_idx, int *n_kp, float *lam, double *curvature, int *pt_num);
 
+/* ---- BSC descriptor encoder on the GPU -----------------------------------------------------
+ * BSCEncoder<PointT>::extractBinaryFeatures (include/binary_feature_extraction.hpp:603-676, called at
+ * test/ghicp_main.cpp:113-116 with voxel_side_num = 7, extract_radius = the keypoint NMS radius, dof_type 0 for the target
+ * and reg_dof for the source): per keypoint the weighted-PCA local frame (:940-1035), the three projected
+ * Gaussian-weighted grids (:197-373), the 9 side^2-bit descriptor (:464-565) and its variants (:762-837).
+ * xyz [n][3] float32; kp_idx [nkp] indices into xyz; pairs [side^2][2] = the sampling pattern (sample_pattern.txt of the
+ * reference, :107-116; ghicp_bsc_default_pattern for side 7).  features = [V][nkp][ceil(9 side^2 / 8)] bytes, V = 1
+ * (dof_type 0), 2 (1..4) or 4 (> 4) — the layout ghicp_set_bsc takes.  lrf [nkp][12] (x, y, z axis, origin of variant 0)
+ * and status [nkp] (0 ok, 1 = fewer than 3 neighbours: descriptor zero) may be NULL.  voxel_side_num <= 9.
+ * Eigenvector signs (Eigen::EigenSolver's are implementation-defined) follow "largest component positive"; see DESIGN.md
+ * §3.9 for the float32 accumulation tolerance against the reference. */
+int ghicp_bsc_extract(int device, const float *xyz, int n, const int *kp_idx, int nkp, float extract_radius, int voxel_side_num,
+                      const int *pairs, int dof_type, unsigned char *features, int *n_variants, float *lrf, int *status);
+/* the pattern the reference's constructor generates (:75-103) in a fresh process; pairs [49][2]; voxel_side_num must be 7 */
+int ghicp_bsc_default_pattern(int voxel_side_num, int *pairs);
+
 /* ---- multi-GPU (one process per GPU; source rows sharded, target replicated) ---------------- */
 /* 128-byte NCCL unique id; rank 0 creates it, the host runtime broadcasts it (torch.distributed,
  * MPI, a file ...). No NCCL symbol is touched unless these are called (world == 1 → never). */

@@ -166,6 +166,73 @@ def ref_detect_keypoints(xyz, radius, ratio_max=0.65, min_pts=20, nms_radius=Non
     return kp[:m].copy()
 
 
+def bsc_bytes(side=7):
+    return (9 * side * side + 7) // 8
+
+
+def bsc_extract(xyz, kp, radius, pairs, side=7, dof_type=6):
+    """Oracle restatement of BSCEncoder::extractBinaryFeatures (oracle/ghicp_bsc_oracle.cpp).
+    Returns (bits [V][nkp][bytes] uint8, lrf [nkp][12] float32, status [nkp])."""
+    L = lib()
+    L.orc_bsc_extract.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32); kp = np.ascontiguousarray(kp, dtype=np.int32)
+    pairs = np.ascontiguousarray(pairs, dtype=np.int32)
+    bits = np.zeros((4, len(kp), bsc_bytes(side)), np.uint8); lrf = np.zeros((len(kp), 12), np.float32)
+    status = np.zeros(len(kp), np.int32)
+    V = L.orc_bsc_extract(xyz.ctypes.data, len(xyz), kp.ctypes.data, len(kp), radius, side, pairs.ctypes.data, dof_type,
+                          bits.ctypes.data, lrf.ctypes.data, status.ctypes.data)
+    return bits[:V].copy(), lrf, status
+
+
+def bsc_grid(xyz, p, radius, side=7):
+    """Gaussian-weighted grids of keypoint p: (point_num [3 side^2] float64, average_depth float32, normalized weight float32)."""
+    L = lib()
+    L.orc_bsc_grid.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+    num = np.zeros(3 * side * side); dep = np.zeros(3 * side * side, np.float32); npw = np.zeros(3 * side * side, np.float32)
+    rc = L.orc_bsc_grid(xyz.ctypes.data, len(xyz), int(p), radius, side, num.ctypes.data, dep.ctypes.data, npw.ctypes.data)
+    return (num, dep, npw) if rc == 0 else None
+
+
+def ref_bsc_lib():
+    """oracle/_ref/libbsc_ref.so = the reference's own include/binary_feature_extraction.hpp compiled verbatim, or None."""
+    if "bsc" in _libs:
+        return _libs["bsc"]
+    build()
+    p = os.path.join(_HERE, "_ref", "libbsc_ref.so")
+    _libs["bsc"] = C.CDLL(p) if os.path.exists(p) else None
+    if _libs["bsc"] is not None:
+        _libs["bsc"].bscref_extract.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_int,
+                                                C.c_void_p, C.c_void_p]
+        _libs["bsc"].bscref_make_pattern.argtypes = [C.c_int, C.c_void_p]
+    return _libs["bsc"]
+
+
+def ref_bsc_pattern(side=7):
+    """The sampling pattern the reference's constructor generates (rand(), default seed); writes ./sample_pattern.txt."""
+    R = ref_bsc_lib()
+    if R is None:
+        return None
+    pairs = np.zeros((side * side, 2), np.int32)
+    assert R.bscref_make_pattern(side, pairs.ctypes.data) == side * side
+    return pairs
+
+
+def ref_bsc_extract(xyz, kp, radius, pairs, side=7, dof_type=6):
+    """The REFERENCE's own BSCEncoder (needs a writable current directory: it reads ./sample_pattern.txt)."""
+    R = ref_bsc_lib()
+    if R is None:
+        return None
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32); kp = np.ascontiguousarray(kp, dtype=np.int32)
+    pairs = np.ascontiguousarray(pairs, dtype=np.int32)
+    bits = np.zeros((4, len(kp), bsc_bytes(side)), np.uint8); lrf = np.zeros((len(kp), 12), np.float32)
+    V = R.bscref_extract(xyz.ctypes.data, len(xyz), kp.ctypes.data, len(kp), radius, side, pairs.ctypes.data, dof_type,
+                         bits.ctypes.data, lrf.ctypes.data)
+    assert V > 0
+    return bits[:V].copy(), lrf
+
+
 class GhrefStats(C.Structure):
     _fields_ = [("iteration", C.c_int), ("cor", C.c_int), ("converged", C.c_int), ("penalty", C.c_double), ("rmse", C.c_double),
                 ("rmse_after", C.c_double), ("fdm", C.c_double), ("fdstd", C.c_double), ("iou", C.c_double),

@@ -29,6 +29,8 @@ template <typename T> struct PointCloud {
   iterator begin() { return points.begin(); }
   iterator end() { return points.end(); }
   void push_back(const T &p) { points.push_back(p); }
+  void resize(size_t n) { points.resize(n); }
+  void swap(PointCloud &o) { points.swap(o.points); std::swap(width, o.width); std::swap(height, o.height); }
   std::shared_ptr<PointCloud<T>> makeShared() const { return std::make_shared<PointCloud<T>>(*this); }
 };
 struct PointIndices { std::vector<int> indices; };
@@ -54,6 +56,18 @@ template <typename P, typename V> void getMinMax3D(const PointCloud<P> &c, V &mn
     first = false;
   }
 }
-template <typename P, typename M> void transformPointCloud(const PointCloud<P> &in, PointCloud<P> &out, const M &) { out = in; }
+// pcl::transformPointCloud(in, out, Matrix4f) as called at include/binary_feature_extraction.hpp:193: out = in with
+// xyz <- M(0..2, 0..2) * xyz + M(0..2, 3) in float, each row summed left to right (PCL 1.7-1.9's plain expression).
+template <typename P, typename M> void transformPointCloud(const PointCloud<P> &in, PointCloud<P> &out, const M &m) {
+  if (&in != &out) out = in;
+  for (size_t i = 0; i < in.points.size(); ++i) {
+    const float x = in.points[i].x, y = in.points[i].y, z = in.points[i].z;
+    out.points[i].x = m(0, 0) * x + m(0, 1) * y + m(0, 2) * z + m(0, 3);
+    out.points[i].y = m(1, 0) * x + m(1, 1) * y + m(1, 2) * z + m(1, 3);
+    out.points[i].z = m(2, 0) * x + m(2, 1) * y + m(2, 2) * z + m(2, 3);
+  }
+}
+struct Correspondence { int index_query = 0, index_match = -1; float distance = 0.f; };
+typedef std::vector<Correspondence> Correspondences;
 }  // namespace pcl
 namespace boost { namespace filesystem {} }   // `using namespace boost::filesystem;` at src/ghicp_reg.cpp:18

@@ -22,5 +22,12 @@ template <typename A, typename B> class TransformationEstimationSVD {
     orc_rigid_fit(s.data(), t.data(), n, ghref_solve_mode(), Rt);
     for (int k = 0; k < 16; ++k) out.v[k] = (float)Rt[k];   // Rt holds float values (cast of the float32 result)
   }
+  // the overload with correspondences (include/binary_feature_extraction.hpp:1136): pairs (index_query, index_match)
+  void estimateRigidTransformation(const pcl::PointCloud<A> &src, const pcl::PointCloud<B> &dst, const pcl::Correspondences &cor,
+                                   Matrix4 &out) const {
+    pcl::PointCloud<A> s; pcl::PointCloud<B> t;
+    for (const pcl::Correspondence &c : cor) { s.points.push_back(src.points[c.index_query]); t.points.push_back(dst.points[c.index_match]); }
+    estimateRigidTransformation(s, t, out);
+  }
 };
 } }

@@ -83,6 +83,7 @@ inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return
 inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 inline long long __double_as_longlong(double d) { long long l; memcpy(&l, &d, 8); return l; }
 inline double __longlong_as_double(long long l) { double d; memcpy(&d, &l, 8); return d; }
+inline long long __double2ll_rn(double x) { return llrint(x); }   // default rounding mode: to nearest even
 inline float __double2float_ru(double x) {
   float f = (float)x;
   if ((double)f < x) f = nextafterf(f, INFINITY);

@@ -209,6 +209,12 @@ int emu_detect_keypoints(const float *xyz, int n, float radius, float ratio_max,
                                     nms_rounds);
 }
 
+// BSC descriptor encoder (k_bsc): bits [V][nkp][bytes], lrf [nkp][12], status [nkp]
+int emu_bsc_extract(const float *xyz, int n, const int *kp, int nkp, float R, int side, const int *pairs, int dof_type,
+                    unsigned char *bits, float *lrf, int *status) {
+  return (int)prep_bsc_extract(nullptr, xyz, n, kp, nkp, R, side, pairs, dof_type, bits, lrf, status);
+}
+
 // ---- the all-double path of ghicp_kernels.cu: FD build + one loop body, driven in the order of ghicp_capi.cu's exact branch ----
 struct emu_iter_out {
   int cor; long long nnz;
