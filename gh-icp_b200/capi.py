@@ -69,7 +69,7 @@ EXPORTS = ["ghicp_abi_version", "ghicp_device_count", "ghicp_last_error", "ghicp
            "ghicp_run", "ghicp_get_pairs", "ghicp_get_source", "ghicp_get_rt", "ghicp_get_fd",
            "ghicp_probe_rowmin", "ghicp_set_state", "ghicp_km_solve", "ghicp_rigid_fit", "ghicp_rigid_fit_ex",
            "ghicp_set_target_normals", "ghicp_set_solver", "ghicp_voxel_downsample", "ghicp_detect_keypoints",
-           "ghicp_comm_unique_id", "ghicp_comm_init"]
+           "ghicp_bsc_extract", "ghicp_bsc_default_pattern", "ghicp_comm_unique_id", "ghicp_comm_init"]
 
 
 def lib():

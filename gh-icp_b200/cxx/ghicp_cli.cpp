@@ -13,15 +13,21 @@
 //   * no viewer windows (the last argument is accepted and ignored; :156-157 cannot run headless);
 //   * feature 'N' (register on coordinates only) WORKS — the reference's switch falls into "Wrong feature input" and
 //     exits (:135-139) although GHRegistration supports Ft = None (src/ghicp_reg.cpp:66-68);
-//   * features 'B' and 'F' need the BSC / FPFH encoders (include/binary_feature_extraction.hpp, include/fpfh.hpp), which
-//     this library does not provide: the driver says so and exits with status 2;
+//   * feature 'B' encodes the BSC descriptors on the GPU like :113-116 (BSCEncoder(curvature_non_max_radius, 7), target
+//     dof 0, source registration_dof).  The sampling pattern is ./sample_pattern.txt when present — as in the reference,
+//     which ships none — else the pattern the reference's constructor generates in a fresh process;
+//   * features 'F' and 'R' need PCL's FPFH / RoPS estimators, which this library does not provide: the driver says so
+//     and exits with status 2 (FPFH histograms computed elsewhere go through Keypoints::setFPFHfeature);
 //   * .las input is not supported (needs libLAS + an interactive prompt).
-// Utility mode (I/O only, no GPU):  ghicp_cli --convert in.{pcd,ply,txt} out.{pcd,ply,txt}
+// Utility modes (no GPU):  ghicp_cli --convert in.{pcd,ply,txt} out.{pcd,ply,txt}
+//                          ghicp_cli --sample-pattern     write ./sample_pattern.txt the way the reference's
+//                              BSCEncoder(radius, 7, true) does (binary_feature_extraction.hpp:75-103), read it back, report
 // Exit status: 0 ok, 2 usage / unsupported option, 3 runtime error (incl. no CUDA device: there is no CPU fallback).
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
 
+#include "bsc_encoder.h"
 #include "cloud_io.h"
 #include "ghicp_reg.h"
 
@@ -46,11 +52,25 @@ int main(int argc, char **argv) {
       std::cout << "converted " << c.size() << " points" << std::endl;
       return 0;
     }
+    if (argc == 2 && std::string(argv[1]) == "--sample-pattern") {
+      BSCEncoder made(1.0f, 7, true);
+      BSCEncoder back(1.0f, 7, false);
+      std::vector<int> shipped(98);
+      check_rc(ghicp_bsc_default_pattern(7, shipped.data()), "default pattern");
+      bool same_back = back.pattern_from_file_, same_shipped = true;
+      for (int i = 0; i < 49; ++i) {
+        same_back = same_back && back.grid_index_pairs_2d_[i] == made.grid_index_pairs_2d_[i];
+        same_shipped = same_shipped && made.grid_index_pairs_2d_[i].first == shipped[2 * i] && made.grid_index_pairs_2d_[i].second == shipped[2 * i + 1];
+      }
+      std::cout << "wrote sample_pattern.txt (49 pairs); read back " << (same_back ? "ok" : "MISMATCH") << "; "
+                << (same_shipped ? "equals" : "differs from") << " the shipped default pattern" << std::endl;
+      return same_back ? 0 : 3;
+    }
     if (argc < 13) {
       std::cerr << "usage: " << argv[0] << " target source registered feature(B|F|R|N) corres(K|N|R) downsample_resolution "
                 << "neighborhood_radius curvature_non_max_radius weight_adjustment_ratio weight_adjustment_step "
                 << "registration_dof appro_overlap_ratio [launch_realtime_viewer]\n       " << argv[0]
-                << " --convert in.{pcd,ply,txt} out.{pcd,ply,txt}" << std::endl;
+                << " --convert in.{pcd,ply,txt} out.{pcd,ply,txt}\n       " << argv[0] << " --sample-pattern" << std::endl;
       return 2;
     }
     const std::string filenameT = argv[1], filenameS = argv[2], filenameR = argv[3];   // test/ghicp_main.cpp:56-58
@@ -68,10 +88,9 @@ int main(int argc, char **argv) {
     const float weight_adjustment_step = (float)atof(argv[10]);
     const int reg_dof = atoi(argv[11]);
     const float estimated_IoU = (float)atof(argv[12]);
-    if (Ft != None) {
-      std::cerr << "feature '" << argv[4] << "': the BSC / FPFH / RoPS encoders are not part of libghicp_b200 (it takes the "
-                << "descriptors through Keypoints::setBSCfeature / setFPFHfeature); run with N, or link the reference's encoders"
-                << std::endl;
+    if (Ft == FPFH || Ft == RoPS) {
+      std::cerr << "feature '" << argv[4] << "': the FPFH / RoPS estimators are PCL's and not part of libghicp_b200 (FPFH histograms "
+                << "computed elsewhere go through Keypoints::setFPFHfeature); run with B or N" << std::endl;
       return 2;
     }
     if (!(resolution > 0.f) || !(neighborhood_radius > 0.f) || !(curvature_non_max_radius > 0.f)) {
@@ -111,6 +130,15 @@ int main(int argc, char **argv) {
     for (int i = 0; i < nkpt; ++i) for (int a = 0; a < 3; ++a) kpTXYZ(i, a) = downT.xyz[3 * (size_t)kpT[i] + a];
     Keypoints Kp;
     Kp.setCoordinate(kpSXYZ, kpTXYZ);
+    if (Ft == BSC) {                                                                     // :109-119
+      kpT.resize(nkpt); kpS.resize(nkps);
+      BSCEncoder bsc(curvature_non_max_radius, 7);
+      doubleVectorSBF bscT, bscS;
+      bsc.extractBinaryFeatures(downT, kpT, 0, bscT);        // fixed feature (one per keypoint)
+      bsc.extractBinaryFeatures(downS, kpS, reg_dof, bscS);  // 2 / 4 features per keypoint
+      Kp.setBSCfeature(bscS, bscT);
+      std::cout << "BSC pattern: " << (bsc.pattern_from_file_ ? "./sample_pattern.txt" : "shipped default") << std::endl;
+    }
 
     // Registration (:141-151)
     Energyfunction Ef;

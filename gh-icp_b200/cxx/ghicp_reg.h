@@ -147,8 +147,9 @@ class GHRegistration {
     if (rc < 0) throw std::runtime_error(std::string(what) + ": " + ghicp_last_error(ctx_));
   }
   void upload_bsc() {
-    const int V = (int)KP.bscS.size();
-    if (V == 0 || KP.bscT.empty()) throw std::runtime_error("GHRegistration: BSC features not set");
+    int V = 0;   // extractBinaryFeatures always returns four vectors; the variants dof_type did not ask for hold empty features
+    while (V < (int)KP.bscS.size() && !KP.bscS[V].empty() && KP.bscS[V][0].size_ > 0) ++V;
+    if (V == 0 || KP.bscT.empty() || KP.bscT[0].empty()) throw std::runtime_error("GHRegistration: BSC features not set");
     const unsigned bits = KP.bscT[0][0].size_, B = KP.bscT[0][0].byte_;
     std::vector<uint8_t> s((size_t)V * KP.kps_num * B), t((size_t)KP.kpt_num * B);
     for (int v = 0; v < V; ++v)

@@ -46,6 +46,11 @@
  *     feature x correspondence x dof combination (tests/test_reference_loop.py) and for GHRegistration::ghicp_reg as a whole.
  *     tests/golden/loop_golden.npz carries that behaviour to machines without /root/reference.
  *     The single exception is the call into PCL (next item).
+ *   - BSC descriptor encoder ("next" row N2; ghicp_bsc_oracle.cpp): PINNED modulo four library substitutions.  The
+ *     reference's own include/binary_feature_extraction.hpp is compiled VERBATIM into oracle/_ref/libbsc_ref.so
+ *     (oracle/bsc_ref_shim.cpp); Eigen::EigenSolver, Matrix4f::inverse, PCL's SVD and FLANN's search are replaced by
+ *     stand-ins the restatement shares (see ghicp_bsc_oracle.cpp).  Descriptors (all variants) and frames agree bit for bit;
+ *     tests/golden/bsc_golden.npz carries them.
  *
  * Build: oracle/Makefile  (g++ -O3 -std=c++17 -ffp-contract=off, no -march: IEEE double, no FMA).
  */
@@ -147,6 +152,13 @@ int orc_voxel_downsample(const float *xyz, int n, float voxel_size, int *out_idx
 int orc_pca_curvature(const float *xyz, int n, float radius, float *lam /*[n][3]*/, double *curvature, int *pt_num);
 int orc_detect_keypoints(const float *xyz, int n, const float *lam, const double *curvature, const int *pt_num,
                          float ratio_max, int min_pts, float nms_radius, int *kp_idx /* cap n */);
+
+/* BSC descriptor encoder ("next" row N2; ghicp_bsc_oracle.cpp): BSCEncoder::extractBinaryFeatures
+   (include/binary_feature_extraction.hpp:603-676).  bits [4][nkp][ceil(9 side^2 / 8)] zero-filled first; lrf [nkp][12] and
+   status [nkp] may be NULL.  Returns the number of variants (1 / 2 / 4 for dof_type 0 / 1..4 / > 4). */
+int orc_bsc_extract(const float *xyz, int n, const int *kp, int nkp, float R, int side, const int *pairs, int dof_type,
+                    unsigned char *bits, float *lrf, int *status);
+int orc_bsc_grid(const float *xyz, int n, int p, float R, int side, double *num, float *depth, float *npw);
 
 typedef int (*orc_km_backend_fn)(const double *W, int n, double eps, int *match);
 void orc_set_km_backend(orc_km_backend_fn fn);

@@ -83,12 +83,29 @@ def test_argument_errors_and_unsupported_options(cli, tmp_path):
     assert subprocess.run([cli]).returncode == 2                                             # usage
     assert subprocess.run(base + ["Q", "N"] + tail, capture_output=True).returncode == 2     # unknown feature
     assert subprocess.run(base + ["N", "X"] + tail, capture_output=True).returncode == 2     # unknown correspondence method
-    r = subprocess.run(base + ["B", "K"] + tail, capture_output=True, text=True)             # encoders are not provided
-    assert r.returncode == 2 and "encoders" in r.stderr
+    r = subprocess.run(base + ["F", "K"] + tail, capture_output=True, text=True)             # PCL's FPFH estimator is not provided
+    assert r.returncode == 2 and "FPFH" in r.stderr
     r = subprocess.run([cli, "--convert", str(tmp_path / "missing.pcd"), str(tmp_path / "o.txt")], capture_output=True, text=True)
     assert r.returncode == 3 and "cannot open" in r.stderr
     r = subprocess.run([cli, "--convert", a, str(tmp_path / "o.las")], capture_output=True, text=True)
     assert r.returncode == 3
+
+
+def test_sample_pattern_mode_generates_the_reference_pattern(g, cli, tmp_path):
+    """BSCEncoder(r, 7, true) of the C++ mirror = the reference's generator (rand() from the default seed, distinct cells, no
+    pair twice): the file it writes holds the shipped default pattern, which tests/test_bsc_encoder.py pins on the
+    reference's own constructor; the reading constructor takes it back, and rejects a damaged file."""
+    r = subprocess.run([cli, "--sample-pattern"], capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr
+    assert "read back ok" in r.stdout and "equals the shipped default pattern" in r.stdout
+    assert np.array_equal(np.loadtxt(tmp_path / "sample_pattern.txt", dtype=np.int32), g.bsc_default_pattern(7))
+    assert np.array_equal(g.read_sample_pattern(str(tmp_path / "sample_pattern.txt")), g.bsc_default_pattern(7))
+    (tmp_path / "bad").mkdir()
+    np.savetxt(tmp_path / "bad" / "sample_pattern.txt", np.array([[1, 2], [3, 99]]), fmt="%d")
+    # registration mode with feature B constructs the reading encoder only after the GPU stages; the damaged file is caught by
+    # the Python reader here and by the C++ constructor on a GPU box (tests/test_zz3_bsc_gpu.py runs the good-file case)
+    with pytest.raises(g.GhicpError):
+        g.read_sample_pattern(str(tmp_path / "bad" / "sample_pattern.txt"))
 
 
 def test_registration_mode_without_a_gpu_fails_loudly(g, cli, tmp_path):
