@@ -470,6 +470,7 @@ constexpr int BSC_MAX_CELLS = 3 * BSC_MAX_SIDE * BSC_MAX_SIDE;
 
 struct BscArgs {
   GridArgs g;
+  const float4 *sorted;               // the points in cell order (position s of g.order), x y z _ : coalesced 16-byte reads
   const int *kp; int nkp;
   float R; int side; const int *pairs; int V;
   unsigned char *bits; int nbytes; float *lrf; int *status;
@@ -531,8 +532,16 @@ __device__ __forceinline__ int bsc_rearranged(int tr, int k, int side) {
   return tr == 1 ? side * side - 1 - k : (tr == 2 ? (side - 1 - i) * side + j : i * side + side - 1 - j);
 }
 
+// points in cell order, padded to 16 bytes
+__global__ void k_bsc_gather(const float *__restrict__ xyz, const int *__restrict__ order, int n, float4 *__restrict__ sorted) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const int k = order[s];
+  sorted[s] = make_float4(xyz[3 * (size_t)k], xyz[3 * (size_t)k + 1], xyz[3 * (size_t)k + 2], 0.f);
+}
+
 __global__ void __launch_bounds__(BSC_T) k_bsc(const BscArgs a) {
-  __shared__ int s_lo[27], s_hi[27];
+  __shared__ int s_lo[27], s_pre[28];  // start of each of the 27 cells' runs in the sorted order, prefix sums of their lengths
   __shared__ unsigned long long s_num[BSC_MAX_CELLS];
   __shared__ long long s_dep[BSC_MAX_CELLS];
   __shared__ float s_depth[BSC_MAX_CELLS], s_npw[BSC_MAX_CELLS];
@@ -554,24 +563,27 @@ __global__ void __launch_bounds__(BSC_T) k_bsc(const BscArgs a) {
       const int u = find_cell(g.ucell, g.nu, cell_key(cx, cy, cz));
       if (u >= 0) { lo = g.cstart[u]; hi = g.cstart[u + 1]; }
     }
-    s_lo[tid] = lo; s_hi[tid] = hi;
+    s_lo[tid] = lo; s_pre[tid + 1] = hi - lo;
   }
   for (int c = tid; c < cells; c += BSC_T) { s_num[c] = 0ull; s_dep[c] = 0ll; }
   __syncthreads();
+  if (tid == 0) { s_pre[0] = 0; for (int c = 0; c < 27; ++c) s_pre[c + 1] += s_pre[c]; }
+  __syncthreads();
+  const int total = s_pre[27];   // candidates of this keypoint; every pass walks them flat, 128 at a time
   const double radius = sqrt(2.0) * (double)a.R;   // :956
   // ---- pass A: count, centroid sums, weight sum (:956-966) ----
   {
     double v[5] = {0, 0, 0, 0, 0};
-    for (int c = 0; c < 27; ++c)
-      for (int s = s_lo[c] + tid; s < s_hi[c]; s += BSC_T) {
-        const int k = g.order[s];
-        const float x = g.xyz[3 * (size_t)k], y = g.xyz[3 * (size_t)k + 1], z = g.xyz[3 * (size_t)k + 2];
-        const float ex = x - qx, ey = y - qy, ez = z - qz;
-        const float d2 = ex * ex + ey * ey + ez * ez;
-        if (!(d2 < g.r2)) continue;
-        v[0] += 1.0; v[1] += (double)x; v[2] += (double)y; v[3] += (double)z;
-        v[4] += radius - (double)sqrtf(d2);
-      }
+    for (int idx = tid, c = 0; idx < total; idx += BSC_T) {
+      while (idx >= s_pre[c + 1]) ++c;
+      const float4 pt = a.sorted[s_lo[c] + (idx - s_pre[c])];
+      const float x = pt.x, y = pt.y, z = pt.z;
+      const float ex = x - qx, ey = y - qy, ez = z - qz;
+      const float d2 = ex * ex + ey * ey + ez * ez;
+      if (!(d2 < g.r2)) continue;
+      v[0] += 1.0; v[1] += (double)x; v[2] += (double)y; v[3] += (double)z;
+      v[4] += radius - (double)sqrtf(d2);
+    }
     block_sum<5, BSC_T>(v, s_red);
     if (tid == 0) {
       s_cnt = (int)v[0];
@@ -592,17 +604,17 @@ __global__ void __launch_bounds__(BSC_T) k_bsc(const BscArgs a) {
   {
     double v[6] = {0, 0, 0, 0, 0, 0};
     const double cx = s_c[0], cy = s_c[1], cz = s_c[2];
-    for (int c = 0; c < 27; ++c)
-      for (int s = s_lo[c] + tid; s < s_hi[c]; s += BSC_T) {
-        const int k = g.order[s];
-        const float x = g.xyz[3 * (size_t)k], y = g.xyz[3 * (size_t)k + 1], z = g.xyz[3 * (size_t)k + 2];
-        const float ex = x - qx, ey = y - qy, ez = z - qz;
-        const float d2 = ex * ex + ey * ey + ez * ez;
-        if (!(d2 < g.r2)) continue;
-        const float weight = (float)(radius - (double)sqrtf(d2));
-        const double dx = (double)x - cx, dy = (double)y - cy, dz = (double)z - cz, w = (double)weight;
-        v[0] += w * dx * dx; v[1] += w * dx * dy; v[2] += w * dx * dz; v[3] += w * dy * dy; v[4] += w * dy * dz; v[5] += w * dz * dz;
-      }
+    for (int idx = tid, c = 0; idx < total; idx += BSC_T) {
+      while (idx >= s_pre[c + 1]) ++c;
+      const float4 pt = a.sorted[s_lo[c] + (idx - s_pre[c])];
+      const float x = pt.x, y = pt.y, z = pt.z;
+      const float ex = x - qx, ey = y - qy, ez = z - qz;
+      const float d2 = ex * ex + ey * ey + ez * ez;
+      if (!(d2 < g.r2)) continue;
+      const float weight = (float)(radius - (double)sqrtf(d2));
+      const double dx = (double)x - cx, dy = (double)y - cy, dz = (double)z - cz, w = (double)weight;
+      v[0] += w * dx * dx; v[1] += w * dx * dy; v[2] += w * dx * dz; v[3] += w * dy * dy; v[4] += w * dy * dz; v[5] += w * dz * dz;
+    }
     block_sum<6, BSC_T>(v, s_red);
     if (tid == 0) {
       const float da = (float)s_c[3];
@@ -666,10 +678,10 @@ __global__ void __launch_bounds__(BSC_T) k_bsc(const BscArgs a) {
   {
     const float m00 = s_M[0], m01 = s_M[1], m02 = s_M[2], m03 = s_M[3], m10 = s_M[4], m11 = s_M[5], m12 = s_M[6], m13 = s_M[7],
                 m20 = s_M[8], m21 = s_M[9], m22 = s_M[10], m23 = s_M[11];
-    for (int c = 0; c < 27; ++c)
-      for (int s = s_lo[c] + tid; s < s_hi[c]; s += BSC_T) {
-        const int k = g.order[s];
-        const float ex = g.xyz[3 * (size_t)k] - qx, ey = g.xyz[3 * (size_t)k + 1] - qy, ez = g.xyz[3 * (size_t)k + 2] - qz;
+    for (int idx = tid, c = 0; idx < total; idx += BSC_T) {
+        while (idx >= s_pre[c + 1]) ++c;
+        const float4 pt = a.sorted[s_lo[c] + (idx - s_pre[c])];
+        const float ex = pt.x - qx, ey = pt.y - qy, ez = pt.z - qz;
         const float d2 = ex * ex + ey * ey + ez * ez;
         if (!(d2 < g.r2)) continue;
         float loc[3];
@@ -775,14 +787,16 @@ cudaError_t prep_bsc_extract(cudaStream_t st, const float *d_xyz, int n, const i
                              const int *d_pairs, int dof_type, unsigned char *d_bits, float *d_lrf, int *d_status) {
   cudaError_t err = cudaSuccess;
   GridArgs g{};
-  int *order = nullptr, *cstart = nullptr; pu64 *ucell = nullptr;
+  int *order = nullptr, *cstart = nullptr; pu64 *ucell = nullptr; float4 *sorted = nullptr;
   if (n <= 0 || nkp <= 0) return cudaSuccess;
   if (side < 1 || side > BSC_MAX_SIDE) return cudaErrorInvalidValue;
   {
     const float search = (float)(sqrt(3.0) * (double)R);            // :643; squared in float32 like the radius of S4
     PCK(build_grid(st, d_xyz, nullptr, n, search, &g, &order, &ucell, &cstart));
+    PCK(pmalloc(&sorted, (size_t)n));
+    GHICP_LAUNCH(k_bsc_gather, blocks(n), PT, 0, st, d_xyz, order, n, sorted);
     BscArgs a{};
-    a.g = g; a.kp = d_kp; a.nkp = nkp; a.R = R; a.side = side; a.pairs = d_pairs;
+    a.g = g; a.sorted = sorted; a.kp = d_kp; a.nkp = nkp; a.R = R; a.side = side; a.pairs = d_pairs;
     a.V = dof_type > 4 ? 4 : (dof_type > 0 ? 2 : 1);
     a.bits = d_bits; a.nbytes = (9 * side * side + 7) / 8; a.lrf = d_lrf; a.status = d_status;
     GHICP_LAUNCH(k_bsc, nkp, BSC_T, 0, st, a);
@@ -792,7 +806,7 @@ cudaError_t prep_bsc_extract(cudaStream_t st, const float *d_xyz, int n, const i
 #endif
   }
 done:
-  pfree(order); pfree(ucell); pfree(cstart);
+  pfree(order); pfree(ucell); pfree(cstart); pfree(sorted);
   return err;
 }
 

@@ -39,6 +39,7 @@ inline cudaError_t cudaFreeAsync(void *p, cudaStream_t) { free(p); return cudaSu
 inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
 
 struct float4 { float x, y, z, w; };
+inline float4 make_float4(float x, float y, float z, float w) { float4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; }
 struct uint2 { unsigned x, y; };
 struct uint4 { unsigned x, y, z, w; };
 
