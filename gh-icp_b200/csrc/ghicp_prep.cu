@@ -526,6 +526,14 @@ __device__ __forceinline__ void bsc_normalize(float a[3]) {
   z = z + a[2] * a[2];
   if (z > 0.f) { const float n = sqrtf(z); a[0] = a[0] / n; a[1] = a[1] / n; a[2] = a[2] / n; }
 }
+// 64-bit add into a (lo, hi) pair of 32-bit shared words: two native atomics, the carry taken from the value the low word
+// held before.  Sums modulo 2^64 whatever the order of arrival (two's complement values included).
+__device__ __forceinline__ void bsc_add64(unsigned *lo, unsigned *hi, unsigned long long v) {
+  const unsigned vlo = (unsigned)v, vhi = (unsigned)(v >> 32);
+  const unsigned old = atomicAdd(lo, vlo);
+  const unsigned up = vhi + ((unsigned)(old + vlo) < vlo ? 1u : 0u);
+  if (up) atomicAdd(hi, up);
+}
 // index of the source cell of re-arranged cell k of one plane (ReArrange_2D :701-757)
 __device__ __forceinline__ int bsc_rearranged(int tr, int k, int side) {
   const int i = k / side, j = k % side;
@@ -542,8 +550,8 @@ __global__ void k_bsc_gather(const float *__restrict__ xyz, const int *__restric
 
 __global__ void __launch_bounds__(BSC_T) k_bsc(const BscArgs a) {
   __shared__ int s_lo[27], s_pre[28];  // start of each of the 27 cells' runs in the sorted order, prefix sums of their lengths
-  __shared__ unsigned long long s_num[BSC_MAX_CELLS];
-  __shared__ long long s_dep[BSC_MAX_CELLS];
+  __shared__ unsigned s_num_lo[BSC_MAX_CELLS], s_num_hi[BSC_MAX_CELLS];   // 64-bit fixed-point sums as two 32-bit words:
+  __shared__ unsigned s_dep_lo[BSC_MAX_CELLS], s_dep_hi[BSC_MAX_CELLS];   // native 32-bit shared atomics + explicit carry
   __shared__ float s_depth[BSC_MAX_CELLS], s_npw[BSC_MAX_CELLS];
   __shared__ double s_red[10 * (BSC_T / 32)];
   __shared__ double s_c[4];            // centroid, weight sum
@@ -565,7 +573,7 @@ __global__ void __launch_bounds__(BSC_T) k_bsc(const BscArgs a) {
     }
     s_lo[tid] = lo; s_pre[tid + 1] = hi - lo;
   }
-  for (int c = tid; c < cells; c += BSC_T) { s_num[c] = 0ull; s_dep[c] = 0ll; }
+  for (int c = tid; c < cells; c += BSC_T) { s_num_lo[c] = 0u; s_num_hi[c] = 0u; s_dep_lo[c] = 0u; s_dep_hi[c] = 0u; }
   __syncthreads();
   if (tid == 0) { s_pre[0] = 0; for (int c = 0; c < 27; ++c) s_pre[c + 1] += s_pre[c]; }
   __syncthreads();
@@ -692,21 +700,23 @@ __global__ void __launch_bounds__(BSC_T) k_bsc(const BscArgs a) {
         for (int pl = 0; pl < 3; ++pl) {
           const float u = loc[pl == 2 ? 1 : 0], v = loc[pl == 0 ? 1 : 2];
           const float depth = loc[pl == 0 ? 2 : (pl == 1 ? 1 : 0)] + R;   // :240, :274, :308
-          const int iu = (int)floorf((u + R) / unit), iv = (int)floorf((v + R) / unit);
-          for (int i = iu - 2; i <= iu + 2; ++i) {
-            if (i < 0 || i >= side) continue;
+          // centres within 1.5 cell edges of u are among i0 - 1 .. i0 + 2, i0 = the cell row whose centre is just below u
+          // (half a cell of margin against the rounding of this index; the float32 test below is the reference's)
+          const int i0 = (int)floorf((u + R) / unit - 0.5f), j0 = (int)floorf((v + R) / unit - 0.5f);
+#pragma unroll 1
+          for (int i = (i0 - 1 < 0 ? 0 : i0 - 1); i <= i0 + 2 && i < side; ++i) {
             const float cu = (float)((i + 0.5) * unit - R);          // :226
             const float du = u - cu;
-            for (int j = iv - 2; j <= iv + 2; ++j) {
-              if (j < 0 || j >= side) continue;
+#pragma unroll 1
+            for (int j = (j0 - 1 < 0 ? 0 : j0 - 1); j <= j0 + 2 && j < side; ++j) {
               const float cv = (float)((j + 0.5) * unit - R);
               const float dv = v - cv;
               const float dd = du * du + dv * dv;
               if (!(dd < rc2)) continue;
               const float wgt = (float)exp((double)(-dd / two_dd));  // :238 exp(float): rounded-to-nearest float32 exponential
               const int cell = i + j * side + pl * S2;
-              atomicAdd(&s_num[cell], (unsigned long long)((double)wgt * 1099511627776.0));
-              atomicAdd((unsigned long long *)&s_dep[cell], (unsigned long long)__double2ll_rn((double)depth * (double)wgt * dep_scale));
+              bsc_add64(&s_num_lo[cell], &s_num_hi[cell], (unsigned long long)((double)wgt * 1099511627776.0));
+              bsc_add64(&s_dep_lo[cell], &s_dep_hi[cell], (unsigned long long)__double2ll_rn((double)depth * (double)wgt * dep_scale));
             }
           }
         }
@@ -719,9 +729,10 @@ __global__ void __launch_bounds__(BSC_T) k_bsc(const BscArgs a) {
     const float dens_n = (float)cnt / area_n;                        // :347
     const float area_g = unit * unit;
     for (int c = tid; c < cells; c += BSC_T) {
-      const double num = (double)s_num[c] * (1.0 / 1099511627776.0);
+      const double num = (double)(((unsigned long long)s_num_hi[c] << 32) | s_num_lo[c]) * (1.0 / 1099511627776.0);
+      const long long dep_fx = (long long)(((unsigned long long)s_dep_hi[c] << 32) | s_dep_lo[c]);
       float depth = 0.f;
-      if (num != 0.0) depth = (float)(((double)s_dep[c] / dep_scale) / num);
+      if (num != 0.0) depth = (float)(((double)dep_fx / dep_scale) / num);
       const float dens_g = (float)(num / (double)area_g);
       s_depth[c] = depth;
       s_npw[c] = (dens_n != 0.0f) ? dens_g / dens_n : 0.f;
