@@ -220,8 +220,9 @@ struct GridArgs {
 };
 // radius PCA of every point (include/pca.h:133-165, 198-233): one thread per point
 __global__ void k_pca(const GridArgs g, int n, float *__restrict__ lam, double *__restrict__ curvature, int *__restrict__ pt_num) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int i = g.order[t];   // threads of a warp take points of the same cell: same 27 runs, loads broadcast instead of scattered
   const float qx = g.xyz[3 * (size_t)i], qy = g.xyz[3 * (size_t)i + 1], qz = g.xyz[3 * (size_t)i + 2];
   const int cx = cell_coord(qx, g.mnx, g.inv), cy = cell_coord(qy, g.mny, g.inv), cz = cell_coord(qz, g.mnz, g.inv);
   int cnt = 0;
@@ -284,8 +285,10 @@ __global__ void k_cand_emit(const int *__restrict__ flags, const int *__restrict
 }
 // one round of the data-parallel non-maximum suppression; state: 0 undecided, 1 kept, 2 suppressed
 __global__ void k_nms_round(const GridArgs g, int m, int *__restrict__ state, int *__restrict__ undecided) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= m || state[r] != 0) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m) return;
+  const int r = g.order[t];   // candidates in cell order (see k_pca)
+  if (state[r] != 0) return;
   const float *q = g.xyz + 3 * (size_t)g.ids[r];
   const int cx = cell_coord(q[0], g.mnx, g.inv), cy = cell_coord(q[1], g.mny, g.inv), cz = cell_coord(q[2], g.mnz, g.inv);
   bool suppressed = false, blocked = false;
