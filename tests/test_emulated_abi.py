@@ -1,0 +1,172 @@
+"""The WHOLE C ABI on the CPU: tests/harness/emu_library.cpp builds ghicp_capi.cu (context, iteration orchestration, every
+extern "C" entry point) on top of the product's own kernels through the host emulation shim — CUDA threads as fibers, device
+memory = the heap — with the two inline-PTX files (TMA streaming kernel, tcgen05 FD build) reported "not supported", which
+routes the ABI onto its all-double kernels exactly as ghicp_config.force_exact / GHICP_FD_POPC do on a GPU.
+
+This module loads that library IN PLACE OF libghicp_b200.so for the duration of a test (the product never does: it has no CPU
+path) and runs, on a machine without a GPU:
+  * the Python mirror (GHRegistration, register_clouds), the ctypes binding and __graft_entry__.smoke();
+  * the command-line driver and the C++ mirror (ghicp_cli finds the emulated library through LD_LIBRARY_PATH);
+  * the `-m gpu` test FUNCTIONS of tests/test_zz*.py themselves — written after the round's GPU budget was spent — with the
+    emulated library as their `g`.  (This is how a missing `build_fd()` and a too small iteration cap in two of them were
+    found before any GPU run.)
+What it cannot show: anything about ghicp_stream.cu / ghicp_fdtc.cu, code generation, memory ordering, performance."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="session")
+def emu_library_path(tmp_path_factory):
+    d = tmp_path_factory.mktemp("emulib")
+    out = d / "libghicp_b200.so"                   # the product's soname: ghicp_cli resolves it through LD_LIBRARY_PATH
+    src = os.path.join(ROOT, "tests", "harness", "emu_library.cpp")
+    extra = os.environ.get("GHICP_EMU_CXXFLAGS", "").split()
+    r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-DGHICP_EMU_HOST"] + extra +
+                       ["-I" + os.path.join(ROOT, "tests", "harness", "cuda_emu"), "-I" + os.path.join(ROOT, "include"), "-x", "c++",
+                        "-shared", "-Wl,--no-undefined", "-o", str(out), src, "-ldl"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return str(out)
+
+
+@pytest.fixture()
+def ge(g, emu_library_path):
+    """The product package with the emulated library swapped in for this test only."""
+    real = g.capi.lib()
+    emu = C.CDLL(emu_library_path)
+    for name in g.capi.EXPORTS:
+        f, e = getattr(real, name), getattr(emu, name)
+        if f.argtypes is not None:
+            e.argtypes = f.argtypes
+        e.restype = f.restype
+    g.capi._lib = emu
+    try:
+        yield g
+    finally:
+        g.capi._lib = real
+
+
+@pytest.fixture()
+def cli_env(emu_library_path):
+    return {"LD_LIBRARY_PATH": os.path.dirname(emu_library_path) + os.pathsep + os.environ.get("LD_LIBRARY_PATH", "")}
+
+
+def test_emulated_library_exports_the_whole_abi_and_reports_one_device(ge, g, emu_library_path):
+    L = C.CDLL(emu_library_path)
+    for s in g.capi.EXPORTS:                       # tests/test_abi.py checks EXPORTS == the header's declarations
+        assert hasattr(L, s), s
+    assert ge.device_count() == 1
+    assert ge.capi.lib() is not None and g.capi._lib is not None
+
+
+# ---- the hot path through the ABI: lock-step with the oracle -------------------------------------------------------------
+@pytest.mark.parametrize("ft,ct,dof", [("none", "nn", 6), ("none", "nnr", 6), ("bsc", "nn", 6), ("bsc", "nnr", 4), ("bsc", "km", 6),
+                                       ("fpfh", "nn", 6), ("fpfh", "nnr", 6)])   # FPFH + KM: the ORACLE's Kuhn-Munkres
+# (slack steps of eps = 0.01 on float costs of order 1e4) takes minutes per iteration; that pair has its -m gpu test
+def test_registration_through_the_abi_in_lock_step_with_the_oracle(ge, orc, ft, ct, dof):
+    g = ge
+    FT = {"none": g.FT_NONE, "bsc": g.FT_BSC, "fpfh": g.FT_FPFH}[ft]
+    CT = {"nn": g.CT_NN, "nnr": g.CT_NNR, "km": g.CT_KM}[ct]
+    N, M, iters = (110, 100, 8) if ct == "km" else (260, 230, 30)   # every emulated auction round runs ~1000 fibers: keep KM small
+    sc = g.synth.gen_points(N, M, overlap=0.9, seed=11)
+    if ft == "bsc":
+        g.synth.add_bsc(sc, V=4 if dof == 6 else 2)
+    if ft == "fpfh":
+        g.synth.add_fpfh(sc)
+    reg = g.registration.from_scene(sc, FT, CT, dof=dof, max_iter=iters)
+    o = orc.Oracle(FT, CT, dof=dof, bbx_magnitude=sc.bbx_magnitude, solve_mode=1, max_iter=iters)
+    o.set_keypoints(sc.S, sc.T)
+    if ft == "bsc":
+        o.set_bsc(sc.bsc_s, sc.bsc_t, sc.bits)
+    if ft == "fpfh":
+        o.set_fpfh(sc.fpfh_s, sc.fpfh_t)
+    o.build_fd()
+    for it in range(iters):
+        a, b = reg.iterate(), o.iterate()
+        if ct == "km":      # eps-optimal matchings are not unique: compare the objective, keep both on one trajectory
+            assert abs(a.km_energy - b.km_energy) <= N * 0.01 + 1e-6 * abs(b.km_energy)
+            o.set_keypoints(reg.source(), sc.T)
+            if ft == "bsc":
+                o.set_bsc(sc.bsc_s, sc.bsc_t, sc.bits)
+            if ft == "fpfh":
+                o.set_fpfh(sc.fpfh_s, sc.fpfh_t)
+            o.build_fd()
+            o.set_state(a.iteration + 1, a.rmse, a.fdm, a.fdstd, a.para1, a.para2)
+        else:
+            assert np.array_equal(reg.pairs()[0], o.pairs()[0]) and np.array_equal(reg.pairs()[1], o.pairs()[1]), it
+            assert a.cor == b.cor and a.rmse == pytest.approx(b.rmse, rel=1e-6)
+        if a.converged or b.converged:
+            break
+    if a.converged:
+        assert g.synth.rot_angle(reg.Rt_tillnow()[:3, :3], sc.R_gt) < 2e-2
+    reg.close()
+
+
+def test_smoke_entry_point(ge):
+    import __graft_entry__ as entry
+    entry.smoke()
+
+
+# ---- the `-m gpu` test functions of tests/test_zz*.py, on the emulated library ------------------------------------------
+def test_zz2_functions(ge, orc, tmp_path, cli_env):
+    import test_zz2_prep_gpu as z
+    z.test_voxel_filter_equals_oracle(ge, orc, 5000, 0.4, 4)
+    z.test_voxel_filter_equals_oracle(ge, orc, 1, 1.0, 6)
+    z.test_keypoint_detection_equals_oracle(ge, orc, 1500, 0.6, 0.6, 9)
+    z.test_prep_error_paths(ge)
+    z.test_pipeline_raw_cloud_to_registration(ge, orc, n_points=12000)
+    z.test_command_line_driver_registers_two_files(ge, orc, tmp_path, n_points=12000, cli_env=cli_env)
+
+
+def test_zz2_python_pipeline_helper(ge, orc, monkeypatch):
+    import test_zz2_prep_gpu as z
+    small = z.scan_like_cloud
+    monkeypatch.setattr(z, "scan_like_cloud", lambda n, seed, **kw: small(min(n, 12000), seed, **kw))
+    z.test_python_pipeline_helper(ge, orc)
+
+
+def test_zz3_functions(ge, orc):
+    import test_zz3_bsc_gpu as z
+    for dof, V in ((0, 1), (4, 2), (6, 4)):
+        z.test_golden_vectors_of_the_reference_build(ge, dof, V)
+    z.test_equals_oracle(ge, orc, 3000, 40, 1.0, 7, 1)
+    z.test_equals_oracle(ge, orc, 2500, 16, 1.2, 9, 5)
+    z.test_isolated_keypoints_borders_and_bad_arguments(ge, orc)
+
+
+def test_zz3_pipeline_and_command_line_with_bsc_features(ge, orc, tmp_path, cli_env):
+    import test_zz3_bsc_gpu as z
+    z.test_raw_clouds_to_transform_with_bsc_features(ge, orc, n_points=7000)
+    z.test_command_line_driver_with_bsc_features(ge, tmp_path, n_points=7000, cli_env=cli_env)
+
+
+@pytest.mark.parametrize("name", ["none_nn", "bsc_nnr", "bsc_km", "bsc_nn_dof4", "fpfh_nnr"])
+def test_zz_loop_fixture_functions(ge, scratch_cwd, name):
+    import test_zz_extensions as z
+    z.test_cuda_path_reproduces_committed_loop_fixture(ge, scratch_cwd, name)
+
+
+def test_zz_feature_distance_fixture_functions(ge):
+    import test_zz_extensions as z
+    for bits in (441, 9, 2048):
+        z.test_fd_bsc_equals_reference_hamming_fixture(ge, bits)
+    for mf in (1, -1):
+        z.test_fd_fpfh_equals_reference_fixture(ge, mf)
+
+
+def test_zz_extension_functions(ge, orc, monkeypatch):
+    import test_zz_extensions as z
+    z.test_fpfh_matrix_free_fd_identical(ge, orc, 100, 77)
+    z.test_fpfh_matrix_free_rowmin_identical(ge, 5, 3)
+    z.test_fpfh_fast_path_equals_exact_path(ge, "nnr", 600, 500)
+    z.test_fpfh_auto_mode_and_overrides(ge, monkeypatch)
+    z.test_weighted_svd_unit_weights_bit_equal_to_rigid_fit(ge, 1000)
+    z.test_estimators_match_oracle(ge, orc, 40)
+    z.test_estimators_degenerate_and_errors(ge)
+    for solver in ("yaw", "plane"):
+        z.test_loop_with_opt_in_estimator_lockstep_with_oracle(ge, orc, solver)

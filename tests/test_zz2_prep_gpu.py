@@ -27,10 +27,10 @@ def test_keypoint_detection_equals_oracle(g, orc, n, radius, nms, seed):
     assert np.array_equal(kp, okp)
 
 
-def test_pipeline_raw_cloud_to_registration(g, orc):
+def test_pipeline_raw_cloud_to_registration(g, orc, n_points=40000):
     """test/ghicp_main.cpp:86-151 end to end on the GPU: downsample both clouds, detect keypoints, register the
     keypoints (no feature, NN) — every stage equal to the oracle's."""
-    T = scan_like_cloud(40000, 21)
+    T = scan_like_cloud(n_points, 21)
     R = g.synth.rot_xyz_deg(0.5, -0.3, 1.5)
     S = ((T.astype(np.float64) - [0.3, -0.2, 0.1]) @ R).astype(np.float32)      # R (s) + t = target
     clouds = {}
@@ -64,20 +64,20 @@ def test_prep_error_paths(g):
         g.detect_keypoints(np.zeros((10, 3), np.float32), -1.0)
 
 
-def test_command_line_driver_registers_two_files(g, orc, tmp_path):
+def test_command_line_driver_registers_two_files(g, orc, tmp_path, n_points=40000, cli_env=None):
     """gh-icp_b200/cxx/ghicp_cli with the reference's argument list (test/ghicp_main.cpp:56-79) on two .pcd files,
     feature N, correspondence N: the transform equals the one of the same pipeline driven through Python + the oracle."""
     import os
     import subprocess
     from test_cli_io import CLI, ROOT, read_pcd_binary, write_pcd
     assert subprocess.run(["make", "-C", os.path.join(ROOT, "gh-icp_b200", "cxx"), "ghicp_cli"], capture_output=True).returncode == 0
-    T = scan_like_cloud(40000, 21)
+    T = scan_like_cloud(n_points, 21)
     R = g.synth.rot_xyz_deg(0.5, -0.3, 1.5)
     S = ((T.astype(np.float64) - [0.3, -0.2, 0.1]) @ R).astype(np.float32)
     ft, fs, fr = str(tmp_path / "t.pcd"), str(tmp_path / "s.pcd"), str(tmp_path / "reg.pcd")
     write_pcd(ft, T, True); write_pcd(fs, S, True)
     r = subprocess.run([CLI, ft, fs, fr, "N", "N", "0.25", "1.0", "1.2", "1.1", "0.1", "6", "0.5", "0"], capture_output=True, text=True,
-                       env=dict(os.environ, GHICP_MAX_ITER="50"))
+                       env=dict(os.environ, GHICP_MAX_ITER="50", **(cli_env or {})))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     Rt = np.loadtxt(fr + ".Rt.txt")
     # the same pipeline through the oracle

@@ -78,11 +78,12 @@ def test_isolated_keypoints_borders_and_bad_arguments(g, orc):
         g.capi.bsc_extract(xyz, kp, 1.0, 6, 7, np.full((49, 2), 49, np.int32))       # pair outside the grid
 
 
-def test_raw_clouds_to_transform_with_bsc_features(g, orc):
+def test_raw_clouds_to_transform_with_bsc_features(g, orc, n_points=40000):
     """test/ghicp_main.cpp:86-151 with Ft = BSC, everything on the GPU: downsample, keypoints, descriptors (target dof 0,
     source dof 6 like :115-116), GHRegistration (NNR).  Fed with the same descriptors the oracle's loop picks the same pairs
-    iteration by iteration, and register_clouds (the one-call form) returns the transform of the stepwise run."""
-    T = scan_like_cloud(40000, 21)
+    iteration by iteration, and register_clouds (the one-call form) returns the transform of the stepwise run.
+    (n_points: tests/test_emulated_abi.py runs this very function on the CPU with a smaller cloud.)"""
+    T = scan_like_cloud(n_points, 21)
     R = g.synth.rot_xyz_deg(0.5, -0.3, 1.5)
     S = ((T.astype(np.float64) - [0.3, -0.2, 0.1]) @ R).astype(np.float32)           # R s + t = target
     cl = {}
@@ -98,40 +99,43 @@ def test_raw_clouds_to_transform_with_bsc_features(g, orc):
     bbx = float(np.float32(ext[0] + ext[1] + ext[2]))
     Kp = g.Keypoints().setCoordinate(cl["S"][1], cl["T"][1]).setBSCfeature(cl["S"][2], cl["T"][2][0], 441)
     Ef = g.Energyfunction().init(Kp.kps_num, Kp.kpt_num, bbx)
-    reg = g.GHRegistration(Kp, Ef, g.FT_BSC, g.CT_NNR, 1.2, max_iter=40)
-    o = orc.Oracle(orc.FT_BSC, orc.CT_NNR, bbx_magnitude=bbx, nonmax=1.2, solve_mode=1, max_iter=40)
+    reg = g.GHRegistration(Kp, Ef, g.FT_BSC, g.CT_NNR, 1.2, max_iter=80)
+    o = orc.Oracle(orc.FT_BSC, orc.CT_NNR, bbx_magnitude=bbx, nonmax=1.2, solve_mode=1, max_iter=80)
     o.set_keypoints(cl["S"][1], cl["T"][1])
     o.set_bsc(cl["S"][2], cl["T"][2][0], 441)
-    for it in range(40):
+    o.build_fd()
+    for it in range(80):                                   # this pair converges after 43 iterations
         a, b = reg.iterate(), o.iterate()
         assert np.array_equal(reg.pairs()[0], o.pairs()[0]) and np.array_equal(reg.pairs()[1], o.pairs()[1]), it
         if a.converged or b.converged:
             break
+    assert a.converged and b.converged
     Rt_step = reg.Rt_tillnow()
     reg.close()
-    Rt, info = g.register_clouds(T, S, 0.25, 1.0, 1.2, corr_type=g.CT_NNR, feature_type=g.FT_BSC, max_iter=40)
+    Rt, info = g.register_clouds(T, S, 0.25, 1.0, 1.2, corr_type=g.CT_NNR, feature_type=g.FT_BSC, max_iter=80)
     assert info["n_source_kp"] == len(cl["S"][1]) and info["n_target_kp"] == len(cl["T"][1])
     assert np.allclose(Rt, Rt_step, atol=1e-12)
 
 
-def test_command_line_driver_with_bsc_features(g, tmp_path):
+def test_command_line_driver_with_bsc_features(g, tmp_path, n_points=40000, cli_env=None):
     """ghicp_cli ... B R ...: the reference's own command line with BSC features and reciprocal-NN correspondences; the
     transform equals the one of the same pipeline through Python (register_clouds).  Run from an empty directory (the shipped
     pattern) and again with a ./sample_pattern.txt holding that pattern (the reference's way): same result."""
     import subprocess
     from test_cli_io import CLI, ROOT, write_pcd
     assert subprocess.run(["make", "-C", os.path.join(ROOT, "gh-icp_b200", "cxx"), "ghicp_cli"], capture_output=True).returncode == 0
-    T = scan_like_cloud(40000, 21)
+    T = scan_like_cloud(n_points, 21)
     R = g.synth.rot_xyz_deg(0.5, -0.3, 1.5)
     S = ((T.astype(np.float64) - [0.3, -0.2, 0.1]) @ R).astype(np.float32)
     ft, fs, fr = str(tmp_path / "t.pcd"), str(tmp_path / "s.pcd"), str(tmp_path / "reg.pcd")
     write_pcd(ft, T, True); write_pcd(fs, S, True)
-    Rt_py, _ = g.register_clouds(T, S, 0.25, 1.0, 1.2, corr_type=g.CT_NNR, feature_type=g.FT_BSC, max_iter=40)
+    Rt_py, _ = g.register_clouds(T, S, 0.25, 1.0, 1.2, corr_type=g.CT_NNR, feature_type=g.FT_BSC, max_iter=80)
     args = [CLI, ft, fs, fr, "B", "R", "0.25", "1.0", "1.2", "1.1", "0.1", "6", "0.5", "0"]
     for with_file in (False, True):
         if with_file:
             np.savetxt(tmp_path / "sample_pattern.txt", g.bsc_default_pattern(7), fmt="%d")
-        r = subprocess.run(args, capture_output=True, text=True, cwd=str(tmp_path), env=dict(os.environ, GHICP_MAX_ITER="40"))
+        r = subprocess.run(args, capture_output=True, text=True, cwd=str(tmp_path),
+                           env=dict(os.environ, GHICP_MAX_ITER="80", **(cli_env or {})))
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         assert ("./sample_pattern.txt" if with_file else "shipped default") in r.stdout
         assert np.allclose(np.loadtxt(fr + ".Rt.txt"), Rt_py, atol=1e-9)
