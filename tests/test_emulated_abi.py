@@ -170,3 +170,27 @@ def test_zz_extension_functions(ge, orc, monkeypatch):
     z.test_estimators_degenerate_and_errors(ge)
     for solver in ("yaw", "plane"):
         z.test_loop_with_opt_in_estimator_lockstep_with_oracle(ge, orc, solver)
+
+
+# ---- bench.py's own arm, end to end (the numbers mean nothing here; the contract does) --------------------------------------
+@pytest.mark.parametrize("workload", ["config2", "config3"])
+def test_bench_line_contract_on_the_emulated_library(ge, capsys, monkeypatch, workload):
+    import json
+    import runpy
+    import sys
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--workload", workload, "--n", "200", "--steps", "3", "--warmup", "3",
+                                      "--cpu-sample", "200"])
+    runpy.run_path(os.path.join(ROOT, "bench.py"), run_name="__main__")
+    lines = [l for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "clocks", "gpu_launches"):
+        assert k in d, k
+    assert d["metric"] == "ICP iterations/sec" and d["steps"] == 3 and d["warmup"] == 3 and d["n_gpus"] == 1
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(d["roofline"])
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(d["cpu_baseline"])
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(d["e2e"])
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert d["gpu_launches"] > 0 and d["vs_baseline"] is None
+    assert "workload" in d["config"] and "model" not in d["config"]
