@@ -234,3 +234,49 @@ def test_random_odd_sizes_in_lock_step_with_the_oracle(ge, orc):
             if a.converged or b.converged:
                 break
         reg.close()
+
+
+def test_random_odd_clouds_through_the_preprocessing_abi(ge, orc):
+    """1-, 2-, 3-point clouds, exact planes and lines, coincident points, centimetre to 50 m scales, offsets of +-1000 m, grids of
+    1 x 1 to 9 x 9 cells: voxel filter, keypoint detector and BSC encoder through the ABI against the oracle.  Voxel indices,
+    eigenvalues, curvatures, counts, keypoints and encoder status must be identical; descriptors are compared on the generic
+    clouds (a 2 x 2 grid on 3 points is decided by rounding noise in the reference too).  300 trials ran clean under ASan."""
+    from test_bsc_encoder import hamming
+    g = ge
+    rng = np.random.default_rng(3)
+    tot = diff = 0
+    for trial in range(60):
+        n = int(rng.choice([1, 2, 3, 5, 17, 100, 700, 3000]))
+        kind = str(rng.choice(["uniform", "plane", "dups", "line", "clusters"]))
+        scale = float(rng.choice([0.01, 1.0, 50.0]))
+        P = rng.random((n, 3)) * scale
+        if kind == "plane":
+            P[:, 2] = 0.3 * scale + 1e-4 * scale * rng.standard_normal(n)
+        if kind == "dups":
+            P = P[rng.integers(0, max(1, n // 3), n)]
+        if kind == "line":
+            P[:, 1:] = 0.5 * scale
+        if kind == "clusters":
+            P = P[rng.integers(0, max(1, n // 10), n)] + 0.02 * scale * rng.standard_normal((n, 3))
+        P = (P + float(rng.choice([0.0, -100.0, 1000.0]))).astype(np.float32)
+        what = (trial, n, kind, scale)
+        vox = float(rng.choice([0.001, 0.05, 0.3, 2.0])) * scale
+        assert np.array_equal(g.voxel_downsample(P, vox), orc.voxel_downsample(P, vox)), what
+        rad = float(rng.choice([0.02, 0.1, 0.4, 3.0])) * scale
+        nms = float(rng.choice([0.05, 0.3, 1.0])) * scale
+        minp = int(rng.choice([3, 20]))
+        kp, lam, curv, cnt = g.detect_keypoints(P, rad, 0.65, minp, nms)
+        okp, olam, ocurv, ocnt = orc.detect_keypoints(P, rad, 0.65, minp, nms)
+        assert np.array_equal(cnt, ocnt) and np.array_equal(lam, olam) and np.array_equal(curv, ocurv) and np.array_equal(kp, okp), what
+        side = int(rng.choice([1, 2, 3, 7, 9])); dof = int(rng.choice([0, 3, 6]))
+        kpi = rng.choice(n, int(min(n, rng.choice([1, 2, 9]))), replace=False).astype(np.int32)
+        pairs = np.stack([rng.integers(0, side * side, side * side), rng.integers(0, side * side, side * side)], axis=1).astype(np.int32)
+        R = float(rng.choice([0.05, 0.3, 2.0])) * scale
+        got, _, st = g.bsc_extract(P, kpi, R, dof, side, pairs)
+        want, _, wst = orc.bsc_extract(P, kpi, R, pairs, side, dof)
+        assert np.array_equal(st, wst), what
+        ok = wst == 0
+        assert got[:, ~ok].sum() == 0
+        if kind in ("uniform", "clusters") and ok.any() and side >= 7 and n >= 100:
+            h = hamming(got[:, ok], want[:, ok]); tot += h.size; diff += int((h > 0).sum())
+    assert tot > 0 and diff <= 0.02 * tot + 1
