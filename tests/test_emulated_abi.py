@@ -21,30 +21,11 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.fixture(scope="session")
-def emu_library_path(tmp_path_factory):
-    d = tmp_path_factory.mktemp("emulib")
-    out = d / "libghicp_b200.so"                   # the product's soname: ghicp_cli resolves it through LD_LIBRARY_PATH
-    src = os.path.join(ROOT, "tests", "harness", "emu_library.cpp")
-    extra = os.environ.get("GHICP_EMU_CXXFLAGS", "").split()
-    r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-DGHICP_EMU_HOST"] + extra +
-                       ["-I" + os.path.join(ROOT, "tests", "harness", "cuda_emu"), "-I" + os.path.join(ROOT, "include"), "-x", "c++",
-                        "-shared", "-Wl,--no-undefined", "-o", str(out), src, "-ldl"], capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr[-3000:]
-    return str(out)
-
-
 @pytest.fixture()
 def ge(g, emu_library_path):
     """The product package with the emulated library swapped in for this test only."""
-    real = g.capi.lib()
-    emu = C.CDLL(emu_library_path)
-    for name in g.capi.EXPORTS:
-        f, e = getattr(real, name), getattr(emu, name)
-        if f.argtypes is not None:
-            e.argtypes = f.argtypes
-        e.restype = f.restype
-    g.capi._lib = emu
+    from conftest import swap_in_library
+    real = swap_in_library(g, emu_library_path)
     try:
         yield g
     finally:
