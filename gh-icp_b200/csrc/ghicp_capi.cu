@@ -315,11 +315,7 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
 
   CK(c, cudaEventRecord(c->ev[0], st));
   const int ft = c->cfg.feature_type, ct = c->cfg.corr_type;
-#if defined(GHICP_EMU_LIBRARY)
-  const bool fast = false;   // tests/harness/emu_library.cpp: the TMA streaming kernel cannot be emulated -> all-double kernels
-#else
   const bool fast = c->use_fast && (ft == GHICP_FT_NONE || ft == GHICP_FT_BSC);
-#endif
   // FPFH: FP32 filter over on-the-fly feature distances + exact refinement (ghicp_fpfh.cu).  Taken when no decision
   // depends on the CD mean, which a filter cannot reproduce in FPFH mode (heavy-tailed ED / FD^ex): NNR has no gate,
   // NN's penalty is RMS*para1*scale*para2 from iteration 2 on (src/ghicp_reg.cpp:327-330).

@@ -43,6 +43,38 @@ constexpr int ST_STAGE_BYTES = ST_UNROLL * ST_SEG_BYTES;     // 2048
 constexpr int ST_RING_BYTES = ST_STAGES * ST_STAGE_BYTES;    // per warp
 constexpr int ST_DYN_SMEM = ST_WARPS * ST_RING_BYTES;
 
+#if defined(GHICP_EMU_HOST)
+__device__ __forceinline__ void fence_proxy_async() {}     // one OS thread: program order is memory order
+__device__ __forceinline__ void fence_mbarrier_init() {}
+// Host emulation (tests/harness): an mbarrier is modelled inside its own 64-bit word — bit 63 the phase, bits 48-62 the
+// arrival count it was initialised with, bits 32-47 the arrivals still pending, bits 0-31 the transaction bytes still
+// pending (signed) — and a bulk copy is a memcpy that completes its bytes at once.  A waiting fiber yields.
+struct EmuBar { int tx; unsigned short pending; unsigned short init_phase; };   // init_phase: bit 15 = phase, low 15 = count
+__device__ __forceinline__ void emu_bar_check(EmuBar *b) {
+  if (b->pending == 0 && b->tx == 0) { b->init_phase ^= 0x8000u; b->pending = (unsigned short)(b->init_phase & 0x7fffu); }
+}
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  EmuBar *b = reinterpret_cast<EmuBar *>(bar);
+  b->tx = 0; b->pending = (unsigned short)count; b->init_phase = (unsigned short)count;
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  EmuBar *b = reinterpret_cast<EmuBar *>(bar);
+  b->tx += (int)bytes; b->pending -= 1;
+  emu_bar_check(b);
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  EmuBar *b = reinterpret_cast<EmuBar *>(bar);
+  while ((unsigned)(b->init_phase >> 15) == parity) emu::yield();
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  memcpy(dst, src, bytes);
+  EmuBar *b = reinterpret_cast<EmuBar *>(bar);
+  b->tx -= (int)bytes;
+  emu_bar_check(b);
+}
+#else
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbarrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -62,8 +94,31 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+#endif
+
 enum { SM_NN = 0, SM_NNR = 1, SM_COUNT = 2, SM_FILL = 3, SM_PRE = 4, SM_PRE_COLS = 5 };
 
+#if defined(GHICP_EMU_HOST)
+// Host emulation of the PTX-only arithmetic: the approximate square root becomes the exact one (inside the filter's error
+// budget), a packed f32x2 operation is two scalar ones with the same single rounding, the mixed f16 x f16 + f32 FMA is an
+// fmaf of the converted halves (their product is exact in float).
+typedef unsigned long long u64;
+__device__ __forceinline__ float sqrt_approx(float x) { return sqrtf(x); }
+__device__ __forceinline__ u64 pack2(float lo, float hi) { return ((u64)__float_as_uint(hi) << 32) | __float_as_uint(lo); }
+__device__ __forceinline__ void unpack2(u64 v, float &lo, float &hi) { lo = __uint_as_float((unsigned)v); hi = __uint_as_float((unsigned)(v >> 32)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  float al, ah, bl, bh, cl, ch; unpack2(a, al, ah); unpack2(b, bl, bh); unpack2(c, cl, ch);
+  return pack2(fmaf(al, bl, cl), fmaf(ah, bh, ch));
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+  float al, ah, bl, bh; unpack2(a, al, ah); unpack2(b, bl, bh);
+  return pack2(al + bl, ah + bh);
+}
+__device__ __forceinline__ float fhfma(unsigned short h, unsigned short w, float c) {
+  return fmaf(__half2float(__ushort_as_half(h)), __half2float(__ushort_as_half(w)), c);
+}
+__device__ __forceinline__ uint4 ldg_stream(const uint4 *p) { return *p; }
+#else
 __device__ __forceinline__ float sqrt_approx(float x) {
   float r;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -87,6 +142,7 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
+#endif
 __device__ __forceinline__ unsigned long long ord64(double v) {  // CD >= 0: bit pattern is monotone
   return (unsigned long long)__double_as_longlong(v);
 }
@@ -94,7 +150,7 @@ __device__ __forceinline__ float half_lo(unsigned w) { return __half2float(__ush
 __device__ __forceinline__ float half_hi(unsigned w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
 
 // exact CD(i,j), the reference's operation order, no FMA contraction (src/ghicp_reg.cpp:122,224,259)
-__device__ __noinline__ double exact_cd(const StreamArgs &a, int i, int j) {
+__device__ GHICP_NOINLINE double exact_cd(const StreamArgs &a, int i, int j) {
   const double sx = a.s[i], sy = a.s[(size_t)a.N + i], sz = a.s[2 * (size_t)a.N + i];
   const double tx = a.t[j], ty = a.t[(size_t)a.M + j], tz = a.t[2 * (size_t)a.M + j];
   const double dx = __dsub_rn(sx, tx), dy = __dsub_rn(sy, ty), dz = __dsub_rn(sz, tz);
@@ -198,14 +254,14 @@ __device__ __forceinline__ void push_candidate(const StreamArgs &a, int which, i
 }
 
 // slow paths (rare): kept out of line so the streaming loop stays compact in the instruction cache
-__device__ __noinline__ void slow_row(const StreamArgs &a, int i, int j, float cdv, float lim) {
+__device__ GHICP_NOINLINE void slow_row(const StreamArgs &a, int i, int j, float cdv, float lim) {
   if (cdv <= lim) {
     const double e = exact_cd(a, i, j);
     atomicMin(&a.rowbest[i], ord64(e));
     push_candidate(a, 0, i, j, e);
   }
 }
-__device__ __noinline__ void slow_col(const StreamArgs &a, int i, int j, float cdv, float lim) {
+__device__ GHICP_NOINLINE void slow_col(const StreamArgs &a, int i, int j, float cdv, float lim) {
   if (cdv <= lim) {
     const double e = exact_cd(a, i, j);
     atomicMin(&a.colbest[j], ord64(e));
@@ -216,7 +272,7 @@ __device__ __noinline__ void slow_col(const StreamArgs &a, int i, int j, float c
 // KM count pass, rare path: a warp-row with `total` gate hits (bit c of mask8 = column j0 + c of this lane).
 // Besides the per-row count the hits are appended to a global edge list, so that the CSR can be scattered
 // from the list instead of streaming the plane a second time (the fill pass stays as the overflow fallback).
-__device__ __noinline__ void emit_hits(const StreamArgs &a, int *s_cnt_r, int row, int j0, unsigned mask8, int total,
+__device__ GHICP_NOINLINE void emit_hits(const StreamArgs &a, int *s_cnt_r, int row, int j0, unsigned mask8, int total,
                                        int lane) {
   if (lane == 0) atomicAdd(s_cnt_r, total);
   if (a.emit_cap == 0) return;  // list switched off (dense graph expected): count only, the fill pass follows
@@ -491,7 +547,7 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, c
       const int k = rb / ST_UNROLL;
       __syncwarp();
       if (lane == 0 && k + ST_STAGES < nbatch) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        fence_proxy_async();
         issue(k + ST_STAGES);
       }
     }
@@ -517,7 +573,11 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, c
 template <int MODE, bool HAS_FD, bool STATS, bool TMA, bool X2>
 __global__ void __launch_bounds__(ST_THREADS, (TMA && !X2) ? 3 : 2) k_stream(const StreamArgs a) {
   __shared__ __align__(16) float s_S8[X2 ? ST_RB * 8 : 8];
+#if defined(GHICP_EMU_HOST)
+  unsigned char *s_ring = reinterpret_cast<unsigned char *>(emu::dyn_smem());   // host emulation: the launch's dynamic shared memory
+#else
   extern __shared__ __align__(128) unsigned char s_ring[];   // [ST_WARPS][ST_RING_BYTES] when TMA
+#endif
   __shared__ __align__(8) unsigned long long s_bar[ST_WARPS][ST_STAGES];
   __shared__ float4 s_S4[ST_RB];
   __shared__ unsigned s_thr[ST_RB];
@@ -531,7 +591,7 @@ __global__ void __launch_bounds__(ST_THREADS, (TMA && !X2) ? 3 : 2) k_stream(con
     const int panel0 = blockIdx.x * ST_CTA_COLS + warp * ST_PANEL;
     if (lane == 0) {
       for (int st = 0; st < ST_STAGES; ++st) mbar_init(&s_bar[warp][st], 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      fence_mbarrier_init();
       if (panel0 < a.M) {
         const unsigned short *pb = a.fd + fd_index(a.fd_rows, r0 - a.row0, panel0);
         const int nbatch = (nrows + ST_UNROLL - 1) / ST_UNROLL;
@@ -737,10 +797,10 @@ cudaError_t launch_stream_prep(Ctx *c, const CostParams &cp, int for_km_gate) {
   const double b = bsc ? (double)c->b_eff : 0.0;
   const int n = c->N > c->M ? c->N : c->M;
   cudaMemsetAsync(&c->d_sdev->r2max_bits, 0, sizeof(unsigned), c->stream);
-  k_prep<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_s, c->d_t, c->N, c->M, c->center[0], c->center[1], c->center[2], A,
+  GHICP_LAUNCH(k_prep, (n + 255) / 256, 256, 0, c->stream, c->d_s, c->d_t, c->N, c->M, c->center[0], c->center[1], c->center[2], A,
                                                  reinterpret_cast<float4 *>(c->d_S4), reinterpret_cast<float4 *>(c->d_T4),
                                                  c->d_sdev);
-  k_margin<<<1, 1, 0, c->stream>>>(c->d_sdev, A, a, b, (double)c->bits, c->d_iter, for_km_gate, 1e-5, kappa);
+  GHICP_LAUNCH(k_margin, 1, 1, 0, c->stream, c->d_sdev, A, a, b, (double)c->bits, c->d_iter, for_km_gate, 1e-5, kappa);
   c->launches += 2;
   return cudaGetLastError();
 }
@@ -748,7 +808,7 @@ cudaError_t launch_stream_prep(Ctx *c, const CostParams &cp, int for_km_gate) {
 cudaError_t launch_stream_gate(Ctx *c, const CostParams &cp) {
   const bool bsc = c->cfg.feature_type == GHICP_FT_BSC;
   const double a = (bsc ? cp.scale * cp.WED : cp.scale) * c->kappa;
-  k_margin<<<1, 1, 0, c->stream>>>(c->d_sdev, a * a, a, bsc ? (double)c->b_eff : 0.0, (double)c->bits, c->d_iter, 1, 1e-5,
+  GHICP_LAUNCH(k_margin, 1, 1, 0, c->stream, c->d_sdev, a * a, a, bsc ? (double)c->b_eff : 0.0, (double)c->bits, c->d_iter, 1, 1e-5,
                                    c->kappa);
   c->launches++;
   return cudaGetLastError();
@@ -758,7 +818,7 @@ cudaError_t launch_stream_seed(Ctx *c, const CostParams &cp, bool with_cols) {
   StreamArgs a = make_args(c, cp);
   if (with_cols) a.col_thr_init = c->d_col_thr;
   const int n = c->N > c->M ? c->N : c->M;
-  k_seed<<<(n + 255) / 256, 256, 0, c->stream>>>(a, c->d_row_idx, c->d_col_idx, c->have_prev ? 1 : 0);
+  GHICP_LAUNCH(k_seed, (n + 255) / 256, 256, 0, c->stream, a, c->d_row_idx, c->d_col_idx, c->have_prev ? 1 : 0);
   c->launches++;
   return cudaGetLastError();
 }
@@ -771,18 +831,23 @@ cudaError_t launch_stream(Ctx *c, const CostParams &cp, int mode, bool stats) {
   const dim3 grid = stream_grid(c);
   const bool fd = a.fd != nullptr;
   static const bool use_tma = getenv("GHICP_STREAM_LDG") == nullptr;
+#if defined(GHICP_EMU_HOST)
+#define GHICP_STREAM_OPT_IN_SMEM(kernel) (void)0
+#else
+#define GHICP_STREAM_OPT_IN_SMEM(kernel) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_DYN_SMEM)
+#endif
 #define LAUNCH(MODE, FD, ST)                                                                                   \
   do {                                                                                                         \
     if (FD && use_tma && c->x2_ok) {                                                                           \
-      cudaFuncSetAttribute(k_stream<MODE, FD, ST, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_DYN_SMEM); \
-      k_stream<MODE, FD, ST, true, true><<<grid, ST_THREADS, ST_DYN_SMEM, c->stream>>>(a);                    \
+      GHICP_STREAM_OPT_IN_SMEM((k_stream<MODE, FD, ST, true, true>));                                             \
+      GHICP_LAUNCH((k_stream<MODE, FD, ST, true, true>), grid, ST_THREADS, ST_DYN_SMEM, c->stream, a);                    \
     } else if (FD && use_tma) {                                                                                \
-      cudaFuncSetAttribute(k_stream<MODE, FD, ST, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_DYN_SMEM); \
-      k_stream<MODE, FD, ST, true, false><<<grid, ST_THREADS, ST_DYN_SMEM, c->stream>>>(a);                   \
+      GHICP_STREAM_OPT_IN_SMEM((k_stream<MODE, FD, ST, true, false>));                                            \
+      GHICP_LAUNCH((k_stream<MODE, FD, ST, true, false>), grid, ST_THREADS, ST_DYN_SMEM, c->stream, a);                   \
     } else if (c->x2_ok) {                                                                                     \
-      k_stream<MODE, FD, ST, false, true><<<grid, ST_THREADS, 0, c->stream>>>(a);                             \
+      GHICP_LAUNCH((k_stream<MODE, FD, ST, false, true>), grid, ST_THREADS, 0, c->stream, a);                             \
     } else {                                                                                                   \
-      k_stream<MODE, FD, ST, false, false><<<grid, ST_THREADS, 0, c->stream>>>(a);                            \
+      GHICP_LAUNCH((k_stream<MODE, FD, ST, false, false>), grid, ST_THREADS, 0, c->stream, a);                            \
     }                                                                                                          \
   } while (0)
 #define PICK(MODE)                                      \
@@ -808,10 +873,10 @@ cudaError_t launch_stream(Ctx *c, const CostParams &cp, int mode, bool stats) {
 
 cudaError_t launch_stream_resolve(Ctx *c, const CostParams &cp, bool with_cols) {
   StreamArgs a = make_args(c, cp);
-  k_resolve<<<148 * 4, 256, 0, c->stream>>>(a, 0);
-  if (with_cols) k_resolve<<<148 * 4, 256, 0, c->stream>>>(a, 1);
+  GHICP_LAUNCH(k_resolve, 148 * 4, 256, 0, c->stream, a, 0);
+  if (with_cols) GHICP_LAUNCH(k_resolve, 148 * 4, 256, 0, c->stream, a, 1);
   const int n = c->N > c->M ? c->N : c->M;
-  k_publish<<<(n + 255) / 256, 256, 0, c->stream>>>(a, c->d_row_cd, c->d_row_idx, with_cols ? c->d_col_cd : nullptr,
+  GHICP_LAUNCH(k_publish, (n + 255) / 256, 256, 0, c->stream, a, c->d_row_cd, c->d_row_idx, with_cols ? c->d_col_cd : nullptr,
                                                     with_cols ? c->d_col_idx : nullptr, c->d_xstats, c->rank);
   c->launches += with_cols ? 3 : 2;
   return cudaGetLastError();
@@ -819,12 +884,12 @@ cudaError_t launch_stream_resolve(Ctx *c, const CostParams &cp, bool with_cols) 
 
 cudaError_t launch_finalize_fast(Ctx *c, const LoopScalars &ls) {
   (void)ls;
-  k_finalize_fast<<<1, 1024, 0, c->stream>>>(c->d_part_stats, stream_num_parts(c), c->d_xstats, c->rank, c->kappa);
+  GHICP_LAUNCH(k_finalize_fast, 1, 1024, 0, c->stream, c->d_part_stats, stream_num_parts(c), c->d_xstats, c->rank, c->kappa);
   c->launches++;
   return cudaGetLastError();
 }
 cudaError_t launch_penalty_only(Ctx *c, const LoopScalars &ls) {
-  k_penalty_only<<<1, 1, 0, c->stream>>>(ls, c->d_iter);
+  GHICP_LAUNCH(k_penalty_only, 1, 1, 0, c->stream, ls, c->d_iter);
   c->launches++;
   return cudaGetLastError();
 }
@@ -845,7 +910,7 @@ __global__ void k_colmerge(const unsigned long long *__restrict__ g_cd, const in
   col_idx[j] = bi;
 }
 cudaError_t launch_colmerge(Ctx *c) {
-  k_colmerge<<<(c->M + 255) / 256, 256, 0, c->stream>>>(c->d_colg_cd, c->d_colg_idx, c->world, c->M, c->d_col_cd, c->d_col_idx);
+  GHICP_LAUNCH(k_colmerge, (c->M + 255) / 256, 256, 0, c->stream, c->d_colg_cd, c->d_colg_idx, c->world, c->M, c->d_col_cd, c->d_col_idx);
   c->launches++;
   return cudaGetLastError();
 }
@@ -859,7 +924,7 @@ __global__ void k_count_valid(const double *__restrict__ gain, long long nnz, St
 }
 cudaError_t launch_count_valid(Ctx *c, long long nnz) {
   cudaMemsetAsync(&c->d_sdev->nnz_valid, 0, sizeof(unsigned long long), c->stream);
-  k_count_valid<<<148 * 4, 256, 0, c->stream>>>(c->d_csr_gain, nnz, c->d_sdev);
+  GHICP_LAUNCH(k_count_valid, 148 * 4, 256, 0, c->stream, c->d_csr_gain, nnz, c->d_sdev);
   c->launches++;
   return cudaGetLastError();
 }
@@ -870,13 +935,13 @@ cudaError_t launch_emit_scatter(Ctx *c, const CostParams &cp, unsigned long long
   StreamArgs a = make_args(c, cp);
   const unsigned long long want = (n_emitted + 255) / 256;
   const int blocks = (int)std::min<unsigned long long>(std::max<unsigned long long>(want, 1), 148ull * 8);
-  k_emit_scatter<<<blocks, 256, 0, c->stream>>>(a, n_emitted);
+  GHICP_LAUNCH(k_emit_scatter, blocks, 256, 0, c->stream, a, n_emitted);
   c->launches++;
   return cudaGetLastError();
 }
 cudaError_t launch_csr_check(Ctx *c, const CostParams &cp) {
   StreamArgs a = make_args(c, cp);
-  k_csr_check<<<148 * 4, 256, 0, c->stream>>>(a, c->d_iter, c->d_csr_gain);
+  GHICP_LAUNCH(k_csr_check, 148 * 4, 256, 0, c->stream, a, c->d_iter, c->d_csr_gain);
   c->launches++;
   return cudaGetLastError();
 }

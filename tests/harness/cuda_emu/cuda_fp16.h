@@ -1,4 +1,4 @@
-// cuda_fp16.h — host emulation shim: just enough of __half for ghicp_device.cuh's h2d()
+// cuda_fp16.h — host emulation shim: just enough of __half for ghicp_device.cuh's h2d() and ghicp_stream.cu's fp16 weights
 #pragma once
 #include <stdint.h>
 #include <string.h>
@@ -32,4 +32,8 @@ inline __half __int2half_rn(int v) {   // exact for |v| <= 2048 (the BSC Hamming
   }
   h.bits = (unsigned short)((s << 15) | ((unsigned)(e + 15) << 10) | m);
   return h;
+}
+inline __half __float2half_rn(float f) {   // round to nearest even, through the compiler's IEEE binary16 type
+  const _Float16 v = (_Float16)f;
+  __half h; memcpy(&h.bits, &v, 2); return h;
 }

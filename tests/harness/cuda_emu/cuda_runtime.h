@@ -59,7 +59,9 @@ inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *
 struct float4 { float x, y, z, w; };
 inline float4 make_float4(float x, float y, float z, float w) { float4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; }
 struct uint2 { unsigned x, y; };
+struct ulonglong2 { unsigned long long x, y; };
 struct uint4 { unsigned x, y, z, w; };
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; }
 
 #define threadIdx (emu::cur()->tidx)
 #define blockIdx (emu::cur()->bidx)
@@ -96,6 +98,25 @@ inline unsigned __ballot_sync(unsigned, int pred) {
   return m;
 }
 inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline void __syncwarp(unsigned = 0xffffffffu) { emu::shfl<int>(0, emu::cur()->tidx.x & 31); }   // a shuffle is a rendezvous of the warp's live lanes
+template <typename T> inline T __shfl_sync(unsigned, T v, int src_lane) { return emu::shfl<T>(v, src_lane & 31); }
+inline int __any_sync(unsigned, int pred) {
+  unsigned all[32];
+  emu::warp_all<unsigned>(pred ? 1u : 0u, all);
+  for (int l = 0; l < 32; ++l) if (all[l] & 1u) return 1;
+  return 0;
+}
+inline unsigned __reduce_add_sync(unsigned, unsigned v) {
+  unsigned all[32], s = 0;
+  emu::warp_all<unsigned>(v, all);
+  for (int l = 0; l < 32; ++l) s += all[l];
+  return s;
+}
+inline double __dsub_rn(double a, double b) { return a - b; }     // built with -ffp-contract=off: separately rounded
+inline double __dadd_rn(double a, double b) { return a + b; }
+inline double __dmul_rn(double a, double b) { return a * b; }
+inline double __dsqrt_rn(double a) { return sqrt(a); }
 template <typename T> inline T __ldcg(const T *p) { return *p; }
 inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
 inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
