@@ -1,16 +1,16 @@
 """The WHOLE C ABI on the CPU: tests/harness/emu_library.cpp builds ghicp_capi.cu (context, iteration orchestration, every
 extern "C" entry point) on top of the product's own kernels through the host emulation shim — CUDA threads as fibers, device
-memory = the heap — with the two inline-PTX files (TMA streaming kernel, tcgen05 FD build) reported "not supported", which
-routes the ABI onto its all-double kernels exactly as ghicp_config.force_exact / GHICP_FD_POPC do on a GPU.
+memory = the heap — the TMA streaming kernel of ghicp_stream.cu included (its PTX wrappers have host stand-ins); only the
+tcgen05 FD build is reported "not supported", which selects the POPC kernel exactly as GHICP_FD_POPC does on a GPU.
 
 This module loads that library IN PLACE OF libghicp_b200.so for the duration of a test (the product never does: it has no CPU
 path) and runs, on a machine without a GPU:
-  * the Python mirror (GHRegistration, register_clouds), the ctypes binding and __graft_entry__.smoke();
+  * the Python mirror (GHRegistration, register_clouds), the ctypes binding, __graft_entry__.smoke() and bench.py's own arm;
   * the command-line driver and the C++ mirror (ghicp_cli finds the emulated library through LD_LIBRARY_PATH);
   * the `-m gpu` test FUNCTIONS of tests/test_zz*.py themselves — written after the round's GPU budget was spent — with the
     emulated library as their `g`.  (This is how a missing `build_fd()` and a too small iteration cap in two of them were
     found before any GPU run.)
-What it cannot show: anything about ghicp_stream.cu / ghicp_fdtc.cu, code generation, memory ordering, performance."""
+What it cannot show: anything about ghicp_fdtc.cu, code generation, memory ordering, asynchrony, performance."""
 import ctypes as C
 import os
 import subprocess
