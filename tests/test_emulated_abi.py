@@ -261,3 +261,11 @@ def test_random_odd_clouds_through_the_preprocessing_abi(ge, orc):
         if kind in ("uniform", "clusters") and ok.any() and side >= 7 and n >= 100:
             h = hamming(got[:, ok], want[:, ok]); tot += h.size; diff += int((h > 0).sum())
     assert tot > 0 and diff <= 0.02 * tot + 1
+
+
+def test_cpp_dropin_demo_on_the_emulated_library(ge, orc, tmp_path, monkeypatch, cli_env):
+    """gh-icp_b200/cxx/dropin_demo (Keypoints / Energyfunction / GHRegistration constructed like test/ghicp_main.cpp:143-151,
+    BSC descriptors uploaded through the C++ mirror) resolves libghicp_b200.so through LD_LIBRARY_PATH: the emulated one."""
+    import test_gpu_dropin as z
+    monkeypatch.setenv("LD_LIBRARY_PATH", cli_env["LD_LIBRARY_PATH"])
+    z.test_cpp_dropin_matches_oracle(ge, orc, tmp_path, "bsc-nn")
