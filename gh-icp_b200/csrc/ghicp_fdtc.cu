@@ -23,7 +23,9 @@ constexpr int TC_TM = 128;   // target rows per A tile  (UMMA M)
 constexpr int TC_TN = 256;   // (source, variant) rows per B tile (UMMA N)
 constexpr int TC_THREADS = 256;
 
+#if !defined(GHICP_EMU_HOST)
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+#endif
 
 // bits -> +/-1 int8, written directly in the TILE-CANONICAL layout the MMA reads from shared memory:
 //   out[tile][k-chunk (16 B)][R rows][16 B]      (R = rows per tile; padding rows / bits are 0)
@@ -62,6 +64,30 @@ __global__ void k_unpack_pm1(const uint64_t *__restrict__ words, int V, int n, i
   *reinterpret_cast<uint4 *>(out + idx * 16) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+#if defined(GHICP_EMU_HOST)
+// Host emulation (tests/harness/cuda_emu): mbarriers and bulk copies as in emu_mbarrier.h; tensor memory is an int32 array
+// [128 lanes][512 columns]; one tcgen05.mma kind::i8 K-step is the plain triple loop over the two no-swizzle K-major tiles
+// (k-chunk of 16 bytes outermost, rows 16 bytes apart: the layout k_unpack_pm1 writes); tcgen05.ld 32x32b.x32 gives thread
+// (warp w, lane l) the 32 columns of lane 32 w + l.  Blocks run one at a time, so one static TMEM serves the launch.
+static int emu_tmem[128][512];
+__device__ __forceinline__ void mbar_init1(unsigned long long *b, int count) { emu::bar_init(b, count); }
+__device__ __forceinline__ void mbar_wait_parity(unsigned long long *b, unsigned parity) { emu::bar_wait(b, parity); }
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  emu::bar_arrive_expect_tx(bar, bytes);
+  emu::bulk_copy(dst, src, bytes, bar);
+}
+inline void emu_umma_i8(int d_col, const unsigned char *a_tile, const unsigned char *b_tile, int k, bool accumulate) {
+  const signed char *A = reinterpret_cast<const signed char *>(a_tile) + (size_t)k * 2 * TC_TM * 16;
+  const signed char *B = reinterpret_cast<const signed char *>(b_tile) + (size_t)k * 2 * TC_TN * 16;
+  for (int m = 0; m < TC_TM; ++m)
+    for (int n = 0; n < TC_TN; ++n) {
+      int acc = accumulate ? emu_tmem[m][d_col + n] : 0;
+      for (int kk = 0; kk < 32; ++kk)
+        acc += (int)A[(size_t)(kk >> 4) * TC_TM * 16 + (size_t)m * 16 + (kk & 15)] * (int)B[(size_t)(kk >> 4) * TC_TN * 16 + (size_t)n * 16 + (kk & 15)];
+      emu_tmem[m][d_col + n] = acc;
+    }
+}
+#else
 __device__ __forceinline__ void mbar_init1(unsigned long long *b, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
 }
@@ -83,6 +109,7 @@ __device__ __forceinline__ void bulk_load(void *dst, const void *src, unsigned b
                  ::"r"(smem_u32((unsigned char *)dst + off)), "l"((const unsigned char *)src + off), "r"(n), "r"(smem_u32(bar)) : "memory");
   }
 }
+#endif
 
 __device__ __forceinline__ uint64_t make_desc(unsigned smem_addr, unsigned lbo_bytes, unsigned sbo_bytes) {
   // SM100 shared-memory matrix descriptor: start address [0,14) (>>4), leading byte offset [16,30) (>>4),
@@ -91,11 +118,22 @@ __device__ __forceinline__ uint64_t make_desc(unsigned smem_addr, unsigned lbo_b
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
 
+// fences have no meaning on one host thread
+#if defined(GHICP_EMU_HOST)
+#define GHICP_TC_ASM(text) (void)0
+#else
+#define GHICP_TC_ASM(text) asm volatile(text ::: "memory")
+#endif
+
 template <int V>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_fd_bsc_tc(const int8_t *__restrict__ T8c, const int8_t *__restrict__ S8c, unsigned short *__restrict__ fd, int N, int M,
             size_t fd_rows, int row0, int nloc, int bits, int KP, int dbg) {
+#if defined(GHICP_EMU_HOST)
+  unsigned char *smem = reinterpret_cast<unsigned char *>(emu::dyn_smem());   // host emulation: the launch's dynamic shared memory
+#else
   extern __shared__ __align__(128) unsigned char smem[];
+#endif
   // barriers: [0,1] A tile landed, [2,3] MMA of tile done, [4,5] TMEM accumulator drained, [6] B tile landed
   __shared__ __align__(8) unsigned long long s_bar[7];
   __shared__ unsigned s_tmem_base;
@@ -107,20 +145,24 @@ k_fd_bsc_tc(const int8_t *__restrict__ T8c, const int8_t *__restrict__ S8c, unsi
   const int src_base = row0 + blockIdx.x * SRC_PER_TILE;   // first source row of this CTA's B tile
   const int n_ttiles = (M + TC_TM - 1) / TC_TM;
 
+#if defined(GHICP_EMU_HOST)
+  if (tid == 0) s_tmem_base = 0;   // the whole emulated TMEM, column 0
+#else
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&s_tmem_base)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
+#endif
   if (tid == 0) {
     mbar_init1(&s_bar[0], 1); mbar_init1(&s_bar[1], 1);
     mbar_init1(&s_bar[2], 1); mbar_init1(&s_bar[3], 1);
     mbar_init1(&s_bar[4], 128); mbar_init1(&s_bar[5], 128);
     mbar_init1(&s_bar[6], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    GHICP_TC_ASM("fence.mbarrier_init.release.cluster;");
   }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  GHICP_TC_ASM("tcgen05.fence::before_thread_sync;");
   __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  GHICP_TC_ASM("tcgen05.fence::after_thread_sync;");
   const unsigned tmem_base = s_tmem_base;
 
   if (warp == 4 && lane == 0) {
@@ -130,7 +172,9 @@ k_fd_bsc_tc(const int8_t *__restrict__ T8c, const int8_t *__restrict__ S8c, unsi
     // N>>3 at [17,23), M>>4 at [24,29)
     const unsigned idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(TC_TN >> 3) << 17) | ((unsigned)(TC_TM >> 4) << 24);
     const int ksteps = KP / 32;
+#if !defined(GHICP_EMU_HOST)
     const unsigned b_addr = smem_u32(Bs);
+#endif
     bulk_load(As[0], T8c, a_bytes, &s_bar[0]);                      // A(0)
     for (int t = 0; t < n_ttiles; ++t) {
       const int s = t & 1;
@@ -138,9 +182,14 @@ k_fd_bsc_tc(const int8_t *__restrict__ T8c, const int8_t *__restrict__ S8c, unsi
       if (t >= 2) mbar_wait_parity(&s_bar[4 + s], ph ^ 1);      // epilogue(t-2) drained TMEM buffer s
       if (t == 0) mbar_wait_parity(&s_bar[6], 0);                // B landed
       mbar_wait_parity(&s_bar[s], ph);                           // A(t) landed
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const unsigned a_addr = smem_u32(As[s]);
+      GHICP_TC_ASM("tcgen05.fence::after_thread_sync;");
       const unsigned d_tmem = tmem_base + (unsigned)(s * TC_TN);
+#if defined(GHICP_EMU_HOST)
+      for (int k = 0; k < ((dbg & 2) ? 1 : ksteps); ++k) emu_umma_i8((int)d_tmem, As[s], Bs, k, k > 0);
+      (void)idesc;
+      emu::bar_arrive(&s_bar[2 + s]);                              // tcgen05.commit: the MMAs above have completed
+#else
+      const unsigned a_addr = smem_u32(As[s]);
       for (int k = 0; k < ((dbg & 2) ? 1 : ksteps); ++k) {
         const uint64_t adesc = make_desc(a_addr + (unsigned)k * 2u * TC_TM * 16u, TC_TM * 16u, 128u);
         const uint64_t bdesc = make_desc(b_addr + (unsigned)k * 2u * TC_TN * 16u, TC_TN * 16u, 128u);
@@ -151,6 +200,7 @@ k_fd_bsc_tc(const int8_t *__restrict__ T8c, const int8_t *__restrict__ S8c, unsi
             ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s_bar[2 + s])) : "memory");
+#endif
       // prefetch A(t+1) into the other buffer as soon as MMA(t-1) has finished reading it: the copy then
       // overlaps MMA(t)
       if (t + 1 < n_ttiles) {
@@ -165,12 +215,15 @@ k_fd_bsc_tc(const int8_t *__restrict__ T8c, const int8_t *__restrict__ S8c, unsi
       const int s = t & 1;
       const unsigned ph = (unsigned)((t >> 1) & 1);
       mbar_wait_parity(&s_bar[2 + s], ph);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      GHICP_TC_ASM("tcgen05.fence::after_thread_sync;");
       const int j = t * TC_TM + warp * 32 + lane;  // target column owned by this thread (TMEM lane)
       const unsigned taddr0 = tmem_base + ((unsigned)(warp * 32) << 16) + (unsigned)(s * TC_TN);
 #pragma unroll 1
       for (int cb = 0; cb < TC_TN; cb += 32) {
         unsigned r[32];
+#if defined(GHICP_EMU_HOST)
+        for (int q = 0; q < 32; ++q) r[q] = (unsigned)emu_tmem[(taddr0 >> 16) + lane][(taddr0 & 0xffffu) + cb + q];
+#else
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -181,6 +234,7 @@ k_fd_bsc_tc(const int8_t *__restrict__ T8c, const int8_t *__restrict__ S8c, unsi
               "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
             : "r"(taddr0 + (unsigned)cb));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#endif
         if (j < M && !(dbg & 1)) {
 #pragma unroll
           for (int q = 0; q < 32 / V; ++q) {
@@ -195,17 +249,28 @@ k_fd_bsc_tc(const int8_t *__restrict__ T8c, const int8_t *__restrict__ S8c, unsi
           }
         }
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      GHICP_TC_ASM("tcgen05.fence::before_thread_sync;");
+#if defined(GHICP_EMU_HOST)
+      emu::bar_arrive(&s_bar[4 + s]);
+#else
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_bar[4 + s])) : "memory");
+#endif
     }
   }
   __syncthreads();
+#if !defined(GHICP_EMU_HOST)
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+#endif
 }
 
 }  // namespace
 
 // Returns cudaErrorNotSupported when the shape does not fit this kernel (caller falls back to k_fd_bsc).
+#if defined(GHICP_EMU_HOST)
+#define GHICP_TC_OPT_IN_SMEM(kernel) (void)0
+#else
+#define GHICP_TC_OPT_IN_SMEM(kernel) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+#endif
 cudaError_t launch_fd_bsc_tc(Ctx *c) {
   const int V = (c->cfg.dof == 6) ? 4 : 2;
   const int KP = (c->bits + 31) / 32 * 32;
@@ -222,18 +287,18 @@ cudaError_t launch_fd_bsc_tc(Ctx *c) {
   if ((e = cudaMallocAsync((void **)&S8, s_bytes, c->stream)) != cudaSuccess) { cudaFreeAsync(T8, c->stream); return e; }
   {
     const long long tot = (long long)(t_bytes / 16);
-    k_unpack_pm1<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(c->d_bt, 1, c->M, c->W64, c->bits, KP, TC_TM, 0, c->M, T8);
+    GHICP_LAUNCH(k_unpack_pm1, (unsigned)((tot + 255) / 256), 256, 0, c->stream, c->d_bt, 1, c->M, c->W64, c->bits, KP, TC_TM, 0, c->M, T8);
     const long long tos = (long long)(s_bytes / 16);
-    k_unpack_pm1<<<(unsigned)((tos + 255) / 256), 256, 0, c->stream>>>(c->d_bs, V, c->N, c->W64, c->bits, KP, TC_TN, c->r0,
-                                                                         c->nloc * V, S8);
+    GHICP_LAUNCH(k_unpack_pm1, (unsigned)((tos + 255) / 256), 256, 0, c->stream, c->d_bs, V, c->N, c->W64, c->bits, KP, TC_TN, c->r0,
+                 c->nloc * V, S8);
     c->launches += 2;
   }
   if (V == 4) {
-    cudaFuncSetAttribute(k_fd_bsc_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_fd_bsc_tc<4><<<grid, TC_THREADS, smem, c->stream>>>(T8, S8, c->d_fd16, c->N, c->M, c->fd_rows, c->r0, c->nloc, c->bits, KP, dbg);
+    GHICP_TC_OPT_IN_SMEM(k_fd_bsc_tc<4>);
+    GHICP_LAUNCH(k_fd_bsc_tc<4>, grid, TC_THREADS, smem, c->stream, T8, S8, c->d_fd16, c->N, c->M, c->fd_rows, c->r0, c->nloc, c->bits, KP, dbg);
   } else {
-    cudaFuncSetAttribute(k_fd_bsc_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_fd_bsc_tc<2><<<grid, TC_THREADS, smem, c->stream>>>(T8, S8, c->d_fd16, c->N, c->M, c->fd_rows, c->r0, c->nloc, c->bits, KP, dbg);
+    GHICP_TC_OPT_IN_SMEM(k_fd_bsc_tc<2>);
+    GHICP_LAUNCH(k_fd_bsc_tc<2>, grid, TC_THREADS, smem, c->stream, T8, S8, c->d_fd16, c->N, c->M, c->fd_rows, c->r0, c->nloc, c->bits, KP, dbg);
   }
   c->launches++;
   e = cudaGetLastError();

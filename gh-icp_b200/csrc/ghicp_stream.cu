@@ -46,32 +46,12 @@ constexpr int ST_DYN_SMEM = ST_WARPS * ST_RING_BYTES;
 #if defined(GHICP_EMU_HOST)
 __device__ __forceinline__ void fence_proxy_async() {}     // one OS thread: program order is memory order
 __device__ __forceinline__ void fence_mbarrier_init() {}
-// Host emulation (tests/harness): an mbarrier is modelled inside its own 64-bit word — bit 63 the phase, bits 48-62 the
-// arrival count it was initialised with, bits 32-47 the arrivals still pending, bits 0-31 the transaction bytes still
-// pending (signed) — and a bulk copy is a memcpy that completes its bytes at once.  A waiting fiber yields.
-struct EmuBar { int tx; unsigned short pending; unsigned short init_phase; };   // init_phase: bit 15 = phase, low 15 = count
-__device__ __forceinline__ void emu_bar_check(EmuBar *b) {
-  if (b->pending == 0 && b->tx == 0) { b->init_phase ^= 0x8000u; b->pending = (unsigned short)(b->init_phase & 0x7fffu); }
-}
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
-  EmuBar *b = reinterpret_cast<EmuBar *>(bar);
-  b->tx = 0; b->pending = (unsigned short)count; b->init_phase = (unsigned short)count;
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-  EmuBar *b = reinterpret_cast<EmuBar *>(bar);
-  b->tx += (int)bytes; b->pending -= 1;
-  emu_bar_check(b);
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-  EmuBar *b = reinterpret_cast<EmuBar *>(bar);
-  while ((unsigned)(b->init_phase >> 15) == parity) emu::yield();
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
-  memcpy(dst, src, bytes);
-  EmuBar *b = reinterpret_cast<EmuBar *>(bar);
-  b->tx -= (int)bytes;
-  emu_bar_check(b);
-}
+// Host emulation (tests/harness/cuda_emu/emu_mbarrier.h): an mbarrier is modelled inside its own 64-bit word, a bulk copy
+// is a memcpy that completes its bytes at once, a waiting fiber yields.
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) { emu::bar_init(bar, count); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) { emu::bar_arrive_expect_tx(bar, bytes); }
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) { emu::bar_wait(bar, parity); }
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) { emu::bulk_copy(dst, src, bytes, bar); }
 #else
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbarrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }

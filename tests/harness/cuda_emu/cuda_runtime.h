@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include "emu.h"
+#include "emu_mbarrier.h"
 
 #define __host__
 #define __device__

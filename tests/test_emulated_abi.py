@@ -1,7 +1,7 @@
 """The WHOLE C ABI on the CPU: tests/harness/emu_library.cpp builds ghicp_capi.cu (context, iteration orchestration, every
 extern "C" entry point) on top of the product's own kernels through the host emulation shim — CUDA threads as fibers, device
-memory = the heap — the TMA streaming kernel of ghicp_stream.cu included (its PTX wrappers have host stand-ins); only the
-tcgen05 FD build is reported "not supported", which selects the POPC kernel exactly as GHICP_FD_POPC does on a GPU.
+memory = the heap — the TMA streaming kernel of ghicp_stream.cu and the tcgen05 FD build of ghicp_fdtc.cu included (their
+PTX statements have host stand-ins: mbarriers, bulk copies, packed arithmetic, tensor memory as an int32 array).
 
 This module loads that library IN PLACE OF libghicp_b200.so for the duration of a test (the product never does: it has no CPU
 path) and runs, on a machine without a GPU:
@@ -10,7 +10,7 @@ path) and runs, on a machine without a GPU:
   * the `-m gpu` test FUNCTIONS of tests/test_zz*.py themselves — written after the round's GPU budget was spent — with the
     emulated library as their `g`.  (This is how a missing `build_fd()` and a too small iteration cap in two of them were
     found before any GPU run.)
-What it cannot show: anything about ghicp_fdtc.cu, code generation, memory ordering, asynchrony, performance."""
+What it cannot show: code generation, memory ordering, asynchrony (copies and MMAs complete at once), performance."""
 import ctypes as C
 import os
 import subprocess
