@@ -47,7 +47,28 @@ inline void *dyn_smem() { return g_dyn.data(); }
 constexpr size_t STACK = 256 * 1024;
 
 inline Fiber *cur() { return &g_fibers[g_cur_index]; }
-inline void yield() { swapcontext(&cur()->ctx, &g_sched); }
+// Stress modes (environment, read once):
+//   GHICP_EMU_SCHED=<seed>     every scheduling sweep visits the fibers in a fresh pseudo-random order instead of 0, 1, 2 ...
+//                              (a correct kernel only depends on its rendezvous points, not on who runs first)
+//   GHICP_EMU_TMA_DELAY=<n>    a bulk copy lands 1..n scheduling ticks AFTER it was issued (emu_mbarrier.h): code that reads
+//                              the destination without waiting on the mbarrier sees stale bytes
+inline unsigned long long g_tick = 0;                 // advances on every yield
+inline void (*g_yield_hook)() = nullptr;              // deferred work that becomes due as ticks pass (emu_mbarrier.h)
+inline unsigned long long g_rng = 0;
+inline int g_sched_random = -1, g_tma_delay = -1;
+inline void read_modes() {
+  if (g_sched_random >= 0) return;
+  const char *s = getenv("GHICP_EMU_SCHED"), *d = getenv("GHICP_EMU_TMA_DELAY");
+  g_sched_random = s ? 1 : 0;
+  g_rng = s ? (unsigned long long)atoll(s) * 0x9E3779B97F4A7C15ull + 0x1234567ull : 0;
+  g_tma_delay = d ? atoi(d) : 0;
+}
+inline unsigned rnd() { g_rng ^= g_rng << 13; g_rng ^= g_rng >> 7; g_rng ^= g_rng << 17; return (unsigned)(g_rng >> 11); }
+inline void yield() {
+  ++g_tick;
+  if (g_yield_hook) g_yield_hook();
+  swapcontext(&cur()->ctx, &g_sched);
+}
 
 inline void syncthreads() {
   BlockState &b = g_blocks[cur()->block];
@@ -120,14 +141,20 @@ inline void fiber_entry() {
 // run the fibers [0, nfib): round-robin until all have returned
 inline void run_fibers(int nfib) {
   long spins = 0;
+  read_modes();
+  std::vector<int> order;
+  if (g_sched_random) { order.resize(nfib); for (int t = 0; t < nfib; ++t) order[t] = t; }
   while (g_live > 0) {
-    for (int t = 0; t < nfib; ++t) {
+    if (g_sched_random) for (int t = nfib - 1; t > 0; --t) std::swap(order[t], order[rnd() % (unsigned)(t + 1)]);
+    for (int q = 0; q < nfib; ++q) {
+      const int t = g_sched_random ? order[q] : q;
       if (g_fibers[t].done) continue;
       g_cur_index = t;
       swapcontext(&g_sched, &g_fibers[t].ctx);
     }
     if (++spins > 100000000L) { fprintf(stderr, "emu: deadlock (divergent barrier / shuffle?)\n"); abort(); }
   }
+  if (g_yield_hook) { g_tick += 1ull << 20; g_yield_hook(); }   // whatever is still in flight lands before the launch "returns"
 }
 inline void prepare_fiber(int t, dim3 tidx, dim3 bidx, int block) {
   Fiber &f = g_fibers[t];

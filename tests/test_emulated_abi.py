@@ -269,3 +269,21 @@ def test_cpp_dropin_demo_on_the_emulated_library(ge, orc, tmp_path, monkeypatch,
     import test_gpu_dropin as z
     monkeypatch.setenv("LD_LIBRARY_PATH", cli_env["LD_LIBRARY_PATH"])
     z.test_cpp_dropin_matches_oracle(ge, orc, tmp_path, "bsc-nn")
+
+
+# ---- stress modes of the emulator: scheduling order and asynchronous copies -------------------------------------------------
+@pytest.mark.parametrize("env,expect_ok", [({}, True),
+                                           ({"GHICP_EMU_SCHED": "1"}, True),
+                                           ({"GHICP_EMU_TMA_DELAY": "7"}, True),
+                                           ({"GHICP_EMU_SCHED": "5", "GHICP_EMU_TMA_DELAY": "40"}, True),
+                                           ({"GHICP_EMU_NEGCTL_NOWAIT": "1", "GHICP_EMU_TMA_DELAY": "7"}, False)])
+def test_tma_and_tcgen05_kernels_under_random_scheduling_and_delayed_copies(emu_library_path, env, expect_ok):
+    """The streaming kernel and the tcgen05 FD build must not depend on which fiber runs first (GHICP_EMU_SCHED: a fresh
+    random order every scheduling sweep) nor on a bulk copy having landed before its mbarrier says so (GHICP_EMU_TMA_DELAY: the
+    destination is poisoned and the bytes land 1..n ticks later).  Negative control: with every mbarrier wait turned into a no-op
+    the same check must FAIL — the modes can see a forgotten wait."""
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "harness", "emu_stress_check.py"), emu_library_path],
+                       env=dict(os.environ, **env), capture_output=True, text=True)
+    assert r.returncode in (0, 1), r.stderr[-2000:]
+    assert (r.returncode == 0) == expect_ok, (env, r.stdout[-500:], r.stderr[-1500:])
