@@ -215,6 +215,7 @@ __device__ __forceinline__ int find_cell(const pu64 *__restrict__ ucell, int nu,
 struct GridArgs {
   const float *xyz; const int *ids;      // point of position k = xyz[ids ? ids[k] : k]
   const int *order;                      // positions sorted by cell (ascending position inside a cell)
+  const float4 *sorted;                  // the same points in that order (x y z _): a cell's run is read with coalesced 16-byte loads
   const pu64 *ucell; const int *cstart; int nu;
   float mnx, mny, mnz, inv, r2;
 };
@@ -247,8 +248,8 @@ __global__ void k_pca(const GridArgs g, int n, float *__restrict__ lam, double *
       int s0, s1;
       column_run(g, x, y, cz, s0, s1);
       for (int s = s0; s < s1; ++s) {
-        const int k = g.order[s];
-        const float ex = g.xyz[3 * (size_t)k] - qx, ey = g.xyz[3 * (size_t)k + 1] - qy, ez = g.xyz[3 * (size_t)k + 2] - qz;
+        const float4 pt = g.sorted[s];
+        const float ex = pt.x - qx, ey = pt.y - qy, ez = pt.z - qz;
         const float d2 = ex * ex + ey * ey + ez * ez;
         if (!(d2 < g.r2)) continue;
         ++cnt;
@@ -313,8 +314,8 @@ __global__ void k_nms_round(const GridArgs g, int m, int *__restrict__ state, in
       for (int s = s0; s < s1; ++s) {
         const int k = g.order[s];
         if (k >= r) continue;                          // only better-ranked candidates can suppress r
-        const float *p = g.xyz + 3 * (size_t)g.ids[k];
-        const float ex = p[0] - q[0], ey = p[1] - q[1], ez = p[2] - q[2];
+        const float4 p = g.sorted[s];
+        const float ex = p.x - q[0], ey = p.y - q[1], ez = p.z - q[2];
         if (!(ex * ex + ey * ey + ez * ez < g.r2)) continue;
         const int sk = state[k];
         if (sk == 1) { suppressed = true; break; }
@@ -336,15 +337,25 @@ __global__ void k_kp_emit(const int *__restrict__ flags, const int *__restrict__
   if (r < m && flags[r]) out[pos[r]] = cand[r];
 }
 
+// points in cell order, padded to 16 bytes
+__global__ void k_gather_sorted(const float *__restrict__ xyz, const int *__restrict__ ids, const int *__restrict__ order, int n,
+                                float4 *__restrict__ sorted) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const int k = ids ? ids[order[s]] : order[s];
+  sorted[s] = make_float4(xyz[3 * (size_t)k], xyz[3 * (size_t)k + 1], xyz[3 * (size_t)k + 2], 0.f);
+}
+
 #define PCK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { err = e__; goto done; } } while (0)
 inline int blocks(int n) { return (n + PT - 1) / PT; }
 
 // uniform grid over the points ids[k] (k < n): returns device arrays (order, ucell, cstart) the caller frees
 cudaError_t build_grid(cudaStream_t st, const float *d_xyz, const int *d_ids, int n, float cell, GridArgs *g, int **o_order,
-                       pu64 **o_ucell, int **o_cstart) {
+                       pu64 **o_ucell, int **o_cstart, float4 **o_sorted) {
   cudaError_t err = cudaSuccess;
   unsigned *d_box = nullptr; unsigned h_box[6];
   pu64 *d_keys = nullptr, *d_ucell = nullptr; int *d_order = nullptr, *d_flags = nullptr, *d_pos = nullptr, *d_cstart = nullptr;
+  float4 *d_sorted = nullptr;
   int nu = 0;
   PCK(pmalloc(&d_box, 6));
   { const unsigned init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u}; PCK(pcopy(d_box, init, sizeof(init), P_H2D, st)); }
@@ -360,11 +371,13 @@ cudaError_t build_grid(cudaStream_t st, const float *d_xyz, const int *d_ids, in
   PCK(pcopy(&nu, d_pos + n, sizeof(int), P_D2H, st)); PCK(psync(st));
   PCK(pmalloc(&d_ucell, (size_t)nu)); PCK(pmalloc(&d_cstart, (size_t)nu + 1));
   GHICP_LAUNCH(k_cell_table, blocks(n + 1), PT, 0, st, d_keys, d_flags, d_pos, n, d_ucell, d_cstart);
-  g->xyz = d_xyz; g->ids = d_ids; g->order = d_order; g->ucell = d_ucell; g->cstart = d_cstart; g->nu = nu;
-  *o_order = d_order; *o_ucell = d_ucell; *o_cstart = d_cstart;
-  d_order = nullptr; d_ucell = nullptr; d_cstart = nullptr;
+  PCK(pmalloc(&d_sorted, (size_t)n));
+  GHICP_LAUNCH(k_gather_sorted, blocks(n), PT, 0, st, d_xyz, d_ids, d_order, n, d_sorted);
+  g->xyz = d_xyz; g->ids = d_ids; g->order = d_order; g->sorted = d_sorted; g->ucell = d_ucell; g->cstart = d_cstart; g->nu = nu;
+  *o_order = d_order; *o_ucell = d_ucell; *o_cstart = d_cstart; *o_sorted = d_sorted;
+  d_order = nullptr; d_ucell = nullptr; d_cstart = nullptr; d_sorted = nullptr;
 done:
-  pfree(d_box); pfree(d_keys); pfree(d_flags); pfree(d_pos); pfree(d_order); pfree(d_ucell); pfree(d_cstart);
+  pfree(d_box); pfree(d_keys); pfree(d_flags); pfree(d_pos); pfree(d_order); pfree(d_ucell); pfree(d_cstart); pfree(d_sorted);
   return err;
 }
 
@@ -412,13 +425,14 @@ cudaError_t prep_detect_keypoints(cudaStream_t st, const float *d_xyz, int n, fl
   cudaError_t err = cudaSuccess;
   GridArgs g{}, g2{};
   int *order = nullptr, *cstart = nullptr, *order2 = nullptr, *cstart2 = nullptr; pu64 *ucell = nullptr, *ucell2 = nullptr;
+  float4 *sorted = nullptr, *sorted2 = nullptr;
   int *d_flags = nullptr, *d_pos = nullptr, *d_cand = nullptr, *d_state = nullptr, *d_und = nullptr; pu64 *d_keys = nullptr;
   int m = 0, rounds = 0;
   *n_kp = 0;
   if (nms_rounds) *nms_rounds = 0;
   if (n <= 0) return cudaSuccess;
   {
-    PCK(build_grid(st, d_xyz, nullptr, n, radius, &g, &order, &ucell, &cstart));
+    PCK(build_grid(st, d_xyz, nullptr, n, radius, &g, &order, &ucell, &cstart, &sorted));
     GHICP_LAUNCH(k_pca, blocks(n), PT, 0, st, g, n, d_lam, d_curv, d_cnt);
     PCK(pmalloc(&d_flags, (size_t)n + 1)); PCK(pmalloc(&d_pos, (size_t)n + 1));
     GHICP_LAUNCH(k_prune, blocks(n + 1), PT, 0, st, d_lam, d_cnt, n, ratio_max, min_pts, d_flags);
@@ -428,7 +442,7 @@ cudaError_t prep_detect_keypoints(cudaStream_t st, const float *d_xyz, int n, fl
     PCK(pmalloc(&d_cand, (size_t)m)); PCK(pmalloc(&d_keys, (size_t)m));
     GHICP_LAUNCH(k_cand_emit, blocks(n), PT, 0, st, d_flags, d_pos, d_curv, n, d_keys, d_cand);
     PCK(sort_pairs(d_keys, d_cand, m, st));   // rank order: descending curvature, ties by ascending index (stable)
-    PCK(build_grid(st, d_xyz, d_cand, m, nms_radius, &g2, &order2, &ucell2, &cstart2));
+    PCK(build_grid(st, d_xyz, d_cand, m, nms_radius, &g2, &order2, &ucell2, &cstart2, &sorted2));
     PCK(pmalloc(&d_state, (size_t)m)); PCK(pmalloc(&d_und, 1));
     PCK(pzero(d_state, sizeof(int) * (size_t)m, st));
     for (;;) {
@@ -450,7 +464,7 @@ cudaError_t prep_detect_keypoints(cudaStream_t st, const float *d_xyz, int n, fl
     if (nms_rounds) *nms_rounds = rounds;
   }
 done:
-  pfree(order); pfree(ucell); pfree(cstart); pfree(order2); pfree(ucell2); pfree(cstart2);
+  pfree(order); pfree(ucell); pfree(cstart); pfree(order2); pfree(ucell2); pfree(cstart2); pfree(sorted); pfree(sorted2);
   pfree(d_flags); pfree(d_pos); pfree(d_cand); pfree(d_state); pfree(d_und); pfree(d_keys);
   return err;
 }
@@ -484,7 +498,6 @@ constexpr int BSC_MAX_CELLS = 3 * BSC_MAX_SIDE * BSC_MAX_SIDE;
 
 struct BscArgs {
   GridArgs g;
-  const float4 *sorted;               // the points in cell order (position s of g.order), x y z _ : coalesced 16-byte reads
   const int *kp; int nkp;
   float R; int side; const int *pairs; int V;
   unsigned char *bits; int nbytes; float *lrf; int *status;
@@ -554,14 +567,6 @@ __device__ __forceinline__ int bsc_rearranged(int tr, int k, int side) {
   return tr == 1 ? side * side - 1 - k : (tr == 2 ? (side - 1 - i) * side + j : i * side + side - 1 - j);
 }
 
-// points in cell order, padded to 16 bytes
-__global__ void k_bsc_gather(const float *__restrict__ xyz, const int *__restrict__ order, int n, float4 *__restrict__ sorted) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n) return;
-  const int k = order[s];
-  sorted[s] = make_float4(xyz[3 * (size_t)k], xyz[3 * (size_t)k + 1], xyz[3 * (size_t)k + 2], 0.f);
-}
-
 __global__ void __launch_bounds__(BSC_T) k_bsc(const BscArgs a) {
   __shared__ int s_lo[27], s_pre[28];  // start of each of the 27 cells' runs in the sorted order, prefix sums of their lengths
   __shared__ unsigned s_num_lo[BSC_MAX_CELLS], s_num_hi[BSC_MAX_CELLS];   // 64-bit fixed-point sums as two 32-bit words:
@@ -598,7 +603,7 @@ __global__ void __launch_bounds__(BSC_T) k_bsc(const BscArgs a) {
     double v[5] = {0, 0, 0, 0, 0};
     for (int idx = tid, c = 0; idx < total; idx += BSC_T) {
       while (idx >= s_pre[c + 1]) ++c;
-      const float4 pt = a.sorted[s_lo[c] + (idx - s_pre[c])];
+      const float4 pt = g.sorted[s_lo[c] + (idx - s_pre[c])];
       const float x = pt.x, y = pt.y, z = pt.z;
       const float ex = x - qx, ey = y - qy, ez = z - qz;
       const float d2 = ex * ex + ey * ey + ez * ez;
@@ -628,7 +633,7 @@ __global__ void __launch_bounds__(BSC_T) k_bsc(const BscArgs a) {
     const double cx = s_c[0], cy = s_c[1], cz = s_c[2];
     for (int idx = tid, c = 0; idx < total; idx += BSC_T) {
       while (idx >= s_pre[c + 1]) ++c;
-      const float4 pt = a.sorted[s_lo[c] + (idx - s_pre[c])];
+      const float4 pt = g.sorted[s_lo[c] + (idx - s_pre[c])];
       const float x = pt.x, y = pt.y, z = pt.z;
       const float ex = x - qx, ey = y - qy, ez = z - qz;
       const float d2 = ex * ex + ey * ey + ez * ez;
@@ -702,7 +707,7 @@ __global__ void __launch_bounds__(BSC_T) k_bsc(const BscArgs a) {
                 m20 = s_M[8], m21 = s_M[9], m22 = s_M[10], m23 = s_M[11];
     for (int idx = tid, c = 0; idx < total; idx += BSC_T) {
         while (idx >= s_pre[c + 1]) ++c;
-        const float4 pt = a.sorted[s_lo[c] + (idx - s_pre[c])];
+        const float4 pt = g.sorted[s_lo[c] + (idx - s_pre[c])];
         const float ex = pt.x - qx, ey = pt.y - qy, ez = pt.z - qz;
         const float d2 = ex * ex + ey * ey + ez * ez;
         if (!(d2 < g.r2)) continue;
@@ -817,11 +822,9 @@ cudaError_t prep_bsc_extract(cudaStream_t st, const float *d_xyz, int n, const i
   if (side < 1 || side > BSC_MAX_SIDE) return cudaErrorInvalidValue;
   {
     const float search = (float)(sqrt(3.0) * (double)R);            // :643; squared in float32 like the radius of S4
-    PCK(build_grid(st, d_xyz, nullptr, n, search, &g, &order, &ucell, &cstart));
-    PCK(pmalloc(&sorted, (size_t)n));
-    GHICP_LAUNCH(k_bsc_gather, blocks(n), PT, 0, st, d_xyz, order, n, sorted);
+    PCK(build_grid(st, d_xyz, nullptr, n, search, &g, &order, &ucell, &cstart, &sorted));
     BscArgs a{};
-    a.g = g; a.sorted = sorted; a.kp = d_kp; a.nkp = nkp; a.R = R; a.side = side; a.pairs = d_pairs;
+    a.g = g; a.kp = d_kp; a.nkp = nkp; a.R = R; a.side = side; a.pairs = d_pairs;
     a.V = dof_type > 4 ? 4 : (dof_type > 0 ? 2 : 1);
     a.bits = d_bits; a.nbytes = (9 * side * side + 7) / 8; a.lrf = d_lrf; a.status = d_status;
     GHICP_LAUNCH(k_bsc, nkp, BSC_T, 0, st, a);
