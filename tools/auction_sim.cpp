@@ -356,6 +356,47 @@ int main(int argc, char **argv) {
       double D = A.free_price_sum();
       if (D > 0.5 * KM_eps * N) A.reverse(0.5 * KM_eps);
       report(mode.c_str(), A, A.total_gain(), D, tnow() - t0);
+    } else if (mode.rfind("warm", 0) == 0) {
+      // warm start across ICP iterations: solve THIS iteration's instance with the shipped schedule, then the NEXT iteration's
+      // instance (same descriptors and geometry, new metric weights / penalty) starting from those prices scaled by the ratio
+      // of the feature weights, assignment empty.  warm=<eps0>: first epsilon of the second solve (0 = final epsilon only).
+      Auction A0 = mk();
+      { auto eps = schedule(I.penalty / 4.0, 5.0, 0.5 * KM_eps);
+        for (size_t ph = 0; ph < eps.size(); ++ph) {
+          std::fill(A0.owner.begin(), A0.owner.end(), -1); std::fill(A0.assign.begin(), A0.assign.end(), -1); std::fill(A0.profit.begin(), A0.profit.end(), 0.0);
+          A0.forward(persons_with_edges(A0), eps[ph]);
+        }
+        if (A0.free_price_sum() > 0.5 * KM_eps * N) A0.reverse(0.5 * KM_eps); }
+      fprintf(stderr, "  iteration %d solved: gain %.1f, %lld + %lld rounds\n", it, A0.total_gain(), A0.fwd.rounds, A0.rev.rounds);
+      Inst J = make_instance(N, N, it + 1, 2, 0.03);
+      const double w0 = it == 0 ? 1.0 : std::exp(-1.0 * it / 6.0), w1 = std::exp(-1.0 * (it + 1) / 6.0);
+      Auction B; B.P = J.N; B.O = J.M; B.rp = J.rp.data(); B.col = J.col.data(); B.g = J.g.data(); B.cp = J.cp.data(); B.row = J.row.data(); B.cg = J.cg.data();
+      const double avg = (double)J.rp[N] / N;
+      B.small_fwd = B.small_rev = std::max(16, std::min(2048, (int)(65536.0 / std::max(1.0, avg)))); B.init();
+      for (int j = 0; j < J.M; ++j) B.price[j] = A0.price[j] * (w1 / w0);
+      double e0 = mode.size() > 5 ? atof(mode.c_str() + 5) : 0.0;
+      auto eps = e0 > 0 ? schedule(e0, 5.0, 0.5 * KM_eps) : std::vector<double>(1, 0.5 * KM_eps);
+      double t1 = tnow();
+      for (size_t ph = 0; ph < eps.size(); ++ph) {
+        std::fill(B.owner.begin(), B.owner.end(), -1); std::fill(B.assign.begin(), B.assign.end(), -1); std::fill(B.profit.begin(), B.profit.end(), 0.0);
+        ll r0 = B.fwd.rounds;
+        B.forward(persons_with_edges(B), eps[ph]);
+        fprintf(stderr, "  warm phase %zu eps %.4f: %lld rounds, D %.1f gain %.1f\n", ph, eps[ph], B.fwd.rounds - r0, B.free_price_sum(), B.total_gain());
+      }
+      double D = B.free_price_sum();
+      if (D > 0.5 * KM_eps * N) B.reverse(0.5 * KM_eps);
+      report(mode.c_str(), B, B.total_gain(), D, tnow() - t1);
+      // the same instance cold, for comparison
+      Auction Cc; Cc.P = J.N; Cc.O = J.M; Cc.rp = J.rp.data(); Cc.col = J.col.data(); Cc.g = J.g.data(); Cc.cp = J.cp.data(); Cc.row = J.row.data(); Cc.cg = J.cg.data();
+      Cc.small_fwd = Cc.small_rev = B.small_fwd; Cc.init();
+      { auto ce = schedule(J.penalty / 4.0, 5.0, 0.5 * KM_eps);
+        for (size_t ph = 0; ph < ce.size(); ++ph) {
+          std::fill(Cc.owner.begin(), Cc.owner.end(), -1); std::fill(Cc.assign.begin(), Cc.assign.end(), -1); std::fill(Cc.profit.begin(), Cc.profit.end(), 0.0);
+          Cc.forward(persons_with_edges(Cc), ce[ph]);
+        }
+        double Dc = Cc.free_price_sum();
+        if (Dc > 0.5 * KM_eps * N) Cc.reverse(0.5 * KM_eps);
+        report("  (next iteration, cold)", Cc, Cc.total_gain(), Dc, 0.0); }
     } else if (mode.rfind("dom", 0) == 0) {
       // dominance pre-matching: a pair (i, j) with g_ij >= (best other gain of row i, or 0) + (best other gain of column j, or 0)
       // belongs to some optimal matching (exchange argument: dropping whatever i and j hold instead loses at most those two
