@@ -8,7 +8,6 @@
 // command-line driver and the GPU test functions themselves on a machine without a GPU.  The product never loads it;
 // libghicp_b200.so has no CPU path.
 #define GHICP_EMU_HOST 1
-#define GHICP_EMU_LIBRARY 1
 #include "../../gh-icp_b200/csrc/ghicp_kernels.cu"
 #include "../../gh-icp_b200/csrc/ghicp_auction.cu"
 #include "../../gh-icp_b200/csrc/ghicp_fpfh.cu"
