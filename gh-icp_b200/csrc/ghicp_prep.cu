@@ -202,16 +202,6 @@ __global__ void k_cell_table(const pu64 *__restrict__ keys, const int *__restric
   if (i < n && flags[i]) { ucell[pos[i]] = keys[i]; cstart[pos[i]] = i; }
   if (i == n) cstart[pos[n]] = n;
 }
-__device__ __forceinline__ int find_cell(const pu64 *__restrict__ ucell, int nu, pu64 key) {
-  int lo = 0, hi = nu - 1;
-  while (lo <= hi) {
-    const int mid = (lo + hi) >> 1;
-    const pu64 v = ucell[mid];
-    if (v == key) return mid;
-    if (v < key) lo = mid + 1; else hi = mid - 1;
-  }
-  return -1;
-}
 struct GridArgs {
   const float *xyz; const int *ids;      // point of position k = xyz[ids ? ids[k] : k]
   const int *order;                      // positions sorted by cell (ascending position inside a cell)
@@ -475,7 +465,8 @@ done:
 // :603-676 — per keypoint the weighted-PCA local frame (:940-1035, :123-160), the change of frame (:163-196, :1085-1138),
 // the three projected Gaussian-weighted side x side grids (:197-373), the 9 side^2-bit descriptor (:464-565) and its
 // re-arranged variants (:678-837).  The reference walks three KD-trees per keypoint on one thread; here one CTA per
-// keypoint walks the 27 cells of a uniform grid (edge = search radius sqrt(3) R) three times:
+// keypoint walks the 3 x 3 columns of a uniform grid (edge = search radius sqrt(3) R; a column's three cells are one contiguous
+// run of the cell-sorted points) three times:
 //   pass A  neighbour count, centroid and the weight sum            (double sums)
 //   pass B  weighted covariance about the centroid                  (double sums, rounded once to float32)
 //   thread 0: eigenvectors (cyclic Jacobi in double, sign "largest component positive"), the frame, the float32
@@ -493,6 +484,7 @@ done:
 namespace {
 
 constexpr int BSC_T = 128;          // threads per keypoint
+constexpr int BSC_RUNS = 9;         // 3 x 3 grid columns around the keypoint, each one contiguous run (column_run)
 constexpr int BSC_MAX_SIDE = 9;     // grids up to 9 x 9 (the reference uses 7)
 constexpr int BSC_MAX_CELLS = 3 * BSC_MAX_SIDE * BSC_MAX_SIDE;
 
@@ -568,7 +560,7 @@ __device__ __forceinline__ int bsc_rearranged(int tr, int k, int side) {
 }
 
 __global__ void __launch_bounds__(BSC_T) k_bsc(const BscArgs a) {
-  __shared__ int s_lo[27], s_pre[28];  // start of each of the 27 cells' runs in the sorted order, prefix sums of their lengths
+  __shared__ int s_lo[BSC_RUNS], s_pre[BSC_RUNS + 1];  // start of each column run in the sorted order, prefix sums of their lengths
   __shared__ unsigned s_num_lo[BSC_MAX_CELLS], s_num_hi[BSC_MAX_CELLS];   // 64-bit fixed-point sums as two 32-bit words:
   __shared__ unsigned s_dep_lo[BSC_MAX_CELLS], s_dep_hi[BSC_MAX_CELLS];   // native 32-bit shared atomics + explicit carry
   __shared__ float s_depth[BSC_MAX_CELLS], s_npw[BSC_MAX_CELLS];
@@ -582,21 +574,17 @@ __global__ void __launch_bounds__(BSC_T) k_bsc(const BscArgs a) {
   const int p = a.kp[q];
   const int side = a.side, S2 = side * side, cells = 3 * S2, nbits = 9 * S2;
   const float qx = g.xyz[3 * (size_t)p], qy = g.xyz[3 * (size_t)p + 1], qz = g.xyz[3 * (size_t)p + 2];
-  if (tid < 27) {
-    const int cx = cell_coord(qx, g.mnx, g.inv) + tid / 9 - 1, cy = cell_coord(qy, g.mny, g.inv) + (tid / 3) % 3 - 1,
-              cz = cell_coord(qz, g.mnz, g.inv) + tid % 3 - 1;
+  if (tid < BSC_RUNS) {   // one contiguous run of the sorted points per grid column (x, y): its cells z - 1 .. z + 1
+    const int cx = cell_coord(qx, g.mnx, g.inv) + tid / 3 - 1, cy = cell_coord(qy, g.mny, g.inv) + tid % 3 - 1;
     int lo = 0, hi = 0;
-    if (cx >= 0 && cy >= 0 && cz >= 0) {
-      const int u = find_cell(g.ucell, g.nu, cell_key(cx, cy, cz));
-      if (u >= 0) { lo = g.cstart[u]; hi = g.cstart[u + 1]; }
-    }
+    if (cx >= 0 && cy >= 0) column_run(g, cx, cy, cell_coord(qz, g.mnz, g.inv), lo, hi);
     s_lo[tid] = lo; s_pre[tid + 1] = hi - lo;
   }
   for (int c = tid; c < cells; c += BSC_T) { s_num_lo[c] = 0u; s_num_hi[c] = 0u; s_dep_lo[c] = 0u; s_dep_hi[c] = 0u; }
   __syncthreads();
-  if (tid == 0) { s_pre[0] = 0; for (int c = 0; c < 27; ++c) s_pre[c + 1] += s_pre[c]; }
+  if (tid == 0) { s_pre[0] = 0; for (int c = 0; c < BSC_RUNS; ++c) s_pre[c + 1] += s_pre[c]; }
   __syncthreads();
-  const int total = s_pre[27];   // candidates of this keypoint; every pass walks them flat, 128 at a time
+  const int total = s_pre[BSC_RUNS];   // candidates of this keypoint; every pass walks them flat, 128 at a time
   const double radius = sqrt(2.0) * (double)a.R;   // :956
   // ---- pass A: count, centroid sums, weight sum (:956-966) ----
   {
