@@ -36,7 +36,7 @@ constexpr int PT = 256;
 
 // ---- plumbing: device memory, sort, scan (CUB under nvcc; the C++ library under the emulation shim) -------------------
 #if defined(GHICP_EMU_HOST)
-template <typename T> cudaError_t pmalloc(T **p, size_t n) { *p = (T *)malloc((n ? n : 1) * sizeof(T)); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+template <typename T> cudaError_t pmalloc(T **p, size_t n) { *p = (T *)emu_poisoned((n ? n : 1) * sizeof(T)); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 template <typename T> void pfree(T *p) { free(p); }
 inline cudaError_t pcopy(void *dst, const void *src, size_t bytes, int, cudaStream_t) { memcpy(dst, src, bytes); return cudaSuccess; }
 inline cudaError_t pzero(void *p, size_t bytes, cudaStream_t) { memset(p, 0, bytes); return cudaSuccess; }

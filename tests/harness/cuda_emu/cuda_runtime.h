@@ -35,7 +35,10 @@ inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr, int) { *v = 2; return cudaSuccess; }   // "2 SMs": small cooperative grids
 template <typename F> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, F, int, size_t) { *n = 1; return cudaSuccess; }
 template <typename T> inline void __stcg(T *p, T v) { *p = v; }
-template <typename T> inline cudaError_t cudaMallocAsync(T **p, size_t bytes, cudaStream_t) { *p = (T *)malloc(bytes ? bytes : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+// fresh "device" memory is POISONED (0xCD bytes: huge negative ints, -6.2e66 doubles): a kernel that reads what nobody wrote
+// produces garbage here instead of the zeros a fresh page usually holds
+inline void *emu_poisoned(size_t bytes) { void *q = malloc(bytes ? bytes : 1); if (q) memset(q, 0xCD, bytes ? bytes : 1); return q; }
+template <typename T> inline cudaError_t cudaMallocAsync(T **p, size_t bytes, cudaStream_t) { *p = (T *)emu_poisoned(bytes); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 inline cudaError_t cudaFreeAsync(void *p, cudaStream_t) { free(p); return cudaSuccess; }
 inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaErrorNotSupported ? "operation not supported (emulation)" : "emulated"; }
 // ---- the host-side runtime calls of ghicp_capi.cu (tests/harness/emu_library.cpp): device memory = the heap, one "device",
@@ -43,9 +46,9 @@ inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaErrorNotS
 enum { cudaStreamNonBlocking = 1 };
 inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvalidValue; }
-inline cudaError_t cudaMalloc(void **p, size_t bytes) { *p = malloc(bytes ? bytes : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+inline cudaError_t cudaMalloc(void **p, size_t bytes) { *p = emu_poisoned(bytes); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
-template <typename T> inline cudaError_t cudaMallocHost(T **p, size_t bytes) { *p = (T *)malloc(bytes ? bytes : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+template <typename T> inline cudaError_t cudaMallocHost(T **p, size_t bytes) { *p = (T *)emu_poisoned(bytes); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void *d, const void *s, size_t bytes, cudaMemcpyKind) { memmove(d, s, bytes); return cudaSuccess; }
 inline cudaError_t cudaMemset(void *p, int v, size_t bytes) { memset(p, v, bytes); return cudaSuccess; }
