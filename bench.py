@@ -127,24 +127,33 @@ def make_scene(g, wl, n_override=None, seed=2):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_stream launch, from the committed `ncu --set full` captures
 # (profiles/r01_summary.md); algorithmic bytes are 5.002e9
-NCU_TRAFFIC = {"config2": 5.0386e9, "config2-nn": 5.311e9}
+NCU_TRAFFIC = {"config2": {"bytes": 5.0386e9, "source": "profiles/r01_summary.md (ncu --set full capture of k_stream KM, round 1)"},
+               "config2-nn": {"bytes": 5.311e9, "source": "profiles/r01_summary.md (ncu --set full capture of k_stream NN, round 1)"}}
 
 FT = {"none": 3, "bsc": 0, "fpfh": 2}
 CT = {"nn": 0, "nnr": 1, "km": 2}
 
 
 # --------------------------------------------------------------------------------------------------
-# CPU baseline: the oracle (restated reference loop) + the reference's own km.cpp when compiled.
+# CPU arm: the REFERENCE's own loop (oracle/_ref/libghreg_ref.so = src/ghicp_reg.cpp + km.cpp + stereo_binary_feature.cpp
+# compiled verbatim, one thread like the reference) or, where that build is absent, the oracle port.  Iteration-matched:
+# the CPU times the SAME iteration indices the GPU arm times (warm-up iterations 0..W-1 are run, not timed; steps are
+# iterations W..W+K-1), on a bounded n_s x n_s sample of the workload generated by the same make_scene().  The workload-size
+# figure is an extrapolation t(N) = t(n_s) * (N / n_s)^p with p FITTED on >= 2 sample sizes (not assumed), and is labelled so.
 # --------------------------------------------------------------------------------------------------
-def _oracle_run(g, wl, ct, threads, n, iters, use_ref):
+def _cpu_loop(g, wl, n, n_iters, kind, threads=1, stop_at_convergence=False):
+    """Per-iteration wall ms of the CPU loop from iteration 0 on an n x n sample; returns (list ms, fd_build_s, converged_at)."""
     import oracle
     import tempfile
     sc = make_scene(g, wl, n_override=n)
     cwd = os.getcwd()
     os.chdir(tempfile.mkdtemp())  # Km::output writes Corres.txt (src/km.cpp:148)
     try:
-        o = oracle.Oracle(FT[wl["ft"]], CT[ct], bbx_magnitude=sc.bbx_magnitude, solve_mode=0,
-                          use_ref_km=use_ref, num_threads=threads)
+        if kind == "reference":
+            o = oracle.Reference(FT[wl["ft"]], CT[wl["ct"]], bbx_magnitude=sc.bbx_magnitude, solve_mode=0)
+        else:
+            o = oracle.Oracle(FT[wl["ft"]], CT[wl["ct"]], bbx_magnitude=sc.bbx_magnitude, solve_mode=0,
+                              use_ref_km=(oracle.ref_km_lib() is not None and wl["ct"] == "km"), num_threads=threads)
         o.set_keypoints(sc.S, sc.T)
         if wl["ft"] == "bsc":
             o.set_bsc(sc.bsc_s, sc.bsc_t, sc.bits)
@@ -153,90 +162,86 @@ def _oracle_run(g, wl, ct, threads, n, iters, use_ref):
         t0 = time.perf_counter()
         o.build_fd()
         t_fd = time.perf_counter() - t0
-        t_cost, t_corr, t_solve = [], [], []
-        for _ in range(iters):
-            st = o.iterate()
-            t_cost.append(st.t_cost_ms); t_corr.append(st.t_corr_ms); t_solve.append(st.t_solve_ms)
-    finally:
-        os.chdir(cwd)
-    return float(np.median(t_cost)), float(np.median(t_corr)), float(np.median(t_solve)), t_fd
-
-
-def _reference_run(g, wl, ct, n, iters):
-    """The REFERENCE's own GHRegistration loop (src/ghicp_reg.cpp + km.cpp + stereo_binary_feature.cpp compiled verbatim into
-    oracle/_ref/libghreg_ref.so; single-threaded like the reference) on an n x n sample: (median ms per iteration, FD build s)."""
-    import oracle
-    import tempfile
-    sc = make_scene(g, wl, n_override=n)
-    cwd = os.getcwd()
-    os.chdir(tempfile.mkdtemp())  # Km::output writes Corres.txt (src/km.cpp:148)
-    try:
-        r = oracle.Reference(FT[wl["ft"]], CT[ct], bbx_magnitude=sc.bbx_magnitude, solve_mode=0)
-        r.set_keypoints(sc.S, sc.T)
-        if wl["ft"] == "bsc":
-            r.set_bsc(sc.bsc_s, sc.bsc_t, sc.bits)
-        elif wl["ft"] == "fpfh":
-            r.set_fpfh(sc.fpfh_s, sc.fpfh_t)
-        t0 = time.perf_counter()
-        r.build_fd()
-        t_fd = time.perf_counter() - t0
-        ts = []
-        for _ in range(iters):
+        ts, conv_at = [], None
+        for it in range(n_iters):
             t0 = time.perf_counter()
-            r.iterate()
+            st = o.iterate()
             ts.append((time.perf_counter() - t0) * 1e3)
+            if st.converged and conv_at is None:
+                conv_at = it + 1
+                if stop_at_convergence:
+                    break
     finally:
         os.chdir(cwd)
-    return float(np.median(ts)), t_fd
+    return ts, t_fd, conv_at
 
 
-def cpu_baseline(g, wl, threads, n_sample, iters=2):
-    """The reference's CPU path on a bounded sample, extrapolated to the workload size (cost / scans ~ N*M, KM ~ n^3, solve ~ n;
-    the reference cannot run 50k x 50k: 24*N*M B of doubles + O(n^3) KM).
-    kind "reference": the reference's OWN compiled loop (oracle/_ref/libghreg_ref.so, one thread — it is single-threaded);
-    kind "port": the oracle restatement (+ OpenMP on the O(N*M) loops when threads > 1) where oracle/_ref is not available."""
+def _fit_power(ns, ts):
+    """Least-squares exponent p and prefactor of t = a * n^p on log-log axes."""
+    ln, lt = np.log(np.asarray(ns, float)), np.log(np.maximum(np.asarray(ts, float), 1e-9))
+    if len(ns) < 2:
+        return None, None
+    p, la = np.polyfit(ln, lt, 1)
+    return float(p), float(math.exp(la))
+
+
+def cpu_arm(g, wl, warmup, steps, sizes, fit_steps=3, threads=1, budget_s=240.0):
+    """Iteration-matched CPU measurement.  `sizes` ascending; the LAST size is the main sample: warm-up + `steps` timed
+    iterations there; the smaller sizes run warm-up + `fit_steps` iterations and only feed the exponent fit."""
     import oracle
     oracle.build()
-    km = wl["ct"] == "km"
+    kind = "reference" if (oracle.ref_ghreg_lib() is not None and threads == 1) else "port"
     N = wl["N"]
-    if oracle.ref_ghreg_lib() is not None:
-        n_cost = min(N, 4000)
-        nn_ct = "nn" if km else wl["ct"]
-        t_iter, t_fd = _reference_run(g, wl, nn_ct, n_cost, iters)
-        parts = [f"reference loop ({nn_ct.upper()}: calED + calCD + scan + solve) {t_iter:.1f} ms / iteration at {n_cost}x{n_cost}"]
-        full_ms = t_iter * (N / n_cost) ** 2
-        if km:
-            n_km = min(n_sample, N)
-            t_km, _ = _reference_run(g, wl, "km", n_km, iters)
-            t_nn_small, _ = _reference_run(g, wl, "nn", n_km, iters)
-            corr = max(t_km - t_nn_small, 0.0)
-            full_ms += corr * (N / n_km) ** 3
-            parts.append(f"findcorrespondenceKM (graph copies + src/km.cpp) {corr:.1f} ms at {n_km}x{n_km}")
-        sample = ("; ".join(parts) + f"; one-time calFD {t_fd:.2f} s at {n_cost}x{n_cost}; median of {iters} iterations; the "
-                  f"reference's own src/ghicp_reg.cpp + km.cpp compiled verbatim (1 thread: it is single-threaded; PCL's SVD "
-                  f"call delegated to the oracle); extrapolated to {N}x{wl['M']} with cost/scan ~ N*M, KM ~ n^3")
-        return dict(value=1000.0 / full_ms, unit="iterations/s", cores=1, kind="reference", sample=sample,
-                    ms_per_step_sample=t_iter, ms_per_step_extrapolated=full_ms)
-    use_ref = oracle.ref_km_lib() is not None and km
-    n_cost = min(N, 6000)
-    cost, scan, solve, t_fd = _oracle_run(g, wl, "nn" if km else wl["ct"], threads, n_cost, iters, False)
-    parts = [f"cost stage (calED+calCD) {cost:.1f} ms at {n_cost}x{n_cost} on {threads} thread(s)"]
-    full_ms = cost * (N / n_cost) ** 2 + solve * (N / n_cost)
-    if km:
-        n_km = min(n_sample, N)
-        _, corr, _, _ = _oracle_run(g, wl, "km", 1, n_km, iters, use_ref)
-        full_ms += corr * (N / n_km) ** 3
-        parts.append(f"KM ({'reference src/km.cpp' if use_ref else 'restated km.cpp'}, 1 thread: it is sequential) "
-                     f"{corr:.1f} ms at {n_km}x{n_km}")
-    else:
-        full_ms += scan * (N / n_cost) ** 2
-        parts.append(f"{wl['ct'].upper()} scan {scan:.1f} ms at {n_cost}x{n_cost}")
-    sample = ("; ".join(parts) + f"; solve {solve:.2f} ms; one-time FD {t_fd * 1e3:.0f} ms; median of {iters} iterations; "
-              f"extrapolated to {N}x{wl['M']} with cost/scan ~ N*M, KM ~ n^3, solve ~ n "
-              f"(the reference cannot run {N}x{wl['M']}: 24*N*M B of doubles + O(n^3) KM, SURVEY.md §6)")
-    return dict(value=1000.0 / full_ms, unit="iterations/s", cores=threads,
-                kind="reference" if use_ref else "port", sample=sample,
-                ms_per_step_sample=cost + (scan if not km else 0.0) + solve, ms_per_step_extrapolated=full_ms)
+    sizes = sorted(set(min(s, N) for s in sizes))
+    rows, t_start = [], time.perf_counter()
+    for k, n in enumerate(sizes):
+        main = (k == len(sizes) - 1)
+        n_it = warmup + (steps if main else min(steps, fit_steps))
+        ts, t_fd, conv_at = _cpu_loop(g, wl, n, n_it, kind, threads)
+        timed = ts[warmup:]
+        rows.append(dict(n=n, iteration_ms=[round(t, 3) for t in ts], timed_mean_ms=float(np.mean(timed)),
+                         timed_median_ms=float(np.median(timed)), fd_build_s=t_fd, converged_at=conv_at,
+                         registration_ms=float(np.sum(ts[:conv_at])) if conv_at else None))
+        if time.perf_counter() - t_start > budget_s and not main:
+            # out of time for the ladder: the next size is the main sample anyway
+            continue
+    main_row = rows[-1]
+    n_s = main_row["n"]
+    ms_sample = main_row["timed_mean_ms"]
+    extrap = n_s < N
+    p_steady, _ = _fit_power([r["n"] for r in rows], [r["timed_median_ms"] for r in rows])
+    fit = None
+    ms_full = ms_sample
+    reg = None
+    if extrap:
+        if p_steady is None:   # a single sample size: the documented asymptotics (cost ~ N*M; KM ~ n^3)
+            p_steady = 3.0 if wl["ct"] == "km" else 2.0
+            fit_src = "assumed (single sample size)"
+        else:
+            fit_src = f"fitted on n = {[r['n'] for r in rows]}"
+        ms_full = ms_sample * (N / n_s) ** p_steady
+        fit = dict(exponent=p_steady, source=fit_src,
+                   samples=[[r["n"], r["timed_median_ms"]] for r in rows])
+    # whole registration (iteration 0 .. convergence): measured at the sample sizes, extrapolated with its own exponent
+    regs = [(r["n"], r["registration_ms"]) for r in rows if r["registration_ms"]]
+    if regs:
+        p_reg, _ = _fit_power([a for a, _ in regs], [b for _, b in regs])
+        n_r, ms_r = regs[-1]
+        conv = [r["converged_at"] for r in rows if r["n"] == n_r][0]
+        reg = dict(sample_n=n_r, iterations=conv, ms_total_sample=ms_r, ms_per_iteration_sample=ms_r / conv)
+        if n_r < N:
+            pr = p_reg if p_reg is not None else p_steady
+            reg.update(extrapolated=True, exponent=pr, ms_per_iteration=ms_r / conv * (N / n_r) ** pr)
+        else:
+            reg.update(extrapolated=False, ms_per_iteration=ms_r / conv)
+    what = ("the reference's own src/ghicp_reg.cpp + km.cpp + stereo_binary_feature.cpp compiled verbatim (oracle/_ref/"
+            "libghreg_ref.so; 1 thread: it is single-threaded; PCL's SVD call delegated to the oracle)") if kind == "reference" \
+        else f"oracle port of the reference loop ({threads} thread(s): OpenMP on the O(N*M) loops, KM serial)"
+    sample = (f"{what}; iterations {warmup}..{warmup + steps - 1} of a registration from iteration 0 (the indices the GPU arm "
+              f"times) on a {n_s}x{n_s} sample of the workload (same generator, same density): {ms_sample:.1f} ms/iteration"
+              + (f"; extrapolated to {N}x{wl['M']} by (N/n_s)^{p_steady:.2f} ({fit['source']})" if extrap else "; no extrapolation"))
+    return dict(value=1000.0 / ms_full, unit="iterations/s", cores=threads, kind=kind, sample=sample,
+                ms_per_step_sample=ms_sample, sample_n=n_s, extrapolated=extrap, fit=fit, registration=reg, ladder=rows)
 
 
 def main():
@@ -246,10 +251,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
-    ap.add_argument("--n", type=int, default=0, help="override N=M (debug; makes the number non-headline)")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="N=M of the CPU baseline sample")
+    ap.add_argument("--n", type=int, default=0, help="override N=M (e.g. 4000: a size the reference runs WITHOUT extrapolation)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="N=M of the CPU arm's main sample")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3  # timing rule: >= 3 warm-up steps
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -262,24 +269,34 @@ def main():
     config = {"parallelism": f"source rows sharded over {args.gpus} GPU(s), target replicated" if args.gpus > 1 else "1 GPU",
               "workload": args.workload + (f" (N=M={args.n} override)" if args.n else ""), "desc": wl["desc"],
               "N_src": wl["N"], "N_tgt": wl["M"], "descriptor_bits": wl["bits"], "correspondence": wl["ct"],
+              "timed_iterations": [args.warmup, args.warmup + args.steps - 1],
               "l2_policy": "inputs larger than L2 (FD plane u16 N x M streamed every step)" if wl["ft"] == "bsc"
               else "matrix-free; working set < L2 by construction"}
     ncores = os.cpu_count() or 1
+    km = wl["ct"] == "km"
 
     # ---------------- reference arm: the reference's CPU implementation on the host cores ------------
     if args.impl == "reference":
         if rank != 0:
             return
-        n_s = args.cpu_sample or (2000 if wl["ct"] == "km" else min(wl["N"], 6000))
         t0 = time.perf_counter()
-        cb = cpu_baseline(g, wl, threads=min(ncores, 32), n_sample=min(n_s, wl["N"]), iters=max(1, min(args.steps, 2)))
+        if wl["N"] <= 4000:
+            sizes = [wl["N"]]                              # measured at the workload size, no extrapolation
+        else:
+            n_s = args.cpu_sample or (2000 if km else 6000)
+            sizes = [max(500, n_s // 2), max(750, (3 * n_s) // 4), n_s]
+        cb = cpu_arm(g, wl, args.warmup, args.steps, sizes, fit_steps=3)
         line = {"impl": "reference", "metric": "ICP iterations/sec", "value": cb["value"], "unit": "iterations/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": cb["ms_per_step_extrapolated"], "higher_is_better": True, "scaling": "strong",
+                # the time of one MEASURED step (an iteration of the bounded sample); `value` is the workload-size figure
+                "ms_per_step": cb["ms_per_step_sample"], "ms_per_step_is": f"measured on the {cb['sample_n']}x{cb['sample_n']} sample",
+                "value_is": "extrapolated to the workload size (see fit)" if cb["extrapolated"] else "measured at the workload size",
+                "extrapolated": cb["extrapolated"], "fit": cb["fit"], "registration": cb["registration"],
+                "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": cb["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+                "ladder": cb["ladder"], "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
         print(json.dumps(line))
         return
 
@@ -309,16 +326,45 @@ def main():
     t0 = time.perf_counter()
     reg.build_fd()
     t_fd = time.perf_counter() - t0
-
-    first_iters = []
-    for _ in range(args.warmup):
-        st = reg.iterate()
-        first_iters.append(dict(it=st.iteration, ms=st.ms_total, cor=st.cor, nnz=st.nnz, rounds=st.km_rounds,
-                                km_energy=st.km_energy))
+    S0 = np.asfortranarray(sc.S, dtype=np.float64)
+    T_host = np.asfortranarray(sc.T, dtype=np.float64)  # the reference holds kpTXYZ column-major (Eigen::MatrixX3d)
 
     def barrier():
         if dist is not None:
             dist.barrier()
+
+    def allmax(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- a whole registration, iteration 0 .. convergence (device time per iteration, CUDA events inside the library):
+    #      what a registration costs, dense first KM iterations included.  Run twice: the first pass also warms every
+    #      allocation the dense iterations grow (edge buffers), the second is the one reported.
+    REG_CAP = 60
+    registration = None
+    for _pass in range(2):
+        reg.reset()
+        reg.set_keypoints(S0, T_host)
+        its = []
+        for _ in range(REG_CAP):
+            st = reg.iterate()
+            its.append(dict(it=st.iteration, ms=st.ms_total, cor=st.cor, nnz=st.nnz, rounds=st.km_rounds, km_energy=st.km_energy))
+            if st.converged:
+                break
+        total = allmax(float(sum(x["ms"] for x in its)))
+        registration = dict(iterations=len(its), converged=bool(st.converged), ms_total=total, ms_per_iteration=total / len(its),
+                            iterations_per_s=(1000.0 * len(its) / total) if total > 0 else None, first_iterations=its[:6],
+                            note="device time of every iteration from 0 to convergence (max over ranks), second of two passes")
+
+    # ---- warm-up: iterations 0..W-1 of a fresh registration; timed steps = iterations W..W+K-1 -----------------------
+    reg.reset()
+    reg.set_keypoints(S0, T_host)
+    for _ in range(args.warmup):
+        st = reg.iterate()
 
     # ---- timed region 1: device-resident steps -----------------------------------------------------
     barrier()
@@ -335,18 +381,12 @@ def main():
         wall = time.perf_counter() - t0
     barrier()
     clocks = cs.summary()
-    ms_per_step = wall * 1e3 / args.steps
-    if dist is not None:
-        import torch
-        t = torch.tensor([ms_per_step], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_per_step = float(t.item())
+    ms_per_step = allmax(wall * 1e3 / args.steps)
 
     # ---- timed region 2: end to end through the host-facing API -----------------------------------
     # every step: host (pinned inside the library) -> device copy of the current source + target
     # coordinates, one iteration, device -> host read of the stats, the pair lists and the updated source.
     S_host = reg.source()
-    T_host = np.asfortranarray(sc.T, dtype=np.float64)  # the reference holds kpTXYZ column-major (Eigen::MatrixX3d)
     # time the same iteration range as the device-resident region (the weight schedule depends on the index)
     reg.set_state(args.warmup, st.rmse, st.fdm, st.fdstd, st.para1, st.para2)
     barrier()
@@ -359,7 +399,7 @@ def main():
         S_host = reg.source()
     e2e_wall = time.perf_counter() - t0
     barrier()
-    e2e_ms = e2e_wall * 1e3 / e2e_steps
+    e2e_ms = allmax(e2e_wall * 1e3 / e2e_steps)
     h2d = 24 * (wl["N"] + wl["M"])
     d2h = 24 * wl["N"] + 8 * int(st.cor) + 400
 
@@ -369,23 +409,27 @@ def main():
     # dominant kernel accounting: the FD-plane stream of the cost stage
     stage = np.array(stage, dtype=np.float64)
     n_sweeps = int(np.median(stage[:, 7]))
-    # algorithmic bytes of ONE streaming pass: the fp16 FD plane once + the float4 operand
-    # arrays (16 B per keypoint) + 12 B per source row of results
-    alg_bytes = (2 * wl["N"] * wl["M"] if wl["ft"] == "bsc" else 0) + 16 * (wl["N"] + wl["M"]) + 12 * wl["N"]
+    # algorithmic bytes of ONE streaming pass ON ONE GPU: its rows of the fp16 FD plane once + the float4
+    # operand arrays (16 B per keypoint) + 12 B per source row of results.  Sharded: rank 0 streams nloc = ceil(N/G) rows;
+    # the kernel time is rank 0's, so both sides of achieved = bytes / time are per GPU.
+    nloc = (wl["N"] + world - 1) // world
+    alg_bytes = (2 * nloc * wl["M"] if wl["ft"] == "bsc" else 0) + 16 * (nloc + wl["M"]) + 12 * nloc
     cost_ms = float(np.median(stage[:, 0]))
     stream_ms = float(np.median(stage[:, 6]))
     achieved = alg_bytes / (stream_ms * 1e-3) / 1e9 if stream_ms > 0 else 0.0
+    traffic = NCU_TRAFFIC.get(args.workload) if (not args.n and world == 1) else None
     roofline = {"kernel": "k_stream (calED+calCD+scan/gate+stats fused over the fp16 FD plane)", "bound": "hbm",
                 "kernel_ms": stream_ms,
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": NCU_TRAFFIC.get(args.workload) if not args.n else None, "peak_source": peak_src,
+                "traffic": traffic["bytes"] if traffic else None, "traffic_source": traffic["source"] if traffic else None,
+                "peak_source": peak_src, "per_gpu": True, "rows_per_gpu": nloc,
                 "algorithmic_bytes_per_launch": alg_bytes, "sweeps_per_step": n_sweeps}
     if wl["ft"] == "fpfh":
         # matrix-free FPFH: O(N+M) bytes for N*M pair evaluations -> the FP32 pipe, not HBM, bounds the sweep.
         # Dominant kernel = k_ff_sweep<MAIN> (FP32 filter; ms_stream is its CUDA-event time).  Algorithmic work per pair
         # (DESIGN.md §3.5): 33 FFMA (histogram dot) + 12 (hi/lo coordinate differences, d2) + 8 (cost, bound, sum) = 53
         # FP32-pipe instructions; peak = 148 SMs x 128 lanes x SM clock.
-        pairs = float(wl["N"]) * wl["M"]
+        pairs = float(nloc) * wl["M"]
         fast = stream_ms > 0
         t_ms = stream_ms if fast else cost_ms
         sm_mhz = (clocks.get("sm_mhz") or 1965.0)
@@ -396,17 +440,20 @@ def main():
                     "bound": "fp32-pipe", "kernel_ms": t_ms, "achieved": ach if fast else None, "peak": peak_ginstr,
                     "unit": "Ginstr/s", "frac": (ach / peak_ginstr) if fast else None, "traffic": None,
                     "pairs_per_s": pairs / (t_ms * 1e-3) if t_ms > 0 else 0.0, "sweeps_per_step": n_sweeps,
-                    "algorithmic_instr_per_pair": 53}
+                    "algorithmic_instr_per_pair": 53, "per_gpu": True}
     line = {
         "metric": "ICP iterations/sec", "value": 1000.0 / ms_per_step,
         "unit": "iterations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": config,
+        "value_is": f"iterations {args.warmup}..{args.warmup + args.steps - 1} of a registration (settled regime); "
+                    "`registration` holds the whole-registration figure, dense first iterations included",
+        "registration": registration,
         "device_ms_per_step": float(np.mean(dev_ms)),
         "stage_ms": {"cost": cost_ms, "corr": float(np.median(stage[:, 1])), "solve": float(np.median(stage[:, 2]))},
-        "km": {"nnz": int(np.median(stage[:, 3])), "rounds": int(np.median(stage[:, 4]))} if wl["ct"] == "km" else None,
+        "km": {"nnz": int(np.median(stage[:, 3])), "rounds": int(np.median(stage[:, 4]))} if km else None,
         "cor": int(stage[-1, 5]),
-        "first_iterations": first_iters,
+        "first_iterations": registration["first_iterations"],
         "one_time": {"fd_build_s": t_fd, "upload_s": t_upload},
         "e2e": {"value": 1000.0 / e2e_ms, "unit": "iterations/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -416,9 +463,22 @@ def main():
         "roofline": roofline,
     }
     if not args.no_cpu:
-        n_s = args.cpu_sample or (2000 if wl["ct"] == "km" else min(wl["N"], 6000))
-        cb = cpu_baseline(g, wl, threads=1, n_sample=min(n_s, wl["N"]))
-        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        # bounded CPU sample, the same iteration indices as the timed region (10-30 s of CPU work)
+        if wl["N"] <= 1500:
+            sizes = [wl["N"]]
+        else:
+            n_s = args.cpu_sample or (1500 if km else 4000)
+            sizes = [max(400, n_s // 2), min(n_s, wl["N"])]
+        cb = cpu_arm(g, wl, args.warmup, min(args.steps, 4), sizes, fit_steps=2)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "extrapolated", "fit", "registration")}
+        try:   # SURVEY.md §8d "fair CPU": the O(N*M) loops on all host cores (OpenMP), KM serial (it is sequential as written)
+            th = min(ncores, 8)
+            fc = cpu_arm(g, wl, args.warmup, min(args.steps, 4), [sizes[-1]], threads=th)
+            line["cpu_baseline"]["fair_cpu"] = {"cores": th, "kind": fc["kind"], "sample_n": fc["sample_n"],
+                                                "ms_per_iteration_sample": fc["ms_per_step_sample"],
+                                                "single_thread_ms_per_iteration_sample": cb["ms_per_step_sample"]}
+        except Exception as e:  # the OpenMP oracle is optional test infrastructure
+            line["cpu_baseline"]["fair_cpu"] = {"unavailable": str(e)[:200]}
     print(json.dumps(line))
 
 

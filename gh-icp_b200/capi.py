@@ -67,7 +67,7 @@ _lib = None
 EXPORTS = ["ghicp_abi_version", "ghicp_device_count", "ghicp_last_error", "ghicp_create", "ghicp_destroy",
            "ghicp_set_keypoints", "ghicp_set_bsc", "ghicp_set_fpfh", "ghicp_build_fd", "ghicp_iterate",
            "ghicp_run", "ghicp_get_pairs", "ghicp_get_source", "ghicp_get_rt", "ghicp_get_fd",
-           "ghicp_probe_rowmin", "ghicp_set_state", "ghicp_km_solve", "ghicp_rigid_fit", "ghicp_rigid_fit_ex",
+           "ghicp_probe_rowmin", "ghicp_set_state", "ghicp_reset", "ghicp_km_solve", "ghicp_rigid_fit", "ghicp_rigid_fit_ex",
            "ghicp_set_target_normals", "ghicp_set_solver", "ghicp_voxel_downsample", "ghicp_detect_keypoints",
            "ghicp_bsc_extract", "ghicp_bsc_default_pattern", "ghicp_comm_unique_id", "ghicp_comm_init"]
 
@@ -100,6 +100,7 @@ def lib():
     L.ghicp_get_fd.argtypes = [vp, dp]
     L.ghicp_probe_rowmin.argtypes = [vp, ip, dp, dp, dp, dp]
     L.ghicp_set_state.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]
+    L.ghicp_reset.argtypes = [vp]
     L.ghicp_km_solve.argtypes = [C.c_int, dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, ip, dp, ip]
     L.ghicp_rigid_fit.argtypes = [C.c_int, dp, dp, C.c_int, dp]
     L.ghicp_rigid_fit_ex.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, C.c_int, dp]

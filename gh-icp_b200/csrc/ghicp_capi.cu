@@ -862,6 +862,17 @@ int ghicp_set_state(ghicp_ctx *ctx, int iteration, double rms, double fdm, doubl
   return GHICP_OK;
 }
 
+int ghicp_reset(ghicp_ctx *ctx) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c) return GHICP_E_ARG;
+  reset_loop_state(c);
+  c->have_prev = false;
+  c->last_local_nnz = -1;
+  c->last_cands = 0;
+  c->last_cor = 0;
+  return GHICP_OK;
+}
+
 // ---- stand-alone stages ------------------------------------------------------------------------
 int ghicp_km_solve(int device, const double *W, int n, int sp, int tp, double eps, double penalty, int *match,
                    double *energy, int *rounds) {

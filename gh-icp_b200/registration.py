@@ -176,6 +176,11 @@ class GHRegistration:
     def set_state(self, iteration, rms, fdm, fdstd, para1, para2):
         capi.check(self.L.ghicp_set_state(self.ctx, iteration, rms, fdm, fdstd, para1, para2), self.ctx)
 
+    def reset(self):
+        """Constructor state again (iteration 0, Rt_tillnow = I); descriptors and the FD plane stay."""
+        capi.check(self.L.ghicp_reset(self.ctx), self.ctx)
+        self.history = []
+
 
 def from_scene(scene, Ft, Ct, dof=6, **kw):
     """Convenience: build Keypoints/Energyfunction/GHRegistration from a synth.Scene."""

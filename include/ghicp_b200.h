@@ -159,6 +159,10 @@ int ghicp_probe_rowmin(ghicp_ctx *ctx, int *idx, double *cd, double *cd_mean, do
 /* Loop state the reference keeps between iterations (include/ghicp_reg.h:173-202); for resume/tests. */
 int ghicp_set_state(ghicp_ctx *ctx, int iteration, double rms, double fdm, double fdstd, double para1,
                     double para2);
+/* Back to the state the GHRegistration constructor leaves (include/ghicp_reg.h:77-117: iteration 0, RMS 99999,
+ * para1 = para2 = 1, converge = 0, Rt_tillnow = I) without touching the descriptors or the FD plane: a second
+ * registration of the same keypoint sets (ghicp_set_keypoints re-uploads the untransformed source). */
+int ghicp_reset(ghicp_ctx *ctx);
 
 /* ---- stand-alone stages -------------------------------------------------------------------- */
 /* Km(graph, eps, penalty).kmsolve() + output() (include/km.h:38-53, src/km.cpp:40-233) on a dense
