@@ -33,6 +33,12 @@ WORKLOADS = {
     # BASELINE.json configs[2]: no N x M array fits (reference: 320 GB of doubles; stored float plane: 160 GB) ->
     # matrix-free FPFH path (gh-icp_b200/csrc/ghicp_fpfh.cu); point-to-point solve like the reference loop
     "config3": dict(N=200000, M=200000, ft="fpfh", ct="nnr", bits=0, desc="200k x 200k, FPFH-33 float, NN + reciprocal, matrix-free"),
+    # BASELINE.json configs[3] / [4]: RAW scans -> voxel filter + curvature keypoints + BSC encoder on the GPU (device-resident
+    # pipeline, ghicp_prep_run) -> KM registration of the keypoint sets (N, M = what the detector finds; filled in at run time)
+    "config4": dict(N=0, M=0, raw=1000000, overlap=0.6, dof=6, ft="bsc", ct="km", bits=441, voxel=0.05, radius=0.5, nms=1.0,
+                    desc="1M + 1M raw points -> voxel 0.05 m + curvature keypoints + BSC-441 on the GPU -> KM, 6-DoF"),
+    "config5": dict(N=0, M=0, raw=5000000, overlap=0.3, dof=4, ft="bsc", ct="km", bits=441, voxel=0.05, radius=0.5, nms=1.0,
+                    desc="5M + 5M raw points, 30 % overlap -> voxel 0.05 m + keypoints + BSC-441 (2 variants: '4-DoF leveled') -> KM"),
 }
 
 
@@ -109,7 +115,47 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+_RAW_CACHE = {}
+
+
+def raw_scans(g, wl):
+    key = (wl["raw"], wl["overlap"])
+    if key not in _RAW_CACHE:
+        _RAW_CACHE[key] = g.synth.scan_pair(wl["raw"], wl["overlap"], seed=4)
+    return _RAW_CACHE[key]
+
+
+def make_scene_from_raw_cpu(g, wl, raw_points):
+    """CPU arm of the pipeline workloads: the ORACLE's voxel filter + keypoint detector + BSC encoder (test infrastructure, the
+    restated include/filter.hpp, keypoint_detect.hpp, pca.h, binary_feature_extraction.hpp) on a crop of the raw scans
+    (a band in y, which keeps the overlap ratio along x) of about `raw_points` points each."""
+    import oracle
+    Tc, Sc, _, _ = raw_scans(g, wl)
+    frac = min(1.0, raw_points / float(wl["raw"]))
+    pat = g.bsc_default_pattern(7)
+    out, t_prep = {}, time.perf_counter()
+    for name, P, dof in (("T", Tc, 0), ("S", Sc, wl["dof"])):
+        if frac < 1.0:
+            y = P[:, 1]
+            P = np.ascontiguousarray(P[y < np.quantile(y, frac)])
+        D = np.ascontiguousarray(P[oracle.voxel_downsample(P, wl["voxel"])])
+        kp, _, _, _ = oracle.detect_keypoints(D, wl["radius"], 0.65, 20, wl["nms"])
+        bits = oracle.bsc_extract(D, kp, wl["nms"], pat, 7, dof)[0]
+        out[name] = (D, kp, bits)
+    t_prep = time.perf_counter() - t_prep
+    D, kp, _ = out["S"]
+    ext = D.max(axis=0) - D.min(axis=0)
+    sc = g.synth.Scene(S=np.asfortranarray(out["S"][0][out["S"][1]].astype(np.float64)),
+                       T=np.asfortranarray(out["T"][0][out["T"][1]].astype(np.float64)),
+                       bbx_magnitude=float(np.float32(ext[0] + ext[1] + ext[2])), R_gt=None, t_gt=None, n_overlap=0, perm=None)
+    sc.bsc_s, sc.bsc_t, sc.bits = out["S"][2], out["T"][2][0], 441
+    sc.meta = dict(cpu_prep_s=t_prep, raw_points=int(raw_points))
+    return sc
+
+
 def make_scene(g, wl, n_override=None, seed=2):
+    if "raw" in wl:
+        return make_scene_from_raw_cpu(g, wl, n_override or wl["raw"])
     N = n_override or wl["N"]
     M = n_override or wl["M"]
     if wl["ft"] == "none":
@@ -146,13 +192,14 @@ def _cpu_loop(g, wl, n, n_iters, kind, threads=1, stop_at_convergence=False):
     import oracle
     import tempfile
     sc = make_scene(g, wl, n_override=n)
+    dof = wl.get("dof", 6)
     cwd = os.getcwd()
     os.chdir(tempfile.mkdtemp())  # Km::output writes Corres.txt (src/km.cpp:148)
     try:
         if kind == "reference":
-            o = oracle.Reference(FT[wl["ft"]], CT[wl["ct"]], bbx_magnitude=sc.bbx_magnitude, solve_mode=0)
+            o = oracle.Reference(FT[wl["ft"]], CT[wl["ct"]], dof=dof, bbx_magnitude=sc.bbx_magnitude, solve_mode=0)
         else:
-            o = oracle.Oracle(FT[wl["ft"]], CT[wl["ct"]], bbx_magnitude=sc.bbx_magnitude, solve_mode=0,
+            o = oracle.Oracle(FT[wl["ft"]], CT[wl["ct"]], dof=dof, bbx_magnitude=sc.bbx_magnitude, solve_mode=0,
                               use_ref_km=(oracle.ref_km_lib() is not None and wl["ct"] == "km"), num_threads=threads)
         o.set_keypoints(sc.S, sc.T)
         if wl["ft"] == "bsc":
@@ -173,7 +220,7 @@ def _cpu_loop(g, wl, n, n_iters, kind, threads=1, stop_at_convergence=False):
                     break
     finally:
         os.chdir(cwd)
-    return ts, t_fd, conv_at
+    return ts, t_fd, conv_at, max(sc.S.shape[0], sc.T.shape[0]), dict(getattr(sc, "meta", {}) or {})
 
 
 def _fit_power(ns, ts):
@@ -191,15 +238,18 @@ def cpu_arm(g, wl, warmup, steps, sizes, fit_steps=3, threads=1, budget_s=240.0)
     import oracle
     oracle.build()
     kind = "reference" if (oracle.ref_ghreg_lib() is not None and threads == 1) else "port"
+    raw = "raw" in wl                     # pipeline workloads: `sizes` are RAW points per scan, n = the keypoints they yield
     N = wl["N"]
-    sizes = sorted(set(min(s, N) for s in sizes))
+    sizes = sorted(set(min(s, wl["raw"] if raw else N) for s in sizes))
     rows, t_start = [], time.perf_counter()
-    for k, n in enumerate(sizes):
+    for k, n_req in enumerate(sizes):
         main = (k == len(sizes) - 1)
         n_it = warmup + (steps if main else min(steps, fit_steps))
-        ts, t_fd, conv_at = _cpu_loop(g, wl, n, n_it, kind, threads)
+        ts, t_fd, conv_at, n, meta = _cpu_loop(g, wl, n_req, n_it, kind, threads)
+        if raw and main and N <= 0:         # full keypoint count unknown on the CPU side: keypoints scale with the scanned area
+            N = int(round(n * wl["raw"] / float(n_req)))
         timed = ts[warmup:]
-        rows.append(dict(n=n, iteration_ms=[round(t, 3) for t in ts], timed_mean_ms=float(np.mean(timed)),
+        rows.append(dict(n=n, meta=meta, iteration_ms=[round(t, 3) for t in ts], timed_mean_ms=float(np.mean(timed)),
                          timed_median_ms=float(np.median(timed)), fd_build_s=t_fd, converged_at=conv_at,
                          registration_ms=float(np.sum(ts[:conv_at])) if conv_at else None))
         if time.perf_counter() - t_start > budget_s and not main:
@@ -238,8 +288,10 @@ def cpu_arm(g, wl, warmup, steps, sizes, fit_steps=3, threads=1, budget_s=240.0)
             "libghreg_ref.so; 1 thread: it is single-threaded; PCL's SVD call delegated to the oracle)") if kind == "reference" \
         else f"oracle port of the reference loop ({threads} thread(s): OpenMP on the O(N*M) loops, KM serial)"
     sample = (f"{what}; iterations {warmup}..{warmup + steps - 1} of a registration from iteration 0 (the indices the GPU arm "
-              f"times) on a {n_s}x{n_s} sample of the workload (same generator, same density): {ms_sample:.1f} ms/iteration"
-              + (f"; extrapolated to {N}x{wl['M']} by (N/n_s)^{p_steady:.2f} ({fit['source']})" if extrap else "; no extrapolation"))
+              f"times) on a {n_s}x{n_s} sample of the workload (same generator, same density"
+              + ("; keypoints + descriptors from the oracle's pre-processing of a y-band of the raw scans" if raw else "")
+              + f"): {ms_sample:.1f} ms/iteration"
+              + (f"; extrapolated to {N} keypoints by (N/n_s)^{p_steady:.2f} ({fit['source']})" if extrap else "; no extrapolation"))
     return dict(value=1000.0 / ms_full, unit="iterations/s", cores=threads, kind=kind, sample=sample,
                 ms_per_step_sample=ms_sample, sample_n=n_s, extrapolated=extrap, fit=fit, registration=reg, ladder=rows)
 
@@ -270,7 +322,9 @@ def main():
               "workload": args.workload + (f" (N=M={args.n} override)" if args.n else ""), "desc": wl["desc"],
               "N_src": wl["N"], "N_tgt": wl["M"], "descriptor_bits": wl["bits"], "correspondence": wl["ct"],
               "timed_iterations": [args.warmup, args.warmup + args.steps - 1],
-              "l2_policy": "inputs larger than L2 (FD plane u16 N x M streamed every step)" if wl["ft"] == "bsc"
+              "l2_policy": ("FD plane of the detected keypoint sets (tens of MB) stays L2-resident across iterations, as in a real "
+                            "registration; no flush") if "raw" in wl else
+              "inputs larger than L2 (FD plane u16 N x M streamed every step)" if wl["ft"] == "bsc"
               else "matrix-free; working set < L2 by construction"}
     ncores = os.cpu_count() or 1
     km = wl["ct"] == "km"
@@ -280,7 +334,10 @@ def main():
         if rank != 0:
             return
         t0 = time.perf_counter()
-        if wl["N"] <= 4000:
+        if "raw" in wl:
+            cap = args.cpu_sample or 250000                # raw points per scan the oracle pre-processes on the CPU
+            sizes = [min(wl["raw"], cap // 2), min(wl["raw"], cap)]
+        elif wl["N"] <= 4000:
             sizes = [wl["N"]]                              # measured at the workload size, no extrapolation
         else:
             n_s = args.cpu_sample or (2000 if km else 6000)
@@ -313,21 +370,54 @@ def main():
         dist_mod.init_process_group("nccl")
         dist = dist_mod
     dev = local_rank
-    sc = make_scene(g, wl)
     comm = None
     if dist is not None:
         # one process per GPU: source rows sharded, NCCL exchange inside the library (unique id via torch)
         uid = [g.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         comm = (uid[0], rank, world)
-    t0 = time.perf_counter()
-    reg = g.registration.from_scene(sc, FT[wl["ft"]], CT[wl["ct"]], device=dev, comm=comm)
-    t_upload = time.perf_counter() - t0
+    preprocessing = None
+    if "raw" in wl:
+        # raw scans -> device-resident pipeline (every rank pre-processes both scans on its own GPU: the stages are
+        # deterministic, so all ranks hold identical keypoint sets; the registration below shards the source keypoints)
+        Tc, Sc, _, _ = raw_scans(g, wl)
+        best = None
+        for _rep in range(2):                              # first pass = module load + allocator warm-up
+            t0 = time.perf_counter()
+            pt = g.Prep(Tc, wl["voxel"], wl["radius"], wl["nms"], bsc_radius=wl["nms"], dof_type=0, device=dev)
+            ps = g.Prep(Sc, wl["voxel"], wl["radius"], wl["nms"], bsc_radius=wl["nms"], dof_type=wl["dof"], device=dev)
+            wall_ms = (time.perf_counter() - t0) * 1e3
+            if best is not None:
+                best[0].close(); best[1].close()
+            best = (pt, ps, wall_ms)
+        pt, ps, wall_ms = best
+        if ps.n_kp < 10 or pt.n_kp < 10:
+            raise SystemExit("bench.py: the detector found too few keypoints")
+        wl["N"], wl["M"] = ps.n_kp, pt.n_kp
+        config.update(N_src=ps.n_kp, N_tgt=pt.n_kp, raw_points=[int(len(Sc)), int(len(Tc))])
+        preprocessing = {"source": dict(points=int(len(Sc)), down=ps.n_down, keypoints=ps.n_kp, stage_ms=ps.stage_ms),
+                         "target": dict(points=int(len(Tc)), down=pt.n_down, keypoints=pt.n_kp, stage_ms=pt.stage_ms),
+                         "wall_ms_both_scans": wall_ms,
+                         "raw_points_per_s": (len(Sc) + len(Tc)) / (ps.stage_ms["total"] + pt.stage_ms["total"]) * 1e3,
+                         "note": "ghicp_prep_run: one upload per scan, voxel filter -> keypoints -> BSC chained on the device; "
+                                 "stage_ms from CUDA events (h2d = the raw scan's host->device copy)"}
+        t0 = time.perf_counter()
+        Ef = g.Energyfunction().init(ps.n_kp, pt.n_kp, ps.bbx_magnitude)
+        reg = g.GHRegistration((ps, pt), Ef, FT[wl["ft"]], CT[wl["ct"]], dof_type=wl["dof"], device=dev, comm=comm)
+        t_upload = time.perf_counter() - t0
+        S0 = np.asfortranarray(ps.keypoints()[1], dtype=np.float64)
+        T_host = np.asfortranarray(pt.keypoints()[1], dtype=np.float64)
+        pt.close(); ps.close()
+    else:
+        sc = make_scene(g, wl)
+        t0 = time.perf_counter()
+        reg = g.registration.from_scene(sc, FT[wl["ft"]], CT[wl["ct"]], device=dev, comm=comm)
+        t_upload = time.perf_counter() - t0
+        S0 = np.asfortranarray(sc.S, dtype=np.float64)
+        T_host = np.asfortranarray(sc.T, dtype=np.float64)  # the reference holds kpTXYZ column-major (Eigen::MatrixX3d)
     t0 = time.perf_counter()
     reg.build_fd()
     t_fd = time.perf_counter() - t0
-    S0 = np.asfortranarray(sc.S, dtype=np.float64)
-    T_host = np.asfortranarray(sc.T, dtype=np.float64)  # the reference holds kpTXYZ column-major (Eigen::MatrixX3d)
 
     def barrier():
         if dist is not None:
@@ -455,6 +545,7 @@ def main():
         "cor": int(stage[-1, 5]),
         "first_iterations": registration["first_iterations"],
         "one_time": {"fd_build_s": t_fd, "upload_s": t_upload},
+        "preprocessing": preprocessing,
         "e2e": {"value": 1000.0 / e2e_ms, "unit": "iterations/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
@@ -464,7 +555,10 @@ def main():
     }
     if not args.no_cpu:
         # bounded CPU sample, the same iteration indices as the timed region (10-30 s of CPU work)
-        if wl["N"] <= 1500:
+        if "raw" in wl:
+            cap = args.cpu_sample or 125000
+            sizes = [min(wl["raw"], cap // 2), min(wl["raw"], cap)]
+        elif wl["N"] <= 1500:
             sizes = [wl["N"]]
         else:
             n_s = args.cpu_sample or (1500 if km else 4000)

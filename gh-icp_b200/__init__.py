@@ -11,7 +11,7 @@ from .capi import (  # noqa: F401
     FT_BSC, FT_ROPS, FT_FPFH, FT_NONE, CT_NN, CT_NNR, CT_KM,
     GhicpError, IterStats, Config, lib, lib_path, build_library, device_count,
     km_solve, rigid_fit, rigid_fit_ex, comm_unique_id, voxel_downsample, detect_keypoints,
-    bsc_extract, bsc_default_pattern, read_sample_pattern,
+    bsc_extract, bsc_default_pattern, read_sample_pattern, Prep, PrepParams,
     SOLVER_SVD, SOLVER_WEIGHTED_SVD, SOLVER_POINT_TO_PLANE, SOLVER_YAW_4DOF,
 )
 from .registration import GHRegistration, Keypoints, Energyfunction  # noqa: F401

@@ -69,7 +69,8 @@ EXPORTS = ["ghicp_abi_version", "ghicp_device_count", "ghicp_last_error", "ghicp
            "ghicp_run", "ghicp_get_pairs", "ghicp_get_source", "ghicp_get_rt", "ghicp_get_fd",
            "ghicp_probe_rowmin", "ghicp_set_state", "ghicp_reset", "ghicp_km_solve", "ghicp_rigid_fit", "ghicp_rigid_fit_ex",
            "ghicp_set_target_normals", "ghicp_set_solver", "ghicp_voxel_downsample", "ghicp_detect_keypoints",
-           "ghicp_bsc_extract", "ghicp_bsc_default_pattern", "ghicp_comm_unique_id", "ghicp_comm_init"]
+           "ghicp_bsc_extract", "ghicp_bsc_default_pattern", "ghicp_comm_unique_id", "ghicp_comm_init",
+           "ghicp_prep_run", "ghicp_prep_info", "ghicp_prep_get", "ghicp_prep_destroy", "ghicp_set_from_prep"]
 
 
 def lib():
@@ -111,6 +112,11 @@ def lib():
     L.ghicp_detect_keypoints.argtypes = [C.c_int, fpp, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, ip, ip, fpp, dp, ip]
     L.ghicp_bsc_extract.argtypes = [C.c_int, fpp, C.c_int, ip, C.c_int, C.c_float, C.c_int, ip, C.c_int, vp, ip, fpp, ip]
     L.ghicp_bsc_default_pattern.argtypes = [C.c_int, ip]
+    L.ghicp_prep_run.argtypes = [C.c_int, fpp, C.c_int, C.POINTER(PrepParams), ip, C.POINTER(vp)]
+    L.ghicp_prep_info.argtypes = [vp, ip, ip, ip, fpp, fpp, fpp]
+    L.ghicp_prep_get.argtypes = [vp, fpp, ip, dp, vp]
+    L.ghicp_prep_destroy.argtypes = [vp]
+    L.ghicp_set_from_prep.argtypes = [vp, vp, vp]
     L.ghicp_comm_unique_id.argtypes = [vp]
     L.ghicp_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
     _lib = L
@@ -119,6 +125,73 @@ def lib():
 
 def device_count():
     return lib().ghicp_device_count()
+
+
+class PrepParams(C.Structure):
+    """ghicp_prep_params (include/ghicp_b200.h): the driver's per-cloud parameters (test/ghicp_main.cpp:89-116)."""
+    _fields_ = [("voxel_size", C.c_float), ("neighborhood_radius", C.c_float), ("ratio_max", C.c_float), ("min_pts", C.c_int),
+                ("nms_radius", C.c_float), ("bsc_radius", C.c_float), ("bsc_side", C.c_int), ("dof_type", C.c_int)]
+
+
+class Prep:
+    """Device-resident pipeline result of ONE cloud (ghicp_prep_run): voxel filter -> curvature keypoints -> BSC encoder,
+    the raw cloud uploaded once, nothing copied back unless asked for."""
+
+    def __init__(self, xyz, voxel_size, neighborhood_radius, nms_radius, bsc_radius=0.0, dof_type=0, ratio_max=0.65, min_pts=20,
+                 side=7, pairs=None, device=0):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+        self.params = PrepParams(voxel_size, neighborhood_radius, ratio_max, min_pts, nms_radius, bsc_radius, side, dof_type)
+        pr = None
+        if bsc_radius > 0:
+            pr = bsc_default_pattern(side) if pairs is None else np.ascontiguousarray(pairs, dtype=np.int32)
+        self.h = C.c_void_p()
+        self.side = side
+        check(lib().ghicp_prep_run(device, xyz.ctypes.data_as(C.POINTER(C.c_float)), len(xyz), C.byref(self.params),
+                                   None if pr is None else _ip(pr), C.byref(self.h)))
+        nd, nk, nv = C.c_int(0), C.c_int(0), C.c_int(0)
+        mn, mx, ms = np.zeros(3, np.float32), np.zeros(3, np.float32), np.zeros(5, np.float32)
+        fpp = C.POINTER(C.c_float)
+        check(lib().ghicp_prep_info(self.h, C.byref(nd), C.byref(nk), C.byref(nv), mn.ctypes.data_as(fpp), mx.ctypes.data_as(fpp),
+                                    ms.ctypes.data_as(fpp)))
+        self.n_down, self.n_kp, self.V = nd.value, nk.value, nv.value
+        self.bbox_min, self.bbox_max = mn, mx
+        self.stage_ms = dict(h2d=float(ms[0]), voxel_filter=float(ms[1]), keypoints=float(ms[2]), bsc=float(ms[3]), total=float(ms[4]))
+
+    @property
+    def bbx_magnitude(self):
+        """getCloudBound of the down-sampled cloud, test/ghicp_main.cpp:91-93 (float32 arithmetic)."""
+        e = self.bbox_max - self.bbox_min
+        return float(np.float32(e[0] + e[1] + e[2]))
+
+    def down(self):
+        out = np.zeros((self.n_down, 3), np.float32)
+        check(lib().ghicp_prep_get(self.h, out.ctypes.data_as(C.POINTER(C.c_float)), None, None, None))
+        return out
+
+    def keypoints(self):
+        """(indices into the down-sampled cloud, coordinates [n_kp][3] float64)."""
+        idx = np.zeros(self.n_kp, np.int32)
+        soa = np.zeros((3, self.n_kp), np.float64)
+        check(lib().ghicp_prep_get(self.h, None, _ip(idx), _dp(soa), None))
+        return idx, np.ascontiguousarray(soa.T)
+
+    def bsc(self):
+        nbytes = (9 * self.side * self.side + 7) // 8
+        out = np.zeros((max(self.V, 1), self.n_kp, nbytes), np.uint8)
+        if self.V > 0:
+            check(lib().ghicp_prep_get(self.h, None, None, None, out.ctypes.data))
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().ghicp_prep_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def check(rc, ctx=None):

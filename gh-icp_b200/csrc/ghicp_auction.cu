@@ -95,6 +95,7 @@ struct AucArgs {
   int *bid_obj; double *bid_val, *bid_aux;
   int *counters;  // [0],[1]: ping-pong list sizes, [2]: base list size
   double eps;
+  int profile;    // GHICP_AUCTION_DEBUG: per-size-class timing of the tail rounds into counters[16..31]
 };
 
 __global__ void k_auc_init(int n_rows, int n_cols, const long long *rowptr, int n_chunks, double *price,
@@ -330,7 +331,8 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const int gthreads = gridDim.x * blockDim.x;
   int cur = 0, rounds = 0;
-  unsigned long long t_mark = 0;
+  unsigned long long t_mark = 0, t_prev = 0;
+  int b_prev = 0;
 #if defined(GHICP_EMU_HOST)
   auto now_ns = []() { return 0ull; };   // host emulation: no device timer
 #else
@@ -350,7 +352,14 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
           if (m == 0 || m > small_n || rounds >= max_rounds) break;
           const int *list = lists[cur];
           int *next = lists[cur ^ 1];
-          if (threadIdx.x == 0) { s_next = 0; atomicAdd((unsigned long long *)&a.counters[8], (unsigned long long)m); }
+          if (threadIdx.x == 0) {
+            s_next = 0; atomicAdd((unsigned long long *)&a.counters[8], (unsigned long long)m);
+            if (a.profile) {   // GHICP_AUCTION_DEBUG: time and rounds per active-set size class
+              const unsigned long long tn = now_ns();
+              if (t_prev) { atomicAdd((unsigned long long *)&a.counters[16 + 2 * b_prev], tn - t_prev); atomicAdd((unsigned long long *)&a.counters[24 + 2 * b_prev], 1ull); }
+              t_prev = tn; b_prev = m == 1 ? 0 : (m <= 16 ? 1 : (m <= 64 ? 2 : 3));
+            }
+          }
           constexpr int NW = PA_THREADS / 32;
           if (m <= NW / 2) {
             // very few bidders: split every adjacency list over G warps so one round costs one short scan
@@ -538,7 +547,7 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
   const int gmax = (nmax + 255) / 256;
   int *base_list = c->d_flags;  // free during KM
 
-  cudaMemsetAsync(c->d_counters, 0, sizeof(int) * 16, st);
+  cudaMemsetAsync(c->d_counters, 0, sizeof(int) * 64, st);
   GHICP_LAUNCH(k_auc_init, gmax, 256, 0, st, n_rows, n_cols, c->d_rowptr, c->n_chunks, c->d_price, base_list, c->d_counters,
                                    c->d_bidmax, c->d_bidwin, nmax);
   c->launches++;
@@ -583,6 +592,7 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
   small_rev = small_rev < 16 ? 16 : (small_rev > PA_SMALL ? PA_SMALL : small_rev);
   if (const char *ov = getenv("GHICP_AUCTION_SMALL")) small_fwd = small_rev = atoi(ov);  // experiment / test hook: 0 = grid rounds only
   const bool debug = getenv("GHICP_AUCTION_DEBUG") != nullptr;
+  a.profile = debug ? 1 : 0;
   const double relax_factor = getenv("GHICP_AUCTION_RELAX") ? atof(getenv("GHICP_AUCTION_RELAX")) : 0.0;
   int last_rounds = 0;
   bool ran_reverse = false;
@@ -652,13 +662,16 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
     cudaMemsetAsync(c->d_bid_obj, 0xff, sizeof(int) * (size_t)nmax, st);
     }
     if (debug) {
-      cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(int) * 16, cudaMemcpyDeviceToHost, st);
+      cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(int) * 64, cudaMemcpyDeviceToHost, st);
       cudaStreamSynchronize(st);
       fprintf(stderr, "[auction] phase %zu eps %.5f rounds %d (cum %d, grid rounds %d) bids(cum) %llu small_fwd %d  tail %.2f ms grid %.2f ms (cum)\n", ph, a.eps,
               c->h_counters[6] - last_rounds, c->h_counters[6], c->h_counters[10],
               *(unsigned long long *)&c->h_counters[8], small_fwd, *(unsigned long long *)&c->h_counters[12] * 1e-6,
               *(unsigned long long *)&c->h_counters[14] * 1e-6);
       last_rounds = c->h_counters[6];
+      const unsigned long long *pb = (const unsigned long long *)&c->h_counters[16];
+      fprintf(stderr, "[auction]   tail rounds by active-set size (cum): m=1: %llu in %.2f ms | 2-16: %llu in %.2f ms | 17-64: %llu in %.2f ms | >64: %llu in %.2f ms\n",
+              pb[4], pb[0] * 1e-6, pb[5], pb[1] * 1e-6, pb[6], pb[2] * 1e-6, pb[7], pb[3] * 1e-6);
     }
   }
   {

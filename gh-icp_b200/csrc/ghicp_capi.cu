@@ -168,7 +168,7 @@ static int alloc_workspaces(Ctx *c) {
   if ((rc = dev_alloc(c, &c->d_tp, (size_t)nmax))) return rc;
   if ((rc = dev_alloc(c, &c->d_iter, 1))) return rc;
   if (!c->h_iter && cudaMallocHost((void **)&c->h_iter, sizeof(DevIter)) != cudaSuccess) return GHICP_E_NOMEM;
-  if (!c->h_counters && cudaMallocHost((void **)&c->h_counters, sizeof(int) * 16) != cudaSuccess) return GHICP_E_NOMEM;
+  if (!c->h_counters && cudaMallocHost((void **)&c->h_counters, sizeof(int) * 64) != cudaSuccess) return GHICP_E_NOMEM;
   if (c->cfg.corr_type == GHICP_CT_KM) {
     if ((rc = dev_alloc(c, &c->d_cnt, L + 2))) return rc;
     if ((rc = dev_alloc(c, &c->d_rowptr, L + 1))) return rc;
@@ -186,7 +186,7 @@ static int alloc_workspaces(Ctx *c) {
     if ((rc = dev_alloc(c, &c->d_bid_aux, (size_t)nmax))) return rc;
     if ((rc = dev_alloc(c, &c->d_list[0], (size_t)nmax))) return rc;
     if ((rc = dev_alloc(c, &c->d_list[1], (size_t)nmax))) return rc;
-    if ((rc = dev_alloc(c, &c->d_counters, 16))) return rc;
+    if ((rc = dev_alloc(c, &c->d_counters, 64))) return rc;
     // edge list of the KM count pass: generous for a settled loop (a few edges per keypoint); denser graphs
     // take the two-pass count + fill route (their time is the auction's anyway)
     const size_t plane = (size_t)std::max(c->nloc, 1) * (size_t)M;
@@ -1077,6 +1077,181 @@ int ghicp_bsc_extract(int device, const float *xyz, int n, const int *kp_idx, in
   if (d_status) cudaFree(d_status);
   if (e != cudaSuccess) { set_error(nullptr, std::string("bsc_extract: ") + cudaGetErrorString(e)); cudaGetLastError(); return e == cudaErrorMemoryAllocation ? GHICP_E_NOMEM : GHICP_E_CUDA; }
   if (n_variants) *n_variants = V;
+  return GHICP_OK;
+}
+
+// ---- device-resident pipeline: raw cloud -> down-sampled cloud -> keypoints -> descriptors ---------------------------------
+struct ghicp_prep {
+  int device = 0;
+  int n = 0, n_down = 0, n_kp = 0, V = 0, side = 0, nbytes = 0;
+  float *d_down = nullptr;          // [n_down][3]
+  int *d_kp = nullptr;              // [n_kp] indices into d_down
+  double *d_kp_xyz = nullptr;       // [3][n_kp]
+  unsigned char *d_bits = nullptr;  // [V][n_kp][nbytes]
+  float bbox_min[3] = {0, 0, 0}, bbox_max[3] = {0, 0, 0};
+  float stage_ms[5] = {0, 0, 0, 0, 0};
+};
+
+int ghicp_prep_destroy(ghicp_prep *h) {
+  if (!h) return GHICP_OK;
+  cudaSetDevice(h->device);
+  if (h->d_down) cudaFree(h->d_down);
+  if (h->d_kp) cudaFree(h->d_kp);
+  if (h->d_kp_xyz) cudaFree(h->d_kp_xyz);
+  if (h->d_bits) cudaFree(h->d_bits);
+  delete h;
+  return GHICP_OK;
+}
+
+int ghicp_prep_run(int device, const float *xyz, int n, const ghicp_prep_params *p, const int *bsc_pairs, ghicp_prep **out) {
+  if (!xyz || !p || !out || n <= 0 || !(p->voxel_size > 0.f) || !(p->neighborhood_radius > 0.f) || !(p->nms_radius > 0.f)) {
+    set_error(nullptr, "prep_run: bad argument");
+    return GHICP_E_ARG;
+  }
+  const bool want_bsc = p->bsc_radius > 0.f;
+  const int side = p->bsc_side > 0 ? p->bsc_side : 7;
+  if (want_bsc && (!bsc_pairs || side > 9)) { set_error(nullptr, "prep_run: BSC needs the sampling pattern and voxel_side_num <= 9"); return GHICP_E_ARG; }
+  if (want_bsc) for (int i = 0; i < 2 * side * side; ++i) if (bsc_pairs[i] < 0 || bsc_pairs[i] >= side * side) { set_error(nullptr, "prep_run: sampling pair out of range"); return GHICP_E_ARG; }
+  if (ghicp_device_count() <= 0) { set_error(nullptr, "prep_run: no CUDA device"); return GHICP_E_NODEV; }
+  if (cudaSetDevice(device) != cudaSuccess) return GHICP_E_CUDA;
+  ghicp_prep *h = new ghicp_prep();
+  h->device = device; h->n = n; h->side = side;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  float *d_xyz = nullptr, *d_lam = nullptr, *d_lrf = nullptr; double *d_curv = nullptr;
+  int *d_keep = nullptr, *d_cnt = nullptr, *d_kpbuf = nullptr, *d_pairs = nullptr, *d_status = nullptr;
+  cudaError_t e = cudaSuccess;
+  auto fail = [&](const char *what) {
+    set_error(nullptr, std::string("prep_run: ") + what + ": " + cudaGetErrorString(e));
+    cudaGetLastError();
+  };
+  for (auto &x : ev) if (e == cudaSuccess) e = cudaEventCreate(&x);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&d_xyz, 3 * (size_t)n * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&d_keep, ((size_t)n + 1) * sizeof(int));
+  if (e == cudaSuccess) e = cudaEventRecord(ev[0], 0);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_xyz, xyz, 3 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, 0);
+  if (e == cudaSuccess) e = cudaEventRecord(ev[1], 0);
+  int n_down = 0, n_kp = 0, rounds = 0;
+  if (e == cudaSuccess) e = prep_voxel_downsample(0, d_xyz, n, p->voxel_size, d_keep, &n_down);
+  if (e == cudaSuccess && n_down <= 0) e = cudaErrorInvalidValue;
+  if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_down, 3 * (size_t)n_down * sizeof(float));
+  if (e == cudaSuccess) e = prep_gather_points(0, d_xyz, d_keep, n_down, h->d_down);
+  if (e == cudaSuccess) e = cudaEventRecord(ev[2], 0);
+  if (e == cudaSuccess) { cudaFree(d_xyz); d_xyz = nullptr; cudaFree(d_keep); d_keep = nullptr; }
+  if (e == cudaSuccess) e = prep_bounds(0, h->d_down, n_down, h->bbox_min, h->bbox_max);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&d_lam, 3 * (size_t)n_down * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&d_curv, (size_t)n_down * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&d_cnt, (size_t)n_down * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&d_kpbuf, (size_t)n_down * sizeof(int));
+  if (e == cudaSuccess) e = prep_detect_keypoints(0, h->d_down, n_down, p->neighborhood_radius, p->ratio_max, p->min_pts, p->nms_radius,
+                                                  d_lam, d_curv, d_cnt, d_kpbuf, &n_kp, &rounds);
+  if (e == cudaSuccess) e = cudaEventRecord(ev[3], 0);
+  h->n_down = n_down; h->n_kp = n_kp;
+  if (e == cudaSuccess && n_kp > 0) {
+    e = cudaMalloc((void **)&h->d_kp, (size_t)n_kp * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h->d_kp, d_kpbuf, (size_t)n_kp * sizeof(int), cudaMemcpyDeviceToDevice, 0);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_kp_xyz, 3 * (size_t)n_kp * sizeof(double));
+    if (e == cudaSuccess) e = prep_kp_coords(0, h->d_down, h->d_kp, n_kp, h->d_kp_xyz);
+    if (e == cudaSuccess && want_bsc) {
+      h->V = p->dof_type > 4 ? 4 : (p->dof_type > 0 ? 2 : 1);
+      h->nbytes = (9 * side * side + 7) / 8;
+      e = cudaMalloc((void **)&h->d_bits, (size_t)h->V * n_kp * h->nbytes);
+      if (e == cudaSuccess) e = cudaMalloc((void **)&d_pairs, 2 * (size_t)side * side * sizeof(int));
+      if (e == cudaSuccess) e = cudaMalloc((void **)&d_lrf, 12 * (size_t)n_kp * sizeof(float));
+      if (e == cudaSuccess) e = cudaMalloc((void **)&d_status, (size_t)n_kp * sizeof(int));
+      if (e == cudaSuccess) e = cudaMemcpyAsync(d_pairs, bsc_pairs, 2 * (size_t)side * side * sizeof(int), cudaMemcpyHostToDevice, 0);
+      if (e == cudaSuccess) e = prep_bsc_extract(0, h->d_down, n_down, h->d_kp, n_kp, p->bsc_radius, side, d_pairs, p->dof_type, h->d_bits, d_lrf, d_status);
+    }
+  }
+  if (e == cudaSuccess) e = cudaEventRecord(ev[4], 0);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+  if (e == cudaSuccess) {
+    for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&h->stage_ms[k], ev[k], ev[k + 1]);
+    cudaEventElapsedTime(&h->stage_ms[4], ev[0], ev[4]);
+  }
+  for (auto &x : ev) if (x) cudaEventDestroy(x);
+  if (d_xyz) cudaFree(d_xyz);
+  if (d_keep) cudaFree(d_keep);
+  if (d_lam) cudaFree(d_lam);
+  if (d_curv) cudaFree(d_curv);
+  if (d_cnt) cudaFree(d_cnt);
+  if (d_kpbuf) cudaFree(d_kpbuf);
+  if (d_pairs) cudaFree(d_pairs);
+  if (d_lrf) cudaFree(d_lrf);
+  if (d_status) cudaFree(d_status);
+  if (e != cudaSuccess) { fail("pipeline"); ghicp_prep_destroy(h); return e == cudaErrorMemoryAllocation ? GHICP_E_NOMEM : GHICP_E_CUDA; }
+  *out = h;
+  return GHICP_OK;
+}
+
+int ghicp_prep_info(const ghicp_prep *h, int *n_down, int *n_kp, int *n_variants, float bbox_min[3], float bbox_max[3], float stage_ms[5]) {
+  if (!h) return GHICP_E_ARG;
+  if (n_down) *n_down = h->n_down;
+  if (n_kp) *n_kp = h->n_kp;
+  if (n_variants) *n_variants = h->V;
+  if (bbox_min) std::memcpy(bbox_min, h->bbox_min, sizeof(float) * 3);
+  if (bbox_max) std::memcpy(bbox_max, h->bbox_max, sizeof(float) * 3);
+  if (stage_ms) std::memcpy(stage_ms, h->stage_ms, sizeof(float) * 5);
+  return GHICP_OK;
+}
+
+int ghicp_prep_get(const ghicp_prep *h, float *down_xyz, int *kp_idx, double *kp_xyz, unsigned char *bsc_bits) {
+  if (!h) return GHICP_E_ARG;
+  if (cudaSetDevice(h->device) != cudaSuccess) return GHICP_E_CUDA;
+  cudaError_t e = cudaSuccess;
+  if (down_xyz && h->n_down > 0) e = cudaMemcpy(down_xyz, h->d_down, 3 * (size_t)h->n_down * sizeof(float), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && kp_idx && h->n_kp > 0) e = cudaMemcpy(kp_idx, h->d_kp, (size_t)h->n_kp * sizeof(int), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && kp_xyz && h->n_kp > 0) e = cudaMemcpy(kp_xyz, h->d_kp_xyz, 3 * (size_t)h->n_kp * sizeof(double), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && bsc_bits && h->d_bits) e = cudaMemcpy(bsc_bits, h->d_bits, (size_t)h->V * h->n_kp * h->nbytes, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) { set_error(nullptr, std::string("prep_get: ") + cudaGetErrorString(e)); return GHICP_E_CUDA; }
+  return GHICP_OK;
+}
+
+int ghicp_set_from_prep(ghicp_ctx *ctx, const ghicp_prep *src, const ghicp_prep *tgt) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !src || !tgt || src->n_kp <= 0 || tgt->n_kp <= 0) { set_error(c, "set_from_prep: bad argument or a cloud without keypoints"); return GHICP_E_ARG; }
+  if (src->device != c->device || tgt->device != c->device) { set_error(c, "set_from_prep: pipeline results live on another device"); return GHICP_E_ARG; }
+  int rc;
+  if ((rc = use_device(c))) return rc;
+  const int N = src->n_kp, M = tgt->n_kp;
+  if (N != c->N || M != c->M) {
+    c->N = N; c->M = M;
+    c->ldM = ((size_t)M + 63) / 64 * 64;
+    if ((rc = dev_alloc(c, &c->d_s, 3 * (size_t)N))) return rc;
+    if ((rc = dev_alloc(c, &c->d_t, 3 * (size_t)M))) return rc;
+    if ((rc = alloc_workspaces(c))) return rc;
+    c->have_bsc = c->have_fpfh = c->fd_built = false;
+    c->have_normals = false;
+    c->have_prev = false;
+    c->last_local_nnz = -1;
+    reset_loop_state(c);
+  }
+  CK(c, cudaMemcpyAsync(c->d_s, src->d_kp_xyz, 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  CK(c, cudaMemcpyAsync(c->d_t, tgt->d_kp_xyz, 3 * (size_t)M * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  {  // centre of the FP32 filter coordinates = target centroid (scalars only; the 24 M bytes read back are not re-uploaded)
+    std::vector<double> ht(3 * (size_t)M);
+    CK(c, cudaMemcpyAsync(ht.data(), tgt->d_kp_xyz, 3 * (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    double cx = 0, cy = 0, cz = 0;
+    for (int j = 0; j < M; ++j) { cx += ht[j]; cy += ht[(size_t)M + j]; cz += ht[2 * (size_t)M + j]; }
+    c->center[0] = cx / M; c->center[1] = cy / M; c->center[2] = cz / M;
+  }
+  if (c->cfg.feature_type == GHICP_FT_BSC) {
+    const int Vneed = (c->cfg.dof == 6) ? 4 : 2;
+    if (!src->d_bits || !tgt->d_bits || src->V < Vneed || src->nbytes != tgt->nbytes) {
+      set_error(c, "set_from_prep: BSC context needs descriptors (source with the context's dof variants, same length)");
+      return GHICP_E_ARG;
+    }
+    const int bits = 9 * src->side * src->side;
+    c->V = src->V; c->bits = bits;
+    c->Bbytes = src->nbytes;
+    c->W64 = (c->Bbytes + 7) / 8;
+    if ((rc = dev_alloc(c, &c->d_bs, (size_t)c->V * c->W64 * c->N))) return rc;
+    if ((rc = dev_alloc(c, &c->d_bt, (size_t)c->W64 * c->M))) return rc;
+    CK(c, launch_pack_bsc(c, src->d_bits, tgt->d_bits));   // the target's variant 0 = its first [M][B] block
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->have_bsc = true;
+    c->fd_built = false;
+  }
   return GHICP_OK;
 }
 

@@ -283,6 +283,11 @@ cudaError_t prep_detect_keypoints(cudaStream_t st, const float *d_xyz, int n, fl
 cudaError_t prep_bsc_extract(cudaStream_t st, const float *d_xyz, int n, const int *d_kp, int nkp, float R, int side,
                              const int *d_pairs, int dof_type, unsigned char *d_bits, float *d_lrf, int *d_status);
 
+// glue of the device-resident pipeline (ghicp_prep_run)
+cudaError_t prep_gather_points(cudaStream_t st, const float *d_xyz, const int *d_idx, int m, float *d_out);
+cudaError_t prep_kp_coords(cudaStream_t st, const float *d_xyz, const int *d_kp, int nkp, double *d_soa);
+cudaError_t prep_bounds(cudaStream_t st, const float *d_xyz, int n, float mn[3], float mx[3]);
+
 // ---- streaming path (ghicp_stream.cu) -----------------------------------------------------------
 cudaError_t launch_stream_prep(Ctx *c, const CostParams &cp, int for_km_gate);
 cudaError_t launch_stream_gate(Ctx *c, const CostParams &cp);

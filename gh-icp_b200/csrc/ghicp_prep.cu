@@ -494,6 +494,50 @@ done:
 }
 
 
+// ---- glue kernels of the device-resident pipeline (ghicp_prep_run, ghicp_capi.cu) --------------------------------------
+namespace {
+__global__ void k_gather_points(const float *__restrict__ xyz, const int *__restrict__ idx, int m, float *__restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m) return;
+  const size_t i = (size_t)idx[k];
+  out[3 * (size_t)k] = xyz[3 * i]; out[3 * (size_t)k + 1] = xyz[3 * i + 1]; out[3 * (size_t)k + 2] = xyz[3 * i + 2];
+}
+// keypoint coordinates as the reference holds them: Eigen::MatrixX3d, column-major = SoA [3][nkp], float32 values widened
+__global__ void k_kp_coords(const float *__restrict__ xyz, const int *__restrict__ kp, int nkp, double *__restrict__ soa) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nkp) return;
+  const size_t i = (size_t)kp[k];
+  soa[k] = (double)xyz[3 * i]; soa[(size_t)nkp + k] = (double)xyz[3 * i + 1]; soa[2 * (size_t)nkp + k] = (double)xyz[3 * i + 2];
+}
+}  // namespace
+cudaError_t prep_gather_points(cudaStream_t st, const float *d_xyz, const int *d_idx, int m, float *d_out) {
+  if (m <= 0) return cudaSuccess;
+  GHICP_LAUNCH(k_gather_points, blocks(m), PT, 0, st, d_xyz, d_idx, m, d_out);
+  return cudaSuccess;
+}
+cudaError_t prep_kp_coords(cudaStream_t st, const float *d_xyz, const int *d_kp, int nkp, double *d_soa) {
+  if (nkp <= 0) return cudaSuccess;
+  GHICP_LAUNCH(k_kp_coords, blocks(nkp), PT, 0, st, d_xyz, d_kp, nkp, d_soa);
+  return cudaSuccess;
+}
+// pcl::getMinMax3D of a device cloud (the bounding box the driver takes its bbx_magnitude from, test/ghicp_main.cpp:91-93)
+cudaError_t prep_bounds(cudaStream_t st, const float *d_xyz, int n, float mn[3], float mx[3]) {
+  cudaError_t err = cudaSuccess;
+  unsigned *d_box = nullptr; unsigned h_box[6];
+  if (n <= 0) return cudaErrorInvalidValue;
+  {
+    PCK(pmalloc(&d_box, 6));
+    const unsigned init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+    PCK(pcopy(d_box, init, sizeof(init), P_H2D, st));
+    GHICP_LAUNCH(k_bbox, n < 148 * 8 * PT ? blocks(n) : 148 * 8, PT, 0, st, d_xyz, (const int *)nullptr, n, d_box, d_box + 3);
+    PCK(pcopy(h_box, d_box, sizeof(h_box), P_D2H, st)); PCK(psync(st));
+    for (int a = 0; a < 3; ++a) { mn[a] = ord2f(h_box[a]); mx[a] = ord2f(h_box[3 + a]); }
+  }
+done:
+  pfree(d_box);
+  return err;
+}
+
 // =====================================================================================================================
 // BSC descriptor encoder: BSCEncoder::extractBinaryFeatures, include/binary_feature_extraction.hpp
 // :603-676 — per keypoint the weighted-PCA local frame (:940-1035, :123-160), the change of frame (:163-196, :1085-1138),

@@ -23,6 +23,29 @@ def register_clouds(target_xyz, source_xyz, resolution, neighborhood_radius, cur
                     dof_type=6, estimated_IoU=0.5, max_iter=0, device=0, bsc_pattern=None, **reg_kw):
     T = np.ascontiguousarray(target_xyz, dtype=np.float32)
     S = np.ascontiguousarray(source_xyz, dtype=np.float32)
+    if features is None:
+        # device-resident pipeline: each raw cloud is uploaded once, the stages chain on the GPU, the keypoint coordinates and
+        # descriptors go device-to-device into the registration context (ghicp_prep_run + ghicp_set_from_prep)
+        want_bsc = feature_type == capi.FT_BSC
+        radius = curvature_non_max_radius if want_bsc else 0.0
+        pt = capi.Prep(T, resolution, neighborhood_radius, curvature_non_max_radius, radius, 0, pairs=bsc_pattern, device=device)       # :89-115
+        ps = capi.Prep(S, resolution, neighborhood_radius, curvature_non_max_radius, radius, dof_type, pairs=bsc_pattern, device=device)  # :116
+        try:
+            for name, pr in (("target", pt), ("source", ps)):
+                if pr.n_kp == 0:
+                    raise capi.GhicpError(-1, f"no keypoints in the {name} cloud: check the radii")
+            bbx = ps.bbx_magnitude                                                       # getCloudBound, :91-93
+            Ef = Energyfunction().init(ps.n_kp, pt.n_kp, bbx)
+            reg = GHRegistration((ps, pt), Ef, feature_type, corr_type, curvature_non_max_radius, weight_adjustment_ratio,
+                                 weight_adjustment_step, dof_type, estimated_IoU, max_iter=max_iter, device=device, **reg_kw)
+            Rt, iterations = reg.ghicp_reg()
+            info = dict(iterations=iterations, n_target_down=pt.n_down, n_source_down=ps.n_down, n_target_kp=pt.n_kp,
+                        n_source_kp=ps.n_kp, bbx_magnitude=bbx, cor=len(reg.pairs()[0]),
+                        stage_ms=dict(target=pt.stage_ms, source=ps.stage_ms))
+            reg.close()
+        finally:
+            pt.close(); ps.close()
+        return Rt, info
     down, kp_idx = {}, {}
     for name, P in (("T", T), ("S", S)):
         keep = capi.voxel_downsample(P, resolution, device=device)                       # :89-90
@@ -33,15 +56,7 @@ def register_clouds(target_xyz, source_xyz, resolution, neighborhood_radius, cur
         down[name], kp_idx[name] = D, kp
     ext = down["S"].max(axis=0) - down["S"].min(axis=0)                                   # getCloudBound, :91-93
     bbx = float(np.float32(ext[0] + ext[1] + ext[2]))
-    if features is not None:
-        Kp = features(down["T"], kp_idx["T"], down["S"], kp_idx["S"])
-    elif feature_type == capi.FT_BSC:
-        bscT, _, _ = capi.bsc_extract(down["T"], kp_idx["T"], curvature_non_max_radius, 0, 7, bsc_pattern, device)        # :115
-        bscS, _, _ = capi.bsc_extract(down["S"], kp_idx["S"], curvature_non_max_radius, dof_type, 7, bsc_pattern, device)  # :116
-        Kp = Keypoints().setCoordinate(down["S"][kp_idx["S"]].astype(np.float64), down["T"][kp_idx["T"]].astype(np.float64))
-        Kp.setBSCfeature(bscS, bscT[0], 9 * 49)
-    else:
-        Kp = Keypoints().setCoordinate(down["S"][kp_idx["S"]].astype(np.float64), down["T"][kp_idx["T"]].astype(np.float64))
+    Kp = features(down["T"], kp_idx["T"], down["S"], kp_idx["S"])
     Ef = Energyfunction().init(Kp.kps_num, Kp.kpt_num, bbx)
     reg = GHRegistration(Kp, Ef, feature_type, corr_type, curvature_non_max_radius, weight_adjustment_ratio,
                          weight_adjustment_step, dof_type, estimated_IoU, max_iter=max_iter, device=device, **reg_kw)

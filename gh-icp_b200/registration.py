@@ -77,9 +77,14 @@ class GHRegistration:
             uid, rank, world = comm
             buf = (C.c_char * 128).from_buffer_copy(uid) if world > 1 else None
             capi.check(self.L.ghicp_comm_init(self.ctx, buf, rank, world), self.ctx)
-        self.N, self.M = Kp.kps_num, Kp.kpt_num
         self.Ft, self.Ct = Ft, Ct
-        self.upload(Kp)
+        if isinstance(Kp, tuple):   # (source Prep, target Prep): device-resident pipeline results, no host copy
+            src, tgt = Kp
+            self.N, self.M = src.n_kp, tgt.n_kp
+            capi.check(self.L.ghicp_set_from_prep(self.ctx, src.h, tgt.h), self.ctx)
+        else:
+            self.N, self.M = Kp.kps_num, Kp.kpt_num
+            self.upload(Kp)
         if target_normals is not None:
             self.set_target_normals(target_normals)
         self.history = []

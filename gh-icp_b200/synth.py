@@ -119,3 +119,73 @@ def rot_angle(Ra, Rb):
     D = Ra @ Rb.T
     sk = 0.5 * np.array([D[2, 1] - D[1, 2], D[0, 2] - D[2, 0], D[1, 0] - D[0, 1]])
     return math.atan2(np.linalg.norm(sk), 0.5 * (np.trace(D) - 1.0))
+
+
+# ---- raw scans (BASELINE.json configs 4 / 5: the input of the pre-processing pipeline) ---------------------------------
+def scan_world(n, seed, extent):
+    """A crude street scene of n points over extent = (Lx, Ly, H): ground, wall segments, poles, boxes, clutter (float64).
+    Surface density stays the same when n and the area grow together; the structures repeat over the area so that curvature
+    keypoints occur everywhere."""
+    rng = np.random.default_rng(seed)
+    Lx, Ly, H = (float(v) for v in extent)
+    area = Lx * Ly
+    n_ground, n_wall, n_pole, n_box = int(0.40 * n), int(0.25 * n), int(0.08 * n), int(0.12 * n)
+    n_clutter = n - n_ground - n_wall - n_pole - n_box
+    parts = []
+    g = np.empty((n_ground, 3)); g[:, 0] = rng.random(n_ground) * Lx; g[:, 1] = rng.random(n_ground) * Ly
+    g[:, 2] = 0.02 * rng.standard_normal(n_ground)
+    parts.append(g)
+    n_walls = max(2, int(area / 250.0))
+    per = np.full(n_walls, n_wall // n_walls); per[: n_wall - per.sum()] += 1
+    for k in range(n_walls):
+        m = int(per[k]); w = np.empty((m, 3))
+        length, height = 8.0 + 10.0 * rng.random(), 2.5 + 2.5 * rng.random()
+        x0, y0 = rng.random() * (Lx - length), rng.random() * (Ly - length)
+        u = rng.random(m) * length
+        if k % 2 == 0:
+            w[:, 0] = x0 + u; w[:, 1] = y0 + 0.02 * rng.standard_normal(m)
+        else:
+            w[:, 0] = x0 + 0.02 * rng.standard_normal(m); w[:, 1] = y0 + u
+        w[:, 2] = rng.random(m) * height
+        parts.append(w)
+    n_poles = max(2, int(area / 80.0))
+    per = np.full(n_poles, n_pole // n_poles); per[: n_pole - per.sum()] += 1
+    for k in range(n_poles):
+        m = int(per[k]); p = np.empty((m, 3))
+        p[:, 0] = rng.random() * Lx + 0.02 * rng.standard_normal(m); p[:, 1] = rng.random() * Ly + 0.02 * rng.standard_normal(m)
+        p[:, 2] = rng.random(m) * (2.0 + 3.0 * rng.random())
+        parts.append(p)
+    n_boxes = max(2, int(area / 150.0))
+    per = np.full(n_boxes, n_box // n_boxes); per[: n_box - per.sum()] += 1
+    for k in range(n_boxes):
+        m = int(per[k]); b = np.empty((m, 3))
+        sx, sy, sz = 1.0 + 2.0 * rng.random(), 1.0 + 2.0 * rng.random(), 0.8 + 1.5 * rng.random()
+        x0, y0 = rng.random() * (Lx - sx), rng.random() * (Ly - sy)
+        face = rng.integers(0, 5, m)
+        u, v = rng.random(m), rng.random(m)
+        b[:, 0] = x0 + np.where(face == 0, 0.0, np.where(face == 1, sx, u * sx))
+        b[:, 1] = y0 + np.where(face == 2, 0.0, np.where(face == 3, sy, np.where(face == 4, v * sy, v * sy)))
+        b[:, 2] = np.where(face == 4, sz, np.where(face < 2, v * sz, u * sz))
+        b += 0.01 * rng.standard_normal((m, 3))
+        parts.append(b)
+    c = rng.random((n_clutter, 3)) * np.array([Lx, Ly, H])
+    parts.append(c)
+    return np.concatenate(parts, axis=0)
+
+
+def scan_pair(n_points, overlap=0.6, seed=4, density=280.0, height=6.0, R_gt=None, t_gt=(0.6, -0.4, 0.1), noise=0.01):
+    """Two raw scans of n_points each (float32 [n][3]) cut from one world with the given overlap ratio along x, the source
+    expressed in its own frame: R_gt s + t_gt lands on the target.  Returns (target, source, R_gt, t_gt)."""
+    rng = np.random.default_rng(seed + 1000)
+    if R_gt is None:
+        R_gt = rot_xyz_deg(0.4, -0.3, 2.0)
+    t_gt = np.asarray(t_gt, dtype=np.float64)
+    area = n_points / density                      # m^2 per scan
+    ly = math.sqrt(area / 1.5); lx = 1.5 * ly       # each scan covers lx x ly
+    Lx = (2.0 - overlap) * lx
+    W = scan_world(int(round(n_points * (2.0 - overlap))), seed, (Lx, ly, height))
+    tgt = W[W[:, 0] < lx]
+    src = W[W[:, 0] >= (1.0 - overlap) * lx]
+    rng.shuffle(tgt, axis=0); rng.shuffle(src, axis=0)
+    src = (src - t_gt) @ R_gt + rng.normal(0.0, noise, size=src.shape)     # row form of R_gt^T (p - t_gt)
+    return tgt.astype(np.float32), src.astype(np.float32), R_gt, t_gt

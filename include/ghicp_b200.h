@@ -212,6 +212,34 @@ int ghicp_bsc_extract(int device, const float *xyz, int n, const int *kp_idx, in
 /* the pattern the reference's constructor generates (:75-103) in a fresh process; pairs [49][2]; voxel_side_num must be 7 */
 int ghicp_bsc_default_pattern(int voxel_side_num, int *pairs);
 
+/* ---- device-resident pre-processing pipeline (BASELINE.json configs 4 / 5) --------------------------------------------
+ * The reference's driver runs, per cloud, voxel filter -> curvature keypoints -> BSC encoder (test/ghicp_main.cpp:89-116)
+ * and hands the keypoint coordinates + descriptors to GHRegistration (:143-151).  ghicp_prep_run uploads the raw cloud ONCE
+ * and chains the three stages on the device (each stage = the stand-alone entry point above, same results bit for bit);
+ * nothing but the keypoint set ever needs to come back, and ghicp_set_from_prep moves even that device to device.
+ * stage_ms [5] = {host->device copy, voxel filter, keypoints, BSC encoder, total} from CUDA events. */
+typedef struct ghicp_prep_params {
+  float voxel_size;           /* CFilter::voxelfilter resolution (:89-90) */
+  float neighborhood_radius;  /* PCA radius (:96) */
+  float ratio_max;            /* 0.65 (:96) */
+  int min_pts;                /* 20   (:97) */
+  float nms_radius;           /* curvature non-maximum suppression radius (:97) */
+  float bsc_radius;           /* BSC extract radius (:113-116: the NMS radius); <= 0: no descriptors */
+  int bsc_side;               /* 7 */
+  int dof_type;               /* BSC variants: 0 -> 1 (target, :115), 1..4 -> 2, > 4 -> 4 (source, :116) */
+} ghicp_prep_params;
+typedef struct ghicp_prep ghicp_prep;
+int ghicp_prep_run(int device, const float *xyz, int n, const ghicp_prep_params *p, const int *bsc_pairs, ghicp_prep **out);
+int ghicp_prep_info(const ghicp_prep *h, int *n_down, int *n_kp, int *n_variants, float bbox_min[3], float bbox_max[3],
+                    float stage_ms[5]);
+/* any of the outputs may be NULL: down_xyz [n_down][3], kp_idx [n_kp] (into the down-sampled cloud), kp_xyz [3][n_kp]
+ * doubles (Eigen::MatrixX3d layout), bsc_bits [V][n_kp][ceil(9 side^2 / 8)] */
+int ghicp_prep_get(const ghicp_prep *h, float *down_xyz, int *kp_idx, double *kp_xyz, unsigned char *bsc_bits);
+int ghicp_prep_destroy(ghicp_prep *h);
+/* Keypoints::setCoordinate + setBSCfeature (include/ghicp_reg.h:52-60) straight from two pipeline results on the same
+ * device (descriptors only when the context's feature type is BSC): no host copy of coordinates or descriptors. */
+int ghicp_set_from_prep(ghicp_ctx *ctx, const ghicp_prep *source, const ghicp_prep *target);
+
 /* ---- multi-GPU (one process per GPU; source rows sharded, target replicated) ---------------- */
 /* 128-byte NCCL unique id; rank 0 creates it, the host runtime broadcasts it (torch.distributed,
  * MPI, a file ...). No NCCL symbol is touched unless these are called (world == 1 → never). */

@@ -116,3 +116,42 @@ def test_python_pipeline_helper(g, orc):
     assert g.synth.rot_angle(Rt[:3, :3], Ro[:3, :3]) < 1e-4 and np.linalg.norm(Rt[:3, 3] - Ro[:3, 3]) < 1e-3
     moved = g.pipeline.transform_cloud(S, Rt)
     assert moved.shape == S.shape and moved.dtype == np.float32
+
+
+def test_device_resident_pipeline_equals_stage_by_stage(g, orc):
+    """ghicp_prep_run (raw cloud uploaded once, voxel filter -> keypoints -> BSC chained on the device) returns exactly what the
+    stand-alone entry points return stage by stage, and ghicp_set_from_prep (device to device) starts the same registration as
+    the host-buffer route."""
+    T = scan_like_cloud(60000, 41, extent=(30.0, 30.0, 5.0))
+    R = g.synth.rot_xyz_deg(0.4, -0.2, 1.2)
+    S = ((T.astype(np.float64) - [0.25, -0.15, 0.05]) @ R).astype(np.float32)
+    preps = {}
+    for name, P, dof in (("T", T, 0), ("S", S, 6)):
+        pr = g.Prep(P, 0.2, 0.8, 1.5, bsc_radius=1.5, dof_type=dof)
+        keep = g.voxel_downsample(P, 0.2)
+        D = np.ascontiguousarray(P[keep])
+        kp, _, _, _ = g.detect_keypoints(D, 0.8, 0.65, 20, 1.5)
+        bits, _, _ = g.bsc_extract(D, kp, 1.5, dof)
+        assert pr.n_down == len(D) and np.array_equal(pr.down(), D)
+        idx, xyz = pr.keypoints()
+        assert np.array_equal(idx, kp) and np.array_equal(xyz, D[kp].astype(np.float64))
+        assert np.array_equal(pr.bsc(), bits)
+        ext = D.max(axis=0) - D.min(axis=0)
+        assert pr.bbx_magnitude == float(np.float32(ext[0] + ext[1] + ext[2]))
+        assert pr.stage_ms["total"] >= 0 and (pr.stage_ms["total"] > 0 or __import__("os").environ.get("GHICP_TEST_EMULATED_ABI"))
+        preps[name] = (pr, D, kp, bits)
+    ps, pt = preps["S"][0], preps["T"][0]
+    assert ps.n_kp >= 20 and pt.n_kp >= 20
+    Ef = g.Energyfunction().init(ps.n_kp, pt.n_kp, ps.bbx_magnitude)
+    a = g.GHRegistration((ps, pt), Ef, g.FT_BSC, g.CT_NN, max_iter=30)
+    Kp = g.Keypoints().setCoordinate(preps["S"][1][preps["S"][2]].astype(np.float64), preps["T"][1][preps["T"][2]].astype(np.float64))
+    Kp.setBSCfeature(preps["S"][3], preps["T"][3][0], 441)
+    b = g.GHRegistration(Kp, Ef, g.FT_BSC, g.CT_NN, max_iter=30)
+    assert np.array_equal(a.fd(), b.fd())
+    for _ in range(6):
+        sa, sb = a.iterate(), b.iterate()
+        assert np.array_equal(a.pairs()[0], b.pairs()[0]) and np.array_equal(a.pairs()[1], b.pairs()[1])
+        assert sa.penalty == sb.penalty
+        if sa.converged:
+            break
+    a.close(); b.close(); ps.close(); pt.close()

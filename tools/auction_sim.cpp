@@ -201,6 +201,59 @@ struct Auction {
       ++rounds;
     }
   }
+  // SYMMETRIC formulation (what the reference's padded n x n matrix is): every person can take EVERY object, non-candidate
+  // objects at gain 0; all objects end up assigned, so there is no dummy, no free object and no reverse phase.
+  // Jacobi rounds; a bidder looks at all O objects (the model does it by brute force; a kernel would use the candidate list
+  // plus the globally cheapest objects).
+  void forward_sym(std::vector<int> act, double eps, ll max_rounds = 100000000) {
+    std::vector<int> bid_obj(P), next;
+    std::vector<double> bid_val(P), bid_gain(P);
+    std::vector<uint64_t> bidmax(O, 0);
+    ll rounds = 0;
+    while (!act.empty() && rounds < max_rounds) {
+      ll edges = 0;
+      const int n = (int)act.size();
+#pragma omp parallel reduction(+ : edges)
+      {
+        std::vector<double> gg(O, 0.0);
+#pragma omp for schedule(dynamic, 16)
+        for (int a = 0; a < n; ++a) {
+          const int i = act[a];
+          for (ll k = rp[i]; k < rp[i + 1]; ++k) gg[col[k]] = g[k];
+          double best = -1e300, second = -1e300, bg = 0; int bi = -1;
+          for (int j = 0; j < O; ++j) {
+            const double v = gg[j] - price[j];
+            if (v > best || (v == best && bi >= 0 && tie_less(i, j, bi))) { second = best; best = v; bi = j; bg = gg[j]; }
+            else if (v > second) second = v;
+          }
+          for (ll k = rp[i]; k < rp[i + 1]; ++k) gg[col[k]] = 0.0;
+          edges += rp[i + 1] - rp[i];
+          bid_obj[i] = bi; bid_val[i] = price[bi] + (best - second) + eps; bid_gain[i] = bg;
+        }
+      }
+      for (int a = 0; a < n; ++a) {
+        const int i = act[a];
+        float f = (float)bid_val[i]; uint32_t fb; memcpy(&fb, &f, 4);
+        uint64_t key = ((uint64_t)fb << 32) | (uint32_t)(i + 1);
+        if (key > bidmax[bid_obj[i]]) bidmax[bid_obj[i]] = key;
+      }
+      next.clear();
+      for (int a = 0; a < n; ++a) {
+        const int i = act[a];
+        const int j = bid_obj[i];
+        if ((int)(bidmax[j] & 0xffffffffu) - 1 == i) {
+          const int prev = owner[j];
+          owner[j] = i; price[j] = bid_val[i]; assign[i] = j; profit[i] = bid_gain[i] - bid_val[i];
+          if (prev >= 0) { assign[prev] = -1; next.push_back(prev); }
+        } else next.push_back(i);
+      }
+      for (int a = 0; a < n; ++a) bidmax[bid_obj[act[a]]] = 0;
+      account(fwd, n, edges, small_fwd);
+      if (getenv("HIST")) fprintf(stderr, "%d ", n);
+      act.swap(next);
+      ++rounds;
+    }
+  }
   double free_price_sum() const { double D = 0; for (int j = 0; j < O; ++j) if (owner[j] < 0) D += price[j]; return D; }
 
   // reverse phase: free objects with positive price lower their price / attract persons
@@ -246,6 +299,7 @@ struct Auction {
       }
       for (int a = 0; a < n; ++a) if (bid_obj[act[a]] >= 0) bidmax[bid_obj[act[a]]] = 0;
       account(rev, n, edges, small_rev);
+      if (getenv("HISTR")) fprintf(stderr, "R%d ", n);
       act.swap(next);
       ++rounds;
     }
@@ -319,8 +373,8 @@ static std::vector<double> schedule(double e0, double div, double eps_last) {
 
 static void report(const char *name, const Auction &A, double gain, double D, double wall) {
   Stats t = A.fwd; t.add(A.rev);
-  printf("%-34s gain %.3f  D %.1f | fwd rounds %lld (grid %lld) rev rounds %lld (grid %lld) | bids %lld edges %.3g | est %.2f ms  [cpu %.1fs]\n",
-         name, gain, D, A.fwd.rounds, A.fwd.grid_rounds, A.rev.rounds, A.rev.grid_rounds, t.bids, (double)t.edges, t.est_us * 1e-3, wall);
+  printf("%-34s gain %.3f  D %.1f | fwd rounds %lld (grid %lld) rev rounds %lld (grid %lld) | rev bids %lld rev edges %.3g | bids %lld edges %.3g | est %.2f ms  [cpu %.1fs]\n",
+         name, gain, D, A.fwd.rounds, A.fwd.grid_rounds, A.rev.rounds, A.rev.grid_rounds, A.rev.bids, (double)A.rev.edges, t.bids, (double)t.edges, t.est_us * 1e-3, wall);
   fflush(stdout);
 }
 
@@ -356,6 +410,20 @@ int main(int argc, char **argv) {
       double D = A.free_price_sum();
       if (D > 0.5 * KM_eps * N) A.reverse(0.5 * KM_eps);
       report(mode.c_str(), A, A.total_gain(), D, tnow() - t0);
+    } else if (mode.rfind("sym", 0) == 0) {
+      // symmetric formulation + forward eps-scaling only.  sym[=e0[,div]]
+      double e0 = I.penalty / 4.0, div = 5.0;
+      if (mode.size() > 4) { e0 = atof(mode.c_str() + 4); const char *c = strchr(mode.c_str(), ','); if (c) div = atof(c + 1); }
+      Auction A = mk();
+      auto eps = schedule(e0, div, KM_eps * 0.999);   // no D term: the whole n*eps budget goes to eps
+      std::vector<int> all(N); for (int i = 0; i < N; ++i) all[i] = i;
+      for (size_t ph = 0; ph < eps.size(); ++ph) {
+        std::fill(A.owner.begin(), A.owner.end(), -1); std::fill(A.assign.begin(), A.assign.end(), -1);
+        ll r0 = A.fwd.rounds, b0 = A.fwd.bids;
+        A.forward_sym(all, eps[ph]);
+        fprintf(stderr, "  sym phase %zu eps %.4f: %lld rounds %lld bids, gain %.1f\n", ph, eps[ph], A.fwd.rounds - r0, A.fwd.bids - b0, A.total_gain());
+      }
+      report(mode.c_str(), A, A.total_gain(), 0.0, tnow() - t0);
     } else if (mode.rfind("warm", 0) == 0) {
       // warm start across ICP iterations: solve THIS iteration's instance with the shipped schedule, then the NEXT iteration's
       // instance (same descriptors and geometry, new metric weights / penalty) starting from those prices scaled by the ratio
