@@ -96,7 +96,21 @@ struct AucArgs {
   int *counters;  // [0],[1]: ping-pong list sizes, [2]: base list size
   double eps;
   int profile;    // GHICP_AUCTION_DEBUG: per-size-class timing of the tail rounds into counters[16..31]
+  // Reverse phase: stop as soon as D = sum of the prices of the objects still free (= the active list) fits the budget.
+  // Dual eps-feasibility (profit_i + price_j >= g_ij - eps on every edge, equality on matched pairs) is an invariant of
+  // the reverse rounds, so OPT - ours <= n*eps + D holds at EVERY round boundary: the rest of the displacement chains
+  // (thousands of rounds with a handful of bidders each) need not be followed.  D is kept in 2^-20 fixed point
+  // (integer adds: the same value on every rank and run whatever order the atomics land in), each price rounded up.
+  unsigned long long d_budget_fx;   // 0 = no early stop
 };
+constexpr double D_FX = 1048576.0;
+__device__ __forceinline__ unsigned long long d_fx(double p) { return p > 0.0 ? (unsigned long long)(p * D_FX) + 1ull : 0ull; }
+// counters (int[64]): [0],[1] list sizes, [2] base list size, [3] sticky round-limit flag, [4] cur, [5] rounds, [6] rounds
+// of the whole solve, [8..9] bids (u64), [10] grid rounds, [12..13] / [14..15] ns in tail / grid rounds, [16..31] tail
+// profile, [32..33] / [34..35] D of list 0 / 1 (u64 fixed point), [36] 1 = the reverse phase stopped on the D budget
+__device__ __forceinline__ unsigned long long *d_slot(int *counters, int which) {
+  return reinterpret_cast<unsigned long long *>(&counters[32 + 2 * which]);
+}
 
 __global__ void k_auc_init(int n_rows, int n_cols, const long long *rowptr, int n_chunks, double *price,
                            int *base_list, int *counters, unsigned long long *bidmax, int *bidwin, int nmax) {
@@ -133,17 +147,20 @@ __global__ void k_auc_phase_start(int n_rows, int n_cols, const long long *rowpt
 // ---- reverse round -------------------------------------------------------------------------------
 // D = sum of the prices of objects left free: the exact amount by which complementary slackness is violated,
 // i.e. the extra term of the optimality bound  OPT - ours <= |M*| * eps + D
-__global__ void k_free_price_sum(int n_cols, const int *owner, const double *price, double *out) {
-  double v = 0.0;
+__global__ void k_free_price_sum(int n_cols, const int *owner, const double *price, unsigned long long *out) {
+  unsigned long long v = 0ull;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_cols; j += gridDim.x * blockDim.x)
-    if (owner[j] < 0) v += price[j];
+    if (owner[j] < 0) v += d_fx(price[j]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(out, v);
+  if ((threadIdx.x & 31) == 0 && v != 0ull) atomicAdd(out, v);
 }
 __global__ void k_rev_collect(int n_cols, const int *owner, const double *price, int *list, int *counters, int cur) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < n_cols && owner[j] < 0 && price[j] > 0.0) list[atomicAdd(&counters[cur], 1)] = j;
+  if (j < n_cols && owner[j] < 0 && price[j] > 0.0) {
+    list[atomicAdd(&counters[cur], 1)] = j;
+    atomicAdd(d_slot(counters, cur), d_fx(price[j]));
+  }
 }
 
 
@@ -245,9 +262,9 @@ __device__ __forceinline__ void fwd_commit_one(const AucArgs &a, int i, Append a
     __stcg(&a.assign[i], j);
     __stcg(&a.profit[i], ldcg_d(&a.bid_aux[i]) - bv);
     __stcg(&a.bidmax[j], 0ull);  // slot back to "no bid" (a loser reading 0 or the key sees "not me" either way)
-    if (prev >= 0) { __stcg(&a.assign[prev], UNASSIGNED); append(prev); }
+    if (prev >= 0) { __stcg(&a.assign[prev], UNASSIGNED); append(prev, 0.0); }
   } else {
-    append(i);
+    append(i, 0.0);
   }
 }
 
@@ -309,27 +326,65 @@ __device__ __forceinline__ void rev_commit_one(const AucArgs &a, int j, Append a
     __stcg(&a.bidmax[i], 0ull);
     if (old >= 0) {
       __stcg(&a.owner[old], -1);
-      if (ldcg_d(&a.price[old]) > 0.0) append(old);
+      const double po = ldcg_d(&a.price[old]);
+      if (po > 0.0) append(old, po);
     }
   } else {
-    append(j);
+    append(j, ldcg_d(&a.price[j]));
   }
 }
 
-// counters: [0],[1] list sizes, [2] base list size, [4] cur after the kernel, [5] rounds executed
+// scan slice `slice` of G of the adjacency list of bidder e (warp-cooperative)
+template <bool REVERSE>
+__device__ __forceinline__ void split_scan(const AucArgs &a, int e, int G, int slice, int lane, Top2 &t, double &bg) {
+  long long b, en;
+  if (REVERSE) { b = a.colptr[e]; en = a.colptr[e + 1]; }
+  else { b = a.rowptr[(size_t)e * a.n_chunks]; en = a.rowptr[(size_t)(e + 1) * a.n_chunks]; }
+  const long long len = en - b;
+  bg = 0.0;
+  if (REVERSE) rev_scan(a, e, lane, b + len * slice / G, b + len * (slice + 1) / G, t);
+  else fwd_scan(a, e, lane, b + len * slice / G, b + len * (slice + 1) / G, t, bg);
+}
+// merge the G partial results pt[0..G) of bidder e (the result does not depend on how the list was split:
+// best value, the tie-order-preferred index among the options of that value, second-best value)
+__device__ __forceinline__ void split_merge(int e, int G, const Top2 *pt, const double *pg, Top2 &t, double &bg) {
+  t = pt[0]; bg = pg[0];
+  for (int q = 1; q < G; ++q) {
+    const Top2 o = pt[q];
+    if (o.idx < 0) continue;
+    if (t.idx < 0) { t = o; bg = pg[q]; continue; }
+    if (o.best > t.best || (o.best == t.best && tie_less(e, o.idx, t.idx))) bg = pg[q];
+    top2_merge_h(t, o.best, o.idx, o.second, e);
+  }
+}
+
 template <bool REVERSE>
 __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a, int *list0, int *list1, int max_rounds,
                                                                       int small_n) {
   cg::grid_group grid = cg::this_grid();
+  constexpr int NW = PA_THREADS / 32;
   __shared__ int s_n, s_next;
-  __shared__ Top2 s_pt[PA_THREADS / 32];
-  __shared__ double s_pg[PA_THREADS / 32];
+  __shared__ unsigned long long s_D, s_Dnext;
+#if defined(GHICP_EMU_HOST)
+  // the emulation shim maps __shared__ to ONE static per kernel; the split scans use these arrays in every block of the
+  // (2-block) emulated grid at once, so each block gets its own copy there
+  static Top2 s_pt_emu[4][NW];
+  static double s_pg_emu[4][NW];
+  Top2 *const s_pt = s_pt_emu[blockIdx.x & 3];
+  double *const s_pg = s_pg_emu[blockIdx.x & 3];
+#else
+  __shared__ Top2 s_pt[NW];
+  __shared__ double s_pg[NW];
+#endif
   int *lists[2] = {list0, list1};
   const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
   const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int gwarps = (gridDim.x * blockDim.x) >> 5;
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const int gthreads = gridDim.x * blockDim.x;
+  const bool cut_on = REVERSE && a.d_budget_fx != 0ull;
+  bool cut = false;
   int cur = 0, rounds = 0;
   unsigned long long t_mark = 0, t_prev = 0;
   int b_prev = 0;
@@ -341,52 +396,43 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
   while (true) {
     const int n = ldcg_i(&a.counters[cur]);
     if (n == 0 || rounds >= max_rounds) break;
+    // every thread of the grid reads the same D (written before the last grid barrier): a uniform decision
+    if (cut_on && __ldcg(d_slot(a.counters, cur)) <= a.d_budget_fx) { cut = true; break; }
     if (gtid == 0) t_mark = now_ns();
     if (n <= small_n) {
       // ---- tail: CTA 0 alone, block-level barriers only
       if (blockIdx.x == 0) {
-        if (threadIdx.x == 0) s_n = n;
+        if (threadIdx.x == 0) { s_n = n; s_D = __ldcg(d_slot(a.counters, cur)); }
         __syncthreads();
         while (true) {
           const int m = s_n;
           if (m == 0 || m > small_n || rounds >= max_rounds) break;
+          if (cut_on && s_D <= a.d_budget_fx) break;   // the outer loop re-reads the same D and stops
           const int *list = lists[cur];
           int *next = lists[cur ^ 1];
           if (threadIdx.x == 0) {
-            s_next = 0; atomicAdd((unsigned long long *)&a.counters[8], (unsigned long long)m);
+            s_next = 0; s_Dnext = 0ull; atomicAdd((unsigned long long *)&a.counters[8], (unsigned long long)m);
             if (a.profile) {   // GHICP_AUCTION_DEBUG: time and rounds per active-set size class
               const unsigned long long tn = now_ns();
               if (t_prev) { atomicAdd((unsigned long long *)&a.counters[16 + 2 * b_prev], tn - t_prev); atomicAdd((unsigned long long *)&a.counters[24 + 2 * b_prev], 1ull); }
               t_prev = tn; b_prev = m == 1 ? 0 : (m <= 16 ? 1 : (m <= 64 ? 2 : 3));
             }
           }
-          constexpr int NW = PA_THREADS / 32;
           if (m <= NW / 2) {
             // very few bidders: split every adjacency list over G warps so one round costs one short scan
             const int G = NW / m;
-            const int warp = threadIdx.x >> 5, bidder = warp / G, slice = warp % G;
+            const int bidder = warp / G, slice = warp % G;
+            int i = -1;
             if (bidder < m) {
-              const int i = ldcg_i(&list[bidder]);
-              long long b, e;
-              if (REVERSE) { b = a.colptr[i]; e = a.colptr[i + 1]; }
-              else { b = a.rowptr[(size_t)i * a.n_chunks]; e = a.rowptr[(size_t)(i + 1) * a.n_chunks]; }
-              const long long len = e - b;
-              Top2 t; double bg = 0.0;
-              if (REVERSE) rev_scan(a, i, lane, b + len * slice / G, b + len * (slice + 1) / G, t);
-              else fwd_scan(a, i, lane, b + len * slice / G, b + len * (slice + 1) / G, t, bg);
+              i = ldcg_i(&list[bidder]);
+              Top2 t; double bg;
+              split_scan<REVERSE>(a, i, G, slice, lane, t, bg);
               if (lane == 0) { s_pt[warp] = t; s_pg[warp] = bg; }
             }
             __syncthreads();
             if (bidder < m && slice == 0 && lane == 0) {
-              const int i = ldcg_i(&list[bidder]);
-              Top2 t = s_pt[warp]; double bg = s_pg[warp];
-              for (int q = 1; q < G; ++q) {
-                const Top2 o = s_pt[warp + q];
-                if (o.idx < 0) continue;
-                if (t.idx < 0) { t = o; bg = s_pg[warp + q]; continue; }
-                if (o.best > t.best || (o.best == t.best && tie_less(i, o.idx, t.idx))) bg = s_pg[warp + q];
-                top2_merge_h(t, o.best, o.idx, o.second, i);
-              }
+              Top2 t; double bg;
+              split_merge(i, G, &s_pt[warp], &s_pg[warp], t, bg);
               if (m == 1) {
                 // a single bidder cannot lose: bid and commit in one step (no key atomics, no second pass).
                 // This is the common case of the tail: one displacement chain advancing one step per round.
@@ -418,7 +464,8 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
                     __stcg(&a.profit[who], ldcg_d(&a.profit[who]) + delta);
                     if (old >= 0) {
                       __stcg(&a.owner[old], -1);
-                      if (ldcg_d(&a.price[old]) > 0.0) { __stcg(&next[0], old); s_next = 1; }
+                      const double po = ldcg_d(&a.price[old]);
+                      if (po > 0.0) { __stcg(&next[0], old); s_next = 1; s_Dnext = d_fx(po); }
                     }
                   }
                 }
@@ -428,12 +475,12 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
               __syncthreads();
               cur ^= 1;
               ++rounds;
-              if (threadIdx.x == 0) s_n = s_next;
+              if (threadIdx.x == 0) { s_n = s_next; s_D = s_Dnext; }
               __syncthreads();
               continue;
             }
           } else {
-            for (int w = threadIdx.x >> 5; w < m; w += NW) {
+            for (int w = warp; w < m; w += NW) {
               const int e = ldcg_i(&list[w]);
               if (REVERSE) rev_offer_one(a, e, lane); else fwd_bid_one(a, e, lane);
             }
@@ -441,17 +488,21 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
           __syncthreads();
           for (int w = threadIdx.x; w < m; w += PA_THREADS) {
             const int e = ldcg_i(&list[w]);
-            auto app = [&](int x) { __stcg(&next[atomicAdd(&s_next, 1)], x); };
+            auto app = [&](int x, double p) {
+              __stcg(&next[atomicAdd(&s_next, 1)], x);
+              if (REVERSE) atomicAdd(&s_Dnext, d_fx(p));
+            };
             if (REVERSE) rev_commit_one(a, e, app); else fwd_commit_one(a, e, app);
           }
           __syncthreads();
           cur ^= 1;
           ++rounds;
-          if (threadIdx.x == 0) s_n = s_next;
+          if (threadIdx.x == 0) { s_n = s_next; s_D = s_Dnext; }
           __syncthreads();
         }
         if (threadIdx.x == 0) {
           __stcg(&a.counters[cur], s_n);
+          __stcg(d_slot(a.counters, cur), s_D);
           __stcg(&a.counters[4], cur);
           __stcg(&a.counters[5], rounds);
         }
@@ -466,16 +517,47 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
     // ---- full-grid round
     const int *list = lists[cur];
     int *next = lists[cur ^ 1];
-    if (gtid == 0) { __stcg(&a.counters[cur ^ 1], 0); atomicAdd((unsigned long long *)&a.counters[8], (unsigned long long)n); __stcg(&a.counters[10], ldcg_i(&a.counters[10]) + 1); }
-    for (int w = gwarp; w < n; w += gwarps) {
-      const int e = ldcg_i(&list[w]);
-      if (REVERSE) rev_offer_one(a, e, lane); else fwd_bid_one(a, e, lane);
+    if (gtid == 0) {
+      __stcg(&a.counters[cur ^ 1], 0); __stcg(d_slot(a.counters, cur ^ 1), 0ull);
+      atomicAdd((unsigned long long *)&a.counters[8], (unsigned long long)n); __stcg(&a.counters[10], ldcg_i(&a.counters[10]) + 1);
+    }
+    // warps per bidder: as many as the grid affords, so that a round with few bidders and long adjacency lists (the
+    // dense first iterations: ~1400 candidates per keypoint) costs one short scan per warp instead of one long one
+    int G = 1;
+    {
+      const long long tw = (long long)gridDim.x * NW;
+      if (16ll * n <= tw) G = 16; else if (8ll * n <= tw) G = 8; else if (4ll * n <= tw) G = 4; else if (2ll * n <= tw) G = 2;
+    }
+    if (G > 1) {
+      const int gpc = NW / G, grp = warp / G, slice = warp % G;
+      const int w = blockIdx.x * gpc + grp;   // n <= gridDim.x * gpc by the choice of G
+      int e = -1;
+      if (w < n) {
+        e = ldcg_i(&list[w]);
+        Top2 t; double bg;
+        split_scan<REVERSE>(a, e, G, slice, lane, t, bg);
+        if (lane == 0) { s_pt[warp] = t; s_pg[warp] = bg; }
+      }
+      __syncthreads();
+      if (w < n && slice == 0 && lane == 0) {
+        Top2 t; double bg;
+        split_merge(e, G, &s_pt[warp], &s_pg[warp], t, bg);
+        if (REVERSE) rev_finish(a, e, t); else fwd_finish(a, e, t, bg);
+      }
+    } else {
+      for (int w = gwarp; w < n; w += gwarps) {
+        const int e = ldcg_i(&list[w]);
+        if (REVERSE) rev_offer_one(a, e, lane); else fwd_bid_one(a, e, lane);
+      }
     }
     __threadfence();
     grid.sync();
     for (int w = gtid; w < n; w += gthreads) {
       const int e = ldcg_i(&list[w]);
-      auto app = [&](int x) { __stcg(&next[atomicAdd(&a.counters[cur ^ 1], 1)], x); };
+      auto app = [&](int x, double p) {
+        __stcg(&next[atomicAdd(&a.counters[cur ^ 1], 1)], x);
+        if (REVERSE) atomicAdd(d_slot(a.counters, cur ^ 1), d_fx(p));
+      };
       if (REVERSE) rev_commit_one(a, e, app); else fwd_commit_one(a, e, app);
     }
     __threadfence();
@@ -487,7 +569,8 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
   if (gtid == 0) {
     __stcg(&a.counters[4], cur);
     __stcg(&a.counters[6], ldcg_i(&a.counters[6]) + rounds);  // accumulated rounds of the whole solve
-    if (ldcg_i(&a.counters[cur]) != 0) __stcg(&a.counters[3], 1);  // sticky: a phase hit the round limit
+    if (cut) __stcg(&a.counters[36], 1);                       // stopped on the D budget: the list is not empty by design
+    else if (ldcg_i(&a.counters[cur]) != 0) __stcg(&a.counters[3], 1);  // sticky: a phase hit the round limit
   }
 }
 
@@ -553,13 +636,19 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
   c->launches++;
   cudaMemsetAsync(c->d_bid_obj, 0xff, sizeof(int) * (size_t)nmax, st);  // -1
 
+  // Split of the optimality budget n*eps_final: eps_last = epsf*eps_final for the forward phases (n*eps_last), the rest
+  // for D = the prices of objects left free (the reverse phase runs while D exceeds it and stops as soon as it fits).
+  double epsf = 0.5;
+  if (const char *ov = getenv("GHICP_AUCTION_EPSF")) { const double v = atof(ov); if (v > 0.0 && v < 1.0) epsf = v; }
+  const double d_budget = (1.0 - epsf) * eps_final * (double)nmax;
+  a.d_budget_fx = getenv("GHICP_AUCTION_NOCUT") ? 0ull : (unsigned long long)(d_budget * D_FX);
   // epsilon schedule
   std::vector<double> eps_list;
   {
     // Optimality bound at termination: OPT - ours <= n*eps_last + D  (D = prices of objects left free).
     // eps_last = eps_final/2 leaves a budget of n*eps_final/2 for D, so the reverse auction (whose rounds are
     // long sequential displacement chains) only runs when D exceeds that budget.
-    const double eps_last = 0.5 * eps_final;
+    const double eps_last = epsf * eps_final;
     double e0 = max_gain / 4.0;
     if (const char *ov = getenv("GHICP_AUCTION_EPS0")) e0 = atof(ov);  // experiment hook: first epsilon (0 = single phase)
     while (e0 > eps_last * 1.0000001) { eps_list.push_back(e0); e0 /= 5.0; }
@@ -569,7 +658,7 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
   // price wars are bounded by the few alternatives a person has, and a single forward phase from zero
   // prices leaves every free object at price zero (D = 0, no reverse auction).
   const bool single_phase = nnz <= (long long)(1.5 * (double)nmax) && getenv("GHICP_AUCTION_SCALING") == nullptr;
-  if (nnz == 0 || single_phase) eps_list.assign(1, 0.5 * eps_final);
+  if (nnz == 0 || single_phase) eps_list.assign(1, epsf * eps_final);
 
   int rounds = 0;
   const int max_rounds = 4000000;
@@ -586,8 +675,9 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
   // CTA 0 takes over the rounds alone once the expected work of a round (active bidders x average
   // adjacency length) is small enough that grid-wide barriers would dominate
   const double avg_row = (double)nnz / (n_rows > 0 ? n_rows : 1), avg_col = (double)nnz / (n_cols > 0 ? n_cols : 1);
-  int small_fwd = (int)(65536.0 / (avg_row > 1.0 ? avg_row : 1.0));
-  int small_rev = (int)(65536.0 / (avg_col > 1.0 ? avg_col : 1.0));
+  // (long adjacency lists: a grid round gives every bidder up to 16 warps, CTA 0 alone only pays below ~16 bidders)
+  int small_fwd = (int)(8192.0 / (avg_row > 1.0 ? avg_row : 1.0));
+  int small_rev = (int)(8192.0 / (avg_col > 1.0 ? avg_col : 1.0));
   small_fwd = small_fwd < 16 ? 16 : (small_fwd > PA_SMALL ? PA_SMALL : small_fwd);
   small_rev = small_rev < 16 ? 16 : (small_rev > PA_SMALL ? PA_SMALL : small_rev);
   if (const char *ov = getenv("GHICP_AUCTION_SMALL")) small_fwd = small_rev = atoi(ov);  // experiment / test hook: 0 = grid rounds only
@@ -625,21 +715,22 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
     // just the next phase's starting prices).
     bool need_reverse = false;
     if (ph + 1 == eps_list.size()) {
-      double *d_D = reinterpret_cast<double *>(c->d_bid_aux);  // free scratch between rounds
-      cudaMemsetAsync(d_D, 0, sizeof(double), st);
+      unsigned long long *d_D = reinterpret_cast<unsigned long long *>(c->d_bid_aux);  // free scratch between rounds
+      cudaMemsetAsync(d_D, 0, sizeof(unsigned long long), st);
       GHICP_LAUNCH(k_free_price_sum, 148, 256, 0, st, n_cols, c->d_owner, c->d_price, d_D);
       c->launches++;
-      double D = 0.0;
-      cudaMemcpyAsync(&D, d_D, sizeof(double), cudaMemcpyDeviceToHost, st);
+      unsigned long long D_fx_host = 0ull;
+      cudaMemcpyAsync(&D_fx_host, d_D, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
       cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(int) * 8, cudaMemcpyDeviceToHost, st);  // final, unless the reverse runs
       cudaStreamSynchronize(st);
-      const double budget = 0.5 * eps_final * (double)(n_rows > n_cols ? n_rows : n_cols);
+      const double D = (double)D_fx_host / D_FX, budget = d_budget;
       need_reverse = D > budget;
       if (debug) fprintf(stderr, "[auction] free-object price sum D = %.4f, budget %.4f -> reverse %s\n", D, budget, need_reverse ? "yes" : "skipped");
     }
     if (need_reverse) {
     ran_reverse = true;
     cudaMemsetAsync(&c->d_counters[0], 0, sizeof(int) * 2, st);
+    cudaMemsetAsync(&c->d_counters[32], 0, sizeof(int) * 5, st);   // D of both lists, the budget-stop flag
     GHICP_LAUNCH(k_rev_collect, gmax, 256, 0, st, n_cols, c->d_owner, c->d_price, c->d_list[0], c->d_counters, 0);
     c->launches++;
     cudaMemsetAsync(c->d_bid_obj, 0xff, sizeof(int) * (size_t)nmax, st);
@@ -672,6 +763,10 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
       const unsigned long long *pb = (const unsigned long long *)&c->h_counters[16];
       fprintf(stderr, "[auction]   tail rounds by active-set size (cum): m=1: %llu in %.2f ms | 2-16: %llu in %.2f ms | 17-64: %llu in %.2f ms | >64: %llu in %.2f ms\n",
               pb[4], pb[0] * 1e-6, pb[5], pb[1] * 1e-6, pb[6], pb[2] * 1e-6, pb[7], pb[3] * 1e-6);
+      if (need_reverse)
+        fprintf(stderr, "[auction]   reverse %s: %d objects still free with a positive price, D left %.3f (budget %.3f)\n",
+                c->h_counters[36] ? "stopped on the D budget" : "ran to completion", c->h_counters[c->h_counters[4] & 1],
+                (double)*(unsigned long long *)&c->h_counters[32 + 2 * (c->h_counters[4] & 1)] / D_FX, d_budget);
     }
   }
   {

@@ -1000,14 +1000,14 @@ int ghicp_voxel_downsample(int device, const float *xyz, int n, float voxel_size
   if (ghicp_device_count() <= 0) { set_error(nullptr, "voxel_downsample: no CUDA device"); return GHICP_E_NODEV; }
   if (cudaSetDevice(device) != cudaSuccess) return GHICP_E_CUDA;
   float *d_xyz = nullptr; int *d_out = nullptr;
-  cudaError_t e = cudaMalloc((void **)&d_xyz, 3 * (size_t)n * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc((void **)&d_out, ((size_t)n + 1) * sizeof(int));
+  cudaError_t e = cudaMallocAsync((void **)&d_xyz, 3 * (size_t)n * sizeof(float), 0);
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_out, ((size_t)n + 1) * sizeof(int), 0);
   if (e == cudaSuccess) e = cudaMemcpy(d_xyz, xyz, 3 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice);
   int m = 0;
   if (e == cudaSuccess) e = prep_voxel_downsample(0, d_xyz, n, voxel_size, d_out, &m);
   if (e == cudaSuccess && m > 0) e = cudaMemcpy(out_idx, d_out, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost);
-  if (d_xyz) cudaFree(d_xyz);
-  if (d_out) cudaFree(d_out);
+  if (d_xyz) cudaFreeAsync(d_xyz, 0);
+  if (d_out) cudaFreeAsync(d_out, 0);
   if (e != cudaSuccess) { set_error(nullptr, std::string("voxel_downsample: ") + cudaGetErrorString(e)); cudaGetLastError(); return e == cudaErrorMemoryAllocation ? GHICP_E_NOMEM : GHICP_E_CUDA; }
   *n_out = m;
   return GHICP_OK;
@@ -1019,11 +1019,11 @@ int ghicp_detect_keypoints(int device, const float *xyz, int n, float radius, fl
   if (ghicp_device_count() <= 0) { set_error(nullptr, "detect_keypoints: no CUDA device"); return GHICP_E_NODEV; }
   if (cudaSetDevice(device) != cudaSuccess) return GHICP_E_CUDA;
   float *d_xyz = nullptr, *d_lam = nullptr; double *d_curv = nullptr; int *d_cnt = nullptr, *d_kp = nullptr;
-  cudaError_t e = cudaMalloc((void **)&d_xyz, 3 * (size_t)n * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc((void **)&d_lam, 3 * (size_t)n * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc((void **)&d_curv, (size_t)n * sizeof(double));
-  if (e == cudaSuccess) e = cudaMalloc((void **)&d_cnt, (size_t)n * sizeof(int));
-  if (e == cudaSuccess) e = cudaMalloc((void **)&d_kp, (size_t)n * sizeof(int));
+  cudaError_t e = cudaMallocAsync((void **)&d_xyz, 3 * (size_t)n * sizeof(float), 0);
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_lam, 3 * (size_t)n * sizeof(float), 0);
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_curv, (size_t)n * sizeof(double), 0);
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_cnt, (size_t)n * sizeof(int), 0);
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_kp, (size_t)n * sizeof(int), 0);
   if (e == cudaSuccess) e = cudaMemcpy(d_xyz, xyz, 3 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice);
   int m = 0, rounds = 0;
   if (e == cudaSuccess) e = prep_detect_keypoints(0, d_xyz, n, radius, ratio_max, min_pts, nms_radius, d_lam, d_curv, d_cnt, d_kp, &m, &rounds);
@@ -1031,11 +1031,11 @@ int ghicp_detect_keypoints(int device, const float *xyz, int n, float radius, fl
   if (e == cudaSuccess && lam) e = cudaMemcpy(lam, d_lam, 3 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && curvature) e = cudaMemcpy(curvature, d_curv, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && pt_num) e = cudaMemcpy(pt_num, d_cnt, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost);
-  if (d_xyz) cudaFree(d_xyz);
-  if (d_lam) cudaFree(d_lam);
-  if (d_curv) cudaFree(d_curv);
-  if (d_cnt) cudaFree(d_cnt);
-  if (d_kp) cudaFree(d_kp);
+  if (d_xyz) cudaFreeAsync(d_xyz, 0);
+  if (d_lam) cudaFreeAsync(d_lam, 0);
+  if (d_curv) cudaFreeAsync(d_curv, 0);
+  if (d_cnt) cudaFreeAsync(d_cnt, 0);
+  if (d_kp) cudaFreeAsync(d_kp, 0);
   if (e != cudaSuccess) { set_error(nullptr, std::string("detect_keypoints: ") + cudaGetErrorString(e)); cudaGetLastError(); return e == cudaErrorMemoryAllocation ? GHICP_E_NOMEM : GHICP_E_CUDA; }
   *n_kp = m;
   return GHICP_OK;
@@ -1056,12 +1056,12 @@ int ghicp_bsc_extract(int device, const float *xyz, int n, const int *kp_idx, in
   const int V = dof_type > 4 ? 4 : (dof_type > 0 ? 2 : 1);
   const size_t nbytes = (size_t)(9 * S2 + 7) / 8, out_bytes = (size_t)V * nkp * nbytes;
   float *d_xyz = nullptr, *d_lrf = nullptr; int *d_kp = nullptr, *d_pairs = nullptr, *d_status = nullptr; unsigned char *d_bits = nullptr;
-  cudaError_t e = cudaMalloc((void **)&d_xyz, 3 * (size_t)n * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc((void **)&d_kp, (size_t)nkp * sizeof(int));
-  if (e == cudaSuccess) e = cudaMalloc((void **)&d_pairs, 2 * (size_t)S2 * sizeof(int));
-  if (e == cudaSuccess) e = cudaMalloc((void **)&d_bits, out_bytes);
-  if (e == cudaSuccess) e = cudaMalloc((void **)&d_lrf, 12 * (size_t)nkp * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc((void **)&d_status, (size_t)nkp * sizeof(int));
+  cudaError_t e = cudaMallocAsync((void **)&d_xyz, 3 * (size_t)n * sizeof(float), 0);
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_kp, (size_t)nkp * sizeof(int), 0);
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_pairs, 2 * (size_t)S2 * sizeof(int), 0);
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_bits, out_bytes, 0);
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_lrf, 12 * (size_t)nkp * sizeof(float), 0);
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_status, (size_t)nkp * sizeof(int), 0);
   if (e == cudaSuccess) e = cudaMemcpy(d_xyz, xyz, 3 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(d_kp, kp_idx, (size_t)nkp * sizeof(int), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(d_pairs, pairs, 2 * (size_t)S2 * sizeof(int), cudaMemcpyHostToDevice);
@@ -1069,12 +1069,12 @@ int ghicp_bsc_extract(int device, const float *xyz, int n, const int *kp_idx, in
   if (e == cudaSuccess) e = cudaMemcpy(features, d_bits, out_bytes, cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && lrf) e = cudaMemcpy(lrf, d_lrf, 12 * (size_t)nkp * sizeof(float), cudaMemcpyDeviceToHost);
   if (e == cudaSuccess && status) e = cudaMemcpy(status, d_status, (size_t)nkp * sizeof(int), cudaMemcpyDeviceToHost);
-  if (d_xyz) cudaFree(d_xyz);
-  if (d_kp) cudaFree(d_kp);
-  if (d_pairs) cudaFree(d_pairs);
-  if (d_bits) cudaFree(d_bits);
-  if (d_lrf) cudaFree(d_lrf);
-  if (d_status) cudaFree(d_status);
+  if (d_xyz) cudaFreeAsync(d_xyz, 0);
+  if (d_kp) cudaFreeAsync(d_kp, 0);
+  if (d_pairs) cudaFreeAsync(d_pairs, 0);
+  if (d_bits) cudaFreeAsync(d_bits, 0);
+  if (d_lrf) cudaFreeAsync(d_lrf, 0);
+  if (d_status) cudaFreeAsync(d_status, 0);
   if (e != cudaSuccess) { set_error(nullptr, std::string("bsc_extract: ") + cudaGetErrorString(e)); cudaGetLastError(); return e == cudaErrorMemoryAllocation ? GHICP_E_NOMEM : GHICP_E_CUDA; }
   if (n_variants) *n_variants = V;
   return GHICP_OK;
@@ -1095,10 +1095,10 @@ struct ghicp_prep {
 int ghicp_prep_destroy(ghicp_prep *h) {
   if (!h) return GHICP_OK;
   cudaSetDevice(h->device);
-  if (h->d_down) cudaFree(h->d_down);
-  if (h->d_kp) cudaFree(h->d_kp);
-  if (h->d_kp_xyz) cudaFree(h->d_kp_xyz);
-  if (h->d_bits) cudaFree(h->d_bits);
+  if (h->d_down) cudaFreeAsync(h->d_down, 0);
+  if (h->d_kp) cudaFreeAsync(h->d_kp, 0);
+  if (h->d_kp_xyz) cudaFreeAsync(h->d_kp_xyz, 0);
+  if (h->d_bits) cudaFreeAsync(h->d_bits, 0);
   delete h;
   return GHICP_OK;
 }
@@ -1125,39 +1125,39 @@ int ghicp_prep_run(int device, const float *xyz, int n, const ghicp_prep_params 
     cudaGetLastError();
   };
   for (auto &x : ev) if (e == cudaSuccess) e = cudaEventCreate(&x);
-  if (e == cudaSuccess) e = cudaMalloc((void **)&d_xyz, 3 * (size_t)n * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc((void **)&d_keep, ((size_t)n + 1) * sizeof(int));
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_xyz, 3 * (size_t)n * sizeof(float), 0);
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_keep, ((size_t)n + 1) * sizeof(int), 0);
   if (e == cudaSuccess) e = cudaEventRecord(ev[0], 0);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_xyz, xyz, 3 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, 0);
   if (e == cudaSuccess) e = cudaEventRecord(ev[1], 0);
   int n_down = 0, n_kp = 0, rounds = 0;
   if (e == cudaSuccess) e = prep_voxel_downsample(0, d_xyz, n, p->voxel_size, d_keep, &n_down);
   if (e == cudaSuccess && n_down <= 0) e = cudaErrorInvalidValue;
-  if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_down, 3 * (size_t)n_down * sizeof(float));
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&h->d_down, 3 * (size_t)n_down * sizeof(float), 0);
   if (e == cudaSuccess) e = prep_gather_points(0, d_xyz, d_keep, n_down, h->d_down);
   if (e == cudaSuccess) e = cudaEventRecord(ev[2], 0);
-  if (e == cudaSuccess) { cudaFree(d_xyz); d_xyz = nullptr; cudaFree(d_keep); d_keep = nullptr; }
+  if (e == cudaSuccess) { cudaFreeAsync(d_xyz, 0); d_xyz = nullptr; cudaFreeAsync(d_keep, 0); d_keep = nullptr; }
   if (e == cudaSuccess) e = prep_bounds(0, h->d_down, n_down, h->bbox_min, h->bbox_max);
-  if (e == cudaSuccess) e = cudaMalloc((void **)&d_lam, 3 * (size_t)n_down * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc((void **)&d_curv, (size_t)n_down * sizeof(double));
-  if (e == cudaSuccess) e = cudaMalloc((void **)&d_cnt, (size_t)n_down * sizeof(int));
-  if (e == cudaSuccess) e = cudaMalloc((void **)&d_kpbuf, (size_t)n_down * sizeof(int));
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_lam, 3 * (size_t)n_down * sizeof(float), 0);
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_curv, (size_t)n_down * sizeof(double), 0);
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_cnt, (size_t)n_down * sizeof(int), 0);
+  if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_kpbuf, (size_t)n_down * sizeof(int), 0);
   if (e == cudaSuccess) e = prep_detect_keypoints(0, h->d_down, n_down, p->neighborhood_radius, p->ratio_max, p->min_pts, p->nms_radius,
                                                   d_lam, d_curv, d_cnt, d_kpbuf, &n_kp, &rounds);
   if (e == cudaSuccess) e = cudaEventRecord(ev[3], 0);
   h->n_down = n_down; h->n_kp = n_kp;
   if (e == cudaSuccess && n_kp > 0) {
-    e = cudaMalloc((void **)&h->d_kp, (size_t)n_kp * sizeof(int));
+    e = cudaMallocAsync((void **)&h->d_kp, (size_t)n_kp * sizeof(int), 0);
     if (e == cudaSuccess) e = cudaMemcpyAsync(h->d_kp, d_kpbuf, (size_t)n_kp * sizeof(int), cudaMemcpyDeviceToDevice, 0);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_kp_xyz, 3 * (size_t)n_kp * sizeof(double));
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&h->d_kp_xyz, 3 * (size_t)n_kp * sizeof(double), 0);
     if (e == cudaSuccess) e = prep_kp_coords(0, h->d_down, h->d_kp, n_kp, h->d_kp_xyz);
     if (e == cudaSuccess && want_bsc) {
       h->V = p->dof_type > 4 ? 4 : (p->dof_type > 0 ? 2 : 1);
       h->nbytes = (9 * side * side + 7) / 8;
-      e = cudaMalloc((void **)&h->d_bits, (size_t)h->V * n_kp * h->nbytes);
-      if (e == cudaSuccess) e = cudaMalloc((void **)&d_pairs, 2 * (size_t)side * side * sizeof(int));
-      if (e == cudaSuccess) e = cudaMalloc((void **)&d_lrf, 12 * (size_t)n_kp * sizeof(float));
-      if (e == cudaSuccess) e = cudaMalloc((void **)&d_status, (size_t)n_kp * sizeof(int));
+      e = cudaMallocAsync((void **)&h->d_bits, (size_t)h->V * n_kp * h->nbytes, 0);
+      if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_pairs, 2 * (size_t)side * side * sizeof(int), 0);
+      if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_lrf, 12 * (size_t)n_kp * sizeof(float), 0);
+      if (e == cudaSuccess) e = cudaMallocAsync((void **)&d_status, (size_t)n_kp * sizeof(int), 0);
       if (e == cudaSuccess) e = cudaMemcpyAsync(d_pairs, bsc_pairs, 2 * (size_t)side * side * sizeof(int), cudaMemcpyHostToDevice, 0);
       if (e == cudaSuccess) e = prep_bsc_extract(0, h->d_down, n_down, h->d_kp, n_kp, p->bsc_radius, side, d_pairs, p->dof_type, h->d_bits, d_lrf, d_status);
     }
@@ -1169,15 +1169,15 @@ int ghicp_prep_run(int device, const float *xyz, int n, const ghicp_prep_params 
     cudaEventElapsedTime(&h->stage_ms[4], ev[0], ev[4]);
   }
   for (auto &x : ev) if (x) cudaEventDestroy(x);
-  if (d_xyz) cudaFree(d_xyz);
-  if (d_keep) cudaFree(d_keep);
-  if (d_lam) cudaFree(d_lam);
-  if (d_curv) cudaFree(d_curv);
-  if (d_cnt) cudaFree(d_cnt);
-  if (d_kpbuf) cudaFree(d_kpbuf);
-  if (d_pairs) cudaFree(d_pairs);
-  if (d_lrf) cudaFree(d_lrf);
-  if (d_status) cudaFree(d_status);
+  if (d_xyz) cudaFreeAsync(d_xyz, 0);
+  if (d_keep) cudaFreeAsync(d_keep, 0);
+  if (d_lam) cudaFreeAsync(d_lam, 0);
+  if (d_curv) cudaFreeAsync(d_curv, 0);
+  if (d_cnt) cudaFreeAsync(d_cnt, 0);
+  if (d_kpbuf) cudaFreeAsync(d_kpbuf, 0);
+  if (d_pairs) cudaFreeAsync(d_pairs, 0);
+  if (d_lrf) cudaFreeAsync(d_lrf, 0);
+  if (d_status) cudaFreeAsync(d_status, 0);
   if (e != cudaSuccess) { fail("pipeline"); ghicp_prep_destroy(h); return e == cudaErrorMemoryAllocation ? GHICP_E_NOMEM : GHICP_E_CUDA; }
   *out = h;
   return GHICP_OK;

@@ -168,8 +168,8 @@ struct Ctx {
   int *d_bid_obj = nullptr; double *d_bid_val = nullptr;  // [max(N,M)]
   double *d_bid_aux = nullptr; // [max(N,M)]
   int *d_list[2] = {nullptr, nullptr};  // active lists [max(N,M)]
-  int *d_counters = nullptr;   // [8]
-  int *h_counters = nullptr;   // pinned [8]
+  int *d_counters = nullptr;   // [64] (layout: ghicp_auction.cu)
+  int *h_counters = nullptr;   // pinned [64]
 
   // streaming path
   bool use_fast = true;

@@ -64,8 +64,22 @@ cudaError_t exclusive_scan(const int *in, int *out, int n, cudaStream_t) {   // 
   return cudaSuccess;
 }
 #else
-template <typename T> cudaError_t pmalloc(T **p, size_t n) { return cudaMalloc((void **)p, (n ? n : 1) * sizeof(T)); }
-template <typename T> void pfree(T *p) { if (p) cudaFree(p); }
+// Workspaces come from the device's stream-ordered pool (the whole pre-processing runs on one stream): a cudaMalloc /
+// cudaFree pair per temporary cost more host time than all the kernels of a 1 M-point scan together (measured on the
+// B200: 376 ms per scan against ~10 ms of kernels), cudaFree being a device-wide synchronisation.  The pool keeps what it
+// has handed out once (release threshold = unlimited), so the second scan of a pair allocates nothing new.
+inline void ppool_init() {
+  static bool done = false;   // per process; set for the current device on first use
+  if (done) return;
+  int dev = 0; cudaMemPool_t pool;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  done = true;
+}
+template <typename T> cudaError_t pmalloc(T **p, size_t n) { ppool_init(); return cudaMallocAsync((void **)p, (n ? n : 1) * sizeof(T), 0); }
+template <typename T> void pfree(T *p) { if (p) cudaFreeAsync(p, 0); }
 enum { P_H2D = cudaMemcpyHostToDevice, P_D2H = cudaMemcpyDeviceToHost, P_D2D = cudaMemcpyDeviceToDevice };
 inline cudaError_t pcopy(void *dst, const void *src, size_t bytes, int kind, cudaStream_t st) { return cudaMemcpyAsync(dst, src, bytes, (cudaMemcpyKind)kind, st); }
 inline cudaError_t pzero(void *p, size_t bytes, cudaStream_t st) { return cudaMemsetAsync(p, 0, bytes, st); }
@@ -75,21 +89,19 @@ cudaError_t sort_pairs(pu64 *keys, int *vals, int n, cudaStream_t st) {   // sta
   cudaError_t e = pmalloc(&k2, (size_t)n);
   if (e == cudaSuccess) e = pmalloc(&v2, (size_t)n);
   if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(nullptr, tb, keys, k2, vals, v2, n, 0, 64, st);
-  if (e == cudaSuccess) e = cudaMalloc(&tmp, tb ? tb : 1);
+  if (e == cudaSuccess) e = cudaMallocAsync(&tmp, tb ? tb : 1, st);
   if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tb, keys, k2, vals, v2, n, 0, 64, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(keys, k2, sizeof(pu64) * (size_t)n, cudaMemcpyDeviceToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(vals, v2, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  pfree(k2); pfree(v2); if (tmp) cudaFree(tmp);
+  pfree(k2); pfree(v2); if (tmp) cudaFreeAsync(tmp, st);   // stream-ordered: no host synchronisation needed
   return e;
 }
 cudaError_t exclusive_scan(const int *in, int *out, int n, cudaStream_t st) {   // out[n] = total (in[n] must be readable)
   void *tmp = nullptr; size_t tb = 0;
   cudaError_t e = cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, n + 1, st);
-  if (e == cudaSuccess) e = cudaMalloc(&tmp, tb ? tb : 1);
+  if (e == cudaSuccess) e = cudaMallocAsync(&tmp, tb ? tb : 1, st);
   if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, tb, in, out, n + 1, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  if (tmp) cudaFree(tmp);
+  if (tmp) cudaFreeAsync(tmp, st);
   return e;
 }
 #endif

@@ -316,7 +316,7 @@ int emu_km_auction(int N, int M, const long long *rowptr, const int *col, const 
   const long long nnz = rowptr[N];
   std::vector<long long> vrowptr(rowptr, rowptr + N + 1), colptr((size_t)M + 2, 0), tile_sum(2 * ((size_t)(nmax + 1023) / 1024 + 1) + 2);
   std::vector<int> vcol(col, col + nnz), colcnt((size_t)M + 2, 0), csc_row((size_t)nnz + 1), vassign(nmax), vowner(nmax), bidwin(nmax),
-      bid_obj(nmax), l0(nmax), l1(nmax), counters(16, 0), hcount(16, 0), flags(nmax);
+      bid_obj(nmax), l0(nmax), l1(nmax), counters(64, 0), hcount(64, 0), flags(nmax);
   std::vector<double> vgain(gain, gain + nnz), csc_gain((size_t)nnz + 1), vprice(nmax, 0.0), profit(nmax, 0.0), bid_val(nmax), bid_aux((size_t)nmax + 2);
   std::vector<unsigned long long> bidmax(nmax, 0ull);
   vcol.resize((size_t)nnz + 1); vgain.resize((size_t)nnz + 1);

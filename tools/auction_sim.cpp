@@ -257,6 +257,11 @@ struct Auction {
   double free_price_sum() const { double D = 0; for (int j = 0; j < O; ++j) if (owner[j] < 0) D += price[j]; return D; }
 
   // reverse phase: free objects with positive price lower their price / attract persons
+  // d_budget >= 0: stop as soon as D = sum of the prices of the objects still free (= the active list) is within the budget:
+  // the bound OPT - ours <= n*eps + D holds at every round boundary (dual eps-feasibility is an invariant of the reverse
+  // auction), so the rest of the displacement chains need not be followed.
+  double d_budget = -1.0;
+  ll rev_cut_round = -1;
   void reverse(double eps, ll max_rounds = 100000000) {
     std::vector<int> act, next;
     for (int j = 0; j < O; ++j) if (owner[j] < 0 && price[j] > 0.0) act.push_back(j);
@@ -266,6 +271,11 @@ struct Auction {
     while (!act.empty() && rounds < max_rounds) {
       ll edges = 0;
       const int n = (int)act.size();
+      if (d_budget >= 0.0) {
+        double Dc = 0; for (int a = 0; a < n; ++a) Dc += price[act[a]];
+        if (getenv("DTRACE") && (rounds % 50 == 0 || n <= 4)) fprintf(stderr, "    rev round %lld active %d D %.2f\n", rounds, n, Dc);
+        if (Dc <= d_budget) { rev_cut_round = rounds; break; }
+      }
 #pragma omp parallel for reduction(+ : edges) schedule(dynamic, 64) if (n > 256)
       for (int a = 0; a < n; ++a) {
         const int j = act[a];
@@ -398,7 +408,8 @@ int main(int argc, char **argv) {
       if (mode.rfind("e0=", 0) == 0) e0 = atof(mode.c_str() + 3);
       if (mode.rfind("relax=", 0) == 0) relax = atof(mode.c_str() + 6);
       Auction A = mk();
-      auto eps = schedule(e0, 5.0, 0.5 * KM_eps);
+      const double epsf = getenv("EPSF") ? atof(getenv("EPSF")) : 0.5;   // eps_last = epsf*KM_eps; D budget = (1-epsf)*KM_eps*n
+      auto eps = schedule(e0, 5.0, epsf * KM_eps);
       for (size_t ph = 0; ph < eps.size(); ++ph) {
         if (ph > 0) { for (auto &p : A.price) p = std::max(0.0, p - relax * eps[ph - 1]); }
         std::fill(A.owner.begin(), A.owner.end(), -1); std::fill(A.assign.begin(), A.assign.end(), -1); std::fill(A.profit.begin(), A.profit.end(), 0.0);
@@ -408,7 +419,9 @@ int main(int argc, char **argv) {
         fprintf(stderr, "  phase %zu eps %.4f: %lld rounds, D %.1f gain %.1f  certificate: viol %.2f + D %.2f\n", ph, eps[ph], A.fwd.rounds - r0, A.free_price_sum(), A.total_gain(), cv, cD);
       }
       double D = A.free_price_sum();
-      if (D > 0.5 * KM_eps * N) A.reverse(0.5 * KM_eps);
+      if (getenv("DCUT")) A.d_budget = (1.0 - epsf) * KM_eps * N;
+      if (D > (1.0 - epsf) * KM_eps * N) A.reverse(epsf * KM_eps);
+      if (A.d_budget >= 0) fprintf(stderr, "  reverse cut at round %lld (budget %.1f), D left %.2f\n", A.rev_cut_round, A.d_budget, A.free_price_sum());
       report(mode.c_str(), A, A.total_gain(), D, tnow() - t0);
     } else if (mode.rfind("sym", 0) == 0) {
       // symmetric formulation + forward eps-scaling only.  sym[=e0[,div]]
