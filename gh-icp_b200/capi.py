@@ -7,6 +7,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "libghicp_b200.so")
+# developer hook for kernel A/B runs (tools/build_variants.sh): another build of the SAME library; never set by the driver
+if os.environ.get("GHICP_B200_LIB"):
+    _LIB = os.environ["GHICP_B200_LIB"]
 
 FT_BSC, FT_ROPS, FT_FPFH, FT_NONE = 0, 1, 2, 3   # include/utility.h:51-57
 CT_NN, CT_NNR, CT_KM = 0, 1, 2                   # include/utility.h:59-64
@@ -70,7 +73,8 @@ EXPORTS = ["ghicp_abi_version", "ghicp_device_count", "ghicp_last_error", "ghicp
            "ghicp_probe_rowmin", "ghicp_set_state", "ghicp_reset", "ghicp_km_solve", "ghicp_rigid_fit", "ghicp_rigid_fit_ex",
            "ghicp_set_target_normals", "ghicp_set_solver", "ghicp_voxel_downsample", "ghicp_detect_keypoints",
            "ghicp_bsc_extract", "ghicp_bsc_default_pattern", "ghicp_comm_unique_id", "ghicp_comm_init",
-           "ghicp_prep_run", "ghicp_prep_info", "ghicp_prep_get", "ghicp_prep_destroy", "ghicp_set_from_prep"]
+           "ghicp_prep_run", "ghicp_prep_info", "ghicp_prep_get", "ghicp_prep_destroy", "ghicp_set_from_prep",
+           "ghicp_host_alloc", "ghicp_host_free"]
 
 
 def lib():
@@ -119,6 +123,8 @@ def lib():
     L.ghicp_set_from_prep.argtypes = [vp, vp, vp]
     L.ghicp_comm_unique_id.argtypes = [vp]
     L.ghicp_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.ghicp_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.ghicp_host_free.argtypes = [vp]
     _lib = L
     return L
 
@@ -207,6 +213,40 @@ def _dp(a):
 
 def _ip(a):
     return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+class _PinnedBlock:
+    """Owner of one page-locked allocation (freed when the last numpy view of it is gone)."""
+
+    def __init__(self, nbytes):
+        self.ptr = C.c_void_p()
+        check(lib().ghicp_host_alloc(max(int(nbytes), 1), C.byref(self.ptr)))
+        self.nbytes = int(nbytes)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().ghicp_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.float64, order="C"):
+    """numpy array in page-locked host memory (ghicp_host_alloc): set_keypoints / pairs(out=) / source(out=) then move it with
+    one DMA, no staging copy inside the library."""
+    dtype = np.dtype(dtype)
+    shape = (shape,) if np.isscalar(shape) else tuple(shape)
+    n = int(np.prod(shape)) if shape else 1
+    blk = _PinnedBlock(n * dtype.itemsize)
+    buf = (C.c_char * max(blk.nbytes, 1)).from_address(blk.ptr.value)
+    buf._pinned_owner = blk   # the array's base object keeps the allocation alive; freed with the last view
+    return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape, order=order)
+
+
+def pinned_copy(a, order="F"):
+    out = pinned_empty(a.shape, a.dtype, order=order)
+    out[...] = a
+    return out
 
 
 def comm_unique_id():

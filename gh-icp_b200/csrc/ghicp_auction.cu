@@ -579,6 +579,11 @@ __global__ void k_col_count(const int *__restrict__ csr_col, long long nnz, int 
   const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k < nnz) atomicAdd(&colcnt[csr_col[k]], 1);
 }
+__global__ void k_col_count_dev(const int *__restrict__ csr_col, const long long *__restrict__ d_nnz, int *__restrict__ colcnt) {
+  const long long nnz = *d_nnz;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += (long long)gridDim.x * blockDim.x)
+    atomicAdd(&colcnt[csr_col[k]], 1);
+}
 __global__ void __launch_bounds__(AUC_BLOCK) k_csc_fill(int n_rows, const long long *rowptr, int n_chunks,
                                                          const int *csr_col, const double *csr_gain,
                                                          const long long *colptr, int *cursor, int *csc_row,
@@ -616,6 +621,86 @@ cudaError_t launch_build_csc(Ctx *c, int n_rows, int n_cols, long long nnz) {
     c->launches++;
   }
   return cudaGetLastError();
+}
+
+// eps of the single forward phase from zero prices (sparse graphs): free objects keep price 0 there (D = 0), so the whole
+// optimality budget n*eps_final goes to eps.  One definition for km_auction and km_auction_settled: the two routes of an
+// iteration must produce the same matching.
+static double single_phase_eps(double eps_final) {
+  double f = 0.95;
+  if (const char *ov = getenv("GHICP_AUCTION_EPS1")) { const double v = atof(ov); if (v > 0.0 && v <= 1.0) f = v; }
+  return f * eps_final;
+}
+
+cudaError_t launch_build_csc_dev(Ctx *c, int n_rows, int n_cols, const long long *d_nnz, long long nnz_bound) {
+  cudaError_t e;
+  if ((e = cudaMemsetAsync(c->d_colcnt, 0, sizeof(int) * (size_t)(n_cols + 1), c->stream)) != cudaSuccess) return e;
+  const long long want = (nnz_bound + 255) / 256;
+  GHICP_LAUNCH(k_col_count_dev, (unsigned)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want)), 256, 0, c->stream, c->d_csr_col, d_nnz,
+               c->d_colcnt);
+  c->launches++;
+  if ((e = launch_scan_i32(c, c->d_colcnt, c->d_colptr, c->d_bid_obj, n_cols, nullptr)) != cudaSuccess) return e;
+  GHICP_LAUNCH(k_csc_fill, AUC_GRID, AUC_BLOCK, 0, c->stream, n_rows, c->d_rowptr, c->n_chunks, c->d_csr_col, c->d_csr_gain,
+               c->d_colptr, c->d_bid_obj, c->d_csc_row, c->d_csc_gain);
+  c->launches++;
+  return cudaGetLastError();
+}
+
+// The settled loop's auction: ONE forward phase at eps_final/2 from zero prices (the sparse-graph schedule of
+// km_auction: every object that ever received a bid stays owned, free objects keep price 0, D = 0, no reverse phase),
+// enqueued without reading anything back.  Correct on any graph; chosen by the caller when last iteration's graph
+// was sparse.
+int km_auction_settled(Ctx *c, int n_rows, int n_cols, long long nnz_hint, double eps_final) {
+  cudaStream_t st = c->stream;
+  AucArgs a{};
+  a.rowptr = c->d_rowptr; a.n_chunks = c->n_chunks; a.csr_col = c->d_csr_col; a.csr_gain = c->d_csr_gain;
+  a.colptr = c->d_colptr; a.csc_row = c->d_csc_row; a.csc_gain = c->d_csc_gain;
+  a.price = c->d_price; a.profit = c->d_profit; a.assign = c->d_assign; a.owner = c->d_owner;
+  a.bidmax = c->d_bidmax; a.bidwin = c->d_bidwin; a.bid_obj = c->d_bid_obj; a.bid_val = c->d_bid_val;
+  a.bid_aux = c->d_bid_aux; a.counters = c->d_counters;
+  a.eps = single_phase_eps(eps_final); a.profile = 0; a.d_budget_fx = 0ull;
+  const int nmax = n_rows > n_cols ? n_rows : n_cols;
+  const int gmax = (nmax + 255) / 256;
+  int *base_list = c->d_flags;  // free during KM
+  cudaMemsetAsync(c->d_counters, 0, sizeof(int) * 64, st);
+  GHICP_LAUNCH(k_auc_init, gmax, 256, 0, st, n_rows, n_cols, c->d_rowptr, c->n_chunks, c->d_price, base_list, c->d_counters,
+                                   c->d_bidmax, c->d_bidwin, nmax);
+  cudaMemsetAsync(c->d_bid_obj, 0xff, sizeof(int) * (size_t)nmax, st);  // -1
+  GHICP_LAUNCH(k_auc_phase_start, gmax, 256, 0, st, n_rows, n_cols, c->d_rowptr, c->n_chunks, c->d_assign, c->d_owner,
+                                          c->d_profit, c->d_price, 0.0);
+  c->launches += 2;
+  cudaMemcpyAsync(c->d_list[0], base_list, sizeof(int) * (size_t)n_rows, cudaMemcpyDeviceToDevice, st);
+  cudaMemcpyAsync(&c->d_counters[0], &c->d_counters[2], sizeof(int), cudaMemcpyDeviceToDevice, st);
+  static int blocks_per_sm = 0;
+  int n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device);
+  if (blocks_per_sm == 0) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_auction_persistent<false>, PA_THREADS, 0);
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+  }
+  const double avg_row = (double)nnz_hint / (n_rows > 0 ? n_rows : 1);
+  int sn = (int)(8192.0 / (avg_row > 1.0 ? avg_row : 1.0));
+  sn = sn < 16 ? 16 : (sn > PA_SMALL ? PA_SMALL : sn);
+  int *l0 = c->d_list[0], *l1 = c->d_list[1];
+  int mr = 4000000;
+  void *args[] = {(void *)&a, (void *)&l0, (void *)&l1, (void *)&mr, (void *)&sn};
+#if defined(GHICP_EMU_HOST)
+  (void)args;
+  emu::launch_cooperative(dim3(n_sm * blocks_per_sm), dim3(PA_THREADS), [&] { k_auction_persistent<false>(a, l0, l1, mr, sn); });
+  cudaError_t e = cudaSuccess;
+#else
+  cudaError_t e = cudaLaunchCooperativeKernel((void *)k_auction_persistent<false>, dim3(n_sm * blocks_per_sm), dim3(PA_THREADS),
+                                              args, 0, st);
+#endif
+  if (e != cudaSuccess) { set_error(c, std::string("auction (settled) launch: ") + cudaGetErrorString(e)); return GHICP_E_CUDA; }
+  c->launches++;
+  cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(int) * 8, cudaMemcpyDeviceToHost, st);
+  return GHICP_OK;
+}
+int km_auction_settled_result(Ctx *c, KmResult *res) {   // after the iteration's stream synchronize
+  if (c->h_counters[3] != 0) { set_error(c, "auction: round limit exceeded"); return GHICP_E_NOCONV; }
+  if (res) { res->rounds = c->h_counters[6]; res->phases = 1; }
+  return GHICP_OK;
 }
 
 int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, double max_gain, KmResult *res) {
@@ -658,7 +743,7 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
   // price wars are bounded by the few alternatives a person has, and a single forward phase from zero
   // prices leaves every free object at price zero (D = 0, no reverse auction).
   const bool single_phase = nnz <= (long long)(1.5 * (double)nmax) && getenv("GHICP_AUCTION_SCALING") == nullptr;
-  if (nnz == 0 || single_phase) eps_list.assign(1, epsf * eps_final);
+  if (nnz == 0 || single_phase) eps_list.assign(1, single_phase_eps(eps_final));
 
   int rounds = 0;
   const int max_rounds = 4000000;

@@ -53,6 +53,14 @@ static void dev_free(T **p) {
   if (*p) { cudaFree(*p); *p = nullptr; }
 }
 
+// Is this host pointer page-locked (cudaMallocHost / ghicp_host_alloc / cudaHostRegister)?  Then the DMA engine reads or
+// writes it directly and the pinned staging copy is skipped.
+static bool is_pinned(const void *p) {
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
 static int use_device(Ctx *c) {
   cudaError_t e = cudaSetDevice(c->device);
   if (e != cudaSuccess) { set_error(c, std::string("cudaSetDevice: ") + cudaGetErrorString(e)); return GHICP_E_CUDA; }
@@ -82,6 +90,8 @@ static void free_all(Ctx *c) {
   dev_free(&c->d_rowbest); dev_free(&c->d_colbest); dev_free(&c->d_rowidx2); dev_free(&c->d_colidx2);
   dev_free(&c->d_cand[0]); dev_free(&c->d_cand[1]);
   dev_free(&c->d_emit); c->emit_cap = 0;
+  dev_free(&c->d_xsend); dev_free(&c->d_xrecv); dev_free(&c->d_xcounts); c->xcap = 0;
+  if (c->h_xcounts) { cudaFreeHost(c->h_xcounts); c->h_xcounts = nullptr; }
   dev_free(&c->d_tile_sum); c->tile_cap = 0; dev_free(&c->d_solve_part);
   if (c->h_sdev) { cudaFreeHost(c->h_sdev); c->h_sdev = nullptr; }
   if (c->h_iter) { cudaFreeHost(c->h_iter); c->h_iter = nullptr; }
@@ -106,6 +116,8 @@ static void reset_loop_state(Ctx *c) {
   c->last_mean = 0.0;
   for (int i = 0; i < 16; ++i) c->Rt_tillnow[i] = (i % 5 == 0) ? 1.0 : 0.0;
 }
+
+static int ensure_edges(Ctx *c, long long nnz);
 
 // workspaces that depend on (N, M)
 static int alloc_workspaces(Ctx *c) {
@@ -191,7 +203,17 @@ static int alloc_workspaces(Ctx *c) {
     // take the two-pass count + fill route (their time is the auction's anyway)
     const size_t plane = (size_t)std::max(c->nloc, 1) * (size_t)M;
     c->emit_cap = std::min(plane, std::max((size_t)1 << 21, (size_t)32 * (size_t)(c->nloc + M)));
+    // settled iterations (ghicp_stream.cu: k_emit_check ...): one candidate block per rank.  Its capacity is the same on
+    // every rank (the choice between the settled and the general route must be: both contain collectives) and the
+    // edge list never holds less; the CSR / CSC arrays can take every block full, so nothing is allocated mid-loop.
+    c->xcap = (std::max((size_t)8192, (size_t)4 * (size_t)c->shard) + 3) & ~(size_t)3;
+    c->emit_cap = std::max(c->emit_cap, c->xcap);
     if ((rc = dev_alloc(c, &c->d_emit, c->emit_cap))) return rc;
+    if ((rc = dev_alloc(c, &c->d_xsend, xblock_bytes(c->xcap)))) return rc;
+    if (c->world > 1) { if ((rc = dev_alloc(c, &c->d_xrecv, xblock_bytes(c->xcap) * (size_t)c->world))) return rc; }
+    if ((rc = dev_alloc(c, &c->d_xcounts, (size_t)c->world))) return rc;
+    if (!c->h_xcounts && cudaMallocHost((void **)&c->h_xcounts, sizeof(unsigned long long) * (size_t)c->world) != cudaSuccess) return GHICP_E_NOMEM;
+    if ((rc = ensure_edges(c, (long long)(c->xcap * (size_t)c->world)))) return rc;
   }
   return GHICP_OK;
 }
@@ -325,6 +347,13 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
   bool ev1_done = false, timed_stream = false;
   int stream_passes = 0;
   const bool sharded = c->world > 1;
+  // Settled KM iteration?  Decided from quantities every rank holds identically (both routes contain collectives).
+  const long long nmax_km = std::max(c->N, c->M);
+  const bool km_settled = fast && ct == GHICP_CT_KM && ft != GHICP_FT_NONE && c->iteration >= 2 && !c->km_settled_off &&
+                          c->xcap > 0 && c->last_total_nnz >= 0 && (double)c->last_total_nnz <= 1.5 * (double)nmax_km &&
+                          c->last_max_local_nnz >= 0 &&
+                          (size_t)c->last_max_local_nnz + (size_t)c->last_max_local_nnz / 2 + 64 <= c->xcap &&
+                          getenv("GHICP_KM_GENERAL") == nullptr && getenv("GHICP_KM_FILL") == nullptr;   // test hooks: general route
   if (sharded && ct == GHICP_CT_KM && !fast) {
     set_error(c, "multi-GPU KM needs the streaming path (BSC / no feature, force_exact = 0)");
     return GHICP_E_ARG;
@@ -391,6 +420,34 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
     if (c->h_iter->overflow_any || (!cols && c->h_iter->ambiguous > 0)) exact_fallback = true;
     else c->have_prev = true;
     c->fallbacks += exact_fallback ? 1 : 0;
+  } else if (fast && km_settled) {
+    // ---- streaming path, KM, settled loop (sparse candidate graph, penalty independent of this iteration's CD):
+    //      one pass over the FD plane, the gate hits checked exactly where they were found, ONE all-gather of the
+    //      per-rank candidate blocks (none on one GPU), CSR / CSC / single-phase auction / selection enqueued behind it.
+    //      The host reads nothing until the iteration's final synchronize; a block overflow (flag travels with the
+    //      statistics, k_apply then leaves the keypoints alone) sends the iteration through the general route below.
+    c->emit_on = true;
+    CK(c, launch_stream_prep(c, cp, 0));
+    CK(c, cudaMemsetAsync(c->d_cnt, 0, sizeof(int) * ((size_t)c->Npad + 2), st));
+    CK(c, launch_penalty_only(c, ls));        // src/ghicp_reg.cpp:279-282: independent of this iteration's CD
+    CK(c, launch_stream_gate(c, cp));
+    CK(c, cudaEventRecord(c->ev[4], st));
+    CK(c, launch_stream(c, cp, 2, true));
+    CK(c, cudaEventRecord(c->ev[5], st));
+    CK(c, launch_finalize_fast(c, ls));
+    CK(c, launch_emit_check(c, cp));
+    if ((rc = comm_allgather_bytes(c, c->d_xsend, c->d_xrecv, xblock_bytes(c->xcap)))) return rc;   // the iteration's one exchange
+    CK(c, launch_xbuild(c));
+    CK(c, launch_penalty(c, 0.0, ls));        // CD mean / std of all ranks' sums (+ the overflow flag)
+    CK(c, cudaEventRecord(c->ev[1], st));
+    stream_passes += 1; timed_stream = true; ev1_done = true;
+    CK(c, launch_build_csc_dev(c, c->N, c->M, &c->d_iter->nnz, (long long)(c->xcap * (size_t)c->world)));
+    if ((rc = km_auction_settled(c, c->N, c->M, c->last_total_nnz, c->KM_eps))) return rc;
+    CK(c, launch_select_km(c));
+    CK(c, launch_pair_fd_km(c));
+    CK(c, cudaMemcpyAsync(c->h_sdev, c->d_sdev, sizeof(StreamDev), cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(c->h_xcounts, c->d_xcounts, sizeof(unsigned long long) * (size_t)c->world, cudaMemcpyDeviceToHost, st));
+    nnz = -1;  // filled from h_sdev after the final synchronize
   } else if (fast) {
     // ---- streaming path, KM: [statistics pass] + count pass + fill pass over the FD plane
     const bool stats_first = (ft == GHICP_FT_NONE) || (c->iteration <= 1);
@@ -436,7 +493,9 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
     const long long nnz_super = c->h_iter->nnz;
     const double penalty = c->h_iter->penalty;
     if ((rc = ensure_edges(c, nnz_super))) return rc;
-    if (nnz_super == 0) c->last_local_nnz = 0;
+    if (nnz_super == 0) c->last_local_nnz = c->last_max_local_nnz = 0;
+    c->last_total_nnz = nnz_super;
+    c->km_settled_off = false;
     if (nnz_super > 0) {
       // this rank's gate hits were appended to the edge list by the count pass (when the list was on and did
       // not overflow): scatter them; otherwise stream the plane a second time (fill pass)
@@ -450,6 +509,10 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
         CK(c, launch_stream(c, cp, 3, false));
       }
       c->last_local_nnz = local_nnz;
+      c->last_max_local_nnz = local_nnz;
+      if (sharded)
+        for (int r = 0; r < c->world; ++r)
+          c->last_max_local_nnz = std::max(c->last_max_local_nnz, c->h_rowptr_cut[r + 1] - c->h_rowptr_cut[r]);
       CK(c, launch_csr_check(c, cp));
       if (sharded) {
         if ((rc = comm_gather_edges(c, c->h_rowptr_cut))) return rc;
@@ -500,10 +563,22 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
   CK(c, launch_solve(c, cp));
   // opt-in estimators replace the transform (and the RMSE after it); the pair statistics stay k_solve's
   if (c->cfg.solver != GHICP_SOLVER_SVD) CK(c, launch_solve_alt(c, c->cfg.solver));
-  CK(c, launch_apply(c));
+  CK(c, launch_apply(c, km_settled));
   CK(c, cudaEventRecord(c->ev[3], st));
   CK(c, cudaMemcpyAsync(c->h_iter, c->d_iter, sizeof(DevIter), cudaMemcpyDeviceToHost, st));
   CK(c, cudaStreamSynchronize(st));
+  if (km_settled) {
+    if (c->h_iter->overflow_any) {   // some rank's candidate block overflowed: nothing was updated, take the general route
+      c->km_settled_off = true;
+      return iterate_impl(c, out);
+    }
+    if ((rc = km_auction_settled_result(c, &kres))) return rc;
+    c->last_total_nnz = c->h_iter->nnz;
+    c->last_local_nnz = (long long)c->h_xcounts[c->rank];
+    c->last_max_local_nnz = 0;
+    for (int r = 0; r < c->world; ++r) c->last_max_local_nnz = std::max(c->last_max_local_nnz, (long long)c->h_xcounts[r]);
+    c->settled_iterations++;
+  }
   if (nnz < 0) nnz = (long long)c->h_sdev->nnz_valid;
 
   // ---- host tail (scalars only) -----------------------------------------------------------
@@ -658,7 +733,7 @@ int ghicp_set_keypoints(ghicp_ctx *ctx, const double *sxyz, int N, const double 
     c->have_bsc = c->have_fpfh = c->fd_built = false;
     c->have_normals = false;
     c->have_prev = false;
-    c->last_local_nnz = -1;
+    c->last_local_nnz = -1; c->last_total_nnz = -1; c->last_max_local_nnz = -1; c->km_settled_off = false;
     reset_loop_state(c);
   }
   const size_t need = 3 * ((size_t)N + M) * sizeof(double);
@@ -668,11 +743,12 @@ int ghicp_set_keypoints(ghicp_ctx *ctx, const double *sxyz, int N, const double 
     c->h_stage_cap = need;
   }
   // pageable -> pinned staging, pipelined with the DMA: the target is staged while the source is in flight,
-  // and the centroid is taken from the staged copy while the target is in flight
+  // and the centroid is taken while the target is in flight.  Page-locked caller buffers are read by the DMA directly.
   double *hs = c->h_stage, *ht = c->h_stage + 3 * (size_t)N;
-  std::memcpy(hs, sxyz, 3 * (size_t)N * sizeof(double));
+  const bool pin_s = is_pinned(sxyz), pin_t = is_pinned(txyz);
+  if (pin_s) hs = const_cast<double *>(sxyz); else std::memcpy(hs, sxyz, 3 * (size_t)N * sizeof(double));
   CK(c, cudaMemcpyAsync(c->d_s, hs, 3 * (size_t)N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  std::memcpy(ht, txyz, 3 * (size_t)M * sizeof(double));
+  if (pin_t) ht = const_cast<double *>(txyz); else std::memcpy(ht, txyz, 3 * (size_t)M * sizeof(double));
   CK(c, cudaMemcpyAsync(c->d_t, ht, 3 * (size_t)M * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   {  // centre of the FP32 filter coordinates: target centroid
     double cx = 0, cy = 0, cz = 0;
@@ -792,8 +868,10 @@ int ghicp_get_pairs(ghicp_ctx *ctx, int *sp, int *tp, int cap, int *n) {
   const int cor = c->last_cor;
   *n = cor;
   const int k = std::min(cor, cap);
-  if (k > 0 && sp) CK(c, cudaMemcpy(sp, c->d_sp, sizeof(int) * (size_t)k, cudaMemcpyDeviceToHost));
-  if (k > 0 && tp) CK(c, cudaMemcpy(tp, c->d_tp, sizeof(int) * (size_t)k, cudaMemcpyDeviceToHost));
+  // both lists in flight at once, one synchronize (page-locked destinations are written by the DMA directly)
+  if (k > 0 && sp) CK(c, cudaMemcpyAsync(sp, c->d_sp, sizeof(int) * (size_t)k, cudaMemcpyDeviceToHost, c->stream));
+  if (k > 0 && tp) CK(c, cudaMemcpyAsync(tp, c->d_tp, sizeof(int) * (size_t)k, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
   return GHICP_OK;
 }
 
@@ -802,7 +880,21 @@ int ghicp_get_source(ghicp_ctx *ctx, double *sxyz) {
   if (!c || !sxyz || c->N <= 0) return GHICP_E_ARG;
   int rc;
   if ((rc = use_device(c))) return rc;
-  CK(c, cudaMemcpy(sxyz, c->d_s, 3 * (size_t)c->N * sizeof(double), cudaMemcpyDeviceToHost));
+  CK(c, cudaMemcpyAsync(sxyz, c->d_s, 3 * (size_t)c->N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  return GHICP_OK;
+}
+
+// Page-locked host memory for the caller's coordinate / result buffers: set_keypoints, get_pairs and get_source then move
+// the data with one DMA each, no staging copy.
+int ghicp_host_alloc(size_t bytes, void **out) {
+  if (!out || bytes == 0) return GHICP_E_ARG;
+  if (ghicp_device_count() <= 0) { set_error(nullptr, "host_alloc: no CUDA device"); return GHICP_E_NODEV; }
+  if (cudaMallocHost(out, bytes) != cudaSuccess) { cudaGetLastError(); *out = nullptr; return GHICP_E_NOMEM; }
+  return GHICP_OK;
+}
+int ghicp_host_free(void *p) {
+  if (p && cudaFreeHost(p) != cudaSuccess) { cudaGetLastError(); return GHICP_E_CUDA; }
   return GHICP_OK;
 }
 
@@ -867,7 +959,7 @@ int ghicp_reset(ghicp_ctx *ctx) {
   if (!c) return GHICP_E_ARG;
   reset_loop_state(c);
   c->have_prev = false;
-  c->last_local_nnz = -1;
+  c->last_local_nnz = -1; c->last_total_nnz = -1; c->last_max_local_nnz = -1; c->km_settled_off = false;
   c->last_cands = 0;
   c->last_cor = 0;
   return GHICP_OK;
@@ -1222,7 +1314,7 @@ int ghicp_set_from_prep(ghicp_ctx *ctx, const ghicp_prep *src, const ghicp_prep 
     c->have_bsc = c->have_fpfh = c->fd_built = false;
     c->have_normals = false;
     c->have_prev = false;
-    c->last_local_nnz = -1;
+    c->last_local_nnz = -1; c->last_total_nnz = -1; c->last_max_local_nnz = -1; c->km_settled_off = false;
     reset_loop_state(c);
   }
   CK(c, cudaMemcpyAsync(c->d_s, src->d_kp_xyz, 3 * (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));

@@ -152,4 +152,13 @@ int comm_gather_edges(Ctx *c, const long long *cut) {
   return GHICP_OK;
 }
 
+// The one exchange of a settled KM iteration: every rank's candidate block (header with its partial CD sums + gate-checked
+// edges) to every rank, in stream, nothing read by the host.
+int comm_allgather_bytes(Ctx *c, const void *send, void *recv, size_t bytes) {
+  if (c->world == 1) return GHICP_OK;
+  NCK(c, g_nccl.AllGather(send, recv, bytes, ncclInt8, (ncclComm_t)c->nccl_comm, c->stream));
+  c->exchanges++;
+  return GHICP_OK;
+}
+
 }  // namespace ghicp_b200

@@ -96,6 +96,13 @@ struct StreamArgs {
   unsigned long long *emit; unsigned long long emit_cap;  // KM edge list: (row << 32 | col) per gate hit
 };
 
+// header of the per-rank candidate block of a settled KM iteration (ghicp_stream.cu: k_emit_check)
+struct XBlockHdr {
+  unsigned long long count;   // candidate edges that follow (0 when the rank overflowed: stats[2] = 1)
+  double stats[4];            // the rank's partial CD sums (sum, sum of squares), overflow flag, spare
+  unsigned long long pad[3];  // 64 bytes: the arrays behind it stay 16-byte aligned
+};
+
 // ---- the context ----------------------------------------------------------------------------------
 struct Ctx {
   ghicp_config cfg{};
@@ -222,6 +229,16 @@ struct Ctx {
   int *d_colg_idx = nullptr;                // [world][M]
   long long *h_rowptr_cut = nullptr;        // pinned [world + 1] CSR offsets at the shard boundaries
   int exchanges = 0;
+  // settled KM iteration: one candidate block per rank, one all-gather, no host round trip inside the iteration
+  size_t xcap = 0;                          // candidate edges a block can carry
+  unsigned char *d_xsend = nullptr;         // this rank's block
+  unsigned char *d_xrecv = nullptr;         // [world] blocks (world > 1)
+  long long last_total_nnz = -1;            // candidate edges of the whole graph last iteration (-1: no history)
+  long long last_max_local_nnz = -1;        // largest per-rank share of them
+  unsigned long long *d_xcounts = nullptr;  // [world] edges per block (device)
+  unsigned long long *h_xcounts = nullptr;  // pinned copy
+  bool km_settled_off = false;              // the last settled attempt overflowed: take the general route once
+  int settled_iterations = 0;
 };
 
 struct KmResult {
@@ -241,7 +258,7 @@ cudaError_t launch_select_nn(Ctx *c, double amb_rel = 0.0);    // flags from row
 cudaError_t launch_select_nnr(Ctx *c);
 cudaError_t launch_select_km(Ctx *c);    // from d_owner
 cudaError_t launch_solve(Ctx *c, const CostParams &cp);  // stats + umeyama + rmse_after → d_iter
-cudaError_t launch_apply(Ctx *c);
+cudaError_t launch_apply(Ctx *c, bool guard_overflow = false);   // guard: no update when DevIter::overflow_any is set
 cudaError_t launch_solve_explicit(cudaStream_t stream, const double *d_s, const double *d_t, int n, DevIter *d_iter);
 cudaError_t launch_get_fd(Ctx *c, double *d_out);
 cudaError_t launch_scan_counts(Ctx *c);  // d_cnt → d_rowptr, nnz → d_iter->nnz
@@ -300,12 +317,20 @@ cudaError_t launch_scan_rows(Ctx *c);
 cudaError_t launch_emit_scatter(Ctx *c, const CostParams &cp, unsigned long long n_emitted);
 cudaError_t launch_csr_check(Ctx *c, const CostParams &cp);
 int stream_num_parts(const Ctx *c);
+size_t xblock_bytes(size_t xcap);
+cudaError_t launch_emit_check(Ctx *c, const CostParams &cp);   // this rank's gate hits, checked exactly -> d_xsend
+cudaError_t launch_xbuild(Ctx *c);                             // gathered blocks -> statistics + CSR, all on the device
 
 // ---- KM (ghicp_auction.cu) ----------------------------------------------------------------------
 // Solves max-gain partial matching on the CSR in the ctx (rows = persons). Result in d_owner/d_assign.
 int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, double max_gain,
                KmResult *res);
 cudaError_t launch_build_csc(Ctx *c, int n_rows, int n_cols, long long nnz);
+// settled loop (sparse graph): the same single forward phase, edge count read on the device, nothing read back;
+// counters land in h_counters with the iteration's final copy (km_auction_settled_result after the synchronize)
+cudaError_t launch_build_csc_dev(Ctx *c, int n_rows, int n_cols, const long long *d_nnz, long long nnz_bound);
+int km_auction_settled(Ctx *c, int n_rows, int n_cols, long long nnz_hint, double eps_final);
+int km_auction_settled_result(Ctx *c, KmResult *res);
 
 // ---- multi-GPU exchange (ghicp_comm.cu) ------------------------------------------------------------
 int comm_unique_id(void *id128);
@@ -315,6 +340,7 @@ int comm_warmup(Ctx *c);
 int comm_exchange(Ctx *c, int what);         // bit0 stats, bit1 rows, bit2 columns
 int comm_gather_counts(Ctx *c);
 int comm_gather_edges(Ctx *c, const long long *cut);
+int comm_allgather_bytes(Ctx *c, const void *send, void *recv, size_t bytes);   // the one exchange of a settled KM iteration
 
 // misc
 int ensure_capacity(Ctx *c, void **ptr, size_t *cap, size_t need_bytes);

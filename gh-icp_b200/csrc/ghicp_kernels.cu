@@ -737,9 +737,10 @@ __global__ void __launch_bounds__(COOP ? 256 : 1024) k_solve(const SolveArgs a) 
 }
 
 // KP.kpSXYZ.row(i) = (R * row^T + t)^T for ALL source keypoints (src/ghicp_reg.cpp:891-894)
-__global__ void k_apply(double *__restrict__ s, int N, const DevIter *__restrict__ iter) {
+__global__ void k_apply(double *__restrict__ s, int N, const DevIter *__restrict__ iter, int guard_overflow) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
+  if (guard_overflow && iter->overflow_any) return;   // settled KM iteration whose candidate block overflowed: redone by the host
   const double *Rt = iter->Rt;
   const double x = s[i], y = s[(size_t)N + i], z = s[2 * (size_t)N + i];
   s[i] = ((Rt[0] * x + Rt[4] * y) + Rt[8] * z) + Rt[12];
@@ -957,8 +958,8 @@ cudaError_t launch_solve_explicit(cudaStream_t stream, const double *d_s, const 
   return cudaGetLastError();
 }
 
-cudaError_t launch_apply(Ctx *c) {
-  GHICP_LAUNCH(k_apply, (c->N + 255) / 256, 256, 0, c->stream, c->d_s, c->N, c->d_iter);
+cudaError_t launch_apply(Ctx *c, bool guard_overflow) {
+  GHICP_LAUNCH(k_apply, (c->N + 255) / 256, 256, 0, c->stream, c->d_s, c->N, c->d_iter, guard_overflow ? 1 : 0);
   c->launches++;
   return cudaGetLastError();
 }

@@ -32,12 +32,22 @@ constexpr int ST_CPL = 8;                         // columns per lane
 constexpr int ST_PANEL = 32 * ST_CPL;             // columns per warp
 constexpr int ST_CTA_COLS = ST_WARPS * ST_PANEL;  // 2048
 constexpr int ST_RB = 256;                        // source rows per CTA
-constexpr int ST_UNROLL = 4;
+// tuning knobs (compile-time; tools/build_variants.sh builds A/B libraries with other values)
+#ifndef GHICP_ST_UNROLL
+#define GHICP_ST_UNROLL 4
+#endif
+#ifndef GHICP_ST_STAGES
+#define GHICP_ST_STAGES 6
+#endif
+#ifndef GHICP_ST_MINB
+#define GHICP_ST_MINB 2
+#endif
+constexpr int ST_UNROLL = GHICP_ST_UNROLL;
 constexpr unsigned INF_BITS = 0x7f800000u;
 // TMA staging of the FD plane: every warp runs its own ring of ST_STAGES stages; a stage holds ST_UNROLL
 // row segments of the warp's 256-column panel (512 B each), brought in by cp.async.bulk (TMA engine,
 // UBLKCP) and signalled on one mbarrier per stage.  No registers are tied up by loads in flight.
-constexpr int ST_STAGES = 6;
+constexpr int ST_STAGES = GHICP_ST_STAGES;
 constexpr int ST_SEG_BYTES = ST_PANEL * 2;                   // 512
 constexpr int ST_STAGE_BYTES = ST_UNROLL * ST_SEG_BYTES;     // 2048
 constexpr int ST_RING_BYTES = ST_STAGES * ST_STAGE_BYTES;    // per warp
@@ -308,6 +318,10 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, c
   const unsigned short bh = (unsigned short)(a.bh | (unsigned short)(s_thr[0] >> 31));
   const float margin = a.dev->margin;
   const float m2 = 2.f * margin;
+  if (MODE == SM_NNR) {
+#pragma unroll
+    for (int c = 0; c < ST_CPL; ++c) colrun[c] += m2;   // (padding columns: cd = +inf never passes a finite threshold)
+  }
   const float thr_hi = a.dev->thr_hi;
   const float b = a.b;
   const bool lane_loads = true;  // the panel-major plane is allocated in whole panels (zero padded)
@@ -432,16 +446,22 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, c
             for (int c = 0; c < ST_CPL; ++c) slow_row(a, r0 + r, j0 + c, cd[c], lim);
             if (lane == 0) atomicMin(&s_thr[r], wmin);
           }
-          if (MODE == SM_NNR) {
+          if (MODE == SM_NNR && do_rows) {
+            // columns: every value within 2*margin of the column's seed (an upper bound of its minimum up to one margin:
+            // last iteration's partner evaluated exactly, or the FP32 minimum of the seed pass) is evaluated exactly.
+            // The threshold is FIXED for the sweep (colrun holds seed + 2*margin): a running minimum would only save
+            // refinements that are already rare, at the price of two more instructions per pair.
             bool hit = false;
 #pragma unroll
-            for (int c = 0; c < ST_CPL; ++c) hit |= (cd[c] <= colrun[c] + m2);
+            for (int c = 0; c < ST_CPL; ++c) hit |= (cd[c] <= colrun[c]);
             if (hit) {
 #pragma unroll
-              for (int c = 0; c < ST_CPL; ++c) slow_col(a, r0 + r, j0 + c, cd[c], colrun[c] + m2);
+              for (int c = 0; c < ST_CPL; ++c) slow_col(a, r0 + r, j0 + c, cd[c], colrun[c]);
             }
+            // rare path only: tighten (a column without a seed — its last partner lives on another rank — starts at
+            // +inf and must not send its whole length to the exact evaluation)
 #pragma unroll
-            for (int c = 0; c < ST_CPL; ++c) colrun[c] = fminf(colrun[c], cd[c]);
+            for (int c = 0; c < ST_CPL; ++c) colrun[c] = fminf(colrun[c], cd[c] + m2);
           }
         } else {
           // KM gate on the superset threshold (exactly re-checked per CSR entry afterwards)
@@ -492,11 +512,6 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, c
 #pragma unroll
           for (int u = 0; u < ST_UNROLL; ++u) decide_row(u, cdm[u], true);
         }
-      } else if (MODE == SM_NNR) {
-        // (batch-level votes push this variant, with its eight running column minima, into register spills:
-        // measured slower than the per-row form)
-#pragma unroll
-        for (int u = 0; u < ST_UNROLL; ++u) decide_row(u, cdm[u], true);
       } else {
         // one vote per batch: does any lane hold a value that can touch the running minimum of its row?
         // (for the seed passes: strictly below it)
@@ -507,6 +522,16 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, c
           const float m8 = fminf(fminf(fminf(cd[0], cd[1]), fminf(cd[2], cd[3])), fminf(fminf(cd[4], cd[5]), fminf(cd[6], cd[7])));
           const float run = __uint_as_float(thrbase[u]);
           touch |= (MODE == SM_PRE || MODE == SM_PRE_COLS) ? (m8 < run) : (m8 <= run + m2);
+        }
+        if (MODE == SM_NNR) {
+          // ... or one that can touch its column's threshold (minimum over the batch's rows per column first)
+#pragma unroll
+          for (int cc = 0; cc < ST_CPL; ++cc) {
+            float bmc = cdm[0][cc];
+#pragma unroll
+            for (int u = 1; u < ST_UNROLL; ++u) bmc = fminf(bmc, cdm[u][cc]);
+            touch |= (bmc <= colrun[cc]);
+          }
         }
         const bool do_rows = __any_sync(0xffffffffu, touch);
 #pragma unroll
@@ -551,7 +576,7 @@ __device__ __forceinline__ void sweep(const StreamArgs &a, const float4 *s_S4, c
 }
 
 template <int MODE, bool HAS_FD, bool STATS, bool TMA, bool X2>
-__global__ void __launch_bounds__(ST_THREADS, (TMA && !X2) ? 3 : 2) k_stream(const StreamArgs a) {
+__global__ void __launch_bounds__(ST_THREADS, (TMA && !X2) ? 3 : GHICP_ST_MINB) k_stream(const StreamArgs a) {
   __shared__ __align__(16) float s_S8[X2 ? ST_RB * 8 : 8];
 #if defined(GHICP_EMU_HOST)
   unsigned char *s_ring = reinterpret_cast<unsigned char *>(emu::dyn_smem());   // host emulation: the launch's dynamic shared memory
@@ -717,6 +742,77 @@ __global__ void k_emit_scatter(const StreamArgs a, unsigned long long n) {
     const long long pos = a.rowptr[row] + atomicAdd(&a.cursor[row], 1);
     a.csr_col[pos] = col;
   }
+}
+
+
+// ---- settled KM iteration: the candidate graph travels as ONE block per rank, no host round trip -----------------------
+// Block layout (bytes): XBlockHdr | keys[xcap] (row << 32 | col) | gains[xcap] (double) | fds[xcap] (float).
+// Every rank gate-checks its own hits exactly (k_emit_check), ONE all-gather moves the blocks, and every rank builds
+// the same CSR from all of them (k_xcount -> tiled scan -> k_xscatter; the order inside a row is arbitrary: the auction
+// breaks ties by a hash of (row, col), never by position).
+__global__ void __launch_bounds__(256) k_emit_check(const StreamArgs a, const DevIter *iter, const double *__restrict__ xstats_rank,
+                                                    XBlockHdr *hdr, unsigned long long *__restrict__ xkey,
+                                                    double *__restrict__ xgain, float *__restrict__ xfd, unsigned long long xcap) {
+  const unsigned long long count = a.dev->emit_count;
+  const bool ovf = count > xcap || count > a.emit_cap;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    hdr->count = ovf ? 0ull : count;
+    hdr->stats[0] = xstats_rank[0]; hdr->stats[1] = xstats_rank[1];
+    hdr->stats[2] = ovf ? 1.0 : 0.0;   // picked up by k_penalty as DevIter::overflow_any (on every rank)
+    hdr->stats[3] = 0.0;
+  }
+  if (ovf) return;
+  const double penalty = iter->penalty;
+  for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < count;
+       k += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long e = a.emit[k];
+    const int i = (int)(e >> 32), j = (int)(unsigned)e;
+    const double cd = exact_cd(a, i, j);
+    xkey[k] = e;
+    xgain[k] = cd < penalty ? penalty - cd : -1e300;   // src/ghicp_reg.cpp:362-363 (strict <)
+    xfd[k] = a.fd ? __half2float(__ushort_as_half(a.fd[fd_index(a.fd_rows, i - a.row0, j)])) : 0.f;
+  }
+}
+__device__ __forceinline__ const XBlockHdr *xblock_hdr(const unsigned char *blocks, size_t block_bytes, int r) {
+  return reinterpret_cast<const XBlockHdr *>(blocks + (size_t)r * block_bytes);
+}
+// per-row candidate counts over all blocks (blockIdx.y = rank); block (0, r) also unpacks the rank's partial CD sums
+__global__ void k_xcount(const unsigned char *__restrict__ blocks, size_t block_bytes, unsigned long long xcap, int *__restrict__ cnt,
+                         double *__restrict__ xstats, unsigned long long *__restrict__ xcounts) {
+  const int r = blockIdx.y;
+  const XBlockHdr *h = xblock_hdr(blocks, block_bytes, r);
+  if (blockIdx.x == 0 && threadIdx.x < 4) xstats[4 * r + threadIdx.x] = h->stats[threadIdx.x];
+  if (blockIdx.x == 0 && threadIdx.x == 4) xcounts[r] = h->count;
+  const unsigned long long count = h->count < xcap ? h->count : xcap;
+  const unsigned long long *key = reinterpret_cast<const unsigned long long *>(h + 1);
+  for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < count;
+       k += (unsigned long long)gridDim.x * blockDim.x)
+    atomicAdd(&cnt[(int)(key[k] >> 32)], 1);
+}
+__global__ void k_xscatter(const unsigned char *__restrict__ blocks, size_t block_bytes, unsigned long long xcap,
+                           const long long *__restrict__ rowptr, int *__restrict__ cursor, int *__restrict__ csr_col,
+                           double *__restrict__ csr_gain, float *__restrict__ csr_fd, StreamDev *dev) {
+  const int r = blockIdx.y;
+  const XBlockHdr *h = xblock_hdr(blocks, block_bytes, r);
+  const unsigned long long count = h->count < xcap ? h->count : xcap;
+  const unsigned long long *key = reinterpret_cast<const unsigned long long *>(h + 1);
+  const double *gain = reinterpret_cast<const double *>(key + xcap);
+  const float *fd = reinterpret_cast<const float *>(gain + xcap);
+  int valid = 0;
+  for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < count;
+       k += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long e = key[k];
+    const int row = (int)(e >> 32);
+    const long long pos = rowptr[row] + atomicAdd(&cursor[row], 1);
+    const double g = gain[k];
+    csr_col[pos] = (int)(unsigned)e;
+    csr_gain[pos] = g;
+    csr_fd[pos] = fd[k];
+    valid += g > 0.0 ? 1 : 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) valid += __shfl_xor_sync(0xffffffffu, valid, o);
+  if ((threadIdx.x & 31) == 0 && valid) atomicAdd(&dev->nnz_valid, (unsigned long long)valid);
 }
 
 }  // namespace
@@ -922,6 +1018,38 @@ cudaError_t launch_emit_scatter(Ctx *c, const CostParams &cp, unsigned long long
 cudaError_t launch_csr_check(Ctx *c, const CostParams &cp) {
   StreamArgs a = make_args(c, cp);
   GHICP_LAUNCH(k_csr_check, 148 * 4, 256, 0, c->stream, a, c->d_iter, c->d_csr_gain);
+  c->launches++;
+  return cudaGetLastError();
+}
+
+
+// ---- settled KM iteration (see the kernels above) -------------------------------------------------------------------
+size_t xblock_bytes(size_t xcap) { return sizeof(XBlockHdr) + xcap * (sizeof(unsigned long long) + sizeof(double) + sizeof(float)); }
+cudaError_t launch_emit_check(Ctx *c, const CostParams &cp) {
+  StreamArgs a = make_args(c, cp);
+  unsigned char *blk = c->d_xsend;
+  XBlockHdr *hdr = reinterpret_cast<XBlockHdr *>(blk);
+  unsigned long long *key = reinterpret_cast<unsigned long long *>(hdr + 1);
+  double *gain = reinterpret_cast<double *>(key + c->xcap);
+  float *fd = reinterpret_cast<float *>(gain + c->xcap);
+  GHICP_LAUNCH(k_emit_check, 148 * 2, 256, 0, c->stream, a, c->d_iter, c->d_xstats + 4 * c->rank, hdr, key, gain, fd,
+               (unsigned long long)c->xcap);
+  c->launches++;
+  return cudaGetLastError();
+}
+// gathered blocks -> d_xstats, CSR (d_rowptr / d_csr_*), DevIter::nnz, StreamDev::nnz_valid; no host involvement
+cudaError_t launch_xbuild(Ctx *c) {
+  const unsigned char *blocks = c->world > 1 ? c->d_xrecv : c->d_xsend;
+  const size_t bb = xblock_bytes(c->xcap);
+  cudaMemsetAsync(c->d_cnt, 0, sizeof(int) * ((size_t)c->Npad + 2), c->stream);
+  cudaMemsetAsync(&c->d_sdev->nnz_valid, 0, sizeof(unsigned long long), c->stream);
+  const dim3 grid(32, c->world);
+  GHICP_LAUNCH(k_xcount, grid, 256, 0, c->stream, blocks, bb, (unsigned long long)c->xcap, c->d_cnt, c->d_xstats, c->d_xcounts);
+  c->launches++;
+  cudaError_t e = launch_scan_rows(c);
+  if (e != cudaSuccess) return e;
+  GHICP_LAUNCH(k_xscatter, grid, 256, 0, c->stream, blocks, bb, (unsigned long long)c->xcap, c->d_rowptr, c->d_cursor, c->d_csr_col,
+               c->d_csr_gain, c->d_csr_fd, c->d_sdev);
   c->launches++;
   return cudaGetLastError();
 }

@@ -147,16 +147,27 @@ class GHRegistration:
         capi.check(self.L.ghicp_run(self.ctx, capi._dp(Rt), C.byref(it)), self.ctx)
         return Rt.reshape(4, 4).T.copy(), it.value
 
-    def pairs(self):
+    def pairs(self, out=None):
+        """(SP, TP) of the last iteration.  out = (sp, tp) int32 buffers of >= max(N, M) entries (e.g. capi.pinned_empty):
+        views of them are returned, nothing is allocated or copied on the host."""
         cap = max(self.N, self.M)
-        sp = np.zeros(cap, np.int32)
-        tp = np.zeros(cap, np.int32)
+        if out is None:
+            sp = np.zeros(cap, np.int32)
+            tp = np.zeros(cap, np.int32)
+        else:
+            sp, tp = out
+            cap = min(cap, sp.shape[0], tp.shape[0])
         n = C.c_int(0)
         capi.check(self.L.ghicp_get_pairs(self.ctx, capi._ip(sp), capi._ip(tp), cap, C.byref(n)), self.ctx)
-        return sp[:n.value].copy(), tp[:n.value].copy()
+        k = min(n.value, cap)
+        if out is None:
+            return sp[:k].copy(), tp[:k].copy()
+        return sp[:k], tp[:k]
 
-    def source(self):
-        out = np.zeros((self.N, 3), dtype=np.float64, order="F")
+    def source(self, out=None):
+        """Current source keypoints (N, 3), column-major like Eigen::MatrixX3d; out = a buffer of that layout to fill."""
+        if out is None:
+            out = np.zeros((self.N, 3), dtype=np.float64, order="F")
         capi.check(self.L.ghicp_get_source(self.ctx, capi._dp(out)), self.ctx)
         return out
 

@@ -150,6 +150,11 @@ int ghicp_run(ghicp_ctx *ctx, double Rt_final[16], int *iterations);
 int ghicp_get_pairs(ghicp_ctx *ctx, int *sp, int *tp, int cap, int *n); /* SP/TP index lists */
 int ghicp_get_source(ghicp_ctx *ctx, double *sxyz);                     /* current KP.kpSXYZ */
 int ghicp_get_rt(ghicp_ctx *ctx, double Rt_tillnow[16]);
+/* Page-locked host memory (cudaMallocHost).  Optional: coordinate / result buffers allocated here (or page-locked by the
+ * caller in any other way) are moved by ghicp_set_keypoints / ghicp_get_pairs / ghicp_get_source with one DMA each; pageable
+ * buffers go through a staging copy inside the library.  The reference has no counterpart (its matrices live in host RAM). */
+int ghicp_host_alloc(size_t bytes, void **out);
+int ghicp_host_free(void *p);
 /* FD plane as doubles, row-major N x M (Energyfunction::FD). Test/debug: O(N*M) host memory. */
 int ghicp_get_fd(ghicp_ctx *ctx, double *fd);
 /* Per-source-row argmin of CD for the state *before* the next iterate (NN scan,

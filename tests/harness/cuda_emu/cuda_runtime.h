@@ -50,6 +50,10 @@ inline cudaError_t cudaMalloc(void **p, size_t bytes) { *p = emu_poisoned(bytes)
 inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
 template <typename T> inline cudaError_t cudaMallocHost(T **p, size_t bytes) { *p = (T *)emu_poisoned(bytes); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+// every host pointer is "pageable" here: the library's staging path is the one exercised
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2 };
+struct cudaPointerAttributes { cudaMemoryType type; };
+inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *) { a->type = cudaMemoryTypeUnregistered; return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void *d, const void *s, size_t bytes, cudaMemcpyKind) { memmove(d, s, bytes); return cudaSuccess; }
 inline cudaError_t cudaMemset(void *p, int v, size_t bytes) { memset(p, v, bytes); return cudaSuccess; }
 inline cudaError_t cudaMemGetInfo(size_t *free_b, size_t *total_b) { *free_b = (size_t)8 << 30; *total_b = (size_t)8 << 30; return cudaSuccess; }

@@ -26,12 +26,27 @@ def make_pair(g, orc, scene, Ft, Ct, dof=6, solve_mode=1, **kw):
 
 
 # ---- one-time FD build ---------------------------------------------------------------------------
-@pytest.mark.parametrize("bits,V,dof", [(441, 4, 6), (672, 4, 6), (441, 2, 4), (64, 4, 6), (9, 2, 4)])
+# 672 / 700 bits: K-chunked tcgen05 kernel with a 256-row B tile; 1000 / 1400: 128 rows; 2048 (the fp16 plane's limit): 64 rows
+@pytest.mark.parametrize("bits,V,dof", [(441, 4, 6), (672, 4, 6), (441, 2, 4), (64, 4, 6), (9, 2, 4), (672, 2, 4), (700, 4, 6),
+                                        (1000, 4, 6), (1400, 2, 4), (2048, 4, 6)])
 @pytest.mark.parametrize("N,M", [(257, 131), (64, 300)])
 def test_fd_bsc_bit_exact(g, orc, bits, V, dof, N, M):
     sc = g.synth.add_bsc(g.synth.gen_points(N, M, seed=bits + N), bits=bits, V=V)
     reg, o = make_pair(g, orc, sc, g.FT_BSC, g.CT_NN, dof=dof)
     assert np.array_equal(reg.fd(), o.fd())
+
+
+def test_fd_bsc_672_many_tiles_equals_popc_kernel(g, orc, monkeypatch):
+    """672-bit descriptors at a size with many A tiles and several CTAs: the K-chunked tensor-core build against the oracle and
+    against the XOR + POPC kernel (GHICP_FD_POPC=1)."""
+    sc = g.synth.add_bsc(g.synth.gen_points(700, 1500, seed=672), bits=672, V=4)
+    reg, o = make_pair(g, orc, sc, g.FT_BSC, g.CT_NN, dof=6)
+    a = reg.fd()
+    assert np.array_equal(a, o.fd())
+    monkeypatch.setenv("GHICP_FD_POPC", "1")
+    reg2 = g.registration.from_scene(sc, g.FT_BSC, g.CT_NN, dof=6)
+    reg2.build_fd()
+    assert np.array_equal(reg2.fd(), a)
 
 
 @pytest.mark.parametrize("N,M", [(100, 77), (33, 260)])
