@@ -54,7 +54,7 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clock / throttle reasons sampled DURING the timed region (NVML, every 5 ms; nvidia-smi fallback)."""
+    """SM clock / throttle reasons sampled DURING the timed region (NVML, every 10 ms; nvidia-smi fallback)."""
 
     def __init__(self, dev=0):
         self.rows, self.stop, self.dev = [], threading.Event(), dev
@@ -78,7 +78,7 @@ class ClockSampler:
                     rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
                         else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
                     self.rows.append((sm, mx, rs))
-                    self.stop.wait(0.005)
+                    self.stop.wait(0.01)
                 else:
                     q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
                          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -297,6 +297,27 @@ def cpu_arm(g, wl, warmup, steps, sizes, fit_steps=3, threads=1, budget_s=240.0)
 
 
 def main():
+    # stdout carries exactly ONE JSON line: whatever libraries print on fd 1 while we run (NCCL's version banner, ...) goes to
+    # stderr; the line itself is written to the saved descriptor at the end
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        _main(saved_stdout)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
+
+
+def _main(saved_stdout):
+    def emit(line):
+        sys.stdout.flush()
+        if sys.stdout is not sys.__stdout__:      # run in-process by a harness that replaced sys.stdout (pytest's capsys)
+            print(json.dumps(line))
+        else:
+            os.write(saved_stdout, (json.dumps(line) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -354,7 +375,7 @@ def main():
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": cb["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "ladder": cb["ladder"], "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
-        print(json.dumps(line))
+        emit(line)
         return
 
     # ---------------- our arm --------------------------------------------------------------------------
@@ -457,13 +478,16 @@ def main():
         st = reg.iterate()
 
     # ---- timed region 1: device-resident steps -----------------------------------------------------
-    barrier()
     launches = 0
-    dev_ms, stage = [], []
+    dev_ms, wall_ms, stage = [], [], []
     with ClockSampler(dev) as cs:
+        time.sleep(0.05)   # the sampler thread's start-up (NVML handles) must not desynchronise the ranks' first timed step
+        barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
+            t_step = time.perf_counter()
             st = reg.iterate()  # ends with a stream synchronize
+            wall_ms.append((time.perf_counter() - t_step) * 1e3)
             dev_ms.append(st.ms_total)
             stage.append((st.ms_cost, st.ms_corr, st.ms_solve, st.nnz, st.km_rounds, st.cor, st.ms_stream,
                           st.stream_passes, st.exact_fallback, st.candidates))
@@ -545,6 +569,8 @@ def main():
                     "`registration` holds the whole-registration figure, dense first iterations included",
         "registration": registration,
         "device_ms_per_step": float(np.mean(dev_ms)),
+        # rank 0's view of every timed step: CUDA-event time of the iteration, wall time of the ghicp_iterate call
+        "per_step": {"device_ms": [round(x, 3) for x in dev_ms], "wall_ms": [round(x, 3) for x in wall_ms]},
         "stage_ms": {"cost": cost_ms, "corr": float(np.median(stage[:, 1])), "solve": float(np.median(stage[:, 2]))},
         "km": {"nnz": int(np.median(stage[:, 3])), "rounds": int(np.median(stage[:, 4]))} if km else None,
         "cor": int(stage[-1, 5]),
@@ -578,7 +604,7 @@ def main():
                                                 "single_thread_ms_per_iteration_sample": cb["ms_per_step_sample"]}
         except Exception as e:  # the OpenMP oracle is optional test infrastructure
             line["cpu_baseline"]["fair_cpu"] = {"unavailable": str(e)[:200]}
-    print(json.dumps(line))
+    emit(line)
 
 
 if __name__ == "__main__":

@@ -312,6 +312,31 @@ __device__ __forceinline__ void rev_offer_one(const AucArgs &a, int j, int lane)
   rev_scan(a, j, lane, a.colptr[j], a.colptr[j + 1], t);
   if (lane == 0) rev_finish(a, j, t);
 }
+// short adjacency lists (a settled loop: about one candidate per keypoint): ONE THREAD per bidder walks its list; the
+// (best, tie-ordered index, second) triple is the same whatever the partition of the list
+template <bool REVERSE>
+__device__ __forceinline__ void bid_serial(const AucArgs &a, int e) {
+  Top2 t;
+  t.best = -1e300; t.second = -1e300; t.idx = -1;
+  double bg = 0.0;
+  if (REVERSE) {
+    for (long long k = a.colptr[e], ke = a.colptr[e + 1]; k < ke; ++k) {
+      const int i = a.csc_row[k];
+      top2_push_h(t, a.csc_gain[k] - ldcg_d(&a.profit[i]), i, e);
+    }
+    rev_finish(a, e, t);
+  } else {
+    for (long long k = a.rowptr[(size_t)e * a.n_chunks], ke = a.rowptr[(size_t)(e + 1) * a.n_chunks]; k < ke; ++k) {
+      const int j = a.csr_col[k];
+      const double g = a.csr_gain[k];
+      const double v = g - ldcg_d(&a.price[j]);
+      if (v > t.best || (v == t.best && t.idx >= 0 && tie_less(e, j, t.idx))) bg = g;
+      top2_push_h(t, v, j, e);
+    }
+    fwd_finish(a, e, t, bg);
+  }
+}
+
 template <typename Append>
 __device__ __forceinline__ void rev_commit_one(const AucArgs &a, int j, Append append) {
   const int i = ldcg_i(&a.bid_obj[j]);
@@ -360,7 +385,7 @@ __device__ __forceinline__ void split_merge(int e, int G, const Top2 *pt, const 
 
 template <bool REVERSE>
 __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a, int *list0, int *list1, int max_rounds,
-                                                                      int small_n) {
+                                                                      int small_n, int short_rows) {
   cg::grid_group grid = cg::this_grid();
   constexpr int NW = PA_THREADS / 32;
   __shared__ int s_n, s_next;
@@ -479,6 +504,8 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
               __syncthreads();
               continue;
             }
+          } else if (short_rows) {
+            for (int w = threadIdx.x; w < m; w += PA_THREADS) bid_serial<REVERSE>(a, ldcg_i(&list[w]));
           } else {
             for (int w = warp; w < m; w += NW) {
               const int e = ldcg_i(&list[w]);
@@ -528,7 +555,9 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
       const long long tw = (long long)gridDim.x * NW;
       if (16ll * n <= tw) G = 16; else if (8ll * n <= tw) G = 8; else if (4ll * n <= tw) G = 4; else if (2ll * n <= tw) G = 2;
     }
-    if (G > 1) {
+    if (short_rows) {
+      for (int w = gtid; w < n; w += gthreads) bid_serial<REVERSE>(a, ldcg_i(&list[w]));
+    } else if (G > 1) {
       const int gpc = NW / G, grp = warp / G, slice = warp % G;
       const int w = blockIdx.x * gpc + grp;   // n <= gridDim.x * gpc by the choice of G
       int e = -1;
@@ -579,11 +608,6 @@ __global__ void k_col_count(const int *__restrict__ csr_col, long long nnz, int 
   const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k < nnz) atomicAdd(&colcnt[csr_col[k]], 1);
 }
-__global__ void k_col_count_dev(const int *__restrict__ csr_col, const long long *__restrict__ d_nnz, int *__restrict__ colcnt) {
-  const long long nnz = *d_nnz;
-  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += (long long)gridDim.x * blockDim.x)
-    atomicAdd(&colcnt[csr_col[k]], 1);
-}
 __global__ void __launch_bounds__(AUC_BLOCK) k_csc_fill(int n_rows, const long long *rowptr, int n_chunks,
                                                          const int *csr_col, const double *csr_gain,
                                                          const long long *colptr, int *cursor, int *csc_row,
@@ -632,20 +656,6 @@ static double single_phase_eps(double eps_final) {
   return f * eps_final;
 }
 
-cudaError_t launch_build_csc_dev(Ctx *c, int n_rows, int n_cols, const long long *d_nnz, long long nnz_bound) {
-  cudaError_t e;
-  if ((e = cudaMemsetAsync(c->d_colcnt, 0, sizeof(int) * (size_t)(n_cols + 1), c->stream)) != cudaSuccess) return e;
-  const long long want = (nnz_bound + 255) / 256;
-  GHICP_LAUNCH(k_col_count_dev, (unsigned)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want)), 256, 0, c->stream, c->d_csr_col, d_nnz,
-               c->d_colcnt);
-  c->launches++;
-  if ((e = launch_scan_i32(c, c->d_colcnt, c->d_colptr, c->d_bid_obj, n_cols, nullptr)) != cudaSuccess) return e;
-  GHICP_LAUNCH(k_csc_fill, AUC_GRID, AUC_BLOCK, 0, c->stream, n_rows, c->d_rowptr, c->n_chunks, c->d_csr_col, c->d_csr_gain,
-               c->d_colptr, c->d_bid_obj, c->d_csc_row, c->d_csc_gain);
-  c->launches++;
-  return cudaGetLastError();
-}
-
 // The settled loop's auction: ONE forward phase at eps_final/2 from zero prices (the sparse-graph schedule of
 // km_auction: every object that ever received a bid stays owned, free objects keep price 0, D = 0, no reverse phase),
 // enqueued without reading anything back.  Correct on any graph; chosen by the caller when last iteration's graph
@@ -683,10 +693,11 @@ int km_auction_settled(Ctx *c, int n_rows, int n_cols, long long nnz_hint, doubl
   sn = sn < 16 ? 16 : (sn > PA_SMALL ? PA_SMALL : sn);
   int *l0 = c->d_list[0], *l1 = c->d_list[1];
   int mr = 4000000;
-  void *args[] = {(void *)&a, (void *)&l0, (void *)&l1, (void *)&mr, (void *)&sn};
+  int sr = avg_row <= 4.0 ? 1 : 0;   // one thread per bidder
+  void *args[] = {(void *)&a, (void *)&l0, (void *)&l1, (void *)&mr, (void *)&sn, (void *)&sr};
 #if defined(GHICP_EMU_HOST)
   (void)args;
-  emu::launch_cooperative(dim3(n_sm * blocks_per_sm), dim3(PA_THREADS), [&] { k_auction_persistent<false>(a, l0, l1, mr, sn); });
+  emu::launch_cooperative(dim3(n_sm * blocks_per_sm), dim3(PA_THREADS), [&] { k_auction_persistent<false>(a, l0, l1, mr, sn, sr); });
   cudaError_t e = cudaSuccess;
 #else
   cudaError_t e = cudaLaunchCooperativeKernel((void *)k_auction_persistent<false>, dim3(n_sm * blocks_per_sm), dim3(PA_THREADS),
@@ -723,7 +734,7 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
 
   // Split of the optimality budget n*eps_final: eps_last = epsf*eps_final for the forward phases (n*eps_last), the rest
   // for D = the prices of objects left free (the reverse phase runs while D exceeds it and stops as soon as it fits).
-  double epsf = 0.5;
+  double epsf = 0.1;
   if (const char *ov = getenv("GHICP_AUCTION_EPSF")) { const double v = atof(ov); if (v > 0.0 && v < 1.0) epsf = v; }
   const double d_budget = (1.0 - epsf) * eps_final * (double)nmax;
   a.d_budget_fx = getenv("GHICP_AUCTION_NOCUT") ? 0ull : (unsigned long long)(d_budget * D_FX);
@@ -783,10 +794,11 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
       int *l0 = c->d_list[0], *l1 = c->d_list[1];
       int mr = max_rounds;
       int sn = small_fwd;
-      void *args[] = {(void *)&a, (void *)&l0, (void *)&l1, (void *)&mr, (void *)&sn};
+      int sr = avg_row <= 4.0 ? 1 : 0;   // short adjacency lists: one thread per bidder
+      void *args[] = {(void *)&a, (void *)&l0, (void *)&l1, (void *)&mr, (void *)&sn, (void *)&sr};
 #if defined(GHICP_EMU_HOST)
       (void)args;   // host emulation: all blocks of the (small) grid run as fibers, the grid barrier is a rendezvous
-      emu::launch_cooperative(dim3(n_sm * coop_blocks_per_sm[0]), dim3(PA_THREADS), [&] { k_auction_persistent<false>(a, l0, l1, mr, sn); });
+      emu::launch_cooperative(dim3(n_sm * coop_blocks_per_sm[0]), dim3(PA_THREADS), [&] { k_auction_persistent<false>(a, l0, l1, mr, sn, sr); });
       cudaError_t e = cudaSuccess;
 #else
       cudaError_t e = cudaLaunchCooperativeKernel((void *)k_auction_persistent<false>, dim3(n_sm * coop_blocks_per_sm[0]),
@@ -814,6 +826,9 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
     }
     if (need_reverse) {
     ran_reverse = true;
+    // the column-wise copy of the graph is only read by the reverse rounds: built here, on demand (a settled loop, one
+    // forward phase from zero prices, never gets here)
+    { cudaError_t e = launch_build_csc(c, n_rows, n_cols, nnz); if (e != cudaSuccess) { set_error(c, std::string("auction: CSC build: ") + cudaGetErrorString(e)); return GHICP_E_CUDA; } }
     cudaMemsetAsync(&c->d_counters[0], 0, sizeof(int) * 2, st);
     cudaMemsetAsync(&c->d_counters[32], 0, sizeof(int) * 5, st);   // D of both lists, the budget-stop flag
     GHICP_LAUNCH(k_rev_collect, gmax, 256, 0, st, n_cols, c->d_owner, c->d_price, c->d_list[0], c->d_counters, 0);
@@ -823,10 +838,11 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
       int *l0 = c->d_list[0], *l1 = c->d_list[1];
       int mr = max_rounds;
       int sn = small_rev;
-      void *args[] = {(void *)&a, (void *)&l0, (void *)&l1, (void *)&mr, (void *)&sn};
+      int sr = avg_col <= 4.0 ? 1 : 0;
+      void *args[] = {(void *)&a, (void *)&l0, (void *)&l1, (void *)&mr, (void *)&sn, (void *)&sr};
 #if defined(GHICP_EMU_HOST)
       (void)args;
-      emu::launch_cooperative(dim3(n_sm * coop_blocks_per_sm[1]), dim3(PA_THREADS), [&] { k_auction_persistent<true>(a, l0, l1, mr, sn); });
+      emu::launch_cooperative(dim3(n_sm * coop_blocks_per_sm[1]), dim3(PA_THREADS), [&] { k_auction_persistent<true>(a, l0, l1, mr, sn, sr); });
       cudaError_t e = cudaSuccess;
 #else
       cudaError_t e = cudaLaunchCooperativeKernel((void *)k_auction_persistent<true>, dim3(n_sm * coop_blocks_per_sm[1]),

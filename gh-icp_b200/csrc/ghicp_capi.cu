@@ -427,6 +427,9 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
     //      The host reads nothing until the iteration's final synchronize; a block overflow (flag travels with the
     //      statistics, k_apply then leaves the keypoints alone) sends the iteration through the general route below.
     c->emit_on = true;
+    // message size of this iteration: twice the largest per-rank share of the last one (the latency-bound all-gather carries
+    // what the graph needs, not what the buffers could hold); an overflow redoes the iteration on the general route
+    c->xuse = std::min(c->xcap, ((size_t)std::max<long long>(1024, 2 * c->last_max_local_nnz + 256) + 3) & ~(size_t)3);
     CK(c, launch_stream_prep(c, cp, 0));
     CK(c, cudaMemsetAsync(c->d_cnt, 0, sizeof(int) * ((size_t)c->Npad + 2), st));
     CK(c, launch_penalty_only(c, ls));        // src/ghicp_reg.cpp:279-282: independent of this iteration's CD
@@ -436,12 +439,11 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
     CK(c, cudaEventRecord(c->ev[5], st));
     CK(c, launch_finalize_fast(c, ls));
     CK(c, launch_emit_check(c, cp));
-    if ((rc = comm_allgather_bytes(c, c->d_xsend, c->d_xrecv, xblock_bytes(c->xcap)))) return rc;   // the iteration's one exchange
+    if ((rc = comm_allgather_bytes(c, c->d_xsend, c->d_xrecv, xblock_bytes(c->xuse)))) return rc;   // the iteration's one exchange
     CK(c, launch_xbuild(c));
     CK(c, launch_penalty(c, 0.0, ls));        // CD mean / std of all ranks' sums (+ the overflow flag)
     CK(c, cudaEventRecord(c->ev[1], st));
     stream_passes += 1; timed_stream = true; ev1_done = true;
-    CK(c, launch_build_csc_dev(c, c->N, c->M, &c->d_iter->nnz, (long long)(c->xcap * (size_t)c->world)));
     if ((rc = km_auction_settled(c, c->N, c->M, c->last_total_nnz, c->KM_eps))) return rc;
     CK(c, launch_select_km(c));
     CK(c, launch_pair_fd_km(c));
@@ -519,7 +521,6 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
         CK(c, launch_count_valid(c, nnz_super));
       }
     }
-    CK(c, launch_build_csc(c, c->N, c->M, nnz_super));
     if ((rc = km_auction(c, c->N, c->M, nnz_super, c->KM_eps, std::max(penalty, c->KM_eps), &kres))) return rc;
     CK(c, launch_select_km(c));
     CK(c, launch_pair_fd_km(c));
@@ -551,7 +552,6 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
       const double penalty = c->h_iter->penalty;
       if ((rc = ensure_edges(c, nnz))) return rc;
       if (nnz > 0) CK(c, mf ? launch_rowsweep_mf(c, 2, cp) : launch_rowsweep(c, 2, cp));
-      CK(c, launch_build_csc(c, c->N, c->M, nnz));
       if ((rc = km_auction(c, c->N, c->M, nnz, c->KM_eps, std::max(penalty, c->KM_eps), &kres))) return rc;
       CK(c, launch_select_km(c));
       CK(c, launch_pair_fd_km(c));
@@ -1008,9 +1008,7 @@ int ghicp_km_solve(int device, const double *W, int n, int sp, int tp, double ep
     cudaMemcpy(c->d_csr_col, col.data(), sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice);
     cudaMemcpy(c->d_csr_gain, gain.data(), sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice);
   }
-  cudaError_t e = launch_build_csc(c, sp, tp, nnz);
-  if (e != cudaSuccess) { set_error(nullptr, cudaGetErrorString(e)); ghicp_destroy(ctx); return GHICP_E_CUDA; }
-  KmResult kres;
+  KmResult kres;   // (the column-wise copy the reverse rounds read is built inside km_auction, when they run)
   rc = km_auction(c, sp, tp, nnz, eps, max_gain, &kres);
   if (rc) { set_error(nullptr, c->err); ghicp_destroy(ctx); return rc; }
   std::vector<int> owner(tp);

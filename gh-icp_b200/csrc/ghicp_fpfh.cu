@@ -698,7 +698,9 @@ cudaError_t launch_fpfh_fast_prep(Ctx *c) {
 cudaError_t launch_fpfh_fast_seed(Ctx *c, const CostParams &cp, bool with_cols, bool use_guess) {
   const FfArgs a = ff_args(c, cp);
   const int n = c->N > c->M ? c->N : c->M;
-  GHICP_LAUNCH(k_ff_seed, (n + 255) / 256, 256, 0, c->stream, a, c->d_row_idx, c->d_col_idx, c->have_prev ? 1 : 0,
+  // sharded: seed a column from this rank's own best row of the last iteration (see launch_stream_seed)
+  const int *prev_cols = (c->world > 1 && c->d_colg_idx) ? c->d_colg_idx + (size_t)c->rank * (size_t)c->M : c->d_col_idx;
+  GHICP_LAUNCH(k_ff_seed, (n + 255) / 256, 256, 0, c->stream, a, c->d_row_idx, prev_cols, c->have_prev ? 1 : 0,
                use_guess ? 1 : 0, with_cols ? 1 : 0, c->d_ff_srec);
   c->launches++;
   return cudaGetLastError();

@@ -230,7 +230,8 @@ struct Ctx {
   long long *h_rowptr_cut = nullptr;        // pinned [world + 1] CSR offsets at the shard boundaries
   int exchanges = 0;
   // settled KM iteration: one candidate block per rank, one all-gather, no host round trip inside the iteration
-  size_t xcap = 0;                          // candidate edges a block can carry
+  size_t xcap = 0;                          // candidate edges a block can carry (allocation)
+  size_t xuse = 0;                          // ... and carries this iteration: 2 x last iteration's largest share (same on every rank)
   unsigned char *d_xsend = nullptr;         // this rank's block
   unsigned char *d_xrecv = nullptr;         // [world] blocks (world > 1)
   long long last_total_nnz = -1;            // candidate edges of the whole graph last iteration (-1: no history)
@@ -328,7 +329,6 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
 cudaError_t launch_build_csc(Ctx *c, int n_rows, int n_cols, long long nnz);
 // settled loop (sparse graph): the same single forward phase, edge count read on the device, nothing read back;
 // counters land in h_counters with the iteration's final copy (km_auction_settled_result after the synchronize)
-cudaError_t launch_build_csc_dev(Ctx *c, int n_rows, int n_cols, const long long *d_nnz, long long nnz_bound);
 int km_auction_settled(Ctx *c, int n_rows, int n_cols, long long nnz_hint, double eps_final);
 int km_auction_settled_result(Ctx *c, KmResult *res);
 

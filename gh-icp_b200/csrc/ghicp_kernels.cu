@@ -772,6 +772,18 @@ __global__ void k_pair_fd_km(const int *__restrict__ sp, const int *__restrict__
   }
 }
 
+// the same with ONE THREAD per pair: a settled loop has about one candidate per row, a warp per pair wastes 31 lanes
+__global__ void k_pair_fd_km_thread(const int *__restrict__ sp, const int *__restrict__ tp, const DevIter *iter,
+                                    const long long *__restrict__ rowptr, const int *__restrict__ csr_col,
+                                    const float *__restrict__ csr_fd, float *__restrict__ pair_fd) {
+  const int cor = iter->cor;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < cor; p += gridDim.x * blockDim.x) {
+    const int i = sp[p], j = tp[p];
+    for (long long k = rowptr[i], e = rowptr[i + 1]; k < e; ++k)
+      if (csr_col[k] == j) { pair_fd[p] = csr_fd[k]; break; }
+  }
+}
+
 template <typename F>
 cudaError_t dispatch_ft(int ft, F &&f) {
   switch (ft) {
@@ -881,6 +893,13 @@ cudaError_t launch_penalty(Ctx *c, double pivot, const LoopScalars &ls) {
   return cudaGetLastError();
 }
 cudaError_t launch_pair_fd_km(Ctx *c) {
+  const long long nmax = std::max(c->N, c->M);
+  if (c->last_total_nnz >= 0 && c->last_total_nnz <= 4 * nmax) {   // short rows (hint: last iteration's edge count)
+    GHICP_LAUNCH(k_pair_fd_km_thread, (unsigned)((nmax + 255) / 256), 256, 0, c->stream, c->d_sp, c->d_tp, c->d_iter, c->d_rowptr,
+                 c->d_csr_col, c->d_csr_fd, c->d_pair_fd);
+    c->launches++;
+    return cudaGetLastError();
+  }
   GHICP_LAUNCH(k_pair_fd_km, 148 * 2, 256, 0, c->stream, c->d_sp, c->d_tp, c->d_iter, c->d_rowptr, c->d_csr_col, c->d_csr_fd,
                                                c->d_pair_fd);
   c->launches++;

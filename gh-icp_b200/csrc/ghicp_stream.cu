@@ -894,7 +894,10 @@ cudaError_t launch_stream_seed(Ctx *c, const CostParams &cp, bool with_cols) {
   StreamArgs a = make_args(c, cp);
   if (with_cols) a.col_thr_init = c->d_col_thr;
   const int n = c->N > c->M ? c->N : c->M;
-  GHICP_LAUNCH(k_seed, (n + 255) / 256, 256, 0, c->stream, a, c->d_row_idx, c->d_col_idx, c->have_prev ? 1 : 0);
+  // sharded NNR: a column is seeded from this rank's OWN best row of the last iteration (its slice of the gathered per-rank
+  // column minima), not from the merged winner, which mostly lives on another rank and would leave the column unseeded
+  const int *prev_cols = (c->world > 1 && c->d_colg_idx) ? c->d_colg_idx + (size_t)c->rank * (size_t)c->M : c->d_col_idx;
+  GHICP_LAUNCH(k_seed, (n + 255) / 256, 256, 0, c->stream, a, c->d_row_idx, prev_cols, c->have_prev ? 1 : 0);
   c->launches++;
   return cudaGetLastError();
 }
@@ -1030,25 +1033,25 @@ cudaError_t launch_emit_check(Ctx *c, const CostParams &cp) {
   unsigned char *blk = c->d_xsend;
   XBlockHdr *hdr = reinterpret_cast<XBlockHdr *>(blk);
   unsigned long long *key = reinterpret_cast<unsigned long long *>(hdr + 1);
-  double *gain = reinterpret_cast<double *>(key + c->xcap);
-  float *fd = reinterpret_cast<float *>(gain + c->xcap);
+  double *gain = reinterpret_cast<double *>(key + c->xuse);
+  float *fd = reinterpret_cast<float *>(gain + c->xuse);
   GHICP_LAUNCH(k_emit_check, 148 * 2, 256, 0, c->stream, a, c->d_iter, c->d_xstats + 4 * c->rank, hdr, key, gain, fd,
-               (unsigned long long)c->xcap);
+               (unsigned long long)c->xuse);
   c->launches++;
   return cudaGetLastError();
 }
 // gathered blocks -> d_xstats, CSR (d_rowptr / d_csr_*), DevIter::nnz, StreamDev::nnz_valid; no host involvement
 cudaError_t launch_xbuild(Ctx *c) {
   const unsigned char *blocks = c->world > 1 ? c->d_xrecv : c->d_xsend;
-  const size_t bb = xblock_bytes(c->xcap);
+  const size_t bb = xblock_bytes(c->xuse);
   cudaMemsetAsync(c->d_cnt, 0, sizeof(int) * ((size_t)c->Npad + 2), c->stream);
   cudaMemsetAsync(&c->d_sdev->nnz_valid, 0, sizeof(unsigned long long), c->stream);
   const dim3 grid(32, c->world);
-  GHICP_LAUNCH(k_xcount, grid, 256, 0, c->stream, blocks, bb, (unsigned long long)c->xcap, c->d_cnt, c->d_xstats, c->d_xcounts);
+  GHICP_LAUNCH(k_xcount, grid, 256, 0, c->stream, blocks, bb, (unsigned long long)c->xuse, c->d_cnt, c->d_xstats, c->d_xcounts);
   c->launches++;
   cudaError_t e = launch_scan_rows(c);
   if (e != cudaSuccess) return e;
-  GHICP_LAUNCH(k_xscatter, grid, 256, 0, c->stream, blocks, bb, (unsigned long long)c->xcap, c->d_rowptr, c->d_cursor, c->d_csr_col,
+  GHICP_LAUNCH(k_xscatter, grid, 256, 0, c->stream, blocks, bb, (unsigned long long)c->xuse, c->d_rowptr, c->d_cursor, c->d_csr_col,
                c->d_csr_gain, c->d_csr_fd, c->d_sdev);
   c->launches++;
   return cudaGetLastError();

@@ -72,6 +72,9 @@ inline void read_pcd(const std::string &name, Cloud &c) {
   if (fields.empty() || sizes.size() != fields.size()) throw std::runtime_error(name + ": malformed PCD header");
   if (counts.empty()) counts.assign(fields.size(), 1);
   if (types.empty()) types.assign(fields.size(), 'F');
+  if (counts.size() != fields.size() || types.size() != fields.size()) throw std::runtime_error(name + ": malformed PCD header (TYPE / COUNT shorter than FIELDS)");
+  for (size_t f = 0; f < fields.size(); ++f)
+    if (sizes[f] <= 0 || counts[f] <= 0) throw std::runtime_error(name + ": malformed PCD header (non-positive SIZE / COUNT)");
   if (points == 0) points = width * height;
   FieldLayout L;
   for (size_t f = 0; f < fields.size(); ++f) {

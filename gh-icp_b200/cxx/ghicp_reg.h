@@ -77,9 +77,15 @@ class GHRegistration {
     cfg.estimated_iou = estimated_IoU; cfg.converge_t = converge_tran; cfg.converge_r = converge_rot;
     cfg.max_iter = 0; cfg.device = 0; cfg.km_eps = Ef.KM_eps;
     check(ghicp_create(&cfg, &ctx_), "ghicp_create");
-    check(ghicp_set_keypoints(ctx_, KP.kpSXYZ.data(), KP.kps_num, KP.kpTXYZ.data(), KP.kpt_num), "ghicp_set_keypoints");
-    if (Ft == BSC) upload_bsc();
-    if (Ft == FPFH) upload_fpfh();
+    try {   // a constructor that throws runs no destructor: release the context here
+      check(ghicp_set_keypoints(ctx_, KP.kpSXYZ.data(), KP.kps_num, KP.kpTXYZ.data(), KP.kpt_num), "ghicp_set_keypoints");
+      if (Ft == BSC) upload_bsc();
+      if (Ft == FPFH) upload_fpfh();
+    } catch (...) {
+      ghicp_destroy(ctx_);
+      ctx_ = nullptr;
+      throw;
+    }
   }
   ~GHRegistration() { if (ctx_) ghicp_destroy(ctx_); }
   GHRegistration(const GHRegistration &) = delete;

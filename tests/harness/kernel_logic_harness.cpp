@@ -327,7 +327,6 @@ int emu_km_auction(int N, int M, const long long *rowptr, const int *col, const 
   c.d_bid_val = bid_val.data(); c.d_bid_aux = bid_aux.data();
   c.d_list[0] = l0.data(); c.d_list[1] = l1.data(); c.d_counters = counters.data(); c.h_counters = hcount.data();
   c.d_flags = flags.data(); c.d_tile_sum = tile_sum.data(); c.tile_cap = tile_sum.size();
-  if (launch_build_csc(&c, N, M, nnz) != cudaSuccess) return -1;
   KmResult kres;
   const int rc = km_auction(&c, N, M, nnz, eps, max_gain, &kres);
   c.h_counters = nullptr;   // not ours to free
