@@ -151,7 +151,7 @@ static int alloc_workspaces(Ctx *c) {
   if ((rc = dev_alloc(c, &c->d_colbest, (size_t)M))) return rc;
   if ((rc = dev_alloc(c, &c->d_rowidx2, (size_t)c->Npad))) return rc;
   if ((rc = dev_alloc(c, &c->d_colidx2, (size_t)M))) return rc;
-  if (c->cfg.corr_type != GHICP_CT_KM) {
+  if (c->cfg.corr_type != GHICP_CT_KM || c->cfg.feature_type == GHICP_FT_FPFH) {   // (FPFH + KM: the filter's KM gate lists its hits there)
     c->cand_cap = (int)std::min<size_t>((size_t)96 * nmax + (1u << 20), (size_t)1 << 28);
     if ((rc = dev_alloc(c, &c->d_cand[0], (size_t)c->cand_cap))) return rc;
     if (c->cfg.corr_type == GHICP_CT_NNR) { if ((rc = dev_alloc(c, &c->d_cand[1], (size_t)c->cand_cap))) return rc; }
@@ -266,7 +266,8 @@ static int build_fd(Ctx *c) {
     if (!mf && c->cfg.fpfh_matrix_free == 0) {
       size_t free_b = 0, total_b = 0;
       CK(c, cudaMemGetInfo(&free_b, &total_b));
-      mf = c->cfg.corr_type != GHICP_CT_KM || (double)plane_bytes > 0.4 * (double)free_b;
+      (void)free_b; (void)total_b;
+      mf = true;   // auto = matrix-free for every correspondence mode (KM: exact sweeps in iterations 0-1, the filter's gate after)
     }
     c->fpfh_mf = mf;
     int rc;
@@ -279,7 +280,7 @@ static int build_fd(Ctx *c) {
       CK(c, launch_fpfh_prepare(c));
       // operands of the FP32 filter (fast NN / NNR path); KM keeps the exact sweeps
       c->fpfh_fast_ready = false;
-      if (c->cfg.corr_type != GHICP_CT_KM) {
+      {
         if ((rc = dev_alloc(c, &c->d_ff_srec, (size_t)c->N * fpfh_fast_rec_floats()))) return rc;
         if ((rc = dev_alloc(c, &c->d_ff_tnT, (size_t)c->M * 36))) return rc;
         if ((rc = dev_alloc(c, &c->d_ff_tco, (size_t)c->M * 6))) return rc;
@@ -343,21 +344,22 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
   // NN's penalty is RMS*para1*scale*para2 from iteration 2 on (src/ghicp_reg.cpp:327-330).
   const bool fpfh_fast = c->use_fast && ft == GHICP_FT_FPFH && c->fpfh_mf && c->fpfh_fast_ready && ct != GHICP_CT_KM &&
                          (ct == GHICP_CT_NNR || c->iteration >= 2) && getenv("GHICP_FPFH_EXACT") == nullptr;
-  bool exact_fallback = !fast && !fpfh_fast;
+  // Settled KM iteration?  Decided from quantities every rank holds identically (both routes contain collectives).
+  const long long nmax_km = std::max(c->N, c->M);
+  const bool km_sparse_history = ct == GHICP_CT_KM && c->iteration >= 2 && !c->km_settled_off && c->xcap > 0 &&
+                                 c->last_total_nnz >= 0 && (double)c->last_total_nnz <= 1.5 * (double)nmax_km &&
+                                 c->last_max_local_nnz >= 0 &&
+                                 (size_t)c->last_max_local_nnz + (size_t)c->last_max_local_nnz / 2 + 64 <= c->xcap &&
+                                 getenv("GHICP_KM_GENERAL") == nullptr && getenv("GHICP_KM_FILL") == nullptr;   // test hooks: general route
+  const bool km_settled = fast && ft != GHICP_FT_NONE && km_sparse_history;
+  // FPFH + KM, settled loop: the FP32 filter as the KM gate (penalty = RMS*para1*scale*para2 from iteration 2 on)
+  const bool fpfh_km_fast = c->use_fast && ft == GHICP_FT_FPFH && c->fpfh_mf && c->fpfh_fast_ready && c->d_cand[0] &&
+                            km_sparse_history && getenv("GHICP_FPFH_EXACT") == nullptr;
+  const bool settled_any = km_settled || fpfh_km_fast;
+  bool exact_fallback = !fast && !fpfh_fast && !fpfh_km_fast;
   bool ev1_done = false, timed_stream = false;
   int stream_passes = 0;
   const bool sharded = c->world > 1;
-  // Settled KM iteration?  Decided from quantities every rank holds identically (both routes contain collectives).
-  const long long nmax_km = std::max(c->N, c->M);
-  const bool km_settled = fast && ct == GHICP_CT_KM && ft != GHICP_FT_NONE && c->iteration >= 2 && !c->km_settled_off &&
-                          c->xcap > 0 && c->last_total_nnz >= 0 && (double)c->last_total_nnz <= 1.5 * (double)nmax_km &&
-                          c->last_max_local_nnz >= 0 &&
-                          (size_t)c->last_max_local_nnz + (size_t)c->last_max_local_nnz / 2 + 64 <= c->xcap &&
-                          getenv("GHICP_KM_GENERAL") == nullptr && getenv("GHICP_KM_FILL") == nullptr;   // test hooks: general route
-  if (sharded && ct == GHICP_CT_KM && !fast) {
-    set_error(c, "multi-GPU KM needs the streaming path (BSC / no feature, force_exact = 0)");
-    return GHICP_E_ARG;
-  }
   if (fpfh_fast) {
     const bool cols = (ct == GHICP_CT_NNR);
     // guesses for the thresholds: last iteration's partners once the loop has settled, else an FP32 argmin pre-pass
@@ -420,6 +422,27 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
     if (c->h_iter->overflow_any || (!cols && c->h_iter->ambiguous > 0)) exact_fallback = true;
     else c->have_prev = true;
     c->fallbacks += exact_fallback ? 1 : 0;
+  } else if (fpfh_km_fast) {
+    // ---- FPFH + KM, settled loop: one filter sweep with every row's threshold at the penalty; the exactly evaluated hits with
+    //      CD < penalty are the KM graph and travel as this rank's candidate block (the settled route below, same tail)
+    c->xuse = std::min(c->xcap, ((size_t)std::max<long long>(1024, 2 * c->last_max_local_nnz + 256) + 3) & ~(size_t)3);
+    CK(c, launch_fpfh_fast_prep(c));
+    CK(c, launch_fpfh_gate_seed(c, cp, ls));
+    CK(c, cudaEventRecord(c->ev[4], st));
+    CK(c, launch_fpfh_fast_sweep(c, cp, false, false));
+    CK(c, cudaEventRecord(c->ev[5], st));
+    CK(c, launch_fpfh_cand_block(c, cp));
+    if ((rc = comm_allgather_bytes(c, c->d_xsend, c->d_xrecv, xblock_bytes(c->xuse)))) return rc;
+    CK(c, launch_xbuild(c));
+    CK(c, launch_penalty(c, 0.0, ls));        // CD mean (the filter's estimate) + the overflow flag; same penalty
+    CK(c, cudaEventRecord(c->ev[1], st));
+    stream_passes += 1; timed_stream = true; ev1_done = true;
+    if ((rc = km_auction_settled(c, c->N, c->M, c->last_total_nnz, c->KM_eps))) return rc;
+    CK(c, launch_select_km(c));
+    CK(c, launch_pair_fd_km(c));
+    CK(c, cudaMemcpyAsync(c->h_sdev, c->d_sdev, sizeof(StreamDev), cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(c->h_xcounts, c->d_xcounts, sizeof(unsigned long long) * (size_t)c->world, cudaMemcpyDeviceToHost, st));
+    nnz = -1;
   } else if (fast && km_settled) {
     // ---- streaming path, KM, settled loop (sparse candidate graph, penalty independent of this iteration's CD):
     //      one pass over the FD plane, the gate hits checked exactly where they were found, ONE all-gather of the
@@ -529,7 +552,6 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
   }
   if (exact_fallback) {
     // ---- all-double path (FPFH; forced; or fallback): calED + calCD_* (+ the row scan of NN / NNR)
-    if (sharded && ct == GHICP_CT_KM) { set_error(c, "multi-GPU KM: all-double fallback not supported"); return GHICP_E_ARG; }
     const bool mf = (ft == GHICP_FT_FPFH) && c->fpfh_mf;   // matrix-free FPFH: FD recomputed inside the sweeps
     CK(c, mf ? launch_rowsweep_mf(c, 0, cp) : launch_rowsweep(c, 0, cp));
     CK(c, launch_finalize_stats(c, cp, ls));
@@ -544,14 +566,31 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
     } else if (ct == GHICP_CT_NNR) {
       CK(c, launch_select_nnr(c));
     } else {
+      // sharded: every rank counts, fills and checks the candidates of ITS rows with the all-double kernels; counts and
+      // edges travel like on the streaming path's general route (all-gather of the counts, one broadcast group of the edges)
+      if (sharded) CK(c, cudaMemsetAsync(c->d_cnt, 0, sizeof(int) * ((size_t)c->Npad + 2), st));
       CK(c, mf ? launch_rowsweep_mf(c, 1, cp) : launch_rowsweep(c, 1, cp));
+      if (sharded && (rc = comm_gather_counts(c))) return rc;
       CK(c, launch_scan_counts(c));
       CK(c, cudaMemcpyAsync(c->h_iter, c->d_iter, sizeof(DevIter), cudaMemcpyDeviceToHost, st));
+      if (sharded)
+        for (int r = 0; r <= c->world; ++r)
+          CK(c, cudaMemcpyAsync(&c->h_rowptr_cut[r], c->d_rowptr + std::min(c->N, r * c->shard), sizeof(long long),
+                                cudaMemcpyDeviceToHost, st));
       CK(c, cudaStreamSynchronize(st));
       nnz = c->h_iter->nnz;
       const double penalty = c->h_iter->penalty;
       if ((rc = ensure_edges(c, nnz))) return rc;
       if (nnz > 0) CK(c, mf ? launch_rowsweep_mf(c, 2, cp) : launch_rowsweep(c, 2, cp));
+      if (sharded && nnz > 0 && (rc = comm_gather_edges(c, c->h_rowptr_cut))) return rc;
+      c->last_total_nnz = nnz;
+      c->last_max_local_nnz = nnz;
+      if (sharded) {
+        c->last_max_local_nnz = 0;
+        for (int r = 0; r < c->world; ++r)
+          c->last_max_local_nnz = std::max(c->last_max_local_nnz, c->h_rowptr_cut[r + 1] - c->h_rowptr_cut[r]);
+      }
+      c->km_settled_off = false;
       if ((rc = km_auction(c, c->N, c->M, nnz, c->KM_eps, std::max(penalty, c->KM_eps), &kres))) return rc;
       CK(c, launch_select_km(c));
       CK(c, launch_pair_fd_km(c));
@@ -563,11 +602,11 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
   CK(c, launch_solve(c, cp));
   // opt-in estimators replace the transform (and the RMSE after it); the pair statistics stay k_solve's
   if (c->cfg.solver != GHICP_SOLVER_SVD) CK(c, launch_solve_alt(c, c->cfg.solver));
-  CK(c, launch_apply(c, km_settled));
+  CK(c, launch_apply(c, settled_any));
   CK(c, cudaEventRecord(c->ev[3], st));
   CK(c, cudaMemcpyAsync(c->h_iter, c->d_iter, sizeof(DevIter), cudaMemcpyDeviceToHost, st));
   CK(c, cudaStreamSynchronize(st));
-  if (km_settled) {
+  if (settled_any) {
     if (c->h_iter->overflow_any) {   // some rank's candidate block overflowed: nothing was updated, take the general route
       c->km_settled_off = true;
       return iterate_impl(c, out);

@@ -601,6 +601,48 @@ __global__ void k_ff_publish(const FfArgs a, double *row_cd, int *row_idx, doubl
     col_idx[k] = found ? i : 0;
   }
 }
+// ---- KM gate on the same filter (FPFH + KM from iteration 2 on: penalty = RMS*para1*scale*para2, src/ghicp_reg.cpp:327-330,
+//      independent of this iteration's CD) -----------------------------------------------------------------------------
+// Every row gets the SAME threshold, the penalty: the sweep then evaluates exactly every pair whose lower bound does not
+// exceed it and leaves (i, j, CD_exact) in the candidate list; the pairs with CD < penalty (strict, :362) are the KM graph.
+// They travel as the candidate block of the settled KM route (ghicp_stream.cu: one all-gather, CSR built on every rank).
+__global__ void k_ff_gate_seed(FfArgs a, LoopScalars ls, DevIter *iter, float *__restrict__ srec) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const double penalty = ls.RMS * ls.para1 * ls.scale * ls.para2;   // the expression of k_penalty: the same double
+  if (k == 0) iter->penalty = penalty;
+  if (k >= a.row0 && k < a.row0 + a.nloc) {
+    const float thr = __double2float_ru(penalty * 1.0000001);
+    a.thr_row[k] = thr;
+    srec[(size_t)k * FF_REC + 39] = thr;
+    a.rowbest[k] = ~0ull;
+    a.rowidx[k] = INT_MAX;
+    a.rowguess[k] = ~0ull;
+  }
+}
+__global__ void k_ff_cand_block(const FfArgs a, const DevIter *iter, XBlockHdr *hdr, unsigned long long *__restrict__ key,
+                                double *__restrict__ gain, float *__restrict__ fd, unsigned long long xuse) {
+  const int n = min(a.dev->cand_count[0], a.cand_cap);
+  const double penalty = iter->penalty;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const Cand c = a.cand[0][k];
+    if (c.cd < penalty) {
+      const unsigned long long pos = atomicAdd(&hdr->count, 1ull);
+      if (pos < xuse) {
+        key[pos] = ((unsigned long long)(unsigned)c.i << 32) | (unsigned)c.j;
+        gain[pos] = penalty - c.cd;
+        fd[pos] = fpfh_fd_pair(a.sc + (size_t)c.i * HP, a.tc + (size_t)c.j * HP);
+      }
+    }
+  }
+}
+__global__ void k_ff_block_hdr(const FfArgs a, const double *__restrict__ xstats_rank, XBlockHdr *hdr, unsigned long long xuse) {
+  const bool ovf = hdr->count > xuse || a.dev->overflow != 0;
+  hdr->stats[0] = xstats_rank[0]; hdr->stats[1] = xstats_rank[1];
+  hdr->stats[2] = ovf ? 1.0 : 0.0;   // picked up by k_penalty as DevIter::overflow_any on every rank
+  hdr->stats[3] = 0.0;
+  if (ovf) hdr->count = 0ull;
+}
+
 __global__ void k_ff_reset(StreamDev *dev) {
   dev->cand_count[0] = 0; dev->cand_count[1] = 0; dev->overflow = 0;
 }
@@ -724,6 +766,29 @@ cudaError_t launch_fpfh_fast_finish(Ctx *c, const CostParams &cp, bool with_cols
   GHICP_LAUNCH(k_ff_publish, (n + 255) / 256, 256, 0, c->stream, a, c->d_row_cd, c->d_row_idx,
                with_cols ? c->d_col_cd : (double *)nullptr, with_cols ? c->d_col_idx : (int *)nullptr, c->d_xstats, c->rank);
   c->launches += with_cols ? 4 : 3;
+  return cudaGetLastError();
+}
+
+
+// FPFH + KM, settled loop: thresholds = penalty, one filter sweep, candidate block (see k_ff_gate_seed)
+cudaError_t launch_fpfh_gate_seed(Ctx *c, const CostParams &cp, const LoopScalars &ls) {
+  const FfArgs a = ff_args(c, cp);
+  const int n = c->N > c->M ? c->N : c->M;
+  GHICP_LAUNCH(k_ff_gate_seed, (n + 255) / 256, 256, 0, c->stream, a, ls, c->d_iter, c->d_ff_srec);
+  c->launches++;
+  return cudaGetLastError();
+}
+cudaError_t launch_fpfh_cand_block(Ctx *c, const CostParams &cp) {
+  const FfArgs a = ff_args(c, cp);
+  XBlockHdr *hdr = reinterpret_cast<XBlockHdr *>(c->d_xsend);
+  unsigned long long *key = reinterpret_cast<unsigned long long *>(hdr + 1);
+  double *gain = reinterpret_cast<double *>(key + c->xuse);
+  float *fd = reinterpret_cast<float *>(gain + c->xuse);
+  cudaMemsetAsync(hdr, 0, sizeof(XBlockHdr), c->stream);
+  GHICP_LAUNCH(k_ff_stats, 1, 1024, 0, c->stream, c->d_ff_part, (int)fpfh_fast_parts(c), c->d_xstats, c->rank);
+  GHICP_LAUNCH(k_ff_cand_block, 148 * 2, 256, 0, c->stream, a, c->d_iter, hdr, key, gain, fd, (unsigned long long)c->xuse);
+  GHICP_LAUNCH(k_ff_block_hdr, 1, 1, 0, c->stream, a, c->d_xstats + 4 * c->rank, hdr, (unsigned long long)c->xuse);
+  c->launches += 3;
   return cudaGetLastError();
 }
 

@@ -284,6 +284,9 @@ cudaError_t launch_fpfh_fast_prep(Ctx *c);                                    //
 cudaError_t launch_fpfh_fast_seed(Ctx *c, const CostParams &cp, bool with_cols, bool use_guess);
 cudaError_t launch_fpfh_fast_sweep(Ctx *c, const CostParams &cp, bool pre, bool with_cols);
 cudaError_t launch_fpfh_fast_finish(Ctx *c, const CostParams &cp, bool with_cols);
+// FPFH + KM (settled loop): the filter as the KM gate, candidates into this rank's block of the settled route
+cudaError_t launch_fpfh_gate_seed(Ctx *c, const CostParams &cp, const LoopScalars &ls);
+cudaError_t launch_fpfh_cand_block(Ctx *c, const CostParams &cp);
 
 // ---- opt-in solvers (ghicp_solvers.cu) -------------------------------------------------------------
 // Overwrites iter->Rt and iter->rmse_after from the pair list in the ctx (after launch_solve produced the statistics)

@@ -25,10 +25,11 @@ dist.broadcast_object_list(uid, src=0)
 mode = sys.argv[1]
 ft = {"none": g.FT_NONE, "bsc": g.FT_BSC, "fpfh": g.FT_FPFH}[mode.split("-")[0]]
 ct = {"nn": g.CT_NN, "nnr": g.CT_NNR, "km": g.CT_KM}[mode.split("-")[1]]
+exact = mode.endswith("-exact")
 sc = g.synth.gen_points(3001, 2750, overlap=0.6, extent=(80, 80, 16), noise=0.04, seed=31)
 if ft == g.FT_BSC: g.synth.add_bsc(sc, bits=441, V=4)
 if ft == g.FT_FPFH: g.synth.add_fpfh(sc)
-reg = g.registration.from_scene(sc, ft, ct, device=rank, comm=(uid[0], rank, world))
+reg = g.registration.from_scene(sc, ft, ct, device=rank, comm=(uid[0], rank, world), force_exact=exact)
 out = []
 for it in range(6):
     st = reg.iterate()
@@ -40,7 +41,9 @@ dist.barrier()
 '''
 
 
-@pytest.mark.parametrize("mode", ["none-nn", "bsc-nn", "bsc-nnr", "bsc-km", "fpfh-nnr", "fpfh-nn"])
+# "-exact" = force_exact: the all-double kernels, sharded (KM: counts / edges gathered like on the streaming path's general route);
+# fpfh-km always takes that route (stored float plane or matrix-free sweeps, no FP32 filter)
+@pytest.mark.parametrize("mode", ["none-nn", "bsc-nn", "bsc-nnr", "bsc-km", "fpfh-nnr", "fpfh-nn", "bsc-km-exact", "fpfh-km"])
 def test_sharded_equals_single_gpu(g, tmp_path, mode):
     import pickle
     if g.device_count() < 2:
@@ -61,7 +64,7 @@ def test_sharded_equals_single_gpu(g, tmp_path, mode):
         g.synth.add_bsc(sc, bits=441, V=4)
     if ft == g.FT_FPFH:
         g.synth.add_fpfh(sc)   # matrix-free: each rank sweeps its block of source rows, column minima merged (§3.5)
-    reg = g.registration.from_scene(sc, ft, ct)
+    reg = g.registration.from_scene(sc, ft, ct, force_exact=mode.endswith("-exact"))
     for it in range(6):
         st = reg.iterate()
         sp, tp = reg.pairs()

@@ -382,3 +382,27 @@ def test_bsc_672_bits_loop(g, orc):
         sp, tp = reg.pairs()
         osp, otp = o.pairs()
         assert np.array_equal(sp, osp) and np.array_equal(tp, otp)
+
+
+def test_page_locked_caller_buffers_give_identical_results(g):
+    """ghicp_host_alloc: coordinates uploaded from and results read into page-locked caller buffers (one DMA each, no staging
+    copy inside the library) — same pairs, same transform, same updated source as with pageable numpy arrays."""
+    sc = g.synth.add_bsc(g.synth.gen_points(900, 1100, overlap=0.6, extent=(50, 50, 10), noise=0.04, seed=77), bits=441, V=4)
+    a = g.registration.from_scene(sc, g.FT_BSC, g.CT_NN)
+    b = g.registration.from_scene(sc, g.FT_BSC, g.CT_NN)
+    S_pin = g.capi.pinned_copy(np.asfortranarray(sc.S, dtype=np.float64), order="F")
+    T_pin = g.capi.pinned_copy(np.asfortranarray(sc.T, dtype=np.float64), order="F")
+    sp_buf = g.capi.pinned_empty(1100, np.int32)
+    tp_buf = g.capi.pinned_empty(1100, np.int32)
+    S_a = np.asfortranarray(sc.S, dtype=np.float64)
+    for it in range(4):
+        a.set_keypoints(S_a, np.asfortranarray(sc.T, dtype=np.float64))
+        b.set_keypoints(S_pin, T_pin)
+        sa, sb = a.iterate(), b.iterate()
+        assert np.array_equal(np.array(sa.Rt), np.array(sb.Rt)) and sa.cor == sb.cor
+        pa = a.pairs()
+        pb = b.pairs(out=(sp_buf, tp_buf))
+        assert np.array_equal(pa[0], pb[0]) and np.array_equal(pa[1], pb[1])
+        S_a = a.source()
+        b.source(out=S_pin)
+        assert np.array_equal(S_a, S_pin)

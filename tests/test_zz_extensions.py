@@ -126,12 +126,38 @@ def test_fpfh_auto_mode_and_overrides(g, monkeypatch):
         assert np.array_equal(r.pairs()[0], plane.pairs()[0]) and np.array_equal(r.pairs()[1], plane.pairs()[1])
     assert np.array_equal(np.array(a.Rt), np.array(b.Rt)) and np.array_equal(np.array(e.Rt), np.array(b.Rt))
     assert e.cd_mean == pytest.approx(b.cd_mean, rel=1e-12)
-    km = g.registration.from_scene(sc, g.FT_FPFH, g.CT_KM)            # KM keeps the stored plane in auto mode
-    km.build_fd()                                                     # (the FD stage is set up lazily: do it before the override)
-    monkeypatch.setenv("GHICP_FPFH_MATRIX_FREE", "1")
-    km_mf = g.registration.from_scene(sc, g.FT_FPFH, g.CT_KM)
+    km = g.registration.from_scene(sc, g.FT_FPFH, g.CT_KM, fpfh_matrix_free=-1)   # the stored float plane
+    km_mf = g.registration.from_scene(sc, g.FT_FPFH, g.CT_KM)                       # auto: matrix-free for KM as well
     x, y = km_mf.iterate(), km.iterate()
     assert x.nnz == y.nnz and abs(x.km_energy - y.km_energy) <= 80 * 0.01 + 1e-9 * abs(y.km_energy)
+
+
+def test_fpfh_km_filter_gate_gives_the_exact_graph(g, monkeypatch):
+    """FPFH + KM from iteration 2 on (penalty = RMS*para1*scale*para2): the FP32 filter with every row's threshold at the
+    penalty + exact evaluation of its hits must produce the SAME candidate graph as the all-double sweeps, hence (same
+    deterministic auction) the same matching and transform, iteration by iteration."""
+    N, M = 700, 640
+    sc = fpfh_scene(g, N, M, 21)
+    fast = g.registration.from_scene(sc, g.FT_FPFH, g.CT_KM)
+    monkeypatch.setenv("GHICP_FPFH_EXACT", "1")
+    slow = g.registration.from_scene(sc, g.FT_FPFH, g.CT_KM)
+    n_gate = 0
+    for it in range(8):
+        monkeypatch.delenv("GHICP_FPFH_EXACT", raising=False)
+        a = fast.iterate()
+        monkeypatch.setenv("GHICP_FPFH_EXACT", "1")
+        b = slow.iterate()
+        assert b.stream_passes == 0
+        n_gate += 1 if a.stream_passes >= 1 else 0
+        assert (a.nnz, a.cor) == (b.nnz, b.cor), it
+        assert a.penalty == b.penalty
+        assert a.km_energy == pytest.approx(b.km_energy, rel=1e-12)
+        pa, pb = fast.pairs(), slow.pairs()
+        assert np.array_equal(pa[0], pb[0]) and np.array_equal(pa[1], pb[1]), it
+        assert np.array_equal(np.array(a.Rt), np.array(b.Rt)), it
+        if a.converged:
+            break
+    assert n_gate >= 1, "the filter's KM gate was never taken"
 
 
 # ---- opt-in estimators --------------------------------------------------------------------------------------------
