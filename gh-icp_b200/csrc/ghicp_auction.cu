@@ -319,22 +319,34 @@ __device__ __forceinline__ void bid_serial(const AucArgs &a, int e) {
   Top2 t;
   t.best = -1e300; t.second = -1e300; t.idx = -1;
   double bg = 0.0;
-  if (REVERSE) {
-    for (long long k = a.colptr[e], ke = a.colptr[e + 1]; k < ke; ++k) {
-      const int i = a.csc_row[k];
-      top2_push_h(t, a.csc_gain[k] - ldcg_d(&a.profit[i]), i, e);
+  long long k, ke;
+  if (REVERSE) { k = a.colptr[e]; ke = a.colptr[e + 1]; }
+  else { k = a.rowptr[(size_t)e * a.n_chunks]; ke = a.rowptr[(size_t)(e + 1) * a.n_chunks]; }
+  const int *__restrict__ adj = REVERSE ? a.csc_row : a.csr_col;
+  const double *__restrict__ gains = REVERSE ? a.csc_gain : a.csr_gain;
+  const double *other = REVERSE ? a.profit : a.price;
+  // four edges in flight: the two dependent loads of an edge (index, then the price / profit it points at) overlap
+  for (; k + 3 < ke; k += 4) {
+    int x[4]; double g[4], p[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { x[u] = adj[k + u]; g[u] = gains[k + u]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) p[u] = ldcg_d(&other[x[u]]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const double v = g[u] - p[u];
+      if (!REVERSE && (v > t.best || (v == t.best && t.idx >= 0 && tie_less(e, x[u], t.idx)))) bg = g[u];
+      top2_push_h(t, v, x[u], e);
     }
-    rev_finish(a, e, t);
-  } else {
-    for (long long k = a.rowptr[(size_t)e * a.n_chunks], ke = a.rowptr[(size_t)(e + 1) * a.n_chunks]; k < ke; ++k) {
-      const int j = a.csr_col[k];
-      const double g = a.csr_gain[k];
-      const double v = g - ldcg_d(&a.price[j]);
-      if (v > t.best || (v == t.best && t.idx >= 0 && tie_less(e, j, t.idx))) bg = g;
-      top2_push_h(t, v, j, e);
-    }
-    fwd_finish(a, e, t, bg);
   }
+  for (; k < ke; ++k) {
+    const int x = adj[k];
+    const double g = gains[k];
+    const double v = g - ldcg_d(&other[x]);
+    if (!REVERSE && (v > t.best || (v == t.best && t.idx >= 0 && tie_less(e, x, t.idx)))) bg = g;
+    top2_push_h(t, v, x, e);
+  }
+  if (REVERSE) rev_finish(a, e, t); else fwd_finish(a, e, t, bg);
 }
 
 template <typename Append>
@@ -504,7 +516,9 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
               __syncthreads();
               continue;
             }
-          } else if (short_rows) {
+          } else if (short_rows == 1 || (short_rows == 2 && m > 3 * NW)) {
+            // one thread per bidder: short lists always; medium lists (<= 32 candidates) once the bidders outnumber the
+            // CTA's warps three to one (16 warps walking 28 lists each in turn cost more than 512 threads walking one each)
             for (int w = threadIdx.x; w < m; w += PA_THREADS) bid_serial<REVERSE>(a, ldcg_i(&list[w]));
           } else {
             for (int w = warp; w < m; w += NW) {
@@ -555,7 +569,7 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
       const long long tw = (long long)gridDim.x * NW;
       if (16ll * n <= tw) G = 16; else if (8ll * n <= tw) G = 8; else if (4ll * n <= tw) G = 4; else if (2ll * n <= tw) G = 2;
     }
-    if (short_rows) {
+    if (short_rows == 1 || (short_rows == 2 && n > 3 * gwarps)) {
       for (int w = gtid; w < n; w += gthreads) bid_serial<REVERSE>(a, ldcg_i(&list[w]));
     } else if (G > 1) {
       const int gpc = NW / G, grp = warp / G, slice = warp % G;
@@ -693,7 +707,7 @@ int km_auction_settled(Ctx *c, int n_rows, int n_cols, long long nnz_hint, doubl
   sn = sn < 16 ? 16 : (sn > PA_SMALL ? PA_SMALL : sn);
   int *l0 = c->d_list[0], *l1 = c->d_list[1];
   int mr = 4000000;
-  int sr = avg_row <= 4.0 ? 1 : 0;   // one thread per bidder
+  int sr = avg_row <= 4.0 ? 1 : (avg_row <= 32.0 ? 2 : 0);   // one thread per bidder (2: only when bidders outnumber warps)
   void *args[] = {(void *)&a, (void *)&l0, (void *)&l1, (void *)&mr, (void *)&sn, (void *)&sr};
 #if defined(GHICP_EMU_HOST)
   (void)args;
@@ -794,7 +808,7 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
       int *l0 = c->d_list[0], *l1 = c->d_list[1];
       int mr = max_rounds;
       int sn = small_fwd;
-      int sr = avg_row <= 4.0 ? 1 : 0;   // short adjacency lists: one thread per bidder
+      int sr = avg_row <= 4.0 ? 1 : (avg_row <= 32.0 ? 2 : 0);   // short / medium adjacency lists: one thread per bidder
       void *args[] = {(void *)&a, (void *)&l0, (void *)&l1, (void *)&mr, (void *)&sn, (void *)&sr};
 #if defined(GHICP_EMU_HOST)
       (void)args;   // host emulation: all blocks of the (small) grid run as fibers, the grid barrier is a rendezvous
@@ -838,7 +852,7 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
       int *l0 = c->d_list[0], *l1 = c->d_list[1];
       int mr = max_rounds;
       int sn = small_rev;
-      int sr = avg_col <= 4.0 ? 1 : 0;
+      int sr = avg_col <= 4.0 ? 1 : (avg_col <= 32.0 ? 2 : 0);
       void *args[] = {(void *)&a, (void *)&l0, (void *)&l1, (void *)&mr, (void *)&sn, (void *)&sr};
 #if defined(GHICP_EMU_HOST)
       (void)args;

@@ -79,6 +79,7 @@ struct StreamArgs {
   size_t fd_rows;            // rows of the plane held by this context
   int N, M;
   int row0, nloc;            // source rows [row0, row0 + nloc) streamed by this context
+  int rb;                    // source rows per CTA of this launch (<= ST_RB, a multiple of the batch)
   const float4 *S4, *T4;
   const double *s, *t;
   double scale, WED, WFD;

@@ -31,7 +31,8 @@ constexpr int ST_WARPS = ST_THREADS / 32;
 constexpr int ST_CPL = 8;                         // columns per lane
 constexpr int ST_PANEL = 32 * ST_CPL;             // columns per warp
 constexpr int ST_CTA_COLS = ST_WARPS * ST_PANEL;  // 2048
-constexpr int ST_RB = 256;                        // source rows per CTA
+constexpr int ST_RB = 256;                        // source rows per CTA (upper bound; StreamArgs::rb is what a launch uses)
+constexpr int ST_RB_MIN = 64;
 // tuning knobs (compile-time; tools/build_variants.sh builds A/B libraries with other values)
 #ifndef GHICP_ST_UNROLL
 #define GHICP_ST_UNROLL 4
@@ -589,8 +590,8 @@ __global__ void __launch_bounds__(ST_THREADS, (TMA && !X2) ? 3 : GHICP_ST_MINB) 
   __shared__ int s_cnt[ST_RB];
   __shared__ double s_red[2][ST_WARPS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int r0 = a.row0 + blockIdx.y * ST_RB;
-  const int nrows = min(ST_RB, a.row0 + a.nloc - r0);
+  const int r0 = a.row0 + blockIdx.y * a.rb;
+  const int nrows = min(a.rb, a.row0 + a.nloc - r0);
   if (TMA && HAS_FD) {
     // start the FD stream first: the operand staging below overlaps with the first bulk copies in flight
     const int panel0 = blockIdx.x * ST_CTA_COLS + warp * ST_PANEL;
@@ -818,11 +819,12 @@ __global__ void k_xscatter(const unsigned char *__restrict__ blocks, size_t bloc
 }  // namespace
 
 // =============================================================================================
+static int stream_rows_per_cta(const Ctx *c);
 static StreamArgs make_args(Ctx *c, const CostParams &cp) {
   StreamArgs a{};
   a.fd = (c->cfg.feature_type == GHICP_FT_BSC) ? c->d_fd16 : nullptr;
   a.fd_rows = c->fd_rows; a.N = c->N; a.M = c->M;
-  a.row0 = c->r0; a.nloc = c->nloc;
+  a.row0 = c->r0; a.nloc = c->nloc; a.rb = stream_rows_per_cta(c);
   a.row_fd = c->d_row_fd; a.csr_fd = c->d_csr_fd;
   a.S4 = reinterpret_cast<const float4 *>(c->d_S4); a.T4 = reinterpret_cast<const float4 *>(c->d_T4);
   a.s = c->d_s; a.t = c->d_t;
@@ -838,10 +840,39 @@ static StreamArgs make_args(Ctx *c, const CostParams &cp) {
   return a;
 }
 
-static dim3 stream_grid(const Ctx *c) {
-  return dim3((c->M + ST_CTA_COLS - 1) / ST_CTA_COLS, (c->nloc + ST_RB - 1) / ST_RB);
+// Source rows per CTA.  The grid is (column blocks) x (row blocks) CTAs of equal cost, two resident per SM: with 256 rows a
+// sharded rank's last wave is mostly empty (6250 rows x 50k columns: 625 CTAs on 296 slots = 3 waves for 2.1 waves of
+// work).  Pick the height (multiple of the batch, 64 ... 256) that minimises waves x rows — 180 rows in that example:
+// 875 CTAs, 2.96 waves.  GHICP_STREAM_RB overrides (tests).
+static int stream_rows_per_cta(const Ctx *c) {
+  static const int forced = getenv("GHICP_STREAM_RB") ? atoi(getenv("GHICP_STREAM_RB")) : 0;
+  if (forced >= ST_RB_MIN && forced <= ST_RB) return forced / ST_UNROLL * ST_UNROLL;
+  static int slots = 0;
+  if (slots == 0) {
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device);
+    slots = 2 * (n_sm > 0 ? n_sm : 148);
+  }
+  const long long gx = (c->M + ST_CTA_COLS - 1) / ST_CTA_COLS;
+  const int nloc = c->nloc > 0 ? c->nloc : 1;
+  int best = ST_RB;
+  long long best_cost = -1;
+  for (int rb = ST_RB; rb >= ST_RB_MIN; rb -= ST_UNROLL) {
+    const long long ctas = gx * ((nloc + rb - 1) / rb);
+    const long long waves = (ctas + slots - 1) / slots;
+    const long long cost = waves * (rb + 6);   // + the CTA's prologue / epilogue, in row equivalents
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = rb; }
+  }
+  return best;
 }
-int stream_num_parts(const Ctx *c) {
+static dim3 stream_grid(const Ctx *c) {
+  const int rb = stream_rows_per_cta(c);
+  return dim3((c->M + ST_CTA_COLS - 1) / ST_CTA_COLS, (c->nloc + rb - 1) / rb);
+}
+int stream_num_parts(const Ctx *c) {   // upper bound over every admissible CTA height (sizes d_part_stats)
+  return (int)(((c->M + ST_CTA_COLS - 1) / ST_CTA_COLS) * ((c->nloc + ST_RB_MIN - 1) / ST_RB_MIN));
+}
+static int stream_num_parts_now(const Ctx *c) {
   dim3 g = stream_grid(c);
   return (int)(g.x * g.y);
 }
@@ -963,7 +994,7 @@ cudaError_t launch_stream_resolve(Ctx *c, const CostParams &cp, bool with_cols) 
 
 cudaError_t launch_finalize_fast(Ctx *c, const LoopScalars &ls) {
   (void)ls;
-  GHICP_LAUNCH(k_finalize_fast, 1, 1024, 0, c->stream, c->d_part_stats, stream_num_parts(c), c->d_xstats, c->rank, c->kappa);
+  GHICP_LAUNCH(k_finalize_fast, 1, 1024, 0, c->stream, c->d_part_stats, stream_num_parts_now(c), c->d_xstats, c->rank, c->kappa);
   c->launches++;
   return cudaGetLastError();
 }
