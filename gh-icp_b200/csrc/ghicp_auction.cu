@@ -175,12 +175,23 @@ namespace cg = cooperative_groups;
 constexpr int PA_THREADS = 512;
 constexpr int PA_SMALL = 2048;  // active-set size below which CTA 0 iterates alone
 
+// State written with plain stores (prices, profits, owners, assignments, bid slots, the active lists) may be read with plain,
+// L1-cached loads: inside CTA 0's tail rounds the CTA's own stores go through the same L1, and every full-grid phase starts
+// behind __threadfence() + grid.sync(), whose acquire makes the other CTAs' earlier stores visible to plain loads (CUDA's
+// grid-synchronisation guarantee).  Words that ATOMICS modify (bid keys, counters, D slots) are always read at L2.
+// GHICP_AUC_L2_LOADS keeps every state load at L2 (ld.global.cg), the round-1 behaviour, for A/B runs.
+#if defined(GHICP_AUC_L2_LOADS)
 __device__ __forceinline__ int ldcg_i(const int *p) { return __ldcg(p); }
+__device__ __forceinline__ double ldcg_d(const double *p) { return __ldcg(p); }
+#else
+__device__ __forceinline__ int ldcg_i(const int *p) { return *p; }
+__device__ __forceinline__ double ldcg_d(const double *p) { return *p; }
+#endif
+__device__ __forceinline__ int ldl2_i(const int *p) { return __ldcg(p); }   // counters (atomically updated): always L2
 __device__ __forceinline__ unsigned long long pack_key(float v, int who) {  // v > 0
   return ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)(who + 1);
 }
 __device__ __forceinline__ int key_who(unsigned long long k) { return (int)(unsigned)(k & 0xffffffffull) - 1; }
-__device__ __forceinline__ double ldcg_d(const double *p) { return __ldcg(p); }
 
 // one person bids (warp-cooperative). Returns nothing; writes bid slots / dummy assignment.
 // scan edges [kb, ke) of person i: best / second-best value (and the gain of the best edge), warp-reduced
@@ -431,7 +442,7 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
   auto now_ns = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
 #endif
   while (true) {
-    const int n = ldcg_i(&a.counters[cur]);
+    const int n = ldl2_i(&a.counters[cur]);
     if (n == 0 || rounds >= max_rounds) break;
     // every thread of the grid reads the same D (written before the last grid barrier): a uniform decision
     if (cut_on && __ldcg(d_slot(a.counters, cur)) <= a.d_budget_fx) { cut = true; break; }
@@ -551,8 +562,8 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
       __threadfence();
       grid.sync();
       if (gtid == 0) atomicAdd((unsigned long long *)&a.counters[12], now_ns() - t_mark);  // ns in tail mode
-      cur = ldcg_i(&a.counters[4]);
-      rounds = ldcg_i(&a.counters[5]);
+      cur = ldl2_i(&a.counters[4]);
+      rounds = ldl2_i(&a.counters[5]);
       continue;
     }
     // ---- full-grid round
@@ -560,7 +571,7 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
     int *next = lists[cur ^ 1];
     if (gtid == 0) {
       __stcg(&a.counters[cur ^ 1], 0); __stcg(d_slot(a.counters, cur ^ 1), 0ull);
-      atomicAdd((unsigned long long *)&a.counters[8], (unsigned long long)n); __stcg(&a.counters[10], ldcg_i(&a.counters[10]) + 1);
+      atomicAdd((unsigned long long *)&a.counters[8], (unsigned long long)n); __stcg(&a.counters[10], ldl2_i(&a.counters[10]) + 1);
     }
     // warps per bidder: as many as the grid affords, so that a round with few bidders and long adjacency lists (the
     // dense first iterations: ~1400 candidates per keypoint) costs one short scan per warp instead of one long one
@@ -611,9 +622,9 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
   }
   if (gtid == 0) {
     __stcg(&a.counters[4], cur);
-    __stcg(&a.counters[6], ldcg_i(&a.counters[6]) + rounds);  // accumulated rounds of the whole solve
+    __stcg(&a.counters[6], ldl2_i(&a.counters[6]) + rounds);  // accumulated rounds of the whole solve
     if (cut) __stcg(&a.counters[36], 1);                       // stopped on the D budget: the list is not empty by design
-    else if (ldcg_i(&a.counters[cur]) != 0) __stcg(&a.counters[3], 1);  // sticky: a phase hit the round limit
+    else if (ldl2_i(&a.counters[cur]) != 0) __stcg(&a.counters[3], 1);  // sticky: a phase hit the round limit
   }
 }
 
