@@ -173,7 +173,7 @@ __global__ void k_rev_collect(int n_cols, const int *owner, const double *price,
 // ---------------------------------------------------------------------------------------------
 namespace cg = cooperative_groups;
 constexpr int PA_THREADS = 512;
-constexpr int PA_SMALL = 2048;  // active-set size below which CTA 0 iterates alone
+constexpr int PA_SMALL = 1024;  // largest active set CTA 0 iterates alone (its lists and bid slots sit in shared memory)
 
 // State written with plain stores (prices, profits, owners, assignments, bid slots, the active lists) may be read with plain,
 // L1-cached loads: inside CTA 0's tail rounds the CTA's own stores go through the same L1, and every full-grid phase starts
@@ -236,42 +236,64 @@ __device__ __forceinline__ void fwd_scan(const AucArgs &a, int i, int lane, long
     }
   }
 }
+// Bid slots: where a bidder leaves (target, value, auxiliary) between the bid half and the commit half of a round.
+// Full-grid rounds: global arrays indexed by the bidder's id; CTA 0's tail rounds: SHARED memory indexed by the bidder's
+// position in the active list (two L2 round trips less per round on the tail's dependent chain).
+struct SlotsGlobal {
+  int *o; double *v, *x;
+  __device__ __forceinline__ void put(int k, int obj, double val, double aux) const { __stcg(&o[k], obj); __stcg(&v[k], val); __stcg(&x[k], aux); }
+  __device__ __forceinline__ void none(int k) const { __stcg(&o[k], -1); }
+  __device__ __forceinline__ int obj(int k) const { return ldcg_i(&o[k]); }
+  __device__ __forceinline__ double val(int k) const { return ldcg_d(&v[k]); }
+  __device__ __forceinline__ double aux(int k) const { return ldcg_d(&x[k]); }
+};
+struct SlotsShared {
+  int *o; double *v, *x;
+  __device__ __forceinline__ void put(int k, int obj, double val, double aux) const { o[k] = obj; v[k] = val; x[k] = aux; }
+  __device__ __forceinline__ void none(int k) const { o[k] = -1; }
+  __device__ __forceinline__ int obj(int k) const { return o[k]; }
+  __device__ __forceinline__ double val(int k) const { return v[k]; }
+  __device__ __forceinline__ double aux(int k) const { return x[k]; }
+};
+__device__ __forceinline__ SlotsGlobal global_slots(const AucArgs &a) { return SlotsGlobal{a.bid_obj, a.bid_val, a.bid_aux}; }
+
 // one thread: turn (best, second) into a bid or retire to the private dummy
-__device__ __forceinline__ void fwd_finish(const AucArgs &a, int i, const Top2 &t, double bgain) {
+template <typename S>
+__device__ __forceinline__ void fwd_finish(const AucArgs &a, int i, const Top2 &t, double bgain, const S &sl, int key) {
   if (t.idx < 0 || t.best <= 0.0) {
     __stcg(&a.assign[i], DUMMY);
     __stcg(&a.profit[i], 0.0);
+    sl.none(key);
   } else {
     const double wv = fmax(t.second, 0.0);
     const double newprice = ldcg_d(&a.price[t.idx]) + (t.best - wv) + a.eps;
-    __stcg(&a.bid_obj[i], t.idx);
-    __stcg(&a.bid_val[i], newprice);
-    __stcg(&a.bid_aux[i], bgain);
+    sl.put(key, t.idx, newprice, bgain);
     // One atomic decides the round's winner: the key orders bidders by their bid rounded to float32, then
     // by id.  ANY bidder may win a round as long as the price becomes its own (exact, double) bid: that is
     // a valid auction step (price rises by >= eps, the winner is eps-happy), so float32 ordering is enough.
     atomicMax(&a.bidmax[t.idx], pack_key((float)newprice, i));
   }
 }
-__device__ __forceinline__ void fwd_bid_one(const AucArgs &a, int i, int lane) {
+template <typename S>
+__device__ __forceinline__ void fwd_bid_one(const AucArgs &a, int i, int lane, const S &sl, int key) {
   const long long b = a.rowptr[(size_t)i * a.n_chunks], e = a.rowptr[(size_t)(i + 1) * a.n_chunks];
   Top2 t;
   double bgain;
   fwd_scan(a, i, lane, b, e, t, bgain);
-  if (lane == 0) fwd_finish(a, i, t, bgain);
+  if (lane == 0) fwd_finish(a, i, t, bgain, sl, key);
 }
 // returns via append(): persons that stay / become unassigned
-template <typename Append>
-__device__ __forceinline__ void fwd_commit_one(const AucArgs &a, int i, Append append) {
+template <typename S, typename Append>
+__device__ __forceinline__ void fwd_commit_one(const AucArgs &a, int i, const S &sl, int key, Append append) {
   if (ldcg_i(&a.assign[i]) != UNASSIGNED) return;
-  const int j = ldcg_i(&a.bid_obj[i]);
+  const int j = sl.obj(key);
   if (key_who(__ldcg(&a.bidmax[j])) == i) {
     const int prev = ldcg_i(&a.owner[j]);
-    const double bv = ldcg_d(&a.bid_val[i]);
+    const double bv = sl.val(key);
     __stcg(&a.owner[j], i);
     __stcg(&a.price[j], bv);
     __stcg(&a.assign[i], j);
-    __stcg(&a.profit[i], ldcg_d(&a.bid_aux[i]) - bv);
+    __stcg(&a.profit[i], sl.aux(key) - bv);
     __stcg(&a.bidmax[j], 0ull);  // slot back to "no bid" (a loser reading 0 or the key sees "not me" either way)
     if (prev >= 0) { __stcg(&a.assign[prev], UNASSIGNED); append(prev, 0.0); }
   } else {
@@ -306,27 +328,27 @@ __device__ __forceinline__ void rev_scan(const AucArgs &a, int j, int lane, long
     }
   }
 }
-__device__ __forceinline__ void rev_finish(const AucArgs &a, int j, const Top2 &t) {
+template <typename S>
+__device__ __forceinline__ void rev_finish(const AucArgs &a, int j, const Top2 &t, const S &sl, int key) {
   if (t.idx < 0 || t.best <= a.eps) {
     __stcg(&a.price[j], 0.0);   // nobody is worth attracting: price falls to the floor, object stays free
-    __stcg(&a.bid_obj[j], -1);
+    sl.none(key);
   } else {
     const double delta = fmin(t.best, (t.best - t.second) + a.eps);
-    __stcg(&a.bid_obj[j], t.idx);
-    __stcg(&a.bid_val[j], delta);
-    __stcg(&a.bid_aux[j], t.best);
+    sl.put(key, t.idx, delta, t.best);
     atomicMax(&a.bidmax[t.idx], pack_key((float)delta, j));
   }
 }
-__device__ __forceinline__ void rev_offer_one(const AucArgs &a, int j, int lane) {
+template <typename S>
+__device__ __forceinline__ void rev_offer_one(const AucArgs &a, int j, int lane, const S &sl, int key) {
   Top2 t;
   rev_scan(a, j, lane, a.colptr[j], a.colptr[j + 1], t);
-  if (lane == 0) rev_finish(a, j, t);
+  if (lane == 0) rev_finish(a, j, t, sl, key);
 }
 // short adjacency lists (a settled loop: about one candidate per keypoint): ONE THREAD per bidder walks its list; the
 // (best, tie-ordered index, second) triple is the same whatever the partition of the list
-template <bool REVERSE>
-__device__ __forceinline__ void bid_serial(const AucArgs &a, int e) {
+template <bool REVERSE, typename S>
+__device__ __forceinline__ void bid_serial(const AucArgs &a, int e, const S &sl, int key) {
   Top2 t;
   t.best = -1e300; t.second = -1e300; t.idx = -1;
   double bg = 0.0;
@@ -357,19 +379,19 @@ __device__ __forceinline__ void bid_serial(const AucArgs &a, int e) {
     if (!REVERSE && (v > t.best || (v == t.best && t.idx >= 0 && tie_less(e, x, t.idx)))) bg = g;
     top2_push_h(t, v, x, e);
   }
-  if (REVERSE) rev_finish(a, e, t); else fwd_finish(a, e, t, bg);
+  if (REVERSE) rev_finish(a, e, t, sl, key); else fwd_finish(a, e, t, bg, sl, key);
 }
 
-template <typename Append>
-__device__ __forceinline__ void rev_commit_one(const AucArgs &a, int j, Append append) {
-  const int i = ldcg_i(&a.bid_obj[j]);
+template <typename S, typename Append>
+__device__ __forceinline__ void rev_commit_one(const AucArgs &a, int j, const S &sl, int key, Append append) {
+  const int i = sl.obj(key);
   if (i < 0) return;
   if (key_who(__ldcg(&a.bidmax[i])) == j) {
     const int old = ldcg_i(&a.assign[i]);
-    const double dl = ldcg_d(&a.bid_val[j]);
+    const double dl = sl.val(key);
     __stcg(&a.assign[i], j);
     __stcg(&a.owner[j], i);
-    __stcg(&a.price[j], ldcg_d(&a.bid_aux[j]) - dl);
+    __stcg(&a.price[j], sl.aux(key) - dl);
     __stcg(&a.profit[i], ldcg_d(&a.profit[i]) + dl);
     __stcg(&a.bidmax[i], 0ull);
     if (old >= 0) {
@@ -424,6 +446,11 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
   __shared__ Top2 s_pt[NW];
   __shared__ double s_pg[NW];
 #endif
+  // CTA 0's tail rounds: active lists and bid slots in shared memory (used by block 0 only)
+  __shared__ int s_list[2][PA_SMALL];
+  __shared__ int s_bobj[PA_SMALL];
+  __shared__ double s_bval[PA_SMALL], s_baux[PA_SMALL];
+  const SlotsGlobal gsl = global_slots(a);
   int *lists[2] = {list0, list1};
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -448,16 +475,19 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
     if (cut_on && __ldcg(d_slot(a.counters, cur)) <= a.d_budget_fx) { cut = true; break; }
     if (gtid == 0) t_mark = now_ns();
     if (n <= small_n) {
-      // ---- tail: CTA 0 alone, block-level barriers only
+      // ---- tail: CTA 0 alone, block-level barriers only; the active lists and the bid slots live in shared memory
       if (blockIdx.x == 0) {
+        int sc = 0;   // which of the two shared lists holds the current bidders
+        for (int w = threadIdx.x; w < n; w += PA_THREADS) s_list[0][w] = lists[cur][w];
         if (threadIdx.x == 0) { s_n = n; s_D = __ldcg(d_slot(a.counters, cur)); }
         __syncthreads();
+        const SlotsShared sl{s_bobj, s_bval, s_baux};
         while (true) {
           const int m = s_n;
           if (m == 0 || m > small_n || rounds >= max_rounds) break;
           if (cut_on && s_D <= a.d_budget_fx) break;   // the outer loop re-reads the same D and stops
-          const int *list = lists[cur];
-          int *next = lists[cur ^ 1];
+          const int *list = s_list[sc];
+          int *next = s_list[sc ^ 1];
           if (threadIdx.x == 0) {
             s_next = 0; s_Dnext = 0ull; atomicAdd((unsigned long long *)&a.counters[8], (unsigned long long)m);
             if (a.profile) {   // GHICP_AUCTION_DEBUG: time and rounds per active-set size class
@@ -472,7 +502,7 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
             const int bidder = warp / G, slice = warp % G;
             int i = -1;
             if (bidder < m) {
-              i = ldcg_i(&list[bidder]);
+              i = list[bidder];
               Top2 t; double bg;
               split_scan<REVERSE>(a, i, G, slice, lane, t, bg);
               if (lane == 0) { s_pt[warp] = t; s_pg[warp] = bg; }
@@ -496,7 +526,7 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
                     __stcg(&a.price[j], newprice);
                     __stcg(&a.assign[i], j);
                     __stcg(&a.profit[i], bg - newprice);
-                    if (prev >= 0) { __stcg(&a.assign[prev], UNASSIGNED); __stcg(&next[0], prev); s_next = 1; }
+                    if (prev >= 0) { __stcg(&a.assign[prev], UNASSIGNED); next[0] = prev; s_next = 1; }
                   }
                 } else {
                   const int j = i;  // the list holds objects in the reverse phase
@@ -513,15 +543,15 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
                     if (old >= 0) {
                       __stcg(&a.owner[old], -1);
                       const double po = ldcg_d(&a.price[old]);
-                      if (po > 0.0) { __stcg(&next[0], old); s_next = 1; s_Dnext = d_fx(po); }
+                      if (po > 0.0) { next[0] = old; s_next = 1; s_Dnext = d_fx(po); }
                     }
                   }
                 }
-              } else if (REVERSE) rev_finish(a, i, t); else fwd_finish(a, i, t, bg);
+              } else if (REVERSE) rev_finish(a, i, t, sl, bidder); else fwd_finish(a, i, t, bg, sl, bidder);
             }
             if (m == 1) {   // committed above
               __syncthreads();
-              cur ^= 1;
+              cur ^= 1; sc ^= 1;
               ++rounds;
               if (threadIdx.x == 0) { s_n = s_next; s_D = s_Dnext; }
               __syncthreads();
@@ -530,27 +560,33 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
           } else if (short_rows == 1 || (short_rows == 2 && m > 3 * NW)) {
             // one thread per bidder: short lists always; medium lists (<= 32 candidates) once the bidders outnumber the
             // CTA's warps three to one (16 warps walking 28 lists each in turn cost more than 512 threads walking one each)
-            for (int w = threadIdx.x; w < m; w += PA_THREADS) bid_serial<REVERSE>(a, ldcg_i(&list[w]));
+            for (int w = threadIdx.x; w < m; w += PA_THREADS) bid_serial<REVERSE>(a, list[w], sl, w);
           } else {
             for (int w = warp; w < m; w += NW) {
-              const int e = ldcg_i(&list[w]);
-              if (REVERSE) rev_offer_one(a, e, lane); else fwd_bid_one(a, e, lane);
+              const int e = list[w];
+              if (REVERSE) rev_offer_one(a, e, lane, sl, w); else fwd_bid_one(a, e, lane, sl, w);
             }
           }
           __syncthreads();
           for (int w = threadIdx.x; w < m; w += PA_THREADS) {
-            const int e = ldcg_i(&list[w]);
+            const int e = list[w];
             auto app = [&](int x, double p) {
-              __stcg(&next[atomicAdd(&s_next, 1)], x);
+              next[atomicAdd(&s_next, 1)] = x;
               if (REVERSE) atomicAdd(&s_Dnext, d_fx(p));
             };
-            if (REVERSE) rev_commit_one(a, e, app); else fwd_commit_one(a, e, app);
+            if (REVERSE) rev_commit_one(a, e, sl, w, app); else fwd_commit_one(a, e, sl, w, app);
           }
           __syncthreads();
-          cur ^= 1;
+          cur ^= 1; sc ^= 1;
           ++rounds;
           if (threadIdx.x == 0) { s_n = s_next; s_D = s_Dnext; }
           __syncthreads();
+        }
+        // hand the current list back to the global arrays (the grid rounds, or the host, continue from there)
+        {
+          const int m = s_n;
+          int *gl = lists[cur];
+          for (int w = threadIdx.x; w < m; w += PA_THREADS) __stcg(&gl[w], s_list[sc][w]);
         }
         if (threadIdx.x == 0) {
           __stcg(&a.counters[cur], s_n);
@@ -581,7 +617,7 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
       if (16ll * n <= tw) G = 16; else if (8ll * n <= tw) G = 8; else if (4ll * n <= tw) G = 4; else if (2ll * n <= tw) G = 2;
     }
     if (short_rows == 1 || (short_rows == 2 && n > 3 * gwarps)) {
-      for (int w = gtid; w < n; w += gthreads) bid_serial<REVERSE>(a, ldcg_i(&list[w]));
+      for (int w = gtid; w < n; w += gthreads) { const int e = ldcg_i(&list[w]); bid_serial<REVERSE>(a, e, gsl, e); }
     } else if (G > 1) {
       const int gpc = NW / G, grp = warp / G, slice = warp % G;
       const int w = blockIdx.x * gpc + grp;   // n <= gridDim.x * gpc by the choice of G
@@ -596,12 +632,12 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
       if (w < n && slice == 0 && lane == 0) {
         Top2 t; double bg;
         split_merge(e, G, &s_pt[warp], &s_pg[warp], t, bg);
-        if (REVERSE) rev_finish(a, e, t); else fwd_finish(a, e, t, bg);
+        if (REVERSE) rev_finish(a, e, t, gsl, e); else fwd_finish(a, e, t, bg, gsl, e);
       }
     } else {
       for (int w = gwarp; w < n; w += gwarps) {
         const int e = ldcg_i(&list[w]);
-        if (REVERSE) rev_offer_one(a, e, lane); else fwd_bid_one(a, e, lane);
+        if (REVERSE) rev_offer_one(a, e, lane, gsl, e); else fwd_bid_one(a, e, lane, gsl, e);
       }
     }
     __threadfence();
@@ -612,7 +648,7 @@ __global__ void __launch_bounds__(PA_THREADS, 2) k_auction_persistent(AucArgs a,
         __stcg(&next[atomicAdd(&a.counters[cur ^ 1], 1)], x);
         if (REVERSE) atomicAdd(d_slot(a.counters, cur ^ 1), d_fx(p));
       };
-      if (REVERSE) rev_commit_one(a, e, app); else fwd_commit_one(a, e, app);
+      if (REVERSE) rev_commit_one(a, e, gsl, e, app); else fwd_commit_one(a, e, gsl, e, app);
     }
     __threadfence();
     grid.sync();
@@ -806,7 +842,10 @@ int km_auction(Ctx *c, int n_rows, int n_cols, long long nnz, double eps_final, 
   int small_rev = (int)(8192.0 / (avg_col > 1.0 ? avg_col : 1.0));
   small_fwd = small_fwd < 16 ? 16 : (small_fwd > PA_SMALL ? PA_SMALL : small_fwd);
   small_rev = small_rev < 16 ? 16 : (small_rev > PA_SMALL ? PA_SMALL : small_rev);
-  if (const char *ov = getenv("GHICP_AUCTION_SMALL")) small_fwd = small_rev = atoi(ov);  // experiment / test hook: 0 = grid rounds only
+  if (const char *ov = getenv("GHICP_AUCTION_SMALL")) {   // experiment / test hook: 0 = grid rounds only
+    small_fwd = small_rev = atoi(ov);
+    if (small_fwd > PA_SMALL) small_fwd = small_rev = PA_SMALL;
+  }
   const bool debug = getenv("GHICP_AUCTION_DEBUG") != nullptr;
   a.profile = debug ? 1 : 0;
   const double relax_factor = getenv("GHICP_AUCTION_RELAX") ? atof(getenv("GHICP_AUCTION_RELAX")) : 0.0;
