@@ -462,29 +462,42 @@ __global__ void k_ff_seed(FfArgs a, const int *__restrict__ prev_row_idx, const 
 }
 
 // The sweep.  PRE = true: FP32 argmin per row (and column) -> guess pairs.  PRE = false: candidate gate + statistics.
-// A thread owns one target column (its normalised histogram and split coordinates stay in registers); the CTA walks
-// FF_ROWS source rows, FF_RB at a time through shared memory.
+// A thread owns TWO target columns (j and j + FF_THREADS; their normalised histograms and split coordinates stay in
+// registers); the CTA walks FF_ROWS source rows, FF_RB at a time through shared memory.  One row's record is read from shared
+// memory once (broadcast LDS.128) and serves both columns: the two 33-term dots are the two independent instruction
+// streams, and the operand traffic per pair is half of the one-column form (ncu, round 2: LSU 31 % of the issue slots there).
+#ifndef GHICP_FF_CPT
+#define GHICP_FF_CPT 2
+#endif
+constexpr int FF_CPT = GHICP_FF_CPT;   // columns per thread (1 = the round-1 form, for A/B builds)
 template <bool PRE, bool COLS>
-__global__ void __launch_bounds__(FF_THREADS) k_ff_sweep(const FfArgs a) {
+__global__ void __launch_bounds__(FF_THREADS, 2) k_ff_sweep(const FfArgs a) {
   __shared__ __align__(16) float s_rec[FF_RB][FF_REC];
   __shared__ ffu64 s_guess[FF_RB];
   __shared__ double s_red[FF_THREADS / 32];
   const int tid = threadIdx.x, lane = tid & 31;
-  const int jraw = blockIdx.x * FF_THREADS + tid;
-  const bool valid = jraw < a.M;
-  const int j = valid ? jraw : a.M - 1;
   const int i_begin = a.row0 + blockIdx.y * FF_ROWS;
   const int i_end = min(a.row0 + a.nloc, i_begin + FF_ROWS);
   const float INF = __uint_as_float(0x7f800000u);
 
-  float ht[33];
+  int jc[FF_CPT]; bool valid[FF_CPT];
+  float ht[FF_CPT][33];
+  float txh[FF_CPT], tyh[FF_CPT], tzh[FF_CPT], txl[FF_CPT], tyl[FF_CPT], tzl[FF_CPT], thr_c[FF_CPT], cmin[FF_CPT];
+  int carg[FF_CPT];
 #pragma unroll
-  for (int k = 0; k < 33; ++k) ht[k] = a.tnT[(size_t)k * a.M + j];
-  const float txh = a.tco[j], tyh = a.tco[(size_t)a.M + j], tzh = a.tco[2 * (size_t)a.M + j];
-  const float txl = a.tco[3 * (size_t)a.M + j], tyl = a.tco[4 * (size_t)a.M + j], tzl = a.tco[5 * (size_t)a.M + j];
-  const float thr_c = (!PRE && COLS && valid) ? a.thr_col[j] : -INF;
-  float cmin = INF;   // PRE: running column minimum over this CTA's rows
-  int carg = 0;
+  for (int c = 0; c < FF_CPT; ++c) {
+    const int jraw = (blockIdx.x * FF_CPT + c) * FF_THREADS + tid;
+    valid[c] = jraw < a.M;
+    const int j = valid[c] ? jraw : a.M - 1;
+    jc[c] = j;
+#pragma unroll
+    for (int k = 0; k < 33; ++k) ht[c][k] = a.tnT[(size_t)k * a.M + j];
+    txh[c] = a.tco[j]; tyh[c] = a.tco[(size_t)a.M + j]; tzh[c] = a.tco[2 * (size_t)a.M + j];
+    txl[c] = a.tco[3 * (size_t)a.M + j]; tyl[c] = a.tco[4 * (size_t)a.M + j]; tzl[c] = a.tco[5 * (size_t)a.M + j];
+    thr_c[c] = (!PRE && COLS && valid[c]) ? a.thr_col[j] : -INF;
+    cmin[c] = INF;   // PRE: running column minimum over this CTA's rows
+    carg[c] = 0;
+  }
   double dsum = 0.0;
 
   for (int ib = i_begin; ib < i_end; ib += FF_RB) {
@@ -494,63 +507,84 @@ __global__ void __launch_bounds__(FF_THREADS) k_ff_sweep(const FfArgs a) {
     if (PRE && tid < FF_RB) s_guess[tid] = ~0ull;
     __syncthreads();
     float fsum = 0.f;
-    // one pair: the filter value and what the rare path needs
-    auto eval = [&](const float *rec, float &cd32, float &dist, float &fd, float &l) {
-      const float dx = (rec[33] - txh) + (rec[36] - txl);
-      const float dy = (rec[34] - tyh) + (rec[37] - tyl);
-      const float dz = (rec[35] - tzh) + (rec[38] - tzl);
-      const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-      // three independent partial sums: the 33-term FFMA chain would otherwise be one 33-deep dependency per row
-      float d0 = 0.f, d1 = 0.f, d2s = 0.f;
-#pragma unroll
-      for (int k = 0; k < 11; ++k) {
-        d0 = fmaf(rec[k], ht[k], d0);
-        d1 = fmaf(rec[11 + k], ht[11 + k], d1);
-        d2s = fmaf(rec[22 + k], ht[22 + k], d2s);
-      }
-      fd = fmaxf(fabsf((d0 + d1) + d2s), 1e-30f);
-      dist = a.scalef * ff_sqrt(d2);   // ED (src/ghicp_reg.cpp:122) in FP32
-      l = ff_lg2(fd);
-      cd32 = valid ? dist * ff_ex2(-a.exf * l) : INF;
-    };
-    auto process = [&](int r, const float *rec, float cd32, float dist, float fd, float l) {
-      if (PRE) {
-        // warp argmin of the row: REDUX on the (non-negative) float bits, first lane holding the minimum
-        const unsigned bits = __float_as_uint(cd32);
-        const unsigned m = __reduce_min_sync(0xffffffffu, bits);
-        const unsigned who = __ballot_sync(0xffffffffu, bits == m);
-        if (lane == __ffs(who) - 1 && m < 0x7f800000u) atomicMin(&s_guess[r], ((ffu64)m << 32) | (unsigned)j);
-        if (COLS && cd32 < cmin) { cmin = cd32; carg = ib + r; }
-      } else {
-        fsum += valid ? cd32 : 0.f;
-        const float rinv = ff_ex2(-l);                         // ~ 1 / fd32
-        // <= exact CD.  The first-order term only holds while FF_G / fd32 <= 1/8: below that the pair always takes the
-        // rare path, which bounds it through fd32 + FF_G instead.
-        const float lb = fd < 8.f * FF_G ? -INF : cd32 * (1.f - FF_D0 - a.c1 * rinv);
-        if (valid && lb <= rec[39]) ff_slow(a, 0, ib + r, j, dist, fd, rec[39]);
-        if (COLS && valid && lb <= thr_c) ff_slow(a, 1, ib + r, j, dist, fd, thr_c);
-      }
-    };
-    // two rows per step: two independent instruction streams for the scheduler (nb is uniform across the CTA)
-    for (int r = 0; r < nb; r += 2) {
+    for (int r = 0; r < nb; ++r) {
       asm volatile("" ::: "memory");   // keep the records in shared memory (no hoisting into registers / local memory)
-      const bool has_b = r + 1 < nb;
-      const float *rec_a = s_rec[r], *rec_b = s_rec[has_b ? r + 1 : r];
-      float cd_a, dist_a, fd_a, l_a, cd_b, dist_b, fd_b, l_b;
-      eval(rec_a, cd_a, dist_a, fd_a, l_a);
-      eval(rec_b, cd_b, dist_b, fd_b, l_b);
-      process(r, rec_a, cd_a, dist_a, fd_a, l_a);
-      if (has_b) process(r + 1, rec_b, cd_b, dist_b, fd_b, l_b);
+      const float *rec = s_rec[r];
+      float cd32[FF_CPT], dist[FF_CPT], fd[FF_CPT], l[FF_CPT];
+      {
+        // the filter value of both columns and what the rare path needs; three independent partial sums per dot
+        float d0[FF_CPT], d1[FF_CPT], d2s[FF_CPT];
+#pragma unroll
+        for (int c = 0; c < FF_CPT; ++c) { d0[c] = 0.f; d1[c] = 0.f; d2s[c] = 0.f; }
+#pragma unroll
+        for (int k = 0; k < 11; ++k) {
+          const float r0 = rec[k], r1 = rec[11 + k], r2 = rec[22 + k];
+#pragma unroll
+          for (int c = 0; c < FF_CPT; ++c) {
+            d0[c] = fmaf(r0, ht[c][k], d0[c]);
+            d1[c] = fmaf(r1, ht[c][11 + k], d1[c]);
+            d2s[c] = fmaf(r2, ht[c][22 + k], d2s[c]);
+          }
+        }
+        const float sxh = rec[33], syh = rec[34], szh = rec[35], sxl = rec[36], syl = rec[37], szl = rec[38];
+#pragma unroll
+        for (int c = 0; c < FF_CPT; ++c) {
+          const float dx = (sxh - txh[c]) + (sxl - txl[c]);
+          const float dy = (syh - tyh[c]) + (syl - tyl[c]);
+          const float dz = (szh - tzh[c]) + (szl - tzl[c]);
+          const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+          fd[c] = fmaxf(fabsf((d0[c] + d1[c]) + d2s[c]), 1e-30f);
+          dist[c] = a.scalef * ff_sqrt(d2);   // ED (src/ghicp_reg.cpp:122) in FP32
+          l[c] = ff_lg2(fd[c]);
+          cd32[c] = valid[c] ? dist[c] * ff_ex2(-a.exf * l[c]) : INF;
+        }
+      }
+      if (PRE) {
+        // warp argmin of the row over both columns of every lane: REDUX on the (non-negative) float bits, then the
+        // smallest column index among the holders of the minimum (= the first minimum of the row scan)
+        unsigned bmin = __float_as_uint(cd32[0]);
+#pragma unroll
+        for (int c = 1; c < FF_CPT; ++c) { const unsigned bc = __float_as_uint(cd32[c]); bmin = bc < bmin ? bc : bmin; }
+        const unsigned m = __reduce_min_sync(0xffffffffu, bmin);
+        if (m < 0x7f800000u) {
+          unsigned jm = 0xffffffffu;
+#pragma unroll
+          for (int c = FF_CPT - 1; c >= 0; --c) if (__float_as_uint(cd32[c]) == m) jm = (unsigned)jc[c];   // jc ascending in c
+          const unsigned jmin = __reduce_min_sync(0xffffffffu, jm);
+          if (jm == jmin && jm != 0xffffffffu) atomicMin(&s_guess[r], ((ffu64)m << 32) | jmin);
+        }
+        if (COLS) {
+#pragma unroll
+          for (int c = 0; c < FF_CPT; ++c)
+            if (cd32[c] < cmin[c]) { cmin[c] = cd32[c]; carg[c] = ib + r; }
+        }
+      } else {
+        const float thr_r = rec[39];
+#pragma unroll
+        for (int c = 0; c < FF_CPT; ++c) {
+          fsum += valid[c] ? cd32[c] : 0.f;
+          const float rinv = ff_ex2(-l[c]);                         // ~ 1 / fd32
+          // <= exact CD.  The first-order term only holds while FF_G / fd32 <= 1/8: below that the pair always takes the
+          // rare path, which bounds it through fd32 + FF_G instead.
+          const float lb = fd[c] < 8.f * FF_G ? -INF : cd32[c] * (1.f - FF_D0 - a.c1 * rinv);
+          if (valid[c] && lb <= thr_r) ff_slow(a, 0, ib + r, jc[c], dist[c], fd[c], thr_r);
+          if (COLS && valid[c] && lb <= thr_c[c]) ff_slow(a, 1, ib + r, jc[c], dist[c], fd[c], thr_c[c]);
+        }
+      }
     }
     if (PRE) {
       __syncthreads();
       if (tid < nb && s_guess[tid] != ~0ull) atomicMin(&a.rowguess[ib + tid], s_guess[tid]);
     } else {
-      dsum += (double)fsum;   // at most FF_RB FP32 values per partial
+      dsum += (double)fsum;   // at most FF_CPT * FF_RB FP32 values per partial
     }
   }
   if (PRE) {
-    if (COLS && valid && cmin < INF) atomicMin(&a.colguess[j], ((ffu64)__float_as_uint(cmin) << 32) | (unsigned)carg);
+    if (COLS) {
+#pragma unroll
+      for (int c = 0; c < FF_CPT; ++c)
+        if (valid[c] && cmin[c] < INF) atomicMin(&a.colguess[jc[c]], ((ffu64)__float_as_uint(cmin[c]) << 32) | (unsigned)carg[c]);
+    }
   } else {
     double v[1] = {dsum};
     block_sum<1, FF_THREADS>(v, s_red);
@@ -717,7 +751,7 @@ static FfArgs ff_args(Ctx *c, const CostParams &cp) {
   a.part = c->d_ff_part;
   return a;
 }
-static dim3 ff_grid(const Ctx *c) { return dim3((c->M + FF_THREADS - 1) / FF_THREADS, (c->nloc + FF_ROWS - 1) / FF_ROWS); }
+static dim3 ff_grid(const Ctx *c) { return dim3((c->M + FF_CPT * FF_THREADS - 1) / (FF_CPT * FF_THREADS), (c->nloc + FF_ROWS - 1) / FF_ROWS); }
 size_t fpfh_fast_parts(const Ctx *c) { const dim3 g = ff_grid(c); return (size_t)g.x * g.y; }
 size_t fpfh_fast_rec_floats() { return FF_REC; }
 
