@@ -321,6 +321,17 @@ static LoopScalars make_loop_scalars(const Ctx *c, const CostParams &cp) {
   return ls;
 }
 
+// Candidate edges a rank's block carries this iteration: twice the largest per-rank share of the last one (same on every
+// rank).  GHICP_KM_XUSE_MAX caps it (test hook: forces the overflow -> general-route fallback).
+static size_t settled_block_size(const Ctx *c) {
+  size_t x = std::min(c->xcap, ((size_t)std::max<long long>(1024, 2 * c->last_max_local_nnz + 256) + 3) & ~(size_t)3);
+  if (const char *ov = getenv("GHICP_KM_XUSE_MAX")) {
+    const long long v = atoll(ov);
+    if (v >= 4) x = std::min(x, (size_t)v & ~(size_t)3);
+  }
+  return x;
+}
+
 static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
   if (c->N <= 0 || c->M <= 0) { set_error(c, "iterate: keypoints not set"); return GHICP_E_ARG; }
   if (c->cfg.solver == GHICP_SOLVER_POINT_TO_PLANE && !c->have_normals) {
@@ -425,7 +436,7 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
   } else if (fpfh_km_fast) {
     // ---- FPFH + KM, settled loop: one filter sweep with every row's threshold at the penalty; the exactly evaluated hits with
     //      CD < penalty are the KM graph and travel as this rank's candidate block (the settled route below, same tail)
-    c->xuse = std::min(c->xcap, ((size_t)std::max<long long>(1024, 2 * c->last_max_local_nnz + 256) + 3) & ~(size_t)3);
+    c->xuse = settled_block_size(c);
     CK(c, launch_fpfh_fast_prep(c));
     CK(c, launch_fpfh_gate_seed(c, cp, ls));
     CK(c, cudaEventRecord(c->ev[4], st));
@@ -452,7 +463,7 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
     c->emit_on = true;
     // message size of this iteration: twice the largest per-rank share of the last one (the latency-bound all-gather carries
     // what the graph needs, not what the buffers could hold); an overflow redoes the iteration on the general route
-    c->xuse = std::min(c->xcap, ((size_t)std::max<long long>(1024, 2 * c->last_max_local_nnz + 256) + 3) & ~(size_t)3);
+    c->xuse = settled_block_size(c);
     CK(c, launch_stream_prep(c, cp, 0));
     CK(c, cudaMemsetAsync(c->d_cnt, 0, sizeof(int) * ((size_t)c->Npad + 2), st));
     CK(c, launch_penalty_only(c, ls));        // src/ghicp_reg.cpp:279-282: independent of this iteration's CD

@@ -88,6 +88,31 @@ def test_registration_through_the_abi_in_lock_step_with_the_oracle(ge, orc, ft, 
     reg.close()
 
 
+def test_settled_km_block_overflow_falls_back_to_the_general_route(ge, monkeypatch):
+    """The settled KM iteration carries each rank's candidates in a fixed-size block; when a block overflows (flag travels with
+    the statistics, the keypoints are left alone) the host repeats the iteration on the general route.  GHICP_KM_XUSE_MAX = 8
+    forces that on every settled iteration: results must equal the general route's (GHICP_KM_GENERAL) and the default's."""
+    g = ge
+    sc = g.synth.add_bsc(g.synth.gen_points(110, 100, overlap=0.9, seed=11), V=4)
+    runs = {}
+    for name, env in (("default", {}), ("overflow", {"GHICP_KM_XUSE_MAX": "8"}), ("general", {"GHICP_KM_GENERAL": "1"})):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        reg = g.registration.from_scene(sc, g.FT_BSC, g.CT_KM, max_iter=7)
+        out = []
+        for it in range(7):
+            st = reg.iterate()
+            out.append((st.cor, st.nnz, st.km_energy, np.array(st.Rt), reg.pairs(), reg.source()))
+        runs[name] = out
+        for k in env:
+            monkeypatch.delenv(k)
+    for name in ("overflow", "general"):
+        for a, b in zip(runs["default"], runs[name]):
+            assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2], name
+            assert np.array_equal(a[3], b[3]) and np.array_equal(a[5], b[5]), name
+            assert np.array_equal(a[4][0], b[4][0]) and np.array_equal(a[4][1], b[4][1]), name
+
+
 def test_smoke_entry_point(ge):
     import __graft_entry__ as entry
     entry.smoke()
