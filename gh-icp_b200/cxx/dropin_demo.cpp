@@ -2,7 +2,9 @@
 // seeded synthetic scene read from a small binary file written by the tests:
 //   header  int32 N, M, bits, V, ft, ct, dof; float bbx
 //   S (N x 3 col-major doubles), T (M x 3), then (if bits) V*N*B + M*B descriptor bytes.
-// Prints the final 4x4 (row by row), the iteration count and the last pair count.
+// Prints the final 4x4 (row by row), the iteration count and the last pair count; in KM mode also the public
+// members the reference fills per iteration (src/ghicp_reg.cpp:443-460): one `km <it> pre rec matched cor energy` line per
+// iteration, `matched` = number of source keypoints whose matchlist column holds a target index.
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -41,6 +43,11 @@ int main(int argc, char **argv) {
     for (int i = 0; i < 4; ++i)
       std::printf("%.17g %.17g %.17g %.17g\n", Rt_final(i, 0), Rt_final(i, 1), Rt_final(i, 2), Rt_final(i, 3));
     std::printf("iterations %zu last_cor %d\n", ghreg.cor.size(), ghreg.cor.empty() ? 0 : ghreg.cor.back());
+    for (size_t it = 0; it < ghreg.pre.size(); ++it) {
+      int matched = 0;
+      for (const auto &row : ghreg.matchlist) matched += it < row.size() && row[it] >= 0;
+      std::printf("km %zu %.17g %.17g %d %d %.17g\n", it, ghreg.pre[it], ghreg.rec[it], matched, ghreg.cor[it], ghreg.energy[it]);
+    }
   } catch (const std::exception &e) {
     std::fprintf(stderr, "error: %s\n", e.what());
     return 1;

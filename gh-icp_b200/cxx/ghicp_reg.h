@@ -8,11 +8,17 @@
 //  * no PCLVisualizer is created (src/ghicp_reg.cpp:26-29 cannot run headless); set_viewer is kept
 //    and ignored; set_raw_pointcloud is accepted and ignored (the clouds only fed the viewer).
 //  * an optional max_iterations guard (default 0 = unbounded like src/ghicp_reg.cpp:49).
+//  * pre / rec (KM mode, src/ghicp_reg.cpp:443-444) count identity pairs among the RETURNED correspondences; the
+//    reference's Km::output (src/km.cpp:159) also counts match[i] == i on penalty edges of the padded graph, where the
+//    assignment is arbitrary (any perfect matching of the left-overs is optimal), so that part has no defined value.
+//  * the CUDA device is chosen per process: GHRegistration::set_default_device(d) or the GHICP_DEVICE environment
+//    variable (the reference has no device notion); one process per GPU shards through ghicp_comm_init.
 #ifndef _INCLUDE_GHICP_REG_H_
 #define _INCLUDE_GHICP_REG_H_
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <iostream>
 #include <stdexcept>
@@ -69,13 +75,14 @@ class GHRegistration {
     PCFD = 0;
     RMS = 99999;
     Rt_tillnow = Identity4();
+    matchlist.resize(KP.kps_num, std::vector<int>(200));   // include/ghicp_reg.h:100
     ghicp_config cfg;
     std::memset(&cfg, 0, sizeof(cfg));
     cfg.feature_type = (int)Ft; cfg.corr_type = (int)Ct; cfg.dof = dof_type;
     cfg.bbx_magnitude = Ef.bbx_magnitude_;
     cfg.nonmax = radiusNonMax; cfg.adjust_ratio = weight_adjustment_ratio; cfg.adjust_step = weight_adjustment_step;
     cfg.estimated_iou = estimated_IoU; cfg.converge_t = converge_tran; cfg.converge_r = converge_rot;
-    cfg.max_iter = 0; cfg.device = 0; cfg.km_eps = Ef.KM_eps;
+    cfg.max_iter = 0; cfg.device = default_device(); cfg.km_eps = Ef.KM_eps;
     check(ghicp_create(&cfg, &ctx_), "ghicp_create");
     try {   // a constructor that throws runs no destructor: release the context here
       check(ghicp_set_keypoints(ctx_, KP.kpSXYZ.data(), KP.kps_num, KP.kpTXYZ.data(), KP.kpt_num), "ghicp_set_keypoints");
@@ -96,6 +103,11 @@ class GHRegistration {
   void set_viewer(bool launch_viewer) { launch_viewer_ = launch_viewer; }
   void set_max_iterations(int n) { max_iterations_ = n; }
   void set_verbose(bool v) { verbose_ = v; }
+  // matchlist / pre / rec (KM mode) need the pair lists on the host every iteration (two int arrays of cor entries);
+  // a caller that reads neither can switch that copy off.
+  void set_track_matches(bool on) { track_matches_ = on; }
+  // Device of the contexts constructed from now on in this process (default: GHICP_DEVICE, else 0).
+  static void set_default_device(int d) { default_device() = d; }
   // Extensions (not in the reference's class): opt-in estimators of include/ghicp_b200.h ghicp_solver_type.
   // GHICP_SOLVER_SVD (default) is what src/ghicp_reg.cpp:857-859 always runs.
   void set_solver(int solver) { check(ghicp_set_solver(ctx_, solver), "ghicp_set_solver"); }
@@ -121,6 +133,7 @@ class GHRegistration {
       if (verbose_)
         std::cout << st.iteration << " : " << st.cor << " pairs, RMSE " << st.rmse << " -> " << st.rmse_after
                   << ", penalty " << st.penalty << std::endl;
+      if (Ct_ == KM && track_matches_) record_matches(st.iteration);
       converge = st.converged != 0;
       if (max_iterations_ > 0 && ++it >= max_iterations_) break;
     }
@@ -152,6 +165,26 @@ class GHRegistration {
   void check(int rc, const char *what) {
     if (rc < 0) throw std::runtime_error(std::string(what) + ": " + ghicp_last_error(ctx_));
   }
+  static int &default_device() {
+    static int d = [] { const char *e = std::getenv("GHICP_DEVICE"); return e ? std::atoi(e) : 0; }();
+    return d;
+  }
+  // src/ghicp_reg.cpp:443-460: precision / recall of this iteration's matching against the identity, and column
+  // `iteration` of matchlist (target index of every matched source keypoint, -1 for the others).
+  void record_matches(int iteration) {
+    std::vector<int> SP, TP;
+    const int n = get_pairs(SP, TP);
+    int exact = 0;
+    for (int k = 0; k < n; ++k) exact += SP[k] == TP[k];
+    pre.push_back(n > 0 ? 1.0 * exact / n : 0.0);
+    rec.push_back(1.0 * exact / std::max(KP.kps_num, KP.kpt_num));
+    if (iteration < 0) return;
+    for (auto &row : matchlist) {
+      if ((int)row.size() <= iteration) row.resize(iteration + 1, 0);   // the reference stops at 200 columns (UB beyond)
+      row[iteration] = -1;
+    }
+    for (int k = 0; k < n; ++k) matchlist[SP[k]][iteration] = TP[k];
+  }
   void upload_bsc() {
     int V = 0;   // extractBinaryFeatures always returns four vectors; the variants dof_type did not ask for hold empty features
     while (V < (int)KP.bscS.size() && !KP.bscS[V].empty() && KP.bscS[V][0].size_ > 0) ++V;
@@ -176,7 +209,7 @@ class GHRegistration {
   FeatureType Ft_;
   CorrespondenceType Ct_;
   ghicp_ctx *ctx_ = nullptr;
-  bool launch_viewer_ = false, verbose_ = false;
+  bool launch_viewer_ = false, verbose_ = false, track_matches_ = true;
   int max_iterations_ = 0;
 };
 

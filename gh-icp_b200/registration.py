@@ -77,7 +77,7 @@ class GHRegistration:
             uid, rank, world = comm
             buf = (C.c_char * 128).from_buffer_copy(uid) if world > 1 else None
             capi.check(self.L.ghicp_comm_init(self.ctx, buf, rank, world), self.ctx)
-        self.Ft, self.Ct = Ft, Ct
+        self.Ft, self.Ct, self.max_iter = Ft, Ct, max_iter
         if isinstance(Kp, tuple):   # (source Prep, target Prep): device-resident pipeline results, no host copy
             src, tgt = Kp
             self.N, self.M = src.n_kp, tgt.n_kp
@@ -140,12 +140,56 @@ class GHRegistration:
         self.history.append(st)
         return st
 
-    def ghicp_reg(self):
-        """Main entrance (src/ghicp_reg.cpp:24-112). Returns (Rt_final 4x4, iterations)."""
-        Rt = np.zeros(16)
-        it = C.c_int(0)
-        capi.check(self.L.ghicp_run(self.ctx, capi._dp(Rt), C.byref(it)), self.ctx)
-        return Rt.reshape(4, 4).T.copy(), it.value
+    def ghicp_reg(self, track_matches=False):
+        """Main entrance (src/ghicp_reg.cpp:24-112). Returns (Rt_final 4x4, iterations).
+
+        track_matches=True runs the loop one ghicp_iterate at a time and fills what the reference's KM branch records per
+        iteration (src/ghicp_reg.cpp:443-460): `pre`, `rec` (identity pairs among the returned correspondences; see
+        gh-icp_b200/cxx/ghicp_reg.h on the penalty-edge part of src/km.cpp:159) and `matchlist` (N x iterations, target index
+        or -1).  The per-iteration statistics (`energy`, `rmse`, `rmseafter`, `cor`, `RMS`) are then available as well; the
+        default hands the whole loop to ghicp_run and keeps only its result."""
+        if not track_matches:
+            Rt = np.zeros(16)
+            it = C.c_int(0)
+            capi.check(self.L.ghicp_run(self.ctx, capi._dp(Rt), C.byref(it)), self.ctx)
+            return Rt.reshape(4, 4).T.copy(), it.value
+        self.build_fd()
+        self.pre, self.rec, cols = [], [], []
+        while True:
+            st = self.iterate()
+            if self.Ct == CT_KM:
+                sp, tp = self.pairs()
+                exact = int((sp == tp).sum())
+                self.pre.append(exact / len(sp) if len(sp) else 0.0)
+                self.rec.append(exact / max(self.N, self.M))
+                col = np.full(self.N, -1, np.int32)
+                col[sp] = tp
+                cols.append(col)
+            if st.converged or (self.max_iter > 0 and len(self.history) >= self.max_iter):
+                break
+        self.matchlist = np.stack(cols, axis=1) if cols else np.zeros((self.N, 0), np.int32)
+        return self.Rt_tillnow(), len(self.history)
+
+    # public members of the reference's class (include/ghicp_reg.h:138-152), from the iterations run through iterate()
+    @property
+    def energy(self):
+        return [st.km_energy for st in self.history]
+
+    @property
+    def rmse(self):
+        return [st.rmse for st in self.history]
+
+    @property
+    def rmseafter(self):
+        return [st.rmse_after for st in self.history]
+
+    @property
+    def cor(self):
+        return [st.cor for st in self.history]
+
+    @property
+    def RMS(self):
+        return self.history[-1].rmse if self.history else 99999.0
 
     def pairs(self, out=None):
         """(SP, TP) of the last iteration.  out = (sp, tp) int32 buffers of >= max(N, M) entries (e.g. capi.pinned_empty):

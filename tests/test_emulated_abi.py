@@ -296,6 +296,76 @@ def test_cpp_dropin_demo_on_the_emulated_library(ge, orc, tmp_path, monkeypatch,
     z.test_cpp_dropin_matches_oracle(ge, orc, tmp_path, "bsc-nn")
 
 
+def test_python_mirror_public_members(ge):
+    """energy / rmse / rmseafter / cor / RMS from the iterations run; ghicp_reg(track_matches=True) adds pre / rec / matchlist
+    (src/ghicp_reg.cpp:443-460) and returns the same transform as the default ghicp_run path."""
+    g = ge
+    sc = g.synth.add_bsc(g.synth.gen_points(110, 100, overlap=0.9, seed=11), V=4)
+    a = g.registration.from_scene(sc, g.FT_BSC, g.CT_KM, max_iter=6)
+    assert a.RMS == 99999.0 and a.cor == []
+    Rt_a, it_a = a.ghicp_reg(track_matches=True)
+    assert it_a == len(a.cor) == len(a.energy) == len(a.rmse) == len(a.rmseafter) == len(a.pre) == len(a.rec)
+    assert a.matchlist.shape == (110, it_a) and a.RMS == a.rmse[-1]
+    for it in range(it_a):
+        assert int((a.matchlist[:, it] >= 0).sum()) == a.cor[it]
+        assert 0.0 <= a.rec[it] <= a.pre[it] <= 1.0
+    sp, tp = a.pairs()
+    assert np.array_equal(a.matchlist[sp, -1], tp)
+    b = g.registration.from_scene(sc, g.FT_BSC, g.CT_KM, max_iter=6)
+    try:
+        Rt_b, it_b = b.ghicp_reg()
+    except g.capi.GhicpError:      # GHICP_E_NOCONV: max_iter reached; the transform so far is what is compared
+        Rt_b, it_b = b.Rt_tillnow(), it_a
+    assert it_b == it_a and np.array_equal(Rt_a, Rt_b)
+    a.close(); b.close()
+
+
+@pytest.mark.skipif(not os.environ.get("GHICP_EMU_SLOW"), reason="minutes on the emulator: set GHICP_EMU_SLOW=1")
+def test_cpp_dropin_demo_km_full_size_on_the_emulated_library(ge, orc, tmp_path, monkeypatch, cli_env):
+    """The `-m gpu` KM drop-in test function itself (700 x 640 keypoints) on the emulated library."""
+    import test_gpu_dropin as z
+    monkeypatch.setenv("LD_LIBRARY_PATH", cli_env["LD_LIBRARY_PATH"])
+    z.test_cpp_dropin_matches_oracle(ge, orc, tmp_path, "bsc-km")
+
+
+def test_cpp_mirror_fills_matchlist_pre_rec_in_km_mode(ge, tmp_path, monkeypatch, cli_env):
+    """Public members of the reference's GHRegistration that its KM branch fills every iteration (src/ghicp_reg.cpp:440-460,
+    src/km.cpp:159,226-227): cor, energy, pre, rec and one matchlist column.  The C++ mirror (dropin_demo) and the Python mirror
+    run the same library on the same scene, so their iterations are identical: the demo's values must be the ones computed here
+    from the Python mirror's pair lists."""
+    import test_gpu_dropin as z
+    g = ge
+    monkeypatch.setenv("LD_LIBRARY_PATH", cli_env["LD_LIBRARY_PATH"])
+    assert subprocess.run(["make", "-C", os.path.join(ROOT, "gh-icp_b200", "cxx")], capture_output=True).returncode == 0
+    sc = g.synth.add_bsc(g.synth.gen_points(110, 100, overlap=0.9, seed=11), V=4)
+    # make the identity a frequent true match so that pre / rec are not trivially zero: the generator pairs source i with
+    # target perm[i]; reorder the targets (coordinates and descriptors) so that the pairing is the identity
+    order = np.concatenate([sc.perm, np.setdiff1d(np.arange(100), sc.perm)])
+    sc.T, sc.bsc_t = np.asfortranarray(sc.T[order]), np.ascontiguousarray(sc.bsc_t[order])
+    p = str(tmp_path / "scene.bin")
+    z.write_scene(p, sc, 0, 2)
+    r = subprocess.run([z.DEMO, p, "6"], capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    km = [ln.split() for ln in lines[5:] if ln.startswith("km ")]
+    reg = g.registration.from_scene(sc, g.FT_BSC, g.CT_KM, max_iter=6)
+    reg.build_fd()
+    n_it = int(lines[4].split()[1])
+    assert len(km) == n_it >= 1
+    seen_exact = 0
+    for it in range(n_it):
+        st = reg.iterate()
+        sp, tp = reg.pairs()
+        exact = int((sp == tp).sum())
+        assert int(km[it][1]) == it == st.iteration
+        assert int(km[it][4]) == int(km[it][5]) == st.cor == len(sp)
+        assert float(km[it][2]) == exact / st.cor and float(km[it][3]) == exact / 110
+        assert float(km[it][6]) == st.km_energy
+        seen_exact = max(seen_exact, exact)
+    assert seen_exact >= 45, "the scene pairs source i with target i on 90 keypoints: identity matches expected"
+    reg.close()
+
+
 # ---- stress modes of the emulator: scheduling order and asynchronous copies -------------------------------------------------
 @pytest.mark.parametrize("env,expect_ok", [({}, True),
                                            ({"GHICP_EMU_SCHED": "1"}, True),

@@ -54,3 +54,11 @@ def test_cpp_dropin_matches_oracle(g, orc, tmp_path, mode):
         # KM: eps-optimal matchings are not unique; the registration must land on the ground truth
         assert g.synth.rot_angle(Rt[:3, :3], sc.R_gt) < 5e-3
         assert np.linalg.norm(Rt[:3, 3] - sc.t_gt) < 0.3
+        # the public members the reference fills per KM iteration (src/ghicp_reg.cpp:440-460): pre, rec, matchlist, cor
+        km = [ln.split() for ln in lines[5:] if ln.startswith("km ")]
+        assert len(km) == int(lines[4].split()[1]) and [int(r[1]) for r in km] == list(range(len(km)))
+        for r in km:
+            pre, rec, matched, cor = float(r[2]), float(r[3]), int(r[4]), int(r[5])
+            assert matched == cor and 0 < cor <= 640           # one matchlist entry per correspondence, at most min(N, M)
+            assert 0.0 <= rec <= pre <= 1.0
+            assert abs(rec * 700 - pre * cor) < 1e-6           # both count the same identity pairs (src/km.cpp:226-227)
