@@ -54,7 +54,10 @@ def g(request):
     import ghicp_b200
     ghicp_b200.build_library()
     if os.environ.get("GHICP_TEST_EMULATED_ABI"):
-        swap_in_library(ghicp_b200, request.getfixturevalue("emu_library_path"))
+        emu = request.getfixturevalue("emu_library_path")
+        swap_in_library(ghicp_b200, emu)
+        # the C++ drivers the tests start (dropin_demo, ghicp_cli) resolve libghicp_b200.so through the loader path
+        os.environ["LD_LIBRARY_PATH"] = os.path.dirname(emu) + os.pathsep + os.environ.get("LD_LIBRARY_PATH", "")
     return ghicp_b200
 
 
