@@ -85,6 +85,8 @@ class GHRegistration {
     cfg.max_iter = 0; cfg.device = default_device(); cfg.km_eps = Ef.KM_eps;
     check(ghicp_create(&cfg, &ctx_), "ghicp_create");
     try {   // a constructor that throws runs no destructor: release the context here
+      const CommSpec &cs = default_comm();
+      if (cs.world > 1) check(ghicp_comm_init(ctx_, cs.id, cs.rank, cs.world), "ghicp_comm_init");   // before the keypoints
       check(ghicp_set_keypoints(ctx_, KP.kpSXYZ.data(), KP.kps_num, KP.kpTXYZ.data(), KP.kpt_num), "ghicp_set_keypoints");
       if (Ft == BSC) upload_bsc();
       if (Ft == FPFH) upload_fpfh();
@@ -108,6 +110,14 @@ class GHRegistration {
   void set_track_matches(bool on) { track_matches_ = on; }
   // Device of the contexts constructed from now on in this process (default: GHICP_DEVICE, else 0).
   static void set_default_device(int d) { default_device() = d; }
+  // One process per GPU (extension): the contexts constructed from now on shard the source keypoints over
+  // `world` processes.  id128 = the 128 bytes rank 0 got from ghicp_comm_unique_id and the host runtime broadcast.
+  // (The sharded path itself is tested through the Python mirror, tests/test_gpu_multi.py; this setter only forwards.)
+  static void set_default_comm(const void *id128, int rank, int world) {
+    CommSpec &cs = default_comm();
+    if (id128) std::memcpy(cs.id, id128, sizeof(cs.id));
+    cs.rank = rank; cs.world = world;
+  }
   // Extensions (not in the reference's class): opt-in estimators of include/ghicp_b200.h ghicp_solver_type.
   // GHICP_SOLVER_SVD (default) is what src/ghicp_reg.cpp:857-859 always runs.
   void set_solver(int solver) { check(ghicp_set_solver(ctx_, solver), "ghicp_set_solver"); }
@@ -165,6 +175,8 @@ class GHRegistration {
   void check(int rc, const char *what) {
     if (rc < 0) throw std::runtime_error(std::string(what) + ": " + ghicp_last_error(ctx_));
   }
+  struct CommSpec { char id[128]; int rank = 0, world = 1; };
+  static CommSpec &default_comm() { static CommSpec cs; return cs; }
   static int &default_device() {
     static int d = [] { const char *e = std::getenv("GHICP_DEVICE"); return e ? std::atoi(e) : 0; }();
     return d;
