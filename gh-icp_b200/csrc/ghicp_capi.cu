@@ -48,6 +48,18 @@ static int dev_alloc(Ctx *c, T **p, size_t count) {
   }
   return GHICP_OK;
 }
+// small page-locked workspaces (read-backs): allocated once per context, kept across resizes
+template <typename T>
+static int host_alloc_once(Ctx *c, T **p, size_t bytes) {
+  if (*p) return GHICP_OK;
+  if (cudaMallocHost((void **)p, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    *p = nullptr;
+    set_error(c, "cudaMallocHost failed (page-locked workspace)");
+    return GHICP_E_NOMEM;
+  }
+  return GHICP_OK;
+}
 template <typename T>
 static void dev_free(T **p) {
   if (*p) { cudaFree(*p); *p = nullptr; }
@@ -127,7 +139,6 @@ static int alloc_workspaces(Ctx *c) {
   c->Npad = c->shard * c->world;
   c->r0 = std::min(N, c->rank * c->shard);
   c->nloc = std::max(0, std::min(N, c->r0 + c->shard) - c->r0);
-  if (c->world > 1 && c->n_chunks != 1) c->n_chunks = 1;
   const int nmax = std::max(c->Npad, M);
   const int row_ctas = (N + 7) / 8;
   int want = (148 * 4 + row_ctas - 1) / row_ctas;
@@ -144,7 +155,7 @@ static int alloc_workspaces(Ctx *c) {
   if ((rc = dev_alloc(c, &c->d_S4, 4 * (size_t)c->Npad))) return rc;
   if ((rc = dev_alloc(c, &c->d_T4, 4 * (size_t)M))) return rc;
   if ((rc = dev_alloc(c, &c->d_sdev, 1))) return rc;
-  if (!c->h_sdev && cudaMallocHost((void **)&c->h_sdev, sizeof(StreamDev)) != cudaSuccess) return GHICP_E_NOMEM;
+  if ((rc = host_alloc_once(c, &c->h_sdev, sizeof(StreamDev)))) return rc;
   if ((rc = dev_alloc(c, &c->d_row_thr, (size_t)c->Npad))) return rc;
   if ((rc = dev_alloc(c, &c->d_col_thr, (size_t)M))) return rc;
   if ((rc = dev_alloc(c, &c->d_rowbest, (size_t)c->Npad))) return rc;
@@ -172,15 +183,15 @@ static int alloc_workspaces(Ctx *c) {
     if ((rc = dev_alloc(c, &c->d_colg_cd, (size_t)c->world * M))) return rc;
     if ((rc = dev_alloc(c, &c->d_colg_idx, (size_t)c->world * M))) return rc;
   }
-  if (!c->h_rowptr_cut && cudaMallocHost((void **)&c->h_rowptr_cut, sizeof(long long) * (c->world + 1)) != cudaSuccess) return GHICP_E_NOMEM;
+  if ((rc = host_alloc_once(c, &c->h_rowptr_cut, sizeof(long long) * (c->world + 1)))) return rc;
   if ((rc = dev_alloc(c, &c->d_col_cd, (size_t)M))) return rc;
   if ((rc = dev_alloc(c, &c->d_col_idx, (size_t)M))) return rc;
   if ((rc = dev_alloc(c, &c->d_flags, (size_t)nmax))) return rc;
   if ((rc = dev_alloc(c, &c->d_sp, (size_t)nmax))) return rc;
   if ((rc = dev_alloc(c, &c->d_tp, (size_t)nmax))) return rc;
   if ((rc = dev_alloc(c, &c->d_iter, 1))) return rc;
-  if (!c->h_iter && cudaMallocHost((void **)&c->h_iter, sizeof(DevIter)) != cudaSuccess) return GHICP_E_NOMEM;
-  if (!c->h_counters && cudaMallocHost((void **)&c->h_counters, sizeof(int) * 64) != cudaSuccess) return GHICP_E_NOMEM;
+  if ((rc = host_alloc_once(c, &c->h_iter, sizeof(DevIter)))) return rc;
+  if ((rc = host_alloc_once(c, &c->h_counters, sizeof(int) * 64))) return rc;
   if (c->cfg.corr_type == GHICP_CT_KM) {
     if ((rc = dev_alloc(c, &c->d_cnt, L + 2))) return rc;
     if ((rc = dev_alloc(c, &c->d_rowptr, L + 1))) return rc;
@@ -212,7 +223,7 @@ static int alloc_workspaces(Ctx *c) {
     if ((rc = dev_alloc(c, &c->d_xsend, xblock_bytes(c->xcap)))) return rc;
     if (c->world > 1) { if ((rc = dev_alloc(c, &c->d_xrecv, xblock_bytes(c->xcap) * (size_t)c->world))) return rc; }
     if ((rc = dev_alloc(c, &c->d_xcounts, (size_t)c->world))) return rc;
-    if (!c->h_xcounts && cudaMallocHost((void **)&c->h_xcounts, sizeof(unsigned long long) * (size_t)c->world) != cudaSuccess) return GHICP_E_NOMEM;
+    if ((rc = host_alloc_once(c, &c->h_xcounts, sizeof(unsigned long long) * (size_t)c->world))) return rc;
     if ((rc = ensure_edges(c, (long long)(c->xcap * (size_t)c->world)))) return rc;
   }
   return GHICP_OK;
@@ -747,7 +758,12 @@ int ghicp_create(const ghicp_config *cfg, ghicp_ctx **out) {
   c->device = cfg->device;
   int rc = use_device(c);
   if (rc) { delete c; return rc; }
-  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return GHICP_E_CUDA; }
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError();
+    set_error(nullptr, "ghicp_create: cudaStreamCreateWithFlags failed");
+    delete c;
+    return GHICP_E_CUDA;
+  }
   for (auto &e : c->ev) cudaEventCreate(&e);
   reset_loop_state(c);
   c->use_fast = (cfg->force_exact == 0);
@@ -777,9 +793,10 @@ int ghicp_set_keypoints(ghicp_ctx *ctx, const double *sxyz, int N, const double 
   if (resize) {
     c->N = N; c->M = M;
     c->ldM = ((size_t)M + 63) / 64 * 64;
-    if ((rc = dev_alloc(c, &c->d_s, 3 * (size_t)N))) return rc;
-    if ((rc = dev_alloc(c, &c->d_t, 3 * (size_t)M))) return rc;
-    if ((rc = alloc_workspaces(c))) return rc;
+    if ((rc = dev_alloc(c, &c->d_s, 3 * (size_t)N)) || (rc = dev_alloc(c, &c->d_t, 3 * (size_t)M)) || (rc = alloc_workspaces(c))) {
+      c->N = c->M = 0;   // half-sized workspaces must not pass for a configured context: every later call answers "keypoints not set"
+      return rc;
+    }
     c->have_bsc = c->have_fpfh = c->fd_built = false;
     c->have_normals = false;
     c->have_prev = false;
@@ -789,7 +806,12 @@ int ghicp_set_keypoints(ghicp_ctx *ctx, const double *sxyz, int N, const double 
   const size_t need = 3 * ((size_t)N + M) * sizeof(double);
   if (need > c->h_stage_cap) {
     if (c->h_stage) cudaFreeHost(c->h_stage);
-    if (cudaMallocHost((void **)&c->h_stage, need) != cudaSuccess) { c->h_stage = nullptr; c->h_stage_cap = 0; return GHICP_E_NOMEM; }
+    if (cudaMallocHost((void **)&c->h_stage, need) != cudaSuccess) {
+      cudaGetLastError();
+      c->h_stage = nullptr; c->h_stage_cap = 0;
+      set_error(c, "set_keypoints: cudaMallocHost of the staging buffer failed");
+      return GHICP_E_NOMEM;
+    }
     c->h_stage_cap = need;
   }
   // pageable -> pinned staging, pipelined with the DMA: the target is staged while the source is in flight,
@@ -1356,9 +1378,10 @@ int ghicp_set_from_prep(ghicp_ctx *ctx, const ghicp_prep *src, const ghicp_prep 
   if (N != c->N || M != c->M) {
     c->N = N; c->M = M;
     c->ldM = ((size_t)M + 63) / 64 * 64;
-    if ((rc = dev_alloc(c, &c->d_s, 3 * (size_t)N))) return rc;
-    if ((rc = dev_alloc(c, &c->d_t, 3 * (size_t)M))) return rc;
-    if ((rc = alloc_workspaces(c))) return rc;
+    if ((rc = dev_alloc(c, &c->d_s, 3 * (size_t)N)) || (rc = dev_alloc(c, &c->d_t, 3 * (size_t)M)) || (rc = alloc_workspaces(c))) {
+      c->N = c->M = 0;   // half-sized workspaces must not pass for a configured context: every later call answers "keypoints not set"
+      return rc;
+    }
     c->have_bsc = c->have_fpfh = c->fd_built = false;
     c->have_normals = false;
     c->have_prev = false;

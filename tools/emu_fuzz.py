@@ -1,5 +1,5 @@
 """Random-shape lock-step fuzz of the whole C ABI on the CPU emulator against the oracle (developer tool, no GPU):
-    python tools/emu_fuzz.py [seconds] [seed]
+    python tools/emu_fuzz.py [seconds] [seed] [max keypoints per side, default 700]
 Shapes, descriptor widths, variants, overlap and correspondence modes are drawn at random; NN / NNR pair lists must be identical
 to the oracle's every iteration, KM energies within n * KM_eps (the oracle is then put back on the library's trajectory)."""
 import os
@@ -17,12 +17,12 @@ import ghicp_b200 as g  # noqa: E402
 import oracle as orc  # noqa: E402
 
 
-def one_case(rng, case):
+def one_case(rng, case, hi_nn=700):
     ft = rng.choice(["none", "bsc", "fpfh"])
     ct = rng.choice(["nn", "nnr", "km"], p=[0.4, 0.4, 0.2])
     if ft == "fpfh" and ct == "km":
         ct = "nnr"            # the oracle's Kuhn-Munkres takes minutes per iteration on float costs
-    hi = 120 if ct == "km" else 700
+    hi = 120 if ct == "km" else hi_nn
     N, M = int(rng.integers(1, hi)), int(rng.integers(1, hi))
     dof = int(rng.choice([6, 4]))
     bits = int(rng.choice([9, 64, 441, 448, 449, 672, 700]))
@@ -79,7 +79,7 @@ def main():
         os.chdir(d)                      # the reference's Km::output writes Corres.txt into the CWD
         t0, case = time.time(), 0
         while time.time() - t0 < budget:
-            one_case(rng, case)
+            one_case(rng, case, int(sys.argv[3]) if len(sys.argv) > 3 else 700)
             case += 1
     print(f"{case} cases, no mismatch")
 
