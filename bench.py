@@ -173,7 +173,16 @@ def make_scene(g, wl, n_override=None, seed=2):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_stream launch, from the committed `ncu --set full` captures
 # (profiles/r01_summary.md); algorithmic bytes are 5.002e9
-NCU_TRAFFIC = {"config2": {"bytes": 5.0386e9, "source": "profiles/r01_summary.md (ncu --set full capture of k_stream KM, round 1)"},
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel's launch in an `ncu --set full` capture of the same command
+# (a constant from the committed capture, labelled with its source: a bench run is never taken under the profiler)
+NCU_TRAFFIC = {"config2": {"bytes": 5.038999e9 + 0.32185856e9,
+                           "source": "profiles/r02_ncu_k_stream_km.raw.csv (ncu --set full, k_stream<2,1,1,1,1>, round 2): "
+                                     "5.039 GB read (algorithmic 5.002 GB) + 0.322 GB written (counts, partial sums, edge list)"},
+               "config2-672": {"bytes": 5.038999e9 + 0.32185856e9,
+                               "source": "profiles/r02_ncu_k_stream_km.raw.csv (the same kernel and plane: the descriptor width only "
+                                         "changes the one-time FD build)"},
+               "config2-nnr": {"bytes": 5.179896e9 + 0.321731584e9,
+                               "source": "profiles/r02_ncu_k_stream_nnr.raw.csv (ncu --set full, k_stream<1,1,1,1,1>, round 2)"},
                "config2-nn": {"bytes": 5.311e9, "source": "profiles/r01_summary.md (ncu --set full capture of k_stream NN, round 1)"}}
 
 FT = {"none": 3, "bsc": 0, "fpfh": 2}
