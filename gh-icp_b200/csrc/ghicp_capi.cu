@@ -631,7 +631,10 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
   if (settled_any) {
     if (c->h_iter->overflow_any) {   // some rank's candidate block overflowed: nothing was updated, take the general route
       c->km_settled_off = true;
-      return iterate_impl(c, out);
+      c->km_redone = true;
+      const int rc_redo = iterate_impl(c, out);
+      c->km_redone = false;
+      return rc_redo;
     }
     if ((rc = km_auction_settled_result(c, &kres))) return rc;
     c->last_total_nnz = c->h_iter->nnz;
@@ -702,7 +705,7 @@ static int iterate_impl(Ctx *c, ghicp_iter_stats *out) {
     out->ax = ax; out->ay = ay; out->az = az;
     out->nnz = nnz; out->km_rounds = kres.rounds; out->km_phases = kres.phases;
     out->gpu_launches = c->launches;
-    out->exact_fallback = ((fast || fpfh_fast) && exact_fallback) ? 1 : 0;
+    out->exact_fallback = (((fast || fpfh_fast) && exact_fallback) ? 1 : 0) | (c->km_redone ? 2 : 0);
     float ms;
     cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); out->ms_cost = ms;
     cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]); out->ms_corr = ms;

@@ -240,6 +240,7 @@ struct Ctx {
   unsigned long long *d_xcounts = nullptr;  // [world] edges per block (device)
   unsigned long long *h_xcounts = nullptr;  // pinned copy
   bool km_settled_off = false;              // the last settled attempt overflowed: take the general route once
+  bool km_redone = false;                   // ... and this is that repeat (reported as bit 1 of ghicp_iter_stats.exact_fallback)
   int settled_iterations = 0;
 };
 

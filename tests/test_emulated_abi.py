@@ -98,14 +98,18 @@ def test_settled_km_block_overflow_falls_back_to_the_general_route(ge, monkeypat
     for name, env in (("default", {}), ("overflow", {"GHICP_KM_XUSE_MAX": "8"}), ("general", {"GHICP_KM_GENERAL": "1"})):
         for k, v in env.items():
             monkeypatch.setenv(k, v)
-        reg = g.registration.from_scene(sc, g.FT_BSC, g.CT_KM, max_iter=7)
+        reg = g.registration.from_scene(sc, g.FT_BSC, g.CT_KM, max_iter=5)
         out = []
-        for it in range(7):
+        for it in range(5):      # the settled route is eligible from iteration 2 on
             st = reg.iterate()
-            out.append((st.cor, st.nnz, st.km_energy, np.array(st.Rt), reg.pairs(), reg.source()))
+            out.append((st.cor, st.nnz, st.km_energy, np.array(st.Rt), reg.pairs(), reg.source(), st.exact_fallback))
         runs[name] = out
         for k in env:
             monkeypatch.delenv(k)
+    # bit 1 of exact_fallback = "the settled iteration's block overflowed, re-ran on the general route": never by default, on
+    # every settled-eligible iteration (2, 3, 4) under the hook
+    assert all(r[6] == 0 for r in runs["default"]) and all(r[6] == 0 for r in runs["general"])
+    assert [r[6] for r in runs["overflow"]] == [0, 0, 2, 2, 2]
     for name in ("overflow", "general"):
         for a, b in zip(runs["default"], runs[name]):
             assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2], name
